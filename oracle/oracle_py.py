@@ -1,0 +1,143 @@
+"""ctypes binding of the CPU parity oracle (oracle/libshc_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package never imports this module.  PARITY UNPINNED: the
+reference ships no golden vectors and cannot be built here, so this restatement is the oracle of record.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from syropod_highlevel_controller_b200.config import ShcConfig, ShcRobotState, ShcStartup
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libshc_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with g++ (a few seconds).  Building the checker is not using it."""
+    if force or not os.path.exists(_LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        dp = C.POINTER(C.c_double)
+        L.shc_oracle_batch_create.restype = C.c_void_p
+        L.shc_oracle_batch_create.argtypes = [C.POINTER(ShcConfig), C.c_int]
+        L.shc_oracle_batch_destroy.argtypes = [C.c_void_p]
+        L.shc_oracle_batch_size.argtypes = [C.c_void_p]
+        L.shc_oracle_startup_loops.argtypes = [C.c_void_p]
+        L.shc_oracle_get_startup.argtypes = [C.c_void_p, C.POINTER(ShcStartup)]
+        L.shc_oracle_batch_step.argtypes = [C.c_void_p, dp, dp, dp, dp, C.c_int]
+        L.shc_oracle_batch_run.restype = C.c_double
+        L.shc_oracle_batch_run.argtypes = [C.c_void_p, dp, C.c_int, C.c_int]
+        L.shc_oracle_batch_get_joints.argtypes = [C.c_void_p, dp]
+        L.shc_oracle_batch_get_state.argtypes = [C.c_void_p, C.POINTER(ShcRobotState)]
+        L.shc_oracle_batch_set_state.argtypes = [C.c_void_p, C.POINTER(ShcRobotState)]
+        L.shc_oracle_smooth_step.restype = C.c_double
+        L.shc_oracle_smooth_step.argtypes = [C.c_double]
+        L.shc_oracle_round_to_int.argtypes = [C.c_double]
+        L.shc_oracle_round_to_even_int.argtypes = [C.c_double]
+        L.shc_oracle_quat_to_euler.argtypes = [dp, C.c_int, dp]
+        L.shc_oracle_euler_to_quat.argtypes = [dp, C.c_int, dp]
+        L.shc_oracle_dh.argtypes = [C.c_double] * 4 + [dp]
+        L.shc_oracle_quartic_bezier.argtypes = [dp, C.c_double, dp, dp]
+        L.shc_oracle_from_two_vectors.argtypes = [dp, dp, dp]
+        L.shc_oracle_slerp.argtypes = [dp, C.c_double, dp, dp]
+        L.shc_oracle_pose_ops.argtypes = [dp, dp, dp, dp, dp]
+        L.shc_oracle_fk.argtypes = [C.POINTER(ShcConfig), C.c_int, dp, dp]
+        L.shc_oracle_solve_ik.argtypes = [C.POINTER(ShcConfig), C.c_int, dp, dp, dp, dp]
+        L.shc_oracle_step_cycle.argtypes = [C.POINTER(ShcConfig), C.POINTER(ShcStartup)]
+        L.shc_oracle_admittance.argtypes = [C.POINTER(ShcConfig), dp, dp, dp]
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _arr(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+class OracleBatch:
+    """N independent copies of the reference controller, started up once and cloned."""
+
+    def __init__(self, cfg: ShcConfig, n_robots: int = 1):
+        self.cfg = cfg
+        self.n = n_robots
+        self.L, self.D = cfg.leg_count, cfg.joint_count
+        self._h = lib().shc_oracle_batch_create(C.byref(cfg), n_robots)
+
+    def close(self):
+        if self._h:
+            lib().shc_oracle_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def startup_loops(self) -> int:
+        return lib().shc_oracle_startup_loops(self._h)
+
+    def startup(self) -> ShcStartup:
+        s = ShcStartup()
+        lib().shc_oracle_get_startup(self._h, C.byref(s))
+        return s
+
+    def step(self, cmd, imu=None, tip_force=None, manual=None, threads: int = 1):
+        cmd, imu, tip_force, manual = _arr(cmd), _arr(imu), _arr(tip_force), _arr(manual)
+        assert cmd.shape == (self.n, 3)
+        lib().shc_oracle_batch_step(self._h, _dp(cmd), _dp(imu), _dp(tip_force), _dp(manual), threads)
+
+    def run(self, cmd, cycles: int, threads: int = 1) -> float:
+        cmd = _arr(cmd)
+        return lib().shc_oracle_batch_run(self._h, _dp(cmd), cycles, threads)
+
+    def joints(self) -> np.ndarray:
+        out = np.empty((self.n, self.L, self.D), dtype=np.float64)
+        lib().shc_oracle_batch_get_joints(self._h, _dp(out))
+        return out
+
+    def get_state(self):
+        arr = (ShcRobotState * self.n)()
+        lib().shc_oracle_batch_get_state(self._h, arr)
+        return arr
+
+    def set_state(self, arr):
+        lib().shc_oracle_batch_set_state(self._h, arr)
+
+
+def fk(cfg, leg, q):
+    q = _arr(q)
+    out = np.empty(3)
+    lib().shc_oracle_fk(C.byref(cfg), leg, _dp(q), _dp(out))
+    return out
+
+
+def solve_ik(cfg, leg, q, qd, delta):
+    q, qd, delta = _arr(q), _arr(qd), _arr(delta)
+    out = np.empty(len(q))
+    lib().shc_oracle_solve_ik(C.byref(cfg), leg, _dp(q), _dp(qd), _dp(delta), _dp(out))
+    return out
+
+
+def step_cycle(cfg) -> ShcStartup:
+    s = ShcStartup()
+    lib().shc_oracle_step_cycle(C.byref(cfg), C.byref(s))
+    return s

@@ -1,0 +1,387 @@
+// shc_oracle_capi.cpp — TEST INFRASTRUCTURE ONLY.  extern "C" surface of the parity oracle for ctypes
+// (tests/, __graft_entry__.smoke(), bench.py cpu_baseline / --impl reference).  PARITY UNPINNED.
+#include <chrono>
+#include <cstdio>
+#include <thread>
+#include <vector>
+
+#include "../include/shc_state.h"
+#include "shc_oracle.hpp"
+
+using namespace shc_oracle;
+
+namespace {
+
+void fixPointers(Robot* r) {
+  for (int i = 0; i < SHC_MAX_LEGS; ++i) {
+    r->legs[i].robot = r;
+    r->legs[i].stepper.robot = r;
+    r->legs[i].stepper.leg_ = &r->legs[i];
+    r->legs[i].poser.robot = r;
+    r->legs[i].poser.leg_ = &r->legs[i];
+  }
+  for (auto& ap : r->auto_posers_) ap.robot = r;
+}
+
+Robot* cloneRobot(const Robot& src) {
+  Robot* r = new Robot(src);
+  fixPointers(r);
+  return r;
+}
+
+void putPose(double* o, const Pose& p) {
+  o[0] = p.position_.x; o[1] = p.position_.y; o[2] = p.position_.z;
+  o[3] = p.rotation_.w; o[4] = p.rotation_.x; o[5] = p.rotation_.y; o[6] = p.rotation_.z;
+}
+Pose getPose(const double* o) { return Pose(Vec3(o[0], o[1], o[2]), Quat(o[3], o[4], o[5], o[6])); }
+void put3(double* o, const Vec3& v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }
+Vec3 get3(const double* o) { return Vec3(o[0], o[1], o[2]); }
+
+void exportState(const Robot& r, shc_robot_state* s) {
+  std::memset(s, 0, sizeof(*s));
+  s->desired_linear_velocity[0] = r.desired_linear_velocity_[0];
+  s->desired_linear_velocity[1] = r.desired_linear_velocity_[1];
+  s->desired_angular_velocity = r.desired_angular_velocity_;
+  s->walk_state = r.walk_state_;
+  s->legs_at_correct_phase = r.legs_at_correct_phase_;
+  s->legs_completed_first_step = r.legs_completed_first_step_;
+  s->return_to_default_attempted = r.return_to_default_attempted_;
+  s->pose_state = r.pose_state_;
+  put3(s->walk_plane, r.walk_plane_);
+  put3(s->walk_plane_normal, r.walk_plane_normal_);
+  putPose(s->odometry_ideal, r.odometry_ideal_);
+  putPose(s->walk_plane_pose, r.walk_plane_pose_);
+  putPose(s->origin_walk_plane_pose, r.origin_walk_plane_pose_);
+  putPose(s->manual_pose, r.manual_pose_);
+  putPose(s->imu_pose, r.imu_pose_);
+  putPose(s->inclination_pose, r.inclination_pose_);
+  putPose(s->auto_pose, r.auto_pose_);
+  put3(s->rotation_absement_error, r.rotation_absement_error_);
+  put3(s->rotation_position_error, r.rotation_position_error_);
+  put3(s->rotation_velocity_error, r.rotation_velocity_error_);
+  s->auto_posing_state = r.auto_posing_state_;
+  s->pose_phase = r.pose_phase_;
+  for (size_t k = 0; k < r.auto_posers_.size() && k < SHC_MAX_AUTO_POSERS; ++k) {
+    const AutoPoser& ap = r.auto_posers_[k];
+    s->auto_poser_flags[k] = (ap.start_check_ ? 1 : 0) | (ap.end_check_first ? 2 : 0) | (ap.end_check_second ? 4 : 0) |
+                             (ap.allow_posing_ ? 8 : 0);
+  }
+  putPose(s->current_pose, r.current_pose_);
+  for (int i = 0; i < r.leg_count_; ++i) {
+    const Leg& leg = r.legs[i];
+    const LegStepper& st = leg.stepper;
+    shc_leg_state& o = s->legs[i];
+    for (int j = 0; j < leg.joint_count_; ++j) {
+      o.joint_position[j] = leg.joints[j + 1].desired_position_;
+      o.joint_velocity[j] = leg.joints[j + 1].desired_velocity_;
+    }
+    put3(o.tip_position, st.current_tip_pose_.position_);
+    put3(o.tip_velocity, st.current_tip_velocity_);
+    put3(o.swing_origin_position, st.swing_origin_tip_position_);
+    put3(o.swing_origin_velocity, st.swing_origin_tip_velocity_);
+    put3(o.stance_origin_position, st.stance_origin_tip_position_);
+    put3(o.default_tip_position, st.default_tip_pose_.position_);
+    put3(o.target_tip_position, st.target_tip_pose_.position_);
+    put3(o.stride_vector, st.stride_vector_);
+    put3(o.walk_plane, st.walk_plane_);
+    put3(o.walk_plane_normal, st.walk_plane_normal_);
+    o.swing_progress = st.swing_progress_;
+    o.stance_progress = st.stance_progress_;
+    o.phase = st.phase_;
+    o.step_state = st.step_state_;
+    o.at_correct_phase = st.at_correct_phase_;
+    o.completed_first_step = st.completed_first_step_;
+    o.admittance_state[0] = leg.admittance_state_[0];
+    o.admittance_state[1] = leg.admittance_state_[1];
+    put3(o.admittance_delta, leg.admittance_delta_);
+    put3(o.tip_force_calculated, leg.tip_force_calculated_);
+    o.negate_auto_pose = leg.poser.negate_auto_pose_;
+    put3(o.model_tip_position, leg.current_tip_pose_.position_);
+    put3(o.desired_tip_position, leg.desired_tip_pose_.position_);
+    o.ik_result = leg.last_ik_result_;
+  }
+}
+
+void importState(Robot& r, const shc_robot_state* s) {
+  r.desired_linear_velocity_[0] = s->desired_linear_velocity[0];
+  r.desired_linear_velocity_[1] = s->desired_linear_velocity[1];
+  r.desired_angular_velocity_ = s->desired_angular_velocity;
+  r.walk_state_ = WalkState(s->walk_state);
+  r.legs_at_correct_phase_ = s->legs_at_correct_phase;
+  r.legs_completed_first_step_ = s->legs_completed_first_step;
+  r.return_to_default_attempted_ = s->return_to_default_attempted != 0;
+  r.pose_state_ = PosingState(s->pose_state);
+  r.walk_plane_ = get3(s->walk_plane);
+  r.walk_plane_normal_ = get3(s->walk_plane_normal);
+  r.odometry_ideal_ = getPose(s->odometry_ideal);
+  r.walk_plane_pose_ = getPose(s->walk_plane_pose);
+  r.origin_walk_plane_pose_ = getPose(s->origin_walk_plane_pose);
+  r.manual_pose_ = getPose(s->manual_pose);
+  r.imu_pose_ = getPose(s->imu_pose);
+  r.inclination_pose_ = getPose(s->inclination_pose);
+  r.auto_pose_ = getPose(s->auto_pose);
+  r.rotation_absement_error_ = get3(s->rotation_absement_error);
+  r.rotation_position_error_ = get3(s->rotation_position_error);
+  r.rotation_velocity_error_ = get3(s->rotation_velocity_error);
+  r.auto_posing_state_ = PosingState(s->auto_posing_state);
+  r.pose_phase_ = s->pose_phase;
+  for (size_t k = 0; k < r.auto_posers_.size() && k < SHC_MAX_AUTO_POSERS; ++k) {
+    AutoPoser& ap = r.auto_posers_[k];
+    ap.start_check_ = s->auto_poser_flags[k] & 1;
+    ap.end_check_first = s->auto_poser_flags[k] & 2;
+    ap.end_check_second = s->auto_poser_flags[k] & 4;
+    ap.allow_posing_ = s->auto_poser_flags[k] & 8;
+  }
+  r.current_pose_ = getPose(s->current_pose);
+  for (int i = 0; i < r.leg_count_; ++i) {
+    Leg& leg = r.legs[i];
+    LegStepper& st = leg.stepper;
+    const shc_leg_state& o = s->legs[i];
+    for (int j = 0; j < leg.joint_count_; ++j) {
+      leg.joints[j + 1].desired_position_ = o.joint_position[j];
+      leg.joints[j + 1].desired_velocity_ = o.joint_velocity[j];
+    }
+    leg.applyFK();  // current_tip_pose_ is a function of the joint positions
+    st.current_tip_pose_.position_ = get3(o.tip_position);
+    st.current_tip_velocity_ = get3(o.tip_velocity);
+    st.swing_origin_tip_position_ = get3(o.swing_origin_position);
+    st.swing_origin_tip_velocity_ = get3(o.swing_origin_velocity);
+    st.stance_origin_tip_position_ = get3(o.stance_origin_position);
+    st.default_tip_pose_.position_ = get3(o.default_tip_position);
+    st.target_tip_pose_.position_ = get3(o.target_tip_position);
+    st.stride_vector_ = get3(o.stride_vector);
+    st.walk_plane_ = get3(o.walk_plane);
+    st.walk_plane_normal_ = get3(o.walk_plane_normal);
+    st.swing_progress_ = o.swing_progress;
+    st.stance_progress_ = o.stance_progress;
+    st.phase_ = o.phase;
+    st.step_state_ = StepState(o.step_state);
+    st.at_correct_phase_ = o.at_correct_phase != 0;
+    st.completed_first_step_ = o.completed_first_step != 0;
+    leg.admittance_state_[0] = o.admittance_state[0];
+    leg.admittance_state_[1] = o.admittance_state[1];
+    leg.admittance_delta_ = get3(o.admittance_delta);
+    leg.tip_force_calculated_ = get3(o.tip_force_calculated);
+    leg.poser.negate_auto_pose_ = o.negate_auto_pose != 0;
+  }
+}
+
+void fillStartup(const Robot& r, shc_startup* out) {
+  std::memset(out, 0, sizeof(*out));
+  for (int i = 0; i < r.leg_count_; ++i) {
+    for (int j = 0; j < r.legs[i].joint_count_; ++j) out->default_joint[i][j] = r.legs[i].joints[j + 1].default_position_;
+    if (!r.legs[i].workspace_.empty()) {
+      const LimitMap& wp = r.legs[i].workspace_.begin()->second;
+      for (int b = 0; b < SHC_N_BEARINGS; ++b) out->workspace[i][b] = wp.count(b * 45) ? wp.at(b * 45) : 0.0;
+    }
+    out->phase_offsets[i] = r.legs[i].stepper.phase_offset_;
+  }
+  for (int b = 0; b < SHC_N_BEARINGS; ++b) {
+    int k = b * 45;
+    out->walkspace[b] = r.walkspace_.count(k) ? r.walkspace_.at(k) : 0.0;
+    out->max_linear_speed[b] = r.max_linear_speed_.count(k) ? r.max_linear_speed_.at(k) : 0.0;
+    out->max_angular_speed[b] = r.max_angular_speed_.count(k) ? r.max_angular_speed_.at(k) : 0.0;
+    out->max_linear_acceleration[b] = r.max_linear_acceleration_.count(k) ? r.max_linear_acceleration_.at(k) : 0.0;
+    out->max_angular_acceleration[b] = r.max_angular_acceleration_.count(k) ? r.max_angular_acceleration_.at(k) : 0.0;
+  }
+  out->step_frequency = r.step_.frequency_;
+  out->period = r.step_.period_;
+  out->swing_period = r.step_.swing_period_;
+  out->stance_period = r.step_.stance_period_;
+  out->stance_end = r.step_.stance_end_;
+  out->swing_start = r.step_.swing_start_;
+  out->swing_end = r.step_.swing_end_;
+  out->stance_start = r.step_.stance_start_;
+  out->pose_phase_length = r.pose_phase_length_;
+  out->pose_normaliser = r.normaliser_;
+  out->auto_pose_reference_leg = r.auto_pose_reference_leg_;
+}
+
+struct Batch {
+  shc_config cfg;
+  std::vector<Robot*> robots;
+  int startup_loops = 0;
+};
+
+void stepOne(Robot& r, const double* cmd, const double* imu, const double* tip_force, const double* manual) {
+  // Inputs arrive through callbacks in ros::spinOnce() before the next loop() (main.cpp:130).
+  if (imu) r.setImuData(Quat(imu[0], imu[1], imu[2], imu[3]), Vec3(imu[7], imu[8], imu[9]), Vec3(imu[4], imu[5], imu[6]));
+  if (tip_force)
+    for (int l = 0; l < r.leg_count_; ++l) r.legs[l].tip_force_measured_ = Vec3(tip_force[l * 3], tip_force[l * 3 + 1], tip_force[l * 3 + 2]);
+  if (manual) {  // poser_->setManualPoseInput (state_controller.cpp:1148)
+    r.translation_velocity_input_ = Vec3(manual[0], manual[1], manual[2]);
+    r.rotation_velocity_input_ = Vec3(manual[3], manual[4], manual[5]);
+  }
+  r.setBodyVelocityInput(cmd[0], cmd[1], cmd[2]);
+  r.loop();
+}
+
+}  // namespace
+
+extern "C" {
+
+// One robot is taken through StateController::init + the direct start-up (PACKED -> READY) once, then cloned n times
+// and put in RUNNING state; engine cycle 0 corresponds to the first full loop() in RUNNING state.
+void* shc_oracle_batch_create(const shc_config* cfg, int n_robots) {
+  Batch* b = new Batch();
+  b->cfg = *cfg;
+  Robot proto(*cfg);
+  proto.stateInit();
+  int loops = 0;
+  while (proto.robot_state_ != READY && loops < 100000) {
+    proto.requestRobotState(RUNNING);
+    proto.loop();
+    ++loops;
+  }
+  b->startup_loops = loops;
+  proto.robot_state_ = RUNNING;
+  proto.new_robot_state_ = RUNNING;
+  proto.transition_state_flag_ = false;
+  for (int i = 0; i < n_robots; ++i) b->robots.push_back(cloneRobot(proto));
+  return b;
+}
+
+void shc_oracle_batch_destroy(void* h) {
+  Batch* b = static_cast<Batch*>(h);
+  for (Robot* r : b->robots) delete r;
+  delete b;
+}
+
+int shc_oracle_batch_size(void* h) { return int(static_cast<Batch*>(h)->robots.size()); }
+int shc_oracle_startup_loops(void* h) { return static_cast<Batch*>(h)->startup_loops; }
+
+void shc_oracle_get_startup(void* h, shc_startup* out) { fillStartup(*static_cast<Batch*>(h)->robots[0], out); }
+
+// cmd [n][3]; imu [n][10] (quat wxyz, gyro xyz, accel xyz) or NULL; tip_force [n][L][3] or NULL; manual [n][6] or NULL.
+void shc_oracle_batch_step(void* h, const double* cmd, const double* imu, const double* tip_force, const double* manual,
+                           int n_threads) {
+  Batch* b = static_cast<Batch*>(h);
+  const int n = int(b->robots.size());
+  const int L = b->cfg.leg_count;
+  auto work = [&](int lo, int hi) {
+    for (int i = lo; i < hi; ++i)
+      stepOne(*b->robots[i], cmd + 3 * i, imu ? imu + 10 * i : nullptr, tip_force ? tip_force + 3 * L * i : nullptr,
+              manual ? manual + 6 * i : nullptr);
+  };
+  if (n_threads <= 1 || n < 2 * n_threads) {
+    work(0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int t = 0; t < n_threads; ++t) th.emplace_back(work, int((long long)n * t / n_threads), int((long long)n * (t + 1) / n_threads));
+  for (auto& t : th) t.join();
+}
+
+// Runs `cycles` control cycles with a constant command per robot and returns wall seconds (CPU baseline timing).
+double shc_oracle_batch_run(void* h, const double* cmd, int cycles, int n_threads) {
+  auto t0 = std::chrono::steady_clock::now();
+  for (int c = 0; c < cycles; ++c) shc_oracle_batch_step(h, cmd, nullptr, nullptr, nullptr, n_threads);
+  auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+void shc_oracle_batch_get_joints(void* h, double* out) {  // [n][L][D]
+  Batch* b = static_cast<Batch*>(h);
+  const int L = b->cfg.leg_count, D = b->cfg.joint_count;
+  for (size_t i = 0; i < b->robots.size(); ++i)
+    for (int l = 0; l < L; ++l)
+      for (int j = 0; j < D; ++j) out[(i * L + l) * D + j] = b->robots[i]->legs[l].joints[j + 1].desired_position_;
+}
+
+void shc_oracle_batch_get_state(void* h, shc_robot_state* out) {
+  Batch* b = static_cast<Batch*>(h);
+  for (size_t i = 0; i < b->robots.size(); ++i) exportState(*b->robots[i], out + i);
+}
+
+void shc_oracle_batch_set_state(void* h, const shc_robot_state* in) {
+  Batch* b = static_cast<Batch*>(h);
+  for (size_t i = 0; i < b->robots.size(); ++i) importState(*b->robots[i], in + i);
+}
+
+int shc_oracle_state_record_size(void) { return int(sizeof(shc_robot_state)); }
+int shc_oracle_config_size(void) { return int(sizeof(shc_config)); }
+int shc_oracle_startup_size(void) { return int(sizeof(shc_startup)); }
+
+// ---- unit-test hooks ------------------------------------------------------------------------------------------
+int shc_oracle_mod(int a, int b) { return om::mod(a, b); }
+int shc_oracle_round_to_int(double x) { return om::roundToInt(x); }
+int shc_oracle_round_to_even_int(double x) { return om::roundToEvenInt(x); }
+double shc_oracle_smooth_step(double c) { return om::smoothStep(c); }
+void shc_oracle_quat_to_euler(const double q[4], int intrinsic, double out[3]) {
+  Vec3 e = om::quaternionToEulerAngles(Quat(q[0], q[1], q[2], q[3]), intrinsic != 0);
+  put3(out, e);
+}
+void shc_oracle_euler_to_quat(const double e[3], int intrinsic, double out[4]) {
+  Quat q = om::eulerAnglesToQuaternion(Vec3(e[0], e[1], e[2]), intrinsic != 0);
+  out[0] = q.w; out[1] = q.x; out[2] = q.y; out[3] = q.z;
+}
+void shc_oracle_dh(double d, double theta, double r, double alpha, double out[16]) {
+  Mat4 m = om::createDHMatrix(d, theta, r, alpha);
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) out[i * 4 + j] = m.m[i][j];
+}
+void shc_oracle_quartic_bezier(const double nodes[15], double t, double out[3], double out_dot[3]) {
+  Vec3 n[5];
+  for (int i = 0; i < 5; ++i) n[i] = get3(nodes + 3 * i);
+  put3(out, om::quarticBezier(n, t));
+  put3(out_dot, om::quarticBezierDot(n, t));
+}
+void shc_oracle_from_two_vectors(const double a[3], const double b[3], double out[4]) {
+  Quat q = om::fromTwoVectors(get3(a), get3(b));
+  out[0] = q.w; out[1] = q.x; out[2] = q.y; out[3] = q.z;
+}
+void shc_oracle_slerp(const double a[4], double t, const double b[4], double out[4]) {
+  Quat q = om::slerp(Quat(a[0], a[1], a[2], a[3]), t, Quat(b[0], b[1], b[2], b[3]));
+  out[0] = q.w; out[1] = q.x; out[2] = q.y; out[3] = q.z;
+}
+void shc_oracle_pose_ops(const double a[7], const double b[7], double add_out[7], double remove_out[7], double inv_out[7]) {
+  Pose A = getPose(a), B = getPose(b);
+  putPose(add_out, A.addPose(B));
+  putPose(remove_out, A.removePose(B));
+  putPose(inv_out, ~A);
+}
+// Forward kinematics of one leg at joint angles q (model.cpp:945): tip position in the base_link frame.
+void shc_oracle_fk(const shc_config* cfg, int leg, const double* q, double out_tip[3]) {
+  Robot r(*cfg);
+  Leg& l = r.legs[leg];
+  for (int j = 0; j < l.joint_count_; ++j) l.joints[j + 1].desired_position_ = q[j];
+  Pose p = l.applyFK();
+  put3(out_tip, p.position_);
+}
+// One Leg::solveIK call (model.cpp:726) at joint state (q, qd) for a leg-frame position delta.
+void shc_oracle_solve_ik(const shc_config* cfg, int leg, const double* q, const double* qd, const double delta[3],
+                         double* out_dq) {
+  Robot r(*cfg);
+  Leg& l = r.legs[leg];
+  for (int j = 0; j < l.joint_count_; ++j) {
+    l.joints[j + 1].desired_position_ = q[j];
+    l.joints[j + 1].desired_velocity_ = qd[j];
+  }
+  l.applyFK();
+  double d6[6] = {delta[0], delta[1], delta[2], 0, 0, 0};
+  l.solveIK(d6, false, out_dq);
+}
+// generateStepCycle only (walk_controller.cpp:365) + phase offsets (walk_controller.cpp:237-278).
+void shc_oracle_step_cycle(const shc_config* cfg, shc_startup* out) {
+  Robot r(*cfg);
+  r.walkerInit();
+  r.generateLimits();  // walkspace empty: only sets the phase offsets
+  fillStartup(r, out);
+}
+// One admittance update for one leg from state x with measured force f (admittance_controller.cpp:22).
+void shc_oracle_admittance(const shc_config* cfg, const double x_in[2], const double force[3], double x_out[2]) {
+  Robot r(*cfg);
+  r.legs[0].admittance_state_[0] = x_in[0];
+  r.legs[0].admittance_state_[1] = x_in[1];
+  // undo the force gain so that `force` is the value seen by the integrator
+  r.params_.force_gain = 1.0;
+  r.legs[0].tip_force_measured_ = get3(force);
+  r.params_.use_joint_effort = 0;
+  r.leg_count_ = 1;
+  r.legs[0].current_tip_pose_ = Pose::Identity();
+  r.updateAdmittance();
+  x_out[0] = r.legs[0].admittance_state_[0];
+  x_out[1] = r.legs[0].admittance_state_[1];
+}
+
+}  // extern "C"
