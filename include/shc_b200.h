@@ -1,0 +1,146 @@
+/*
+ * shc_b200.h — C-ABI of the batched, B200-native SHC control-cycle engine (libshc_b200.so).
+ *
+ * The reference (csiro-robotics/syropod_highlevel_controller v0.5.11) has no plugin / FFI interface: it is one ROS
+ * executable (CMakeLists.txt:116-117,146).  The only seam is the C++ class surface StateController drives each
+ * cycle.  Every entry point below therefore cites the reference call(s) it replaces; the C++ facade in
+ * include/shc_facade.hpp re-exposes them under the reference's own class and method names.
+ *
+ * One engine = N independent robots of one morphology (L legs x D joints) on one CUDA device, state resident in HBM.
+ * All functions return 0 on success and a negative SHC_E_* code on failure; nothing throws.  An engine handle is not
+ * re-entrant; different handles may be used from different threads (as the reference: single-threaded per controller,
+ * main.cpp:106-132).  There is NO CPU fallback: without a CUDA device shc_create fails with SHC_E_CUDA.
+ */
+#ifndef SHC_B200_H
+#define SHC_B200_H
+
+#include <stddef.h>
+
+#include "shc_config.h"
+#include "shc_state.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct shc_engine shc_engine;
+
+enum {
+  SHC_OK = 0,
+  SHC_E_INVALID = -1,     /* bad argument / unsupported configuration (message via shc_last_error) */
+  SHC_E_CUDA = -2,        /* CUDA runtime error or no device */
+  SHC_E_UNSUPPORTED = -3  /* reference feature outside the hot-path scope (rough terrain, manual legs, ...) */
+};
+
+/* Arithmetic of the device path. */
+enum {
+  SHC_PRECISION_F64 = 0,   /* state and arithmetic in double: tracks the reference's Eigen double path to ~1e-12 */
+  SHC_PRECISION_MIXED = 1  /* fp32 state/IO, fp64 only for the open-loop accumulators and branch decisions */
+};
+
+/* Per-robot status word written by shc_step when flags are enabled (shc_set_options).  Replaces the reference's
+ * rosconsole warnings / ROS_FATAL (model.cpp:852,916-929; pose_controller.cpp:1228-1232). */
+enum {
+  SHC_FLAG_IK_DEVIATION = 1,   /* some leg: |FK(q) - desired| > IK_TOLERANCE on an axis (applyIK would return 0) */
+  SHC_FLAG_POSITION_CLAMP = 2, /* some joint clamped to its position limit */
+  SHC_FLAG_VELOCITY_CLAMP = 4, /* some joint clamped to its velocity limit */
+  SHC_FLAG_IMU_UNSTABLE = 8    /* IMU PID correction beyond STABILITY_THRESHOLD */
+};
+
+enum { SHC_OPT_STATUS_FLAGS = 1 }; /* compute the status word each cycle (costs one extra FK per leg) */
+
+/* Creates an engine for n_robots robots in the state the reference reaches at the end of its direct start-up
+ * (StateController::init + transitionRobotState PACKED->READY->RUNNING, state_controller.cpp:127-281).
+ * `startup` may be NULL: the engine then runs its own host-side restatement of directStartup / generateWorkspaces /
+ * generateWalkspace / generateLimits once (pose_controller.cpp:463, model.cpp:120, walk_controller.cpp:57,231);
+ * otherwise the given constants are used as they are.  `device` is the CUDA ordinal. */
+int shc_create(const shc_config* cfg, const shc_startup* startup, int n_robots, int device, int precision,
+               shc_engine** out);
+void shc_destroy(shc_engine* e);
+
+/* The start-up constants alone (host arithmetic only; needs no device): what shc_create computes when `startup` is
+ * NULL.  Mirrors WalkController::generateStepCycle / generateLimits / generateWalkspace, Model::generateWorkspaces and
+ * PoseController::directStartup of the reference. */
+int shc_compute_startup(const shc_config* cfg, shc_startup* out);
+
+/* Host (double) evaluation of the Leg::applyIK routine shared with the kernels: one leg, q/qd [D] in/out. */
+int shc_host_apply_ik(const shc_config* cfg, int leg, double* q, double* qd, const double* desired, int simulation,
+                      double* tip_out, double* ik_result);
+
+/* Last error text of this thread (static storage). */
+const char* shc_last_error(void);
+
+/* Start-up constants in use (WalkController::getWalkspace / limit maps / getStepCycle). */
+int shc_get_startup(const shc_engine* e, shc_startup* out);
+int shc_n_robots(const shc_engine* e);
+int shc_options(const shc_engine* e);
+int shc_set_options(shc_engine* e, int options);
+/* PoseController::setPoseResetMode (pose_controller.h:105); applies to every robot of the batch. */
+int shc_set_pose_reset_mode(shc_engine* e, int mode);
+
+/* Whole-batch state exchange in the array-of-structs record of shc_state.h (n_robots records).
+ * Replaces the reference's getters over Model/Leg/LegStepper/PoseController members (state_controller.cpp:809-1078). */
+int shc_get_state(shc_engine* e, shc_robot_state* out, size_t n_records);
+int shc_set_state(shc_engine* e, const shc_robot_state* in, size_t n_records);
+
+/* ONE control cycle for every robot = StateController::loop() in RUNNING state (state_controller.cpp:162-193):
+ *   PoseController::updateCurrentPose -> WalkController::setPoseState -> [AdmittanceController::updateStiffness,
+ *   updateAdmittance] -> runningState(): WalkController::updateWalk -> PoseController::updateStance ->
+ *   Model::updateModel (Leg::setDesiredTipPose + Leg::applyIK per leg).
+ * All pointers are DEVICE pointers, float32:
+ *   cmd        [N][3]  body velocity command (vx, vy, wz) as published on the reference's velocity topic; the
+ *                      bodyVelocityInputCallback scaling/clamp (state_controller.cpp:1127-1136) is applied inside
+ *   imu        [N][10] or NULL: orientation quaternion (w,x,y,z), angular velocity (3), linear acceleration (3)
+ *                      (imuCallback -> Model::setImuData, state_controller.cpp:1551-1562)
+ *   tip_force  [N][L][3] or NULL: measured tip force (tipStatesCallback, state_controller.cpp:1618-1646)
+ *   manual     [N][6]  or NULL: manual pose velocity input, translation xyz + rotation rpy (setManualPoseInput :1148)
+ *   joints_out [N][L][D] desired joint positions + offset, the order of Leg::generateDesiredJointStateMsg
+ *                      (model.cpp:605-617) / publishDesiredJointState (state_controller.cpp:777-805)
+ * `stream` is a cudaStream_t (NULL = the engine's own stream).  Asynchronous. */
+int shc_step(shc_engine* e, const float* cmd, const float* imu, const float* tip_force, const float* manual,
+             float* joints_out, void* stream);
+
+/* Same cycle with HOST buffers: pinned staging, host->device copy of the inputs, kernel, device->host copy of the joint
+ * angles, then a stream synchronize.  This is the call the C++ facade makes per cycle. */
+int shc_step_host(shc_engine* e, const float* cmd, const float* imu, const float* tip_force, const float* manual,
+                  float* joints_out);
+
+/* k_cycles cycles with device-resident per-cycle commands cmd_seq [k][N][3] (imu_seq / force_seq likewise or NULL);
+ * joints_out receives the last cycle.  Launches are captured once into a CUDA graph per (k, pointer set). */
+int shc_rollout(shc_engine* e, int k_cycles, const float* cmd_seq, const float* imu_seq, const float* force_seq,
+                float* joints_out, void* stream);
+
+/* Measured joint efforts for Leg::calculateTipForce (jointStatesCallback, state_controller.cpp:1565-1590): device
+ * pointer float [N][L][D], latched until changed; NULL = all zero.  Only read when use_joint_effort is set. */
+int shc_set_joint_efforts(shc_engine* e, const float* efforts_dev);
+
+/* The engine's own CUDA stream (cudaStream_t) and a blocking wait on it. */
+void* shc_stream(shc_engine* e);
+int shc_synchronize(shc_engine* e);
+
+/* Device pointer to the per-robot status words (int32 [N]) of the last cycle; NULL unless SHC_OPT_STATUS_FLAGS. */
+const int* shc_status_flags_device(const shc_engine* e);
+/* Blocking copy of the status words to host memory (int32 [N]). */
+int shc_get_status_flags(shc_engine* e, int* host_out);
+
+/* Stand-alone batched Leg::applyIK (model.cpp:861) on caller-provided joint state, used by the start-up sweeps
+ * (workspace generation) and by the kernel unit tests.  Device pointers; n_legs rows each using the chain of leg
+ * index leg_id[i]:  q, qd [n][D] (in/out, double), desired_tip [n][3] (base_link frame, double), simulation flag as
+ * Leg::applyIK(simulation); ik_result [n] (double) receives applyIK's return value. */
+int shc_apply_ik(shc_engine* e, int n_legs, const int* leg_id, double* q, double* qd, const double* desired_tip,
+                 int simulation, double* tip_out, double* ik_result, void* stream);
+
+/* Byte sizes for binding checks. */
+size_t shc_sizeof_config(void);
+size_t shc_sizeof_startup(void);
+size_t shc_sizeof_robot_state(void);
+
+/* Algorithmic bytes one control cycle moves per robot for this engine's configuration (state read + write, inputs,
+ * outputs), as laid out on the device; and the figure of SURVEY.md §8(d) (4-byte words) for the same configuration. */
+size_t shc_bytes_per_step_device(const shc_engine* e);
+size_t shc_bytes_per_step_algorithmic(const shc_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHC_B200_H */

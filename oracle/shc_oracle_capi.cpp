@@ -273,9 +273,23 @@ void shc_oracle_batch_step(void* h, const double* cmd, const double* imu, const 
 }
 
 // Runs `cycles` control cycles with a constant command per robot and returns wall seconds (CPU baseline timing).
+// Robots are partitioned over n_threads std::threads; each thread runs all cycles of its own robots (robots are
+// independent, so no per-cycle synchronisation is needed).
 double shc_oracle_batch_run(void* h, const double* cmd, int cycles, int n_threads) {
+  Batch* b = static_cast<Batch*>(h);
+  const int n = int(b->robots.size());
+  auto work = [&](int lo, int hi) {
+    for (int i = lo; i < hi; ++i)
+      for (int c = 0; c < cycles; ++c) stepOne(*b->robots[i], cmd + 3 * i, nullptr, nullptr, nullptr);
+  };
   auto t0 = std::chrono::steady_clock::now();
-  for (int c = 0; c < cycles; ++c) shc_oracle_batch_step(h, cmd, nullptr, nullptr, nullptr, n_threads);
+  if (n_threads <= 1) {
+    work(0, n);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work, int((long long)n * t / n_threads), int((long long)n * (t + 1) / n_threads));
+    for (auto& t : th) t.join();
+  }
   auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();
 }
@@ -385,3 +399,25 @@ void shc_oracle_admittance(const shc_config* cfg, const double x_in[2], const do
 }
 
 }  // extern "C"
+
+extern "C" {
+// One Leg::applyIK (model.cpp:861) from joint state (q, qd) toward `desired` (base_link frame).
+double shc_oracle_apply_ik(const shc_config* cfg, int leg, double* q, double* qd, const double desired[3], int simulation,
+                           double tip_out[3]) {
+  Robot r(*cfg);
+  Leg& l = r.legs[leg];
+  for (int j = 0; j < l.joint_count_; ++j) {
+    l.joints[j + 1].desired_position_ = q[j];
+    l.joints[j + 1].desired_velocity_ = qd[j];
+  }
+  l.applyFK();
+  l.setDesiredTipPose(Pose(get3(desired), UndefinedRotation()));
+  double res = l.applyIK(simulation != 0);
+  for (int j = 0; j < l.joint_count_; ++j) {
+    q[j] = l.joints[j + 1].desired_position_;
+    qd[j] = l.joints[j + 1].desired_velocity_;
+  }
+  put3(tip_out, l.current_tip_pose_.position_);
+  return res;
+}
+}

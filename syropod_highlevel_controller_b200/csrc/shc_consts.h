@@ -1,0 +1,90 @@
+// shc_consts.h — batch-wide constants of one engine, passed to every kernel as a __grid_constant__ parameter
+// (constant bank, uniform access).  Everything here is either a reference parameter (include/shc_config.h) or a
+// value the reference's start-up path produces once (include/shc_config.h: shc_startup), pre-digested on the host in
+// IEEE double exactly as the reference computes it (e.g. the FP-derived iteration counts of
+// walk_controller.cpp:1035-1041 — SURVEY.md §7 "FP-derived integers").
+#pragma once
+#include "../../include/shc_config.h"
+
+namespace shc {
+
+constexpr int kMaxLegs = SHC_MAX_LEGS;
+constexpr int kMaxDof = SHC_MAX_DOF;
+constexpr int kMaxPosers = SHC_MAX_AUTO_POSERS;
+
+// Real-valued constants in one precision.
+template <class R> struct RealConsts {
+  // per leg ---------------------------------------------------------------------------------------------------
+  R t1r[kMaxLegs][9];  // rotation of the constant base transform T1 = DH(link 0), row-major (model.cpp:224, A.1)
+  R t1p[kMaxLegs][3];  // translation of T1
+  R dh_d[kMaxLegs][kMaxDof], dh_theta[kMaxLegs][kMaxDof], dh_r[kMaxLegs][kMaxDof];  // links 1..D
+  R dh_ca[kMaxLegs][kMaxDof], dh_sa[kMaxLegs][kMaxDof];                            // cos/sin(alpha) are constants
+  R jmin[kMaxLegs][kMaxDof], jmax[kMaxLegs][kMaxDof], vmax[kMaxLegs][kMaxDof];
+  R joffset[kMaxLegs][kMaxDof];     // added to the published joint command only (state_controller.cpp:795)
+  R jcentre[kMaxLegs][kMaxDof];     // min + range/2                                   (model.cpp:771)
+  R jcost_pos[kMaxLegs][kMaxDof];   // w / range (0 when range == 0)                   (model.cpp:775)
+  R jgrad_pos[kMaxLegs][kMaxDof];   // -w^2 / range^2 (0 when range == 0)              (model.cpp:777)
+  R jcost_vel[kMaxLegs][kMaxDof];   // w / (2 vmax)                                    (model.cpp:784)
+  R jgrad_vel[kMaxLegs][kMaxDof];   // -w^2 / (2 vmax)^2                               (model.cpp:786)
+  R identity_x[kMaxLegs], identity_y[kMaxLegs];  // identity tip position (walk_controller.cpp:34-42)
+  R ysign[kMaxLegs];                // +1 when identity y > 0 else -1 (walk_controller.cpp:1244)
+  R span_dy[kMaxLegs];              // calculateStanceSpanChange().y with the simple one-plane workspace (:949)
+  R stance_dt_mod[kMaxLegs];        // 1/stance_iterations with modified_stance_start = phase offset (:1025-1041)
+  R stride_scaler_mod[kMaxLegs];    // modified_stance_period / stance_period (:1167)
+  // robot-wide --------------------------------------------------------------------------------------------------
+  R dt, inv_dt;
+  R swing_dt;          // swing_delta_t_ (:1037)
+  R stance_dt_std;     // stance_delta_t_ for the standard stance period
+  R stride_scale;      // on_ground_ratio / frequency (:940-941)
+  R swing_height, swing_width, body_clearance;
+  R lambda2;           // DLS_COEFFICIENT^2 (model.h:19)
+  R limits[4][SHC_N_BEARINGS];  // max linear speed, angular speed, linear accel, angular accel (walk_controller.cpp:231)
+  R swing_progress_scaler;      // max(1, swing_phase / phase_offset) (pose_controller.cpp:1102)
+  R inv_swing_period, inv_stance_period;
+  R max_translation[3], max_rotation[3], max_translation_velocity, max_rotation_velocity;
+  R pid_p, pid_i, pid_d;
+  R adm_P[4], adm_q[2];  // 30 RK4 steps of the virtual mass-spring-damper as one affine map x <- P x + q F (A.6)
+  R force_gain;
+  R body_velocity_scaler;  // bodyVelocityInputCallback (state_controller.cpp:1131)
+  // auto posers (pose_controller.cpp:1338)
+  R ap_pos[kMaxPosers][3], ap_rot[kMaxPosers][3], ap_gravity[kMaxPosers];
+  R neg_ratio[kMaxLegs];
+};
+
+struct IntConsts {
+  int L, D;
+  int n_robots, n_pad;  // plane stride (n_pad is a multiple of 32)
+  // StepCycle (walk_controller.h:23)
+  int period, swing_period, stance_period, stance_end, swing_start, swing_end, stance_start;
+  int swing_iterations;        // even-rounded (:1035-1036)
+  int phase_offset[kMaxLegs];
+  int mod_stance_start[kMaxLegs];  // = phase offset
+  // flags
+  int manual_posing, auto_posing, inclination_posing, imu_posing, admittance_control, use_joint_effort;
+  int clamp_joint_positions, clamp_joint_velocities, velocity_input_mode, force_normal_touchdown;
+  // auto posing
+  int n_posers, pose_phase_length, pose_normaliser, pose_sync, auto_ref_leg;
+  int ap_start[kMaxPosers], ap_end[kMaxPosers];
+  int neg_start[kMaxLegs], neg_end[kMaxLegs];
+  // plane indices (see shc_layout.h)
+  int nS, nD, nI;              // number of storage / double / int planes
+  int offS_imu, offS_auto, offS_leg, strideS_leg, offS_leg_adm;
+  int offD_leg, strideD_leg;
+  int offI_leg, strideI_leg, offI_auto;
+};
+
+struct Consts {
+  IntConsts i;
+  RealConsts<double> d;
+  RealConsts<float> f;
+};
+
+template <class R> struct ConstSel;
+template <> struct ConstSel<double> {
+  static __host__ __device__ __forceinline__ const RealConsts<double>& get(const Consts& c) { return c.d; }
+};
+template <> struct ConstSel<float> {
+  static __host__ __device__ __forceinline__ const RealConsts<float>& get(const Consts& c) { return c.f; }
+};
+
+}  // namespace shc

@@ -1,0 +1,974 @@
+// shc_cycle.cuh — one fused control cycle for one robot (device code shared by the control_cycle kernels).
+//
+// Replaces, in the reference's call order (state_controller.cpp:162-193, 379-447):
+//   PoseController::updateCurrentPose      pose_controller.cpp:811   (walk-plane :1092, manual :863, inclination :1240,
+//                                                                     IMU PID :1191, auto :1134/:1338/:1716)
+//   AdmittanceController::updateAdmittance admittance_controller.cpp:22
+//   WalkController::updateWalk             walk_controller.cpp:440   (getLimit :414, LegStepper::updateTipPosition :1018,
+//                                                                     iteratePhase :871, updateWalkPlane :748, odometry :783)
+//   PoseController::updateStance           pose_controller.cpp:110
+//   Model::updateModel                     model.cpp:142             (setDesiredTipPose :653, applyIK :861, solveIK :726,
+//                                                                     updateJointPositions :799, applyFK :945,
+//                                                                     calculateTipForce :667)
+//
+// Precision policy P: S = storage planes, T = trajectory arithmetic, K = pose/kinematics arithmetic.  Branch decisions
+// the reference takes on doubles (limit-map bucket, walk-plane progress window, stop tolerance) are always taken in
+// double from the double accumulators, so the fp32 instantiation follows the same control flow as the reference.
+#pragma once
+#include "shc_consts.h"
+#include "shc_layout.h"
+#include "shc_math.cuh"
+
+namespace shc {
+
+template <class S_, class T_, class K_> struct Prec {
+  using S = S_;
+  using T = T_;
+  using K = K_;
+};
+using PrecF64 = Prec<double, double, double>;
+
+struct StepIO {
+  const float* cmd;        // [N][3]
+  const float* imu;        // [N][10] or null
+  const float* tip_force;  // [N][L][3] or null
+  const float* manual;     // [N][6] or null
+  const float* efforts;    // [N][L][D] or null: measured joint efforts (jointStatesCallback, state_controller.cpp:1565)
+  float* joints_out;       // [N][L][D]
+  int* flags_out;          // [N] or null
+  int pose_reset_mode;
+};
+
+template <class S> struct Planes {
+  S* s;
+  double* d;
+  int* i;
+};
+
+// DH chain of one leg in the leg (joint-1) frame.  Frame i (i = 1..D-1) is the frame of joint i+1, i.e. the product
+// T2..T(i+1) of A.1; `tip` is T2..TD*Ttip.  Composition uses the sparse DH form
+//   x' = x c + y s ; u = y c - x s ; y' = u ca + z sa ; z' = z ca - u sa ; p' = p + r x' + d z
+template <class K, int D> struct Chain {
+  V3<K> z[D];  // joint axes in the leg frame (z[0] = (0,0,1))
+  V3<K> p[D];  // joint origins in the leg frame (p[0] = 0)
+  V3<K> tip;   // tip position in the leg frame
+  V3<K> tipx;  // x axis of the tip frame in the leg frame (last-link direction)
+};
+
+template <class K, int D, class QT>
+SHC_HD void leg_chain(const RealConsts<K>& ck, int leg, const QT* q, Chain<K, D>& ch) {
+  V3<K> ax{K(1), K(0), K(0)}, ay{K(0), K(1), K(0)}, az{K(0), K(0), K(1)}, ap{K(0), K(0), K(0)};
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    ch.z[j] = az;
+    ch.p[j] = ap;
+    K s, c;
+    sincos_(ck.dh_theta[leg][j] + K(q[j]), &s, &c);
+    const K ca = ck.dh_ca[leg][j], sa = ck.dh_sa[leg][j];
+    V3<K> nx = ax * c + ay * s;
+    V3<K> u = ay * c - ax * s;
+    V3<K> ny = u * ca + az * sa;
+    V3<K> nz = az * ca - u * sa;
+    ap = ap + nx * ck.dh_r[leg][j] + az * ck.dh_d[leg][j];
+    ax = nx; ay = ny; az = nz;
+  }
+  ch.tip = ap;
+  ch.tipx = ax;
+}
+
+template <class K> SHC_HD V3<K> t1_rotate(const RealConsts<K>& ck, int leg, V3<K> v) {
+  const K* r = ck.t1r[leg];
+  return {r[0] * v.x + r[1] * v.y + r[2] * v.z, r[3] * v.x + r[4] * v.y + r[5] * v.z, r[6] * v.x + r[7] * v.y + r[8] * v.z};
+}
+template <class K> SHC_HD V3<K> t1_rotate_inv(const RealConsts<K>& ck, int leg, V3<K> v) {
+  const K* r = ck.t1r[leg];
+  return {r[0] * v.x + r[3] * v.y + r[6] * v.z, r[1] * v.x + r[4] * v.y + r[7] * v.z, r[2] * v.x + r[5] * v.y + r[8] * v.z};
+}
+
+// Solve the symmetric positive definite 3x3 system A x = b (A = Jp Jp^T + lambda^2 I) by Cholesky.
+template <class K> SHC_HD V3<K> spd3_solve(K a00, K a01, K a02, K a11, K a12, K a22, V3<K> b) {
+  K l00 = sqrt_(a00);
+  K i00 = K(1) / l00;
+  K l10 = a01 * i00, l20 = a02 * i00;
+  K l11 = sqrt_(a11 - l10 * l10);
+  K i11 = K(1) / l11;
+  K l21 = (a12 - l20 * l10) * i11;
+  K l22 = sqrt_(a22 - l20 * l20 - l21 * l21);
+  K i22 = K(1) / l22;
+  K y0 = b.x * i00;
+  K y1 = (b.y - l10 * y0) * i11;
+  K y2 = (b.z - l20 * y0 - l21 * y1) * i22;
+  K x2 = y2 * i22;
+  K x1 = (y1 - l21 * x2) * i11;
+  K x0 = (y0 - l10 * x1 - l20 * x2) * i00;
+  return {x0, x1, x2};
+}
+
+// Solve the symmetric positive definite DxD system A x = b in place (Cholesky), D <= 5.
+template <class K, int D> SHC_HD void spdN_solve(K A[D][D], K b[D]) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      K sum = A[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) sum -= A[i][k] * A[j][k];
+      if (i == j) A[i][i] = sqrt_(sum);
+      else A[i][j] = sum / A[j][j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    K sum = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) sum -= A[i][k] * b[k];
+    b[i] = sum / A[i][i];
+  }
+#pragma unroll
+  for (int i = D - 1; i >= 0; --i) {
+    K sum = b[i];
+#pragma unroll
+    for (int k = i + 1; k < D; ++k) sum -= A[k][i] * b[k];
+    b[i] = sum / A[i][i];
+  }
+}
+
+// Leg::calculateTipForce (model.cpp:667-708): F_leg = Jp (J^T J + l^2 I_D)^-1 tau with the full 6xD Jacobian
+// (angular rows = joint axes), rotated by the rotation of T1^-1, before the low-pass filter.
+template <class K, int D>
+SHC_HD V3<K> raw_tip_force(const RealConsts<K>& ck, int leg, const Chain<K, D>& ch, const K* tau) {
+  V3<K> Jp[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) Jp[j] = cross(ch.z[j], ch.tip - ch.p[j]);
+  K A[D][D];
+  K x[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    x[i] = tau[i];
+#pragma unroll
+    for (int j = 0; j < D; ++j) A[i][j] = dot(Jp[i], Jp[j]) + dot(ch.z[i], ch.z[j]) + (i == j ? ck.lambda2 : K(0));
+  }
+  spdN_solve<K, D>(A, x);
+  V3<K> f{K(0), K(0), K(0)};
+#pragma unroll
+  for (int j = 0; j < D; ++j) f = f + Jp[j] * x[j];
+  return t1_rotate_inv(ck, leg, f);
+}
+
+// Leg::solveIK (position rows only: the angular rows of J are zero when solve_rotation is false, so
+// J^T (J J^T + l^2 I6)^-1 [dp;0] = Jp^T (Jp Jp^T + l^2 I3)^-1 dp and J^+ J = Jp^T (..)^-1 Jp — model.cpp:726-795).
+template <class K, int D>
+SHC_HD void solve_ik(const RealConsts<K>& ck, int leg, const Chain<K, D>& ch, V3<K> dp, const K* q,
+                                         const K* qd, K* dq) {
+  V3<K> J[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) J[j] = cross(ch.z[j], ch.tip - ch.p[j]);
+  K a00 = ck.lambda2, a01 = K(0), a02 = K(0), a11 = ck.lambda2, a12 = K(0), a22 = ck.lambda2;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    a00 += J[j].x * J[j].x; a01 += J[j].x * J[j].y; a02 += J[j].x * J[j].z;
+    a11 += J[j].y * J[j].y; a12 += J[j].y * J[j].z; a22 += J[j].z * J[j].z;
+  }
+  // joint limit cost gradient (model.cpp:759-790)
+  K g[D];
+  K pos_cost = K(0), vel_cost = K(0);
+  K gp[D], gv[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    K e = q[j] - ck.jcentre[leg][j];
+    K cp = ck.jcost_pos[leg][j] * e;
+    pos_cost += cp * cp;
+    gp[j] = ck.jgrad_pos[leg][j] * e;
+    K cv = ck.jcost_vel[leg][j] * qd[j];
+    vel_cost += cv * cv;
+    gv[j] = ck.jgrad_vel[leg][j] * qd[j];
+  }
+  K sp = pos_cost == K(0) ? K(0) : K(1) / sqrt_(pos_cost);
+  K sv = vel_cost == K(0) ? K(0) : K(1) / sqrt_(vel_cost);
+  V3<K> Jg{K(0), K(0), K(0)};
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    g[j] = K(0.25) * (gp[j] * sp) + K(0.75) * (gv[j] * sv);
+    Jg = Jg + J[j] * g[j];
+  }
+  // dq = Jp^T A^-1 (dp - Jp g) + g
+  V3<K> x = spd3_solve(a00, a01, a02, a11, a12, a22, dp - Jg);
+#pragma unroll
+  for (int j = 0; j < D; ++j) dq[j] = dot(J[j], x) + g[j];
+}
+
+// Leg::applyIK without the trailing FK (model.cpp:861-904): position delta in the leg frame from the chain at the
+// current joint angles, one DLS step, Leg::updateJointPositions (:799).  q/qd are updated in place; returns the
+// SHC_FLAG_*_CLAMP bits.  `des_leg_out` receives the desired tip position in the leg frame.
+template <class K, int D>
+SHC_HD int apply_ik_step(const RealConsts<K>& ck, int leg, const Chain<K, D>& ch, K* q, K* qd, V3<K> desired_robot,
+                         bool clamp_positions, bool clamp_velocities, V3<K>* des_leg_out) {
+  V3<K> des_leg = t1_rotate_inv(ck, leg, desired_robot - V3<K>{ck.t1p[leg][0], ck.t1p[leg][1], ck.t1p[leg][2]});
+  *des_leg_out = des_leg;
+  K dq[D];
+  solve_ik<K, D>(ck, leg, ch, des_leg - ch.tip, q, qd, dq);
+  int status = 0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    K v = dq[j] / ck.dt;
+    if (clamp_velocities && abs_(v) > ck.vmax[leg][j]) {
+      v = clamp_(v, -ck.vmax[leg][j], ck.vmax[leg][j]);
+      status |= 4;
+    }
+    K nq = q[j] + v * ck.dt;
+    if (clamp_positions) {
+      if (nq < ck.jmin[leg][j]) { nq = ck.jmin[leg][j]; status |= 2; }
+      else if (nq > ck.jmax[leg][j]) { nq = ck.jmax[leg][j]; status |= 2; }
+    }
+    q[j] = nq;
+    qd[j] = v;
+  }
+  return status;
+}
+
+// Return value of Leg::applyIK (model.cpp:845-856, 916-929): the smallest joint-limit proximity, or 0 when the tip
+// deviates from the desired position by more than IK_TOLERANCE on a base_link axis.  `ch2` is the chain at the NEW q.
+template <class K, int D>
+SHC_HD K ik_result_value(const RealConsts<K>& ck, int leg, const Chain<K, D>& ch2, const K* q, V3<K> des_leg) {
+  K prox = K(1);
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    K min_diff = abs_(ck.jmin[leg][j] - q[j]);
+    K max_diff = abs_(ck.jmax[leg][j] - q[j]);
+    K half = (ck.jmax[leg][j] - ck.jmin[leg][j]) / K(2);
+    K lp = half != K(0) ? min_(min_diff, max_diff) / half : K(1);
+    prox = min_(lp, prox);
+  }
+  V3<K> er = t1_rotate(ck, leg, ch2.tip - des_leg);
+  if (abs_(er.x) > K(0.005) || abs_(er.y) > K(0.005) || abs_(er.z) > K(0.005)) prox = K(0);
+  return prox;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+template <class P, int D> struct Cycle {
+  using S = typename P::S;
+  using T = typename P::T;
+  using K = typename P::K;
+  using LS = LegS<D>;
+
+  static __device__ __forceinline__ V3<K> ld3K(const S* sp, size_t np, int plane, int r) {
+    return {K(sp[(size_t)plane * np + r]), K(sp[(size_t)(plane + 1) * np + r]), K(sp[(size_t)(plane + 2) * np + r])};
+  }
+  static __device__ __forceinline__ V3<T> ld3T(const S* sp, size_t np, int plane, int r) {
+    return {T(sp[(size_t)plane * np + r]), T(sp[(size_t)(plane + 1) * np + r]), T(sp[(size_t)(plane + 2) * np + r])};
+  }
+  template <class R> static __device__ __forceinline__ void st3(S* sp, size_t np, int plane, int r, V3<R> v) {
+    sp[(size_t)plane * np + r] = S(v.x);
+    sp[(size_t)(plane + 1) * np + r] = S(v.y);
+    sp[(size_t)(plane + 2) * np + r] = S(v.z);
+  }
+  static __device__ __forceinline__ PoseT<K> ldPose(const S* sp, size_t np, int plane, int r) {
+    PoseT<K> p;
+    p.p = ld3K(sp, np, plane, r);
+    p.q = {K(sp[(size_t)(plane + 3) * np + r]), K(sp[(size_t)(plane + 4) * np + r]), K(sp[(size_t)(plane + 5) * np + r]),
+           K(sp[(size_t)(plane + 6) * np + r])};
+    return p;
+  }
+  static __device__ __forceinline__ void stPose(S* sp, size_t np, int plane, int r, PoseT<K> p) {
+    st3(sp, np, plane, r, p.p);
+    sp[(size_t)(plane + 3) * np + r] = S(p.q.w);
+    sp[(size_t)(plane + 4) * np + r] = S(p.q.x);
+    sp[(size_t)(plane + 5) * np + r] = S(p.q.y);
+    sp[(size_t)(plane + 6) * np + r] = S(p.q.z);
+  }
+
+  // PoseController::updateManualPose (pose_controller.cpp:863-1003); default_pose_ is the identity (no manually
+  // manipulated legs in the batched engine, so calculateDefaultPose never moves it).
+  static __device__ __forceinline__ PoseT<K> manual_pose_update(const RealConsts<K>& ck, PoseT<K> man, const float* in6,
+                                                                int reset_mode) {
+    if (reset_mode == 5) return pose_identity<K>();  // IMMEDIATE_ALL_RESET
+    V3<K> cur_rot = quat_to_euler(man.q, true);
+    K tin[3] = {K(0), K(0), K(0)}, rin[3] = {K(0), K(0), K(0)};
+    if (in6) {
+      tin[0] = K(in6[0]); tin[1] = K(in6[1]); tin[2] = K(in6[2]);
+      rin[0] = K(in6[3]); rin[1] = K(in6[4]); rin[2] = K(in6[5]);
+    }
+    bool rt[3] = {false, false, false}, rr[3] = {false, false, false};
+    if (reset_mode == 1) { rt[2] = true; rr[2] = true; }
+    else if (reset_mode == 2) { rt[0] = rt[1] = true; }
+    else if (reset_mode == 3) { rr[0] = rr[1] = true; }
+    else if (reset_mode == 4) { rt[0] = rt[1] = rt[2] = true; rr[0] = rr[1] = rr[2] = true; }
+    K cp[3] = {man.p.x, man.p.y, man.p.z};
+    K cr[3] = {cur_rot.x, cur_rot.y, cur_rot.z};
+    K dpv[3], drv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (rt[i]) {
+        if (cp[i] < K(0)) tin[i] = K(1);
+        else if (cp[i] > K(0)) tin[i] = K(-1);
+      }
+      if (rr[i]) {
+        if (cr[i] < K(0)) rin[i] = K(1);
+        else if (cr[i] > K(0)) rin[i] = K(-1);
+      }
+      K tv = tin[i] * ck.max_translation_velocity;
+      K rv = rin[i] * ck.max_rotation_velocity;
+      K dpos = cp[i] + tv * ck.dt;
+      K drot = cr[i] + rv * ck.dt;
+      K tlim = sign_(tv) * ck.max_translation[i];
+      if (rt[i] && K(0) < ck.max_translation[i] && K(0) > -ck.max_translation[i]) tlim = K(0);
+      bool ptv = sign_(tv) > K(0);
+      if ((ptv && dpos > tlim) || (!ptv && dpos < tlim)) tv = (tlim - cp[i]) / ck.dt;
+      K rlim = sign_(rv) * ck.max_rotation[i];
+      if (rr[i] && K(0) < ck.max_rotation[i] && K(0) > -ck.max_rotation[i]) rlim = K(0);
+      bool prv = sign_(rv) > K(0);
+      if ((prv && drot > rlim) || (!prv && drot < rlim)) rv = (rlim - cr[i]) / ck.dt;
+      dpv[i] = cp[i] + tv * ck.dt;
+      drv[i] = cr[i] + rv * ck.dt;
+    }
+    PoseT<K> out;
+    out.p = {dpv[0], dpv[1], dpv[2]};
+    out.q = correct_rotation(euler_to_quat(V3<K>{drv[0], drv[1], drv[2]}, true), qidentity<K>());
+    return out;
+  }
+
+  // Model::estimateGravity (model.cpp:156) from the raw IMU orientation (all-zero quaternion when no IMU data: the
+  // rotation matrix of the zero quaternion is the identity).
+  static __device__ __forceinline__ V3<K> estimate_gravity(Q4<K> imu_raw) {
+    V3<K> e = quat_to_euler(imu_raw, false);
+    K s, c;
+    sincos_(-e.y, &s, &c);  // rotate (0,0,g) about Y by -pitch
+    const K g = K(-9.81);
+    V3<K> v{s * g, K(0), c * g};
+    sincos_(-e.x, &s, &c);  // then about X by -roll
+    return {v.x, c * v.y - s * v.z, s * v.y + c * v.z};
+  }
+
+  static __device__ void run(const Consts& c, Planes<S> pl, int r, const StepIO& io) {
+    const IntConsts& ci = c.i;
+    const RealConsts<T>& ct = ConstSel<T>::get(c);
+    const RealConsts<K>& ck = ConstSel<K>::get(c);
+    const RealConsts<double>& cd = c.d;
+    const size_t np = (size_t)ci.n_pad;
+    const int L = ci.L;
+    S* sp = pl.s;
+    double* dp = pl.d;
+    int* ip = pl.i;
+
+    // ---- inputs: bodyVelocityInputCallback (state_controller.cpp:1127-1136) --------------------------------------
+    double vin_x = (double)io.cmd[3 * (size_t)r + 0] * cd.body_velocity_scaler;
+    double vin_y = (double)io.cmd[3 * (size_t)r + 1] * cd.body_velocity_scaler;
+    double win = (double)io.cmd[3 * (size_t)r + 2] * cd.body_velocity_scaler;
+    double in_norm = sqrt(vin_x * vin_x + vin_y * vin_y);
+    if (ci.velocity_input_mode == SHC_VELOCITY_THROTTLE && in_norm > 1.0) {
+      double s = fmin(1.0, in_norm);
+      vin_x = s * (vin_x / in_norm);
+      vin_y = s * (vin_y / in_norm);
+      in_norm = sqrt(vin_x * vin_x + vin_y * vin_y);
+    }
+
+    Q4<K> imu_raw{K(0), K(0), K(0), K(0)};  // Model::imu_data_.orientation (UNDEFINED until set)
+    V3<K> gyro{K(0), K(0), K(0)};
+    if (io.imu) {
+      const float* m = io.imu + 10 * (size_t)r;
+      imu_raw = qnormalized(Q4<K>{K(m[0]), K(m[1]), K(m[2]), K(m[3])});  // Model::setImuData (model.h:146)
+      gyro = {K(m[4]), K(m[5]), K(m[6])};
+    }
+    // Model::getImuData (model.h:132): undefined orientation reads as identity
+    Q4<K> imu_q = (imu_raw.w == K(0) && imu_raw.x == K(0) && imu_raw.y == K(0) && imu_raw.z == K(0)) ? qidentity<K>() : imu_raw;
+
+    int rbits = ip[(size_t)RI_BITS * np + r];
+    int walk_state = rbits & 3;
+    int legs_at_correct = (rbits >> 2) & 15;
+    int legs_completed = (rbits >> 6) & 15;
+    int rtd = (rbits >> 10) & 1;
+    int auto_state = (rbits >> 13) & 3;
+    int status = 0;
+
+    // =================================================================================================================
+    // 1. PoseController::updateCurrentPose
+    // =================================================================================================================
+    // updateWalkPlanePose (pose_controller.cpp:1092): the last leg (id order) whose scaled swing progress is in [0,1]
+    double c_in = 0.0;
+    int ref_leg = -1;
+    for (int l = 0; l < L; ++l) {
+      int prog = ip[(size_t)(ci.offI_leg + l * ci.strideI_leg + LI_PROG) * np + r];
+      int swing_num = (int)(short)(prog & 0xffff);
+      double swing_progress = swing_num < 0 ? -1.0 : (double)swing_num / (double)ci.swing_period;
+      swing_progress *= cd.swing_progress_scaler;
+      if (swing_progress >= 0.0 && swing_progress <= 1.0) {
+        c_in = smooth_step(swing_progress);
+        ref_leg = l;
+      }
+    }
+    K wp_z = K(0);
+    V3<K> wpn_ref{K(0), K(0), K(1)};
+    if (ref_leg >= 0) {
+      int base = ci.offS_leg + ref_leg * ci.strideS_leg;
+      wp_z = K(sp[(size_t)(base + LS::WP + 2) * np + r]);
+      wpn_ref = ld3K(sp, np, base + LS::WPN, r);
+    }
+    PoseT<K> new_wpp;
+    new_wpp.q = correct_rotation(from_two_vectors(V3<K>{K(0), K(0), K(1)}, wpn_ref), qidentity<K>());
+    new_wpp.p = qrot(new_wpp.q, V3<K>{K(0), K(0), ck.body_clearance});
+    new_wpp.p.z += wp_z;
+    PoseT<K> owpp = ldPose(sp, np, RS_OWPP, r);
+    PoseT<K> wpp = pose_interpolate(owpp, K(c_in), new_wpp);
+    stPose(sp, np, RS_WPP, r, wpp);
+    if (c_in == 1.0) stPose(sp, np, RS_OWPP, r, wpp);
+
+    PoseT<K> cur_pose = pose_add(pose_identity<K>(), wpp);
+    PoseT<K> man = pose_identity<K>();
+    if (ci.manual_posing) {
+      man = ldPose(sp, np, RS_MAN, r);
+      man = manual_pose_update(ck, man, io.manual ? io.manual + 6 * (size_t)r : nullptr, io.pose_reset_mode);
+      stPose(sp, np, RS_MAN, r, man);
+      cur_pose = pose_add(cur_pose, man);
+    }
+    PoseT<K> auto_pose = pose_identity<K>();
+    if (ci.auto_posing) auto_pose = ldPose(sp, np, ci.offS_auto + AUTO_POSE, r);
+    if (ci.inclination_posing) {  // updateInclinationPose (:1240)
+      Q4<K> comb = qnormalized(qmul(man.q, auto_pose.q));
+      Q4<K> removed = qnormalized(qmul(imu_q, qinverse(comb)));
+      V3<K> e = quat_to_euler(removed, false);
+      K lon = -ck.body_clearance * tan_(e.y);
+      K lat = ck.body_clearance * tan_(e.x);
+      lon = clamp_(lon, -ck.max_translation[0], ck.max_translation[0]);
+      lat = clamp_(lat, -ck.max_translation[1], ck.max_translation[1]);
+      sp[(size_t)(ci.offS_imu + IMU_INCL) * np + r] = S(lon);
+      sp[(size_t)(ci.offS_imu + IMU_INCL + 1) * np + r] = S(lat);
+      PoseT<K> incl = pose_identity<K>();
+      incl.p = {lon, lat, K(0)};
+      cur_pose = pose_add(cur_pose, incl);
+    }
+    int master_phase = 0;
+    bool run_auto = false;
+    if (ci.imu_posing) {  // updateIMUPose (:1191); robot_state is RUNNING in every engine cycle
+      Q4<K> current_rotation = correct_rotation(imu_q, qidentity<K>());
+      Q4<K> target_rotation = correct_rotation(man.q, qidentity<K>());
+      Q4<K> rot_err = qnormalized(qmul(current_rotation, qinverse(target_rotation)));
+      V3<K> pe = quat_to_euler(rot_err, false);
+      pe.z = K(0);
+      const int b = ci.offS_imu;
+      Q4<K> imu_pose_q{K(sp[(size_t)(b + IMU_Q) * np + r]), K(sp[(size_t)(b + IMU_Q + 1) * np + r]),
+                       K(sp[(size_t)(b + IMU_Q + 2) * np + r]), K(sp[(size_t)(b + IMU_Q + 3) * np + r])};
+      // IMU_POSING_DEADBAND is 0.0: "norm < 0" never holds, the PID always runs (pose_controller.h:25)
+      V3<K> abs_err = ld3K(sp, np, b + IMU_ABS, r) + pe * ck.dt;
+      V3<K> vel_err = (-gyro) * K(0.15) + ld3K(sp, np, b + IMU_VEL, r) * (K(1) - K(0.15));
+      st3(sp, np, b + IMU_ABS, r, abs_err);
+      st3(sp, np, b + IMU_VEL, r, vel_err);
+      V3<K> corr = -(vel_err * ck.pid_d + pe * ck.pid_p + abs_err * ck.pid_i);
+      corr.x = clamp_(corr.x, -ck.max_rotation[0], ck.max_rotation[0]);
+      corr.y = clamp_(corr.y, -ck.max_rotation[1], ck.max_rotation[1]);
+      corr.z = quat_to_euler(target_rotation, false).z;
+      if (norm(corr) > K(100)) status |= 8;
+      imu_pose_q = correct_rotation(euler_to_quat(corr, false), target_rotation);
+      sp[(size_t)(b + IMU_Q) * np + r] = S(imu_pose_q.w);
+      sp[(size_t)(b + IMU_Q + 1) * np + r] = S(imu_pose_q.x);
+      sp[(size_t)(b + IMU_Q + 2) * np + r] = S(imu_pose_q.y);
+      sp[(size_t)(b + IMU_Q + 3) * np + r] = S(imu_pose_q.z);
+      PoseT<K> imu_pose = pose_identity<K>();
+      imu_pose.q = imu_pose_q;
+      cur_pose = pose_add(cur_pose, imu_pose);
+    } else if (ci.auto_posing) {  // updateAutoPose (:1134)
+      run_auto = true;
+      const int rb = ci.offI_leg + ci.auto_ref_leg * ci.strideI_leg;
+      int ref_bits = ip[(size_t)(rb + LI_BITS) * np + r];
+      // zero_body_velocity of the reference leg: stride_vector_.norm() == 0
+      V3<T> ref_stride = ld3T(sp, np, ci.offS_leg + ci.auto_ref_leg * ci.strideS_leg + LS::STRIDE, r);
+      bool zero_body_velocity = (ref_stride.x * ref_stride.x + ref_stride.y * ref_stride.y + ref_stride.z * ref_stride.z) == T(0);
+      if (walk_state == WALK_STARTING || walk_state == WALK_MOVING) auto_state = POSE_POSING;
+      else if ((zero_body_velocity && walk_state == WALK_STOPPING) || walk_state == WALK_STOPPED) auto_state = POSE_STOP_POSING;
+      int pose_phase = ip[(size_t)(ci.offI_auto + AI_PHASE) * np + r];
+      if (ci.pose_sync) {
+        master_phase = ref_bits & 0xffff;
+      } else {
+        master_phase = pose_phase;
+        pose_phase = (pose_phase + 1) % ci.pose_phase_length;
+        ip[(size_t)(ci.offI_auto + AI_PHASE) * np + r] = pose_phase;
+      }
+      int pflags = ip[(size_t)(ci.offI_auto + AI_FLAGS) * np + r];
+      auto_pose = pose_identity<K>();
+      int complete = 0;
+      V3<K> grav_dir{K(0), K(0), K(-1)};
+      bool grav_done = false;
+      for (int a = 0; a < ci.n_posers; ++a) {  // AutoPoser::updatePose (:1338)
+        int f = (pflags >> (4 * a)) & 15;
+        bool start_check = f & 1, end1 = f & 2, end2 = f & 4, allow = f & 8;
+        int phase = master_phase;
+        int start_phase = ci.ap_start[a] * ci.pose_normaliser;
+        int end_phase = ci.ap_end[a] * ci.pose_normaliser;
+        if (start_phase > end_phase) {
+          end_phase += ci.pose_phase_length;
+          if (phase < start_phase) phase += ci.pose_phase_length;
+        }
+        start_check = !ci.pose_sync || (!start_check && auto_state == POSE_POSING && phase == start_phase);
+        end1 = end1 || (auto_state == POSE_STOP_POSING && phase == start_phase);
+        end2 = end2 || (auto_state == POSE_STOP_POSING && phase == end_phase && end1);
+        if (!allow && start_check) {
+          allow = true;
+          end1 = end2 = false;
+        } else if (allow && ci.pose_sync && end1 && end2) {
+          allow = false;
+          start_check = false;
+        }
+        PoseT<K> upd = pose_identity<K>();
+        if (phase >= start_phase && phase < end_phase && allow) {
+          int iteration = phase - start_phase + 1;
+          int num_iterations = end_phase - start_phase;
+          bool first_half = iteration <= num_iterations / 2;
+          V3<K> rot_amp{ck.ap_rot[a][0], ck.ap_rot[a][1], ck.ap_rot[a][2]};
+          V3<K> pos_amp{ck.ap_pos[a][0], ck.ap_pos[a][1], ck.ap_pos[a][2]};
+          if (ck.ap_gravity[a] != K(0)) {
+            if (!grav_done) { grav_dir = normalized(estimate_gravity(imu_raw)); grav_done = true; }
+            pos_amp = grav_dir * ck.ap_gravity[a];
+          }
+          K delta_t = K(1) / (K(num_iterations) / K(2));
+          int offset = (int)(first_half ? 0.0 : num_iterations / 2.0);
+          K t = K(iteration - offset) * delta_t;
+          K s = K(1) - t;
+          // quartic Bezier with nodes {0,0,0,A,A} (first half) or {A,A,0,0,0} (second half)
+          K w = first_half ? (K(4) * t * t * t * s + t * t * t * t) : (s * s * s * s + K(4) * t * s * s * s);
+          upd.p = pos_amp * w;
+          upd.q = euler_to_quat(rot_amp * w, false);
+        }
+        complete += allow ? 0 : 1;
+        auto_pose = pose_add(auto_pose, upd);
+        f = (start_check ? 1 : 0) | (end1 ? 2 : 0) | (end2 ? 4 : 0) | (allow ? 8 : 0);
+        pflags = (pflags & ~(15 << (4 * a))) | (f << (4 * a));
+      }
+      if (complete == ci.n_posers) auto_state = POSE_COMPLETE;
+      ip[(size_t)(ci.offI_auto + AI_FLAGS) * np + r] = pflags;
+      stPose(sp, np, ci.offS_auto + AUTO_POSE, r, auto_pose);
+      cur_pose = pose_add(cur_pose, auto_pose);
+    }
+    const int pose_state = auto_state;  // walker_->setPoseState(poser_->getAutoPoseState())
+
+    // =================================================================================================================
+    // 2. WalkController::updateWalk — robot-level part (walk_controller.cpp:440-564)
+    // =================================================================================================================
+    double lim[4] = {2147483647.0, 2147483647.0, 2147483647.0, 2147483647.0};
+    for (int l = 0; l < L; ++l) {  // getLimit (:414): the four calls share the bearing of each leg
+      const int db = ci.offD_leg + l * ci.strideD_leg + LD_TIP;
+      double tx = dp[(size_t)db * np + r], ty = dp[(size_t)(db + 1) * np + r];
+      double sx = vin_x + win * (-ty), sy = vin_y + win * tx;
+      int bearing = imod(round_to_int((atan2(sy, sx) / (2.0 * kPi)) * 360.0), 360);
+      int bucket = bearing / 45;  // int/int interpolation input floors to the 45-degree bucket (trap 1)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) lim[k] = fmin(lim[k], cd.limits[k][bucket]);
+    }
+    T max_lin_speed = T(lim[0]), max_ang_speed = T(lim[1]), max_lin_acc = T(lim[2]), max_ang_acc = T(lim[3]);
+
+    T nvx, nvy, nw;
+    if (walk_state != WALK_STOPPING) {
+      if (ci.velocity_input_mode == SHC_VELOCITY_THROTTLE) {
+        T cx = T(vin_x), cy = T(vin_y);
+        if (in_norm > 1.0) {
+          cx = T(vin_x * (1.0 / in_norm));
+          cy = T(vin_y * (1.0 / in_norm));
+        }
+        T k = T(1) - T(fabs(win));
+        nvx = cx * max_lin_speed * k;
+        nvy = cy * max_lin_speed * k;
+        nw = T(fmax(-1.0, fmin(win, 1.0))) * max_ang_speed;
+      } else {
+        T cx = T(vin_x), cy = T(vin_y);
+        if (in_norm > (double)max_lin_speed) {
+          cx = T(vin_x * ((double)max_lin_speed / in_norm));
+          cy = T(vin_y * ((double)max_lin_speed / in_norm));
+        }
+        nw = clamp_(T(win), -max_ang_speed, max_ang_speed);
+        T k = max_ang_speed != T(0) ? (T(1) - abs_(nw / max_ang_speed)) : T(0);
+        nvx = cx * k;
+        nvy = cy * k;
+      }
+    } else {
+      nvx = nvy = nw = T(0);
+    }
+    const bool has_cmd = (in_norm != 0.0) || (win != 0.0);
+
+    T dvx = T(sp[(size_t)(RS_VEL)*np + r]), dvy = T(sp[(size_t)(RS_VEL + 1) * np + r]), dw = T(sp[(size_t)RS_ANGVEL * np + r]);
+    {
+      T ax = nvx - dvx, ay = nvy - dvy;
+      T an = sqrt_(ax * ax + ay * ay);
+      if (an < max_lin_acc * ct.dt) {
+        dvx += ax;
+        dvy += ay;
+      } else {
+        T n2 = ax * ax + ay * ay;
+        T ux = ax, uy = ay;
+        if (n2 > T(0)) {
+          T inv = T(1) / sqrt_(n2);
+          ux *= inv;
+          uy *= inv;
+        }
+        dvx += ux * max_lin_acc * ct.dt;
+        dvy += uy * max_lin_acc * ct.dt;
+      }
+      T aa = nw - dw;
+      if (abs_(aa) < max_ang_acc * ct.dt) dw += aa;
+      else dw += sign_(aa) * max_ang_acc * ct.dt;
+    }
+    sp[(size_t)(RS_VEL)*np + r] = S(dvx);
+    sp[(size_t)(RS_VEL + 1) * np + r] = S(dvy);
+    sp[(size_t)RS_ANGVEL * np + r] = S(dw);
+
+    bool starting_now = false;  // STOPPED -> STARTING returns before any tip update (trap 7)
+    if (walk_state == WALK_STOPPED && has_cmd) {
+      walk_state = WALK_STARTING;
+      starting_now = true;
+    } else if (walk_state == WALK_STARTING && legs_at_correct == L && legs_completed == L) {
+      legs_at_correct = 0;
+      legs_completed = 0;
+      walk_state = WALK_MOVING;
+    } else if (walk_state == WALK_MOVING && !has_cmd) {
+      walk_state = WALK_STOPPING;
+    } else if (walk_state == WALK_STOPPING && legs_at_correct == L && pose_state == POSE_COMPLETE) {
+      legs_at_correct = 0;
+      walk_state = WALK_STOPPED;
+    }
+
+    const V3<T> walker_wp = ld3T(sp, np, RS_WPL, r);
+    const V3<T> walker_wpn = ld3T(sp, np, RS_WPN, r);
+
+    // walk-plane least squares accumulators (updateWalkPlane :748): A = [x y 1], b = z over the default tips
+    double sxx = 0, sxy = 0, sx1 = 0, syy = 0, sy1 = 0, sxz = 0, syz = 0, sz1 = 0;
+
+    // =================================================================================================================
+    // 3. per leg: walk state machine + LegStepper + updateStance + Leg::applyIK
+    // =================================================================================================================
+#pragma unroll 1
+    for (int l = 0; l < L; ++l) {
+      const int sb = ci.offS_leg + l * ci.strideS_leg;
+      const int db = ci.offD_leg + l * ci.strideD_leg;
+      const int ib = ci.offI_leg + l * ci.strideI_leg;
+      int bits = ip[(size_t)(ib + LI_BITS) * np + r];
+      int prog = ip[(size_t)(ib + LI_PROG) * np + r];
+      int phase = bits & 0xffff;
+      int step_state = (bits >> 16) & 3;
+      bool at_correct = (bits >> 18) & 1;
+      bool completed = (bits >> 19) & 1;
+      bool negate = (bits >> 20) & 1;
+      int swing_num = (int)(short)(prog & 0xffff);
+      int stance_num = (int)(short)((prog >> 16) & 0xffff);
+
+      double tipx = dp[(size_t)(db + LD_TIP) * np + r];
+      double tipy = dp[(size_t)(db + LD_TIP + 1) * np + r];
+      double tipz = dp[(size_t)(db + LD_TIP + 2) * np + r];
+
+      // LegPoser::updateAutoPose (pose_controller.cpp:1716) — uses the step state of the previous cycle
+      PoseT<K> leg_auto = auto_pose;
+      if (run_auto) {
+        int start_phase = ci.neg_start[l] * ci.pose_normaliser;
+        int end_phase = ci.neg_end[l] * ci.pose_normaliser;
+        int negation_phase = master_phase;
+        if (start_phase == 0) start_phase = ci.pose_phase_length;
+        if (end_phase == 0) end_phase = ci.pose_phase_length;
+        if (start_phase > end_phase) {
+          end_phase += ci.pose_phase_length;
+          if (negation_phase < start_phase) negation_phase += ci.pose_phase_length;
+        }
+        if (step_state != STEP_FORCE_STANCE && step_state != STEP_FORCE_STOP && negation_phase == start_phase) negate = true;
+        if (negation_phase < start_phase || negation_phase > end_phase) negate = false;
+        if (negate) {
+          int iteration = negation_phase - start_phase + 1;
+          int num_iterations = end_phase - start_phase;
+          bool first_half = iteration <= num_iterations / 2;
+          K ctrl = K(1);
+          if (ck.neg_ratio[l] > K(0)) {
+            if (first_half) ctrl = min_(K(1), K(iteration) / (K(num_iterations) * ck.neg_ratio[l]));
+            else ctrl = min_(K(1), K(num_iterations - iteration) / (K(num_iterations) * ck.neg_ratio[l]));
+          }
+          ctrl = smooth_step(ctrl);
+          PoseT<K> negation = pose_interpolate(pose_identity<K>(), ctrl, auto_pose);
+          leg_auto = pose_remove(auto_pose, negation);
+        }
+      } else if (ci.auto_posing) {
+        leg_auto = pose_identity<K>();  // LegPoser::auto_pose_ is only refreshed by updateAutoPose; IMU posing keeps identity
+      }
+
+      V3<T> def = ld3T(sp, np, sb + LS::DEF, r);
+
+      if (starting_now) {
+        // walk_controller.cpp:535-545
+        at_correct = false;
+        completed = false;
+        step_state = STEP_STANCE;
+        phase = ci.phase_offset[l];
+        if (phase >= ci.swing_start && phase < ci.swing_end) step_state = STEP_SWING;
+        else if (phase < ci.stance_end || phase >= ci.stance_start) step_state = STEP_STANCE;
+      } else {
+        V3<T> stride = ld3T(sp, np, sb + LS::STRIDE, r);
+        V3<T> tgt = ld3T(sp, np, sb + LS::TGT, r);
+        // ---- walk state machine for this leg (walk_controller.cpp:573-632) ----
+        if (walk_state == WALK_STARTING) {
+          if (legs_at_correct == L) {
+            if (phase == ci.swing_end && !completed) {
+              completed = true;
+              legs_completed++;
+            }
+          }
+          if (!at_correct) {
+            if (ci.phase_offset[l] > ci.swing_start && ci.phase_offset[l] < ci.swing_end && phase != ci.swing_end) {
+              step_state = STEP_FORCE_STANCE;
+            } else {
+              legs_at_correct++;
+              at_correct = true;
+            }
+          }
+        } else if (walk_state == WALK_MOVING) {
+          at_correct = false;
+        } else if (walk_state == WALK_STOPPING) {
+          bool zero_body_velocity = (stride.x * stride.x + stride.y * stride.y + stride.z * stride.z) == T(0);
+          if (zero_body_velocity && !at_correct && phase == ci.swing_end) {
+            V3<double> wpn_l = cvt<double>(ld3T(sp, np, sb + LS::WPN, r));
+            V3<double> err{tipx - (double)tgt.x, tipy - (double)tgt.y, tipz - (double)tgt.z};
+            err = rejection(err, wpn_l);
+            bool at_target = norm(err) < 0.01;  // TIP_TOLERANCE (pose_controller.h:19)
+            if (at_target || rtd) {
+              rtd = 0;
+              // LegStepper::updateDefaultTipPosition (:984), no external default
+              V3<K> idt{ck.identity_x[l], ck.identity_y[l] + ck.span_dy[l], K(0)};
+              idt = pose_transform(wpp, idt);  // Model::default_pose_ = walk_plane_pose_ (pose_controller.cpp:819)
+              V3<K> sto = ld3K(sp, np, sb + LS::STO_P, r);
+              V3<K> proj = projection(sto - idt, cvt<K>(wpn_l));
+              def = cvt<T>(idt + proj);
+              st3(sp, np, sb + LS::DEF, r, def);
+              step_state = STEP_FORCE_STOP;
+              at_correct = true;
+              legs_at_correct++;
+            } else {
+              rtd = 1;
+            }
+          }
+        } else {  // STOPPED
+          step_state = STEP_FORCE_STOP;
+          phase = 0;
+        }
+
+        // ---- LegStepper::updateTipPosition (walk_controller.cpp:1018) ----
+        const bool standard = (step_state == STEP_SWING || completed);
+        const T stance_dt = standard ? ct.stance_dt_std : ct.stance_dt_mod[l];
+        tgt = def + stride * T(0.5);  // uses the previous cycle's stride (trap 5)
+        st3(sp, np, sb + LS::TGT, r, tgt);
+        if (step_state != STEP_FORCE_STOP) {
+          // updateStride (:921)
+          stride = V3<T>{dvx - dw * T(tipy), dvy + dw * T(tipx), T(0)} * ct.stride_scale;
+          st3(sp, np, sb + LS::STRIDE, r, stride);
+          st3(sp, np, sb + LS::WP, r, walker_wp);
+          st3(sp, np, sb + LS::WPN, r, walker_wpn);
+          V3<T> delta;
+          if (step_state == STEP_SWING) {
+            int iteration = phase - ci.swing_start + 1;
+            bool first_half = iteration <= ci.swing_iterations / 2;
+            V3<T> swo_p, swo_v;
+            if (iteration == 1) {
+              swo_p = V3<T>{T(tipx), T(tipy), T(tipz)};
+              swo_v = ld3T(sp, np, sb + LS::TIPVEL, r);
+              st3(sp, np, sb + LS::SWO_P, r, swo_p);
+              st3(sp, np, sb + LS::SWO_V, r, swo_v);
+            } else {
+              swo_p = ld3T(sp, np, sb + LS::SWO_P, r);
+              swo_v = ld3T(sp, np, sb + LS::SWO_V, r);
+            }
+            // Control nodes relative to the swing origin (generatePrimary/SecondarySwingControlNodes :1238-1291);
+            // only node differences enter quarticBezierDot, so the origin cancels.
+            V3<T> clr = normalized(walker_wpn) * ct.swing_height;
+            V3<T> tr = tgt - swo_p;
+            V3<T> mid{tr.x * T(0.5) + clr.x, tr.y * T(0.5) + clr.y + ct.ysign[l] * ct.swing_width, max_(T(0), tr.z) + clr.z};
+            V3<T> sep1 = swo_v * (T(0.25) * (ct.dt / ct.swing_dt));
+            V3<T> n2 = sep1 * T(2);
+            V3<T> n3 = (mid + n2) * T(0.5);
+            n3.z = mid.z;
+            V3<T> n4 = mid;
+            V3<T> ftv = -stride * (stance_dt / ct.dt);
+            V3<T> sep2 = ftv * (T(0.25) * (ct.dt / ct.swing_dt));
+            V3<T> m0 = n4;
+            V3<T> m2 = tr - sep2 * T(2);
+            V3<T> m1;
+            if (ci.force_normal_touchdown) {  // forceNormalTouchdown (:1314)
+              V3<T> bo = tr - sep2 * T(4);
+              bo.z = max_(T(0), tr.z);
+              bo = bo + clr;
+              n4 = bo;
+              m0 = bo;
+              n3 = m0 - (m2 - bo) * T(0.5);
+              m1 = m0 + (m2 - bo) * T(0.5);
+            } else {
+              m1 = n4 - (n3 - n4);
+            }
+            if (first_half) {
+              T t = ct.swing_dt * T(iteration);
+              delta = quartic_bezier_dot(V3<T>{T(0), T(0), T(0)}, sep1, n2, n3, n4, t) * ct.swing_dt;
+            } else {
+              T t = ct.swing_dt * T(iteration - ci.swing_iterations / 2);
+              V3<T> m3 = tr - sep2;
+              delta = quartic_bezier_dot(m0, m1, m2, m3, tr, t) * ct.swing_dt;
+            }
+          } else {  // STANCE / FORCE_STANCE
+            int mod_start = standard ? ci.stance_start : ci.phase_offset[l];
+            int iteration = imod(phase + (ci.period - mod_start), ci.period) + 1;
+            if (iteration == 1) st3(sp, np, sb + LS::STO_P, r, V3<T>{T(tipx), T(tipy), T(tipz)});
+            T scaler = standard ? T(1) : ct.stride_scaler_mod[l];
+            V3<T> sep = -stride * scaler * T(0.25);
+            // stance nodes are origin + k*sep (generateStanceControlNodes :1295): all four node differences are sep
+            T t = T(iteration) * stance_dt;
+            T s = T(1) - t;
+            T w = T(4) * s * s * s + T(12) * s * s * t + T(12) * s * t * t + T(4) * t * t * t;
+            delta = sep * w * stance_dt;
+          }
+          tipx += (double)delta.x;
+          tipy += (double)delta.y;
+          tipz += (double)delta.z;
+          dp[(size_t)(db + LD_TIP) * np + r] = tipx;
+          dp[(size_t)(db + LD_TIP + 1) * np + r] = tipy;
+          dp[(size_t)(db + LD_TIP + 2) * np + r] = tipz;
+          st3(sp, np, sb + LS::TIPVEL, r, delta * ct.inv_dt);
+        }
+
+        // ---- LegStepper::iteratePhase (:871) + updateStepState (:901) ----
+        phase = (phase + 1) % ci.period;
+        if (step_state != STEP_FORCE_STOP) {
+          if (phase >= ci.swing_start && phase < ci.swing_end && step_state != STEP_FORCE_STANCE) step_state = STEP_SWING;
+          else if (phase < ci.stance_end || phase >= ci.stance_start) step_state = STEP_STANCE;
+        }
+        if (step_state == STEP_SWING) {
+          swing_num = min(max(phase - ci.swing_start + 1, 0), ci.swing_period);
+          stance_num = -1;
+        } else if (step_state == STEP_STANCE) {
+          stance_num = min(max(imod(phase + (ci.period - ci.stance_start), ci.period) + 1, 0), ci.stance_period);
+          swing_num = -1;
+        } else if (step_state == STEP_FORCE_STOP) {
+          stance_num = 0;
+          swing_num = -1;
+        }
+      }
+      bits = (phase & 0xffff) | (step_state << 16) | ((at_correct ? 1 : 0) << 18) | ((completed ? 1 : 0) << 19) |
+             ((negate ? 1 : 0) << 20);
+      prog = (swing_num & 0xffff) | ((stance_num & 0xffff) << 16);
+      ip[(size_t)(ib + LI_BITS) * np + r] = bits;
+      ip[(size_t)(ib + LI_PROG) * np + r] = prog;
+
+      {  // walk plane normal equations over the (possibly updated) default tips
+        double x = (double)def.x, y = (double)def.y, z = (double)def.z;
+        sxx += x * x; sxy += x * y; sx1 += x; syy += y * y; sy1 += y; sxz += x * z; syz += y * z; sz1 += z;
+      }
+
+      // ---- PoseController::updateStance (pose_controller.cpp:110) ----
+      PoseT<K> leg_pose = cur_pose;
+      if (ci.auto_posing) {
+        leg_pose = pose_remove(leg_pose, auto_pose);
+        leg_pose = pose_add(leg_pose, leg_auto);
+      }
+      V3<K> desired = pose_inverse_transform(leg_pose, V3<K>{K(tipx), K(tipy), K(tipz)});
+
+      // ---- joint state + chain at the previous joint angles ----
+      K q[D], qd[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        q[j] = K(sp[(size_t)(sb + LS::Q + j) * np + r]);
+        qd[j] = K(sp[(size_t)(sb + LS::QD + j) * np + r]);
+      }
+      Chain<K, D> ch;
+      leg_chain<K, D>(ck, l, q, ch);
+
+      // ---- AdmittanceController::updateAdmittance (admittance_controller.cpp:22) ----
+      if (ci.admittance_control) {
+        const int ab = sb + ci.offS_leg_adm;
+        K x0 = K(sp[(size_t)(ab + ADM_X) * np + r]), x1 = K(sp[(size_t)(ab + ADM_X + 1) * np + r]);
+        V3<K> force{K(0), K(0), K(0)};
+        if (ci.use_joint_effort) force = ld3K(sp, np, ab + ADM_FORCE, r);
+        else if (io.tip_force) {
+          const float* f = io.tip_force + 3 * ((size_t)r * L + l);
+          force = {K(f[0]), K(f[1]), K(f[2])};
+        }
+        force = force * ck.force_gain;
+        K fa[3] = {force.x, force.y, force.z};
+        K da[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {  // the same 2-state is integrated once per axis (trap 2)
+          K F = max_(fa[a], K(0));
+          K n0 = ck.adm_P[0] * x0 + ck.adm_P[1] * x1 + ck.adm_q[0] * F;
+          K n1 = ck.adm_P[2] * x0 + ck.adm_P[3] * x1 + ck.adm_q[1] * F;
+          x0 = n0;
+          x1 = n1;
+          K dl = clamp_(-x0, K(-0.2), K(0.2));
+          da[a] = abs_(dl) > K(0) ? (dl / abs_(dl)) * abs_(dl) : K(0);  // deadband 0 (trap 8)
+        }
+        sp[(size_t)(ab + ADM_X) * np + r] = S(x0);
+        sp[(size_t)(ab + ADM_X + 1) * np + r] = S(x1);
+        // Leg::setAdmittanceDelta (model.h:365): projection onto the tip frame x axis (base_link frame)
+        V3<K> dirx = t1_rotate(ck, l, ch.tipx);
+        V3<K> adelta = projection(V3<K>{da[0], da[1], da[2]}, dirx);
+        st3(sp, np, ab + ADM_DELTA, r, adelta);
+        desired = desired + adelta;  // Leg::setDesiredTipPose (model.cpp:653)
+      }
+
+      // ---- Leg::applyIK (model.cpp:861): one DLS step ----
+      V3<K> des_leg;
+      status |= apply_ik_step<K, D>(ck, l, ch, q, qd, desired, ci.clamp_joint_positions != 0, ci.clamp_joint_velocities != 0,
+                                    &des_leg);
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        sp[(size_t)(sb + LS::Q + j) * np + r] = S(q[j]);
+        sp[(size_t)(sb + LS::QD + j) * np + r] = S(qd[j]);
+        io.joints_out[((size_t)r * L + l) * D + j] = (float)(q[j] + ck.joffset[l][j]);  // state_controller.cpp:795
+      }
+      if (io.flags_out || ci.use_joint_effort) {
+        // applyFK at the new joint angles (model.cpp:904) for the IK tolerance check (:916-929)
+        Chain<K, D> ch2;
+        leg_chain<K, D>(ck, l, q, ch2);
+        V3<K> er = t1_rotate(ck, l, ch2.tip - des_leg);  // current - desired tip position in the base_link frame
+        if (abs_(er.x) > K(0.005) || abs_(er.y) > K(0.005) || abs_(er.z) > K(0.005)) status |= 1;
+        if (ci.use_joint_effort) {  // calculateTipForce (model.cpp:938)
+          K tau[D];
+#pragma unroll
+          for (int j = 0; j < D; ++j) tau[j] = io.efforts ? K(io.efforts[((size_t)r * L + l) * D + j]) : K(0);
+          V3<K> raw = raw_tip_force<K, D>(ck, l, ch2, tau);
+          const int ab = sb + ci.offS_leg_adm;
+          V3<K> f = ld3K(sp, np, ab + ADM_FORCE, r);
+          f = raw * (K(0.15) * ck.force_gain) + f * (K(1) - K(0.15));
+          st3(sp, np, ab + ADM_FORCE, r, f);
+        }
+      }
+    }
+
+    // =================================================================================================================
+    // 4. updateWalkPlane (:748) + odometry (:783)
+    // =================================================================================================================
+    if (!starting_now) {
+      if (L >= 3) {
+        // solve (A^T A) w = A^T b with A^T A = [[sxx sxy sx1],[sxy syy sy1],[sx1 sy1 L]]
+        double n = (double)L;
+        double c00 = syy * n - sy1 * sy1, c01 = sx1 * sy1 - sxy * n, c02 = sxy * sy1 - syy * sx1;
+        double c11 = sxx * n - sx1 * sx1, c12 = sxy * sx1 - sxx * sy1;
+        double c22 = sxx * syy - sxy * sxy;
+        double det = sxx * c00 + sxy * c01 + sx1 * c02;
+        double id = 1.0 / det;
+        double a = (c00 * sxz + c01 * syz + c02 * sz1) * id;
+        double b = (c01 * sxz + c11 * syz + c12 * sz1) * id;
+        double cc = (c02 * sxz + c12 * syz + c22 * sz1) * id;
+        V3<double> nrm = normalized(V3<double>{-a, -b, 1.0});
+        st3(sp, np, RS_WPL, r, V3<double>{a, b, cc});
+        st3(sp, np, RS_WPN, r, nrm);
+      } else {
+        st3(sp, np, RS_WPL, r, V3<double>{0.0, 0.0, 0.0});
+        st3(sp, np, RS_WPN, r, V3<double>{0.0, 0.0, 1.0});
+      }
+      // odometry_ideal_ = odometry_ideal_.addPose(calculateOdometry(dt))
+      Q4<T> oq{T(sp[(size_t)RS_ODOMQ * np + r]), T(sp[(size_t)(RS_ODOMQ + 1) * np + r]), T(sp[(size_t)(RS_ODOMQ + 2) * np + r]),
+               T(sp[(size_t)(RS_ODOMQ + 3) * np + r])};
+      V3<T> dpos = qrot(oq, V3<T>{dvx * ct.dt, dvy * ct.dt, T(0)});
+      dp[(size_t)(RD_ODOMP)*np + r] += (double)dpos.x;
+      dp[(size_t)(RD_ODOMP + 1) * np + r] += (double)dpos.y;
+      dp[(size_t)(RD_ODOMP + 2) * np + r] += (double)dpos.z;
+      Q4<T> nq = qmul(oq, q_axis_z(dw * ct.dt));
+      sp[(size_t)RS_ODOMQ * np + r] = S(nq.w);
+      sp[(size_t)(RS_ODOMQ + 1) * np + r] = S(nq.x);
+      sp[(size_t)(RS_ODOMQ + 2) * np + r] = S(nq.y);
+      sp[(size_t)(RS_ODOMQ + 3) * np + r] = S(nq.z);
+    }
+
+    rbits = (walk_state & 3) | ((legs_at_correct & 15) << 2) | ((legs_completed & 15) << 6) | ((rtd & 1) << 10) |
+            ((pose_state & 3) << 11) | ((auto_state & 3) << 13) | (status << 16);
+    ip[(size_t)RI_BITS * np + r] = rbits;
+    if (io.flags_out) io.flags_out[r] = status;
+  }
+};
+
+}  // namespace shc

@@ -1,0 +1,768 @@
+// shc_engine.cu — kernels + C-ABI of libshc_b200.so (include/shc_b200.h).
+//
+// Kernels (sm_100a):
+//   control_cycle_kernel<P, D>  one fused control cycle, one thread per robot (DESIGN.md "Kernels")
+//   apply_ik_kernel<D>          stand-alone batched Leg::applyIK (model.cpp:861) in double
+// There is no CPU fallback: every entry point that computes needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/shc_b200.h"
+#include "shc_host.cuh"
+
+namespace shc {
+
+using PrecMixed = Prec<float, float, double>;  // fp32 state + trajectory; fp64 pose/kinematics (see DESIGN.md "Precision")
+
+template <class P, int D>
+__global__ void __launch_bounds__(128) control_cycle_kernel(const __grid_constant__ Consts c, Planes<typename P::S> pl, StepIO io) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= c.i.n_robots) return;
+  Cycle<P, D>::run(c, pl, r, io);
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) apply_ik_kernel(const __grid_constant__ Consts c, int n, const int* __restrict__ leg_id,
+                                                       double* __restrict__ q_io, double* __restrict__ qd_io,
+                                                       const double* __restrict__ desired, int simulation,
+                                                       double* __restrict__ tip_out, double* __restrict__ result) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const RealConsts<double>& ck = c.d;
+  const int leg = leg_id[i];
+  double q[D], qd[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    q[j] = q_io[(size_t)i * D + j];
+    qd[j] = qd_io[(size_t)i * D + j];
+  }
+  Chain<double, D> ch;
+  leg_chain<double, D>(ck, leg, q, ch);
+  V3<double> des{desired[3 * (size_t)i], desired[3 * (size_t)i + 1], desired[3 * (size_t)i + 2]};
+  V3<double> des_leg;
+  apply_ik_step<double, D>(ck, leg, ch, q, qd, des, c.i.clamp_joint_positions != 0, c.i.clamp_joint_velocities != 0 && !simulation,
+                           &des_leg);
+  Chain<double, D> ch2;
+  leg_chain<double, D>(ck, leg, q, ch2);
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    q_io[(size_t)i * D + j] = q[j];
+    qd_io[(size_t)i * D + j] = qd[j];
+  }
+  if (tip_out) {
+    V3<double> t = t1_rotate(ck, leg, ch2.tip) + V3<double>{ck.t1p[leg][0], ck.t1p[leg][1], ck.t1p[leg][2]};
+    tip_out[3 * (size_t)i] = t.x;
+    tip_out[3 * (size_t)i + 1] = t.y;
+    tip_out[3 * (size_t)i + 2] = t.z;
+  }
+  if (result) result[i] = ik_result_value<double, D>(ck, leg, ch2, q, des_leg);
+}
+
+}  // namespace shc
+
+using namespace shc;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(x)                                                                                   \
+  do {                                                                                                \
+    cudaError_t err__ = (x);                                                                          \
+    if (err__ != cudaSuccess) return fail(SHC_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(err__)); \
+  } while (0)
+
+struct GraphKey {
+  int k;
+  const float *cmd, *imu, *force;
+  float* out;
+  bool operator<(const GraphKey& o) const {
+    if (k != o.k) return k < o.k;
+    if (cmd != o.cmd) return cmd < o.cmd;
+    if (imu != o.imu) return imu < o.imu;
+    if (force != o.force) return force < o.force;
+    return out < o.out;
+  }
+};
+
+struct shc_engine {
+  shc_config cfg;
+  shc_startup su;
+  Consts c;
+  int device = 0;
+  int precision = SHC_PRECISION_F64;
+  int n = 0, n_pad = 0;
+  int options = 0;
+  int pose_reset_mode = 0;
+  size_t s_elem = 8;  // bytes per storage word
+  void* s_planes = nullptr;
+  double* d_planes = nullptr;
+  int* i_planes = nullptr;
+  int* d_flags = nullptr;
+  const float* d_efforts = nullptr;
+  cudaStream_t stream = nullptr;
+  // pinned staging for shc_step_host
+  float *h_cmd = nullptr, *h_imu = nullptr, *h_force = nullptr, *h_manual = nullptr, *h_out = nullptr;
+  float *d_cmd = nullptr, *d_imu = nullptr, *d_force = nullptr, *d_manual = nullptr, *d_out = nullptr;
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+};
+
+static void layout(const shc_config& cfg, int n, IntConsts& ci) {
+  ci.L = cfg.leg_count;
+  ci.D = cfg.joint_count;
+  ci.n_robots = n;
+  ci.n_pad = (n + 31) / 32 * 32;
+  const int D = cfg.joint_count;
+  const bool imu = cfg.imu_posing || cfg.inclination_posing;
+  const bool adm = cfg.admittance_control || cfg.use_joint_effort;
+  int s = RS_COUNT;
+  ci.offS_imu = s;
+  if (imu) s += IMU_COUNT;
+  ci.offS_auto = s;
+  if (cfg.auto_posing) s += AUTO_COUNT;
+  ci.offS_leg = s;
+  ci.offS_leg_adm = 2 * D + 27;
+  ci.strideS_leg = 2 * D + 27 + (adm ? ADM_COUNT : 0);
+  ci.nS = s + ci.strideS_leg * cfg.leg_count;
+  ci.offD_leg = RD_COUNT;
+  ci.strideD_leg = LD_COUNT;
+  ci.nD = RD_COUNT + LD_COUNT * cfg.leg_count;
+  int i = RI_COUNT;
+  ci.offI_auto = i;
+  if (cfg.auto_posing) i += AI_COUNT;
+  ci.offI_leg = i;
+  ci.strideI_leg = LI_COUNT;
+  ci.nI = i + LI_COUNT * cfg.leg_count;
+  ci.manual_posing = cfg.manual_posing;
+  ci.auto_posing = cfg.auto_posing;
+  ci.inclination_posing = cfg.inclination_posing;
+  ci.imu_posing = cfg.imu_posing;
+  ci.admittance_control = cfg.admittance_control;
+  ci.use_joint_effort = cfg.use_joint_effort;
+  ci.clamp_joint_positions = cfg.clamp_joint_positions;
+  ci.clamp_joint_velocities = cfg.clamp_joint_velocities;
+  ci.velocity_input_mode = cfg.velocity_input_mode;
+  ci.force_normal_touchdown = cfg.force_normal_touchdown;
+  ci.n_posers = cfg.auto_poser_count;
+  ci.pose_sync = cfg.pose_frequency == -1.0;
+  for (int a = 0; a < cfg.auto_poser_count; ++a) {
+    ci.ap_start[a] = cfg.pose_phase_starts[a];
+    ci.ap_end[a] = cfg.pose_phase_ends[a];
+  }
+  for (int l = 0; l < cfg.leg_count; ++l) {
+    ci.neg_start[l] = cfg.pose_negation_phase_starts[l];
+    ci.neg_end[l] = cfg.pose_negation_phase_ends[l];
+  }
+}
+
+template <int D> static void host_startup(shc_engine* e) {
+  compute_startup<D>(e->cfg, e->c.d, e->su);
+}
+template <int D> static void host_initial_state(shc_engine* e, shc_robot_state& s) {
+  initial_state<D>(e->cfg, e->c.d, e->su, s);
+}
+
+// ---- state record <-> planes (host side; get/set are not on the hot path) -----------------------------------------
+namespace {
+struct HostPlanes {
+  std::vector<double> s;  // storage planes widened to double
+  std::vector<double> d;
+  std::vector<int> i;
+};
+
+int download(shc_engine* e, HostPlanes& h) {
+  const IntConsts& ci = e->c.i;
+  const size_t np = ci.n_pad;
+  h.s.resize((size_t)ci.nS * np);
+  h.d.resize((size_t)ci.nD * np);
+  h.i.resize((size_t)ci.nI * np);
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (e->precision == SHC_PRECISION_F64) {
+    CUDA_TRY(cudaMemcpy(h.s.data(), e->s_planes, h.s.size() * 8, cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<float> tmp(h.s.size());
+    CUDA_TRY(cudaMemcpy(tmp.data(), e->s_planes, tmp.size() * 4, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < tmp.size(); ++k) h.s[k] = tmp[k];
+  }
+  CUDA_TRY(cudaMemcpy(h.d.data(), e->d_planes, h.d.size() * 8, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(h.i.data(), e->i_planes, h.i.size() * 4, cudaMemcpyDeviceToHost));
+  return SHC_OK;
+}
+
+int upload(shc_engine* e, const HostPlanes& h) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (e->precision == SHC_PRECISION_F64) {
+    CUDA_TRY(cudaMemcpy(e->s_planes, h.s.data(), h.s.size() * 8, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<float> tmp(h.s.size());
+    for (size_t k = 0; k < tmp.size(); ++k) tmp[k] = (float)h.s[k];
+    CUDA_TRY(cudaMemcpy(e->s_planes, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice));
+  }
+  CUDA_TRY(cudaMemcpy(e->d_planes, h.d.data(), h.d.size() * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(e->i_planes, h.i.data(), h.i.size() * 4, cudaMemcpyHostToDevice));
+  return SHC_OK;
+}
+
+inline int prog_num(double progress, int den) {
+  if (progress < 0.0) return -1;
+  int n = (int)(progress * den + 0.5);
+  return std::min(std::max(n, 0), den);
+}
+
+void pack(const shc_engine* e, const shc_robot_state* in, size_t n, HostPlanes& h) {
+  const IntConsts& ci = e->c.i;
+  const size_t np = ci.n_pad;
+  const int D = ci.D, L = ci.L;
+  const bool imu = e->cfg.imu_posing || e->cfg.inclination_posing;
+  const bool adm = e->cfg.admittance_control || e->cfg.use_joint_effort;
+  auto S = [&](int plane, size_t r) -> double& { return h.s[(size_t)plane * np + r]; };
+  auto Dd = [&](int plane, size_t r) -> double& { return h.d[(size_t)plane * np + r]; };
+  auto I = [&](int plane, size_t r) -> int& { return h.i[(size_t)plane * np + r]; };
+  for (size_t r = 0; r < n; ++r) {
+    const shc_robot_state& s = in[r];
+    S(RS_VEL, r) = s.desired_linear_velocity[0];
+    S(RS_VEL + 1, r) = s.desired_linear_velocity[1];
+    S(RS_ANGVEL, r) = s.desired_angular_velocity;
+    for (int k = 0; k < 3; ++k) {
+      S(RS_WPL + k, r) = s.walk_plane[k];
+      S(RS_WPN + k, r) = s.walk_plane_normal[k];
+      Dd(RD_ODOMP + k, r) = s.odometry_ideal[k];
+    }
+    for (int k = 0; k < 4; ++k) S(RS_ODOMQ + k, r) = s.odometry_ideal[3 + k];
+    for (int k = 0; k < 7; ++k) {
+      S(RS_WPP + k, r) = s.walk_plane_pose[k];
+      S(RS_OWPP + k, r) = s.origin_walk_plane_pose[k];
+      S(RS_MAN + k, r) = s.manual_pose[k];
+    }
+    if (imu) {
+      for (int k = 0; k < 4; ++k) S(ci.offS_imu + IMU_Q + k, r) = s.imu_pose[3 + k];
+      for (int k = 0; k < 3; ++k) {
+        S(ci.offS_imu + IMU_ABS + k, r) = s.rotation_absement_error[k];
+        S(ci.offS_imu + IMU_VEL + k, r) = s.rotation_velocity_error[k];
+      }
+      S(ci.offS_imu + IMU_INCL, r) = s.inclination_pose[0];
+      S(ci.offS_imu + IMU_INCL + 1, r) = s.inclination_pose[1];
+    }
+    if (e->cfg.auto_posing) {
+      for (int k = 0; k < 7; ++k) S(ci.offS_auto + AUTO_POSE + k, r) = s.auto_pose[k];
+      int pf = 0;
+      for (int a = 0; a < e->cfg.auto_poser_count; ++a) pf |= (s.auto_poser_flags[a] & 15) << (4 * a);
+      I(ci.offI_auto + AI_FLAGS, r) = pf;
+      I(ci.offI_auto + AI_PHASE, r) = s.pose_phase;
+    }
+    I(RI_BITS, r) = (s.walk_state & 3) | ((s.legs_at_correct_phase & 15) << 2) | ((s.legs_completed_first_step & 15) << 6) |
+                    ((s.return_to_default_attempted & 1) << 10) | ((s.pose_state & 3) << 11) | ((s.auto_posing_state & 3) << 13);
+    for (int l = 0; l < L; ++l) {
+      const shc_leg_state& g = s.legs[l];
+      const int sb = ci.offS_leg + l * ci.strideS_leg;
+      for (int j = 0; j < D; ++j) {
+        S(sb + j, r) = g.joint_position[j];
+        S(sb + D + j, r) = g.joint_velocity[j];
+      }
+      const int o = sb + 2 * D;
+      for (int k = 0; k < 3; ++k) {
+        S(o + 0 + k, r) = g.tip_velocity[k];
+        S(o + 3 + k, r) = g.swing_origin_position[k];
+        S(o + 6 + k, r) = g.swing_origin_velocity[k];
+        S(o + 9 + k, r) = g.stance_origin_position[k];
+        S(o + 12 + k, r) = g.default_tip_position[k];
+        S(o + 15 + k, r) = g.target_tip_position[k];
+        S(o + 18 + k, r) = g.stride_vector[k];
+        S(o + 21 + k, r) = g.walk_plane[k];
+        S(o + 24 + k, r) = g.walk_plane_normal[k];
+        Dd(ci.offD_leg + l * ci.strideD_leg + LD_TIP + k, r) = g.tip_position[k];
+      }
+      if (adm) {
+        const int ab = sb + ci.offS_leg_adm;
+        S(ab + ADM_X, r) = g.admittance_state[0];
+        S(ab + ADM_X + 1, r) = g.admittance_state[1];
+        for (int k = 0; k < 3; ++k) {
+          S(ab + ADM_DELTA + k, r) = g.admittance_delta[k];
+          S(ab + ADM_FORCE + k, r) = g.tip_force_calculated[k];
+        }
+      }
+      const int ib = ci.offI_leg + l * ci.strideI_leg;
+      I(ib + LI_BITS, r) = (g.phase & 0xffff) | ((g.step_state & 3) << 16) | ((g.at_correct_phase ? 1 : 0) << 18) |
+                           ((g.completed_first_step ? 1 : 0) << 19) | ((g.negate_auto_pose ? 1 : 0) << 20);
+      int sn = prog_num(g.swing_progress, ci.swing_period), tn = prog_num(g.stance_progress, ci.stance_period);
+      I(ib + LI_PROG, r) = (sn & 0xffff) | ((tn & 0xffff) << 16);
+    }
+  }
+}
+
+template <int D> void unpack(const shc_engine* e, const HostPlanes& h, shc_robot_state* out, size_t n) {
+  const IntConsts& ci = e->c.i;
+  const RealConsts<double>& ck = e->c.d;
+  const size_t np = ci.n_pad;
+  const int L = ci.L;
+  const bool imu = e->cfg.imu_posing || e->cfg.inclination_posing;
+  const bool adm = e->cfg.admittance_control || e->cfg.use_joint_effort;
+  auto S = [&](int plane, size_t r) { return h.s[(size_t)plane * np + r]; };
+  auto Dd = [&](int plane, size_t r) { return h.d[(size_t)plane * np + r]; };
+  auto I = [&](int plane, size_t r) { return h.i[(size_t)plane * np + r]; };
+  for (size_t r = 0; r < n; ++r) {
+    shc_robot_state& s = out[r];
+    std::memset(&s, 0, sizeof(s));
+    s.desired_linear_velocity[0] = S(RS_VEL, r);
+    s.desired_linear_velocity[1] = S(RS_VEL + 1, r);
+    s.desired_angular_velocity = S(RS_ANGVEL, r);
+    for (int k = 0; k < 3; ++k) {
+      s.walk_plane[k] = S(RS_WPL + k, r);
+      s.walk_plane_normal[k] = S(RS_WPN + k, r);
+      s.odometry_ideal[k] = Dd(RD_ODOMP + k, r);
+    }
+    for (int k = 0; k < 4; ++k) s.odometry_ideal[3 + k] = S(RS_ODOMQ + k, r);
+    for (int k = 0; k < 7; ++k) {
+      s.walk_plane_pose[k] = S(RS_WPP + k, r);
+      s.origin_walk_plane_pose[k] = S(RS_OWPP + k, r);
+      s.manual_pose[k] = S(RS_MAN + k, r);
+    }
+    auto ident = [](double* p) { for (int i = 0; i < 7; ++i) p[i] = 0.0; p[3] = 1.0; };
+    ident(s.imu_pose); ident(s.inclination_pose); ident(s.auto_pose);
+    if (!e->cfg.manual_posing) ident(s.manual_pose);
+    if (imu) {
+      for (int k = 0; k < 4; ++k) s.imu_pose[3 + k] = S(ci.offS_imu + IMU_Q + k, r);
+      for (int k = 0; k < 3; ++k) {
+        s.rotation_absement_error[k] = S(ci.offS_imu + IMU_ABS + k, r);
+        s.rotation_velocity_error[k] = S(ci.offS_imu + IMU_VEL + k, r);
+      }
+      s.inclination_pose[0] = S(ci.offS_imu + IMU_INCL, r);
+      s.inclination_pose[1] = S(ci.offS_imu + IMU_INCL + 1, r);
+    }
+    if (e->cfg.auto_posing) {
+      for (int k = 0; k < 7; ++k) s.auto_pose[k] = S(ci.offS_auto + AUTO_POSE + k, r);
+      int pf = I(ci.offI_auto + AI_FLAGS, r);
+      for (int a = 0; a < e->cfg.auto_poser_count; ++a) s.auto_poser_flags[a] = (pf >> (4 * a)) & 15;
+      s.pose_phase = I(ci.offI_auto + AI_PHASE, r);
+    }
+    int rb = I(RI_BITS, r);
+    s.walk_state = rb & 3;
+    s.legs_at_correct_phase = (rb >> 2) & 15;
+    s.legs_completed_first_step = (rb >> 6) & 15;
+    s.return_to_default_attempted = (rb >> 10) & 1;
+    s.pose_state = (rb >> 11) & 3;
+    s.auto_posing_state = (rb >> 13) & 3;
+    s.status_flags = (rb >> 16) & 0xffff;
+    // Model::current_pose_ is recomputed every cycle from the stored sub-poses (pose_controller.cpp:811-859)
+    {
+      PoseT<double> p = pose_identity<double>();
+      auto rd = [](const double* a) { return PoseT<double>{{a[0], a[1], a[2]}, {a[3], a[4], a[5], a[6]}}; };
+      p = pose_add(p, rd(s.walk_plane_pose));
+      if (e->cfg.manual_posing) p = pose_add(p, rd(s.manual_pose));
+      if (e->cfg.inclination_posing) p = pose_add(p, rd(s.inclination_pose));
+      if (e->cfg.imu_posing) p = pose_add(p, rd(s.imu_pose));
+      else if (e->cfg.auto_posing) p = pose_add(p, rd(s.auto_pose));
+      s.current_pose[0] = p.p.x; s.current_pose[1] = p.p.y; s.current_pose[2] = p.p.z;
+      s.current_pose[3] = p.q.w; s.current_pose[4] = p.q.x; s.current_pose[5] = p.q.y; s.current_pose[6] = p.q.z;
+    }
+    for (int l = 0; l < L; ++l) {
+      shc_leg_state& g = s.legs[l];
+      const int sb = ci.offS_leg + l * ci.strideS_leg;
+      for (int j = 0; j < D; ++j) {
+        g.joint_position[j] = S(sb + j, r);
+        g.joint_velocity[j] = S(sb + D + j, r);
+      }
+      const int o = sb + 2 * D;
+      for (int k = 0; k < 3; ++k) {
+        g.tip_velocity[k] = S(o + 0 + k, r);
+        g.swing_origin_position[k] = S(o + 3 + k, r);
+        g.swing_origin_velocity[k] = S(o + 6 + k, r);
+        g.stance_origin_position[k] = S(o + 9 + k, r);
+        g.default_tip_position[k] = S(o + 12 + k, r);
+        g.target_tip_position[k] = S(o + 15 + k, r);
+        g.stride_vector[k] = S(o + 18 + k, r);
+        g.walk_plane[k] = S(o + 21 + k, r);
+        g.walk_plane_normal[k] = S(o + 24 + k, r);
+        g.tip_position[k] = Dd(ci.offD_leg + l * ci.strideD_leg + LD_TIP + k, r);
+      }
+      if (adm) {
+        const int ab = sb + ci.offS_leg_adm;
+        g.admittance_state[0] = S(ab + ADM_X, r);
+        g.admittance_state[1] = S(ab + ADM_X + 1, r);
+        for (int k = 0; k < 3; ++k) {
+          g.admittance_delta[k] = S(ab + ADM_DELTA + k, r);
+          g.tip_force_calculated[k] = S(ab + ADM_FORCE + k, r);
+        }
+      }
+      const int ib = ci.offI_leg + l * ci.strideI_leg;
+      int b = I(ib + LI_BITS, r), pg = I(ib + LI_PROG, r);
+      g.phase = b & 0xffff;
+      g.step_state = (b >> 16) & 3;
+      g.at_correct_phase = (b >> 18) & 1;
+      g.completed_first_step = (b >> 19) & 1;
+      g.negate_auto_pose = (b >> 20) & 1;
+      int sn = (int)(short)(pg & 0xffff), tn = (int)(short)((pg >> 16) & 0xffff);
+      g.swing_progress = sn < 0 ? -1.0 : (double)sn / (double)ci.swing_period;
+      g.stance_progress = tn < 0 ? -1.0 : (double)tn / (double)ci.stance_period;
+      V3<double> tip = host_fk<D>(ck, l, g.joint_position);  // Leg::current_tip_pose_ = FK(joint positions)
+      g.model_tip_position[0] = tip.x; g.model_tip_position[1] = tip.y; g.model_tip_position[2] = tip.z;
+      g.ik_result = 1.0;
+    }
+  }
+}
+}  // namespace
+
+template <class F> static int dispatch_D(int D, F&& f) {
+  switch (D) {
+    case 3: return f(std::integral_constant<int, 3>());
+    case 4: return f(std::integral_constant<int, 4>());
+    case 5: return f(std::integral_constant<int, 5>());
+  }
+  return fail(SHC_E_UNSUPPORTED, "unsupported joint count");
+}
+
+static int launch_cycle(shc_engine* e, const StepIO& io, cudaStream_t st) {
+  const int threads = 128;
+  const int blocks = (e->n + threads - 1) / threads;
+  return dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int {
+    constexpr int D = decltype(dtag)::value;
+    if (e->precision == SHC_PRECISION_F64) {
+      Planes<double> pl{(double*)e->s_planes, e->d_planes, e->i_planes};
+      control_cycle_kernel<PrecF64, D><<<blocks, threads, 0, st>>>(e->c, pl, io);
+    } else {
+      Planes<float> pl{(float*)e->s_planes, e->d_planes, e->i_planes};
+      control_cycle_kernel<PrecMixed, D><<<blocks, threads, 0, st>>>(e->c, pl, io);
+    }
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(SHC_E_CUDA, std::string("control_cycle launch: ") + cudaGetErrorString(err));
+    return SHC_OK;
+  });
+}
+
+extern "C" {
+
+const char* shc_last_error(void) { return g_err.c_str(); }
+size_t shc_sizeof_config(void) { return sizeof(shc_config); }
+size_t shc_sizeof_startup(void) { return sizeof(shc_startup); }
+size_t shc_sizeof_robot_state(void) { return sizeof(shc_robot_state); }
+
+int shc_create(const shc_config* cfg, const shc_startup* startup, int n_robots, int device, int precision, shc_engine** out) {
+  if (!cfg || !out || n_robots < 1) return fail(SHC_E_INVALID, "shc_create: bad arguments");
+  if (precision != SHC_PRECISION_F64 && precision != SHC_PRECISION_MIXED) return fail(SHC_E_INVALID, "unknown precision");
+  std::string err;
+  bool unsupported = false;
+  if (!validate_config(*cfg, err, unsupported)) return fail(unsupported ? SHC_E_UNSUPPORTED : SHC_E_INVALID, err);
+  if (cfg->auto_posing && cfg->pose_frequency != -1.0)
+    return fail(SHC_E_UNSUPPORTED, "auto posing with its own pose_frequency (not synced to the step cycle) is not implemented");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
+    return fail(SHC_E_CUDA, "no CUDA device: the SHC engine has no CPU fallback");
+  if (device < 0 || device >= count) return fail(SHC_E_INVALID, "device ordinal out of range");
+  CUDA_TRY(cudaSetDevice(device));
+
+  shc_engine* e = new shc_engine();
+  e->cfg = *cfg;
+  e->device = device;
+  e->precision = precision;
+  e->n = n_robots;
+  std::memset(&e->c, 0, sizeof(e->c));
+  layout(*cfg, n_robots, e->c.i);
+  e->n_pad = e->c.i.n_pad;
+  fill_static_consts<double>(*cfg, e->c.d);
+  fill_static_consts<float>(*cfg, e->c.f);
+  std::memset(&e->su, 0, sizeof(e->su));
+  if (startup) {
+    e->su = *startup;
+  } else {
+    compute_step_cycle(*cfg, e->su);
+    dispatch_D(cfg->joint_count, [&](auto dtag) -> int { host_startup<decltype(dtag)::value>(e); return 0; });
+  }
+  IntConsts tmp = e->c.i;
+  fill_startup_consts<double>(*cfg, e->su, e->c.d, e->c.i);
+  fill_startup_consts<float>(*cfg, e->su, e->c.f, tmp);
+
+  e->s_elem = precision == SHC_PRECISION_F64 ? 8 : 4;
+  const IntConsts& ci = e->c.i;
+  const size_t np = ci.n_pad;
+  auto cleanup = [&](int code, const std::string& m) { shc_destroy(e); return fail(code, m); };
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return cleanup(SHC_E_CUDA, "stream create failed");
+  if (cudaMalloc(&e->s_planes, (size_t)ci.nS * np * e->s_elem) != cudaSuccess ||
+      cudaMalloc((void**)&e->d_planes, (size_t)ci.nD * np * 8) != cudaSuccess ||
+      cudaMalloc((void**)&e->i_planes, (size_t)ci.nI * np * 4) != cudaSuccess ||
+      cudaMalloc((void**)&e->d_flags, np * 4) != cudaSuccess)
+    return cleanup(SHC_E_CUDA, "device allocation failed");
+  cudaMemset(e->s_planes, 0, (size_t)ci.nS * np * e->s_elem);
+  cudaMemset(e->d_planes, 0, (size_t)ci.nD * np * 8);
+  cudaMemset(e->i_planes, 0, (size_t)ci.nI * np * 4);
+  cudaMemset(e->d_flags, 0, np * 4);
+
+  // every robot starts in the post-start-up state
+  shc_robot_state init;
+  dispatch_D(cfg->joint_count, [&](auto dtag) -> int { host_initial_state<decltype(dtag)::value>(e, init); return 0; });
+  {
+    HostPlanes h;
+    h.s.assign((size_t)ci.nS * np, 0.0);
+    h.d.assign((size_t)ci.nD * np, 0.0);
+    h.i.assign((size_t)ci.nI * np, 0);
+    HostPlanes one;
+    one.s.assign((size_t)ci.nS * np, 0.0);  // pack() writes column r of each plane; pack robot 0 then replicate
+    one.d.assign((size_t)ci.nD * np, 0.0);
+    one.i.assign((size_t)ci.nI * np, 0);
+    pack(e, &init, 1, one);
+    for (int p = 0; p < ci.nS; ++p) std::fill(h.s.begin() + (size_t)p * np, h.s.begin() + (size_t)p * np + e->n, one.s[(size_t)p * np]);
+    for (int p = 0; p < ci.nD; ++p) std::fill(h.d.begin() + (size_t)p * np, h.d.begin() + (size_t)p * np + e->n, one.d[(size_t)p * np]);
+    for (int p = 0; p < ci.nI; ++p) std::fill(h.i.begin() + (size_t)p * np, h.i.begin() + (size_t)p * np + e->n, one.i[(size_t)p * np]);
+    int rc = upload(e, h);
+    if (rc != SHC_OK) { std::string m = g_err; return cleanup(rc, m); }
+  }
+  *out = e;
+  return SHC_OK;
+}
+
+// Start-up constants only (host arithmetic, no device needed): the engine's restatement of generateStepCycle,
+// directStartup, generateWorkspaces, generateWalkspace and generateLimits for `cfg`.
+int shc_compute_startup(const shc_config* cfg, shc_startup* out) {
+  if (!cfg || !out) return fail(SHC_E_INVALID, "null argument");
+  std::string err;
+  bool unsupported = false;
+  if (!validate_config(*cfg, err, unsupported)) return fail(unsupported ? SHC_E_UNSUPPORTED : SHC_E_INVALID, err);
+  RealConsts<double>* ck = new RealConsts<double>();
+  fill_static_consts<double>(*cfg, *ck);
+  std::memset(out, 0, sizeof(*out));
+  compute_step_cycle(*cfg, *out);
+  dispatch_D(cfg->joint_count, [&](auto dtag) -> int { compute_startup<decltype(dtag)::value>(*cfg, *ck, *out); return 0; });
+  delete ck;
+  return SHC_OK;
+}
+
+// Host evaluation (double) of the same Leg::applyIK routine the kernels run, for CPU-side unit tests of the shared
+// kinematics code and for the start-up sweeps.  q/qd [D] in/out, desired/tip in the base_link frame.
+int shc_host_apply_ik(const shc_config* cfg, int leg, double* q, double* qd, const double* desired, int simulation,
+                      double* tip_out, double* ik_result) {
+  if (!cfg || !q || !qd || !desired) return fail(SHC_E_INVALID, "null argument");
+  std::string err;
+  bool unsupported = false;
+  if (!validate_config(*cfg, err, unsupported)) return fail(unsupported ? SHC_E_UNSUPPORTED : SHC_E_INVALID, err);
+  if (leg < 0 || leg >= cfg->leg_count) return fail(SHC_E_INVALID, "leg out of range");
+  RealConsts<double>* ck = new RealConsts<double>();
+  fill_static_consts<double>(*cfg, *ck);
+  int rc = dispatch_D(cfg->joint_count, [&](auto dtag) -> int {
+    constexpr int D = decltype(dtag)::value;
+    V3<double> tip;
+    double res = host_apply_ik<D>(*ck, *cfg, leg, q, qd, V3<double>{desired[0], desired[1], desired[2]}, simulation != 0, &tip);
+    if (tip_out) { tip_out[0] = tip.x; tip_out[1] = tip.y; tip_out[2] = tip.z; }
+    if (ik_result) *ik_result = res;
+    return SHC_OK;
+  });
+  delete ck;
+  return rc;
+}
+
+void shc_destroy(shc_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  cudaFree(e->s_planes);
+  cudaFree(e->d_planes);
+  cudaFree(e->i_planes);
+  cudaFree(e->d_flags);
+  cudaFree(e->d_cmd); cudaFree(e->d_imu); cudaFree(e->d_force); cudaFree(e->d_manual); cudaFree(e->d_out);
+  cudaFreeHost(e->h_cmd); cudaFreeHost(e->h_imu); cudaFreeHost(e->h_force); cudaFreeHost(e->h_manual); cudaFreeHost(e->h_out);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int shc_get_startup(const shc_engine* e, shc_startup* out) {
+  if (!e || !out) return fail(SHC_E_INVALID, "null argument");
+  *out = e->su;
+  return SHC_OK;
+}
+int shc_n_robots(const shc_engine* e) { return e ? e->n : 0; }
+int shc_options(const shc_engine* e) { return e ? e->options : 0; }
+int shc_set_options(shc_engine* e, int options) {
+  if (!e) return fail(SHC_E_INVALID, "null engine");
+  e->options = options;
+  return SHC_OK;
+}
+int shc_set_pose_reset_mode(shc_engine* e, int mode) {
+  if (!e || mode < 0 || mode > 5) return fail(SHC_E_INVALID, "bad pose reset mode");
+  e->pose_reset_mode = mode;
+  return SHC_OK;
+}
+int shc_set_joint_efforts(shc_engine* e, const float* efforts_dev) {
+  if (!e) return fail(SHC_E_INVALID, "null engine");
+  e->d_efforts = efforts_dev;
+  return SHC_OK;
+}
+
+int shc_get_state(shc_engine* e, shc_robot_state* out, size_t n_records) {
+  if (!e || !out || n_records != (size_t)e->n) return fail(SHC_E_INVALID, "shc_get_state: need n_robots records");
+  CUDA_TRY(cudaSetDevice(e->device));
+  HostPlanes h;
+  int rc = download(e, h);
+  if (rc != SHC_OK) return rc;
+  return dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int { unpack<decltype(dtag)::value>(e, h, out, n_records); return SHC_OK; });
+}
+
+int shc_set_state(shc_engine* e, const shc_robot_state* in, size_t n_records) {
+  if (!e || !in || n_records != (size_t)e->n) return fail(SHC_E_INVALID, "shc_set_state: need n_robots records");
+  CUDA_TRY(cudaSetDevice(e->device));
+  const IntConsts& ci = e->c.i;
+  HostPlanes h;
+  h.s.assign((size_t)ci.nS * ci.n_pad, 0.0);
+  h.d.assign((size_t)ci.nD * ci.n_pad, 0.0);
+  h.i.assign((size_t)ci.nI * ci.n_pad, 0);
+  pack(e, in, n_records, h);
+  return upload(e, h);
+}
+
+int shc_step(shc_engine* e, const float* cmd, const float* imu, const float* tip_force, const float* manual, float* joints_out,
+             void* stream) {
+  if (!e || !cmd || !joints_out) return fail(SHC_E_INVALID, "shc_step: cmd and joints_out are required");
+  StepIO io;
+  io.cmd = cmd; io.imu = imu; io.tip_force = tip_force; io.manual = manual; io.efforts = e->d_efforts;
+  io.joints_out = joints_out;
+  io.flags_out = (e->options & SHC_OPT_STATUS_FLAGS) ? e->d_flags : nullptr;
+  io.pose_reset_mode = e->pose_reset_mode;
+  return launch_cycle(e, io, stream ? (cudaStream_t)stream : e->stream);
+}
+
+static int ensure_staging(shc_engine* e, bool imu, bool force, bool manual) {
+  const size_t n = e->n, L = e->cfg.leg_count, D = e->cfg.joint_count;
+  if (!e->h_cmd) {
+    CUDA_TRY(cudaMallocHost((void**)&e->h_cmd, n * 3 * 4));
+    CUDA_TRY(cudaMalloc((void**)&e->d_cmd, n * 3 * 4));
+    CUDA_TRY(cudaMallocHost((void**)&e->h_out, n * L * D * 4));
+    CUDA_TRY(cudaMalloc((void**)&e->d_out, n * L * D * 4));
+  }
+  if (imu && !e->h_imu) {
+    CUDA_TRY(cudaMallocHost((void**)&e->h_imu, n * 10 * 4));
+    CUDA_TRY(cudaMalloc((void**)&e->d_imu, n * 10 * 4));
+  }
+  if (force && !e->h_force) {
+    CUDA_TRY(cudaMallocHost((void**)&e->h_force, n * L * 3 * 4));
+    CUDA_TRY(cudaMalloc((void**)&e->d_force, n * L * 3 * 4));
+  }
+  if (manual && !e->h_manual) {
+    CUDA_TRY(cudaMallocHost((void**)&e->h_manual, n * 6 * 4));
+    CUDA_TRY(cudaMalloc((void**)&e->d_manual, n * 6 * 4));
+  }
+  return SHC_OK;
+}
+
+int shc_step_host(shc_engine* e, const float* cmd, const float* imu, const float* tip_force, const float* manual,
+                  float* joints_out) {
+  if (!e || !cmd || !joints_out) return fail(SHC_E_INVALID, "shc_step_host: cmd and joints_out are required");
+  CUDA_TRY(cudaSetDevice(e->device));
+  int rc = ensure_staging(e, imu != nullptr, tip_force != nullptr, manual != nullptr);
+  if (rc != SHC_OK) return rc;
+  const size_t n = e->n, L = e->cfg.leg_count, D = e->cfg.joint_count;
+  cudaStream_t st = e->stream;
+  std::memcpy(e->h_cmd, cmd, n * 3 * 4);
+  CUDA_TRY(cudaMemcpyAsync(e->d_cmd, e->h_cmd, n * 3 * 4, cudaMemcpyHostToDevice, st));
+  if (imu) {
+    std::memcpy(e->h_imu, imu, n * 10 * 4);
+    CUDA_TRY(cudaMemcpyAsync(e->d_imu, e->h_imu, n * 10 * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (tip_force) {
+    std::memcpy(e->h_force, tip_force, n * L * 3 * 4);
+    CUDA_TRY(cudaMemcpyAsync(e->d_force, e->h_force, n * L * 3 * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (manual) {
+    std::memcpy(e->h_manual, manual, n * 6 * 4);
+    CUDA_TRY(cudaMemcpyAsync(e->d_manual, e->h_manual, n * 6 * 4, cudaMemcpyHostToDevice, st));
+  }
+  rc = shc_step(e, e->d_cmd, imu ? e->d_imu : nullptr, tip_force ? e->d_force : nullptr, manual ? e->d_manual : nullptr, e->d_out, st);
+  if (rc != SHC_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(e->h_out, e->d_out, n * L * D * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  std::memcpy(joints_out, e->h_out, n * L * D * 4);
+  return SHC_OK;
+}
+
+int shc_rollout(shc_engine* e, int k_cycles, const float* cmd_seq, const float* imu_seq, const float* force_seq, float* joints_out,
+                void* stream) {
+  if (!e || !cmd_seq || !joints_out || k_cycles < 1) return fail(SHC_E_INVALID, "shc_rollout: bad arguments");
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  GraphKey key{k_cycles, cmd_seq, imu_seq, force_seq, joints_out};
+  auto it = e->graphs.find(key);
+  if (it == e->graphs.end()) {
+    const size_t n = e->n, L = e->cfg.leg_count;
+    cudaGraph_t graph;
+    // capture on the engine's own stream (the legacy default stream cannot be captured), launch on the caller's
+    cudaStream_t cap = e->stream;
+    CUDA_TRY(cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed));
+    int rc = SHC_OK;
+    for (int k = 0; k < k_cycles && rc == SHC_OK; ++k)
+      rc = shc_step(e, cmd_seq + (size_t)k * n * 3, imu_seq ? imu_seq + (size_t)k * n * 10 : nullptr,
+                    force_seq ? force_seq + (size_t)k * n * L * 3 : nullptr, nullptr, joints_out, cap);
+    cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+    if (rc != SHC_OK) return rc;
+    if (ce != cudaSuccess) return fail(SHC_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+    cudaGraphExec_t exec;
+    CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    it = e->graphs.emplace(key, exec).first;
+  }
+  CUDA_TRY(cudaGraphLaunch(it->second, st));
+  return SHC_OK;
+}
+
+const int* shc_status_flags_device(const shc_engine* e) {
+  return (e && (e->options & SHC_OPT_STATUS_FLAGS)) ? e->d_flags : nullptr;
+}
+
+int shc_get_status_flags(shc_engine* e, int* host_out) {
+  if (!e || !host_out) return fail(SHC_E_INVALID, "null argument");
+  if (!(e->options & SHC_OPT_STATUS_FLAGS)) return fail(SHC_E_INVALID, "status flags are not enabled (shc_set_options)");
+  CUDA_TRY(cudaSetDevice(e->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(host_out, e->d_flags, (size_t)e->n * 4, cudaMemcpyDeviceToHost));
+  return SHC_OK;
+}
+
+int shc_apply_ik(shc_engine* e, int n_legs, const int* leg_id, double* q, double* qd, const double* desired_tip, int simulation,
+                 double* tip_out, double* ik_result, void* stream) {
+  if (!e || n_legs < 1 || !leg_id || !q || !qd || !desired_tip) return fail(SHC_E_INVALID, "shc_apply_ik: bad arguments");
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  const int threads = 128, blocks = (n_legs + threads - 1) / threads;
+  return dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int {
+    constexpr int D = decltype(dtag)::value;
+    apply_ik_kernel<D><<<blocks, threads, 0, st>>>(e->c, n_legs, leg_id, q, qd, desired_tip, simulation, tip_out, ik_result);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(SHC_E_CUDA, std::string("apply_ik launch: ") + cudaGetErrorString(err));
+    return SHC_OK;
+  });
+}
+
+int shc_synchronize(shc_engine* e) {
+  if (!e) return fail(SHC_E_INVALID, "null engine");
+  CUDA_TRY(cudaSetDevice(e->device));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return SHC_OK;
+}
+void* shc_stream(shc_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+size_t shc_bytes_per_step_device(const shc_engine* e) {
+  if (!e) return 0;
+  const IntConsts& ci = e->c.i;
+  size_t state = (size_t)ci.nS * e->s_elem + (size_t)ci.nD * 8 + (size_t)ci.nI * 4;
+  size_t in = 3 * 4 + (e->cfg.imu_posing || e->cfg.inclination_posing ? 10 * 4 : 0) +
+              (e->cfg.admittance_control && !e->cfg.use_joint_effort ? (size_t)ci.L * 3 * 4 : 0);
+  size_t outb = (size_t)ci.L * ci.D * 4;
+  return 2 * state + in + outb;
+}
+
+size_t shc_bytes_per_step_algorithmic(const shc_engine* e) {
+  // B_alg = 4 * [ 2 * (L * (2D + 33 + e_leg) + 38 + e_robot) + in + out ]
+  if (!e) return 0;
+  const int L = e->cfg.leg_count, D = e->cfg.joint_count;
+  const bool imu = e->cfg.imu_posing || e->cfg.inclination_posing;
+  int e_leg = e->cfg.admittance_control ? 8 : 0;
+  int e_robot = imu ? 18 : 0;
+  int in = 3 + (imu ? 10 : 0) + (e->cfg.admittance_control ? 3 * L : 0);
+  int outw = L * D;
+  return 4 * (size_t)(2 * (L * (2 * D + 33 + e_leg) + 38 + e_robot) + in + outw);
+}
+
+}  // extern "C"

@@ -1,0 +1,455 @@
+// shc_host.cuh — host side of the engine: configuration checks, the constants block, and the engine's own restatement
+// of the reference's one-off start-up computations whose results the per-cycle path treats as constants:
+//   WalkController::generateStepCycle   walk_controller.cpp:365      generateLimits      walk_controller.cpp:231
+//   PoseController::directStartup       pose_controller.cpp:463      (LegPoser::stepToPosition :1571,
+//                                                                     LegPoser::transitionConfiguration :1476)
+//   Model::generateWorkspaces           model.cpp:120 / Leg::generateWorkspace :309 (simple, one-plane workspace)
+//   WalkController::generateWalkspace   walk_controller.cpp:57
+// This runs once per engine on the CPU in double (it is start-up, not the hot path; SURVEY.md §8b "Non-cycle methods
+// still called ... Host implementations; results uploaded as constants") and reuses the same chain / DLS routines the
+// kernels use.  It shares no code with oracle/.
+#pragma once
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/shc_state.h"
+#include "shc_cycle.cuh"
+
+namespace shc {
+
+inline bool validate_config(const shc_config& c, std::string& err, bool& unsupported) {
+  unsupported = false;
+  auto bad = [&](const char* m) { err = m; return false; };
+  if (c.leg_count < 1 || c.leg_count > SHC_MAX_LEGS) return bad("leg_count must be 1..8");
+  if (c.joint_count < 1 || c.joint_count > SHC_MAX_DOF) return bad("joint_count must be 1..5");
+  if (!(c.time_delta > 0.0)) return bad("time_delta must be > 0");
+  if (c.stance_phase <= 0 || c.swing_phase <= 0 || c.phase_offset <= 0) return bad("gait phases must be > 0");
+  if (!(c.step_frequency > 0.0)) return bad("step_frequency must be > 0");
+  if (c.auto_poser_count < 0 || c.auto_poser_count > SHC_MAX_AUTO_POSERS) return bad("auto_poser_count out of range");
+  if (c.rough_terrain_mode) { unsupported = true; return bad("rough_terrain_mode is outside the hot-path scope (needs tf2 / TipState touchdown inputs)"); }
+  if (c.gravity_aligned_tips) { unsupported = true; return bad("gravity_aligned_tips (tip rotation IK / tip-align pose) is not implemented"); }
+  if (c.joint_count != 3 && c.joint_count != 4 && c.joint_count != 5) { unsupported = true; return bad("kernels are instantiated for 3, 4 and 5 joints per leg"); }
+  return true;
+}
+
+template <class R> void fill_static_consts(const shc_config& c, RealConsts<R>& k) {
+  std::memset(&k, 0, sizeof(k));
+  const double w = 0.1;  // JOINT_LIMIT_COST_WEIGHT (model.h:20)
+  for (int l = 0; l < c.leg_count; ++l) {
+    double th = c.link_theta[l][0], al = c.link_alpha[l][0], r = c.link_r[l][0], d = c.link_d[l][0];
+    double m[9] = {cos(th), -sin(th) * cos(al), sin(th) * sin(al), sin(th), cos(th) * cos(al), -cos(th) * sin(al), 0.0, sin(al), cos(al)};
+    for (int i = 0; i < 9; ++i) k.t1r[l][i] = R(m[i]);
+    k.t1p[l][0] = R(r * cos(th)); k.t1p[l][1] = R(r * sin(th)); k.t1p[l][2] = R(d);
+    for (int j = 0; j < c.joint_count; ++j) {
+      k.dh_d[l][j] = R(c.link_d[l][j + 1]);
+      k.dh_theta[l][j] = R(c.link_theta[l][j + 1]);
+      k.dh_r[l][j] = R(c.link_r[l][j + 1]);
+      k.dh_ca[l][j] = R(cos(c.link_alpha[l][j + 1]));
+      k.dh_sa[l][j] = R(sin(c.link_alpha[l][j + 1]));
+      double lo = c.joint_min[l][j], hi = c.joint_max[l][j], vm = c.joint_max_vel[l][j];
+      double range = hi - lo;
+      k.jmin[l][j] = R(lo); k.jmax[l][j] = R(hi); k.vmax[l][j] = R(vm);
+      k.joffset[l][j] = R(c.joint_offset[l][j]);
+      k.jcentre[l][j] = R(lo + range / 2.0);
+      k.jcost_pos[l][j] = R(range != 0.0 ? w / range : 0.0);
+      k.jgrad_pos[l][j] = R(range != 0.0 ? -(w * w) / (range * range) : 0.0);
+      double vr = 2 * vm;
+      k.jcost_vel[l][j] = R(w / vr);
+      k.jgrad_vel[l][j] = R(-(w * w) / (vr * vr));
+    }
+    k.identity_x[l] = R(c.stance_x[l]);
+    k.identity_y[l] = R(c.stance_y[l]);
+    k.ysign[l] = R(c.stance_y[l] > 0.0 ? 1.0 : -1.0);
+    k.neg_ratio[l] = R(c.negation_transition_ratio[l]);
+  }
+  k.dt = R(c.time_delta);
+  k.inv_dt = R(1.0 / c.time_delta);
+  k.swing_height = R(c.swing_height);
+  k.swing_width = R(c.swing_width);
+  k.body_clearance = R(c.body_clearance);
+  k.lambda2 = R(0.02 * 0.02);
+  k.swing_progress_scaler = R(std::max(1.0, double(c.swing_phase) / c.phase_offset));
+  for (int i = 0; i < 3; ++i) {
+    k.max_translation[i] = R(c.max_translation[i]);
+    k.max_rotation[i] = R(c.max_rotation[i]);
+  }
+  k.max_translation_velocity = R(c.max_translation_velocity);
+  k.max_rotation_velocity = R(c.max_rotation_velocity);
+  k.pid_p = R(c.rotation_pid_p); k.pid_i = R(c.rotation_pid_i); k.pid_d = R(c.rotation_pid_d);
+  k.force_gain = R(c.force_gain);
+  k.body_velocity_scaler = R(c.body_velocity_scaler);
+  for (int a = 0; a < c.auto_poser_count; ++a) {
+    k.ap_pos[a][0] = R(c.x_amplitudes[a]); k.ap_pos[a][1] = R(c.y_amplitudes[a]); k.ap_pos[a][2] = R(c.z_amplitudes[a]);
+    k.ap_rot[a][0] = R(c.roll_amplitudes[a]); k.ap_rot[a][1] = R(c.pitch_amplitudes[a]); k.ap_rot[a][2] = R(c.yaw_amplitudes[a]);
+    k.ap_gravity[a] = R(c.gravity_amplitudes[a]);
+  }
+  // AdmittanceController::updateAdmittance (admittance_controller.cpp:33-52): 30 classic RK4 steps of the linear ODE
+  // x' = A x + b F, A = [[0,1],[-k/m,-c/m]], b = (0,-1/m), h = step_time/30, collapse to x <- P x + q F.
+  {
+    double m_ = c.virtual_mass, ks = c.virtual_stiffness, z = c.virtual_damping_ratio;
+    double cdamp = z * 2 * sqrt(m_ * ks);
+    double h = c.integrator_step_time / 30;
+    double A[2][2] = {{0.0, 1.0}, {-ks / m_, -cdamp / m_}};
+    double b[2] = {0.0, -1.0 / m_};
+    auto mul = [](const double X[2][2], const double Y[2][2], double Z[2][2]) {
+      double t[2][2];
+      for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) t[i][j] = X[i][0] * Y[0][j] + X[i][1] * Y[1][j];
+      std::memcpy(Z, t, sizeof(t));
+    };
+    double A2[2][2], A3[2][2], A4[2][2];
+    mul(A, A, A2); mul(A2, A, A3); mul(A3, A, A4);
+    double Ph[2][2], Bh[2][2];  // one RK4 step: x <- Ph x + Bh b F
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 2; ++j) {
+        double I = i == j ? 1.0 : 0.0;
+        Ph[i][j] = I + h * A[i][j] + h * h / 2 * A2[i][j] + h * h * h / 6 * A3[i][j] + h * h * h * h / 24 * A4[i][j];
+        Bh[i][j] = h * (I + h / 2 * A[i][j] + h * h / 6 * A2[i][j] + h * h * h / 24 * A3[i][j]);
+      }
+    double qh[2] = {Bh[0][0] * b[0] + Bh[0][1] * b[1], Bh[1][0] * b[0] + Bh[1][1] * b[1]};
+    double P[2][2] = {{1, 0}, {0, 1}}, q[2] = {0, 0};
+    for (int s = 0; s < 30; ++s) {
+      double nq[2] = {Ph[0][0] * q[0] + Ph[0][1] * q[1] + qh[0], Ph[1][0] * q[0] + Ph[1][1] * q[1] + qh[1]};
+      q[0] = nq[0]; q[1] = nq[1];
+      mul(Ph, P, P);
+    }
+    if (m_ > 0 && ks >= 0) {
+      k.adm_P[0] = R(P[0][0]); k.adm_P[1] = R(P[0][1]); k.adm_P[2] = R(P[1][0]); k.adm_P[3] = R(P[1][1]);
+      k.adm_q[0] = R(q[0]); k.adm_q[1] = R(q[1]);
+    }
+  }
+}
+
+// WalkController::generateStepCycle (walk_controller.cpp:365) and the phase offsets of generateLimits (:237-278)
+inline void compute_step_cycle(const shc_config& c, shc_startup& su) {
+  int stance_end = int(c.stance_phase * 0.5);
+  int swing_start = stance_end;
+  int swing_end = swing_start + c.swing_phase;
+  int stance_start = swing_end;
+  int base = c.stance_phase + c.swing_phase;
+  double swing_ratio = double(c.swing_phase) / double(base);
+  double raw = ((1.0 / c.step_frequency) / c.time_delta) / swing_ratio;
+  su.period = round_to_even_int(raw / base) * base;
+  su.step_frequency = 1.0 / (su.period * c.time_delta);
+  int normaliser = su.period / base;
+  su.stance_end = stance_end * normaliser;
+  su.swing_start = swing_start * normaliser;
+  su.swing_end = swing_end * normaliser;
+  su.stance_start = stance_start * normaliser;
+  su.stance_period = imod(su.stance_end - su.stance_start, su.period);
+  su.swing_period = su.swing_end - su.swing_start;
+  int base_offset = int(c.phase_offset * normaliser);
+  for (int l = 0; l < c.leg_count; ++l) su.phase_offsets[l] = (base_offset * c.offset_multiplier[l]) % su.period;
+  // PoseController::setAutoPoseParams (pose_controller.cpp:44-63)
+  int base_len;
+  double raw_len;
+  if (c.pose_frequency == -1.0) {
+    base_len = c.stance_phase + c.swing_phase;
+    double sr = double(c.swing_phase) / base_len;
+    raw_len = ((1.0 / c.step_frequency) / c.time_delta) / sr;
+  } else {
+    base_len = c.pose_phase_length;
+    raw_len = ((1.0 / c.pose_frequency) / c.time_delta);
+  }
+  if (base_len > 0) {
+    su.pose_phase_length = round_to_even_int(raw_len / base_len) * base_len;
+    su.pose_normaliser = su.pose_phase_length / base_len;
+  }
+  su.auto_pose_reference_leg = 0;
+  for (int l = 0; l < c.leg_count; ++l)
+    if (c.offset_multiplier[l] == 0) su.auto_pose_reference_leg = l;
+}
+
+// One Leg::applyIK(simulation) on host joint arrays; returns applyIK's value and the new tip (base_link frame).
+template <int D>
+double host_apply_ik(const RealConsts<double>& ck, const shc_config& c, int leg, double* q, double* qd, V3<double> desired,
+                     bool simulation, V3<double>* tip_robot) {
+  Chain<double, D> ch;
+  leg_chain<double, D>(ck, leg, q, ch);
+  V3<double> des_leg;
+  apply_ik_step<double, D>(ck, leg, ch, q, qd, desired, c.clamp_joint_positions != 0, c.clamp_joint_velocities != 0 && !simulation,
+                           &des_leg);
+  Chain<double, D> ch2;
+  leg_chain<double, D>(ck, leg, q, ch2);
+  if (tip_robot) *tip_robot = t1_rotate(ck, leg, ch2.tip) + V3<double>{ck.t1p[leg][0], ck.t1p[leg][1], ck.t1p[leg][2]};
+  return ik_result_value<double, D>(ck, leg, ch2, q, des_leg);
+}
+
+template <int D> V3<double> host_fk(const RealConsts<double>& ck, int leg, const double* q) {
+  Chain<double, D> ch;
+  leg_chain<double, D>(ck, leg, q, ch);
+  return t1_rotate(ck, leg, ch.tip) + V3<double>{ck.t1p[leg][0], ck.t1p[leg][1], ck.t1p[leg][2]};
+}
+
+// directStartup + generateWorkspaces + generateWalkspace + generateLimits.
+template <int D> void compute_startup(const shc_config& c, const RealConsts<double>& ck, shc_startup& su) {
+  const int L = c.leg_count;
+  const double dt = c.time_delta;
+  // Body pose during the start-up cycles: walk-plane pose (0,0,clearance) with identity rotation; manual, inclination
+  // and auto poses are identities while STOPPED with no inputs (pose_controller.cpp:811-859).
+  const PoseT<double> body{{0.0, 0.0, c.body_clearance}, qidentity<double>()};
+  const double pi = kPi;
+
+  for (int l = 0; l < L; ++l) {
+    // ---- PoseController::directStartup (:463): simulate stepToPosition + applyIK(true) from the default joint state
+    double q0[D], q[D], qd[D];
+    for (int j = 0; j < D; ++j) {
+      q0[j] = clamp_(0.0, c.joint_min[l][j], c.joint_max[l][j]);  // Joint::default_position_ (model.cpp:1038)
+      q[j] = q0[j];
+      qd[j] = 0.0;
+    }
+    V3<double> origin = host_fk<D>(ck, l, q);
+    V3<double> target{c.stance_x[l], c.stance_y[l], 0.0};  // default tip pose, walk-plane frame
+    V3<double> pdelta = origin - pose_inverse_transform(body, target);
+    if (norm(pdelta) > 0.01) {  // TIP_TOLERANCE; lift_height is 0
+      int num = std::max(1, round_to_int(c.time_to_start / dt));
+      double delta_t = 1.0 / num;
+      int half = num / 2;
+      V3<double> o2t = origin - target;
+      V3<double> n1[5] = {origin, origin, origin, target + o2t * 0.75, target + o2t * 0.5};
+      V3<double> n2[5] = {target + o2t * 0.5, target + o2t * 0.25, target, target, target};
+      for (int count = 1; count <= num; ++count) {
+        double ratio = double(count - 1) / double(num);
+        PoseT<double> dpose = pose_interpolate(pose_identity<double>(), smooth_step(ratio), body);
+        int sic = (count + (num - 1)) % num + 1;
+        V3<double> tip;
+        if (sic <= half) tip = quartic_bezier(n1, sic * delta_t * 2.0);
+        else tip = quartic_bezier(n2, (sic - half) * delta_t * 2.0);
+        V3<double> cmd = pose_inverse_transform(dpose, tip);
+        host_apply_ik<D>(ck, c, l, q, qd, cmd, true, nullptr);
+      }
+    }
+    // LegPoser::transitionConfiguration (:1476): cubic Bezier (o,o,d,d); the last sample is at t = num * (1/num)
+    {
+      int num = std::max(1, round_to_int(c.time_to_start / dt));
+      double t = num * (1.0 / num), s = 1.0 - t;
+      for (int j = 0; j < D; ++j)
+        su.default_joint[l][j] = q0[j] * (s * s * s) + q0[j] * (3.0 * t * s * s) + q[j] * (3.0 * t * t * s) + q[j] * (t * t * t);
+    }
+  }
+
+  // ---- Leg::generateWorkspace (model.cpp:309), simple workspace: one plane at height 0, 8 bearings ----
+  for (int l = 0; l < L; ++l) {
+    double qdef[D];
+    for (int j = 0; j < D; ++j) qdef[j] = su.default_joint[l][j];
+    V3<double> identity_tip = pose_inverse_transform(body, V3<double>{c.stance_x[l], c.stance_y[l], 0.0});
+    V3<double> cur = host_fk<D>(ck, l, qdef);
+    for (int b = 0; b < SHC_N_BEARINGS; ++b) su.workspace[l][b] = 1.0;  // MAX_WORKSPACE_RADIUS
+    if (norm(identity_tip - cur) > 0.005) {
+      for (int b = 0; b < SHC_N_BEARINGS; ++b) su.workspace[l][b] = 0.0;
+      continue;
+    }
+    double q[D], qd[D];
+    // bearing 0 pass: track from the current tip to the workplane origin, then make that the search default
+    {
+      for (int j = 0; j < D; ++j) { q[j] = qdef[j]; qd[j] = 0.0; }
+      int n = std::max(1, round_to_int((1.0 / 10) / 0.002));
+      V3<double> o = cur, tg = identity_tip, tip = cur;
+      bool within = true;
+      for (int it = 1; it <= n; ++it) {
+        double i = double(it) / n;
+        double res = host_apply_ik<D>(ck, c, l, q, qd, o * (1.0 - i) + tg * i, true, &tip);
+        within = within && res != 0.0;
+        if (!within) break;
+      }
+      for (int j = 0; j < D; ++j) qdef[j] = q[j];
+    }
+    for (int bearing = 45; bearing <= 360; bearing += 45) {
+      for (int j = 0; j < D; ++j) { q[j] = qdef[j]; qd[j] = 0.0; }
+      int n = round_to_int(1.0 / 0.002);
+      V3<double> o = identity_tip, tg = identity_tip;
+      double rad = bearing / 360.0 * 2.0 * pi;
+      tg.x += 1.0 * cos(rad);
+      tg.y += 1.0 * sin(rad);
+      V3<double> tip = identity_tip;
+      bool within = true;
+      for (int it = 1; it <= n; ++it) {
+        double i = double(it) / n;
+        double res = host_apply_ik<D>(ck, c, l, q, qd, o * (1.0 - i) + tg * i, true, &tip);
+        within = within && res != 0.0;
+        if (!within) break;
+      }
+      su.workspace[l][bearing / 45] = norm(tip - identity_tip);
+    }
+    su.workspace[l][0] = su.workspace[l][8];
+  }
+
+  // ---- WalkController::generateWalkspace (walk_controller.cpp:57) ----
+  double ws[SHC_N_BEARINGS];
+  bool have[SHC_N_BEARINGS] = {false};
+  for (int l = 0; l < L; ++l) {
+    int a1 = imod(l + 1, L), a2 = imod(l - 1, L);
+    double dx1 = c.stance_x[a1] - c.stance_x[l], dy1 = c.stance_y[a1] - c.stance_y[l];
+    double dx2 = c.stance_x[a2] - c.stance_x[l], dy2 = c.stance_y[a2] - c.stance_y[l];
+    double dist1 = sqrt(dx1 * dx1 + dy1 * dy1 + 0.0) / 2.0, dist2 = sqrt(dx2 * dx2 + dy2 * dy2 + 0.0) / 2.0;
+    double b1 = (atan2(dy1, dx1) / (2.0 * pi)) * 360.0, b2 = (atan2(dy2, dx2) / (2.0 * pi)) * 360.0;
+    for (int bi = 0; bi < SHC_N_BEARINGS; ++bi) {
+      int bearing = bi * 45;
+      int diff1 = abs(imod(int(b1), 360) - bearing), diff2 = abs(imod(int(b2), 360) - bearing);
+      double o1 = 2147483647.0, o2 = 2147483647.0;
+      if ((diff1 < 90 || diff1 > 270) && dist1 > 0.0) o1 = dist1 / cos(diff1 / 360.0 * 2.0 * pi);
+      if ((diff2 < 90 || diff2 > 270) && dist2 > 0.0) o2 = dist2 / cos(diff2 / 360.0 * 2.0 * pi);
+      double md = c.overlapping_walkspaces ? 1.0 : std::min(o1, o2);
+      md = std::min(md, 1.0);
+      if (have[bi] && md < ws[bi]) ws[bi] = md;
+      else if (!have[bi]) { ws[bi] = md; have[bi] = true; }
+    }
+  }
+  for (int l = 0; l < L; ++l) {
+    // default tip == identity tip at start-up, so the target workplane is the one plane at height 0 and the radius
+    // is the workplane radius itself (walk_controller.cpp:137-140)
+    for (int bi = 0; bi < SHC_N_BEARINGS; ++bi) {
+      double radius = su.workspace[l][bi];
+      int opp = imod(bi * 45 + 180, 360) / 45;
+      if (radius < ws[bi]) {
+        ws[bi] = radius;
+        ws[opp] = radius;
+      }
+    }
+  }
+  ws[8] = ws[0];
+  for (int bi = 0; bi < SHC_N_BEARINGS; ++bi) su.walkspace[bi] = ws[bi];
+
+  // ---- WalkController::generateLimits (walk_controller.cpp:231) ----
+  int max_ext = 0;
+  for (int l = 0; l < L; ++l) {
+    int off = su.phase_offsets[l];
+    if (off > su.swing_start && off < su.swing_end) max_ext = std::max(max_ext, su.swing_end - off);
+  }
+  double t_max = (max_ext + su.stance_period + su.swing_period) * dt;
+  double stance_radius = sqrt(c.stance_x[0] * c.stance_x[0] + c.stance_y[0] * c.stance_y[0]);
+  for (int bi = 0; bi < SHC_N_BEARINGS; ++bi) {
+    double wr = ws[bi];
+    double ogr = double(su.stance_period) / su.period;
+    double max_speed = (wr * 2.0) / (ogr / su.step_frequency);
+    double max_acc = max_speed / t_max;
+    double overshoot = 0;
+    for (int l = 0; l < L; ++l) {
+      double off = su.phase_offsets[l];
+      double t = off * dt;
+      double tse = t_max - t;
+      double v0 = max_acc * tse;
+      double sl = v0 * (ogr / su.step_frequency);
+      double d0 = -sl / 2.0;
+      double d1 = d0 + v0 * t + 0.5 * max_acc * (t * t);
+      double d2 = max_speed * (su.stance_period * dt - t);
+      overshoot = std::max(overshoot, d1 + d2 - wr);
+    }
+    double swing_overshoot = 0.5 * max_speed * su.swing_period / (2.0 * su.period * su.step_frequency);
+    double scaled = (wr / (wr + overshoot + swing_overshoot)) * wr;
+    double mls = (scaled * 2.0) / (ogr / su.step_frequency);
+    double mla = mls / t_max;
+    double mas = mls / stance_radius;
+    double maa = mas / t_max;
+    if (wr == 0.0) { mls = 0.0; mla = 2147483647.0; mas = 0.0; maa = 2147483647.0; }
+    su.max_linear_speed[bi] = mls;
+    su.max_linear_acceleration[bi] = mla;
+    su.max_angular_speed[bi] = mas;
+    su.max_angular_acceleration[bi] = maa;
+  }
+}
+
+// Constants that depend on the start-up results (timing, limit tables, stance-span shift).
+template <class R> void fill_startup_consts(const shc_config& c, const shc_startup& su, RealConsts<R>& k, IntConsts& ci) {
+  const double dt = c.time_delta;
+  ci.period = su.period; ci.swing_period = su.swing_period; ci.stance_period = su.stance_period;
+  ci.stance_end = su.stance_end; ci.swing_start = su.swing_start; ci.swing_end = su.swing_end; ci.stance_start = su.stance_start;
+  // LegStepper::updateTipPosition (walk_controller.cpp:1035-1041), evaluated in double exactly as written
+  int swing_iterations = int((double(su.swing_period) / su.period) / (su.step_frequency * dt));
+  swing_iterations = round_to_even_int(swing_iterations);
+  ci.swing_iterations = swing_iterations;
+  k.swing_dt = R(1.0 / (swing_iterations / 2.0));
+  auto stance_iter = [&](int mod_period) { return int((double(mod_period) / su.period) / (su.step_frequency * dt)); };
+  int std_period = imod(su.stance_end - su.stance_start, su.period);
+  if (su.stance_end == su.stance_start) std_period = su.period;
+  k.stance_dt_std = R(1.0 / stance_iter(std_period));
+  for (int l = 0; l < c.leg_count; ++l) {
+    ci.phase_offset[l] = su.phase_offsets[l];
+    ci.mod_stance_start[l] = su.phase_offsets[l];
+    int mp = imod(su.stance_end - su.phase_offsets[l], su.period);
+    if (su.stance_end == su.phase_offsets[l]) mp = su.period;
+    k.stance_dt_mod[l] = R(1.0 / stance_iter(mp));
+    k.stride_scaler_mod[l] = R(double(mp) / imod(su.stance_end - su.stance_start, su.period));
+    // LegStepper::calculateStanceSpanChange (:949) with the one-plane workspace
+    double ssm = c.stance_span_modifier;
+    bool pos_y = c.stance_y[l] > 0.0;
+    int bearing = (pos_y ^ (ssm > 0.0)) ? 270 : 90;
+    ssm *= (pos_y ? 1.0 : -1.0);
+    k.span_dy[l] = R(su.workspace[l][bearing / 45] * ssm);
+  }
+  double ogr = double(su.stance_period) / su.period;
+  k.stride_scale = R(ogr / su.step_frequency);
+  k.inv_swing_period = R(1.0 / su.swing_period);
+  k.inv_stance_period = R(1.0 / su.stance_period);
+  for (int b = 0; b < SHC_N_BEARINGS; ++b) {
+    k.limits[0][b] = R(su.max_linear_speed[b]);
+    k.limits[1][b] = R(su.max_angular_speed[b]);
+    k.limits[2][b] = R(su.max_linear_acceleration[b]);
+    k.limits[3][b] = R(su.max_angular_acceleration[b]);
+  }
+  ci.pose_phase_length = su.pose_phase_length;
+  ci.pose_normaliser = su.pose_normaliser;
+  ci.auto_ref_leg = su.auto_pose_reference_leg;
+}
+
+// State at the end of the direct start-up (READY -> RUNNING): every robot of a new engine starts here.
+template <int D> void initial_state(const shc_config& c, const RealConsts<double>& ck, const shc_startup& su, shc_robot_state& s) {
+  std::memset(&s, 0, sizeof(s));
+  s.walk_state = WALK_STOPPED;
+  s.pose_state = POSE_COMPLETE;
+  s.auto_posing_state = POSE_COMPLETE;
+  s.walk_plane_normal[2] = 1.0;
+  auto ident = [](double* p) { for (int i = 0; i < 7; ++i) p[i] = 0.0; p[3] = 1.0; };
+  ident(s.odometry_ideal); ident(s.walk_plane_pose); ident(s.origin_walk_plane_pose); ident(s.manual_pose);
+  ident(s.imu_pose); ident(s.inclination_pose); ident(s.auto_pose); ident(s.current_pose);
+  s.walk_plane_pose[2] = c.body_clearance;
+  s.origin_walk_plane_pose[2] = c.body_clearance;
+  s.current_pose[2] = c.body_clearance;
+  for (int l = 0; l < c.leg_count; ++l) {
+    shc_leg_state& g = s.legs[l];
+    for (int j = 0; j < D; ++j) g.joint_position[j] = su.default_joint[l][j];
+    double id[3] = {c.stance_x[l], c.stance_y[l], 0.0};
+    for (int k = 0; k < 3; ++k) {
+      g.tip_position[k] = id[k];
+      g.swing_origin_position[k] = id[k];
+      g.stance_origin_position[k] = id[k];
+      g.default_tip_position[k] = id[k];
+      g.target_tip_position[k] = id[k];
+    }
+    g.walk_plane_normal[2] = 1.0;
+    g.swing_progress = -1.0;
+    g.stance_progress = -1.0;
+    g.phase = 0;
+    g.step_state = STEP_STANCE;
+    V3<double> tip = host_fk<D>(ck, l, g.joint_position);
+    g.model_tip_position[0] = tip.x; g.model_tip_position[1] = tip.y; g.model_tip_position[2] = tip.z;
+    g.desired_tip_position[0] = tip.x; g.desired_tip_position[1] = tip.y; g.desired_tip_position[2] = tip.z;
+    g.ik_result = 1.0;
+  }
+  if (c.auto_posing) {
+    // The reference runs updateAutoPose during the ~300 start-up cycles (walk state STOPPED, master phase 0).  The
+    // latches reach a fixed point after one evaluation (pose_controller.cpp:1359-1371, 1743-1751).
+    const int len = su.pose_phase_length, norm = su.pose_normaliser;
+    const bool sync = c.pose_frequency == -1.0;
+    s.auto_posing_state = POSE_COMPLETE;
+    for (int a = 0; a < c.auto_poser_count; ++a) {
+      int phase = 0, sp = c.pose_phase_starts[a] * norm, ep = c.pose_phase_ends[a] * norm;
+      if (sp > ep) { ep += len; if (phase < sp) phase += len; }
+      bool start_check = !sync, end1 = (phase == sp), end2 = (phase == ep && end1), allow = false;
+      if (!allow && start_check) { allow = true; end1 = end2 = false; }
+      s.auto_poser_flags[a] = (start_check ? 1 : 0) | (end1 ? 2 : 0) | (end2 ? 4 : 0) | (allow ? 8 : 0);
+    }
+    for (int l = 0; l < c.leg_count; ++l) {
+      int sp = c.pose_negation_phase_starts[l] * norm, ep = c.pose_negation_phase_ends[l] * norm, np_ = 0;
+      if (sp == 0) sp = len;
+      if (ep == 0) ep = len;
+      if (sp > ep) { ep += len; if (np_ < sp) np_ += len; }
+      bool negate = (np_ == sp);
+      if (np_ < sp || np_ > ep) negate = false;
+      s.legs[l].negate_auto_pose = negate;
+    }
+  }
+}
+
+}  // namespace shc

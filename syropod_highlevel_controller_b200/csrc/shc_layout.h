@@ -1,0 +1,71 @@
+// shc_layout.h — device state layout: struct-of-arrays planes, robot index fastest (DESIGN.md "Data layout in HBM").
+//
+//   storage planes  S[nS][n_pad]   S = float (mixed) or double (f64): everything that is not an open-loop accumulator
+//   double planes   D[nD][n_pad]   open-loop integrated accumulators: stepper tip position, odometry position
+//   int planes      I[nI][n_pad]   packed integer state
+//
+// A warp of 32 consecutive robots reads/writes 32 consecutive words of a plane: one fully used 128-byte line (256 B for
+// double planes).  Field -> reference member mapping is the one of include/shc_state.h.
+#pragma once
+
+namespace shc {
+
+// robot-level storage planes (always present)
+enum : int {
+  RS_VEL = 0,    // desired_linear_velocity_ (2)
+  RS_ANGVEL = 2, // desired_angular_velocity_
+  RS_WPL = 3,    // WalkController::walk_plane_ (3)
+  RS_WPN = 6,    // WalkController::walk_plane_normal_ (3)
+  RS_ODOMQ = 9,  // odometry_ideal_.rotation_ (4: w x y z)
+  RS_WPP = 13,   // walk_plane_pose_ (7: p, q)
+  RS_OWPP = 20,  // origin_walk_plane_pose_ (7)
+  RS_MAN = 27,   // manual_pose_ (7)
+  RS_COUNT = 34
+};
+// optional IMU block (imu_posing || inclination_posing), relative to offS_imu
+enum : int { IMU_Q = 0 /*imu_pose_.rotation_ (4)*/, IMU_ABS = 4 /*absement (3)*/, IMU_VEL = 7 /*velocity err (3)*/,
+             IMU_INCL = 10 /*inclination_pose_ x,y (2)*/, IMU_COUNT = 12 };
+// optional auto-pose block (auto_posing), relative to offS_auto
+enum : int { AUTO_POSE = 0 /*auto_pose_ (7)*/, AUTO_COUNT = 7 };
+
+// per-leg storage planes, relative to offS_leg + leg * strideS_leg; joint planes first: q[D], qd[D]
+template <int D> struct LegS {
+  enum : int {
+    Q = 0, QD = D,
+    TIPVEL = 2 * D,      // LegStepper::current_tip_velocity_
+    SWO_P = 2 * D + 3,   // swing_origin_tip_position_
+    SWO_V = 2 * D + 6,   // swing_origin_tip_velocity_
+    STO_P = 2 * D + 9,   // stance_origin_tip_position_
+    DEF = 2 * D + 12,    // default_tip_pose_.position_
+    TGT = 2 * D + 15,    // target_tip_pose_.position_
+    STRIDE = 2 * D + 18, // stride_vector_
+    WP = 2 * D + 21,     // walk_plane_ (saved)
+    WPN = 2 * D + 24,    // walk_plane_normal_ (saved)
+    COUNT = 2 * D + 27
+  };
+};
+// optional admittance block appended to each leg (admittance_control), relative to offS_leg_adm within the leg
+enum : int { ADM_X = 0 /*admittance_state_ (2)*/, ADM_DELTA = 2 /*admittance_delta_ (3)*/,
+             ADM_FORCE = 5 /*tip_force_calculated_ (3)*/, ADM_COUNT = 8 };
+
+// double planes
+enum : int { RD_ODOMP = 0 /*odometry_ideal_.position_ (3)*/, RD_COUNT = 3 };
+enum : int { LD_TIP = 0 /*LegStepper::current_tip_pose_.position_ (3)*/, LD_COUNT = 3 };
+
+// int planes
+enum : int { RI_BITS = 0, RI_COUNT = 1 };
+enum : int { AI_FLAGS = 0 /*4 latch bits per AutoPoser*/, AI_PHASE = 1 /*pose_phase_*/, AI_COUNT = 2 };
+enum : int { LI_BITS = 0, LI_PROG = 1, LI_COUNT = 2 };
+
+// RI_BITS: walk_state[0:2) legs_at_correct_phase[2:6) legs_completed_first_step[6:10) return_to_default_attempted[10]
+//          pose_state[11:13) auto_posing_state[13:15)  status flags [16:32)
+// LI_BITS: phase[0:16) step_state[16:18) at_correct_phase[18] completed_first_step[19] negate_auto_pose[20]
+// LI_PROG: swing progress numerator (int16, -1 = "-1.0") | stance progress numerator (int16) << 16
+//          progress = numerator / swing_period (resp. stance_period): walk_controller.cpp:878-896 divides two ints
+//          converted to double, so keeping the numerator makes the value exact in every precision.
+
+enum : int { WALK_STARTING = 0, WALK_MOVING = 1, WALK_STOPPING = 2, WALK_STOPPED = 3 };   // parameters_and_states.h:103
+enum : int { STEP_SWING = 0, STEP_STANCE = 1, STEP_FORCE_STANCE = 2, STEP_FORCE_STOP = 3 }; // :116
+enum : int { POSE_POSING = 0, POSE_STOP_POSING = 1, POSE_COMPLETE = 2 };                    // :128
+
+}  // namespace shc

@@ -1,0 +1,254 @@
+"""ctypes binding of libshc_b200.so — the Python face of the C-ABI in include/shc_b200.h.
+
+PyTorch provides device buffers, streams and (in bench.py / multi-GPU runs) torch.distributed; every computation
+happens in the hand-written CUDA kernels behind the C-ABI.  There is no CPU or eager fallback: if the shared library
+is missing or no CUDA device is present, construction fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from .config import ShcConfig, ShcRobotState, ShcStartup
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libshc_b200.so")
+_lib = None
+
+PRECISION = {"f64": 0, "mixed": 1}
+OPT_STATUS_FLAGS = 1
+FLAG_IK_DEVIATION, FLAG_POSITION_CLAMP, FLAG_VELOCITY_CLAMP, FLAG_IMU_UNSTABLE = 1, 2, 4, 8
+
+
+class ShcError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libshc_b200.so (built in-tree by `python -m syropod_highlevel_controller_b200.build`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ShcError(f"{LIB_PATH} is missing: build the CUDA extension first "
+                           "(python -m syropod_highlevel_controller_b200.build); there is no fallback path")
+        L = C.CDLL(LIB_PATH)
+        fp, vp = C.POINTER(C.c_float), C.c_void_p
+        L.shc_create.argtypes = [C.POINTER(ShcConfig), C.POINTER(ShcStartup), C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.shc_destroy.argtypes = [vp]
+        L.shc_destroy.restype = None
+        L.shc_last_error.restype = C.c_char_p
+        L.shc_compute_startup.argtypes = [C.POINTER(ShcConfig), C.POINTER(ShcStartup)]
+        dp = C.POINTER(C.c_double)
+        L.shc_host_apply_ik.argtypes = [C.POINTER(ShcConfig), C.c_int, dp, dp, dp, C.c_int, dp, dp]
+        L.shc_get_startup.argtypes = [vp, C.POINTER(ShcStartup)]
+        L.shc_n_robots.argtypes = [vp]
+        L.shc_options.argtypes = [vp]
+        L.shc_set_options.argtypes = [vp, C.c_int]
+        L.shc_set_pose_reset_mode.argtypes = [vp, C.c_int]
+        L.shc_get_state.argtypes = [vp, C.POINTER(ShcRobotState), C.c_size_t]
+        L.shc_set_state.argtypes = [vp, C.POINTER(ShcRobotState), C.c_size_t]
+        L.shc_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.shc_step_host.argtypes = [vp, fp, fp, fp, fp, fp]
+        L.shc_rollout.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
+        L.shc_set_joint_efforts.argtypes = [vp, vp]
+        L.shc_stream.argtypes = [vp]
+        L.shc_stream.restype = vp
+        L.shc_synchronize.argtypes = [vp]
+        L.shc_status_flags_device.argtypes = [vp]
+        L.shc_status_flags_device.restype = vp
+        L.shc_get_status_flags.argtypes = [vp, C.POINTER(C.c_int)]
+        L.shc_apply_ik.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp]
+        for name in ("shc_sizeof_config", "shc_sizeof_startup", "shc_sizeof_robot_state"):
+            getattr(L, name).restype = C.c_size_t
+        for name in ("shc_bytes_per_step_device", "shc_bytes_per_step_algorithmic"):
+            getattr(L, name).restype = C.c_size_t
+            getattr(L, name).argtypes = [vp]
+        if L.shc_sizeof_config() != C.sizeof(ShcConfig) or L.shc_sizeof_startup() != C.sizeof(ShcStartup) or \
+                L.shc_sizeof_robot_state() != C.sizeof(ShcRobotState):
+            raise ShcError("ctypes struct layout does not match include/shc_config.h / shc_state.h")
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise ShcError(f"shc error {rc}: {lib().shc_last_error().decode()}")
+
+
+def compute_startup(cfg: ShcConfig) -> ShcStartup:
+    """Start-up constants (host arithmetic only, no GPU needed)."""
+    s = ShcStartup()
+    _check(lib().shc_compute_startup(C.byref(cfg), C.byref(s)))
+    return s
+
+
+def host_apply_ik(cfg: ShcConfig, leg: int, q, qd, desired, simulation: bool = True):
+    """One Leg::applyIK on the host with the kernels' own kinematics code (double).  Returns (q, qd, tip, result)."""
+    dp = C.POINTER(C.c_double)
+    q = np.array(q, dtype=np.float64)
+    qd = np.array(qd, dtype=np.float64)
+    des = np.ascontiguousarray(desired, dtype=np.float64)
+    tip = np.empty(3)
+    res = C.c_double()
+    _check(lib().shc_host_apply_ik(C.byref(cfg), leg, q.ctypes.data_as(dp), qd.ctypes.data_as(dp), des.ctypes.data_as(dp),
+                                   int(simulation), tip.ctypes.data_as(dp), C.byref(res)))
+    return q, qd, tip, res.value
+
+
+def _stream_handle(torch, device, stream):
+    """cudaStream_t for the C-ABI: torch's current stream unless given.  torch's default stream is the legacy default
+    stream, whose handle is 0 — spelled cudaStreamLegacy (0x1) here because NULL means "the engine's own stream"."""
+    st = torch.cuda.current_stream(device).cuda_stream if stream is None else stream
+    return C.c_void_p(st if st else 1)
+
+
+def _ptr(t) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Engine:
+    """N robots of one morphology resident on one B200.  One `step()` = one control cycle for every robot."""
+
+    def __init__(self, cfg: ShcConfig, n_robots: int, device: int = 0, precision: str = "mixed",
+                 startup: Optional[ShcStartup] = None):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise ShcError("no CUDA device: the SHC engine has no CPU fallback")
+        self.torch = torch
+        self.cfg = cfg
+        self.n = int(n_robots)
+        self.L, self.D = cfg.leg_count, cfg.joint_count
+        self.device = torch.device("cuda", device)
+        self.precision = precision
+        self._h = C.c_void_p()
+        _check(lib().shc_create(C.byref(cfg), C.byref(startup) if startup is not None else None, self.n, device,
+                                PRECISION[precision], C.byref(self._h)))
+        self.joints = torch.empty((self.n, self.L, self.D), dtype=torch.float32, device=self.device)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().shc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- introspection -------------------------------------------------------------------------------------------
+    def startup(self) -> ShcStartup:
+        s = ShcStartup()
+        _check(lib().shc_get_startup(self._h, C.byref(s)))
+        return s
+
+    @property
+    def bytes_per_step_device(self) -> int:
+        return lib().shc_bytes_per_step_device(self._h)
+
+    @property
+    def bytes_per_step_algorithmic(self) -> int:
+        return lib().shc_bytes_per_step_algorithmic(self._h)
+
+    def set_options(self, options: int):
+        _check(lib().shc_set_options(self._h, options))
+
+    def set_pose_reset_mode(self, mode: int):
+        _check(lib().shc_set_pose_reset_mode(self._h, mode))
+
+    def status_flags(self) -> np.ndarray:
+        """int32 [N] status words of the last cycle (needs OPT_STATUS_FLAGS)."""
+        out = np.empty(self.n, dtype=np.int32)
+        _check(lib().shc_get_status_flags(self._h, out.ctypes.data_as(C.POINTER(C.c_int))))
+        return out
+
+    # ---- state ------------------------------------------------------------------------------------------------------
+    def get_state(self):
+        arr = (ShcRobotState * self.n)()
+        _check(lib().shc_get_state(self._h, arr, self.n))
+        return arr
+
+    def set_state(self, arr):
+        _check(lib().shc_set_state(self._h, arr, self.n))
+
+    # ---- stepping --------------------------------------------------------------------------------------------------
+    def _f32(self, t, shape):
+        if t is None:
+            return None
+        torch = self.torch
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(np.ascontiguousarray(t, dtype=np.float32))
+        t = t.to(device=self.device, dtype=torch.float32).contiguous()
+        assert tuple(t.shape) == shape, (tuple(t.shape), shape)
+        return t
+
+    def step(self, cmd, imu=None, tip_force=None, manual=None, out=None, stream=None):
+        """One control cycle with device-resident inputs (torch CUDA tensors).  Asynchronous on `stream` (default:
+        torch's current stream).  Returns the [N, L, D] float32 joint-angle tensor."""
+        torch = self.torch
+        cmd = self._f32(cmd, (self.n, 3))
+        imu = self._f32(imu, (self.n, 10))
+        tip_force = self._f32(tip_force, (self.n, self.L, 3))
+        manual = self._f32(manual, (self.n, 6))
+        out = self.joints if out is None else out
+        _check(lib().shc_step(self._h, _ptr(cmd), _ptr(imu), _ptr(tip_force), _ptr(manual), _ptr(out),
+                              _stream_handle(torch, self.device, stream)))
+        self._keep = (cmd, imu, tip_force, manual)  # keep inputs alive until the launch has consumed them
+        return out
+
+    def step_host(self, cmd, imu=None, tip_force=None, manual=None) -> np.ndarray:
+        """One control cycle with HOST numpy buffers through the C-ABI (pinned staging, H2D, kernel, D2H, sync)."""
+        fp = C.POINTER(C.c_float)
+
+        def h(a, shape):
+            if a is None:
+                return None, None
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            assert a.shape == shape
+            return a, a.ctypes.data_as(fp)
+
+        cmd, pc = h(cmd, (self.n, 3))
+        imu, pi_ = h(imu, (self.n, 10))
+        tip_force, pf = h(tip_force, (self.n, self.L, 3))
+        manual, pm = h(manual, (self.n, 6))
+        out = np.empty((self.n, self.L, self.D), dtype=np.float32)
+        _check(lib().shc_step_host(self._h, pc, pi_, pf, pm, out.ctypes.data_as(fp)))
+        return out
+
+    def rollout(self, cmd_seq, imu_seq=None, force_seq=None, out=None, stream=None):
+        """k cycles with per-cycle device-resident inputs cmd_seq [k, N, 3]; one CUDA graph launch."""
+        torch = self.torch
+        k = int(cmd_seq.shape[0])
+        assert cmd_seq.is_cuda and cmd_seq.dtype == torch.float32 and cmd_seq.is_contiguous()
+        out = self.joints if out is None else out
+        _check(lib().shc_rollout(self._h, k, _ptr(cmd_seq), _ptr(imu_seq), _ptr(force_seq), _ptr(out),
+                                 _stream_handle(torch, self.device, stream)))
+        self._keep = (cmd_seq, imu_seq, force_seq)
+        return out
+
+    def set_joint_efforts(self, efforts):
+        efforts = self._f32(efforts, (self.n, self.L, self.D))
+        self._efforts = efforts
+        _check(lib().shc_set_joint_efforts(self._h, _ptr(efforts)))
+
+    def apply_ik(self, leg_id, q, qd, desired_tip, simulation: bool = True):
+        """Stand-alone batched Leg::applyIK in double.  Returns (q, qd, tip, ik_result) as torch tensors."""
+        torch = self.torch
+        leg_id = torch.as_tensor(leg_id, dtype=torch.int32, device=self.device).contiguous()
+        n = leg_id.numel()
+        q = torch.as_tensor(q, dtype=torch.float64, device=self.device).clone().contiguous()
+        qd = torch.as_tensor(qd, dtype=torch.float64, device=self.device).clone().contiguous()
+        des = torch.as_tensor(desired_tip, dtype=torch.float64, device=self.device).contiguous()
+        tip = torch.empty((n, 3), dtype=torch.float64, device=self.device)
+        res = torch.empty((n,), dtype=torch.float64, device=self.device)
+        _check(lib().shc_apply_ik(self._h, n, _ptr(leg_id), _ptr(q), _ptr(qd), _ptr(des), int(simulation), _ptr(tip),
+                                  _ptr(res), _stream_handle(torch, self.device, None)))
+        return q, qd, tip, res
+
+    def synchronize(self):
+        self.torch.cuda.synchronize(self.device)
+        _check(lib().shc_synchronize(self._h))
