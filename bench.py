@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py — control-cycle steps/sec of the batched SHC hot path on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 50 --warmup 5                    # this repo's CUDA path
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                        # N > 1, one rank per GPU over NCCL
+    python bench.py --impl reference --gpus 1 --steps 50 --warmup 5   # the reference path on the host cores
+
+One "step" = one full control cycle (pose + admittance + walk + Bezier tip trajectories + DLS IK) for
+every robot of the batch.  Workload: BASELINE.json configs[4]'s per-GPU shard — 131072 hexapods (6 legs x 3 DOF) per
+GPU, tripod gait, per-robot synthetic command streams; weak scaling (8 GPUs = the 1,048,576-robot job), one NCCL
+all-gather of the joint angles per cycle when N > 1.  State (272 MB per GPU in the f64 parity mode) is larger than
+the 126 MB L2, so every step streams it from HBM.
+
+Prints ONE JSON line (rank 0).  `value` = robots x steps / max-over-ranks device time with inputs resident in HBM;
+`e2e` = the same metric through the C-ABI host entry point (pinned staging, H2D of the commands, kernel, D2H of the
+joint angles every step); `roofline` = algorithmic bytes (2260 B per hexapod step) / kernel time against
+the measured HBM copy bandwidth; `cpu_baseline` = the CPU oracle (a port of the reference arithmetic; the reference
+itself needs ROS + Eigen + Boost and cannot be built) on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "control-cycle steps/sec (6-leg x 3-DOF IK+Bezier)"
+UNIT = "steps/s"
+ROBOTS_PER_GPU = 131072
+REF_SAMPLE_ROBOTS = 16384
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(precision):
+    """dram bytes per launch of the control-cycle kernel from the committed ncu --set full capture, if any."""
+    path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return d.get("traffic_bytes_per_launch", {}).get(precision)
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self._halt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._halt.wait(0.05)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline(cfg, threads, robots=8192, cycles=200):
+    """The CPU oracle on the host cores (bounded sample of the same workload)."""
+    from oracle import oracle_py as O
+    from syropod_highlevel_controller_b200.streams import CommandStream
+
+    ob = O.OracleBatch(cfg, robots)
+    cmd = CommandStream(robots).next().astype(np.float64)
+    ob.run(cmd, 20, threads)  # warm-up: leaves the STOPPED state
+    secs = ob.run(cmd, cycles, threads)
+    ob.close()
+    return {"value": robots * cycles / secs, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{robots} hexapods x {cycles} cycles, constant per-robot commands from the synthetic stream, "
+                      f"{threads} std::thread(s) over robots, g++ -O3 -march=native; a restatement with static storage "
+                      f"(upper bound on the real reference, which cannot be built without ROS/Eigen/Boost)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port) on the host cores, same metric / config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle_py as O
+    from syropod_highlevel_controller_b200.config import hexapod_config
+    from syropod_highlevel_controller_b200.streams import CommandStream
+
+    cfg = hexapod_config("tripod_gait")
+    threads = os.cpu_count() or 1
+    n = REF_SAMPLE_ROBOTS
+    ob = O.OracleBatch(cfg, n)
+    cs = CommandStream(n)
+    for _ in range(args.warmup):
+        ob.step(cs.next().astype(np.float64), threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ob.step(cs.next().astype(np.float64), threads=threads)
+    secs = time.perf_counter() - t0
+    value = n * args.steps / secs
+    sample = (f"each step = one control cycle over a {n}-robot sample of the {ROBOTS_PER_GPU}-robot per-GPU workload, "
+              f"CPU oracle (port of the reference arithmetic), {threads} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"config5 shard: {ROBOTS_PER_GPU} hexapods/GPU, tripod gait, default.yaml", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="f64", choices=["f64", "mixed"], help="f64 = parity mode (default)")
+    ap.add_argument("--robots-per-gpu", type=int, default=ROBOTS_PER_GPU)
+    ap.add_argument("--gait", default="tripod_gait")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from syropod_highlevel_controller_b200.config import hexapod_config
+    from syropod_highlevel_controller_b200.engine import Engine
+    from syropod_highlevel_controller_b200.parallel import JointGather, shard_robots
+    from syropod_highlevel_controller_b200.streams import CommandStream
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the SHC engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.robots_per_gpu
+    shard = shard_robots(n * world, rank, world)
+    cfg = hexapod_config(args.gait)
+    L, D = cfg.leg_count, cfg.joint_count
+    K, W = args.steps, args.warmup
+
+    eng = Engine(cfg, n, device=local_rank, precision=args.precision)
+    # synthetic per-robot command streams, resident in HBM before the timed region
+    cs = CommandStream(n, robot_offset=shard.offset)
+    pre = 300  # untimed pre-roll so that the batch is in its steady mix of walk states (STARTING/MOVING/STOPPING/STOPPED)
+    cmd_host = np.stack([cs.next() for _ in range(pre + W + K)])
+    cmd_dev = torch.from_numpy(cmd_host).to(dev)
+    gather = JointGather(shard, L, D, dev) if world > 1 else None
+
+    def step(i):
+        if gather is None:
+            eng.step(cmd_dev[i])
+        else:
+            eng.step(cmd_dev[i], out=gather.next_local_buffer())
+            gather.gather()
+
+    for i in range(pre + W):
+        step(i)
+    if gather is not None:
+        gather.wait()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for i in range(pre + W, pre + W + K):
+        step(i)
+    if gather is not None:
+        gather.wait()
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / K
+    value = n * world * K / (ms_total * 1e-3)
+
+    # kernel-only duration (no all-gather in the region) for the roofline: one launch per step on this stream
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    k0.record()
+    for i in range(pre + W, pre + W + K):
+        eng.step(cmd_dev[i])
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / K
+    peak, peak_src = measured_peak()
+    b_alg = eng.bytes_per_step_algorithmic
+    achieved = n * b_alg / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(args.precision), "kernel": "control_cycle_kernel", "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_step": b_alg, "device_bytes_per_step": eng.bytes_per_step_device,
+                "device_bytes_GBps": n * eng.bytes_per_step_device / (kernel_ms * 1e-3) / 1e9, "peak_source": peak_src}
+
+    # end to end through the C-ABI host entry point: H2D of the commands and D2H of the joint angles every step
+    e2e_steps = max(3, min(K, 20))
+    host_cmd = cmd_host[pre + W: pre + W + e2e_steps]
+    eng.step_host(host_cmd[0])
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        eng.step_host(host_cmd[i])
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = {"value": n * world * e2e_steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": n * 3 * 4,
+           "d2h_bytes_per_step": n * L * D * 4, "steps": e2e_steps,
+           "api": "shc_step_host (C-ABI, host buffers; pinned staging + cudaMemcpyAsync + kernel + D2H + stream sync)"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"config5 shard: {n} hexapods/GPU (6 legs x 3 DOF), {args.gait}, default.yaml parameters, "
+                                   f"per-robot splitmix64 command streams" + ("; NCCL all-gather of joint angles per cycle" if world > 1 else ""),
+                       "robots_per_gpu": n, "robots_total": n * world, "precision": args.precision,
+                       "l2": f"state {n * (eng.bytes_per_step_device - 84) // 2 / 1e6:.0f} MB per GPU > 126 MB L2 (inputs larger than L2, no flush)",
+                       "pre_roll_cycles": pre},
+            "gpu_launches": K, "e2e": e2e, "roofline": roofline, "clocks": clocks}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline(cfg, os.cpu_count() or 1)
+        except Exception as ex:  # the baseline is a reported number, never a reason to lose the GPU measurement
+            line["cpu_baseline"] = {"error": str(ex)}
+    if rank == 0:
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -40,6 +40,8 @@ template <class R> struct RealConsts {
   R lambda2;           // DLS_COEFFICIENT^2 (model.h:19)
   R limits[4][SHC_N_BEARINGS];  // max linear speed, angular speed, linear accel, angular accel (walk_controller.cpp:231)
   R swing_progress_scaler;      // max(1, swing_phase / phase_offset) (pose_controller.cpp:1102)
+  // cos/sin of the limit-map bucket edges (walk_controller.cpp:426-431): 44.5, 89.5, 134.5, 179.5, 0.5, 45.5, 90.5, 135.5 deg
+  R sec_cos[8], sec_sin[8];
   R inv_swing_period, inv_stance_period;
   R max_translation[3], max_rotation[3], max_translation_velocity, max_rotation_velocity;
   R pid_p, pid_i, pid_d;

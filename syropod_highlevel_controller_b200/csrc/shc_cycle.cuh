@@ -39,6 +39,14 @@ struct StepIO {
   int pose_reset_mode;
 };
 
+// TMA bulk prefetch into L2 (cp.async.bulk.prefetch.L2): one lane asks for a whole contiguous chunk of a tile's planes,
+// so the demand loads that follow find their lines in L2 instead of paying the HBM latency inside the dependent chain.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#endif
+}
+
 template <class S> struct Planes {
   S* s;
   double* d;
@@ -251,30 +259,30 @@ template <class P, int D> struct Cycle {
   using K = typename P::K;
   using LS = LegS<D>;
 
-  static __device__ __forceinline__ V3<K> ld3K(const S* sp, size_t np, int plane, int r) {
-    return {K(sp[(size_t)plane * np + r]), K(sp[(size_t)(plane + 1) * np + r]), K(sp[(size_t)(plane + 2) * np + r])};
+  static __device__ __forceinline__ V3<K> ld3K(const S* sp, int plane) {
+    return {K(sp[(plane) * 32]), K(sp[(plane + 1) * 32]), K(sp[(plane + 2) * 32])};
   }
-  static __device__ __forceinline__ V3<T> ld3T(const S* sp, size_t np, int plane, int r) {
-    return {T(sp[(size_t)plane * np + r]), T(sp[(size_t)(plane + 1) * np + r]), T(sp[(size_t)(plane + 2) * np + r])};
+  static __device__ __forceinline__ V3<T> ld3T(const S* sp, int plane) {
+    return {T(sp[(plane) * 32]), T(sp[(plane + 1) * 32]), T(sp[(plane + 2) * 32])};
   }
-  template <class R> static __device__ __forceinline__ void st3(S* sp, size_t np, int plane, int r, V3<R> v) {
-    sp[(size_t)plane * np + r] = S(v.x);
-    sp[(size_t)(plane + 1) * np + r] = S(v.y);
-    sp[(size_t)(plane + 2) * np + r] = S(v.z);
+  template <class R> static __device__ __forceinline__ void st3(S* sp, int plane, V3<R> v) {
+    sp[(plane) * 32] = S(v.x);
+    sp[(plane + 1) * 32] = S(v.y);
+    sp[(plane + 2) * 32] = S(v.z);
   }
-  static __device__ __forceinline__ PoseT<K> ldPose(const S* sp, size_t np, int plane, int r) {
+  static __device__ __forceinline__ PoseT<K> ldPose(const S* sp, int plane) {
     PoseT<K> p;
-    p.p = ld3K(sp, np, plane, r);
-    p.q = {K(sp[(size_t)(plane + 3) * np + r]), K(sp[(size_t)(plane + 4) * np + r]), K(sp[(size_t)(plane + 5) * np + r]),
-           K(sp[(size_t)(plane + 6) * np + r])};
+    p.p = ld3K(sp, plane);
+    p.q = {K(sp[(plane + 3) * 32]), K(sp[(plane + 4) * 32]), K(sp[(plane + 5) * 32]),
+           K(sp[(plane + 6) * 32])};
     return p;
   }
-  static __device__ __forceinline__ void stPose(S* sp, size_t np, int plane, int r, PoseT<K> p) {
-    st3(sp, np, plane, r, p.p);
-    sp[(size_t)(plane + 3) * np + r] = S(p.q.w);
-    sp[(size_t)(plane + 4) * np + r] = S(p.q.x);
-    sp[(size_t)(plane + 5) * np + r] = S(p.q.y);
-    sp[(size_t)(plane + 6) * np + r] = S(p.q.z);
+  static __device__ __forceinline__ void stPose(S* sp, int plane, PoseT<K> p) {
+    st3(sp, plane, p.p);
+    sp[(plane + 3) * 32] = S(p.q.w);
+    sp[(plane + 4) * 32] = S(p.q.x);
+    sp[(plane + 5) * 32] = S(p.q.y);
+    sp[(plane + 6) * 32] = S(p.q.z);
   }
 
   // PoseController::updateManualPose (pose_controller.cpp:863-1003); default_pose_ is the identity (no manually
@@ -344,11 +352,15 @@ template <class P, int D> struct Cycle {
     const RealConsts<T>& ct = ConstSel<T>::get(c);
     const RealConsts<K>& ck = ConstSel<K>::get(c);
     const RealConsts<double>& cd = c.d;
-    const size_t np = (size_t)ci.n_pad;
     const int L = ci.L;
-    S* sp = pl.s;
-    double* dp = pl.d;
-    int* ip = pl.i;
+    // tile-major planes [tile][plane][32 lanes]: every field of this robot is at a compile-time offset from these bases
+    const size_t tile = (size_t)(r >> 5);
+    const int lane = r & 31;
+    S* __restrict__ sp = pl.s + tile * (size_t)(ci.nS * 32) + lane;
+    double* __restrict__ dp = pl.d + tile * (size_t)(ci.nD * 32) + lane;
+    int* __restrict__ ip = pl.i + tile * (size_t)(ci.nI * 32) + lane;
+    const unsigned leg_chunk_bytes = (unsigned)(ci.strideS_leg * 32 * sizeof(S));
+    if (lane == 0) l2_prefetch_bulk(sp + ci.offS_leg * 32, leg_chunk_bytes);  // leg 0's planes, needed after the pose stage
 
     // ---- inputs: bodyVelocityInputCallback (state_controller.cpp:1127-1136) --------------------------------------
     double vin_x = (double)io.cmd[3 * (size_t)r + 0] * cd.body_velocity_scaler;
@@ -372,7 +384,7 @@ template <class P, int D> struct Cycle {
     // Model::getImuData (model.h:132): undefined orientation reads as identity
     Q4<K> imu_q = (imu_raw.w == K(0) && imu_raw.x == K(0) && imu_raw.y == K(0) && imu_raw.z == K(0)) ? qidentity<K>() : imu_raw;
 
-    int rbits = ip[(size_t)RI_BITS * np + r];
+    int rbits = ip[(RI_BITS) * 32];
     int walk_state = rbits & 3;
     int legs_at_correct = (rbits >> 2) & 15;
     int legs_completed = (rbits >> 6) & 15;
@@ -387,7 +399,7 @@ template <class P, int D> struct Cycle {
     double c_in = 0.0;
     int ref_leg = -1;
     for (int l = 0; l < L; ++l) {
-      int prog = ip[(size_t)(ci.offI_leg + l * ci.strideI_leg + LI_PROG) * np + r];
+      int prog = ip[(ci.offI_leg + l * ci.strideI_leg + LI_PROG) * 32];
       int swing_num = (int)(short)(prog & 0xffff);
       double swing_progress = swing_num < 0 ? -1.0 : (double)swing_num / (double)ci.swing_period;
       swing_progress *= cd.swing_progress_scaler;
@@ -400,28 +412,45 @@ template <class P, int D> struct Cycle {
     V3<K> wpn_ref{K(0), K(0), K(1)};
     if (ref_leg >= 0) {
       int base = ci.offS_leg + ref_leg * ci.strideS_leg;
-      wp_z = K(sp[(size_t)(base + LS::WP + 2) * np + r]);
-      wpn_ref = ld3K(sp, np, base + LS::WPN, r);
+      wp_z = K(sp[(base + LS::WP + 2) * 32]);
+      wpn_ref = ld3K(sp, base + LS::WPN);
     }
-    PoseT<K> new_wpp;
-    new_wpp.q = correct_rotation(from_two_vectors(V3<K>{K(0), K(0), K(1)}, wpn_ref), qidentity<K>());
-    new_wpp.p = qrot(new_wpp.q, V3<K>{K(0), K(0), ck.body_clearance});
-    new_wpp.p.z += wp_z;
-    PoseT<K> owpp = ldPose(sp, np, RS_OWPP, r);
-    PoseT<K> wpp = pose_interpolate(owpp, K(c_in), new_wpp);
-    stPose(sp, np, RS_WPP, r, wpp);
-    if (c_in == 1.0) stPose(sp, np, RS_OWPP, r, wpp);
+    PoseT<K> owpp = ldPose(sp, RS_OWPP);
+    PoseT<K> wpp = owpp;
+    if (c_in != 0.0) {
+      PoseT<K> new_wpp;
+      if (wpn_ref.x == K(0) && wpn_ref.y == K(0) && wpn_ref.z == K(1)) {
+        // FromTwoVectors(z, z) is exactly the identity and rotating by it is exact: same bits as the general path
+        new_wpp.q = qidentity<K>();
+        new_wpp.p = V3<K>{K(0), K(0), ck.body_clearance};
+      } else {
+        new_wpp.q = correct_rotation(from_two_vectors(V3<K>{K(0), K(0), K(1)}, wpn_ref), qidentity<K>());
+        new_wpp.p = qrot(new_wpp.q, V3<K>{K(0), K(0), ck.body_clearance});
+      }
+      new_wpp.p.z += wp_z;
+      wpp = pose_interpolate(owpp, K(c_in), new_wpp);
+      stPose(sp, RS_WPP, wpp);
+      if (c_in == 1.0) stPose(sp, RS_OWPP, wpp);
+    } else {
+      // c = 0: interpolate(origin, 0, new) returns the origin pose bit for bit (scale0 = 1, scale1 = 0)
+      stPose(sp, RS_WPP, wpp);
+    }
 
     PoseT<K> cur_pose = pose_add(pose_identity<K>(), wpp);
     PoseT<K> man = pose_identity<K>();
     if (ci.manual_posing) {
-      man = ldPose(sp, np, RS_MAN, r);
-      man = manual_pose_update(ck, man, io.manual ? io.manual + 6 * (size_t)r : nullptr, io.pose_reset_mode);
-      stPose(sp, np, RS_MAN, r, man);
-      cur_pose = pose_add(cur_pose, man);
+      man = ldPose(sp, RS_MAN);
+      const bool man_identity = man.p.x == K(0) && man.p.y == K(0) && man.p.z == K(0) && man.q.w == K(1) &&
+                                man.q.x == K(0) && man.q.y == K(0) && man.q.z == K(0);
+      if (!(man_identity && io.manual == nullptr && io.pose_reset_mode == 0)) {
+        // (with an identity pose, no input and no reset the update returns the identity again, exactly)
+        man = manual_pose_update(ck, man, io.manual ? io.manual + 6 * (size_t)r : nullptr, io.pose_reset_mode);
+        stPose(sp, RS_MAN, man);
+        cur_pose = pose_add(cur_pose, man);
+      }
     }
     PoseT<K> auto_pose = pose_identity<K>();
-    if (ci.auto_posing) auto_pose = ldPose(sp, np, ci.offS_auto + AUTO_POSE, r);
+    if (ci.auto_posing) auto_pose = ldPose(sp, ci.offS_auto + AUTO_POSE);
     if (ci.inclination_posing) {  // updateInclinationPose (:1240)
       Q4<K> comb = qnormalized(qmul(man.q, auto_pose.q));
       Q4<K> removed = qnormalized(qmul(imu_q, qinverse(comb)));
@@ -430,8 +459,8 @@ template <class P, int D> struct Cycle {
       K lat = ck.body_clearance * tan_(e.x);
       lon = clamp_(lon, -ck.max_translation[0], ck.max_translation[0]);
       lat = clamp_(lat, -ck.max_translation[1], ck.max_translation[1]);
-      sp[(size_t)(ci.offS_imu + IMU_INCL) * np + r] = S(lon);
-      sp[(size_t)(ci.offS_imu + IMU_INCL + 1) * np + r] = S(lat);
+      sp[(ci.offS_imu + IMU_INCL) * 32] = S(lon);
+      sp[(ci.offS_imu + IMU_INCL + 1) * 32] = S(lat);
       PoseT<K> incl = pose_identity<K>();
       incl.p = {lon, lat, K(0)};
       cur_pose = pose_add(cur_pose, incl);
@@ -445,44 +474,44 @@ template <class P, int D> struct Cycle {
       V3<K> pe = quat_to_euler(rot_err, false);
       pe.z = K(0);
       const int b = ci.offS_imu;
-      Q4<K> imu_pose_q{K(sp[(size_t)(b + IMU_Q) * np + r]), K(sp[(size_t)(b + IMU_Q + 1) * np + r]),
-                       K(sp[(size_t)(b + IMU_Q + 2) * np + r]), K(sp[(size_t)(b + IMU_Q + 3) * np + r])};
+      Q4<K> imu_pose_q{K(sp[(b + IMU_Q) * 32]), K(sp[(b + IMU_Q + 1) * 32]),
+                       K(sp[(b + IMU_Q + 2) * 32]), K(sp[(b + IMU_Q + 3) * 32])};
       // IMU_POSING_DEADBAND is 0.0: "norm < 0" never holds, the PID always runs (pose_controller.h:25)
-      V3<K> abs_err = ld3K(sp, np, b + IMU_ABS, r) + pe * ck.dt;
-      V3<K> vel_err = (-gyro) * K(0.15) + ld3K(sp, np, b + IMU_VEL, r) * (K(1) - K(0.15));
-      st3(sp, np, b + IMU_ABS, r, abs_err);
-      st3(sp, np, b + IMU_VEL, r, vel_err);
+      V3<K> abs_err = ld3K(sp, b + IMU_ABS) + pe * ck.dt;
+      V3<K> vel_err = (-gyro) * K(0.15) + ld3K(sp, b + IMU_VEL) * (K(1) - K(0.15));
+      st3(sp, b + IMU_ABS, abs_err);
+      st3(sp, b + IMU_VEL, vel_err);
       V3<K> corr = -(vel_err * ck.pid_d + pe * ck.pid_p + abs_err * ck.pid_i);
       corr.x = clamp_(corr.x, -ck.max_rotation[0], ck.max_rotation[0]);
       corr.y = clamp_(corr.y, -ck.max_rotation[1], ck.max_rotation[1]);
       corr.z = quat_to_euler(target_rotation, false).z;
       if (norm(corr) > K(100)) status |= 8;
       imu_pose_q = correct_rotation(euler_to_quat(corr, false), target_rotation);
-      sp[(size_t)(b + IMU_Q) * np + r] = S(imu_pose_q.w);
-      sp[(size_t)(b + IMU_Q + 1) * np + r] = S(imu_pose_q.x);
-      sp[(size_t)(b + IMU_Q + 2) * np + r] = S(imu_pose_q.y);
-      sp[(size_t)(b + IMU_Q + 3) * np + r] = S(imu_pose_q.z);
+      sp[(b + IMU_Q) * 32] = S(imu_pose_q.w);
+      sp[(b + IMU_Q + 1) * 32] = S(imu_pose_q.x);
+      sp[(b + IMU_Q + 2) * 32] = S(imu_pose_q.y);
+      sp[(b + IMU_Q + 3) * 32] = S(imu_pose_q.z);
       PoseT<K> imu_pose = pose_identity<K>();
       imu_pose.q = imu_pose_q;
       cur_pose = pose_add(cur_pose, imu_pose);
     } else if (ci.auto_posing) {  // updateAutoPose (:1134)
       run_auto = true;
       const int rb = ci.offI_leg + ci.auto_ref_leg * ci.strideI_leg;
-      int ref_bits = ip[(size_t)(rb + LI_BITS) * np + r];
+      int ref_bits = ip[(rb + LI_BITS) * 32];
       // zero_body_velocity of the reference leg: stride_vector_.norm() == 0
-      V3<T> ref_stride = ld3T(sp, np, ci.offS_leg + ci.auto_ref_leg * ci.strideS_leg + LS::STRIDE, r);
+      V3<T> ref_stride = ld3T(sp, ci.offS_leg + ci.auto_ref_leg * ci.strideS_leg + LS::STRIDE);
       bool zero_body_velocity = (ref_stride.x * ref_stride.x + ref_stride.y * ref_stride.y + ref_stride.z * ref_stride.z) == T(0);
       if (walk_state == WALK_STARTING || walk_state == WALK_MOVING) auto_state = POSE_POSING;
       else if ((zero_body_velocity && walk_state == WALK_STOPPING) || walk_state == WALK_STOPPED) auto_state = POSE_STOP_POSING;
-      int pose_phase = ip[(size_t)(ci.offI_auto + AI_PHASE) * np + r];
+      int pose_phase = ip[(ci.offI_auto + AI_PHASE) * 32];
       if (ci.pose_sync) {
         master_phase = ref_bits & 0xffff;
       } else {
         master_phase = pose_phase;
         pose_phase = (pose_phase + 1) % ci.pose_phase_length;
-        ip[(size_t)(ci.offI_auto + AI_PHASE) * np + r] = pose_phase;
+        ip[(ci.offI_auto + AI_PHASE) * 32] = pose_phase;
       }
-      int pflags = ip[(size_t)(ci.offI_auto + AI_FLAGS) * np + r];
+      int pflags = ip[(ci.offI_auto + AI_FLAGS) * 32];
       auto_pose = pose_identity<K>();
       int complete = 0;
       V3<K> grav_dir{K(0), K(0), K(-1)};
@@ -533,8 +562,8 @@ template <class P, int D> struct Cycle {
         pflags = (pflags & ~(15 << (4 * a))) | (f << (4 * a));
       }
       if (complete == ci.n_posers) auto_state = POSE_COMPLETE;
-      ip[(size_t)(ci.offI_auto + AI_FLAGS) * np + r] = pflags;
-      stPose(sp, np, ci.offS_auto + AUTO_POSE, r, auto_pose);
+      ip[(ci.offI_auto + AI_FLAGS) * 32] = pflags;
+      stPose(sp, ci.offS_auto + AUTO_POSE, auto_pose);
       cur_pose = pose_add(cur_pose, auto_pose);
     }
     const int pose_state = auto_state;  // walker_->setPoseState(poser_->getAutoPoseState())
@@ -545,10 +574,25 @@ template <class P, int D> struct Cycle {
     double lim[4] = {2147483647.0, 2147483647.0, 2147483647.0, 2147483647.0};
     for (int l = 0; l < L; ++l) {  // getLimit (:414): the four calls share the bearing of each leg
       const int db = ci.offD_leg + l * ci.strideD_leg + LD_TIP;
-      double tx = dp[(size_t)db * np + r], ty = dp[(size_t)(db + 1) * np + r];
+      double tx = dp[(db) * 32], ty = dp[(db + 1) * 32];
       double sx = vin_x + win * (-ty), sy = vin_y + win * tx;
-      int bearing = imod(round_to_int((atan2(sy, sx) / (2.0 * kPi)) * 360.0), 360);
-      int bucket = bearing / 45;  // int/int interpolation input floors to the 45-degree bucket (trap 1)
+      // bucket = mod(roundToInt(deg(atan2(sy, sx))), 360) / 45 (int / int floors to the 45-degree bucket, trap 1),
+      // decided without atan2: the rounding makes the bucket edges sit at 44.5, 89.5, 134.5, 179.5 degrees on the upper
+      // half plane and at -0.5, -45.5, -90.5, -135.5 on the lower one; theta >= phi <=> sin(theta - phi) >= 0.
+      int bucket;
+      if (sx == 0.0 && sy == 0.0) {
+        bucket = 0;
+      } else if (sy >= 0.0) {
+        bucket = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bucket += (sy * cd.sec_cos[k] - sx * cd.sec_sin[k] >= 0.0) ? 1 : 0;
+      } else {
+        bucket = 4;
+        if (sy * cd.sec_cos[4] + sx * cd.sec_sin[4] > 0.0) bucket = 0;
+        else if (sy * cd.sec_cos[5] + sx * cd.sec_sin[5] > 0.0) bucket = 7;
+        else if (sy * cd.sec_cos[6] + sx * cd.sec_sin[6] > 0.0) bucket = 6;
+        else if (sy * cd.sec_cos[7] + sx * cd.sec_sin[7] > 0.0) bucket = 5;
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) lim[k] = fmin(lim[k], cd.limits[k][bucket]);
     }
@@ -582,7 +626,7 @@ template <class P, int D> struct Cycle {
     }
     const bool has_cmd = (in_norm != 0.0) || (win != 0.0);
 
-    T dvx = T(sp[(size_t)(RS_VEL)*np + r]), dvy = T(sp[(size_t)(RS_VEL + 1) * np + r]), dw = T(sp[(size_t)RS_ANGVEL * np + r]);
+    T dvx = T(sp[(RS_VEL) * 32]), dvy = T(sp[(RS_VEL + 1) * 32]), dw = T(sp[(RS_ANGVEL) * 32]);
     {
       T ax = nvx - dvx, ay = nvy - dvy;
       T an = sqrt_(ax * ax + ay * ay);
@@ -604,9 +648,9 @@ template <class P, int D> struct Cycle {
       if (abs_(aa) < max_ang_acc * ct.dt) dw += aa;
       else dw += sign_(aa) * max_ang_acc * ct.dt;
     }
-    sp[(size_t)(RS_VEL)*np + r] = S(dvx);
-    sp[(size_t)(RS_VEL + 1) * np + r] = S(dvy);
-    sp[(size_t)RS_ANGVEL * np + r] = S(dw);
+    sp[(RS_VEL) * 32] = S(dvx);
+    sp[(RS_VEL + 1) * 32] = S(dvy);
+    sp[(RS_ANGVEL) * 32] = S(dw);
 
     bool starting_now = false;  // STOPPED -> STARTING returns before any tip update (trap 7)
     if (walk_state == WALK_STOPPED && has_cmd) {
@@ -623,8 +667,8 @@ template <class P, int D> struct Cycle {
       walk_state = WALK_STOPPED;
     }
 
-    const V3<T> walker_wp = ld3T(sp, np, RS_WPL, r);
-    const V3<T> walker_wpn = ld3T(sp, np, RS_WPN, r);
+    const V3<T> walker_wp = ld3T(sp, RS_WPL);
+    const V3<T> walker_wpn = ld3T(sp, RS_WPN);
 
     // walk-plane least squares accumulators (updateWalkPlane :748): A = [x y 1], b = z over the default tips
     double sxx = 0, sxy = 0, sx1 = 0, syy = 0, sy1 = 0, sxz = 0, syz = 0, sz1 = 0;
@@ -634,11 +678,13 @@ template <class P, int D> struct Cycle {
     // =================================================================================================================
 #pragma unroll 1
     for (int l = 0; l < L; ++l) {
-      const int sb = ci.offS_leg + l * ci.strideS_leg;
-      const int db = ci.offD_leg + l * ci.strideD_leg;
-      const int ib = ci.offI_leg + l * ci.strideI_leg;
-      int bits = ip[(size_t)(ib + LI_BITS) * np + r];
-      int prog = ip[(size_t)(ib + LI_PROG) * np + r];
+      // per-leg plane bases: every field of this leg is at an immediate offset from these pointers
+      S* __restrict__ sl = sp + (ci.offS_leg + l * ci.strideS_leg) * 32;
+      double* __restrict__ dl = dp + (ci.offD_leg + l * ci.strideD_leg) * 32;
+      int* __restrict__ il = ip + (ci.offI_leg + l * ci.strideI_leg) * 32;
+      if (lane == 0 && l + 1 < L) l2_prefetch_bulk(sl - lane + ci.strideS_leg * 32, leg_chunk_bytes);  // next leg -> L2
+      int bits = il[(LI_BITS) * 32];
+      int prog = il[(LI_PROG) * 32];
       int phase = bits & 0xffff;
       int step_state = (bits >> 16) & 3;
       bool at_correct = (bits >> 18) & 1;
@@ -647,9 +693,9 @@ template <class P, int D> struct Cycle {
       int swing_num = (int)(short)(prog & 0xffff);
       int stance_num = (int)(short)((prog >> 16) & 0xffff);
 
-      double tipx = dp[(size_t)(db + LD_TIP) * np + r];
-      double tipy = dp[(size_t)(db + LD_TIP + 1) * np + r];
-      double tipz = dp[(size_t)(db + LD_TIP + 2) * np + r];
+      double tipx = dl[(LD_TIP) * 32];
+      double tipy = dl[(LD_TIP + 1) * 32];
+      double tipz = dl[(LD_TIP + 2) * 32];
 
       // LegPoser::updateAutoPose (pose_controller.cpp:1716) — uses the step state of the previous cycle
       PoseT<K> leg_auto = auto_pose;
@@ -682,7 +728,7 @@ template <class P, int D> struct Cycle {
         leg_auto = pose_identity<K>();  // LegPoser::auto_pose_ is only refreshed by updateAutoPose; IMU posing keeps identity
       }
 
-      V3<T> def = ld3T(sp, np, sb + LS::DEF, r);
+      V3<T> def = ld3T(sl, LS::DEF);
 
       if (starting_now) {
         // walk_controller.cpp:535-545
@@ -693,8 +739,8 @@ template <class P, int D> struct Cycle {
         if (phase >= ci.swing_start && phase < ci.swing_end) step_state = STEP_SWING;
         else if (phase < ci.stance_end || phase >= ci.stance_start) step_state = STEP_STANCE;
       } else {
-        V3<T> stride = ld3T(sp, np, sb + LS::STRIDE, r);
-        V3<T> tgt = ld3T(sp, np, sb + LS::TGT, r);
+        V3<T> stride = ld3T(sl, LS::STRIDE);
+        V3<T> tgt = ld3T(sl, LS::TGT);
         // ---- walk state machine for this leg (walk_controller.cpp:573-632) ----
         if (walk_state == WALK_STARTING) {
           if (legs_at_correct == L) {
@@ -716,7 +762,7 @@ template <class P, int D> struct Cycle {
         } else if (walk_state == WALK_STOPPING) {
           bool zero_body_velocity = (stride.x * stride.x + stride.y * stride.y + stride.z * stride.z) == T(0);
           if (zero_body_velocity && !at_correct && phase == ci.swing_end) {
-            V3<double> wpn_l = cvt<double>(ld3T(sp, np, sb + LS::WPN, r));
+            V3<double> wpn_l = cvt<double>(ld3T(sl, LS::WPN));
             V3<double> err{tipx - (double)tgt.x, tipy - (double)tgt.y, tipz - (double)tgt.z};
             err = rejection(err, wpn_l);
             bool at_target = norm(err) < 0.01;  // TIP_TOLERANCE (pose_controller.h:19)
@@ -725,10 +771,10 @@ template <class P, int D> struct Cycle {
               // LegStepper::updateDefaultTipPosition (:984), no external default
               V3<K> idt{ck.identity_x[l], ck.identity_y[l] + ck.span_dy[l], K(0)};
               idt = pose_transform(wpp, idt);  // Model::default_pose_ = walk_plane_pose_ (pose_controller.cpp:819)
-              V3<K> sto = ld3K(sp, np, sb + LS::STO_P, r);
+              V3<K> sto = ld3K(sl, LS::STO_P);
               V3<K> proj = projection(sto - idt, cvt<K>(wpn_l));
               def = cvt<T>(idt + proj);
-              st3(sp, np, sb + LS::DEF, r, def);
+              st3(sl, LS::DEF, def);
               step_state = STEP_FORCE_STOP;
               at_correct = true;
               legs_at_correct++;
@@ -745,13 +791,13 @@ template <class P, int D> struct Cycle {
         const bool standard = (step_state == STEP_SWING || completed);
         const T stance_dt = standard ? ct.stance_dt_std : ct.stance_dt_mod[l];
         tgt = def + stride * T(0.5);  // uses the previous cycle's stride (trap 5)
-        st3(sp, np, sb + LS::TGT, r, tgt);
+        st3(sl, LS::TGT, tgt);
         if (step_state != STEP_FORCE_STOP) {
           // updateStride (:921)
           stride = V3<T>{dvx - dw * T(tipy), dvy + dw * T(tipx), T(0)} * ct.stride_scale;
-          st3(sp, np, sb + LS::STRIDE, r, stride);
-          st3(sp, np, sb + LS::WP, r, walker_wp);
-          st3(sp, np, sb + LS::WPN, r, walker_wpn);
+          st3(sl, LS::STRIDE, stride);
+          st3(sl, LS::WP, walker_wp);
+          st3(sl, LS::WPN, walker_wpn);
           V3<T> delta;
           if (step_state == STEP_SWING) {
             int iteration = phase - ci.swing_start + 1;
@@ -759,12 +805,12 @@ template <class P, int D> struct Cycle {
             V3<T> swo_p, swo_v;
             if (iteration == 1) {
               swo_p = V3<T>{T(tipx), T(tipy), T(tipz)};
-              swo_v = ld3T(sp, np, sb + LS::TIPVEL, r);
-              st3(sp, np, sb + LS::SWO_P, r, swo_p);
-              st3(sp, np, sb + LS::SWO_V, r, swo_v);
+              swo_v = ld3T(sl, LS::TIPVEL);
+              st3(sl, LS::SWO_P, swo_p);
+              st3(sl, LS::SWO_V, swo_v);
             } else {
-              swo_p = ld3T(sp, np, sb + LS::SWO_P, r);
-              swo_v = ld3T(sp, np, sb + LS::SWO_V, r);
+              swo_p = ld3T(sl, LS::SWO_P);
+              swo_v = ld3T(sl, LS::SWO_V);
             }
             // Control nodes relative to the swing origin (generatePrimary/SecondarySwingControlNodes :1238-1291);
             // only node differences enter quarticBezierDot, so the origin cancels.
@@ -803,7 +849,7 @@ template <class P, int D> struct Cycle {
           } else {  // STANCE / FORCE_STANCE
             int mod_start = standard ? ci.stance_start : ci.phase_offset[l];
             int iteration = imod(phase + (ci.period - mod_start), ci.period) + 1;
-            if (iteration == 1) st3(sp, np, sb + LS::STO_P, r, V3<T>{T(tipx), T(tipy), T(tipz)});
+            if (iteration == 1) st3(sl, LS::STO_P, V3<T>{T(tipx), T(tipy), T(tipz)});
             T scaler = standard ? T(1) : ct.stride_scaler_mod[l];
             V3<T> sep = -stride * scaler * T(0.25);
             // stance nodes are origin + k*sep (generateStanceControlNodes :1295): all four node differences are sep
@@ -815,10 +861,10 @@ template <class P, int D> struct Cycle {
           tipx += (double)delta.x;
           tipy += (double)delta.y;
           tipz += (double)delta.z;
-          dp[(size_t)(db + LD_TIP) * np + r] = tipx;
-          dp[(size_t)(db + LD_TIP + 1) * np + r] = tipy;
-          dp[(size_t)(db + LD_TIP + 2) * np + r] = tipz;
-          st3(sp, np, sb + LS::TIPVEL, r, delta * ct.inv_dt);
+          dl[(LD_TIP) * 32] = tipx;
+          dl[(LD_TIP + 1) * 32] = tipy;
+          dl[(LD_TIP + 2) * 32] = tipz;
+          st3(sl, LS::TIPVEL, delta * ct.inv_dt);
         }
 
         // ---- LegStepper::iteratePhase (:871) + updateStepState (:901) ----
@@ -841,8 +887,8 @@ template <class P, int D> struct Cycle {
       bits = (phase & 0xffff) | (step_state << 16) | ((at_correct ? 1 : 0) << 18) | ((completed ? 1 : 0) << 19) |
              ((negate ? 1 : 0) << 20);
       prog = (swing_num & 0xffff) | ((stance_num & 0xffff) << 16);
-      ip[(size_t)(ib + LI_BITS) * np + r] = bits;
-      ip[(size_t)(ib + LI_PROG) * np + r] = prog;
+      il[(LI_BITS) * 32] = bits;
+      il[(LI_PROG) * 32] = prog;
 
       {  // walk plane normal equations over the (possibly updated) default tips
         double x = (double)def.x, y = (double)def.y, z = (double)def.z;
@@ -861,18 +907,18 @@ template <class P, int D> struct Cycle {
       K q[D], qd[D];
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        q[j] = K(sp[(size_t)(sb + LS::Q + j) * np + r]);
-        qd[j] = K(sp[(size_t)(sb + LS::QD + j) * np + r]);
+        q[j] = K(sl[(LS::Q + j) * 32]);
+        qd[j] = K(sl[(LS::QD + j) * 32]);
       }
       Chain<K, D> ch;
       leg_chain<K, D>(ck, l, q, ch);
 
       // ---- AdmittanceController::updateAdmittance (admittance_controller.cpp:22) ----
       if (ci.admittance_control) {
-        const int ab = sb + ci.offS_leg_adm;
-        K x0 = K(sp[(size_t)(ab + ADM_X) * np + r]), x1 = K(sp[(size_t)(ab + ADM_X + 1) * np + r]);
+        S* __restrict__ sa = sl + ci.offS_leg_adm * 32;
+        K x0 = K(sa[(ADM_X) * 32]), x1 = K(sa[(ADM_X + 1) * 32]);
         V3<K> force{K(0), K(0), K(0)};
-        if (ci.use_joint_effort) force = ld3K(sp, np, ab + ADM_FORCE, r);
+        if (ci.use_joint_effort) force = ld3K(sa, ADM_FORCE);
         else if (io.tip_force) {
           const float* f = io.tip_force + 3 * ((size_t)r * L + l);
           force = {K(f[0]), K(f[1]), K(f[2])};
@@ -890,12 +936,12 @@ template <class P, int D> struct Cycle {
           K dl = clamp_(-x0, K(-0.2), K(0.2));
           da[a] = abs_(dl) > K(0) ? (dl / abs_(dl)) * abs_(dl) : K(0);  // deadband 0 (trap 8)
         }
-        sp[(size_t)(ab + ADM_X) * np + r] = S(x0);
-        sp[(size_t)(ab + ADM_X + 1) * np + r] = S(x1);
+        sa[(ADM_X) * 32] = S(x0);
+        sa[(ADM_X + 1) * 32] = S(x1);
         // Leg::setAdmittanceDelta (model.h:365): projection onto the tip frame x axis (base_link frame)
         V3<K> dirx = t1_rotate(ck, l, ch.tipx);
         V3<K> adelta = projection(V3<K>{da[0], da[1], da[2]}, dirx);
-        st3(sp, np, ab + ADM_DELTA, r, adelta);
+        st3(sa, ADM_DELTA, adelta);
         desired = desired + adelta;  // Leg::setDesiredTipPose (model.cpp:653)
       }
 
@@ -905,8 +951,8 @@ template <class P, int D> struct Cycle {
                                     &des_leg);
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        sp[(size_t)(sb + LS::Q + j) * np + r] = S(q[j]);
-        sp[(size_t)(sb + LS::QD + j) * np + r] = S(qd[j]);
+        sl[(LS::Q + j) * 32] = S(q[j]);
+        sl[(LS::QD + j) * 32] = S(qd[j]);
         io.joints_out[((size_t)r * L + l) * D + j] = (float)(q[j] + ck.joffset[l][j]);  // state_controller.cpp:795
       }
       if (io.flags_out || ci.use_joint_effort) {
@@ -920,10 +966,10 @@ template <class P, int D> struct Cycle {
 #pragma unroll
           for (int j = 0; j < D; ++j) tau[j] = io.efforts ? K(io.efforts[((size_t)r * L + l) * D + j]) : K(0);
           V3<K> raw = raw_tip_force<K, D>(ck, l, ch2, tau);
-          const int ab = sb + ci.offS_leg_adm;
-          V3<K> f = ld3K(sp, np, ab + ADM_FORCE, r);
+          S* __restrict__ sa2 = sl + ci.offS_leg_adm * 32;
+          V3<K> f = ld3K(sa2, ADM_FORCE);
           f = raw * (K(0.15) * ck.force_gain) + f * (K(1) - K(0.15));
-          st3(sp, np, ab + ADM_FORCE, r, f);
+          st3(sa2, ADM_FORCE, f);
         }
       }
     }
@@ -944,29 +990,29 @@ template <class P, int D> struct Cycle {
         double b = (c01 * sxz + c11 * syz + c12 * sz1) * id;
         double cc = (c02 * sxz + c12 * syz + c22 * sz1) * id;
         V3<double> nrm = normalized(V3<double>{-a, -b, 1.0});
-        st3(sp, np, RS_WPL, r, V3<double>{a, b, cc});
-        st3(sp, np, RS_WPN, r, nrm);
+        st3(sp, RS_WPL, V3<double>{a, b, cc});
+        st3(sp, RS_WPN, nrm);
       } else {
-        st3(sp, np, RS_WPL, r, V3<double>{0.0, 0.0, 0.0});
-        st3(sp, np, RS_WPN, r, V3<double>{0.0, 0.0, 1.0});
+        st3(sp, RS_WPL, V3<double>{0.0, 0.0, 0.0});
+        st3(sp, RS_WPN, V3<double>{0.0, 0.0, 1.0});
       }
       // odometry_ideal_ = odometry_ideal_.addPose(calculateOdometry(dt))
-      Q4<T> oq{T(sp[(size_t)RS_ODOMQ * np + r]), T(sp[(size_t)(RS_ODOMQ + 1) * np + r]), T(sp[(size_t)(RS_ODOMQ + 2) * np + r]),
-               T(sp[(size_t)(RS_ODOMQ + 3) * np + r])};
+      Q4<T> oq{T(sp[(RS_ODOMQ) * 32]), T(sp[(RS_ODOMQ + 1) * 32]), T(sp[(RS_ODOMQ + 2) * 32]),
+               T(sp[(RS_ODOMQ + 3) * 32])};
       V3<T> dpos = qrot(oq, V3<T>{dvx * ct.dt, dvy * ct.dt, T(0)});
-      dp[(size_t)(RD_ODOMP)*np + r] += (double)dpos.x;
-      dp[(size_t)(RD_ODOMP + 1) * np + r] += (double)dpos.y;
-      dp[(size_t)(RD_ODOMP + 2) * np + r] += (double)dpos.z;
+      dp[(RD_ODOMP) * 32] += (double)dpos.x;
+      dp[(RD_ODOMP + 1) * 32] += (double)dpos.y;
+      dp[(RD_ODOMP + 2) * 32] += (double)dpos.z;
       Q4<T> nq = qmul(oq, q_axis_z(dw * ct.dt));
-      sp[(size_t)RS_ODOMQ * np + r] = S(nq.w);
-      sp[(size_t)(RS_ODOMQ + 1) * np + r] = S(nq.x);
-      sp[(size_t)(RS_ODOMQ + 2) * np + r] = S(nq.y);
-      sp[(size_t)(RS_ODOMQ + 3) * np + r] = S(nq.z);
+      sp[(RS_ODOMQ) * 32] = S(nq.w);
+      sp[(RS_ODOMQ + 1) * 32] = S(nq.x);
+      sp[(RS_ODOMQ + 2) * 32] = S(nq.y);
+      sp[(RS_ODOMQ + 3) * 32] = S(nq.z);
     }
 
     rbits = (walk_state & 3) | ((legs_at_correct & 15) << 2) | ((legs_completed & 15) << 6) | ((rtd & 1) << 10) |
             ((pose_state & 3) << 11) | ((auto_state & 3) << 13) | (status << 16);
-    ip[(size_t)RI_BITS * np + r] = rbits;
+    ip[(RI_BITS) * 32] = rbits;
     if (io.flags_out) io.flags_out[r] = status;
   }
 };

@@ -20,8 +20,15 @@ namespace shc {
 
 using PrecMixed = Prec<float, float, double>;  // fp32 state + trajectory; fp64 pose/kinematics (see DESIGN.md "Precision")
 
+#ifndef SHC_MIN_BLOCKS
+#define SHC_MIN_BLOCKS 4
+#endif
+#ifndef SHC_BLOCK
+#define SHC_BLOCK 128
+#endif
+
 template <class P, int D>
-__global__ void __launch_bounds__(128) control_cycle_kernel(const __grid_constant__ Consts c, Planes<typename P::S> pl, StepIO io) {
+__global__ void __launch_bounds__(SHC_BLOCK, SHC_MIN_BLOCKS) control_cycle_kernel(const __grid_constant__ Consts c, Planes<typename P::S> pl, StepIO io) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= c.i.n_robots) return;
   Cycle<P, D>::run(c, pl, r, io);
@@ -222,9 +229,10 @@ void pack(const shc_engine* e, const shc_robot_state* in, size_t n, HostPlanes& 
   const int D = ci.D, L = ci.L;
   const bool imu = e->cfg.imu_posing || e->cfg.inclination_posing;
   const bool adm = e->cfg.admittance_control || e->cfg.use_joint_effort;
-  auto S = [&](int plane, size_t r) -> double& { return h.s[(size_t)plane * np + r]; };
-  auto Dd = [&](int plane, size_t r) -> double& { return h.d[(size_t)plane * np + r]; };
-  auto I = [&](int plane, size_t r) -> int& { return h.i[(size_t)plane * np + r]; };
+  // tile-major planes: [tile][plane][32 lanes] (shc_layout.h)
+  auto S = [&](int plane, size_t r) -> double& { return h.s[((r >> 5) * ci.nS + plane) * 32 + (r & 31)]; };
+  auto Dd = [&](int plane, size_t r) -> double& { return h.d[((r >> 5) * ci.nD + plane) * 32 + (r & 31)]; };
+  auto I = [&](int plane, size_t r) -> int& { return h.i[((r >> 5) * ci.nI + plane) * 32 + (r & 31)]; };
   for (size_t r = 0; r < n; ++r) {
     const shc_robot_state& s = in[r];
     S(RS_VEL, r) = s.desired_linear_velocity[0];
@@ -304,9 +312,9 @@ template <int D> void unpack(const shc_engine* e, const HostPlanes& h, shc_robot
   const int L = ci.L;
   const bool imu = e->cfg.imu_posing || e->cfg.inclination_posing;
   const bool adm = e->cfg.admittance_control || e->cfg.use_joint_effort;
-  auto S = [&](int plane, size_t r) { return h.s[(size_t)plane * np + r]; };
-  auto Dd = [&](int plane, size_t r) { return h.d[(size_t)plane * np + r]; };
-  auto I = [&](int plane, size_t r) { return h.i[(size_t)plane * np + r]; };
+  auto S = [&](int plane, size_t r) { return h.s[((r >> 5) * ci.nS + plane) * 32 + (r & 31)]; };
+  auto Dd = [&](int plane, size_t r) { return h.d[((r >> 5) * ci.nD + plane) * 32 + (r & 31)]; };
+  auto I = [&](int plane, size_t r) { return h.i[((r >> 5) * ci.nI + plane) * 32 + (r & 31)]; };
   for (size_t r = 0; r < n; ++r) {
     shc_robot_state& s = out[r];
     std::memset(&s, 0, sizeof(s));
@@ -419,7 +427,7 @@ template <class F> static int dispatch_D(int D, F&& f) {
 }
 
 static int launch_cycle(shc_engine* e, const StepIO& io, cudaStream_t st) {
-  const int threads = 128;
+  const int threads = SHC_BLOCK;
   const int blocks = (e->n + threads - 1) / threads;
   return dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int {
     constexpr int D = decltype(dtag)::value;
@@ -501,14 +509,15 @@ int shc_create(const shc_config* cfg, const shc_startup* startup, int n_robots, 
     h.s.assign((size_t)ci.nS * np, 0.0);
     h.d.assign((size_t)ci.nD * np, 0.0);
     h.i.assign((size_t)ci.nI * np, 0);
-    HostPlanes one;
-    one.s.assign((size_t)ci.nS * np, 0.0);  // pack() writes column r of each plane; pack robot 0 then replicate
-    one.d.assign((size_t)ci.nD * np, 0.0);
-    one.i.assign((size_t)ci.nI * np, 0);
-    pack(e, &init, 1, one);
-    for (int p = 0; p < ci.nS; ++p) std::fill(h.s.begin() + (size_t)p * np, h.s.begin() + (size_t)p * np + e->n, one.s[(size_t)p * np]);
-    for (int p = 0; p < ci.nD; ++p) std::fill(h.d.begin() + (size_t)p * np, h.d.begin() + (size_t)p * np + e->n, one.d[(size_t)p * np]);
-    for (int p = 0; p < ci.nI; ++p) std::fill(h.i.begin() + (size_t)p * np, h.i.begin() + (size_t)p * np + e->n, one.i[(size_t)p * np]);
+    // pack one full tile of identical robots, then replicate the tile
+    std::vector<shc_robot_state> tile_states(32, init);
+    pack(e, tile_states.data(), 32, h);
+    const size_t n_tiles = np / 32;
+    for (size_t t = 1; t < n_tiles; ++t) {
+      std::copy(h.s.begin(), h.s.begin() + (size_t)ci.nS * 32, h.s.begin() + t * (size_t)ci.nS * 32);
+      std::copy(h.d.begin(), h.d.begin() + (size_t)ci.nD * 32, h.d.begin() + t * (size_t)ci.nD * 32);
+      std::copy(h.i.begin(), h.i.begin() + (size_t)ci.nI * 32, h.i.begin() + t * (size_t)ci.nI * 32);
+    }
     int rc = upload(e, h);
     if (rc != SHC_OK) { std::string m = g_err; return cleanup(rc, m); }
   }

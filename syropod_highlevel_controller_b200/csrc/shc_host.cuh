@@ -70,6 +70,13 @@ template <class R> void fill_static_consts(const shc_config& c, RealConsts<R>& k
   k.body_clearance = R(c.body_clearance);
   k.lambda2 = R(0.02 * 0.02);
   k.swing_progress_scaler = R(std::max(1.0, double(c.swing_phase) / c.phase_offset));
+  {
+    const double edges[8] = {44.5, 89.5, 134.5, 179.5, 0.5, 45.5, 90.5, 135.5};
+    for (int i = 0; i < 8; ++i) {
+      k.sec_cos[i] = R(cos(edges[i] / 360.0 * 2.0 * kPi));
+      k.sec_sin[i] = R(sin(edges[i] / 360.0 * 2.0 * kPi));
+    }
+  }
   for (int i = 0; i < 3; ++i) {
     k.max_translation[i] = R(c.max_translation[i]);
     k.max_rotation[i] = R(c.max_rotation[i]);

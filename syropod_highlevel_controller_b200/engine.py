@@ -15,7 +15,7 @@ import numpy as np
 from .config import ShcConfig, ShcRobotState, ShcStartup
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libshc_b200.so")
+LIB_PATH = os.environ.get("SHC_B200_LIB", os.path.join(_PKG, "libshc_b200.so"))  # override: kernel-tuning builds only
 _lib = None
 
 PRECISION = {"f64": 0, "mixed": 1}
