@@ -12,25 +12,30 @@ constexpr int kMaxLegs = SHC_MAX_LEGS;
 constexpr int kMaxDof = SHC_MAX_DOF;
 constexpr int kMaxPosers = SHC_MAX_AUTO_POSERS;
 
+// Per-leg constants in one precision, array-of-structs so that one uniform base offset per leg addresses them all.
+template <class R> struct LegConsts {
+  R t1r[9];  // rotation of the constant base transform T1 = DH(link 0), row-major (model.cpp:224, A.1)
+  R t1p[3];  // translation of T1
+  R dh_d[kMaxDof], dh_theta[kMaxDof], dh_r[kMaxDof];  // links 1..D
+  R dh_ca[kMaxDof], dh_sa[kMaxDof];                   // cos/sin(alpha) are constants
+  R jmin[kMaxDof], jmax[kMaxDof], vmax[kMaxDof];
+  R joffset[kMaxDof];    // added to the published joint command only (state_controller.cpp:795)
+  R jcentre[kMaxDof];    // min + range/2                                   (model.cpp:771)
+  R jcost_pos[kMaxDof];  // w / range (0 when range == 0)                   (model.cpp:775)
+  R jgrad_pos[kMaxDof];  // -w^2 / range^2 (0 when range == 0)              (model.cpp:777)
+  R jcost_vel[kMaxDof];  // w / (2 vmax)                                    (model.cpp:784)
+  R jgrad_vel[kMaxDof];  // -w^2 / (2 vmax)^2                               (model.cpp:786)
+  R identity_x, identity_y;  // identity tip position (walk_controller.cpp:34-42)
+  R ysign;                   // +1 when identity y > 0 else -1 (walk_controller.cpp:1244)
+  R span_dy;                 // calculateStanceSpanChange().y with the simple one-plane workspace (:949)
+  R stance_dt_mod;           // 1/stance_iterations with modified_stance_start = phase offset (:1025-1041)
+  R stride_scaler_mod;       // modified_stance_period / stance_period (:1167)
+  R neg_ratio;               // negation_transition_ratio (pose_controller.cpp:1763)
+};
+
 // Real-valued constants in one precision.
 template <class R> struct RealConsts {
-  // per leg ---------------------------------------------------------------------------------------------------
-  R t1r[kMaxLegs][9];  // rotation of the constant base transform T1 = DH(link 0), row-major (model.cpp:224, A.1)
-  R t1p[kMaxLegs][3];  // translation of T1
-  R dh_d[kMaxLegs][kMaxDof], dh_theta[kMaxLegs][kMaxDof], dh_r[kMaxLegs][kMaxDof];  // links 1..D
-  R dh_ca[kMaxLegs][kMaxDof], dh_sa[kMaxLegs][kMaxDof];                            // cos/sin(alpha) are constants
-  R jmin[kMaxLegs][kMaxDof], jmax[kMaxLegs][kMaxDof], vmax[kMaxLegs][kMaxDof];
-  R joffset[kMaxLegs][kMaxDof];     // added to the published joint command only (state_controller.cpp:795)
-  R jcentre[kMaxLegs][kMaxDof];     // min + range/2                                   (model.cpp:771)
-  R jcost_pos[kMaxLegs][kMaxDof];   // w / range (0 when range == 0)                   (model.cpp:775)
-  R jgrad_pos[kMaxLegs][kMaxDof];   // -w^2 / range^2 (0 when range == 0)              (model.cpp:777)
-  R jcost_vel[kMaxLegs][kMaxDof];   // w / (2 vmax)                                    (model.cpp:784)
-  R jgrad_vel[kMaxLegs][kMaxDof];   // -w^2 / (2 vmax)^2                               (model.cpp:786)
-  R identity_x[kMaxLegs], identity_y[kMaxLegs];  // identity tip position (walk_controller.cpp:34-42)
-  R ysign[kMaxLegs];                // +1 when identity y > 0 else -1 (walk_controller.cpp:1244)
-  R span_dy[kMaxLegs];              // calculateStanceSpanChange().y with the simple one-plane workspace (:949)
-  R stance_dt_mod[kMaxLegs];        // 1/stance_iterations with modified_stance_start = phase offset (:1025-1041)
-  R stride_scaler_mod[kMaxLegs];    // modified_stance_period / stance_period (:1167)
+  LegConsts<R> leg[kMaxLegs];
   // robot-wide --------------------------------------------------------------------------------------------------
   R dt, inv_dt;
   R swing_dt;          // swing_delta_t_ (:1037)
@@ -50,7 +55,6 @@ template <class R> struct RealConsts {
   R body_velocity_scaler;  // bodyVelocityInputCallback (state_controller.cpp:1131)
   // auto posers (pose_controller.cpp:1338)
   R ap_pos[kMaxPosers][3], ap_rot[kMaxPosers][3], ap_gravity[kMaxPosers];
-  R neg_ratio[kMaxLegs];
 };
 
 struct IntConsts {

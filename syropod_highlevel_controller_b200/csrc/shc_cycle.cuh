@@ -64,32 +64,32 @@ template <class K, int D> struct Chain {
 };
 
 template <class K, int D, class QT>
-SHC_HD void leg_chain(const RealConsts<K>& ck, int leg, const QT* q, Chain<K, D>& ch) {
+SHC_HD void leg_chain(const LegConsts<K>& lc, const QT* q, Chain<K, D>& ch) {
   V3<K> ax{K(1), K(0), K(0)}, ay{K(0), K(1), K(0)}, az{K(0), K(0), K(1)}, ap{K(0), K(0), K(0)};
 #pragma unroll
   for (int j = 0; j < D; ++j) {
     ch.z[j] = az;
     ch.p[j] = ap;
     K s, c;
-    sincos_(ck.dh_theta[leg][j] + K(q[j]), &s, &c);
-    const K ca = ck.dh_ca[leg][j], sa = ck.dh_sa[leg][j];
+    sincos_(lc.dh_theta[j] + K(q[j]), &s, &c);
+    const K ca = lc.dh_ca[j], sa = lc.dh_sa[j];
     V3<K> nx = ax * c + ay * s;
     V3<K> u = ay * c - ax * s;
     V3<K> ny = u * ca + az * sa;
     V3<K> nz = az * ca - u * sa;
-    ap = ap + nx * ck.dh_r[leg][j] + az * ck.dh_d[leg][j];
+    ap = ap + nx * lc.dh_r[j] + az * lc.dh_d[j];
     ax = nx; ay = ny; az = nz;
   }
   ch.tip = ap;
   ch.tipx = ax;
 }
 
-template <class K> SHC_HD V3<K> t1_rotate(const RealConsts<K>& ck, int leg, V3<K> v) {
-  const K* r = ck.t1r[leg];
+template <class K> SHC_HD V3<K> t1_rotate(const LegConsts<K>& lc, V3<K> v) {
+  const K* r = lc.t1r;
   return {r[0] * v.x + r[1] * v.y + r[2] * v.z, r[3] * v.x + r[4] * v.y + r[5] * v.z, r[6] * v.x + r[7] * v.y + r[8] * v.z};
 }
-template <class K> SHC_HD V3<K> t1_rotate_inv(const RealConsts<K>& ck, int leg, V3<K> v) {
-  const K* r = ck.t1r[leg];
+template <class K> SHC_HD V3<K> t1_rotate_inv(const LegConsts<K>& lc, V3<K> v) {
+  const K* r = lc.t1r;
   return {r[0] * v.x + r[3] * v.y + r[6] * v.z, r[1] * v.x + r[4] * v.y + r[7] * v.z, r[2] * v.x + r[5] * v.y + r[8] * v.z};
 }
 
@@ -144,7 +144,7 @@ template <class K, int D> SHC_HD void spdN_solve(K A[D][D], K b[D]) {
 // Leg::calculateTipForce (model.cpp:667-708): F_leg = Jp (J^T J + l^2 I_D)^-1 tau with the full 6xD Jacobian
 // (angular rows = joint axes), rotated by the rotation of T1^-1, before the low-pass filter.
 template <class K, int D>
-SHC_HD V3<K> raw_tip_force(const RealConsts<K>& ck, int leg, const Chain<K, D>& ch, const K* tau) {
+SHC_HD V3<K> raw_tip_force(const RealConsts<K>& ck, const LegConsts<K>& lc, const Chain<K, D>& ch, const K* tau) {
   V3<K> Jp[D];
 #pragma unroll
   for (int j = 0; j < D; ++j) Jp[j] = cross(ch.z[j], ch.tip - ch.p[j]);
@@ -160,13 +160,13 @@ SHC_HD V3<K> raw_tip_force(const RealConsts<K>& ck, int leg, const Chain<K, D>& 
   V3<K> f{K(0), K(0), K(0)};
 #pragma unroll
   for (int j = 0; j < D; ++j) f = f + Jp[j] * x[j];
-  return t1_rotate_inv(ck, leg, f);
+  return t1_rotate_inv(lc, f);
 }
 
 // Leg::solveIK (position rows only: the angular rows of J are zero when solve_rotation is false, so
 // J^T (J J^T + l^2 I6)^-1 [dp;0] = Jp^T (Jp Jp^T + l^2 I3)^-1 dp and J^+ J = Jp^T (..)^-1 Jp — model.cpp:726-795).
 template <class K, int D>
-SHC_HD void solve_ik(const RealConsts<K>& ck, int leg, const Chain<K, D>& ch, V3<K> dp, const K* q,
+SHC_HD void solve_ik(const RealConsts<K>& ck, const LegConsts<K>& lc, const Chain<K, D>& ch, V3<K> dp, const K* q,
                                          const K* qd, K* dq) {
   V3<K> J[D];
 #pragma unroll
@@ -183,13 +183,13 @@ SHC_HD void solve_ik(const RealConsts<K>& ck, int leg, const Chain<K, D>& ch, V3
   K gp[D], gv[D];
 #pragma unroll
   for (int j = 0; j < D; ++j) {
-    K e = q[j] - ck.jcentre[leg][j];
-    K cp = ck.jcost_pos[leg][j] * e;
+    K e = q[j] - lc.jcentre[j];
+    K cp = lc.jcost_pos[j] * e;
     pos_cost += cp * cp;
-    gp[j] = ck.jgrad_pos[leg][j] * e;
-    K cv = ck.jcost_vel[leg][j] * qd[j];
+    gp[j] = lc.jgrad_pos[j] * e;
+    K cv = lc.jcost_vel[j] * qd[j];
     vel_cost += cv * cv;
-    gv[j] = ck.jgrad_vel[leg][j] * qd[j];
+    gv[j] = lc.jgrad_vel[j] * qd[j];
   }
   K sp = pos_cost == K(0) ? K(0) : K(1) / sqrt_(pos_cost);
   K sv = vel_cost == K(0) ? K(0) : K(1) / sqrt_(vel_cost);
@@ -209,24 +209,24 @@ SHC_HD void solve_ik(const RealConsts<K>& ck, int leg, const Chain<K, D>& ch, V3
 // current joint angles, one DLS step, Leg::updateJointPositions (:799).  q/qd are updated in place; returns the
 // SHC_FLAG_*_CLAMP bits.  `des_leg_out` receives the desired tip position in the leg frame.
 template <class K, int D>
-SHC_HD int apply_ik_step(const RealConsts<K>& ck, int leg, const Chain<K, D>& ch, K* q, K* qd, V3<K> desired_robot,
+SHC_HD int apply_ik_step(const RealConsts<K>& ck, const LegConsts<K>& lc, const Chain<K, D>& ch, K* q, K* qd, V3<K> desired_robot,
                          bool clamp_positions, bool clamp_velocities, V3<K>* des_leg_out) {
-  V3<K> des_leg = t1_rotate_inv(ck, leg, desired_robot - V3<K>{ck.t1p[leg][0], ck.t1p[leg][1], ck.t1p[leg][2]});
+  V3<K> des_leg = t1_rotate_inv(lc, desired_robot - V3<K>{lc.t1p[0], lc.t1p[1], lc.t1p[2]});
   *des_leg_out = des_leg;
   K dq[D];
-  solve_ik<K, D>(ck, leg, ch, des_leg - ch.tip, q, qd, dq);
+  solve_ik<K, D>(ck, lc, ch, des_leg - ch.tip, q, qd, dq);
   int status = 0;
 #pragma unroll
   for (int j = 0; j < D; ++j) {
     K v = dq[j] / ck.dt;
-    if (clamp_velocities && abs_(v) > ck.vmax[leg][j]) {
-      v = clamp_(v, -ck.vmax[leg][j], ck.vmax[leg][j]);
+    if (clamp_velocities && abs_(v) > lc.vmax[j]) {
+      v = clamp_(v, -lc.vmax[j], lc.vmax[j]);
       status |= 4;
     }
     K nq = q[j] + v * ck.dt;
     if (clamp_positions) {
-      if (nq < ck.jmin[leg][j]) { nq = ck.jmin[leg][j]; status |= 2; }
-      else if (nq > ck.jmax[leg][j]) { nq = ck.jmax[leg][j]; status |= 2; }
+      if (nq < lc.jmin[j]) { nq = lc.jmin[j]; status |= 2; }
+      else if (nq > lc.jmax[j]) { nq = lc.jmax[j]; status |= 2; }
     }
     q[j] = nq;
     qd[j] = v;
@@ -237,23 +237,25 @@ SHC_HD int apply_ik_step(const RealConsts<K>& ck, int leg, const Chain<K, D>& ch
 // Return value of Leg::applyIK (model.cpp:845-856, 916-929): the smallest joint-limit proximity, or 0 when the tip
 // deviates from the desired position by more than IK_TOLERANCE on a base_link axis.  `ch2` is the chain at the NEW q.
 template <class K, int D>
-SHC_HD K ik_result_value(const RealConsts<K>& ck, int leg, const Chain<K, D>& ch2, const K* q, V3<K> des_leg) {
+SHC_HD K ik_result_value(const LegConsts<K>& lc, const Chain<K, D>& ch2, const K* q, V3<K> des_leg) {
   K prox = K(1);
 #pragma unroll
   for (int j = 0; j < D; ++j) {
-    K min_diff = abs_(ck.jmin[leg][j] - q[j]);
-    K max_diff = abs_(ck.jmax[leg][j] - q[j]);
-    K half = (ck.jmax[leg][j] - ck.jmin[leg][j]) / K(2);
+    K min_diff = abs_(lc.jmin[j] - q[j]);
+    K max_diff = abs_(lc.jmax[j] - q[j]);
+    K half = (lc.jmax[j] - lc.jmin[j]) / K(2);
     K lp = half != K(0) ? min_(min_diff, max_diff) / half : K(1);
     prox = min_(lp, prox);
   }
-  V3<K> er = t1_rotate(ck, leg, ch2.tip - des_leg);
+  V3<K> er = t1_rotate(lc, ch2.tip - des_leg);
   if (abs_(er.x) > K(0.005) || abs_(er.y) > K(0.005) || abs_(er.z) > K(0.005)) prox = K(0);
   return prox;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-template <class P, int D> struct Cycle {
+// FULL = false compiles the walking-only engine (no auto / IMU / inclination posing, no admittance): the optional stages
+// and the registers they keep alive across the leg loop disappear at compile time.
+template <class P, int D, bool FULL> struct Cycle {
   using S = typename P::S;
   using T = typename P::T;
   using K = typename P::K;
@@ -353,6 +355,8 @@ template <class P, int D> struct Cycle {
     const RealConsts<K>& ck = ConstSel<K>::get(c);
     const RealConsts<double>& cd = c.d;
     const int L = ci.L;
+    const bool f_auto = FULL && ci.auto_posing, f_incl = FULL && ci.inclination_posing, f_imu = FULL && ci.imu_posing;
+    const bool f_adm = FULL && ci.admittance_control, f_effort = FULL && ci.use_joint_effort;
     // tile-major planes [tile][plane][32 lanes]: every field of this robot is at a compile-time offset from these bases
     const size_t tile = (size_t)(r >> 5);
     const int lane = r & 31;
@@ -376,7 +380,7 @@ template <class P, int D> struct Cycle {
 
     Q4<K> imu_raw{K(0), K(0), K(0), K(0)};  // Model::imu_data_.orientation (UNDEFINED until set)
     V3<K> gyro{K(0), K(0), K(0)};
-    if (io.imu) {
+    if (FULL && io.imu) {
       const float* m = io.imu + 10 * (size_t)r;
       imu_raw = qnormalized(Q4<K>{K(m[0]), K(m[1]), K(m[2]), K(m[3])});  // Model::setImuData (model.h:146)
       gyro = {K(m[4]), K(m[5]), K(m[6])};
@@ -450,8 +454,8 @@ template <class P, int D> struct Cycle {
       }
     }
     PoseT<K> auto_pose = pose_identity<K>();
-    if (ci.auto_posing) auto_pose = ldPose(sp, ci.offS_auto + AUTO_POSE);
-    if (ci.inclination_posing) {  // updateInclinationPose (:1240)
+    if (f_auto) auto_pose = ldPose(sp, ci.offS_auto + AUTO_POSE);
+    if (f_incl) {  // updateInclinationPose (:1240)
       Q4<K> comb = qnormalized(qmul(man.q, auto_pose.q));
       Q4<K> removed = qnormalized(qmul(imu_q, qinverse(comb)));
       V3<K> e = quat_to_euler(removed, false);
@@ -467,7 +471,7 @@ template <class P, int D> struct Cycle {
     }
     int master_phase = 0;
     bool run_auto = false;
-    if (ci.imu_posing) {  // updateIMUPose (:1191); robot_state is RUNNING in every engine cycle
+    if (f_imu) {  // updateIMUPose (:1191); robot_state is RUNNING in every engine cycle
       Q4<K> current_rotation = correct_rotation(imu_q, qidentity<K>());
       Q4<K> target_rotation = correct_rotation(man.q, qidentity<K>());
       Q4<K> rot_err = qnormalized(qmul(current_rotation, qinverse(target_rotation)));
@@ -494,7 +498,7 @@ template <class P, int D> struct Cycle {
       PoseT<K> imu_pose = pose_identity<K>();
       imu_pose.q = imu_pose_q;
       cur_pose = pose_add(cur_pose, imu_pose);
-    } else if (ci.auto_posing) {  // updateAutoPose (:1134)
+    } else if (f_auto) {  // updateAutoPose (:1134)
       run_auto = true;
       const int rb = ci.offI_leg + ci.auto_ref_leg * ci.strideI_leg;
       int ref_bits = ip[(rb + LI_BITS) * 32];
@@ -667,11 +671,7 @@ template <class P, int D> struct Cycle {
       walk_state = WALK_STOPPED;
     }
 
-    const V3<T> walker_wp = ld3T(sp, RS_WPL);
-    const V3<T> walker_wpn = ld3T(sp, RS_WPN);
 
-    // walk-plane least squares accumulators (updateWalkPlane :748): A = [x y 1], b = z over the default tips
-    double sxx = 0, sxy = 0, sx1 = 0, syy = 0, sy1 = 0, sxz = 0, syz = 0, sz1 = 0;
 
     // =================================================================================================================
     // 3. per leg: walk state machine + LegStepper + updateStance + Leg::applyIK
@@ -682,6 +682,8 @@ template <class P, int D> struct Cycle {
       S* __restrict__ sl = sp + (ci.offS_leg + l * ci.strideS_leg) * 32;
       double* __restrict__ dl = dp + (ci.offD_leg + l * ci.strideD_leg) * 32;
       int* __restrict__ il = ip + (ci.offI_leg + l * ci.strideI_leg) * 32;
+      const LegConsts<K>& lk = ck.leg[l];
+      const LegConsts<T>& lt = ct.leg[l];
       if (lane == 0 && l + 1 < L) l2_prefetch_bulk(sl - lane + ci.strideS_leg * 32, leg_chunk_bytes);  // next leg -> L2
       int bits = il[(LI_BITS) * 32];
       int prog = il[(LI_PROG) * 32];
@@ -716,15 +718,15 @@ template <class P, int D> struct Cycle {
           int num_iterations = end_phase - start_phase;
           bool first_half = iteration <= num_iterations / 2;
           K ctrl = K(1);
-          if (ck.neg_ratio[l] > K(0)) {
-            if (first_half) ctrl = min_(K(1), K(iteration) / (K(num_iterations) * ck.neg_ratio[l]));
-            else ctrl = min_(K(1), K(num_iterations - iteration) / (K(num_iterations) * ck.neg_ratio[l]));
+          if (lk.neg_ratio > K(0)) {
+            if (first_half) ctrl = min_(K(1), K(iteration) / (K(num_iterations) * lk.neg_ratio));
+            else ctrl = min_(K(1), K(num_iterations - iteration) / (K(num_iterations) * lk.neg_ratio));
           }
           ctrl = smooth_step(ctrl);
           PoseT<K> negation = pose_interpolate(pose_identity<K>(), ctrl, auto_pose);
           leg_auto = pose_remove(auto_pose, negation);
         }
-      } else if (ci.auto_posing) {
+      } else if (f_auto) {
         leg_auto = pose_identity<K>();  // LegPoser::auto_pose_ is only refreshed by updateAutoPose; IMU posing keeps identity
       }
 
@@ -769,8 +771,8 @@ template <class P, int D> struct Cycle {
             if (at_target || rtd) {
               rtd = 0;
               // LegStepper::updateDefaultTipPosition (:984), no external default
-              V3<K> idt{ck.identity_x[l], ck.identity_y[l] + ck.span_dy[l], K(0)};
-              idt = pose_transform(wpp, idt);  // Model::default_pose_ = walk_plane_pose_ (pose_controller.cpp:819)
+              V3<K> idt{lk.identity_x, lk.identity_y + lk.span_dy, K(0)};
+              idt = pose_transform(ldPose(sp, RS_WPP), idt);  // Model::default_pose_ = walk_plane_pose_ (pose_controller.cpp:819)
               V3<K> sto = ld3K(sl, LS::STO_P);
               V3<K> proj = projection(sto - idt, cvt<K>(wpn_l));
               def = cvt<T>(idt + proj);
@@ -789,12 +791,16 @@ template <class P, int D> struct Cycle {
 
         // ---- LegStepper::updateTipPosition (walk_controller.cpp:1018) ----
         const bool standard = (step_state == STEP_SWING || completed);
-        const T stance_dt = standard ? ct.stance_dt_std : ct.stance_dt_mod[l];
+        const T stance_dt = standard ? ct.stance_dt_std : lt.stance_dt_mod;
         tgt = def + stride * T(0.5);  // uses the previous cycle's stride (trap 5)
         st3(sl, LS::TGT, tgt);
         if (step_state != STEP_FORCE_STOP) {
-          // updateStride (:921)
-          stride = V3<T>{dvx - dw * T(tipy), dvy + dw * T(tipx), T(0)} * ct.stride_scale;
+          // updateStride (:921); the body velocity and the walker's plane were written / are still held in this
+          // robot's planes (L1 hits), which keeps them out of the loop's live registers
+          const V3<T> walker_wp = ld3T(sp, RS_WPL);
+          const V3<T> walker_wpn = ld3T(sp, RS_WPN);
+          const T bvx = T(sp[(RS_VEL) * 32]), bvy = T(sp[(RS_VEL + 1) * 32]), bw = T(sp[(RS_ANGVEL) * 32]);
+          stride = V3<T>{bvx - bw * T(tipy), bvy + bw * T(tipx), T(0)} * ct.stride_scale;
           st3(sl, LS::STRIDE, stride);
           st3(sl, LS::WP, walker_wp);
           st3(sl, LS::WPN, walker_wpn);
@@ -816,7 +822,7 @@ template <class P, int D> struct Cycle {
             // only node differences enter quarticBezierDot, so the origin cancels.
             V3<T> clr = normalized(walker_wpn) * ct.swing_height;
             V3<T> tr = tgt - swo_p;
-            V3<T> mid{tr.x * T(0.5) + clr.x, tr.y * T(0.5) + clr.y + ct.ysign[l] * ct.swing_width, max_(T(0), tr.z) + clr.z};
+            V3<T> mid{tr.x * T(0.5) + clr.x, tr.y * T(0.5) + clr.y + lt.ysign * ct.swing_width, max_(T(0), tr.z) + clr.z};
             V3<T> sep1 = swo_v * (T(0.25) * (ct.dt / ct.swing_dt));
             V3<T> n2 = sep1 * T(2);
             V3<T> n3 = (mid + n2) * T(0.5);
@@ -850,7 +856,7 @@ template <class P, int D> struct Cycle {
             int mod_start = standard ? ci.stance_start : ci.phase_offset[l];
             int iteration = imod(phase + (ci.period - mod_start), ci.period) + 1;
             if (iteration == 1) st3(sl, LS::STO_P, V3<T>{T(tipx), T(tipy), T(tipz)});
-            T scaler = standard ? T(1) : ct.stride_scaler_mod[l];
+            T scaler = standard ? T(1) : lt.stride_scaler_mod;
             V3<T> sep = -stride * scaler * T(0.25);
             // stance nodes are origin + k*sep (generateStanceControlNodes :1295): all four node differences are sep
             T t = T(iteration) * stance_dt;
@@ -890,14 +896,9 @@ template <class P, int D> struct Cycle {
       il[(LI_BITS) * 32] = bits;
       il[(LI_PROG) * 32] = prog;
 
-      {  // walk plane normal equations over the (possibly updated) default tips
-        double x = (double)def.x, y = (double)def.y, z = (double)def.z;
-        sxx += x * x; sxy += x * y; sx1 += x; syy += y * y; sy1 += y; sxz += x * z; syz += y * z; sz1 += z;
-      }
-
       // ---- PoseController::updateStance (pose_controller.cpp:110) ----
       PoseT<K> leg_pose = cur_pose;
-      if (ci.auto_posing) {
+      if (f_auto) {
         leg_pose = pose_remove(leg_pose, auto_pose);
         leg_pose = pose_add(leg_pose, leg_auto);
       }
@@ -911,14 +912,14 @@ template <class P, int D> struct Cycle {
         qd[j] = K(sl[(LS::QD + j) * 32]);
       }
       Chain<K, D> ch;
-      leg_chain<K, D>(ck, l, q, ch);
+      leg_chain<K, D>(lk, q, ch);
 
       // ---- AdmittanceController::updateAdmittance (admittance_controller.cpp:22) ----
-      if (ci.admittance_control) {
+      if (f_adm) {
         S* __restrict__ sa = sl + ci.offS_leg_adm * 32;
         K x0 = K(sa[(ADM_X) * 32]), x1 = K(sa[(ADM_X + 1) * 32]);
         V3<K> force{K(0), K(0), K(0)};
-        if (ci.use_joint_effort) force = ld3K(sa, ADM_FORCE);
+        if (f_effort) force = ld3K(sa, ADM_FORCE);
         else if (io.tip_force) {
           const float* f = io.tip_force + 3 * ((size_t)r * L + l);
           force = {K(f[0]), K(f[1]), K(f[2])};
@@ -939,7 +940,7 @@ template <class P, int D> struct Cycle {
         sa[(ADM_X) * 32] = S(x0);
         sa[(ADM_X + 1) * 32] = S(x1);
         // Leg::setAdmittanceDelta (model.h:365): projection onto the tip frame x axis (base_link frame)
-        V3<K> dirx = t1_rotate(ck, l, ch.tipx);
+        V3<K> dirx = t1_rotate(lk, ch.tipx);
         V3<K> adelta = projection(V3<K>{da[0], da[1], da[2]}, dirx);
         st3(sa, ADM_DELTA, adelta);
         desired = desired + adelta;  // Leg::setDesiredTipPose (model.cpp:653)
@@ -947,25 +948,25 @@ template <class P, int D> struct Cycle {
 
       // ---- Leg::applyIK (model.cpp:861): one DLS step ----
       V3<K> des_leg;
-      status |= apply_ik_step<K, D>(ck, l, ch, q, qd, desired, ci.clamp_joint_positions != 0, ci.clamp_joint_velocities != 0,
+      status |= apply_ik_step<K, D>(ck, lk, ch, q, qd, desired, ci.clamp_joint_positions != 0, ci.clamp_joint_velocities != 0,
                                     &des_leg);
 #pragma unroll
       for (int j = 0; j < D; ++j) {
         sl[(LS::Q + j) * 32] = S(q[j]);
         sl[(LS::QD + j) * 32] = S(qd[j]);
-        io.joints_out[((size_t)r * L + l) * D + j] = (float)(q[j] + ck.joffset[l][j]);  // state_controller.cpp:795
+        io.joints_out[((size_t)r * L + l) * D + j] = (float)(q[j] + lk.joffset[j]);  // state_controller.cpp:795
       }
-      if (io.flags_out || ci.use_joint_effort) {
+      if (io.flags_out || f_effort) {
         // applyFK at the new joint angles (model.cpp:904) for the IK tolerance check (:916-929)
         Chain<K, D> ch2;
-        leg_chain<K, D>(ck, l, q, ch2);
-        V3<K> er = t1_rotate(ck, l, ch2.tip - des_leg);  // current - desired tip position in the base_link frame
+        leg_chain<K, D>(lk, q, ch2);
+        V3<K> er = t1_rotate(lk, ch2.tip - des_leg);  // current - desired tip position in the base_link frame
         if (abs_(er.x) > K(0.005) || abs_(er.y) > K(0.005) || abs_(er.z) > K(0.005)) status |= 1;
-        if (ci.use_joint_effort) {  // calculateTipForce (model.cpp:938)
+        if (f_effort) {  // calculateTipForce (model.cpp:938)
           K tau[D];
 #pragma unroll
           for (int j = 0; j < D; ++j) tau[j] = io.efforts ? K(io.efforts[((size_t)r * L + l) * D + j]) : K(0);
-          V3<K> raw = raw_tip_force<K, D>(ck, l, ch2, tau);
+          V3<K> raw = raw_tip_force<K, D>(ck, lk, ch2, tau);
           S* __restrict__ sa2 = sl + ci.offS_leg_adm * 32;
           V3<K> f = ld3K(sa2, ADM_FORCE);
           f = raw * (K(0.15) * ck.force_gain) + f * (K(1) - K(0.15));
@@ -979,6 +980,14 @@ template <class P, int D> struct Cycle {
     // =================================================================================================================
     if (!starting_now) {
       if (L >= 3) {
+        // normal equations over the (possibly updated) default tips: A = [x y 1], b = z.  Re-read here rather than
+        // accumulated inside the leg loop to keep eight doubles out of its live registers.
+        double sxx = 0, sxy = 0, sx1 = 0, syy = 0, sy1 = 0, sxz = 0, syz = 0, sz1 = 0;
+        for (int l = 0; l < L; ++l) {
+          const S* __restrict__ sl = sp + (ci.offS_leg + l * ci.strideS_leg) * 32;
+          double x = (double)sl[(LS::DEF) * 32], y = (double)sl[(LS::DEF + 1) * 32], z = (double)sl[(LS::DEF + 2) * 32];
+          sxx += x * x; sxy += x * y; sx1 += x; syy += y * y; sy1 += y; sxz += x * z; syz += y * z; sz1 += z;
+        }
         // solve (A^T A) w = A^T b with A^T A = [[sxx sxy sx1],[sxy syy sy1],[sx1 sy1 L]]
         double n = (double)L;
         double c00 = syy * n - sy1 * sy1, c01 = sx1 * sy1 - sxy * n, c02 = sxy * sy1 - syy * sx1;
@@ -999,11 +1008,12 @@ template <class P, int D> struct Cycle {
       // odometry_ideal_ = odometry_ideal_.addPose(calculateOdometry(dt))
       Q4<T> oq{T(sp[(RS_ODOMQ) * 32]), T(sp[(RS_ODOMQ + 1) * 32]), T(sp[(RS_ODOMQ + 2) * 32]),
                T(sp[(RS_ODOMQ + 3) * 32])};
-      V3<T> dpos = qrot(oq, V3<T>{dvx * ct.dt, dvy * ct.dt, T(0)});
+      const T ovx = T(sp[(RS_VEL) * 32]), ovy = T(sp[(RS_VEL + 1) * 32]), ow = T(sp[(RS_ANGVEL) * 32]);
+      V3<T> dpos = qrot(oq, V3<T>{ovx * ct.dt, ovy * ct.dt, T(0)});
       dp[(RD_ODOMP) * 32] += (double)dpos.x;
       dp[(RD_ODOMP + 1) * 32] += (double)dpos.y;
       dp[(RD_ODOMP + 2) * 32] += (double)dpos.z;
-      Q4<T> nq = qmul(oq, q_axis_z(dw * ct.dt));
+      Q4<T> nq = qmul(oq, q_axis_z(ow * ct.dt));
       sp[(RS_ODOMQ) * 32] = S(nq.w);
       sp[(RS_ODOMQ + 1) * 32] = S(nq.x);
       sp[(RS_ODOMQ + 2) * 32] = S(nq.y);

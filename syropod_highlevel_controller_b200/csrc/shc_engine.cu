@@ -27,11 +27,11 @@ using PrecMixed = Prec<float, float, double>;  // fp32 state + trajectory; fp64 
 #define SHC_BLOCK 128
 #endif
 
-template <class P, int D>
+template <class P, int D, bool FULL>
 __global__ void __launch_bounds__(SHC_BLOCK, SHC_MIN_BLOCKS) control_cycle_kernel(const __grid_constant__ Consts c, Planes<typename P::S> pl, StepIO io) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= c.i.n_robots) return;
-  Cycle<P, D>::run(c, pl, r, io);
+  Cycle<P, D, FULL>::run(c, pl, r, io);
 }
 
 template <int D>
@@ -50,25 +50,26 @@ __global__ void __launch_bounds__(128) apply_ik_kernel(const __grid_constant__ C
     qd[j] = qd_io[(size_t)i * D + j];
   }
   Chain<double, D> ch;
-  leg_chain<double, D>(ck, leg, q, ch);
+  const LegConsts<double>& lc = ck.leg[leg];
+  leg_chain<double, D>(lc, q, ch);
   V3<double> des{desired[3 * (size_t)i], desired[3 * (size_t)i + 1], desired[3 * (size_t)i + 2]};
   V3<double> des_leg;
-  apply_ik_step<double, D>(ck, leg, ch, q, qd, des, c.i.clamp_joint_positions != 0, c.i.clamp_joint_velocities != 0 && !simulation,
+  apply_ik_step<double, D>(ck, lc, ch, q, qd, des, c.i.clamp_joint_positions != 0, c.i.clamp_joint_velocities != 0 && !simulation,
                            &des_leg);
   Chain<double, D> ch2;
-  leg_chain<double, D>(ck, leg, q, ch2);
+  leg_chain<double, D>(lc, q, ch2);
 #pragma unroll
   for (int j = 0; j < D; ++j) {
     q_io[(size_t)i * D + j] = q[j];
     qd_io[(size_t)i * D + j] = qd[j];
   }
   if (tip_out) {
-    V3<double> t = t1_rotate(ck, leg, ch2.tip) + V3<double>{ck.t1p[leg][0], ck.t1p[leg][1], ck.t1p[leg][2]};
+    V3<double> t = t1_rotate(lc, ch2.tip) + V3<double>{lc.t1p[0], lc.t1p[1], lc.t1p[2]};
     tip_out[3 * (size_t)i] = t.x;
     tip_out[3 * (size_t)i + 1] = t.y;
     tip_out[3 * (size_t)i + 2] = t.z;
   }
-  if (result) result[i] = ik_result_value<double, D>(ck, leg, ch2, q, des_leg);
+  if (result) result[i] = ik_result_value<double, D>(lc, ch2, q, des_leg);
 }
 
 }  // namespace shc
@@ -429,14 +430,18 @@ template <class F> static int dispatch_D(int D, F&& f) {
 static int launch_cycle(shc_engine* e, const StepIO& io, cudaStream_t st) {
   const int threads = SHC_BLOCK;
   const int blocks = (e->n + threads - 1) / threads;
+  const bool full = e->cfg.auto_posing || e->cfg.admittance_control || e->cfg.imu_posing || e->cfg.inclination_posing ||
+                    e->cfg.use_joint_effort;
   return dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int {
     constexpr int D = decltype(dtag)::value;
     if (e->precision == SHC_PRECISION_F64) {
       Planes<double> pl{(double*)e->s_planes, e->d_planes, e->i_planes};
-      control_cycle_kernel<PrecF64, D><<<blocks, threads, 0, st>>>(e->c, pl, io);
+      if (full) control_cycle_kernel<PrecF64, D, true><<<blocks, threads, 0, st>>>(e->c, pl, io);
+      else control_cycle_kernel<PrecF64, D, false><<<blocks, threads, 0, st>>>(e->c, pl, io);
     } else {
       Planes<float> pl{(float*)e->s_planes, e->d_planes, e->i_planes};
-      control_cycle_kernel<PrecMixed, D><<<blocks, threads, 0, st>>>(e->c, pl, io);
+      if (full) control_cycle_kernel<PrecMixed, D, true><<<blocks, threads, 0, st>>>(e->c, pl, io);
+      else control_cycle_kernel<PrecMixed, D, false><<<blocks, threads, 0, st>>>(e->c, pl, io);
     }
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(SHC_E_CUDA, std::string("control_cycle launch: ") + cudaGetErrorString(err));

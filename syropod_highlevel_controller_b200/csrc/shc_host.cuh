@@ -39,29 +39,29 @@ template <class R> void fill_static_consts(const shc_config& c, RealConsts<R>& k
   for (int l = 0; l < c.leg_count; ++l) {
     double th = c.link_theta[l][0], al = c.link_alpha[l][0], r = c.link_r[l][0], d = c.link_d[l][0];
     double m[9] = {cos(th), -sin(th) * cos(al), sin(th) * sin(al), sin(th), cos(th) * cos(al), -cos(th) * sin(al), 0.0, sin(al), cos(al)};
-    for (int i = 0; i < 9; ++i) k.t1r[l][i] = R(m[i]);
-    k.t1p[l][0] = R(r * cos(th)); k.t1p[l][1] = R(r * sin(th)); k.t1p[l][2] = R(d);
+    for (int i = 0; i < 9; ++i) k.leg[l].t1r[i] = R(m[i]);
+    k.leg[l].t1p[0] = R(r * cos(th)); k.leg[l].t1p[1] = R(r * sin(th)); k.leg[l].t1p[2] = R(d);
     for (int j = 0; j < c.joint_count; ++j) {
-      k.dh_d[l][j] = R(c.link_d[l][j + 1]);
-      k.dh_theta[l][j] = R(c.link_theta[l][j + 1]);
-      k.dh_r[l][j] = R(c.link_r[l][j + 1]);
-      k.dh_ca[l][j] = R(cos(c.link_alpha[l][j + 1]));
-      k.dh_sa[l][j] = R(sin(c.link_alpha[l][j + 1]));
+      k.leg[l].dh_d[j] = R(c.link_d[l][j + 1]);
+      k.leg[l].dh_theta[j] = R(c.link_theta[l][j + 1]);
+      k.leg[l].dh_r[j] = R(c.link_r[l][j + 1]);
+      k.leg[l].dh_ca[j] = R(cos(c.link_alpha[l][j + 1]));
+      k.leg[l].dh_sa[j] = R(sin(c.link_alpha[l][j + 1]));
       double lo = c.joint_min[l][j], hi = c.joint_max[l][j], vm = c.joint_max_vel[l][j];
       double range = hi - lo;
-      k.jmin[l][j] = R(lo); k.jmax[l][j] = R(hi); k.vmax[l][j] = R(vm);
-      k.joffset[l][j] = R(c.joint_offset[l][j]);
-      k.jcentre[l][j] = R(lo + range / 2.0);
-      k.jcost_pos[l][j] = R(range != 0.0 ? w / range : 0.0);
-      k.jgrad_pos[l][j] = R(range != 0.0 ? -(w * w) / (range * range) : 0.0);
+      k.leg[l].jmin[j] = R(lo); k.leg[l].jmax[j] = R(hi); k.leg[l].vmax[j] = R(vm);
+      k.leg[l].joffset[j] = R(c.joint_offset[l][j]);
+      k.leg[l].jcentre[j] = R(lo + range / 2.0);
+      k.leg[l].jcost_pos[j] = R(range != 0.0 ? w / range : 0.0);
+      k.leg[l].jgrad_pos[j] = R(range != 0.0 ? -(w * w) / (range * range) : 0.0);
       double vr = 2 * vm;
-      k.jcost_vel[l][j] = R(w / vr);
-      k.jgrad_vel[l][j] = R(-(w * w) / (vr * vr));
+      k.leg[l].jcost_vel[j] = R(w / vr);
+      k.leg[l].jgrad_vel[j] = R(-(w * w) / (vr * vr));
     }
-    k.identity_x[l] = R(c.stance_x[l]);
-    k.identity_y[l] = R(c.stance_y[l]);
-    k.ysign[l] = R(c.stance_y[l] > 0.0 ? 1.0 : -1.0);
-    k.neg_ratio[l] = R(c.negation_transition_ratio[l]);
+    k.leg[l].identity_x = R(c.stance_x[l]);
+    k.leg[l].identity_y = R(c.stance_y[l]);
+    k.leg[l].ysign = R(c.stance_y[l] > 0.0 ? 1.0 : -1.0);
+    k.leg[l].neg_ratio = R(c.negation_transition_ratio[l]);
   }
   k.dt = R(c.time_delta);
   k.inv_dt = R(1.0 / c.time_delta);
@@ -173,20 +173,20 @@ template <int D>
 double host_apply_ik(const RealConsts<double>& ck, const shc_config& c, int leg, double* q, double* qd, V3<double> desired,
                      bool simulation, V3<double>* tip_robot) {
   Chain<double, D> ch;
-  leg_chain<double, D>(ck, leg, q, ch);
+  leg_chain<double, D>(ck.leg[leg], q, ch);
   V3<double> des_leg;
-  apply_ik_step<double, D>(ck, leg, ch, q, qd, desired, c.clamp_joint_positions != 0, c.clamp_joint_velocities != 0 && !simulation,
+  apply_ik_step<double, D>(ck, ck.leg[leg], ch, q, qd, desired, c.clamp_joint_positions != 0, c.clamp_joint_velocities != 0 && !simulation,
                            &des_leg);
   Chain<double, D> ch2;
-  leg_chain<double, D>(ck, leg, q, ch2);
-  if (tip_robot) *tip_robot = t1_rotate(ck, leg, ch2.tip) + V3<double>{ck.t1p[leg][0], ck.t1p[leg][1], ck.t1p[leg][2]};
-  return ik_result_value<double, D>(ck, leg, ch2, q, des_leg);
+  leg_chain<double, D>(ck.leg[leg], q, ch2);
+  if (tip_robot) *tip_robot = t1_rotate(ck.leg[leg], ch2.tip) + V3<double>{ck.leg[leg].t1p[0], ck.leg[leg].t1p[1], ck.leg[leg].t1p[2]};
+  return ik_result_value<double, D>(ck.leg[leg], ch2, q, des_leg);
 }
 
 template <int D> V3<double> host_fk(const RealConsts<double>& ck, int leg, const double* q) {
   Chain<double, D> ch;
-  leg_chain<double, D>(ck, leg, q, ch);
-  return t1_rotate(ck, leg, ch.tip) + V3<double>{ck.t1p[leg][0], ck.t1p[leg][1], ck.t1p[leg][2]};
+  leg_chain<double, D>(ck.leg[leg], q, ch);
+  return t1_rotate(ck.leg[leg], ch.tip) + V3<double>{ck.leg[leg].t1p[0], ck.leg[leg].t1p[1], ck.leg[leg].t1p[2]};
 }
 
 // directStartup + generateWorkspaces + generateWalkspace + generateLimits.
@@ -376,14 +376,14 @@ template <class R> void fill_startup_consts(const shc_config& c, const shc_start
     ci.mod_stance_start[l] = su.phase_offsets[l];
     int mp = imod(su.stance_end - su.phase_offsets[l], su.period);
     if (su.stance_end == su.phase_offsets[l]) mp = su.period;
-    k.stance_dt_mod[l] = R(1.0 / stance_iter(mp));
-    k.stride_scaler_mod[l] = R(double(mp) / imod(su.stance_end - su.stance_start, su.period));
+    k.leg[l].stance_dt_mod = R(1.0 / stance_iter(mp));
+    k.leg[l].stride_scaler_mod = R(double(mp) / imod(su.stance_end - su.stance_start, su.period));
     // LegStepper::calculateStanceSpanChange (:949) with the one-plane workspace
     double ssm = c.stance_span_modifier;
     bool pos_y = c.stance_y[l] > 0.0;
     int bearing = (pos_y ^ (ssm > 0.0)) ? 270 : 90;
     ssm *= (pos_y ? 1.0 : -1.0);
-    k.span_dy[l] = R(su.workspace[l][bearing / 45] * ssm);
+    k.leg[l].span_dy = R(su.workspace[l][bearing / 45] * ssm);
   }
   double ogr = double(su.stance_period) / su.period;
   k.stride_scale = R(ogr / su.step_frequency);
