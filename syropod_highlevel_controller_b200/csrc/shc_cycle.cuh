@@ -95,14 +95,12 @@ template <class K> SHC_HD V3<K> t1_rotate_inv(const LegConsts<K>& lc, V3<K> v) {
 
 // Solve the symmetric positive definite 3x3 system A x = b (A = Jp Jp^T + lambda^2 I) by Cholesky.
 template <class K> SHC_HD V3<K> spd3_solve(K a00, K a01, K a02, K a11, K a12, K a22, V3<K> b) {
-  K l00 = sqrt_(a00);
-  K i00 = K(1) / l00;
+  // only the reciprocals of the Cholesky diagonal are needed
+  K i00 = rsqrt_(a00);
   K l10 = a01 * i00, l20 = a02 * i00;
-  K l11 = sqrt_(a11 - l10 * l10);
-  K i11 = K(1) / l11;
+  K i11 = rsqrt_(a11 - l10 * l10);
   K l21 = (a12 - l20 * l10) * i11;
-  K l22 = sqrt_(a22 - l20 * l20 - l21 * l21);
-  K i22 = K(1) / l22;
+  K i22 = rsqrt_(a22 - l20 * l20 - l21 * l21);
   K y0 = b.x * i00;
   K y1 = (b.y - l10 * y0) * i11;
   K y2 = (b.z - l20 * y0 - l21 * y1) * i22;
@@ -191,8 +189,8 @@ SHC_HD void solve_ik(const RealConsts<K>& ck, const LegConsts<K>& lc, const Chai
     vel_cost += cv * cv;
     gv[j] = lc.jgrad_vel[j] * qd[j];
   }
-  K sp = pos_cost == K(0) ? K(0) : K(1) / sqrt_(pos_cost);
-  K sv = vel_cost == K(0) ? K(0) : K(1) / sqrt_(vel_cost);
+  K sp = pos_cost == K(0) ? K(0) : rsqrt_(pos_cost);
+  K sv = vel_cost == K(0) ? K(0) : rsqrt_(vel_cost);
   V3<K> Jg{K(0), K(0), K(0)};
 #pragma unroll
   for (int j = 0; j < D; ++j) {
@@ -218,7 +216,7 @@ SHC_HD int apply_ik_step(const RealConsts<K>& ck, const LegConsts<K>& lc, const 
   int status = 0;
 #pragma unroll
   for (int j = 0; j < D; ++j) {
-    K v = dq[j] / ck.dt;
+    K v = dq[j] * ck.inv_dt;
     if (clamp_velocities && abs_(v) > lc.vmax[j]) {
       v = clamp_(v, -lc.vmax[j], lc.vmax[j]);
       status |= 4;
@@ -676,6 +674,9 @@ template <class P, int D, bool FULL> struct Cycle {
     // =================================================================================================================
     // 3. per leg: walk state machine + LegStepper + updateStance + Leg::applyIK
     // =================================================================================================================
+    // integer state of the next leg is fetched one iteration ahead: it decides the control flow at the top of the body
+    int next_bits = ip[(ci.offI_leg + LI_BITS) * 32];
+    int next_prog = ip[(ci.offI_leg + LI_PROG) * 32];
 #pragma unroll 1
     for (int l = 0; l < L; ++l) {
       // per-leg plane bases: every field of this leg is at an immediate offset from these pointers
@@ -685,8 +686,25 @@ template <class P, int D, bool FULL> struct Cycle {
       const LegConsts<K>& lk = ck.leg[l];
       const LegConsts<T>& lt = ct.leg[l];
       if (lane == 0 && l + 1 < L) l2_prefetch_bulk(sl - lane + ci.strideS_leg * 32, leg_chunk_bytes);  // next leg -> L2
-      int bits = il[(LI_BITS) * 32];
-      int prog = il[(LI_PROG) * 32];
+      int bits = next_bits;
+      int prog = next_prog;
+      // every unconditional load of this leg is issued here, back to back, so their latencies overlap
+      double tipx = dl[(LD_TIP) * 32];
+      double tipy = dl[(LD_TIP + 1) * 32];
+      double tipz = dl[(LD_TIP + 2) * 32];
+      V3<T> def = ld3T(sl, LS::DEF);
+      V3<T> stride = ld3T(sl, LS::STRIDE);
+      V3<T> tgt = ld3T(sl, LS::TGT);
+      K q[D], qd[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        q[j] = K(sl[(LS::Q + j) * 32]);
+        qd[j] = K(sl[(LS::QD + j) * 32]);
+      }
+      if (l + 1 < L) {
+        next_bits = il[(ci.strideI_leg + LI_BITS) * 32];
+        next_prog = il[(ci.strideI_leg + LI_PROG) * 32];
+      }
       int phase = bits & 0xffff;
       int step_state = (bits >> 16) & 3;
       bool at_correct = (bits >> 18) & 1;
@@ -694,10 +712,6 @@ template <class P, int D, bool FULL> struct Cycle {
       bool negate = (bits >> 20) & 1;
       int swing_num = (int)(short)(prog & 0xffff);
       int stance_num = (int)(short)((prog >> 16) & 0xffff);
-
-      double tipx = dl[(LD_TIP) * 32];
-      double tipy = dl[(LD_TIP + 1) * 32];
-      double tipz = dl[(LD_TIP + 2) * 32];
 
       // LegPoser::updateAutoPose (pose_controller.cpp:1716) — uses the step state of the previous cycle
       PoseT<K> leg_auto = auto_pose;
@@ -730,8 +744,6 @@ template <class P, int D, bool FULL> struct Cycle {
         leg_auto = pose_identity<K>();  // LegPoser::auto_pose_ is only refreshed by updateAutoPose; IMU posing keeps identity
       }
 
-      V3<T> def = ld3T(sl, LS::DEF);
-
       if (starting_now) {
         // walk_controller.cpp:535-545
         at_correct = false;
@@ -741,8 +753,6 @@ template <class P, int D, bool FULL> struct Cycle {
         if (phase >= ci.swing_start && phase < ci.swing_end) step_state = STEP_SWING;
         else if (phase < ci.stance_end || phase >= ci.stance_start) step_state = STEP_STANCE;
       } else {
-        V3<T> stride = ld3T(sl, LS::STRIDE);
-        V3<T> tgt = ld3T(sl, LS::TGT);
         // ---- walk state machine for this leg (walk_controller.cpp:573-632) ----
         if (walk_state == WALK_STARTING) {
           if (legs_at_correct == L) {
@@ -905,12 +915,6 @@ template <class P, int D, bool FULL> struct Cycle {
       V3<K> desired = pose_inverse_transform(leg_pose, V3<K>{K(tipx), K(tipy), K(tipz)});
 
       // ---- joint state + chain at the previous joint angles ----
-      K q[D], qd[D];
-#pragma unroll
-      for (int j = 0; j < D; ++j) {
-        q[j] = K(sl[(LS::Q + j) * 32]);
-        qd[j] = K(sl[(LS::QD + j) * 32]);
-      }
       Chain<K, D> ch;
       leg_chain<K, D>(lk, q, ch);
 

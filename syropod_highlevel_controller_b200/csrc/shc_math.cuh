@@ -19,8 +19,20 @@ namespace shc {
 constexpr double kPi = 3.14159265358979323846;
 
 // ---- overload set so templated code picks the right-precision routine ------------------------------------------
-SHC_HD float rsqrt_(float x) { return 1.0f / sqrtf(x); }
-SHC_HD double rsqrt_(double x) { return 1.0 / sqrt(x); }
+SHC_HD float rsqrt_(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+SHC_HD double rsqrt_(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);  // MUFU.RSQ64H seed + Newton steps: ~1 ulp, a third of the instructions of sqrt followed by a divide
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
 SHC_HD float sqrt_(float x) { return sqrtf(x); }
 SHC_HD double sqrt_(double x) { return sqrt(x); }
 SHC_HD float abs_(float x) { return fabsf(x); }
@@ -80,7 +92,7 @@ template <class R> SHC_HD R norm(V3<R> a) { return sqrt_(dot(a, a)); }
 // Eigen normalized(): unchanged when the squared norm is not > 0
 template <class R> SHC_HD V3<R> normalized(V3<R> a) {
   R n2 = dot(a, a);
-  return n2 > R(0) ? a * (R(1) / sqrt_(n2)) : a;
+  return n2 > R(0) ? a * rsqrt_(n2) : a;
 }
 template <class A, class B> SHC_HD V3<A> cvt(V3<B> v) { return {A(v.x), A(v.y), A(v.z)}; }
 // standard_includes.h:173 / :190
