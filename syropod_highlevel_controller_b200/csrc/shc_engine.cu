@@ -412,7 +412,20 @@ template <int D> void unpack(const shc_engine* e, const HostPlanes& h, shc_robot
       g.stance_progress = tn < 0 ? -1.0 : (double)tn / (double)ci.stance_period;
       V3<double> tip = host_fk<D>(ck, l, g.joint_position);  // Leg::current_tip_pose_ = FK(joint positions)
       g.model_tip_position[0] = tip.x; g.model_tip_position[1] = tip.y; g.model_tip_position[2] = tip.z;
-      g.ik_result = 1.0;
+      {  // Leg::desired_tip_pose_ = poser tip pose (+ admittance delta); the per-leg auto pose is not stored
+        PoseT<double> cp{{s.current_pose[0], s.current_pose[1], s.current_pose[2]},
+                         {s.current_pose[3], s.current_pose[4], s.current_pose[5], s.current_pose[6]}};
+        V3<double> des = pose_inverse_transform(cp, V3<double>{g.tip_position[0], g.tip_position[1], g.tip_position[2]});
+        g.desired_tip_position[0] = des.x + g.admittance_delta[0];
+        g.desired_tip_position[1] = des.y + g.admittance_delta[1];
+        g.desired_tip_position[2] = des.z + g.admittance_delta[2];
+        // Leg::applyIK's return value (model.cpp:845-856, 916-929)
+        Chain<double, D> ch;
+        leg_chain<double, D>(ck.leg[l], g.joint_position, ch);
+        V3<double> des_leg = t1_rotate_inv(ck.leg[l], V3<double>{g.desired_tip_position[0], g.desired_tip_position[1], g.desired_tip_position[2]} -
+                                                        V3<double>{ck.leg[l].t1p[0], ck.leg[l].t1p[1], ck.leg[l].t1p[2]});
+        g.ik_result = ik_result_value<double, D>(ck.leg[l], ch, g.joint_position, des_leg);
+      }
     }
   }
 }
