@@ -167,7 +167,7 @@ def main():
 
     from syropod_highlevel_controller_b200.config import hexapod_config
     from syropod_highlevel_controller_b200.engine import Engine
-    from syropod_highlevel_controller_b200.parallel import JointGather, shard_robots
+    from syropod_highlevel_controller_b200.parallel import shard_robots
     from syropod_highlevel_controller_b200.streams import CommandStream
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -191,19 +191,21 @@ def main():
     pre = 300  # untimed pre-roll so that the batch is in its steady mix of walk states (STARTING/MOVING/STOPPING/STOPPED)
     cmd_host = np.stack([cs.next() for _ in range(pre + W + K)])
     cmd_dev = torch.from_numpy(cmd_host).to(dev)
-    gather = JointGather(shard, L, D, dev) if world > 1 else None
+    # N > 1: one NCCL all-gather of the joint angles per cycle, issued by the library on a side stream and double
+    # buffered so that cycle t's gather overlaps cycle t+1's kernel (shc_rollout_allgather)
+    if world > 1:
+        eng.init_nccl(rank, world)
+        local2 = torch.empty((2, n, L, D), dtype=torch.float32, device=dev)
+        full2 = torch.empty((2, n * world, L, D), dtype=torch.float32, device=dev)
 
-    def step(i):
-        if gather is None:
-            eng.step(cmd_dev[i])
+    def run(lo, hi):
+        if world == 1:
+            for i in range(lo, hi):
+                eng.step(cmd_dev[i])
         else:
-            eng.step(cmd_dev[i], out=gather.next_local_buffer())
-            gather.gather()
+            eng.rollout_allgather(cmd_dev[lo:hi], local2, full2)
 
-    for i in range(pre + W):
-        step(i)
-    if gather is not None:
-        gather.wait()
+    run(0, pre + W)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -212,10 +214,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
-    for i in range(pre + W, pre + W + K):
-        step(i)
-    if gather is not None:
-        gather.wait()
+    run(pre + W, pre + W + K)
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:

@@ -114,6 +114,20 @@ int shc_rollout(shc_engine* e, int k_cycles, const float* cmd_seq, const float* 
  * pointer float [N][L][D], latched until changed; NULL = all zero.  Only read when use_joint_effort is set. */
 int shc_set_joint_efforts(shc_engine* e, const float* efforts_dev);
 
+/* Multi-GPU: robots are independent, so the batch is sharded across ranks with no data-path
+ * collective; the one exchange is an all-gather of the joint angles per control cycle (BASELINE configs[4]).  NCCL is
+ * resolved at run time from the libnccl already loaded in the process.
+ *   shc_nccl_unique_id   rank 0 creates the 128-byte id, the caller broadcasts it (e.g. torch.distributed)
+ *   shc_nccl_init        every rank joins (one communicator per engine)
+ *   shc_allgather_joints local [n][L][D] -> full [world*n][L][D] on `stream` (NULL = the engine's side stream)
+ *   shc_rollout_allgather k cycles; cycle t's gather runs on a side stream, double buffered (local2 = 2 x [n][L][D],
+ *                        full2 = 2 x [world*n][L][D]), overlapping cycle t+1's kernel; `stream` resumes after the last
+ *                        gather. */
+int shc_nccl_unique_id(void* out128);
+int shc_nccl_init(shc_engine* e, const void* uid128, int rank, int world_size);
+int shc_allgather_joints(shc_engine* e, const float* local, float* full, void* stream);
+int shc_rollout_allgather(shc_engine* e, int k_cycles, const float* cmd_seq, float* local2, float* full2, void* stream);
+
 /* The engine's own CUDA stream (cudaStream_t) and a blocking wait on it. */
 void* shc_stream(shc_engine* e);
 int shc_synchronize(shc_engine* e);

@@ -34,7 +34,9 @@ struct StepIO {
   const float* tip_force;  // [N][L][3] or null
   const float* manual;     // [N][6] or null
   const float* efforts;    // [N][L][D] or null: measured joint efforts (jointStatesCallback, state_controller.cpp:1565)
-  float* joints_out;       // [N][L][D]
+  float* joints_out;       // [N][L][D] (destination 0)
+  float* peer_out[7];      // fused all-gather: this shard's slice inside up to 7 peer GPUs' gather buffers (NVLink stores)
+  int n_peers;             // number of valid peer_out entries
   int* flags_out;          // [N] or null
   int pose_reset_mode;
 };
@@ -347,7 +349,9 @@ template <class P, int D, bool FULL> struct Cycle {
     return {v.x, c * v.y - s * v.z, s * v.y + c * v.z};
   }
 
-  static __device__ void run(const Consts& c, Planes<S> pl, int r, const StepIO& io) {
+  // `stage` = this robot's L*D floats inside the warp's shared-memory tile: the joint commands are staged there and
+  // written out by the whole warp as coalesced 128-byte lines (to HBM and, when sharded, to every peer GPU).
+  static __device__ void run(const Consts& c, Planes<S> pl, int r, const StepIO& io, float* __restrict__ stage) {
     const IntConsts& ci = c.i;
     const RealConsts<T>& ct = ConstSel<T>::get(c);
     const RealConsts<K>& ck = ConstSel<K>::get(c);
@@ -958,7 +962,7 @@ template <class P, int D, bool FULL> struct Cycle {
       for (int j = 0; j < D; ++j) {
         sl[(LS::Q + j) * 32] = S(q[j]);
         sl[(LS::QD + j) * 32] = S(qd[j]);
-        io.joints_out[((size_t)r * L + l) * D + j] = (float)(q[j] + lk.joffset[j]);  // state_controller.cpp:795
+        stage[l * D + j] = (float)(q[j] + lk.joffset[j]);  // state_controller.cpp:795
       }
       if (io.flags_out || f_effort) {
         // applyFK at the new joint angles (model.cpp:904) for the IK tolerance check (:916-929)

@@ -5,6 +5,7 @@
 //   apply_ik_kernel<D>          stand-alone batched Leg::applyIK (model.cpp:861) in double
 // There is no CPU fallback: every entry point that computes needs a CUDA device.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -29,9 +30,28 @@ using PrecMixed = Prec<float, float, double>;  // fp32 state + trajectory; fp64 
 
 template <class P, int D, bool FULL>
 __global__ void __launch_bounds__(SHC_BLOCK, SHC_MIN_BLOCKS) control_cycle_kernel(const __grid_constant__ Consts c, Planes<typename P::S> pl, StepIO io) {
+  // per-warp staging tile for the joint commands: [32 robots][L*D] floats, the layout of joints_out
+  __shared__ float stage[SHC_BLOCK / 32][32 * kMaxLegs * D];
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= c.i.n_robots) return;
-  Cycle<P, D, FULL>::run(c, pl, r, io);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int LD = c.i.L * D;
+  if (r < c.i.n_robots) Cycle<P, D, FULL>::run(c, pl, r, io, &stage[warp][lane * LD]);
+  __syncwarp();
+  // Fused output + all-gather: the warp writes its tile as coalesced 128-byte lines to the local buffer and straight
+  // into every peer GPU's gather buffer over NVLink (peer-mapped pointers), so the transfer overlaps the computation
+  // of the other tiles instead of running as a separate collective after the kernel.
+  const int tile_first = r - lane;
+  const int valid = min(32, c.i.n_robots - tile_first) * LD;
+  if (valid > 0) {
+    const size_t base = (size_t)tile_first * LD;
+    const float* src = stage[warp];
+    float* dst0 = io.joints_out + base;
+    for (int i = lane; i < valid; i += 32) dst0[i] = src[i];
+    for (int p = 0; p < io.n_peers; ++p) {
+      float* dst = io.peer_out[p] + base;
+      for (int i = lane; i < valid; i += 32) dst[i] = src[i];
+    }
+  }
 }
 
 template <int D>
@@ -120,7 +140,45 @@ struct shc_engine {
   float *h_cmd = nullptr, *h_imu = nullptr, *h_force = nullptr, *h_manual = nullptr, *h_out = nullptr;
   float *d_cmd = nullptr, *d_imu = nullptr, *d_force = nullptr, *d_manual = nullptr, *d_out = nullptr;
   std::map<GraphKey, cudaGraphExec_t> graphs;
+  // multi-GPU: NCCL communicator (opaque) + side stream / events for the overlapped per-cycle all-gather
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  bool done_valid[2] = {false, false};
 };
+
+// NCCL is resolved at run time from the libnccl already loaded in the process (torch's), so libshc_b200.so has no
+// link-time dependency on it and single-GPU users never touch it.
+namespace {
+struct NcclUid { char internal[128]; };
+struct NcclApi {
+  int (*GetUniqueId)(NcclUid*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      api.GetUniqueId = (int (*)(NcclUid*))dlsym(h, "ncclGetUniqueId");
+      api.CommInitRank = (int (*)(void**, int, NcclUid, int))dlsym(h, "ncclCommInitRank");
+      api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+      api.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+      api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy;
+    }
+  }
+  return api;
+}
+}  // namespace
 
 static void layout(const shc_config& cfg, int n, IntConsts& ci) {
   ci.L = cfg.leg_count;
@@ -586,6 +644,12 @@ void shc_destroy(shc_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  if (e->nccl_comm && nccl().ok) nccl().CommDestroy(e->nccl_comm);
+  for (int b = 0; b < 2; ++b) {
+    if (e->ev_ready[b]) cudaEventDestroy(e->ev_ready[b]);
+    if (e->ev_done[b]) cudaEventDestroy(e->ev_done[b]);
+  }
+  if (e->side) cudaStreamDestroy(e->side);
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->s_planes);
   cudaFree(e->d_planes);
@@ -647,6 +711,8 @@ int shc_step(shc_engine* e, const float* cmd, const float* imu, const float* tip
   StepIO io;
   io.cmd = cmd; io.imu = imu; io.tip_force = tip_force; io.manual = manual; io.efforts = e->d_efforts;
   io.joints_out = joints_out;
+  io.n_peers = 0;
+  for (int p = 0; p < 7; ++p) io.peer_out[p] = nullptr;
   io.flags_out = (e->options & SHC_OPT_STATUS_FLAGS) ? e->d_flags : nullptr;
   io.pose_reset_mode = e->pose_reset_mode;
   return launch_cycle(e, io, stream ? (cudaStream_t)stream : e->stream);
@@ -760,6 +826,65 @@ int shc_apply_ik(shc_engine* e, int n_legs, const int* leg_id, double* q, double
     if (err != cudaSuccess) return fail(SHC_E_CUDA, std::string("apply_ik launch: ") + cudaGetErrorString(err));
     return SHC_OK;
   });
+}
+
+int shc_nccl_unique_id(void* out128) {
+  if (!out128) return fail(SHC_E_INVALID, "null argument");
+  if (!nccl().ok) return fail(SHC_E_UNSUPPORTED, "libnccl.so.2 is not available in this process");
+  int rc = nccl().GetUniqueId((NcclUid*)out128);
+  if (rc != 0) return fail(SHC_E_CUDA, std::string("ncclGetUniqueId: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error"));
+  return SHC_OK;
+}
+
+int shc_nccl_init(shc_engine* e, const void* uid128, int rank, int world_size) {
+  if (!e || !uid128 || rank < 0 || rank >= world_size) return fail(SHC_E_INVALID, "shc_nccl_init: bad arguments");
+  if (!nccl().ok) return fail(SHC_E_UNSUPPORTED, "libnccl.so.2 is not available in this process");
+  CUDA_TRY(cudaSetDevice(e->device));
+  NcclUid uid;
+  std::memcpy(&uid, uid128, sizeof(uid));
+  int rc = nccl().CommInitRank(&e->nccl_comm, world_size, uid, rank);
+  if (rc != 0) return fail(SHC_E_CUDA, std::string("ncclCommInitRank: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error"));
+  e->rank = rank;
+  e->world = world_size;
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_ready[b], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_done[b], cudaEventDisableTiming));
+  }
+  return SHC_OK;
+}
+
+int shc_allgather_joints(shc_engine* e, const float* local, float* full, void* stream) {
+  if (!e || !local || !full) return fail(SHC_E_INVALID, "shc_allgather_joints: bad arguments");
+  if (!e->nccl_comm) return fail(SHC_E_INVALID, "shc_nccl_init has not been called");
+  size_t count = (size_t)e->n * e->cfg.leg_count * e->cfg.joint_count;
+  int rc = nccl().AllGather(local, full, count, /*ncclFloat32*/ 7, e->nccl_comm, stream ? (cudaStream_t)stream : e->side);
+  if (rc != 0) return fail(SHC_E_CUDA, std::string("ncclAllGather: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error"));
+  return SHC_OK;
+}
+
+int shc_rollout_allgather(shc_engine* e, int k_cycles, const float* cmd_seq, float* local2, float* full2, void* stream) {
+  if (!e || !cmd_seq || !local2 || !full2 || k_cycles < 1) return fail(SHC_E_INVALID, "shc_rollout_allgather: bad arguments");
+  if (!e->nccl_comm) return fail(SHC_E_INVALID, "shc_nccl_init has not been called");
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  const size_t n = e->n, per_rank = n * e->cfg.leg_count * e->cfg.joint_count;
+  for (int k = 0; k < k_cycles; ++k) {
+    const int b = k & 1;
+    if (e->done_valid[b]) CUDA_TRY(cudaStreamWaitEvent(st, e->ev_done[b], 0));  // buffer b's previous gather has drained
+    int rc = shc_step(e, cmd_seq + (size_t)k * n * 3, nullptr, nullptr, nullptr, local2 + b * per_rank, st);
+    if (rc != SHC_OK) return rc;
+    CUDA_TRY(cudaEventRecord(e->ev_ready[b], st));
+    CUDA_TRY(cudaStreamWaitEvent(e->side, e->ev_ready[b], 0));
+    rc = shc_allgather_joints(e, local2 + b * per_rank, full2 + (size_t)b * per_rank * e->world, e->side);
+    if (rc != SHC_OK) return rc;
+    CUDA_TRY(cudaEventRecord(e->ev_done[b], e->side));
+    e->done_valid[b] = true;
+  }
+  // join: the caller's stream continues only after the last gathers
+  for (int b = 0; b < 2; ++b)
+    if (e->done_valid[b]) CUDA_TRY(cudaStreamWaitEvent(st, e->ev_done[b], 0));
+  return SHC_OK;
 }
 
 int shc_synchronize(shc_engine* e) {

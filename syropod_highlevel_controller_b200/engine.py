@@ -54,6 +54,10 @@ def lib():
         L.shc_step_host.argtypes = [vp, fp, fp, fp, fp, fp]
         L.shc_rollout.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
         L.shc_set_joint_efforts.argtypes = [vp, vp]
+        L.shc_nccl_unique_id.argtypes = [vp]
+        L.shc_nccl_init.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.shc_allgather_joints.argtypes = [vp, vp, vp, vp]
+        L.shc_rollout_allgather.argtypes = [vp, C.c_int, vp, vp, vp, vp]
         L.shc_stream.argtypes = [vp]
         L.shc_stream.restype = vp
         L.shc_synchronize.argtypes = [vp]
@@ -229,6 +233,33 @@ class Engine:
                                  _stream_handle(torch, self.device, stream)))
         self._keep = (cmd_seq, imu_seq, force_seq)
         return out
+
+    # ---- multi-GPU ---------------------------------------------------------------------------------------------------
+    def init_nccl(self, rank: int, world_size: int):
+        """Joins this engine to an NCCL communicator over the ranks of the default torch.distributed group (the 128-byte
+        unique id travels through torch.distributed; the collective itself is issued by the library)."""
+        import torch.distributed as dist
+
+        torch = self.torch
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_char * 128)()
+            _check(lib().shc_nccl_unique_id(buf))
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        uid = uid.to(self.device)
+        dist.broadcast(uid, src=0)
+        raw = bytes(uid.cpu().numpy().tobytes())
+        _check(lib().shc_nccl_init(self._h, C.c_char_p(raw), rank, world_size))
+        self.world_size = world_size
+
+    def rollout_allgather(self, cmd_seq, local2, full2, stream=None):
+        """k cycles, each followed by the all-gather of its joint angles (overlapped, double buffered)."""
+        torch = self.torch
+        k = int(cmd_seq.shape[0])
+        assert cmd_seq.is_cuda and cmd_seq.dtype == torch.float32 and cmd_seq.is_contiguous()
+        _check(lib().shc_rollout_allgather(self._h, k, _ptr(cmd_seq), _ptr(local2), _ptr(full2),
+                                           _stream_handle(torch, self.device, stream)))
+        self._keep = (cmd_seq, local2, full2)
 
     def set_joint_efforts(self, efforts):
         efforts = self._f32(efforts, (self.n, self.L, self.D))
