@@ -74,7 +74,9 @@ struct IntConsts {
   int neg_start[kMaxLegs], neg_end[kMaxLegs];
   // plane indices (see shc_layout.h)
   int nS, nD, nI;              // number of storage / double / int planes
-  int offS_imu, offS_auto, offS_leg, strideS_leg, offS_leg_adm;
+  int offS_imu, offS_auto, offS_leg, strideS_leg;
+  int frontS_leg;              // staged admittance planes in front of each leg's joint planes (0 or LegS::FRONT)
+  int smem_per_warp;           // bytes of dynamic shared memory per warp (two staging slots + joint tile + barriers)
   int offD_leg, strideD_leg;
   int offI_leg, strideI_leg, offI_auto;
 };

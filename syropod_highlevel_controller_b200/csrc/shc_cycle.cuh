@@ -41,12 +41,37 @@ struct StepIO {
   int pose_reset_mode;
 };
 
-// TMA bulk prefetch into L2 (cp.async.bulk.prefetch.L2): one lane asks for a whole contiguous chunk of a tile's planes,
-// so the demand loads that follow find their lines in L2 instead of paying the HBM latency inside the dependent chain.
-__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-#endif
+// ---- TMA bulk copies + mbarrier (sm_90+; SASS: UBLKCP.S.G / SYNCS) ------------------------------------------------
+// Each warp owns a two-slot staging ring in shared memory.  Lane 0 asks the TMA unit for the whole contiguous chunk of
+// a leg's every-cycle planes (one cp.async.bulk per plane set) two legs ahead of the arithmetic; completion is
+// signalled on a warp-private mbarrier by byte count.  The dependent chain of a robot therefore never waits on HBM
+// inside the leg loop: its loads are shared-memory reads of data that landed while the previous legs were computed.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
 }
 
 template <class S> struct Planes {
@@ -349,9 +374,21 @@ template <class P, int D, bool FULL> struct Cycle {
     return {v.x, c * v.y - s * v.z, s * v.y + c * v.z};
   }
 
-  // `stage` = this robot's L*D floats inside the warp's shared-memory tile: the joint commands are staged there and
-  // written out by the whole warp as coalesced 128-byte lines (to HBM and, when sharded, to every peer GPU).
-  static __device__ void run(const Consts& c, Planes<S> pl, int r, const StepIO& io, float* __restrict__ stage) {
+  // Bytes of one staging slot: the staged storage planes of a leg, its double planes and its int planes.
+  static __host__ __device__ __forceinline__ int slot_s_bytes(int frontS) { return (LS::STAGED + frontS) * 32 * (int)sizeof(S); }
+  static __host__ __device__ __forceinline__ int slot_bytes(int frontS) {
+    return slot_s_bytes(frontS) + LD_COUNT * 32 * 8 + LI_COUNT * 32 * 4;
+  }
+  // Dynamic shared memory of one warp: [slot 0][slot 1][joint tile: 32 robots x L*D floats][2 mbarriers], 128-B granular.
+  static __host__ __device__ __forceinline__ int smem_per_warp(int frontS, int L) {
+    return (2 * slot_bytes(frontS) + 32 * L * D * 4 + 16 + 127) / 128 * 128;
+  }
+
+  // One warp = one tile of 32 robots (lane = robot).  `wsm` is the warp's shared memory (see smem_per_warp): the joint
+  // commands are staged in its joint tile and written out by the whole warp as coalesced 128-byte lines by the caller.
+  // Lanes past n_robots run on the (initialised) padding robots of the last tile so that the warp-collective staging
+  // stays convergent; they read the inputs of the last real robot and their outputs are dropped by the caller.
+  static __device__ void run(const Consts& c, Planes<S> pl, int tile_idx, int lane, const StepIO& io, unsigned char* __restrict__ wsm) {
     const IntConsts& ci = c.i;
     const RealConsts<T>& ct = ConstSel<T>::get(c);
     const RealConsts<K>& ck = ConstSel<K>::get(c);
@@ -359,14 +396,58 @@ template <class P, int D, bool FULL> struct Cycle {
     const int L = ci.L;
     const bool f_auto = FULL && ci.auto_posing, f_incl = FULL && ci.inclination_posing, f_imu = FULL && ci.imu_posing;
     const bool f_adm = FULL && ci.admittance_control, f_effort = FULL && ci.use_joint_effort;
+    const int front = FULL ? ci.frontS_leg : 0;
     // tile-major planes [tile][plane][32 lanes]: every field of this robot is at a compile-time offset from these bases
-    const size_t tile = (size_t)(r >> 5);
-    const int lane = r & 31;
+    const size_t tile = (size_t)tile_idx;
+    const int r_real = tile_idx * 32 + lane;
+    const bool live = r_real < ci.n_robots;
+    const int r = live ? r_real : ci.n_robots - 1;  // index for the per-robot INPUT arrays only
     S* __restrict__ sp = pl.s + tile * (size_t)(ci.nS * 32) + lane;
     double* __restrict__ dp = pl.d + tile * (size_t)(ci.nD * 32) + lane;
     int* __restrict__ ip = pl.i + tile * (size_t)(ci.nI * 32) + lane;
-    const unsigned leg_chunk_bytes = (unsigned)(ci.strideS_leg * 32 * sizeof(S));
-    if (lane == 0) l2_prefetch_bulk(sp + ci.offS_leg * 32, leg_chunk_bytes);  // leg 0's planes, needed after the pose stage
+
+    // ---- staging ring ------------------------------------------------------------------------------------------------
+    const int sS_bytes = slot_s_bytes(front), s_bytes = slot_bytes(front);
+    float* __restrict__ stage = reinterpret_cast<float*>(wsm + 2 * s_bytes) + lane * (L * D);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + 2 * s_bytes + 32 * L * D * 4);
+    const S* tileS = pl.s + tile * (size_t)(ci.nS * 32);
+    const double* tileD = pl.d + tile * (size_t)(ci.nD * 32);
+    const int* tileI = pl.i + tile * (size_t)(ci.nI * 32);
+    auto issue_leg = [&](int l) {  // lane 0: ask the TMA unit for leg l's every-cycle planes
+      unsigned char* slot = wsm + (l & 1) * s_bytes;
+      uint64_t* bar = bars + (l & 1);
+      mbar_expect_tx(bar, (unsigned)s_bytes);
+      bulk_g2s(slot, tileS + (ci.offS_leg + l * ci.strideS_leg - front) * 32, (unsigned)sS_bytes, bar);
+      bulk_g2s(slot + sS_bytes, tileD + (ci.offD_leg + l * ci.strideD_leg) * 32, LD_COUNT * 32 * 8, bar);
+      bulk_g2s(slot + sS_bytes + LD_COUNT * 32 * 8, tileI + (ci.offI_leg + l * ci.strideI_leg) * 32, LI_COUNT * 32 * 4, bar);
+    };
+    if (lane == 0) {
+      mbar_init(bars, 1);
+      mbar_init(bars + 1, 1);
+      fence_mbar_init();
+      issue_leg(0);
+      if (L > 1) issue_leg(1);
+    }
+    __syncwarp();
+
+    // ---- every unconditional robot-level load, issued back to back (one exposed HBM latency for the whole stage) ------
+    int rbits = ip[(RI_BITS) * 32];
+    int progs[kMaxLegs];
+    double tips_x[kMaxLegs], tips_y[kMaxLegs];
+#pragma unroll
+    for (int l = 0; l < kMaxLegs; ++l) {
+      progs[l] = -1;
+      tips_x[l] = tips_y[l] = 0.0;
+      if (l < L) {
+        progs[l] = ip[(ci.offI_leg + l * ci.strideI_leg + LI_PROG) * 32];
+        tips_x[l] = dp[(ci.offD_leg + l * ci.strideD_leg + LD_TIP) * 32];
+        tips_y[l] = dp[(ci.offD_leg + l * ci.strideD_leg + LD_TIP + 1) * 32];
+      }
+    }
+    PoseT<K> owpp = ldPose(sp, RS_OWPP);
+    PoseT<K> man = pose_identity<K>();
+    if (ci.manual_posing) man = ldPose(sp, RS_MAN);
+    T dvx = T(sp[(RS_VEL) * 32]), dvy = T(sp[(RS_VEL + 1) * 32]), dw = T(sp[(RS_ANGVEL) * 32]);
 
     // ---- inputs: bodyVelocityInputCallback (state_controller.cpp:1127-1136) --------------------------------------
     double vin_x = (double)io.cmd[3 * (size_t)r + 0] * cd.body_velocity_scaler;
@@ -390,7 +471,6 @@ template <class P, int D, bool FULL> struct Cycle {
     // Model::getImuData (model.h:132): undefined orientation reads as identity
     Q4<K> imu_q = (imu_raw.w == K(0) && imu_raw.x == K(0) && imu_raw.y == K(0) && imu_raw.z == K(0)) ? qidentity<K>() : imu_raw;
 
-    int rbits = ip[(RI_BITS) * 32];
     int walk_state = rbits & 3;
     int legs_at_correct = (rbits >> 2) & 15;
     int legs_completed = (rbits >> 6) & 15;
@@ -404,16 +484,18 @@ template <class P, int D, bool FULL> struct Cycle {
     // updateWalkPlanePose (pose_controller.cpp:1092): the last leg (id order) whose scaled swing progress is in [0,1]
     double c_in = 0.0;
     int ref_leg = -1;
-    for (int l = 0; l < L; ++l) {
-      int prog = ip[(ci.offI_leg + l * ci.strideI_leg + LI_PROG) * 32];
-      int swing_num = (int)(short)(prog & 0xffff);
+    double ref_progress = 0.0;
+#pragma unroll
+    for (int l = 0; l < kMaxLegs; ++l) {
+      int swing_num = (int)(short)(progs[l] & 0xffff);  // -1 for the legs past L
       double swing_progress = swing_num < 0 ? -1.0 : (double)swing_num / (double)ci.swing_period;
       swing_progress *= cd.swing_progress_scaler;
       if (swing_progress >= 0.0 && swing_progress <= 1.0) {
-        c_in = smooth_step(swing_progress);
+        ref_progress = swing_progress;
         ref_leg = l;
       }
     }
+    if (ref_leg >= 0) c_in = smooth_step(ref_progress);
     K wp_z = K(0);
     V3<K> wpn_ref{K(0), K(0), K(1)};
     if (ref_leg >= 0) {
@@ -421,7 +503,6 @@ template <class P, int D, bool FULL> struct Cycle {
       wp_z = K(sp[(base + LS::WP + 2) * 32]);
       wpn_ref = ld3K(sp, base + LS::WPN);
     }
-    PoseT<K> owpp = ldPose(sp, RS_OWPP);
     PoseT<K> wpp = owpp;
     if (c_in != 0.0) {
       PoseT<K> new_wpp;
@@ -443,9 +524,7 @@ template <class P, int D, bool FULL> struct Cycle {
     }
 
     PoseT<K> cur_pose = pose_add(pose_identity<K>(), wpp);
-    PoseT<K> man = pose_identity<K>();
     if (ci.manual_posing) {
-      man = ldPose(sp, RS_MAN);
       const bool man_identity = man.p.x == K(0) && man.p.y == K(0) && man.p.z == K(0) && man.q.w == K(1) &&
                                 man.q.x == K(0) && man.q.y == K(0) && man.q.z == K(0);
       if (!(man_identity && io.manual == nullptr && io.pose_reset_mode == 0)) {
@@ -578,9 +657,10 @@ template <class P, int D, bool FULL> struct Cycle {
     // 2. WalkController::updateWalk — robot-level part (walk_controller.cpp:440-564)
     // =================================================================================================================
     double lim[4] = {2147483647.0, 2147483647.0, 2147483647.0, 2147483647.0};
-    for (int l = 0; l < L; ++l) {  // getLimit (:414): the four calls share the bearing of each leg
-      const int db = ci.offD_leg + l * ci.strideD_leg + LD_TIP;
-      double tx = dp[(db) * 32], ty = dp[(db + 1) * 32];
+#pragma unroll
+    for (int l = 0; l < kMaxLegs; ++l) {  // getLimit (:414): the four calls share the bearing of each leg
+      if (l >= L) break;
+      const double tx = tips_x[l], ty = tips_y[l];
       double sx = vin_x + win * (-ty), sy = vin_y + win * tx;
       // bucket = mod(roundToInt(deg(atan2(sy, sx))), 360) / 45 (int / int floors to the 45-degree bucket, trap 1),
       // decided without atan2: the rounding makes the bucket edges sit at 44.5, 89.5, 134.5, 179.5 degrees on the upper
@@ -632,7 +712,6 @@ template <class P, int D, bool FULL> struct Cycle {
     }
     const bool has_cmd = (in_norm != 0.0) || (win != 0.0);
 
-    T dvx = T(sp[(RS_VEL) * 32]), dvy = T(sp[(RS_VEL + 1) * 32]), dw = T(sp[(RS_ANGVEL) * 32]);
     {
       T ax = nvx - dvx, ay = nvy - dvy;
       T an = sqrt_(ax * ax + ay * ay);
@@ -678,37 +757,49 @@ template <class P, int D, bool FULL> struct Cycle {
     // =================================================================================================================
     // 3. per leg: walk state machine + LegStepper + updateStance + Leg::applyIK
     // =================================================================================================================
-    // integer state of the next leg is fetched one iteration ahead: it decides the control flow at the top of the body
-    int next_bits = ip[(ci.offI_leg + LI_BITS) * 32];
-    int next_prog = ip[(ci.offI_leg + LI_PROG) * 32];
 #pragma unroll 1
     for (int l = 0; l < L; ++l) {
-      // per-leg plane bases: every field of this leg is at an immediate offset from these pointers
+      // per-leg plane bases in HBM (stores, rare loads): every field of this leg is at an immediate offset from them
       S* __restrict__ sl = sp + (ci.offS_leg + l * ci.strideS_leg) * 32;
       double* __restrict__ dl = dp + (ci.offD_leg + l * ci.strideD_leg) * 32;
       int* __restrict__ il = ip + (ci.offI_leg + l * ci.strideI_leg) * 32;
       const LegConsts<K>& lk = ck.leg[l];
       const LegConsts<T>& lt = ct.leg[l];
-      if (lane == 0 && l + 1 < L) l2_prefetch_bulk(sl - lane + ci.strideS_leg * 32, leg_chunk_bytes);  // next leg -> L2
-      int bits = next_bits;
-      int prog = next_prog;
-      // every unconditional load of this leg is issued here, back to back, so their latencies overlap
-      double tipx = dl[(LD_TIP) * 32];
-      double tipy = dl[(LD_TIP + 1) * 32];
-      double tipz = dl[(LD_TIP + 2) * 32];
-      V3<T> def = ld3T(sl, LS::DEF);
-      V3<T> stride = ld3T(sl, LS::STRIDE);
-      V3<T> tgt = ld3T(sl, LS::TGT);
+      // the staged copy of this leg's every-cycle planes: wait for the TMA transfer issued two legs ago
+      const unsigned char* slot = wsm + (l & 1) * s_bytes;
+      mbar_wait(bars + (l & 1), (unsigned)((l >> 1) & 1));
+      const S* __restrict__ ss = reinterpret_cast<const S*>(slot) + front * 32 + lane;
+      const double* __restrict__ sd = reinterpret_cast<const double*>(slot + sS_bytes) + lane;
+      const int* __restrict__ si = reinterpret_cast<const int*>(slot + sS_bytes + LD_COUNT * 32 * 8) + lane;
+      int bits = si[(LI_BITS) * 32];
+      int prog = si[(LI_PROG) * 32];
+      double tipx = sd[(LD_TIP) * 32];
+      double tipy = sd[(LD_TIP + 1) * 32];
+      double tipz = sd[(LD_TIP + 2) * 32];
+      V3<T> def = ld3T(ss, LS::DEF);
+      V3<T> stride = ld3T(ss, LS::STRIDE);
+      V3<T> tgt;
       K q[D], qd[D];
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        q[j] = K(sl[(LS::Q + j) * 32]);
-        qd[j] = K(sl[(LS::QD + j) * 32]);
+        q[j] = K(ss[(LS::Q + j) * 32]);
+        qd[j] = K(ss[(LS::QD + j) * 32]);
       }
-      if (l + 1 < L) {
-        next_bits = il[(ci.strideI_leg + LI_BITS) * 32];
-        next_prog = il[(ci.strideI_leg + LI_PROG) * 32];
+      K adm_x0 = K(0), adm_x1 = K(0);
+      V3<K> adm_force{K(0), K(0), K(0)};
+      if (f_adm || f_effort) {
+        adm_x0 = K(ss[(LS::ADM_X) * 32]);
+        adm_x1 = K(ss[(LS::ADM_X + 1) * 32]);
+        if (f_effort) adm_force = ld3K(ss, LS::ADM_FORCE);
+        else if (io.tip_force) {
+          const float* f = io.tip_force + 3 * ((size_t)r * L + l);
+          adm_force = {K(f[0]), K(f[1]), K(f[2])};
+        }
       }
+      // the one HBM read the swing branch may need (tip velocity at the first swing iteration), issued early
+      const bool swing_begins = (bits & 0xffff) == ci.swing_start;
+      V3<T> tipvel_prev{T(0), T(0), T(0)};
+      if (swing_begins) tipvel_prev = ld3T(sl, LS::TIPVEL);
       int phase = bits & 0xffff;
       int step_state = (bits >> 16) & 3;
       bool at_correct = (bits >> 18) & 1;
@@ -779,6 +870,7 @@ template <class P, int D, bool FULL> struct Cycle {
           bool zero_body_velocity = (stride.x * stride.x + stride.y * stride.y + stride.z * stride.z) == T(0);
           if (zero_body_velocity && !at_correct && phase == ci.swing_end) {
             V3<double> wpn_l = cvt<double>(ld3T(sl, LS::WPN));
+            tgt = ld3T(sl, LS::TGT);  // last cycle's target (rare path: straight from HBM)
             V3<double> err{tipx - (double)tgt.x, tipy - (double)tgt.y, tipz - (double)tgt.z};
             err = rejection(err, wpn_l);
             bool at_target = norm(err) < 0.01;  // TIP_TOLERANCE (pose_controller.h:19)
@@ -825,12 +917,12 @@ template <class P, int D, bool FULL> struct Cycle {
             V3<T> swo_p, swo_v;
             if (iteration == 1) {
               swo_p = V3<T>{T(tipx), T(tipy), T(tipz)};
-              swo_v = ld3T(sl, LS::TIPVEL);
+              swo_v = swing_begins ? tipvel_prev : ld3T(sl, LS::TIPVEL);
               st3(sl, LS::SWO_P, swo_p);
               st3(sl, LS::SWO_V, swo_v);
             } else {
-              swo_p = ld3T(sl, LS::SWO_P);
-              swo_v = ld3T(sl, LS::SWO_V);
+              swo_p = ld3T(ss, LS::SWO_P);
+              swo_v = ld3T(ss, LS::SWO_V);
             }
             // Control nodes relative to the swing origin (generatePrimary/SecondarySwingControlNodes :1238-1291);
             // only node differences enter quarticBezierDot, so the origin cancels.
@@ -868,7 +960,8 @@ template <class P, int D, bool FULL> struct Cycle {
             }
           } else {  // STANCE / FORCE_STANCE
             int mod_start = standard ? ci.stance_start : ci.phase_offset[l];
-            int iteration = imod(phase + (ci.period - mod_start), ci.period) + 1;
+            int iteration = phase - mod_start;  // mod(phase + (period - start), period) + 1, both in [0, period)
+            iteration += iteration < 0 ? ci.period + 1 : 1;
             if (iteration == 1) st3(sl, LS::STO_P, V3<T>{T(tipx), T(tipy), T(tipz)});
             T scaler = standard ? T(1) : lt.stride_scaler_mod;
             V3<T> sep = -stride * scaler * T(0.25);
@@ -888,7 +981,7 @@ template <class P, int D, bool FULL> struct Cycle {
         }
 
         // ---- LegStepper::iteratePhase (:871) + updateStepState (:901) ----
-        phase = (phase + 1) % ci.period;
+        phase = phase + 1 == ci.period ? 0 : phase + 1;  // (phase + 1) % period with phase in [0, period)
         if (step_state != STEP_FORCE_STOP) {
           if (phase >= ci.swing_start && phase < ci.swing_end && step_state != STEP_FORCE_STANCE) step_state = STEP_SWING;
           else if (phase < ci.stance_end || phase >= ci.stance_start) step_state = STEP_STANCE;
@@ -897,12 +990,20 @@ template <class P, int D, bool FULL> struct Cycle {
           swing_num = min(max(phase - ci.swing_start + 1, 0), ci.swing_period);
           stance_num = -1;
         } else if (step_state == STEP_STANCE) {
-          stance_num = min(max(imod(phase + (ci.period - ci.stance_start), ci.period) + 1, 0), ci.stance_period);
+          int since = phase - ci.stance_start;
+          since += since < 0 ? ci.period + 1 : 1;
+          stance_num = min(max(since, 0), ci.stance_period);
           swing_num = -1;
         } else if (step_state == STEP_FORCE_STOP) {
           stance_num = 0;
           swing_num = -1;
         }
+      }
+      // every lane has read what it needs from this slot: hand it back to the TMA unit for leg l + 2
+      __syncwarp();
+      if (lane == 0 && l + 2 < L) {
+        fence_proxy_async_smem();
+        issue_leg(l + 2);
       }
       bits = (phase & 0xffff) | (step_state << 16) | ((at_correct ? 1 : 0) << 18) | ((completed ? 1 : 0) << 19) |
              ((negate ? 1 : 0) << 20);
@@ -924,15 +1025,8 @@ template <class P, int D, bool FULL> struct Cycle {
 
       // ---- AdmittanceController::updateAdmittance (admittance_controller.cpp:22) ----
       if (f_adm) {
-        S* __restrict__ sa = sl + ci.offS_leg_adm * 32;
-        K x0 = K(sa[(ADM_X) * 32]), x1 = K(sa[(ADM_X + 1) * 32]);
-        V3<K> force{K(0), K(0), K(0)};
-        if (f_effort) force = ld3K(sa, ADM_FORCE);
-        else if (io.tip_force) {
-          const float* f = io.tip_force + 3 * ((size_t)r * L + l);
-          force = {K(f[0]), K(f[1]), K(f[2])};
-        }
-        force = force * ck.force_gain;
+        K x0 = adm_x0, x1 = adm_x1;
+        V3<K> force = adm_force * ck.force_gain;
         K fa[3] = {force.x, force.y, force.z};
         K da[3];
 #pragma unroll
@@ -945,12 +1039,12 @@ template <class P, int D, bool FULL> struct Cycle {
           K dl = clamp_(-x0, K(-0.2), K(0.2));
           da[a] = abs_(dl) > K(0) ? (dl / abs_(dl)) * abs_(dl) : K(0);  // deadband 0 (trap 8)
         }
-        sa[(ADM_X) * 32] = S(x0);
-        sa[(ADM_X + 1) * 32] = S(x1);
+        sl[(LS::ADM_X) * 32] = S(x0);
+        sl[(LS::ADM_X + 1) * 32] = S(x1);
         // Leg::setAdmittanceDelta (model.h:365): projection onto the tip frame x axis (base_link frame)
         V3<K> dirx = t1_rotate(lk, ch.tipx);
         V3<K> adelta = projection(V3<K>{da[0], da[1], da[2]}, dirx);
-        st3(sa, ADM_DELTA, adelta);
+        st3(sl, LS::ADM_DELTA, adelta);
         desired = desired + adelta;  // Leg::setDesiredTipPose (model.cpp:653)
       }
 
@@ -975,10 +1069,8 @@ template <class P, int D, bool FULL> struct Cycle {
 #pragma unroll
           for (int j = 0; j < D; ++j) tau[j] = io.efforts ? K(io.efforts[((size_t)r * L + l) * D + j]) : K(0);
           V3<K> raw = raw_tip_force<K, D>(ck, lk, ch2, tau);
-          S* __restrict__ sa2 = sl + ci.offS_leg_adm * 32;
-          V3<K> f = ld3K(sa2, ADM_FORCE);
-          f = raw * (K(0.15) * ck.force_gain) + f * (K(1) - K(0.15));
-          st3(sa2, ADM_FORCE, f);
+          V3<K> f = raw * (K(0.15) * ck.force_gain) + adm_force * (K(1) - K(0.15));
+          st3(sl, LS::ADM_FORCE, f);
         }
       }
     }
@@ -991,7 +1083,9 @@ template <class P, int D, bool FULL> struct Cycle {
         // normal equations over the (possibly updated) default tips: A = [x y 1], b = z.  Re-read here rather than
         // accumulated inside the leg loop to keep eight doubles out of its live registers.
         double sxx = 0, sxy = 0, sx1 = 0, syy = 0, sy1 = 0, sxz = 0, syz = 0, sz1 = 0;
-        for (int l = 0; l < L; ++l) {
+#pragma unroll
+        for (int l = 0; l < kMaxLegs; ++l) {
+          if (l >= L) break;
           const S* __restrict__ sl = sp + (ci.offS_leg + l * ci.strideS_leg) * 32;
           double x = (double)sl[(LS::DEF) * 32], y = (double)sl[(LS::DEF + 1) * 32], z = (double)sl[(LS::DEF + 2) * 32];
           sxx += x * x; sxy += x * y; sx1 += x; syy += y * y; sy1 += y; sxz += x * z; syz += y * z; sz1 += z;
@@ -1031,7 +1125,7 @@ template <class P, int D, bool FULL> struct Cycle {
     rbits = (walk_state & 3) | ((legs_at_correct & 15) << 2) | ((legs_completed & 15) << 6) | ((rtd & 1) << 10) |
             ((pose_state & 3) << 11) | ((auto_state & 3) << 13) | (status << 16);
     ip[(RI_BITS) * 32] = rbits;
-    if (io.flags_out) io.flags_out[r] = status;
+    if (io.flags_out && live) io.flags_out[r] = status;
   }
 };
 

@@ -28,29 +28,32 @@ using PrecMixed = Prec<float, float, double>;  // fp32 state + trajectory; fp64 
 #define SHC_BLOCK 128
 #endif
 
+// One warp per tile of 32 robots (lane = robot); warps are independent (no block-level synchronisation), each with
+// its own slice of the dynamic shared memory: two TMA staging slots, the joint-command tile and two mbarriers.
 template <class P, int D, bool FULL>
 __global__ void __launch_bounds__(SHC_BLOCK, SHC_MIN_BLOCKS) control_cycle_kernel(const __grid_constant__ Consts c, Planes<typename P::S> pl, StepIO io) {
-  // per-warp staging tile for the joint commands: [32 robots][L*D] floats, the layout of joints_out
-  __shared__ float stage[SHC_BLOCK / 32][32 * kMaxLegs * D];
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ __align__(128) unsigned char shc_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int LD = c.i.L * D;
-  if (r < c.i.n_robots) Cycle<P, D, FULL>::run(c, pl, r, io, &stage[warp][lane * LD]);
+  const int tile = blockIdx.x * (SHC_BLOCK / 32) + warp;
+  const int tile_first = tile * 32;
+  if (tile_first >= c.i.n_robots) return;  // whole warp
+  using CY = Cycle<P, D, FULL>;
+  const int front = FULL ? c.i.frontS_leg : 0;
+  unsigned char* wsm = shc_smem + (size_t)warp * c.i.smem_per_warp;
+  CY::run(c, pl, tile, lane, io, wsm);
   __syncwarp();
   // Fused output + all-gather: the warp writes its tile as coalesced 128-byte lines to the local buffer and straight
   // into every peer GPU's gather buffer over NVLink (peer-mapped pointers), so the transfer overlaps the computation
   // of the other tiles instead of running as a separate collective after the kernel.
-  const int tile_first = r - lane;
+  const int LD = c.i.L * D;
   const int valid = min(32, c.i.n_robots - tile_first) * LD;
-  if (valid > 0) {
-    const size_t base = (size_t)tile_first * LD;
-    const float* src = stage[warp];
-    float* dst0 = io.joints_out + base;
-    for (int i = lane; i < valid; i += 32) dst0[i] = src[i];
-    for (int p = 0; p < io.n_peers; ++p) {
-      float* dst = io.peer_out[p] + base;
-      for (int i = lane; i < valid; i += 32) dst[i] = src[i];
-    }
+  const size_t base = (size_t)tile_first * LD;
+  const float* src = reinterpret_cast<const float*>(wsm + 2 * CY::slot_bytes(front));
+  float* dst0 = io.joints_out + base;
+  for (int i = lane; i < valid; i += 32) dst0[i] = src[i];
+  for (int p = 0; p < io.n_peers; ++p) {
+    float* dst = io.peer_out[p] + base;
+    for (int i = lane; i < valid; i += 32) dst[i] = src[i];
   }
 }
 
@@ -130,6 +133,7 @@ struct shc_engine {
   int options = 0;
   int pose_reset_mode = 0;
   size_t s_elem = 8;  // bytes per storage word
+  size_t smem_block = 0;  // dynamic shared memory per block of the control-cycle kernel
   void* s_planes = nullptr;
   double* d_planes = nullptr;
   int* i_planes = nullptr;
@@ -193,9 +197,10 @@ static void layout(const shc_config& cfg, int n, IntConsts& ci) {
   if (imu) s += IMU_COUNT;
   ci.offS_auto = s;
   if (cfg.auto_posing) s += AUTO_COUNT;
-  ci.offS_leg = s;
-  ci.offS_leg_adm = 2 * D + 27;
-  ci.strideS_leg = 2 * D + 27 + (adm ? ADM_COUNT : 0);
+  const LegOff lo(D);
+  ci.frontS_leg = adm ? -lo.ADM_X : 0;
+  ci.offS_leg = s + ci.frontS_leg;  // plane of leg 0's first joint position; the staged admittance planes sit in front
+  ci.strideS_leg = lo.COUNT + (adm ? ADM_COUNT : 0);
   ci.nS = s + ci.strideS_leg * cfg.leg_count;
   ci.offD_leg = RD_COUNT;
   ci.strideD_leg = LD_COUNT;
@@ -282,18 +287,21 @@ inline int prog_num(double progress, int den) {
   return std::min(std::max(n, 0), den);
 }
 
-void pack(const shc_engine* e, const shc_robot_state* in, size_t n, HostPlanes& h) {
+// Packs records in[0..n) into lanes [0, n_fill): lanes past n repeat the last record (padding robots of the last tile
+// run through the kernel like any other lane, so they must hold a valid state).
+void pack(const shc_engine* e, const shc_robot_state* in, size_t n, HostPlanes& h, size_t n_fill) {
   const IntConsts& ci = e->c.i;
   const size_t np = ci.n_pad;
   const int D = ci.D, L = ci.L;
+  const LegOff lo(D);
   const bool imu = e->cfg.imu_posing || e->cfg.inclination_posing;
   const bool adm = e->cfg.admittance_control || e->cfg.use_joint_effort;
   // tile-major planes: [tile][plane][32 lanes] (shc_layout.h)
   auto S = [&](int plane, size_t r) -> double& { return h.s[((r >> 5) * ci.nS + plane) * 32 + (r & 31)]; };
   auto Dd = [&](int plane, size_t r) -> double& { return h.d[((r >> 5) * ci.nD + plane) * 32 + (r & 31)]; };
   auto I = [&](int plane, size_t r) -> int& { return h.i[((r >> 5) * ci.nI + plane) * 32 + (r & 31)]; };
-  for (size_t r = 0; r < n; ++r) {
-    const shc_robot_state& s = in[r];
+  for (size_t r = 0; r < n_fill; ++r) {
+    const shc_robot_state& s = in[r < n ? r : n - 1];
     S(RS_VEL, r) = s.desired_linear_velocity[0];
     S(RS_VEL + 1, r) = s.desired_linear_velocity[1];
     S(RS_ANGVEL, r) = s.desired_angular_velocity;
@@ -330,29 +338,27 @@ void pack(const shc_engine* e, const shc_robot_state* in, size_t n, HostPlanes& 
       const shc_leg_state& g = s.legs[l];
       const int sb = ci.offS_leg + l * ci.strideS_leg;
       for (int j = 0; j < D; ++j) {
-        S(sb + j, r) = g.joint_position[j];
-        S(sb + D + j, r) = g.joint_velocity[j];
+        S(sb + lo.Q + j, r) = g.joint_position[j];
+        S(sb + lo.QD + j, r) = g.joint_velocity[j];
       }
-      const int o = sb + 2 * D;
       for (int k = 0; k < 3; ++k) {
-        S(o + 0 + k, r) = g.tip_velocity[k];
-        S(o + 3 + k, r) = g.swing_origin_position[k];
-        S(o + 6 + k, r) = g.swing_origin_velocity[k];
-        S(o + 9 + k, r) = g.stance_origin_position[k];
-        S(o + 12 + k, r) = g.default_tip_position[k];
-        S(o + 15 + k, r) = g.target_tip_position[k];
-        S(o + 18 + k, r) = g.stride_vector[k];
-        S(o + 21 + k, r) = g.walk_plane[k];
-        S(o + 24 + k, r) = g.walk_plane_normal[k];
+        S(sb + lo.TIPVEL + k, r) = g.tip_velocity[k];
+        S(sb + lo.SWO_P + k, r) = g.swing_origin_position[k];
+        S(sb + lo.SWO_V + k, r) = g.swing_origin_velocity[k];
+        S(sb + lo.STO_P + k, r) = g.stance_origin_position[k];
+        S(sb + lo.DEF + k, r) = g.default_tip_position[k];
+        S(sb + lo.TGT + k, r) = g.target_tip_position[k];
+        S(sb + lo.STRIDE + k, r) = g.stride_vector[k];
+        S(sb + lo.WP + k, r) = g.walk_plane[k];
+        S(sb + lo.WPN + k, r) = g.walk_plane_normal[k];
         Dd(ci.offD_leg + l * ci.strideD_leg + LD_TIP + k, r) = g.tip_position[k];
       }
       if (adm) {
-        const int ab = sb + ci.offS_leg_adm;
-        S(ab + ADM_X, r) = g.admittance_state[0];
-        S(ab + ADM_X + 1, r) = g.admittance_state[1];
+        S(sb + lo.ADM_X, r) = g.admittance_state[0];
+        S(sb + lo.ADM_X + 1, r) = g.admittance_state[1];
         for (int k = 0; k < 3; ++k) {
-          S(ab + ADM_DELTA + k, r) = g.admittance_delta[k];
-          S(ab + ADM_FORCE + k, r) = g.tip_force_calculated[k];
+          S(sb + lo.ADM_DELTA + k, r) = g.admittance_delta[k];
+          S(sb + lo.ADM_FORCE + k, r) = g.tip_force_calculated[k];
         }
       }
       const int ib = ci.offI_leg + l * ci.strideI_leg;
@@ -433,29 +439,28 @@ template <int D> void unpack(const shc_engine* e, const HostPlanes& h, shc_robot
       shc_leg_state& g = s.legs[l];
       const int sb = ci.offS_leg + l * ci.strideS_leg;
       for (int j = 0; j < D; ++j) {
-        g.joint_position[j] = S(sb + j, r);
-        g.joint_velocity[j] = S(sb + D + j, r);
+        g.joint_position[j] = S(sb + LegS<D>::Q + j, r);
+        g.joint_velocity[j] = S(sb + LegS<D>::QD + j, r);
       }
-      const int o = sb + 2 * D;
+      using LS = LegS<D>;
       for (int k = 0; k < 3; ++k) {
-        g.tip_velocity[k] = S(o + 0 + k, r);
-        g.swing_origin_position[k] = S(o + 3 + k, r);
-        g.swing_origin_velocity[k] = S(o + 6 + k, r);
-        g.stance_origin_position[k] = S(o + 9 + k, r);
-        g.default_tip_position[k] = S(o + 12 + k, r);
-        g.target_tip_position[k] = S(o + 15 + k, r);
-        g.stride_vector[k] = S(o + 18 + k, r);
-        g.walk_plane[k] = S(o + 21 + k, r);
-        g.walk_plane_normal[k] = S(o + 24 + k, r);
+        g.tip_velocity[k] = S(sb + LS::TIPVEL + k, r);
+        g.swing_origin_position[k] = S(sb + LS::SWO_P + k, r);
+        g.swing_origin_velocity[k] = S(sb + LS::SWO_V + k, r);
+        g.stance_origin_position[k] = S(sb + LS::STO_P + k, r);
+        g.default_tip_position[k] = S(sb + LS::DEF + k, r);
+        g.target_tip_position[k] = S(sb + LS::TGT + k, r);
+        g.stride_vector[k] = S(sb + LS::STRIDE + k, r);
+        g.walk_plane[k] = S(sb + LS::WP + k, r);
+        g.walk_plane_normal[k] = S(sb + LS::WPN + k, r);
         g.tip_position[k] = Dd(ci.offD_leg + l * ci.strideD_leg + LD_TIP + k, r);
       }
       if (adm) {
-        const int ab = sb + ci.offS_leg_adm;
-        g.admittance_state[0] = S(ab + ADM_X, r);
-        g.admittance_state[1] = S(ab + ADM_X + 1, r);
+        g.admittance_state[0] = S(sb + LS::ADM_X, r);
+        g.admittance_state[1] = S(sb + LS::ADM_X + 1, r);
         for (int k = 0; k < 3; ++k) {
-          g.admittance_delta[k] = S(ab + ADM_DELTA + k, r);
-          g.tip_force_calculated[k] = S(ab + ADM_FORCE + k, r);
+          g.admittance_delta[k] = S(sb + LS::ADM_DELTA + k, r);
+          g.tip_force_calculated[k] = S(sb + LS::ADM_FORCE + k, r);
         }
       }
       const int ib = ci.offI_leg + l * ci.strideI_leg;
@@ -498,22 +503,48 @@ template <class F> static int dispatch_D(int D, F&& f) {
   return fail(SHC_E_UNSUPPORTED, "unsupported joint count");
 }
 
-static int launch_cycle(shc_engine* e, const StepIO& io, cudaStream_t st) {
-  const int threads = SHC_BLOCK;
-  const int blocks = (e->n + threads - 1) / threads;
-  const bool full = e->cfg.auto_posing || e->cfg.admittance_control || e->cfg.imu_posing || e->cfg.inclination_posing ||
-                    e->cfg.use_joint_effort;
+static bool engine_full(const shc_config& cfg) {
+  return cfg.auto_posing || cfg.admittance_control || cfg.imu_posing || cfg.inclination_posing || cfg.use_joint_effort;
+}
+
+// Calls f(kernel pointer, Planes) for the instantiation this engine runs.
+template <class F> static int with_cycle_kernel(shc_engine* e, F&& f) {
+  const bool full = engine_full(e->cfg);
   return dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int {
     constexpr int D = decltype(dtag)::value;
     if (e->precision == SHC_PRECISION_F64) {
       Planes<double> pl{(double*)e->s_planes, e->d_planes, e->i_planes};
-      if (full) control_cycle_kernel<PrecF64, D, true><<<blocks, threads, 0, st>>>(e->c, pl, io);
-      else control_cycle_kernel<PrecF64, D, false><<<blocks, threads, 0, st>>>(e->c, pl, io);
-    } else {
-      Planes<float> pl{(float*)e->s_planes, e->d_planes, e->i_planes};
-      if (full) control_cycle_kernel<PrecMixed, D, true><<<blocks, threads, 0, st>>>(e->c, pl, io);
-      else control_cycle_kernel<PrecMixed, D, false><<<blocks, threads, 0, st>>>(e->c, pl, io);
+      return full ? f(control_cycle_kernel<PrecF64, D, true>, pl) : f(control_cycle_kernel<PrecF64, D, false>, pl);
     }
+    Planes<float> pl{(float*)e->s_planes, e->d_planes, e->i_planes};
+    return full ? f(control_cycle_kernel<PrecMixed, D, true>, pl) : f(control_cycle_kernel<PrecMixed, D, false>, pl);
+  });
+}
+
+// Shared memory of the control-cycle kernel is dynamic (it depends on L, D, the precision and the admittance block):
+// size it, opt in above 48 KB and ask for the full shared-memory carve-out once per engine.
+static int configure_cycle_kernel(shc_engine* e) {
+  const bool full = engine_full(e->cfg);
+  const int front = full ? e->c.i.frontS_leg : 0;
+  dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int {
+    constexpr int D = decltype(dtag)::value;
+    e->c.i.smem_per_warp = e->precision == SHC_PRECISION_F64 ? Cycle<PrecF64, D, false>::smem_per_warp(front, e->cfg.leg_count)
+                                                            : Cycle<PrecMixed, D, false>::smem_per_warp(front, e->cfg.leg_count);
+    return 0;
+  });
+  e->smem_block = (size_t)e->c.i.smem_per_warp * (SHC_BLOCK / 32);
+  return with_cycle_kernel(e, [&](auto kernel, auto) -> int {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_block));
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    return SHC_OK;
+  });
+}
+
+static int launch_cycle(shc_engine* e, const StepIO& io, cudaStream_t st) {
+  const int threads = SHC_BLOCK;
+  const int blocks = (e->n + threads - 1) / threads;
+  return with_cycle_kernel(e, [&](auto kernel, auto pl) -> int {
+    kernel<<<blocks, threads, e->smem_block, st>>>(e->c, pl, io);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(SHC_E_CUDA, std::string("control_cycle launch: ") + cudaGetErrorString(err));
     return SHC_OK;
@@ -563,6 +594,10 @@ int shc_create(const shc_config* cfg, const shc_startup* startup, int n_robots, 
   fill_startup_consts<float>(*cfg, e->su, e->c.f, tmp);
 
   e->s_elem = precision == SHC_PRECISION_F64 ? 8 : 4;
+  {
+    int rc = configure_cycle_kernel(e);
+    if (rc != SHC_OK) { std::string m = g_err; shc_destroy(e); return fail(rc, m); }
+  }
   const IntConsts& ci = e->c.i;
   const size_t np = ci.n_pad;
   auto cleanup = [&](int code, const std::string& m) { shc_destroy(e); return fail(code, m); };
@@ -587,7 +622,7 @@ int shc_create(const shc_config* cfg, const shc_startup* startup, int n_robots, 
     h.i.assign((size_t)ci.nI * np, 0);
     // pack one full tile of identical robots, then replicate the tile
     std::vector<shc_robot_state> tile_states(32, init);
-    pack(e, tile_states.data(), 32, h);
+    pack(e, tile_states.data(), 32, h, 32);
     const size_t n_tiles = np / 32;
     for (size_t t = 1; t < n_tiles; ++t) {
       std::copy(h.s.begin(), h.s.begin() + (size_t)ci.nS * 32, h.s.begin() + t * (size_t)ci.nS * 32);
@@ -701,7 +736,7 @@ int shc_set_state(shc_engine* e, const shc_robot_state* in, size_t n_records) {
   h.s.assign((size_t)ci.nS * ci.n_pad, 0.0);
   h.d.assign((size_t)ci.nD * ci.n_pad, 0.0);
   h.i.assign((size_t)ci.nI * ci.n_pad, 0);
-  pack(e, in, n_records, h);
+  pack(e, in, n_records, h, ci.n_pad);
   return upload(e, h);
 }
 

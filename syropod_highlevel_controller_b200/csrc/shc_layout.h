@@ -28,25 +28,39 @@ enum : int { IMU_Q = 0 /*imu_pose_.rotation_ (4)*/, IMU_ABS = 4 /*absement (3)*/
 // optional auto-pose block (auto_posing), relative to offS_auto
 enum : int { AUTO_POSE = 0 /*auto_pose_ (7)*/, AUTO_COUNT = 7 };
 
-// per-leg storage planes, relative to offS_leg + leg * strideS_leg; joint planes first: q[D], qd[D]
+// per-leg storage planes, relative to offS_leg + leg * strideS_leg (the plane of the leg's first joint position).
+// The planes every cycle reads come first and are contiguous: [front .. STAGED) is what one TMA bulk copy stages into
+// shared memory per leg (shc_cycle.cuh); the rest is write-mostly and goes to HBM with plain coalesced stores.
 template <int D> struct LegS {
   enum : int {
+    // optional admittance planes IN FRONT of the joint planes (negative offsets; present when admittance_control ||
+    // use_joint_effort): they are read every cycle, so they sit inside the staged range
+    ADM_X = -5,          // admittance_state_ (2)
+    ADM_FORCE = -3,      // tip_force_calculated_ (3)
     Q = 0, QD = D,
-    TIPVEL = 2 * D,      // LegStepper::current_tip_velocity_
-    SWO_P = 2 * D + 3,   // swing_origin_tip_position_
-    SWO_V = 2 * D + 6,   // swing_origin_tip_velocity_
-    STO_P = 2 * D + 9,   // stance_origin_tip_position_
-    DEF = 2 * D + 12,    // default_tip_pose_.position_
-    TGT = 2 * D + 15,    // target_tip_pose_.position_
-    STRIDE = 2 * D + 18, // stride_vector_
+    DEF = 2 * D,         // default_tip_pose_.position_
+    STRIDE = 2 * D + 3,  // stride_vector_
+    SWO_P = 2 * D + 6,   // swing_origin_tip_position_
+    SWO_V = 2 * D + 9,   // swing_origin_tip_velocity_
+    STAGED = 2 * D + 12, // end of the staged range
+    TIPVEL = 2 * D + 12, // LegStepper::current_tip_velocity_
+    STO_P = 2 * D + 15,  // stance_origin_tip_position_
+    TGT = 2 * D + 18,    // target_tip_pose_.position_
     WP = 2 * D + 21,     // walk_plane_ (saved)
     WPN = 2 * D + 24,    // walk_plane_normal_ (saved)
-    COUNT = 2 * D + 27
+    COUNT = 2 * D + 27,
+    ADM_DELTA = COUNT    // admittance_delta_ (3), appended when the admittance block is present
   };
 };
-// optional admittance block appended to each leg (admittance_control), relative to offS_leg_adm within the leg
-enum : int { ADM_X = 0 /*admittance_state_ (2)*/, ADM_DELTA = 2 /*admittance_delta_ (3)*/,
-             ADM_FORCE = 5 /*tip_force_calculated_ (3)*/, ADM_COUNT = 8 };
+// the same offsets for host code that knows D only at run time (pack)
+struct LegOff {
+  int Q, QD, DEF, STRIDE, SWO_P, SWO_V, STAGED, TIPVEL, STO_P, TGT, WP, WPN, COUNT, ADM_X, ADM_FORCE, ADM_DELTA;
+  explicit LegOff(int D)
+      : Q(0), QD(D), DEF(2 * D), STRIDE(2 * D + 3), SWO_P(2 * D + 6), SWO_V(2 * D + 9), STAGED(2 * D + 12), TIPVEL(2 * D + 12),
+        STO_P(2 * D + 15), TGT(2 * D + 18), WP(2 * D + 21), WPN(2 * D + 24), COUNT(2 * D + 27), ADM_X(-5), ADM_FORCE(-3),
+        ADM_DELTA(2 * D + 27) {}
+};
+enum : int { ADM_COUNT = 8 };  // planes of the optional per-leg admittance block (5 in front + 3 appended)
 
 // double planes
 enum : int { RD_ODOMP = 0 /*odometry_ideal_.position_ (3)*/, RD_COUNT = 3 };
