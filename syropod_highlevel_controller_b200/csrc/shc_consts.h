@@ -63,6 +63,7 @@ struct IntConsts {
   // StepCycle (walk_controller.h:23)
   int period, swing_period, stance_period, stance_end, swing_start, swing_end, stance_start;
   int swing_iterations;        // even-rounded (:1035-1036)
+  int swing_ref_max;           // largest swing-progress numerator n with (n / swing_period) * swing_progress_scaler <= 1
   int phase_offset[kMaxLegs];
   int mod_stance_start[kMaxLegs];  // = phase offset
   // flags
@@ -75,8 +76,8 @@ struct IntConsts {
   // plane indices (see shc_layout.h)
   int nS, nD, nI;              // number of storage / double / int planes
   int offS_imu, offS_auto, offS_leg, strideS_leg;
-  int frontS_leg;              // staged admittance planes in front of each leg's joint planes (0 or LegS::FRONT)
-  int smem_per_warp;           // bytes of dynamic shared memory per warp (two staging slots + joint tile + barriers)
+  int frontS_leg;              // staged admittance planes in front of each leg's joint planes (0 or 5)
+  int smem_per_warp;           // bytes of dynamic shared memory per warp (two staging slots + barriers)
   int offD_leg, strideD_leg;
   int offI_leg, strideI_leg, offI_auto;
 };

@@ -484,18 +484,18 @@ template <class P, int D, bool FULL> struct Cycle {
     // updateWalkPlanePose (pose_controller.cpp:1092): the last leg (id order) whose scaled swing progress is in [0,1]
     double c_in = 0.0;
     int ref_leg = -1;
-    double ref_progress = 0.0;
+    // scaled progress = (n / swing_period) * scaler is monotonic in the integer numerator n, so "0 <= progress <= 1" is
+    // the integer window 0 <= n <= swing_ref_max (found on the host with the same two double operations)
+    int ref_num = 0;
 #pragma unroll
     for (int l = 0; l < kMaxLegs; ++l) {
       int swing_num = (int)(short)(progs[l] & 0xffff);  // -1 for the legs past L
-      double swing_progress = swing_num < 0 ? -1.0 : (double)swing_num / (double)ci.swing_period;
-      swing_progress *= cd.swing_progress_scaler;
-      if (swing_progress >= 0.0 && swing_progress <= 1.0) {
-        ref_progress = swing_progress;
+      if (swing_num >= 0 && swing_num <= ci.swing_ref_max) {
+        ref_num = swing_num;
         ref_leg = l;
       }
     }
-    if (ref_leg >= 0) c_in = smooth_step(ref_progress);
+    if (ref_leg >= 0) c_in = smooth_step(((double)ref_num / (double)ci.swing_period) * cd.swing_progress_scaler);
     K wp_z = K(0);
     V3<K> wpn_ref{K(0), K(0), K(1)};
     if (ref_leg >= 0) {

@@ -21,17 +21,24 @@ namespace shc {
 
 using PrecMixed = Prec<float, float, double>;  // fp32 state + trajectory; fp64 pose/kinematics (see DESIGN.md "Precision")
 
+// One warp per block: warps never synchronise with each other, and 32-thread blocks let the block scheduler refill an SM
+// warp by warp (measured 7 % faster than 128-thread blocks at the same register budget: profiles/).
 #ifndef SHC_MIN_BLOCKS
-#define SHC_MIN_BLOCKS 4
+#define SHC_MIN_BLOCKS 16
 #endif
 #ifndef SHC_BLOCK
-#define SHC_BLOCK 128
+#define SHC_BLOCK 32
 #endif
 
 // One warp per tile of 32 robots (lane = robot); warps are independent (no block-level synchronisation), each with
 // its own slice of the dynamic shared memory: two TMA staging slots, the joint-command tile and two mbarriers.
+#ifdef SHC_MAXNREG
+#define SHC_KERNEL_BOUNDS __maxnreg__(SHC_MAXNREG)
+#else
+#define SHC_KERNEL_BOUNDS __launch_bounds__(SHC_BLOCK, SHC_MIN_BLOCKS)
+#endif
 template <class P, int D, bool FULL>
-__global__ void __launch_bounds__(SHC_BLOCK, SHC_MIN_BLOCKS) control_cycle_kernel(const __grid_constant__ Consts c, Planes<typename P::S> pl, StepIO io) {
+__global__ void SHC_KERNEL_BOUNDS control_cycle_kernel(const __grid_constant__ Consts c, Planes<typename P::S> pl, StepIO io) {
   extern __shared__ __align__(128) unsigned char shc_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tile = blockIdx.x * (SHC_BLOCK / 32) + warp;
@@ -533,6 +540,7 @@ static int configure_cycle_kernel(shc_engine* e) {
     return 0;
   });
   e->smem_block = (size_t)e->c.i.smem_per_warp * (SHC_BLOCK / 32);
+  if (const char* pad = getenv("SHC_SMEM_PAD")) e->smem_block += (size_t)atoi(pad);  // kernel tuning: lowers the occupancy
   return with_cycle_kernel(e, [&](auto kernel, auto) -> int {
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_block));
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

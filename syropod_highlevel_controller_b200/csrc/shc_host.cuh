@@ -366,6 +366,18 @@ template <class R> void fill_startup_consts(const shc_config& c, const shc_start
   int swing_iterations = int((double(su.swing_period) / su.period) / (su.step_frequency * dt));
   swing_iterations = round_to_even_int(swing_iterations);
   ci.swing_iterations = swing_iterations;
+  {
+    // updateWalkPlanePose (pose_controller.cpp:1102-1106) accepts a leg when (n / swing_period) * scaler <= 1.0; both
+    // operations are monotonic in n, so the test is an integer window ending at the largest n that still passes
+    const double scaler = std::max(1.0, double(c.swing_phase) / c.phase_offset);
+    int nmax = -1;
+    for (int n = 0; n <= su.swing_period; ++n) {
+      volatile double progress = (double)n / (double)su.swing_period;
+      volatile double scaled = progress * scaler;
+      if (scaled <= 1.0) nmax = n;
+    }
+    ci.swing_ref_max = nmax;
+  }
   k.swing_dt = R(1.0 / (swing_iterations / 2.0));
   auto stance_iter = [&](int mod_period) { return int((double(mod_period) / su.period) / (su.step_frequency * dt)); };
   int std_period = imod(su.stance_end - su.stance_start, su.period);
