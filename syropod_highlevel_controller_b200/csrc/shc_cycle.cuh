@@ -34,9 +34,9 @@ struct StepIO {
   const float* tip_force;  // [N][L][3] or null
   const float* manual;     // [N][6] or null
   const float* efforts;    // [N][L][D] or null: measured joint efforts (jointStatesCallback, state_controller.cpp:1565)
-  float* joints_out;       // [N][L][D] (destination 0)
-  float* peer_out[7];      // fused all-gather: this shard's slice inside up to 7 peer GPUs' gather buffers (NVLink stores)
-  int n_peers;             // number of valid peer_out entries
+  float* joints_out;       // [N][L][D]
+  int tile_begin, tile_end;  // tiles (32 robots each) of this launch: a step may be issued as several tile ranges so that
+                             // the D2H copy of one range overlaps the arithmetic of the next (shc_step_host)
   int* flags_out;          // [N] or null
   int pose_reset_mode;
 };

@@ -41,27 +41,21 @@ template <class P, int D, bool FULL>
 __global__ void SHC_KERNEL_BOUNDS control_cycle_kernel(const __grid_constant__ Consts c, Planes<typename P::S> pl, StepIO io) {
   extern __shared__ __align__(128) unsigned char shc_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tile = blockIdx.x * (SHC_BLOCK / 32) + warp;
+  const int tile = io.tile_begin + blockIdx.x * (SHC_BLOCK / 32) + warp;
   const int tile_first = tile * 32;
-  if (tile_first >= c.i.n_robots) return;  // whole warp
+  if (tile >= io.tile_end || tile_first >= c.i.n_robots) return;  // whole warp
   using CY = Cycle<P, D, FULL>;
   const int front = FULL ? c.i.frontS_leg : 0;
   unsigned char* wsm = shc_smem + (size_t)warp * c.i.smem_per_warp;
   CY::run(c, pl, tile, lane, io, wsm);
   __syncwarp();
-  // Fused output + all-gather: the warp writes its tile as coalesced 128-byte lines to the local buffer and straight
-  // into every peer GPU's gather buffer over NVLink (peer-mapped pointers), so the transfer overlaps the computation
-  // of the other tiles instead of running as a separate collective after the kernel.
+  // the warp writes its tile of joint commands as coalesced 128-byte lines
   const int LD = c.i.L * D;
   const int valid = min(32, c.i.n_robots - tile_first) * LD;
   const size_t base = (size_t)tile_first * LD;
   const float* src = reinterpret_cast<const float*>(wsm + 2 * CY::slot_bytes(front));
   float* dst0 = io.joints_out + base;
   for (int i = lane; i < valid; i += 32) dst0[i] = src[i];
-  for (int p = 0; p < io.n_peers; ++p) {
-    float* dst = io.peer_out[p] + base;
-    for (int i = lane; i < valid; i += 32) dst[i] = src[i];
-  }
 }
 
 template <int D>
@@ -117,6 +111,8 @@ static int fail(int code, const std::string& msg) {
     if (err__ != cudaSuccess) return fail(SHC_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(err__)); \
   } while (0)
 
+constexpr int kHostChunks = 8;  // tile ranges of one shc_step_host call (kernel k+1 overlaps the D2H of range k)
+
 struct GraphKey {
   int k;
   const float *cmd, *imu, *force;
@@ -147,6 +143,8 @@ struct shc_engine {
   int* d_flags = nullptr;
   const float* d_efforts = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy = nullptr;                       // D2H of shc_step_host, behind the tile-range kernels
+  cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // pinned staging for shc_step_host
   float *h_cmd = nullptr, *h_imu = nullptr, *h_force = nullptr, *h_manual = nullptr, *h_out = nullptr;
   float *d_cmd = nullptr, *d_imu = nullptr, *d_force = nullptr, *d_manual = nullptr, *d_out = nullptr;
@@ -548,9 +546,12 @@ static int configure_cycle_kernel(shc_engine* e) {
   });
 }
 
+// Launches the control cycle for the tiles [io.tile_begin, tile_end) (tile = 32 robots).
 static int launch_cycle(shc_engine* e, const StepIO& io, cudaStream_t st) {
   const int threads = SHC_BLOCK;
-  const int blocks = (e->n + threads - 1) / threads;
+  const int tiles = io.tile_end - io.tile_begin;
+  if (tiles <= 0) return SHC_OK;
+  const int blocks = (tiles + threads / 32 - 1) / (threads / 32);
   return with_cycle_kernel(e, [&](auto kernel, auto pl) -> int {
     kernel<<<blocks, threads, e->smem_block, st>>>(e->c, pl, io);
     cudaError_t err = cudaGetLastError();
@@ -693,6 +694,9 @@ void shc_destroy(shc_engine* e) {
     if (e->ev_done[b]) cudaEventDestroy(e->ev_done[b]);
   }
   if (e->side) cudaStreamDestroy(e->side);
+  if (e->copy) cudaStreamDestroy(e->copy);
+  for (auto ev : e->ev_chunk)
+    if (ev) cudaEventDestroy(ev);
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->s_planes);
   cudaFree(e->d_planes);
@@ -748,17 +752,21 @@ int shc_set_state(shc_engine* e, const shc_robot_state* in, size_t n_records) {
   return upload(e, h);
 }
 
-int shc_step(shc_engine* e, const float* cmd, const float* imu, const float* tip_force, const float* manual, float* joints_out,
-             void* stream) {
-  if (!e || !cmd || !joints_out) return fail(SHC_E_INVALID, "shc_step: cmd and joints_out are required");
+static StepIO make_io(shc_engine* e, const float* cmd, const float* imu, const float* tip_force, const float* manual, float* joints_out) {
   StepIO io;
   io.cmd = cmd; io.imu = imu; io.tip_force = tip_force; io.manual = manual; io.efforts = e->d_efforts;
   io.joints_out = joints_out;
-  io.n_peers = 0;
-  for (int p = 0; p < 7; ++p) io.peer_out[p] = nullptr;
+  io.tile_begin = 0;
+  io.tile_end = (e->n + 31) / 32;
   io.flags_out = (e->options & SHC_OPT_STATUS_FLAGS) ? e->d_flags : nullptr;
   io.pose_reset_mode = e->pose_reset_mode;
-  return launch_cycle(e, io, stream ? (cudaStream_t)stream : e->stream);
+  return io;
+}
+
+int shc_step(shc_engine* e, const float* cmd, const float* imu, const float* tip_force, const float* manual, float* joints_out,
+             void* stream) {
+  if (!e || !cmd || !joints_out) return fail(SHC_E_INVALID, "shc_step: cmd and joints_out are required");
+  return launch_cycle(e, make_io(e, cmd, imu, tip_force, manual, joints_out), stream ? (cudaStream_t)stream : e->stream);
 }
 
 static int ensure_staging(shc_engine* e, bool imu, bool force, bool manual) {
@@ -768,6 +776,8 @@ static int ensure_staging(shc_engine* e, bool imu, bool force, bool manual) {
     CUDA_TRY(cudaMalloc((void**)&e->d_cmd, n * 3 * 4));
     CUDA_TRY(cudaMallocHost((void**)&e->h_out, n * L * D * 4));
     CUDA_TRY(cudaMalloc((void**)&e->d_out, n * L * D * 4));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
+    for (int k = 0; k < kHostChunks; ++k) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_chunk[k], cudaEventDisableTiming));
   }
   if (imu && !e->h_imu) {
     CUDA_TRY(cudaMallocHost((void**)&e->h_imu, n * 10 * 4));
@@ -784,6 +794,20 @@ static int ensure_staging(shc_engine* e, bool imu, bool force, bool manual) {
   return SHC_OK;
 }
 
+// Page-locked (cudaMallocHost / cudaHostRegister) host memory can be the source / target of the DMA directly.
+static bool host_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// One control cycle with HOST buffers.  Inputs go up in one copy each (straight from the caller's buffer when it is
+// page-locked, through the engine's pinned staging buffer otherwise); the batch is then issued as kHostChunks tile
+// ranges on the engine's stream, and each range's joint angles start their way down on a second stream as soon as its
+// kernel has finished, so that all but the first range's arithmetic hides behind the D2H transfer (the longer of the two).
 int shc_step_host(shc_engine* e, const float* cmd, const float* imu, const float* tip_force, const float* manual,
                   float* joints_out) {
   if (!e || !cmd || !joints_out) return fail(SHC_E_INVALID, "shc_step_host: cmd and joints_out are required");
@@ -792,25 +816,36 @@ int shc_step_host(shc_engine* e, const float* cmd, const float* imu, const float
   if (rc != SHC_OK) return rc;
   const size_t n = e->n, L = e->cfg.leg_count, D = e->cfg.joint_count;
   cudaStream_t st = e->stream;
-  std::memcpy(e->h_cmd, cmd, n * 3 * 4);
-  CUDA_TRY(cudaMemcpyAsync(e->d_cmd, e->h_cmd, n * 3 * 4, cudaMemcpyHostToDevice, st));
-  if (imu) {
-    std::memcpy(e->h_imu, imu, n * 10 * 4);
-    CUDA_TRY(cudaMemcpyAsync(e->d_imu, e->h_imu, n * 10 * 4, cudaMemcpyHostToDevice, st));
+  auto upload = [&](const float* src, float* staging, float* dev, size_t bytes) -> int {
+    const float* from = src;
+    if (!host_pinned(src)) {
+      std::memcpy(staging, src, bytes);
+      from = staging;
+    }
+    CUDA_TRY(cudaMemcpyAsync(dev, from, bytes, cudaMemcpyHostToDevice, st));
+    return SHC_OK;
+  };
+  if ((rc = upload(cmd, e->h_cmd, e->d_cmd, n * 3 * 4)) != SHC_OK) return rc;
+  if (imu && (rc = upload(imu, e->h_imu, e->d_imu, n * 10 * 4)) != SHC_OK) return rc;
+  if (tip_force && (rc = upload(tip_force, e->h_force, e->d_force, n * L * 3 * 4)) != SHC_OK) return rc;
+  if (manual && (rc = upload(manual, e->h_manual, e->d_manual, n * 6 * 4)) != SHC_OK) return rc;
+
+  const bool out_pinned = host_pinned(joints_out);
+  float* down = out_pinned ? joints_out : e->h_out;
+  StepIO io = make_io(e, e->d_cmd, imu ? e->d_imu : nullptr, tip_force ? e->d_force : nullptr, manual ? e->d_manual : nullptr, e->d_out);
+  const int tiles = (int)((n + 31) / 32);
+  const int chunks = tiles >= 64 * kHostChunks ? kHostChunks : 1;
+  for (int k = 0; k < chunks; ++k) {
+    io.tile_begin = (int)((long long)tiles * k / chunks);
+    io.tile_end = (int)((long long)tiles * (k + 1) / chunks);
+    if ((rc = launch_cycle(e, io, st)) != SHC_OK) return rc;
+    CUDA_TRY(cudaEventRecord(e->ev_chunk[k], st));
+    CUDA_TRY(cudaStreamWaitEvent(e->copy, e->ev_chunk[k], 0));
+    const size_t r0 = (size_t)io.tile_begin * 32, r1 = std::min((size_t)io.tile_end * 32, n);
+    CUDA_TRY(cudaMemcpyAsync(down + r0 * L * D, e->d_out + r0 * L * D, (r1 - r0) * L * D * 4, cudaMemcpyDeviceToHost, e->copy));
   }
-  if (tip_force) {
-    std::memcpy(e->h_force, tip_force, n * L * 3 * 4);
-    CUDA_TRY(cudaMemcpyAsync(e->d_force, e->h_force, n * L * 3 * 4, cudaMemcpyHostToDevice, st));
-  }
-  if (manual) {
-    std::memcpy(e->h_manual, manual, n * 6 * 4);
-    CUDA_TRY(cudaMemcpyAsync(e->d_manual, e->h_manual, n * 6 * 4, cudaMemcpyHostToDevice, st));
-  }
-  rc = shc_step(e, e->d_cmd, imu ? e->d_imu : nullptr, tip_force ? e->d_force : nullptr, manual ? e->d_manual : nullptr, e->d_out, st);
-  if (rc != SHC_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(e->h_out, e->d_out, n * L * D * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
-  std::memcpy(joints_out, e->h_out, n * L * D * 4);
+  CUDA_TRY(cudaStreamSynchronize(e->copy));
+  if (!out_pinned) std::memcpy(joints_out, e->h_out, n * L * D * 4);
   return SHC_OK;
 }
 

@@ -204,8 +204,17 @@ class Engine:
         self._keep = (cmd, imu, tip_force, manual)  # keep inputs alive until the launch has consumed them
         return out
 
-    def step_host(self, cmd, imu=None, tip_force=None, manual=None) -> np.ndarray:
-        """One control cycle with HOST numpy buffers through the C-ABI (pinned staging, H2D, kernel, D2H, sync)."""
+    def pinned_host(self, *shape) -> np.ndarray:
+        """A page-locked float32 host array (numpy view of a pinned torch tensor): shc_step_host moves such buffers by
+        DMA directly instead of staging them."""
+        t = self.torch.empty(shape, dtype=self.torch.float32, pin_memory=True)
+        a = t.numpy()
+        self._pinned = getattr(self, "_pinned", []) + [t]  # keep the owner alive
+        return a
+
+    def step_host(self, cmd, imu=None, tip_force=None, manual=None, out=None) -> np.ndarray:
+        """One control cycle with HOST numpy buffers through the C-ABI (H2D, tile-range kernels overlapped with the D2H of
+        the joint angles, sync).  Page-locked arrays (pinned_host) are transferred in place; others go through staging."""
         fp = C.POINTER(C.c_float)
 
         def h(a, shape):
@@ -219,7 +228,9 @@ class Engine:
         imu, pi_ = h(imu, (self.n, 10))
         tip_force, pf = h(tip_force, (self.n, self.L, 3))
         manual, pm = h(manual, (self.n, 6))
-        out = np.empty((self.n, self.L, self.D), dtype=np.float32)
+        if out is None:
+            out = np.empty((self.n, self.L, self.D), dtype=np.float32)
+        assert out.dtype == np.float32 and out.shape == (self.n, self.L, self.D) and out.flags["C_CONTIGUOUS"]
         _check(lib().shc_step_host(self._h, pc, pi_, pf, pm, out.ctypes.data_as(fp)))
         return out
 
