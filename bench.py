@@ -156,7 +156,13 @@ def main():
     ap.add_argument("--precision", default="f64", choices=["f64", "mixed"], help="f64 = parity mode (default)")
     ap.add_argument("--robots-per-gpu", type=int, default=ROBOTS_PER_GPU)
     ap.add_argument("--gait", default="tripod_gait")
+    ap.add_argument("--workload", default="hexapod", choices=["hexapod", "octopod"],
+                    help="hexapod = the headline workload (configs[4] shard); octopod = configs[3]: 8 legs x 5 DOF with "
+                         "admittance + IMU + inclination posing, 262144 robots (secondary line, same JSON shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: fused = the kernel stores joint angles into every rank's buffer over NVLink (peer memory); "
+                         "nccl = library-issued ncclAllGather per cycle on a side stream")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -165,10 +171,10 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from syropod_highlevel_controller_b200.config import hexapod_config
+    from syropod_highlevel_controller_b200.config import hexapod_config, octopod_config
     from syropod_highlevel_controller_b200.engine import Engine
     from syropod_highlevel_controller_b200.parallel import shard_robots
-    from syropod_highlevel_controller_b200.streams import CommandStream
+    from syropod_highlevel_controller_b200.streams import CommandStream, ForceStream, ImuStream
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -179,9 +185,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n = args.robots_per_gpu
+    octo = args.workload == "octopod"
+    n = args.robots_per_gpu if not octo or args.robots_per_gpu != ROBOTS_PER_GPU else 262144
     shard = shard_robots(n * world, rank, world)
-    cfg = hexapod_config(args.gait)
+    cfg = octopod_config(args.gait) if octo else hexapod_config(args.gait)
     L, D = cfg.leg_count, cfg.joint_count
     K, W = args.steps, args.warmup
 
@@ -191,17 +198,28 @@ def main():
     pre = 300  # untimed pre-roll so that the batch is in its steady mix of walk states (STARTING/MOVING/STOPPING/STOPPED)
     cmd_host = np.stack([cs.next() for _ in range(pre + W + K)])
     cmd_dev = torch.from_numpy(cmd_host).to(dev)
+    # configs[3]: IMU orientation / gyro and tip forces are per-cycle inputs too (a short cycle of distinct frames)
+    imu_dev = force_dev = None
+    if octo:
+        ims, fs = ImuStream(n, robot_offset=shard.offset), ForceStream(n, L, robot_offset=shard.offset)
+        imu_dev = torch.from_numpy(np.stack([ims.next(cfg.time_delta) for _ in range(8)])).to(dev)
+        force_dev = torch.from_numpy(np.stack([fs.next() for _ in range(8)])).to(dev)
     # N > 1: one NCCL all-gather of the joint angles per cycle, issued by the library on a side stream and double
     # buffered so that cycle t's gather overlaps cycle t+1's kernel (shc_rollout_allgather)
     if world > 1:
         eng.init_nccl(rank, world)
-        local2 = torch.empty((2, n, L, D), dtype=torch.float32, device=dev)
-        full2 = torch.empty((2, n * world, L, D), dtype=torch.float32, device=dev)
+        if args.gather == "fused":
+            eng.init_gather_fused(rank, world)
+        else:
+            local2 = torch.empty((2, n, L, D), dtype=torch.float32, device=dev)
+            full2 = torch.empty((2, n * world, L, D), dtype=torch.float32, device=dev)
 
     def run(lo, hi):
         if world == 1:
             for i in range(lo, hi):
-                eng.step(cmd_dev[i])
+                eng.step(cmd_dev[i], None if imu_dev is None else imu_dev[i & 7], None if force_dev is None else force_dev[i & 7])
+        elif args.gather == "fused":
+            eng.rollout_gather_fused(cmd_dev[lo:hi])
         else:
             eng.rollout_allgather(cmd_dev[lo:hi], local2, full2)
 
@@ -233,7 +251,7 @@ def main():
     torch.cuda.synchronize()
     k0.record()
     for i in range(pre + W, pre + W + K):
-        eng.step(cmd_dev[i])
+        eng.step(cmd_dev[i], None if imu_dev is None else imu_dev[i & 7], None if force_dev is None else force_dev[i & 7])
     k1.record()
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / K
@@ -241,7 +259,7 @@ def main():
     b_alg = eng.bytes_per_step_algorithmic
     achieved = n * b_alg / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.precision), "kernel": "control_cycle_kernel", "kernel_ms": kernel_ms,
+                "traffic": None if octo else ncu_traffic(args.precision), "kernel": "control_cycle_kernel", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_step": b_alg, "device_bytes_per_step": eng.bytes_per_step_device,
                 "device_bytes_GBps": n * eng.bytes_per_step_device / (kernel_ms * 1e-3) / 1e9, "peak_source": peak_src}
 
@@ -251,17 +269,22 @@ def main():
     host_cmd = eng.pinned_host(e2e_steps, n, 3)
     host_cmd[:] = cmd_host[pre + W: pre + W + e2e_steps]
     host_out = eng.pinned_host(n, L, D)
-    eng.step_host(host_cmd[0], out=host_out)
+    host_imu = host_force = None
+    if octo:
+        host_imu, host_force = eng.pinned_host(n, 10), eng.pinned_host(n, L, 3)
+        host_imu[:] = imu_dev[0].cpu().numpy()
+        host_force[:] = force_dev[0].cpu().numpy()
+    eng.step_host(host_cmd[0], host_imu, host_force, out=host_out)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        eng.step_host(host_cmd[i], out=host_out)
+        eng.step_host(host_cmd[i], host_imu, host_force, out=host_out)
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e = {"value": n * world * e2e_steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": n * 3 * 4,
+    e2e = {"value": n * world * e2e_steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": n * (3 + (10 + 3 * L if octo else 0)) * 4,
            "d2h_bytes_per_step": n * L * D * 4, "steps": e2e_steps,
            "api": "shc_step_host (C-ABI, page-locked host buffers: H2D of the commands, 8 tile-range kernel launches, "
                   "D2H of each range's joint angles overlapped with the next range's kernel, stream sync)",
@@ -270,8 +293,11 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"config5 shard: {n} hexapods/GPU (6 legs x 3 DOF), {args.gait}, default.yaml parameters, "
-                                   f"per-robot splitmix64 command streams" + ("; NCCL all-gather of joint angles per cycle" if world > 1 else ""),
+            "config": {"workload": (f"configs[3]: {n} octopods/GPU (8 legs x 5 DOF), admittance + IMU + inclination posing, {args.gait}, "
+                                    f"per-robot command / IMU / tip-force streams" if octo else
+                                    f"config5 shard: {n} hexapods/GPU (6 legs x 3 DOF), {args.gait}, default.yaml parameters, "
+                                    f"per-robot splitmix64 command streams") + (("; all-gather of joint angles per cycle fused into the kernel (peer-memory stores over NVLink)" if args.gather == "fused"
+                                     else "; NCCL all-gather of joint angles per cycle") if world > 1 else ""),
                        "robots_per_gpu": n, "robots_total": n * world, "precision": args.precision,
                        "l2": f"state {n * (eng.bytes_per_step_device - 84) // 2 / 1e6:.0f} MB per GPU > 126 MB L2 (inputs larger than L2, no flush)",
                        "pre_roll_cycles": pre},

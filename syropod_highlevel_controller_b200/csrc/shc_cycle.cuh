@@ -34,7 +34,13 @@ struct StepIO {
   const float* tip_force;  // [N][L][3] or null
   const float* manual;     // [N][6] or null
   const float* efforts;    // [N][L][D] or null: measured joint efforts (jointStatesCallback, state_controller.cpp:1565)
-  float* joints_out;       // [N][L][D]
+  float* joints_out;       // [N][L][D] (this shard's joint commands)
+  // Fused all-gather (multi-GPU): when n_gather > 0 the tile is ALSO stored into every rank's gather buffer
+  // gather[p][gather_offset + ...], p = 0 .. n_gather-1 — peer-mapped device pointers (CUDA IPC), i.e. plain stores that
+  // travel over NVLink / NVSwitch while the other tiles are still being computed.  The own rank's buffer is one of them.
+  float* gather[8];
+  long long gather_offset;  // elements: buffer index * world * N * L * D + rank * N * L * D
+  int n_gather;
   int tile_begin, tile_end;  // tiles (32 robots each) of this launch: a step may be issued as several tile ranges so that
                              // the D2H copy of one range overlaps the arithmetic of the next (shc_step_host)
   int* flags_out;          // [N] or null

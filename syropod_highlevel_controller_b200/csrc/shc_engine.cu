@@ -56,6 +56,12 @@ __global__ void SHC_KERNEL_BOUNDS control_cycle_kernel(const __grid_constant__ C
   const float* src = reinterpret_cast<const float*>(wsm + 2 * CY::slot_bytes(front));
   float* dst0 = io.joints_out + base;
   for (int i = lane; i < valid; i += 32) dst0[i] = src[i];
+  // fused all-gather: the same lines go straight into every rank's gather buffer over NVLink (peer-mapped memory), so
+  // the transfer overlaps the computation of the other tiles instead of running as a separate collective afterwards
+  for (int p = 0; p < io.n_gather; ++p) {
+    float* dst = io.gather[p] + io.gather_offset + base;
+    for (int i = lane; i < valid; i += 32) dst[i] = src[i];
+  }
 }
 
 template <int D>
@@ -111,6 +117,7 @@ static int fail(int code, const std::string& msg) {
     if (err__ != cudaSuccess) return fail(SHC_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(err__)); \
   } while (0)
 
+constexpr int kGatherBuffers = 3;  // cycle k writes buffer k % 3; it waits for the "landed" signal of cycle k - 2
 constexpr int kHostChunks = 8;  // tile ranges of one shc_step_host call (kernel k+1 overlaps the D2H of range k)
 
 struct GraphKey {
@@ -155,6 +162,15 @@ struct shc_engine {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   bool done_valid[2] = {false, false};
+  // fused all-gather over peer memory: this rank's gather buffer (kGatherBuffers x world x N x L x D floats, cudaMalloc'ed
+  // so that it can be exported through CUDA IPC), the peers' buffers opened from their handles, a 1-element buffer for the
+  // per-cycle NCCL all-reduce that tells every rank "all shards of this cycle have landed"
+  float* gather_own = nullptr;
+  float* gather_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool gather_opened[8] = {false, false, false, false, false, false, false, false};
+  int* gather_token = nullptr;
+  cudaEvent_t ev_kernel[4] = {nullptr, nullptr, nullptr, nullptr}, ev_landed[4] = {nullptr, nullptr, nullptr, nullptr};
+  long long gather_cycle = 0;
 };
 
 // NCCL is resolved at run time from the libnccl already loaded in the process (torch's), so libshc_b200.so has no
@@ -165,6 +181,7 @@ struct NcclApi {
   int (*GetUniqueId)(NcclUid*) = nullptr;
   int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool ok = false;
@@ -180,9 +197,10 @@ NcclApi& nccl() {
       api.GetUniqueId = (int (*)(NcclUid*))dlsym(h, "ncclGetUniqueId");
       api.CommInitRank = (int (*)(void**, int, NcclUid, int))dlsym(h, "ncclCommInitRank");
       api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+      api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
       api.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
       api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
-      api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy;
+      api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.AllReduce && api.CommDestroy;
     }
   }
   return api;
@@ -695,6 +713,14 @@ void shc_destroy(shc_engine* e) {
   }
   if (e->side) cudaStreamDestroy(e->side);
   if (e->copy) cudaStreamDestroy(e->copy);
+  for (int p = 0; p < 8; ++p)
+    if (e->gather_opened[p]) cudaIpcCloseMemHandle(e->gather_peer[p]);
+  cudaFree(e->gather_own);
+  cudaFree(e->gather_token);
+  for (int b = 0; b < 4; ++b) {
+    if (e->ev_kernel[b]) cudaEventDestroy(e->ev_kernel[b]);
+    if (e->ev_landed[b]) cudaEventDestroy(e->ev_landed[b]);
+  }
   for (auto ev : e->ev_chunk)
     if (ev) cudaEventDestroy(ev);
   if (e->stream) cudaStreamSynchronize(e->stream);
@@ -758,6 +784,9 @@ static StepIO make_io(shc_engine* e, const float* cmd, const float* imu, const f
   io.joints_out = joints_out;
   io.tile_begin = 0;
   io.tile_end = (e->n + 31) / 32;
+  io.n_gather = 0;
+  io.gather_offset = 0;
+  for (auto& g : io.gather) g = nullptr;
   io.flags_out = (e->options & SHC_OPT_STATUS_FLAGS) ? e->d_flags : nullptr;
   io.pose_reset_mode = e->pose_reset_mode;
   return io;
@@ -962,6 +991,88 @@ int shc_rollout_allgather(shc_engine* e, int k_cycles, const float* cmd_seq, flo
   // join: the caller's stream continues only after the last gathers
   for (int b = 0; b < 2; ++b)
     if (e->done_valid[b]) CUDA_TRY(cudaStreamWaitEvent(st, e->ev_done[b], 0));
+  return SHC_OK;
+}
+
+// ---- fused all-gather over peer memory (NVLink / NVSwitch) ---------------------------------------------------------------
+// Every rank allocates its gather buffer with cudaMalloc and exports it (CUDA IPC, 64-byte handle); the caller exchanges
+// the handles (e.g. torch.distributed.all_gather_object) and every rank opens its peers' buffers.  The control-cycle
+// kernel then stores each tile's joint commands into ALL ranks' buffers as it finishes the tile.
+int shc_gather_alloc(shc_engine* e, void* handle64_out, float** buffer_out) {
+  if (!e || !handle64_out) return fail(SHC_E_INVALID, "shc_gather_alloc: bad arguments");
+  if (!e->nccl_comm) return fail(SHC_E_INVALID, "shc_nccl_init has not been called");
+  if (e->world > 8) return fail(SHC_E_UNSUPPORTED, "fused gather supports up to 8 ranks (one node)");
+  CUDA_TRY(cudaSetDevice(e->device));
+  const size_t per_rank = (size_t)e->n * e->cfg.leg_count * e->cfg.joint_count;
+  if (!e->gather_own) {
+    CUDA_TRY(cudaMalloc((void**)&e->gather_own, (size_t)kGatherBuffers * e->world * per_rank * 4));
+    CUDA_TRY(cudaMemset(e->gather_own, 0, (size_t)kGatherBuffers * e->world * per_rank * 4));
+    CUDA_TRY(cudaMalloc((void**)&e->gather_token, 4));
+    CUDA_TRY(cudaMemset(e->gather_token, 0, 4));
+    for (int b = 0; b < kGatherBuffers; ++b) {
+      CUDA_TRY(cudaEventCreateWithFlags(&e->ev_kernel[b], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&e->ev_landed[b], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, e->gather_own));
+  static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+  std::memcpy(handle64_out, &h, 64);
+  e->gather_peer[e->rank] = e->gather_own;
+  if (buffer_out) *buffer_out = e->gather_own;
+  return SHC_OK;
+}
+
+int shc_gather_open_peer(shc_engine* e, int peer_rank, const void* handle64) {
+  if (!e || !handle64 || peer_rank < 0 || peer_rank >= e->world || peer_rank >= 8) return fail(SHC_E_INVALID, "shc_gather_open_peer: bad arguments");
+  if (peer_rank == e->rank) return SHC_OK;
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  e->gather_peer[peer_rank] = (float*)p;
+  e->gather_opened[peer_rank] = true;
+  return SHC_OK;
+}
+
+int shc_gather_buffers(void) { return kGatherBuffers; }
+
+// k control cycles; cycle t stores its joint commands into buffer (t % 3) of EVERY rank's gather buffer from inside the
+// kernel, then a 1-element NCCL all-reduce on the side stream tells every rank that all shards of cycle t have landed.
+// Cycle t + 2 (which overwrites the buffer cycle t - 1 used... i.e. reuses a buffer three cycles later) waits for the
+// signal of cycle t, so the signal's latency is off the critical path.  On return (stream-ordered) the caller's stream
+// has waited for the last signals; *last_buffer_out = index of the buffer holding the last cycle.
+int shc_rollout_gather_fused(shc_engine* e, int k_cycles, const float* cmd_seq, int* last_buffer_out, void* stream) {
+  if (!e || !cmd_seq || k_cycles < 1) return fail(SHC_E_INVALID, "shc_rollout_gather_fused: bad arguments");
+  if (!e->gather_own) return fail(SHC_E_INVALID, "shc_gather_alloc has not been called");
+  for (int p = 0; p < e->world; ++p)
+    if (!e->gather_peer[p]) return fail(SHC_E_INVALID, "shc_gather_open_peer has not been called for every peer");
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  const size_t n = e->n, per_rank = n * e->cfg.leg_count * e->cfg.joint_count;
+  for (int k = 0; k < k_cycles; ++k) {
+    const long long cyc = e->gather_cycle++;
+    const int b = (int)(cyc % kGatherBuffers);
+    if (cyc >= 2) CUDA_TRY(cudaStreamWaitEvent(st, e->ev_landed[(cyc - 2) % kGatherBuffers], 0));
+    StepIO io = make_io(e, cmd_seq + (size_t)k * n * 3, nullptr, nullptr, nullptr, e->gather_own + ((size_t)b * e->world + e->rank) * per_rank);
+    io.n_gather = 0;
+    for (int p = 0; p < e->world; ++p)
+      if (p != e->rank) io.gather[io.n_gather++] = e->gather_peer[p];
+    io.gather_offset = (long long)(((size_t)b * e->world + e->rank) * per_rank);
+    int rc = launch_cycle(e, io, st);
+    if (rc != SHC_OK) return rc;
+    CUDA_TRY(cudaEventRecord(e->ev_kernel[b], st));
+    CUDA_TRY(cudaStreamWaitEvent(e->side, e->ev_kernel[b], 0));
+    static const bool no_signal = getenv("SHC_GATHER_NOSIGNAL") != nullptr;  // kernel tuning only: timing without the signal
+    rc = no_signal ? 0 : nccl().AllReduce(e->gather_token, e->gather_token, 1, /*ncclInt32*/ 2, /*ncclSum*/ 0, e->nccl_comm, e->side);
+    if (rc != 0) return fail(SHC_E_CUDA, std::string("ncclAllReduce: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error"));
+    CUDA_TRY(cudaEventRecord(e->ev_landed[b], e->side));
+    if (last_buffer_out) *last_buffer_out = b;
+  }
+  const long long done = e->gather_cycle;
+  for (long long c = std::max(0LL, done - 2); c < done; ++c) CUDA_TRY(cudaStreamWaitEvent(st, e->ev_landed[c % kGatherBuffers], 0));
   return SHC_OK;
 }
 

@@ -58,6 +58,9 @@ def lib():
         L.shc_nccl_init.argtypes = [vp, vp, C.c_int, C.c_int]
         L.shc_allgather_joints.argtypes = [vp, vp, vp, vp]
         L.shc_rollout_allgather.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+        L.shc_gather_alloc.argtypes = [vp, vp, C.POINTER(vp)]
+        L.shc_gather_open_peer.argtypes = [vp, C.c_int, vp]
+        L.shc_rollout_gather_fused.argtypes = [vp, C.c_int, vp, C.POINTER(C.c_int), vp]
         L.shc_stream.argtypes = [vp]
         L.shc_stream.restype = vp
         L.shc_synchronize.argtypes = [vp]
@@ -271,6 +274,42 @@ class Engine:
         _check(lib().shc_rollout_allgather(self._h, k, _ptr(cmd_seq), _ptr(local2), _ptr(full2),
                                            _stream_handle(torch, self.device, stream)))
         self._keep = (cmd_seq, local2, full2)
+
+    def init_gather_fused(self, rank: int, world_size: int):
+        """Sets up the fused all-gather over peer memory (after init_nccl): allocates this rank's gather buffer, exchanges
+        the CUDA IPC handles through torch.distributed and maps every peer's buffer.  Returns the own buffer as a torch
+        tensor [buffers, world, n, L, D] (a view of library-owned device memory)."""
+        import torch.distributed as dist
+
+        torch = self.torch
+        handle = (C.c_char * 64)()
+        buf = C.c_void_p()
+        _check(lib().shc_gather_alloc(self._h, handle, C.byref(buf)))
+        handles = [None] * world_size
+        dist.all_gather_object(handles, bytes(handle.raw))
+        for p, hb in enumerate(handles):
+            if p != rank:
+                _check(lib().shc_gather_open_peer(self._h, p, C.c_char_p(hb)))
+        dist.barrier()
+        nb = int(lib().shc_gather_buffers())
+        shape = (nb, world_size, self.n, self.L, self.D)
+
+        class _Dev:  # __cuda_array_interface__ view of the library's buffer
+            __cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (int(buf.value), False), "version": 2}
+
+        self.gather = torch.as_tensor(_Dev(), device=self.device)
+        return self.gather
+
+    def rollout_gather_fused(self, cmd_seq, stream=None) -> int:
+        """k cycles whose joint commands land in every rank's gather buffer from inside the kernel (peer-memory stores over
+        NVLink).  Returns the index of the buffer that holds the last cycle."""
+        torch = self.torch
+        k = int(cmd_seq.shape[0])
+        assert cmd_seq.is_cuda and cmd_seq.dtype == torch.float32 and cmd_seq.is_contiguous()
+        last = C.c_int(-1)
+        _check(lib().shc_rollout_gather_fused(self._h, k, _ptr(cmd_seq), C.byref(last), _stream_handle(torch, self.device, stream)))
+        self._keep = (cmd_seq,)
+        return int(last.value)
 
     def set_joint_efforts(self, efforts):
         efforts = self._f32(efforts, (self.n, self.L, self.D))

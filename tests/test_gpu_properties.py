@@ -1,6 +1,7 @@
 """GPU: size-independent properties at BASELINE.json's full batch sizes (where the oracle would take minutes), the
 host/graph entry points, the stand-alone IK kernel and the status flags."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -193,3 +194,48 @@ def test_status_flags_match_oracle_and_do_not_change_results(shc_lib, oracle):
     for e in (plain, flagged):
         e.close()
     ob.close()
+
+
+@pytest.mark.gpu
+def test_fused_gather_two_gpus():
+    """N > 1: the kernel's peer-memory stores deliver every rank's joint angles to every rank, bit for
+    bit what a plain all_gather of the per-rank results gives.  Needs two GPUs on the box; runs under torchrun."""
+    import subprocess
+    import sys
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "dev_p2p_check.py"), "2065"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("-> OK") == 2
+
+
+def test_host_entry_point_tile_ranges_and_pinned_buffers(shc_lib):
+    """shc_step_host issues a large batch as 8 tile ranges (D2H of one overlapping the kernel of the next) and moves
+    page-locked caller buffers by DMA in place: same bits as one device-resident launch, pinned or pageable, and the tail
+    tile (n not a multiple of 32) is handled."""
+    import torch
+
+    cfg = hexapod_config("tripod_gait")
+    n, k = 20011, 12
+    a = _engine(cfg, n, "f64")
+    b = _engine(cfg, n, "f64", startup=a.startup())
+    c_ = _engine(cfg, n, "f64", startup=a.startup())
+    cs = CommandStream(n, min_len=3, max_len=8)
+    pin_cmd, pin_out = b.pinned_host(n, 3), b.pinned_host(n, 6, 3)
+    for i in range(k):
+        cmd = cs.next()
+        ja = a.step(torch.from_numpy(cmd).cuda()).cpu().numpy()
+        pin_cmd[:] = cmd
+        jb = b.step_host(pin_cmd, out=pin_out)
+        jc = c_.step_host(cmd)
+        assert jb is pin_out
+        assert np.array_equal(ja, jb), i
+        assert np.array_equal(ja, jc), i
+    assert bytes(a.get_state()) == bytes(b.get_state()) == bytes(c_.get_state())
+    for e in (a, b, c_):
+        e.close()
