@@ -454,6 +454,8 @@ template <class P, int D, bool FULL> struct Cycle {
     PoseT<K> man = pose_identity<K>();
     if (ci.manual_posing) man = ldPose(sp, RS_MAN);
     T dvx = T(sp[(RS_VEL) * 32]), dvy = T(sp[(RS_VEL + 1) * 32]), dw = T(sp[(RS_ANGVEL) * 32]);
+    const K walker_wp_z = K(sp[(RS_WPL + 2) * 32]);
+    const V3<K> walker_wpn_k = ld3K(sp, RS_WPN);
 
     // ---- inputs: bodyVelocityInputCallback (state_controller.cpp:1127-1136) --------------------------------------
     double vin_x = (double)io.cmd[3 * (size_t)r + 0] * cd.body_velocity_scaler;
@@ -505,9 +507,18 @@ template <class P, int D, bool FULL> struct Cycle {
     K wp_z = K(0);
     V3<K> wpn_ref{K(0), K(0), K(1)};
     if (ref_leg >= 0) {
-      int base = ci.offS_leg + ref_leg * ci.strideS_leg;
-      wp_z = K(sp[(base + LS::WP + 2) * 32]);
-      wpn_ref = ld3K(sp, base + LS::WPN);
+      // A leg with a valid swing progress ran its tip update in the previous cycle and saved the walker's plane of that
+      // cycle's start (walk_controller.cpp:1049).  Unless the previous cycle's updateWalkPlane changed the plane
+      // (RB_PLANE_CHANGED, also set for states written from outside), that is the walker's plane held now: no
+      // dependent HBM round trip for the leg's saved copy.
+      if ((rbits >> RB_PLANE_CHANGED) & 1) {
+        int base = ci.offS_leg + ref_leg * ci.strideS_leg;
+        wp_z = K(sp[(base + LS::WP + 2) * 32]);
+        wpn_ref = ld3K(sp, base + LS::WPN);
+      } else {
+        wp_z = walker_wp_z;
+        wpn_ref = walker_wpn_k;
+      }
     }
     PoseT<K> wpp = owpp;
     if (c_in != 0.0) {
@@ -1084,7 +1095,9 @@ template <class P, int D, bool FULL> struct Cycle {
     // =================================================================================================================
     // 4. updateWalkPlane (:748) + odometry (:783)
     // =================================================================================================================
+    bool plane_changed = false;  // a cycle without updateWalkPlane (trap 7) leaves the plane as it was
     if (!starting_now) {
+      V3<double> new_wpl{0.0, 0.0, 0.0}, new_wpn{0.0, 0.0, 1.0};
       if (L >= 3) {
         // normal equations over the (possibly updated) default tips: A = [x y 1], b = z.  Re-read here rather than
         // accumulated inside the leg loop to keep eight doubles out of its live registers.
@@ -1107,11 +1120,17 @@ template <class P, int D, bool FULL> struct Cycle {
         double b = (c01 * sxz + c11 * syz + c12 * sz1) * id;
         double cc = (c02 * sxz + c12 * syz + c22 * sz1) * id;
         V3<double> nrm = normalized(V3<double>{-a, -b, 1.0});
-        st3(sp, RS_WPL, V3<double>{a, b, cc});
-        st3(sp, RS_WPN, nrm);
-      } else {
-        st3(sp, RS_WPL, V3<double>{0.0, 0.0, 0.0});
-        st3(sp, RS_WPN, V3<double>{0.0, 0.0, 1.0});
+        new_wpl = V3<double>{a, b, cc};
+        new_wpn = nrm;
+      }
+      {
+        // stored values as the next cycle will read them; "changed" compares the stored bits
+        const V3<S> ol = {sp[(RS_WPL) * 32], sp[(RS_WPL + 1) * 32], sp[(RS_WPL + 2) * 32]};
+        const V3<S> on = {sp[(RS_WPN) * 32], sp[(RS_WPN + 1) * 32], sp[(RS_WPN + 2) * 32]};
+        plane_changed = !(ol.x == S(new_wpl.x) && ol.y == S(new_wpl.y) && ol.z == S(new_wpl.z) && on.x == S(new_wpn.x) &&
+                          on.y == S(new_wpn.y) && on.z == S(new_wpn.z));
+        st3(sp, RS_WPL, new_wpl);
+        st3(sp, RS_WPN, new_wpn);
       }
       // odometry_ideal_ = odometry_ideal_.addPose(calculateOdometry(dt))
       Q4<T> oq{T(sp[(RS_ODOMQ) * 32]), T(sp[(RS_ODOMQ + 1) * 32]), T(sp[(RS_ODOMQ + 2) * 32]),
@@ -1129,7 +1148,7 @@ template <class P, int D, bool FULL> struct Cycle {
     }
 
     rbits = (walk_state & 3) | ((legs_at_correct & 15) << 2) | ((legs_completed & 15) << 6) | ((rtd & 1) << 10) |
-            ((pose_state & 3) << 11) | ((auto_state & 3) << 13) | (status << 16);
+            ((pose_state & 3) << 11) | ((auto_state & 3) << 13) | ((plane_changed ? 1 : 0) << RB_PLANE_CHANGED) | (status << 16);
     ip[(RI_BITS) * 32] = rbits;
     if (io.flags_out && live) io.flags_out[r] = status;
   }

@@ -32,10 +32,15 @@ using PrecMixed = Prec<float, float, double>;  // fp32 state + trajectory; fp64 
 
 // One warp per tile of 32 robots (lane = robot); warps are independent (no block-level synchronisation), each with
 // its own slice of the dynamic shared memory: two TMA staging slots, the joint-command tile and two mbarriers.
+// The full engine (auto / IMU / inclination posing, admittance) keeps more state live across the leg loop: it trades
+// occupancy for registers (SHC_MIN_BLOCKS_FULL warps per SM) instead of spilling.
+#ifndef SHC_MIN_BLOCKS_FULL
+#define SHC_MIN_BLOCKS_FULL 10
+#endif
 #ifdef SHC_MAXNREG
 #define SHC_KERNEL_BOUNDS __maxnreg__(SHC_MAXNREG)
 #else
-#define SHC_KERNEL_BOUNDS __launch_bounds__(SHC_BLOCK, SHC_MIN_BLOCKS)
+#define SHC_KERNEL_BOUNDS __launch_bounds__(SHC_BLOCK, FULL ? SHC_MIN_BLOCKS_FULL : SHC_MIN_BLOCKS)
 #endif
 template <class P, int D, bool FULL>
 __global__ void SHC_KERNEL_BOUNDS control_cycle_kernel(const __grid_constant__ Consts c, Planes<typename P::S> pl, StepIO io) {
@@ -356,7 +361,8 @@ void pack(const shc_engine* e, const shc_robot_state* in, size_t n, HostPlanes& 
       I(ci.offI_auto + AI_PHASE, r) = s.pose_phase;
     }
     I(RI_BITS, r) = (s.walk_state & 3) | ((s.legs_at_correct_phase & 15) << 2) | ((s.legs_completed_first_step & 15) << 6) |
-                    ((s.return_to_default_attempted & 1) << 10) | ((s.pose_state & 3) << 11) | ((s.auto_posing_state & 3) << 13);
+                    ((s.return_to_default_attempted & 1) << 10) | ((s.pose_state & 3) << 11) | ((s.auto_posing_state & 3) << 13) |
+                    (1 << RB_PLANE_CHANGED);  // a state written from outside: the first cycle reads the legs' saved planes
     for (int l = 0; l < L; ++l) {
       const shc_leg_state& g = s.legs[l];
       const int sb = ci.offS_leg + l * ci.strideS_leg;

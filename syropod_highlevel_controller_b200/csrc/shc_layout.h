@@ -72,7 +72,8 @@ enum : int { AI_FLAGS = 0 /*4 latch bits per AutoPoser*/, AI_PHASE = 1 /*pose_ph
 enum : int { LI_BITS = 0, LI_PROG = 1, LI_COUNT = 2 };
 
 // RI_BITS: walk_state[0:2) legs_at_correct_phase[2:6) legs_completed_first_step[6:10) return_to_default_attempted[10]
-//          pose_state[11:13) auto_posing_state[13:15)  status flags [16:32)
+//          pose_state[11:13) auto_posing_state[13:15) walk plane changed by the last cycle / unknown [15]  status flags [16:32)
+enum : int { RB_PLANE_CHANGED = 15 };
 // LI_BITS: phase[0:16) step_state[16:18) at_correct_phase[18] completed_first_step[19] negate_auto_pose[20]
 // LI_PROG: swing progress numerator (int16, -1 = "-1.0") | stance progress numerator (int16) << 16
 //          progress = numerator / swing_period (resp. stance_period): walk_controller.cpp:878-896 divides two ints
