@@ -54,19 +54,40 @@ __global__ void SHC_KERNEL_BOUNDS control_cycle_kernel(const __grid_constant__ C
   unsigned char* wsm = shc_smem + (size_t)warp * c.i.smem_per_warp;
   CY::run(c, pl, tile, lane, io, wsm);
   __syncwarp();
-  // the warp writes its tile of joint commands as coalesced 128-byte lines
+  // The tile of joint commands leaves shared memory as TMA bulk stores: one request to the local buffer and, in the
+  // fused all-gather, one per rank straight into that rank's gather buffer over NVLink (peer-mapped memory) — the
+  // exchange overlaps the computation of the other tiles instead of running as a separate collective afterwards.
   const int LD = c.i.L * D;
-  const int valid = min(32, c.i.n_robots - tile_first) * LD;
+  const int robots = min(32, c.i.n_robots - tile_first);
+  const int valid = robots * LD;
   const size_t base = (size_t)tile_first * LD;
   const float* src = reinterpret_cast<const float*>(wsm + 2 * CY::slot_bytes(front));
-  float* dst0 = io.joints_out + base;
-  for (int i = lane; i < valid; i += 32) dst0[i] = src[i];
-  // fused all-gather: the same lines go straight into every rank's gather buffer over NVLink (peer-mapped memory), so
-  // the transfer overlaps the computation of the other tiles instead of running as a separate collective afterwards
-  for (int p = 0; p < io.n_gather; ++p) {
-    float* dst = io.gather[p] + io.gather_offset + base;
-    for (int i = lane; i < valid; i += 32) dst[i] = src[i];
-  }
+  bool any_bulk = false;
+  auto put = [&](float* dst) {
+    // whole tiles go as one bulk store when the destination is 16-byte aligned (always, unless a shard's robot count makes
+    // its slice of a gather buffer start off a 16-byte boundary); the batch's tail tile goes as plain coalesced stores
+    if (robots == 32 && (reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) {
+      if (lane == 0) bulk_s2g(dst, src, (unsigned)(valid * 4));
+      any_bulk = true;
+    } else {
+      for (int i = lane; i < valid; i += 32) dst[i] = src[i];
+    }
+  };
+  if (lane == 0) fence_proxy_async_smem();  // the lanes' generic-proxy writes of the tile, ordered by the __syncwarp above
+  put(io.joints_out + base);
+  for (int p = 0; p < io.n_gather; ++p) put(io.gather[p] + io.gather_offset + base);
+  if (any_bulk && lane == 0) bulk_commit_and_wait_read();  // shared memory may go away once the TMA unit has read it
+}
+
+// "This rank's shard of cycle c has landed everywhere": launched behind the control-cycle kernel on the same stream (its
+// peer-memory stores are performed when it completes), it raises this rank's flag in every peer's flag array.  The peers
+// wait on their local flags with stream memory operations (cuStreamWaitValue32): no collective per cycle.
+struct SignalArgs {
+  int* flag[8];
+  int n, value;
+};
+__global__ void gather_signal_kernel(SignalArgs a) {
+  if (threadIdx.x < a.n) store_release_sys(a.flag[threadIdx.x], a.value);
 }
 
 template <int D>
@@ -122,7 +143,10 @@ static int fail(int code, const std::string& msg) {
     if (err__ != cudaSuccess) return fail(SHC_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(err__)); \
   } while (0)
 
-constexpr int kGatherBuffers = 3;  // cycle k writes buffer k % 3; it waits for the "landed" signal of cycle k - 2
+// Cycle k writes buffer k % 8 of every rank.  Rewriting a buffer needs the landed signal of cycle k - 7 (every rank has
+// then started the cycle after the one whose data is overwritten, i.e. is past any stream-ordered consumer of it), so one
+// wait covers the next six cycles: the waits are rare and never on the critical path.
+constexpr int kGatherBuffers = 8;
 constexpr int kHostChunks = 8;  // tile ranges of one shc_step_host call (kernel k+1 overlaps the D2H of range k)
 
 struct GraphKey {
@@ -170,12 +194,13 @@ struct shc_engine {
   // fused all-gather over peer memory: this rank's gather buffer (kGatherBuffers x world x N x L x D floats, cudaMalloc'ed
   // so that it can be exported through CUDA IPC), the peers' buffers opened from their handles, a 1-element buffer for the
   // per-cycle NCCL all-reduce that tells every rank "all shards of this cycle have landed"
+  int gather_signal_mode = 0;       // 0 = flags + cuStreamWaitValue32, 1 = 1-element NCCL all-reduce, 2 = none (tuning)
   float* gather_own = nullptr;
   float* gather_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool gather_opened[8] = {false, false, false, false, false, false, false, false};
   int* gather_token = nullptr;
-  cudaEvent_t ev_kernel[4] = {nullptr, nullptr, nullptr, nullptr}, ev_landed[4] = {nullptr, nullptr, nullptr, nullptr};
-  long long gather_cycle = 0;
+  cudaEvent_t ev_kernel[kGatherBuffers] = {}, ev_landed[kGatherBuffers] = {};
+  long long gather_cycle = 0, gather_waited = -1;  // cycles issued; newest cycle whose landed signal this stream waited for
 };
 
 // NCCL is resolved at run time from the libnccl already loaded in the process (torch's), so libshc_b200.so has no
@@ -209,6 +234,26 @@ NcclApi& nccl() {
     }
   }
   return api;
+}
+}  // namespace
+
+// cuStreamWaitValue32 (driver API) is resolved at run time from the libcuda already loaded in the process, so the
+// library has no link-time dependency on it (the CPU-only symbol checks load libshc_b200.so without a driver).
+namespace {
+typedef int (*StreamWaitValue32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+StreamWaitValue32Fn stream_wait_value32() {
+  static StreamWaitValue32Fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      fn = (StreamWaitValue32Fn)dlsym(h, "cuStreamWaitValue32_v2");
+      if (!fn) fn = (StreamWaitValue32Fn)dlsym(h, "cuStreamWaitValue32");
+    }
+  }
+  return fn;
 }
 }  // namespace
 
@@ -722,8 +767,9 @@ void shc_destroy(shc_engine* e) {
   for (int p = 0; p < 8; ++p)
     if (e->gather_opened[p]) cudaIpcCloseMemHandle(e->gather_peer[p]);
   cudaFree(e->gather_own);
+
   cudaFree(e->gather_token);
-  for (int b = 0; b < 4; ++b) {
+  for (int b = 0; b < kGatherBuffers; ++b) {
     if (e->ev_kernel[b]) cudaEventDestroy(e->ev_kernel[b]);
     if (e->ev_landed[b]) cudaEventDestroy(e->ev_landed[b]);
   }
@@ -793,6 +839,7 @@ static StepIO make_io(shc_engine* e, const float* cmd, const float* imu, const f
   io.n_gather = 0;
   io.gather_offset = 0;
   for (auto& g : io.gather) g = nullptr;
+
   io.flags_out = (e->options & SHC_OPT_STATUS_FLAGS) ? e->d_flags : nullptr;
   io.pose_reset_mode = e->pose_reset_mode;
   return io;
@@ -1011,8 +1058,12 @@ int shc_gather_alloc(shc_engine* e, void* handle64_out, float** buffer_out) {
   CUDA_TRY(cudaSetDevice(e->device));
   const size_t per_rank = (size_t)e->n * e->cfg.leg_count * e->cfg.joint_count;
   if (!e->gather_own) {
-    CUDA_TRY(cudaMalloc((void**)&e->gather_own, (size_t)kGatherBuffers * e->world * per_rank * 4));
-    CUDA_TRY(cudaMemset(e->gather_own, 0, (size_t)kGatherBuffers * e->world * per_rank * 4));
+    // [kGatherBuffers][world][n][L][D] floats, then (256-byte aligned) one landed flag per source rank
+    const size_t data_bytes = ((size_t)kGatherBuffers * e->world * per_rank * 4 + 255) / 256 * 256;
+    CUDA_TRY(cudaMalloc((void**)&e->gather_own, data_bytes + 256));
+    CUDA_TRY(cudaMemset(e->gather_own, 0, data_bytes + 256));
+    if (const char* m = getenv("SHC_GATHER_SIGNAL")) e->gather_signal_mode = !strcmp(m, "nccl") ? 1 : !strcmp(m, "none") ? 2 : 0;
+    if (e->gather_signal_mode == 0 && !stream_wait_value32()) e->gather_signal_mode = 1;
     CUDA_TRY(cudaMalloc((void**)&e->gather_token, 4));
     CUDA_TRY(cudaMemset(e->gather_token, 0, 4));
     for (int b = 0; b < kGatherBuffers; ++b) {
@@ -1045,11 +1096,12 @@ int shc_gather_open_peer(shc_engine* e, int peer_rank, const void* handle64) {
 
 int shc_gather_buffers(void) { return kGatherBuffers; }
 
-// k control cycles; cycle t stores its joint commands into buffer (t % 3) of EVERY rank's gather buffer from inside the
-// kernel, then a 1-element NCCL all-reduce on the side stream tells every rank that all shards of cycle t have landed.
-// Cycle t + 2 (which overwrites the buffer cycle t - 1 used... i.e. reuses a buffer three cycles later) waits for the
-// signal of cycle t, so the signal's latency is off the critical path.  On return (stream-ordered) the caller's stream
-// has waited for the last signals; *last_buffer_out = index of the buffer holding the last cycle.
+// k control cycles; cycle t stores its joint commands into buffer (t % shc_gather_buffers()) of EVERY rank's gather buffer
+// from inside the kernel (TMA bulk stores to peer-mapped memory); a one-warp kernel behind it raises this rank's "cycle t
+// has landed" flag on every peer, which the peers wait on with stream memory operations (SHC_GATHER_SIGNAL=nccl falls back
+// to a 1-element NCCL all-reduce per cycle on a side stream).
+// On return (stream-ordered) the caller's stream has waited for the last cycle's signals; *last_buffer_out = index of
+// the buffer holding the last cycle.
 int shc_rollout_gather_fused(shc_engine* e, int k_cycles, const float* cmd_seq, int* last_buffer_out, void* stream) {
   if (!e || !cmd_seq || k_cycles < 1) return fail(SHC_E_INVALID, "shc_rollout_gather_fused: bad arguments");
   if (!e->gather_own) return fail(SHC_E_INVALID, "shc_gather_alloc has not been called");
@@ -1058,27 +1110,64 @@ int shc_rollout_gather_fused(shc_engine* e, int k_cycles, const float* cmd_seq, 
   CUDA_TRY(cudaSetDevice(e->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
   const size_t n = e->n, per_rank = n * e->cfg.leg_count * e->cfg.joint_count;
+  const size_t data_bytes = ((size_t)kGatherBuffers * e->world * per_rank * 4 + 255) / 256 * 256;
+  auto flags_of = [&](int p) { return reinterpret_cast<int*>(reinterpret_cast<char*>(e->gather_peer[p]) + data_bytes); };
+  // waits (stream-ordered) until every shard of cycle `c` has landed in this rank's buffer
+  auto wait_landed = [&](long long c) -> int {
+    if (e->gather_signal_mode == 0) {
+      for (int p = 0; p < e->world; ++p) {
+        if (p == e->rank) continue;
+        int rc = stream_wait_value32()(st, (unsigned long long)(uintptr_t)(flags_of(e->rank) + p), (unsigned)(c + 1), /*CU_STREAM_WAIT_VALUE_GEQ*/ 0);
+        if (rc != 0) return fail(SHC_E_CUDA, "cuStreamWaitValue32 failed");
+      }
+    } else if (e->gather_signal_mode == 1) {
+      CUDA_TRY(cudaStreamWaitEvent(st, e->ev_landed[c % kGatherBuffers], 0));
+    }
+    return SHC_OK;
+  };
   for (int k = 0; k < k_cycles; ++k) {
     const long long cyc = e->gather_cycle++;
     const int b = (int)(cyc % kGatherBuffers);
-    if (cyc >= 2) CUDA_TRY(cudaStreamWaitEvent(st, e->ev_landed[(cyc - 2) % kGatherBuffers], 0));
+    int rc;
+    if (cyc - kGatherBuffers + 1 > e->gather_waited) {
+      const long long target = std::max(cyc - kGatherBuffers + 1, cyc - 2);  // the newest cycle that is surely on its way
+      if ((rc = wait_landed(target)) != SHC_OK) return rc;
+      e->gather_waited = target;
+    }
     StepIO io = make_io(e, cmd_seq + (size_t)k * n * 3, nullptr, nullptr, nullptr, e->gather_own + ((size_t)b * e->world + e->rank) * per_rank);
     io.n_gather = 0;
     for (int p = 0; p < e->world; ++p)
       if (p != e->rank) io.gather[io.n_gather++] = e->gather_peer[p];
     io.gather_offset = (long long)(((size_t)b * e->world + e->rank) * per_rank);
-    int rc = launch_cycle(e, io, st);
+    rc = launch_cycle(e, io, st);
     if (rc != SHC_OK) return rc;
-    CUDA_TRY(cudaEventRecord(e->ev_kernel[b], st));
-    CUDA_TRY(cudaStreamWaitEvent(e->side, e->ev_kernel[b], 0));
-    static const bool no_signal = getenv("SHC_GATHER_NOSIGNAL") != nullptr;  // kernel tuning only: timing without the signal
-    rc = no_signal ? 0 : nccl().AllReduce(e->gather_token, e->gather_token, 1, /*ncclInt32*/ 2, /*ncclSum*/ 0, e->nccl_comm, e->side);
-    if (rc != 0) return fail(SHC_E_CUDA, std::string("ncclAllReduce: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error"));
-    CUDA_TRY(cudaEventRecord(e->ev_landed[b], e->side));
+    if (e->gather_signal_mode == 0) {
+      SignalArgs sa;
+      sa.n = 0;
+      for (int p = 0; p < e->world; ++p)
+        if (p != e->rank) sa.flag[sa.n++] = flags_of(p) + e->rank;
+      sa.value = (int)(cyc + 1);
+      gather_signal_kernel<<<1, 32, 0, st>>>(sa);
+    }
+    if (e->gather_signal_mode == 1) {
+      CUDA_TRY(cudaEventRecord(e->ev_kernel[b], st));
+      CUDA_TRY(cudaStreamWaitEvent(e->side, e->ev_kernel[b], 0));
+      rc = nccl().AllReduce(e->gather_token, e->gather_token, 1, /*ncclInt32*/ 2, /*ncclSum*/ 0, e->nccl_comm, e->side);
+      if (rc != 0) return fail(SHC_E_CUDA, std::string("ncclAllReduce: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error"));
+      CUDA_TRY(cudaEventRecord(e->ev_landed[b], e->side));
+    }
     if (last_buffer_out) *last_buffer_out = b;
   }
+  // the caller's stream resumes once the last cycle has landed from every rank (in NCCL mode the events of the last
+  // cycles; the flags are monotonic, so one wait on the newest value covers all earlier cycles)
   const long long done = e->gather_cycle;
-  for (long long c = std::max(0LL, done - 2); c < done; ++c) CUDA_TRY(cudaStreamWaitEvent(st, e->ev_landed[c % kGatherBuffers], 0));
+  if (e->gather_signal_mode == 1) {
+    for (long long c = std::max(0LL, done - kGatherBuffers); c < done; ++c) CUDA_TRY(cudaStreamWaitEvent(st, e->ev_landed[c % kGatherBuffers], 0));
+  } else {
+    int rc = wait_landed(done - 1);
+    if (rc != SHC_OK) return rc;
+  }
+  e->gather_waited = done - 1;
   return SHC_OK;
 }
 
