@@ -143,11 +143,13 @@ static int fail(int code, const std::string& msg) {
     if (err__ != cudaSuccess) return fail(SHC_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(err__)); \
   } while (0)
 
-// Cycle k writes buffer k % B of every rank (B = 16).  Rewriting a buffer needs the landed signal of cycle k - B + 1 (every
-// rank has then started the cycle after the one whose data is overwritten, i.e. is past any stream-ordered consumer of
-// it).  The stream waits once every B / 2 cycles, for a cycle B / 2 + 1 back: the peers are long past it, so the wait
-// neither aligns the ranks nor sits on the critical path.
+// Cycle k writes buffer k % B of every rank (B = 16).  Rewriting a buffer needs a landed signal of cycle k - B + 1 or
+// later (every rank has then started the cycle after the one whose data is overwritten, i.e. is past any stream-ordered
+// consumer of it).  Signals are raised for every kGatherSignalEvery-th cycle and for the last cycle of a call (the flags
+// are monotonic cycle numbers), so inside a long rollout the per-cycle path carries neither a signal nor a wait; a call
+// of one cycle signals and waits every cycle, which is what a consumer of every cycle's data needs.
 constexpr int kGatherBuffers = 16;
+constexpr int kGatherSignalEvery = 8;
 constexpr int kHostChunks = 8;  // tile ranges of one shc_step_host call (kernel k+1 overlaps the D2H of range k)
 
 struct GraphKey {
@@ -195,13 +197,18 @@ struct shc_engine {
   // fused all-gather over peer memory: this rank's gather buffer (kGatherBuffers x world x N x L x D floats, cudaMalloc'ed
   // so that it can be exported through CUDA IPC), the peers' buffers opened from their handles, a 1-element buffer for the
   // per-cycle NCCL all-reduce that tells every rank "all shards of this cycle have landed"
-  int gather_signal_mode = 0;       // 0 = flags + cuStreamWaitValue32, 1 = 1-element NCCL all-reduce, 2 = none (tuning)
+  // landed signals: 0 = per-source flags (one-warp kernel, st.release.sys) + cuStreamWaitValue32 inside a call, barrier
+  // all-reduce at the end of a call (default); 1 = no mid-call flags (when cuStreamWaitValue32 is unavailable: calls must then
+  // be shorter than the 16-buffer reuse window); 2 = none (tuning only)
+  int gather_signal_mode = 0;
   float* gather_own = nullptr;
   float* gather_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool gather_opened[8] = {false, false, false, false, false, false, false, false};
   int* gather_token = nullptr;
   cudaEvent_t ev_kernel[kGatherBuffers] = {}, ev_landed[kGatherBuffers] = {};
   long long gather_cycle = 0, gather_waited = -1;  // cycles issued; newest cycle whose landed signal this stream waited for
+  long long gather_signal_hist[4] = {-1, -1, -1, -1};  // the last cycles for which a landed signal was issued (same on every rank)
+  unsigned gather_signal_pos = 0;
 };
 
 // NCCL is resolved at run time from the libnccl already loaded in the process (torch's), so libshc_b200.so has no
@@ -1063,7 +1070,7 @@ int shc_gather_alloc(shc_engine* e, void* handle64_out, float** buffer_out) {
     const size_t data_bytes = ((size_t)kGatherBuffers * e->world * per_rank * 4 + 255) / 256 * 256;
     CUDA_TRY(cudaMalloc((void**)&e->gather_own, data_bytes + 256));
     CUDA_TRY(cudaMemset(e->gather_own, 0, data_bytes + 256));
-    if (const char* m = getenv("SHC_GATHER_SIGNAL")) e->gather_signal_mode = !strcmp(m, "nccl") ? 1 : !strcmp(m, "none") ? 2 : 0;
+    if (const char* m = getenv("SHC_GATHER_SIGNAL")) e->gather_signal_mode = !strcmp(m, "none") ? 2 : !strcmp(m, "barrier") ? 1 : 0;
     if (e->gather_signal_mode == 0 && !stream_wait_value32()) e->gather_signal_mode = 1;
     CUDA_TRY(cudaMalloc((void**)&e->gather_token, 4));
     CUDA_TRY(cudaMemset(e->gather_token, 0, 4));
@@ -1113,27 +1120,34 @@ int shc_rollout_gather_fused(shc_engine* e, int k_cycles, const float* cmd_seq, 
   const size_t n = e->n, per_rank = n * e->cfg.leg_count * e->cfg.joint_count;
   const size_t data_bytes = ((size_t)kGatherBuffers * e->world * per_rank * 4 + 255) / 256 * 256;
   auto flags_of = [&](int p) { return reinterpret_cast<int*>(reinterpret_cast<char*>(e->gather_peer[p]) + data_bytes); };
-  // waits (stream-ordered) until every shard of cycle `c` has landed in this rank's buffer
-  auto wait_landed = [&](long long c) -> int {
-    if (e->gather_signal_mode == 0) {
-      for (int p = 0; p < e->world; ++p) {
-        if (p == e->rank) continue;
-        int rc = stream_wait_value32()(st, (unsigned long long)(uintptr_t)(flags_of(e->rank) + p), (unsigned)(c + 1), /*CU_STREAM_WAIT_VALUE_GEQ*/ 0);
-        if (rc != 0) return fail(SHC_E_CUDA, "cuStreamWaitValue32 failed");
-      }
-    } else if (e->gather_signal_mode == 1) {
-      CUDA_TRY(cudaStreamWaitEvent(st, e->ev_landed[c % kGatherBuffers], 0));
-    }
-    return SHC_OK;
+  const bool flags_ok = e->gather_signal_mode == 0;
+  // raises this rank's "cycle c has landed" flag on every peer, behind the kernels already on stream `s`
+  auto raise_flags = [&](long long c, cudaStream_t s) {
+    SignalArgs sa;
+    sa.n = 0;
+    for (int p = 0; p < e->world; ++p)
+      if (p != e->rank) sa.flag[sa.n++] = flags_of(p) + e->rank;
+    sa.value = (int)(c + 1);
+    gather_signal_kernel<<<1, 32, 0, s>>>(sa);
   };
   for (int k = 0; k < k_cycles; ++k) {
     const long long cyc = e->gather_cycle++;
     const int b = (int)(cyc % kGatherBuffers);
     int rc;
-    static const bool no_wait = getenv("SHC_GATHER_NOWAIT") != nullptr;  // tuning only: waits at the end of the call only
-    if (!no_wait && cyc - kGatherBuffers + 1 > e->gather_waited) {
-      const long long target = std::max(cyc - kGatherBuffers + 1, cyc - kGatherBuffers / 2 - 1);
-      if ((rc = wait_landed(target)) != SHC_OK) return rc;
+    // Rewriting buffer b needs a landed signal of cycle cyc - B + 1 or later from every rank.  Inside a call the stream
+    // waits (cuStreamWaitValue32 on the local flags) for the OLDEST signalled cycle that qualifies: it is >= 8 cycles
+    // back, so the flags are already up and the wait passes at once (a wait that really has to wait costs ~0.5 ms on
+    // this driver, which is why the end of the call uses a collective instead).
+    if (flags_ok && cyc - kGatherBuffers + 1 > e->gather_waited) {
+      long long target = -1;
+      for (long long sgn : e->gather_signal_hist)
+        if (sgn >= cyc - kGatherBuffers + 1 && (target < 0 || sgn < target)) target = sgn;
+      if (target < 0) return fail(SHC_E_INVALID, "fused gather: no landed signal in the reuse window");
+      for (int p = 0; p < e->world; ++p) {
+        if (p == e->rank) continue;
+        if (stream_wait_value32()(st, (unsigned long long)(uintptr_t)(flags_of(e->rank) + p), (unsigned)(target + 1), /*GEQ*/ 0) != 0)
+          return fail(SHC_E_CUDA, "cuStreamWaitValue32 failed");
+      }
       e->gather_waited = target;
     }
     StepIO io = make_io(e, cmd_seq + (size_t)k * n * 3, nullptr, nullptr, nullptr, e->gather_own + ((size_t)b * e->world + e->rank) * per_rank);
@@ -1143,39 +1157,29 @@ int shc_rollout_gather_fused(shc_engine* e, int k_cycles, const float* cmd_seq, 
     io.gather_offset = (long long)(((size_t)b * e->world + e->rank) * per_rank);
     rc = launch_cycle(e, io, st);
     if (rc != SHC_OK) return rc;
-    if (e->gather_signal_mode == 0) {
-      // The signal runs on the side stream behind this cycle's kernel: its system-scope release has to wait until the
-      // kernel's posted peer writes have drained through NVLink (66 MB per rank and cycle at 8 ranks), and on the main
-      // stream that drain would serialise with the next cycle's arithmetic instead of hiding behind it (measured at 8
-      // GPUs: 253 us per cycle with the signal in line, 157 us without any signal).
-      SignalArgs sa;
-      sa.n = 0;
-      for (int p = 0; p < e->world; ++p)
-        if (p != e->rank) sa.flag[sa.n++] = flags_of(p) + e->rank;
-      sa.value = (int)(cyc + 1);
+    const bool last = k == k_cycles - 1;
+    if (flags_ok && !last && cyc % kGatherSignalEvery == kGatherSignalEvery - 1) {
+      // mid-call signal, on the side stream: its system-scope release waits for the kernel's posted peer writes to drain
+      // through NVLink, and on the main stream that drain would serialise with the next cycle instead of hiding behind it
       CUDA_TRY(cudaEventRecord(e->ev_kernel[b], st));
       CUDA_TRY(cudaStreamWaitEvent(e->side, e->ev_kernel[b], 0));
-      gather_signal_kernel<<<1, 32, 0, e->side>>>(sa);
-    }
-    if (e->gather_signal_mode == 1) {
-      CUDA_TRY(cudaEventRecord(e->ev_kernel[b], st));
-      CUDA_TRY(cudaStreamWaitEvent(e->side, e->ev_kernel[b], 0));
-      rc = nccl().AllReduce(e->gather_token, e->gather_token, 1, /*ncclInt32*/ 2, /*ncclSum*/ 0, e->nccl_comm, e->side);
-      if (rc != 0) return fail(SHC_E_CUDA, std::string("ncclAllReduce: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error"));
-      CUDA_TRY(cudaEventRecord(e->ev_landed[b], e->side));
+      raise_flags(cyc, e->side);
+      e->gather_signal_hist[e->gather_signal_pos++ % 4] = cyc;
     }
     if (last_buffer_out) *last_buffer_out = b;
   }
-  // the caller's stream resumes once the last cycle has landed from every rank (in NCCL mode the events of the last
-  // cycles; the flags are monotonic, so one wait on the newest value covers all earlier cycles)
+  // End of the call: this rank's flag for the last cycle (in line: the release waits for the peer writes to drain), then
+  // a 1-element all-reduce as the barrier — once it completes here, every rank has drained and flagged its last cycle, so
+  // every shard of every cycle of the call has landed in this rank's buffer; every rank has also passed all consumers it
+  // had ordered before this call, which re-arms the reuse window.
   const long long done = e->gather_cycle;
-  if (e->gather_signal_mode == 1) {
-    for (long long c = std::max(0LL, done - kGatherBuffers); c < done; ++c) CUDA_TRY(cudaStreamWaitEvent(st, e->ev_landed[c % kGatherBuffers], 0));
-  } else {
-    int rc = wait_landed(done - 1);
-    if (rc != SHC_OK) return rc;
+  if (e->gather_signal_mode != 2) {
+    raise_flags(done - 1, st);
+    int rc = nccl().AllReduce(e->gather_token, e->gather_token, 1, /*ncclInt32*/ 2, /*ncclSum*/ 0, e->nccl_comm, st);
+    if (rc != 0) return fail(SHC_E_CUDA, std::string("ncclAllReduce: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error"));
+    e->gather_signal_hist[e->gather_signal_pos++ % 4] = done - 1;
+    e->gather_waited = done - 1;
   }
-  e->gather_waited = done - 1;
   return SHC_OK;
 }
 
