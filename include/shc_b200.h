@@ -130,17 +130,18 @@ int shc_rollout_allgather(shc_engine* e, int k_cycles, const float* cmd_seq, flo
 
 /* Fused all-gather over peer memory (one node, <= 8 ranks, after shc_nccl_init): the control-cycle kernel stores every
  * finished tile of joint commands into ALL ranks' gather buffers (TMA bulk stores to peer-mapped device memory, CUDA
- * IPC), so the exchange travels over NVLink / NVSwitch while the rest of the batch is still being computed.  A one-warp
- * kernel behind it raises this rank's "cycle t has landed" flag on every peer; peers wait on their local flags with
- * stream memory operations (cuStreamWaitValue32) — no collective on the per-cycle path.
+ * IPC), so the exchange travels over NVLink / NVSwitch while the rest of the batch is still being computed.
  *   shc_gather_alloc         allocates this rank's buffer (shc_gather_buffers() x world x [n][L][D] floats + flags),
  *                            returns its 64-byte IPC handle and (optionally) its device address
  *   shc_gather_open_peer     maps rank `peer_rank`'s buffer from its handle (the caller exchanges the handles)
- *   shc_rollout_gather_fused k cycles; cycle t lands in buffer t % shc_gather_buffers() of every rank: element
- *                            [buffer][rank r][robot][leg][joint].  A buffer is rewritten shc_gather_buffers() cycles
- *                            later, after every rank has signalled the cycle that follows its last use, so consumers
- *                            ordered on `stream` before the next call see complete data.  On return `stream` has waited
- *                            for the last cycle from every rank; *last_buffer_out = buffer of the last cycle. */
+ *   shc_rollout_gather_fused k cycles (every rank must make the same sequence of calls); cycle t lands in buffer
+ *                            t % shc_gather_buffers() of every rank: element [buffer][rank r][robot][leg][joint].
+ *                            Inside a call, sparse "landed" flags (one-warp kernel on a side stream, awaited with
+ *                            cuStreamWaitValue32 on values that are already up) protect the reuse of a buffer 16 cycles
+ *                            later; the call ends with the last cycle's flag and a 1-element ncclAllReduce on `stream`:
+ *                            work ordered on `stream` after the call sees every rank's shard of every cycle of the call,
+ *                            and a buffer is not rewritten before every rank has passed the consumers it ordered before
+ *                            its next call.  *last_buffer_out = buffer of the last cycle. */
 int shc_gather_alloc(shc_engine* e, void* handle64_out, float** buffer_out);
 int shc_gather_open_peer(shc_engine* e, int peer_rank, const void* handle64);
 int shc_gather_buffers(void);
