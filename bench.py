@@ -286,9 +286,9 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = {"value": n * world * e2e_steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": n * (3 + (10 + 3 * L if octo else 0)) * 4,
            "d2h_bytes_per_step": n * L * D * 4, "steps": e2e_steps,
-           "api": "shc_step_host (C-ABI, page-locked host buffers: H2D of the commands, 8 tile-range kernel launches, "
-                  "D2H of each range's joint angles overlapped with the next range's kernel, stream sync)",
-           "gpu_launches_per_step": 8}
+           "api": "shc_step_host (C-ABI, page-locked host buffers: H2D of the commands, one kernel launch whose TMA bulk "
+                  "stores write each tile's joint angles straight into the caller's page-locked buffer over PCIe, stream sync)",
+           "gpu_launches_per_step": 1}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

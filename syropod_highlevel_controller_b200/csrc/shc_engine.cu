@@ -921,6 +921,20 @@ int shc_step_host(shc_engine* e, const float* cmd, const float* imu, const float
   if (manual && (rc = upload(manual, e->h_manual, e->d_manual, n * 6 * 4)) != SHC_OK) return rc;
 
   const bool out_pinned = host_pinned(joints_out);
+  // Page-locked output: the kernel's TMA bulk stores can target the caller's buffer directly (mapped host memory, same
+  // address under UVA), so the joint angles cross PCIe as posted writes while the rest of the batch is still being
+  // computed — one launch, no D2H copy.  SHC_HOST_ZEROCOPY=0 keeps the tile-range / copy-engine path below.
+  static const bool zero_copy = [] { const char* v = getenv("SHC_HOST_ZEROCOPY"); return !(v && v[0] == '0'); }();
+  if (out_pinned && zero_copy) {
+    float* alias = nullptr;
+    if (cudaHostGetDevicePointer((void**)&alias, joints_out, 0) == cudaSuccess && alias) {
+      StepIO io = make_io(e, e->d_cmd, imu ? e->d_imu : nullptr, tip_force ? e->d_force : nullptr, manual ? e->d_manual : nullptr, alias);
+      if ((rc = launch_cycle(e, io, st)) != SHC_OK) return rc;
+      CUDA_TRY(cudaStreamSynchronize(st));
+      return SHC_OK;
+    }
+    cudaGetLastError();
+  }
   float* down = out_pinned ? joints_out : e->h_out;
   StepIO io = make_io(e, e->d_cmd, imu ? e->d_imu : nullptr, tip_force ? e->d_force : nullptr, manual ? e->d_manual : nullptr, e->d_out);
   const int tiles = (int)((n + 31) / 32);
