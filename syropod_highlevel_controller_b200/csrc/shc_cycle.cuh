@@ -45,7 +45,21 @@ struct StepIO {
                              // the D2H copy of one range overlaps the arithmetic of the next (shc_step_host)
   int* flags_out;          // [N] or null
   int pose_reset_mode;
+#ifdef SHC_TRACE
+  unsigned long long* trace;  // kernel-tuning builds only (-DSHC_TRACE): [tiles][32] globaltimer stamps written by lane 0
+#endif
 };
+// Kernel-tuning builds (-DSHC_TRACE, tools/dev_trace.py): per-tile timeline of the control cycle.  Compiles to nothing otherwise.
+#ifdef SHC_TRACE
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define SHC_STAMP(k) do { if (io.trace && lane == 0) io.trace[(size_t)tile_idx * 32 + (k)] = gtimer(); } while (0)
+#else
+#define SHC_STAMP(k) do { } while (0)
+#endif
 
 // ---- TMA bulk copies + mbarrier (sm_90+; SASS: UBLKCP.S.G / SYNCS) ------------------------------------------------
 // Each warp owns a two-slot staging ring in shared memory.  Lane 0 asks the TMA unit for the whole contiguous chunk of
@@ -425,6 +439,7 @@ template <class P, int D, bool FULL> struct Cycle {
     double* __restrict__ dp = pl.d + tile * (size_t)(ci.nD * 32) + lane;
     int* __restrict__ ip = pl.i + tile * (size_t)(ci.nI * 32) + lane;
 
+    SHC_STAMP(0);
     // ---- staging ring ------------------------------------------------------------------------------------------------
     const int sS_bytes = slot_s_bytes(front), s_bytes = slot_bytes(front);
     float* __restrict__ stage = reinterpret_cast<float*>(wsm + 2 * s_bytes) + lane * (L * D);
@@ -497,6 +512,7 @@ template <class P, int D, bool FULL> struct Cycle {
       issue_leg(0);
       if (L > 1) issue_leg(1);
     }
+    SHC_STAMP(2);
     int walk_state = rbits & 3;
     int legs_at_correct = (rbits >> 2) & 15;
     int legs_completed = (rbits >> 6) & 15;
@@ -792,6 +808,7 @@ template <class P, int D, bool FULL> struct Cycle {
     // =================================================================================================================
     // 3. per leg: walk state machine + LegStepper + updateStance + Leg::applyIK
     // =================================================================================================================
+    SHC_STAMP(3);
 #pragma unroll 1
     for (int l = 0; l < L; ++l) {
       // per-leg plane bases in HBM (stores, rare loads): every field of this leg is at an immediate offset from them
@@ -802,7 +819,9 @@ template <class P, int D, bool FULL> struct Cycle {
       const LegConsts<T>& lt = ct.leg[l];
       // the staged copy of this leg's every-cycle planes: wait for the TMA transfer issued two legs ago
       const unsigned char* slot = wsm + (l & 1) * s_bytes;
+      SHC_STAMP(4 + 3 * l);
       mbar_wait(bars + (l & 1), (unsigned)((l >> 1) & 1));
+      SHC_STAMP(5 + 3 * l);
       const S* __restrict__ ss = reinterpret_cast<const S*>(slot) + front * 32 + lane;
       const double* __restrict__ sd = reinterpret_cast<const double*>(slot + sS_bytes) + lane;
       const int* __restrict__ si = reinterpret_cast<const int*>(slot + sS_bytes + LD_COUNT * 32 * 8) + lane;
@@ -1040,6 +1059,7 @@ template <class P, int D, bool FULL> struct Cycle {
         fence_proxy_async_smem();
         issue_leg(l + 2);
       }
+      SHC_STAMP(6 + 3 * l);
       bits = (phase & 0xffff) | (step_state << 16) | ((at_correct ? 1 : 0) << 18) | ((completed ? 1 : 0) << 19) |
              ((negate ? 1 : 0) << 20);
       prog = (swing_num & 0xffff) | ((stance_num & 0xffff) << 16);
@@ -1169,6 +1189,7 @@ template <class P, int D, bool FULL> struct Cycle {
             ((pose_state & 3) << 11) | ((auto_state & 3) << 13) | ((plane_changed ? 1 : 0) << RB_PLANE_CHANGED) | (status << 16);
     ip[(RI_BITS) * 32] = rbits;
     if (io.flags_out && live) io.flags_out[r] = status;
+    SHC_STAMP(30);
   }
 };
 

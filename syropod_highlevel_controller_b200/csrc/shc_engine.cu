@@ -77,6 +77,9 @@ __global__ void SHC_KERNEL_BOUNDS control_cycle_kernel(const __grid_constant__ C
   put(io.joints_out + base);
   for (int p = 0; p < io.n_gather; ++p) put(io.gather[p] + io.gather_offset + base);
   if (any_bulk && lane == 0) bulk_commit_and_wait_read();  // shared memory may go away once the TMA unit has read it
+#ifdef SHC_TRACE
+  if (io.trace && lane == 0) io.trace[(size_t)tile * 32 + 31] = gtimer();
+#endif
 }
 
 // "This rank's shard of cycle c has landed everywhere": launched behind the control-cycle kernel on the same stream (its
@@ -176,6 +179,9 @@ struct shc_engine {
   int pose_reset_mode = 0;
   size_t s_elem = 8;  // bytes per storage word
   size_t smem_block = 0;  // dynamic shared memory per block of the control-cycle kernel
+#ifdef SHC_TRACE
+  unsigned long long* trace = nullptr;
+#endif
   void* s_planes = nullptr;
   double* d_planes = nullptr;
   int* i_planes = nullptr;
@@ -850,6 +856,9 @@ static StepIO make_io(shc_engine* e, const float* cmd, const float* imu, const f
 
   io.flags_out = (e->options & SHC_OPT_STATUS_FLAGS) ? e->d_flags : nullptr;
   io.pose_reset_mode = e->pose_reset_mode;
+#ifdef SHC_TRACE
+  io.trace = e->trace;
+#endif
   return io;
 }
 
@@ -1197,6 +1206,9 @@ int shc_rollout_gather_fused(shc_engine* e, int k_cycles, const float* cmd_seq, 
   return SHC_OK;
 }
 
+#ifdef SHC_TRACE
+int shc_debug_trace(shc_engine* e, unsigned long long* dev_buf) { e->trace = dev_buf; return SHC_OK; }
+#endif
 int shc_synchronize(shc_engine* e) {
   if (!e) return fail(SHC_E_INVALID, "null engine");
   CUDA_TRY(cudaSetDevice(e->device));
