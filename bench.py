@@ -47,14 +47,14 @@ def measured_peak():
         with open(path) as f:
             d = json.load(f)
 
-        def find(obj, want):
+        def find(obj, want, path=""):
             if isinstance(obj, dict):
                 for k, v in obj.items():
-                    kl = k.lower()
+                    kl = (path + "/" + k).lower()
                     if isinstance(v, (int, float)) and all(w in kl for w in want):
                         return float(v)
-                for v in obj.values():
-                    r = find(v, want)
+                for k, v in obj.items():
+                    r = find(v, want, path + "/" + k)
                     if r:
                         return r
             return None
