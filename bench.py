@@ -230,8 +230,13 @@ def main():
     if world > 1:
         eng.init_nccl(rank, world)
         if args.gather == "fused":
-            eng.init_gather_fused(rank, world)
-        else:
+            try:
+                eng.init_gather_fused(rank, world)
+            except RuntimeError as ex:  # raised on every rank together: CUDA IPC / peer access not available on this box
+                if rank == 0:
+                    print(f"bench.py: {ex}; falling back to --gather nccl", file=sys.stderr)
+                args.gather = "nccl"
+        if args.gather != "fused":
             local2 = torch.empty((2, n, L, D), dtype=torch.float32, device=dev)
             full2 = torch.empty((2, n * world, L, D), dtype=torch.float32, device=dev)
 

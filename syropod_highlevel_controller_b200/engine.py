@@ -278,19 +278,30 @@ class Engine:
     def init_gather_fused(self, rank: int, world_size: int):
         """Sets up the fused all-gather over peer memory (after init_nccl): allocates this rank's gather buffer, exchanges
         the CUDA IPC handles through torch.distributed and maps every peer's buffer.  Returns the own buffer as a torch
-        tensor [buffers, world, n, L, D] (a view of library-owned device memory)."""
+        tensor [buffers, world, n, L, D] (a view of library-owned device memory).  Collective: every rank must call it;
+        if any rank cannot allocate, export or map a buffer, every rank raises RuntimeError (so that callers can fall
+        back to the NCCL path together)."""
         import torch.distributed as dist
 
         torch = self.torch
+
+        def agree(ok: bool, what: str):
+            flag = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                raise RuntimeError(f"fused gather unavailable on at least one rank ({what})")
+
         handle = (C.c_char * 64)()
         buf = C.c_void_p()
-        _check(lib().shc_gather_alloc(self._h, handle, C.byref(buf)))
+        rc = lib().shc_gather_alloc(self._h, handle, C.byref(buf))
+        agree(rc == 0, "shc_gather_alloc")
         handles = [None] * world_size
         dist.all_gather_object(handles, bytes(handle.raw))
+        ok = True
         for p, hb in enumerate(handles):
-            if p != rank:
-                _check(lib().shc_gather_open_peer(self._h, p, C.c_char_p(hb)))
-        dist.barrier()
+            if p != rank and lib().shc_gather_open_peer(self._h, p, C.c_char_p(hb)) != 0:
+                ok = False
+        agree(ok, "shc_gather_open_peer")
         nb = int(lib().shc_gather_buffers())
         shape = (nb, world_size, self.n, self.L, self.D)
 
