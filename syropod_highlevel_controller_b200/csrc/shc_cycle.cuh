@@ -413,8 +413,15 @@ template <class P, int D, bool FULL> struct Cycle {
     return slot_s_bytes(frontS) + LD_COUNT * 32 * 8 + LI_COUNT * 32 * 4;
   }
   // Dynamic shared memory of one warp: [slot 0][slot 1][joint tile: 32 robots x L*D floats][2 mbarriers], 128-B granular.
+  // -DSHC_ALIAS_BARRIERS (round-2 experiment, not yet measured): the two mbarriers live in the last 16 bytes of the joint
+  // tile instead — lane 31's entries of the last two legs, which are only written after the last wait on the respective
+  // barrier — so a hexapod f64 warp needs 13568 B and a 16th one-warp block fits on an SM.
   static __host__ __device__ __forceinline__ int smem_per_warp(int frontS, int L) {
+#ifdef SHC_ALIAS_BARRIERS
+    return (2 * slot_bytes(frontS) + 32 * L * D * 4 + 127) / 128 * 128;
+#else
     return (2 * slot_bytes(frontS) + 32 * L * D * 4 + 16 + 127) / 128 * 128;
+#endif
   }
 
   // One warp = one tile of 32 robots (lane = robot).  `wsm` is the warp's shared memory (see smem_per_warp): the joint
@@ -443,21 +450,29 @@ template <class P, int D, bool FULL> struct Cycle {
     // ---- staging ring ------------------------------------------------------------------------------------------------
     const int sS_bytes = slot_s_bytes(front), s_bytes = slot_bytes(front);
     float* __restrict__ stage = reinterpret_cast<float*>(wsm + 2 * s_bytes) + lane * (L * D);
+#ifdef SHC_ALIAS_BARRIERS
+    // slot (L-1)&1 is waited on last at the start of leg L-1, the other slot at the start of leg L-2; the aliased tile entries
+    // (lane 31: [leg L-2, last joint .. leg L-1]) are written at the end of those legs, i.e. after the barrier is dead
+    uint64_t* bars_end = reinterpret_cast<uint64_t*>(wsm + 2 * s_bytes + 32 * L * D * 4) - 2;
+    auto bar_of = [&](int s) { return bars_end + (s == ((L - 1) & 1) ? 1 : 0); };
+#else
     uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + 2 * s_bytes + 32 * L * D * 4);
+    auto bar_of = [&](int s) { return bars + s; };
+#endif
     const S* tileS = pl.s + tile * (size_t)(ci.nS * 32);
     const double* tileD = pl.d + tile * (size_t)(ci.nD * 32);
     const int* tileI = pl.i + tile * (size_t)(ci.nI * 32);
     auto issue_leg = [&](int l) {  // lane 0: ask the TMA unit for leg l's every-cycle planes
       unsigned char* slot = wsm + (l & 1) * s_bytes;
-      uint64_t* bar = bars + (l & 1);
+      uint64_t* bar = bar_of(l & 1);
       mbar_expect_tx(bar, (unsigned)s_bytes);
       bulk_g2s(slot, tileS + (ci.offS_leg + l * ci.strideS_leg - front) * 32, (unsigned)sS_bytes, bar);
       bulk_g2s(slot + sS_bytes, tileD + (ci.offD_leg + l * ci.strideD_leg) * 32, LD_COUNT * 32 * 8, bar);
       bulk_g2s(slot + sS_bytes + LD_COUNT * 32 * 8, tileI + (ci.offI_leg + l * ci.strideI_leg) * 32, LI_COUNT * 32 * 4, bar);
     };
     if (lane == 0) {
-      mbar_init(bars, 1);
-      mbar_init(bars + 1, 1);
+      mbar_init(bar_of(0), 1);
+      mbar_init(bar_of(1), 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -820,7 +835,7 @@ template <class P, int D, bool FULL> struct Cycle {
       // the staged copy of this leg's every-cycle planes: wait for the TMA transfer issued two legs ago
       const unsigned char* slot = wsm + (l & 1) * s_bytes;
       SHC_STAMP(4 + 3 * l);
-      mbar_wait(bars + (l & 1), (unsigned)((l >> 1) & 1));
+      mbar_wait(bar_of(l & 1), (unsigned)((l >> 1) & 1));
       SHC_STAMP(5 + 3 * l);
       const S* __restrict__ ss = reinterpret_cast<const S*>(slot) + front * 32 + lane;
       const double* __restrict__ sd = reinterpret_cast<const double*>(slot + sS_bytes) + lane;
