@@ -413,9 +413,9 @@ template <class P, int D, bool FULL> struct Cycle {
     return slot_s_bytes(frontS) + LD_COUNT * 32 * 8 + LI_COUNT * 32 * 4;
   }
   // Dynamic shared memory of one warp: [slot 0][slot 1][joint tile: 32 robots x L*D floats][2 mbarriers], 128-B granular.
-  // -DSHC_ALIAS_BARRIERS (round-2 experiment, not yet measured): the two mbarriers live in the last 16 bytes of the joint
-  // tile instead — lane 31's entries of the last two legs, which are only written after the last wait on the respective
-  // barrier — so a hexapod f64 warp needs 13568 B and a 16th one-warp block fits on an SM.
+  // -DSHC_ALIAS_BARRIERS (tuning variant, off: measured 94.1 us against 94.5 us per launch, i.e. no gain): the two mbarriers
+  // live in the last 16 bytes of the joint tile instead — lane 31's entries of the last two legs, which are only written
+  // after the last wait on the respective barrier — so a hexapod f64 warp needs 13568 B and a 16th one-warp block fits.
   static __host__ __device__ __forceinline__ int smem_per_warp(int frontS, int L) {
 #ifdef SHC_ALIAS_BARRIERS
     return (2 * slot_bytes(frontS) + 32 * L * D * 4 + 127) / 128 * 128;
