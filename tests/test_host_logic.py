@@ -141,3 +141,21 @@ def test_command_stream_is_deterministic_and_shard_independent():
         assert np.all(np.hypot(f[:, 0], f[:, 1]) <= 1.0 + 1e-6) and np.all(np.abs(f[:, 2]) <= 1.0)
         zeros += np.sum(np.all(f == 0, axis=1))
     assert 0.1 < zeros / (500 * 64) < 0.3  # about 20 % of the segments are all-zero
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver's reference arm) runs without a GPU and prints the contract's JSON line."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "steps/s" and line["value"] > 0
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 2
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["e2e"]["value"] == line["value"]
