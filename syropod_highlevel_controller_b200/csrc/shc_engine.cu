@@ -211,7 +211,7 @@ struct shc_engine {
   float* gather_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool gather_opened[8] = {false, false, false, false, false, false, false, false};
   int* gather_token = nullptr;
-  cudaEvent_t ev_kernel[kGatherBuffers] = {}, ev_landed[kGatherBuffers] = {};
+  cudaEvent_t ev_kernel[kGatherBuffers] = {};  // "cycle's kernel done", for the side-stream flag kernels
   long long gather_cycle = 0, gather_waited = -1;  // cycles issued; newest cycle whose landed signal this stream waited for
   long long gather_signal_hist[4] = {-1, -1, -1, -1};  // the last cycles for which a landed signal was issued (same on every rank)
   unsigned gather_signal_pos = 0;
@@ -785,7 +785,6 @@ void shc_destroy(shc_engine* e) {
   cudaFree(e->gather_token);
   for (int b = 0; b < kGatherBuffers; ++b) {
     if (e->ev_kernel[b]) cudaEventDestroy(e->ev_kernel[b]);
-    if (e->ev_landed[b]) cudaEventDestroy(e->ev_landed[b]);
   }
   for (auto ev : e->ev_chunk)
     if (ev) cudaEventDestroy(ev);
@@ -1099,7 +1098,6 @@ int shc_gather_alloc(shc_engine* e, void* handle64_out, float** buffer_out) {
     CUDA_TRY(cudaMemset(e->gather_token, 0, 4));
     for (int b = 0; b < kGatherBuffers; ++b) {
       CUDA_TRY(cudaEventCreateWithFlags(&e->ev_kernel[b], cudaEventDisableTiming));
-      CUDA_TRY(cudaEventCreateWithFlags(&e->ev_landed[b], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaDeviceSynchronize());
   }
