@@ -26,11 +26,29 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def variant_lib(name: str, cxxflags: str):
+    """A second build of the same oracle sources with other compiler flags (oracle/_build/libshc_oracle_<name>.so), e.g.
+    -ffp-contract=fast: used by tests/test_oracle_chatter.py to show how far two correct double-precision builds of
+    the reference arithmetic drift apart inside the stand-still limit cycle."""
+    out = os.path.join(_HERE, "_build", f"libshc_oracle_{name}.so")
+    srcs = [os.path.join(_HERE, f) for f in ("shc_oracle_model.cpp", "shc_oracle_walk.cpp", "shc_oracle_pose.cpp", "shc_oracle_capi.cpp")]
+    deps = srcs + [os.path.join(_HERE, f) for f in ("oracle_math.hpp", "shc_oracle.hpp")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++"] + cxxflags.split() + ["-std=c++17", "-fPIC", "-pthread", "-shared", "-o", out] + srcs)
+    return _bind(C.CDLL(out))
+
+
 def lib():
     global _lib
     if _lib is None:
         build()
-        L = C.CDLL(_LIB_PATH)
+        _lib = _bind(C.CDLL(_LIB_PATH))
+    return _lib
+
+
+def _bind(L):
+    if True:
         dp = C.POINTER(C.c_double)
         L.shc_oracle_batch_create.restype = C.c_void_p
         L.shc_oracle_batch_create.argtypes = [C.POINTER(ShcConfig), C.c_int]
@@ -44,6 +62,8 @@ def lib():
         L.shc_oracle_batch_get_joints.argtypes = [C.c_void_p, dp]
         L.shc_oracle_batch_get_state.argtypes = [C.c_void_p, C.POINTER(ShcRobotState)]
         L.shc_oracle_batch_set_state.argtypes = [C.c_void_p, C.POINTER(ShcRobotState)]
+        L.shc_oracle_batch_set_pose_reset_mode.argtypes = [C.c_void_p, C.c_int]
+        L.shc_oracle_batch_set_joint_efforts.argtypes = [C.c_void_p, dp]
         L.shc_oracle_smooth_step.restype = C.c_double
         L.shc_oracle_smooth_step.argtypes = [C.c_double]
         L.shc_oracle_round_to_int.argtypes = [C.c_double]
@@ -59,8 +79,7 @@ def lib():
         L.shc_oracle_solve_ik.argtypes = [C.POINTER(ShcConfig), C.c_int, dp, dp, dp, dp]
         L.shc_oracle_step_cycle.argtypes = [C.POINTER(ShcConfig), C.POINTER(ShcStartup)]
         L.shc_oracle_admittance.argtypes = [C.POINTER(ShcConfig), dp, dp, dp]
-        _lib = L
-    return _lib
+    return L
 
 
 def _dp(a):
@@ -74,15 +93,16 @@ def _arr(a):
 class OracleBatch:
     """N independent copies of the reference controller, started up once and cloned."""
 
-    def __init__(self, cfg: ShcConfig, n_robots: int = 1):
+    def __init__(self, cfg: ShcConfig, n_robots: int = 1, library=None):
         self.cfg = cfg
         self.n = n_robots
         self.L, self.D = cfg.leg_count, cfg.joint_count
-        self._h = lib().shc_oracle_batch_create(C.byref(cfg), n_robots)
+        self._lib = library if library is not None else lib()
+        self._h = self._lib.shc_oracle_batch_create(C.byref(cfg), n_robots)
 
     def close(self):
         if self._h:
-            lib().shc_oracle_batch_destroy(self._h)
+            self._lib.shc_oracle_batch_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -93,34 +113,44 @@ class OracleBatch:
 
     @property
     def startup_loops(self) -> int:
-        return lib().shc_oracle_startup_loops(self._h)
+        return self._lib.shc_oracle_startup_loops(self._h)
 
     def startup(self) -> ShcStartup:
         s = ShcStartup()
-        lib().shc_oracle_get_startup(self._h, C.byref(s))
+        self._lib.shc_oracle_get_startup(self._h, C.byref(s))
         return s
 
     def step(self, cmd, imu=None, tip_force=None, manual=None, threads: int = 1):
         cmd, imu, tip_force, manual = _arr(cmd), _arr(imu), _arr(tip_force), _arr(manual)
         assert cmd.shape == (self.n, 3)
-        lib().shc_oracle_batch_step(self._h, _dp(cmd), _dp(imu), _dp(tip_force), _dp(manual), threads)
+        self._lib.shc_oracle_batch_step(self._h, _dp(cmd), _dp(imu), _dp(tip_force), _dp(manual), threads)
 
     def run(self, cmd, cycles: int, threads: int = 1) -> float:
         cmd = _arr(cmd)
-        return lib().shc_oracle_batch_run(self._h, _dp(cmd), cycles, threads)
+        return self._lib.shc_oracle_batch_run(self._h, _dp(cmd), cycles, threads)
+
+    def set_pose_reset_mode(self, mode: int):
+        """poser_->setPoseResetMode (state_controller.cpp:1199): 0 none, 1 Z+yaw, 2 X+Y, 3 pitch+roll, 4 all, 5 immediate."""
+        self._lib.shc_oracle_batch_set_pose_reset_mode(self._h, int(mode))
+
+    def set_joint_efforts(self, efforts):
+        """Measured joint efforts [n, L, D] (jointStatesCallback, state_controller.cpp:1565) for calculateTipForce."""
+        e = _arr(efforts)
+        assert e is None or e.shape == (self.n, self.L, self.D)
+        self._lib.shc_oracle_batch_set_joint_efforts(self._h, _dp(e))
 
     def joints(self) -> np.ndarray:
         out = np.empty((self.n, self.L, self.D), dtype=np.float64)
-        lib().shc_oracle_batch_get_joints(self._h, _dp(out))
+        self._lib.shc_oracle_batch_get_joints(self._h, _dp(out))
         return out
 
     def get_state(self):
         arr = (ShcRobotState * self.n)()
-        lib().shc_oracle_batch_get_state(self._h, arr)
+        self._lib.shc_oracle_batch_get_state(self._h, arr)
         return arr
 
     def set_state(self, arr):
-        lib().shc_oracle_batch_set_state(self._h, arr)
+        self._lib.shc_oracle_batch_set_state(self._h, arr)
 
 
 def fk(cfg, leg, q):

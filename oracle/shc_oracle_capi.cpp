@@ -312,6 +312,22 @@ void shc_oracle_batch_set_state(void* h, const shc_robot_state* in) {
   for (size_t i = 0; i < b->robots.size(); ++i) importState(*b->robots[i], in + i);
 }
 
+// poser_->setPoseResetMode (state_controller.cpp:1199) for every robot of the batch.
+void shc_oracle_batch_set_pose_reset_mode(void* h, int mode) {
+  Batch* b = static_cast<Batch*>(h);
+  for (Robot* r : b->robots) r->pose_reset_mode_ = PoseResetMode(mode);
+}
+
+// jointStatesCallback (state_controller.cpp:1565-1590): measured joint efforts [n][L][D] (NULL = zero), read by
+// Leg::calculateTipForce (model.cpp:667) when use_joint_effort is set.
+void shc_oracle_batch_set_joint_efforts(void* h, const double* eff) {
+  Batch* b = static_cast<Batch*>(h);
+  const int L = b->cfg.leg_count, D = b->cfg.joint_count;
+  for (size_t i = 0; i < b->robots.size(); ++i)
+    for (int l = 0; l < L; ++l)
+      for (int j = 0; j < D; ++j) b->robots[i]->legs[l].joints[j + 1].current_effort_ = eff ? eff[(i * L + l) * D + j] : 0.0;
+}
+
 int shc_oracle_state_record_size(void) { return int(sizeof(shc_robot_state)); }
 int shc_oracle_config_size(void) { return int(sizeof(shc_config)); }
 int shc_oracle_startup_size(void) { return int(sizeof(shc_startup)); }

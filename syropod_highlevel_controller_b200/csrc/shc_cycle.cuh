@@ -18,6 +18,7 @@
 #include "shc_consts.h"
 #include "shc_layout.h"
 #include "shc_math.cuh"
+#include <cstring>
 
 namespace shc {
 
@@ -66,6 +67,18 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // a leg's every-cycle planes (one cp.async.bulk per plane set) two legs ahead of the arithmetic; completion is
 // signalled on a warp-private mbarrier by byte count.  The dependent chain of a robot therefore never waits on HBM
 // inside the leg loop: its loads are shared-memory reads of data that landed while the previous legs were computed.
+//
+// -DSHC_EMU (tests/cpp/shc_emu.cpp only, compiled by plain g++ — never the product library): Cycle::run is compiled for the
+// host, where the staging primitives below degenerate to a memcpy per lane and the lanes of a tile run one after the other.  That lets the
+// CPU test-suite drive the very source the kernel is built from against the oracle; it is not a fallback of the engine.
+#if defined(SHC_EMU)
+#define SHC_CYCLE_FN __host__ __device__
+#else
+#define SHC_CYCLE_FN __device__
+#endif
+#if defined(__CUDACC__)
+#define SHC_LANE0(lane) ((lane) == 0)
+#define SHC_SYNCWARP() __syncwarp()
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -106,6 +119,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         : "memory");
   } while (!done);
 }
+#else
+// host pass (SHC_EMU): every lane stages its own copy synchronously
+#define SHC_LANE0(lane) (true)
+#define SHC_SYNCWARP() do { } while (0)
+inline void mbar_init(uint64_t*, unsigned) {}
+inline void fence_mbar_init() {}
+inline void fence_proxy_async_smem() {}
+inline void mbar_expect_tx(uint64_t*, unsigned) {}
+inline void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t*) { std::memcpy(dst, src, bytes); }
+inline void mbar_wait(uint64_t*, unsigned) {}
+#endif
 
 template <class S> struct Planes {
   S* s;
@@ -319,25 +343,25 @@ template <class P, int D, bool FULL> struct Cycle {
   using K = typename P::K;
   using LS = LegS<D>;
 
-  static __device__ __forceinline__ V3<K> ld3K(const S* sp, int plane) {
+  static SHC_CYCLE_FN __forceinline__ V3<K> ld3K(const S* sp, int plane) {
     return {K(sp[(plane) * 32]), K(sp[(plane + 1) * 32]), K(sp[(plane + 2) * 32])};
   }
-  static __device__ __forceinline__ V3<T> ld3T(const S* sp, int plane) {
+  static SHC_CYCLE_FN __forceinline__ V3<T> ld3T(const S* sp, int plane) {
     return {T(sp[(plane) * 32]), T(sp[(plane + 1) * 32]), T(sp[(plane + 2) * 32])};
   }
-  template <class R> static __device__ __forceinline__ void st3(S* sp, int plane, V3<R> v) {
+  template <class R> static SHC_CYCLE_FN __forceinline__ void st3(S* sp, int plane, V3<R> v) {
     sp[(plane) * 32] = S(v.x);
     sp[(plane + 1) * 32] = S(v.y);
     sp[(plane + 2) * 32] = S(v.z);
   }
-  static __device__ __forceinline__ PoseT<K> ldPose(const S* sp, int plane) {
+  static SHC_CYCLE_FN __forceinline__ PoseT<K> ldPose(const S* sp, int plane) {
     PoseT<K> p;
     p.p = ld3K(sp, plane);
     p.q = {K(sp[(plane + 3) * 32]), K(sp[(plane + 4) * 32]), K(sp[(plane + 5) * 32]),
            K(sp[(plane + 6) * 32])};
     return p;
   }
-  static __device__ __forceinline__ void stPose(S* sp, int plane, PoseT<K> p) {
+  static SHC_CYCLE_FN __forceinline__ void stPose(S* sp, int plane, PoseT<K> p) {
     st3(sp, plane, p.p);
     sp[(plane + 3) * 32] = S(p.q.w);
     sp[(plane + 4) * 32] = S(p.q.x);
@@ -347,7 +371,7 @@ template <class P, int D, bool FULL> struct Cycle {
 
   // PoseController::updateManualPose (pose_controller.cpp:863-1003); default_pose_ is the identity (no manually
   // manipulated legs in the batched engine, so calculateDefaultPose never moves it).
-  static __device__ __forceinline__ PoseT<K> manual_pose_update(const RealConsts<K>& ck, PoseT<K> man, const float* in6,
+  static SHC_CYCLE_FN __forceinline__ PoseT<K> manual_pose_update(const RealConsts<K>& ck, PoseT<K> man, const float* in6,
                                                                 int reset_mode) {
     if (reset_mode == 5) return pose_identity<K>();  // IMMEDIATE_ALL_RESET
     V3<K> cur_rot = quat_to_euler(man.q, true);
@@ -397,7 +421,7 @@ template <class P, int D, bool FULL> struct Cycle {
 
   // Model::estimateGravity (model.cpp:156) from the raw IMU orientation (all-zero quaternion when no IMU data: the
   // rotation matrix of the zero quaternion is the identity).
-  static __device__ __forceinline__ V3<K> estimate_gravity(Q4<K> imu_raw) {
+  static SHC_CYCLE_FN __forceinline__ V3<K> estimate_gravity(Q4<K> imu_raw) {
     V3<K> e = quat_to_euler(imu_raw, false);
     K s, c;
     sincos_(-e.y, &s, &c);  // rotate (0,0,g) about Y by -pitch
@@ -428,7 +452,7 @@ template <class P, int D, bool FULL> struct Cycle {
   // commands are staged in its joint tile and written out by the whole warp as coalesced 128-byte lines by the caller.
   // Lanes past n_robots run on the (initialised) padding robots of the last tile so that the warp-collective staging
   // stays convergent; they read the inputs of the last real robot and their outputs are dropped by the caller.
-  static __device__ void run(const Consts& c, Planes<S> pl, int tile_idx, int lane, const StepIO& io, unsigned char* __restrict__ wsm) {
+  static SHC_CYCLE_FN void run(const Consts& c, Planes<S> pl, int tile_idx, int lane, const StepIO& io, unsigned char* __restrict__ wsm) {
     const IntConsts& ci = c.i;
     const RealConsts<T>& ct = ConstSel<T>::get(c);
     const RealConsts<K>& ck = ConstSel<K>::get(c);
@@ -470,12 +494,12 @@ template <class P, int D, bool FULL> struct Cycle {
       bulk_g2s(slot + sS_bytes, tileD + (ci.offD_leg + l * ci.strideD_leg) * 32, LD_COUNT * 32 * 8, bar);
       bulk_g2s(slot + sS_bytes + LD_COUNT * 32 * 8, tileI + (ci.offI_leg + l * ci.strideI_leg) * 32, LI_COUNT * 32 * 4, bar);
     };
-    if (lane == 0) {
+    if (SHC_LANE0(lane)) {
       mbar_init(bar_of(0), 1);
       mbar_init(bar_of(1), 1);
       fence_mbar_init();
     }
-    __syncwarp();
+    SHC_SYNCWARP();
 
     // ---- every unconditional robot-level load, issued back to back (one exposed HBM latency for the whole stage) ------
     int rbits = ip[(RI_BITS) * 32];
@@ -523,7 +547,7 @@ template <class P, int D, bool FULL> struct Cycle {
     // The first two legs' transfers start once the robot-level loads are back (rbits is the first of them; the
     // comparison only creates the dependency): the opening HBM burst of a wave of warps is then the 8 KB the first stage
     // needs, and the legs' planes stream in behind it while that stage computes (-3 % per launch, measured).
-    if (lane == 0 && rbits != 0x7fffffff) {
+    if (SHC_LANE0(lane) && rbits != 0x7fffffff) {
       issue_leg(0);
       if (L > 1) issue_leg(1);
     }
@@ -1056,12 +1080,12 @@ template <class P, int D, bool FULL> struct Cycle {
           else if (phase < ci.stance_end || phase >= ci.stance_start) step_state = STEP_STANCE;
         }
         if (step_state == STEP_SWING) {
-          swing_num = min(max(phase - ci.swing_start + 1, 0), ci.swing_period);
+          swing_num = min_(max_(phase - ci.swing_start + 1, 0), ci.swing_period);
           stance_num = -1;
         } else if (step_state == STEP_STANCE) {
           int since = phase - ci.stance_start;
           since += since < 0 ? ci.period + 1 : 1;
-          stance_num = min(max(since, 0), ci.stance_period);
+          stance_num = min_(max_(since, 0), ci.stance_period);
           swing_num = -1;
         } else if (step_state == STEP_FORCE_STOP) {
           stance_num = 0;
@@ -1069,8 +1093,8 @@ template <class P, int D, bool FULL> struct Cycle {
         }
       }
       // every lane has read what it needs from this slot: hand it back to the TMA unit for leg l + 2
-      __syncwarp();
-      if (lane == 0 && l + 2 < L) {
+      SHC_SYNCWARP();
+      if (SHC_LANE0(lane) && l + 2 < L) {
         fence_proxy_async_smem();
         issue_leg(l + 2);
       }

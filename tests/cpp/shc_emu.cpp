@@ -1,0 +1,157 @@
+// shc_emu.cpp — TEST INFRASTRUCTURE ONLY: runs the control-cycle source the CUDA kernel is built from (csrc/shc_cycle.cuh,
+// Cycle<P, D, FULL>::run) on the host, lane after lane, over host-resident planes.  Built by tests/emu.py with plain g++
+// into tests/cpp/_build/libshc_emu.so and loaded only by the CPU test-suite: it lets `pytest -m "not gpu"` check every
+// branch of the cycle code against the oracle where no GPU exists.  It is not part of libshc_b200.so, the product has no
+// CPU path, and nothing outside tests/ may load it.  Device-only pieces (TMA staging ring, mbarriers, the bounded sincos /
+// rsqrt sequences) are replaced by their host equivalents in the headers themselves (#if defined(__CUDA_ARCH__)), so the
+// emulator agrees with the device to rounding (1e-11 on one cycle), not bit for bit.
+#define __host__
+#define __device__
+#define __forceinline__ inline __attribute__((always_inline))
+#define SHC_EMU 1
+#include <cstdint>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "../../syropod_highlevel_controller_b200/csrc/shc_pack.cuh"
+
+using namespace shc;
+using PrecMixed = Prec<float, float, double>;
+
+struct shc_emu {
+  shc_config cfg;
+  shc_startup su;
+  Consts c;
+  int precision = 0, n = 0, n_pad = 0;
+  int options = 0, pose_reset_mode = 0;
+  std::vector<double> s64;
+  std::vector<float> s32;
+  std::vector<double> d;
+  std::vector<int> i;
+  std::vector<int> flags;
+  std::vector<float> efforts;
+  bool have_efforts = false;
+};
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& m) { g_err = m; return code; }
+
+static void to_host(const shc_emu* e, HostPlanes& h) {
+  if (e->precision == SHC_PRECISION_F64) h.s = e->s64;
+  else h.s.assign(e->s32.begin(), e->s32.end());
+  h.d = e->d;
+  h.i = e->i;
+}
+static void from_host(shc_emu* e, const HostPlanes& h) {
+  if (e->precision == SHC_PRECISION_F64) e->s64 = h.s;
+  else { e->s32.resize(h.s.size()); for (size_t k = 0; k < h.s.size(); ++k) e->s32[k] = (float)h.s[k]; }
+  e->d = h.d;
+  e->i = h.i;
+}
+
+template <class P, int D, bool FULL>
+static void step_all(shc_emu* e, const StepIO& io_in) {
+  using CY = Cycle<P, D, FULL>;
+  using S = typename P::S;
+  const IntConsts& ci = e->c.i;
+  Planes<S> pl;
+  if constexpr (sizeof(S) == 8) pl.s = (S*)e->s64.data(); else pl.s = (S*)e->s32.data();
+  pl.d = e->d.data();
+  pl.i = e->i.data();
+  const int front = FULL ? ci.frontS_leg : 0;
+  std::vector<unsigned char> raw(ci.smem_per_warp + 256);
+  unsigned char* wsm = (unsigned char*)(((uintptr_t)raw.data() + 127) / 128 * 128);
+  const int LD = ci.L * D;
+  const int tiles = (e->n + 31) / 32;
+  for (int tile = 0; tile < tiles; ++tile) {
+    for (int lane = 0; lane < 32; ++lane) CY::run(e->c, pl, tile, lane, io_in, wsm);
+    const float* src = reinterpret_cast<const float*>(wsm + 2 * CY::slot_bytes(front));
+    const int robots = std::min(32, e->n - tile * 32);
+    for (int k = 0; k < robots * LD; ++k) io_in.joints_out[(size_t)tile * 32 * LD + k] = src[k];
+  }
+}
+
+extern "C" {
+const char* shc_emu_last_error(void) { return g_err.c_str(); }
+
+int shc_emu_create(const shc_config* cfg, const shc_startup* startup, int n_robots, int precision, shc_emu** out) {
+  if (!cfg || !out || n_robots < 1) return fail(SHC_E_INVALID, "bad arguments");
+  std::string err;
+  bool unsupported = false;
+  if (!check_supported(*cfg, err, unsupported)) return fail(unsupported ? SHC_E_UNSUPPORTED : SHC_E_INVALID, err);
+  shc_emu* e = new shc_emu();
+  core_init(e, *cfg, startup, n_robots, precision);
+  const bool full = engine_full(e->cfg);
+  const int front = full ? e->c.i.frontS_leg : 0;
+  dispatch_D_raw(cfg->joint_count, [&](auto dtag) -> int {
+    constexpr int D = decltype(dtag)::value;
+    e->c.i.smem_per_warp = precision == SHC_PRECISION_F64 ? Cycle<PrecF64, D, false>::smem_per_warp(front, cfg->leg_count)
+                                                          : Cycle<PrecMixed, D, false>::smem_per_warp(front, cfg->leg_count);
+    return 0;
+  });
+  HostPlanes h;
+  initial_planes(e, h);
+  from_host(e, h);
+  e->flags.assign(e->n_pad, 0);
+  *out = e;
+  return SHC_OK;
+}
+void shc_emu_destroy(shc_emu* e) { delete e; }
+int shc_emu_get_startup(const shc_emu* e, shc_startup* out) { *out = e->su; return SHC_OK; }
+int shc_emu_set_options(shc_emu* e, int o) { e->options = o; return SHC_OK; }
+int shc_emu_set_pose_reset_mode(shc_emu* e, int m) {
+  if (m < 0 || m > 5) return fail(SHC_E_INVALID, "bad pose reset mode");
+  e->pose_reset_mode = m;
+  return SHC_OK;
+}
+int shc_emu_set_joint_efforts(shc_emu* e, const float* eff) {
+  e->have_efforts = eff != nullptr;
+  if (eff) e->efforts.assign(eff, eff + (size_t)e->n * e->cfg.leg_count * e->cfg.joint_count);
+  return SHC_OK;
+}
+int shc_emu_get_status_flags(shc_emu* e, int* out) {
+  if (!(e->options & SHC_OPT_STATUS_FLAGS)) return fail(SHC_E_INVALID, "status flags are not enabled");
+  for (int r = 0; r < e->n; ++r) out[r] = e->flags[r];
+  return SHC_OK;
+}
+int shc_emu_get_state(shc_emu* e, shc_robot_state* out, size_t n) {
+  if (n != (size_t)e->n) return fail(SHC_E_INVALID, "need n_robots records");
+  HostPlanes h;
+  to_host(e, h);
+  return dispatch_D_raw(e->cfg.joint_count, [&](auto dtag) -> int { unpack<decltype(dtag)::value>(e, h, out, n); return SHC_OK; });
+}
+int shc_emu_set_state(shc_emu* e, const shc_robot_state* in, size_t n) {
+  if (n != (size_t)e->n) return fail(SHC_E_INVALID, "need n_robots records");
+  const IntConsts& ci = e->c.i;
+  HostPlanes h;
+  h.s.assign((size_t)ci.nS * ci.n_pad, 0.0);
+  h.d.assign((size_t)ci.nD * ci.n_pad, 0.0);
+  h.i.assign((size_t)ci.nI * ci.n_pad, 0);
+  pack(e, in, n, h, ci.n_pad);
+  from_host(e, h);
+  return SHC_OK;
+}
+int shc_emu_step(shc_emu* e, const float* cmd, const float* imu, const float* tip_force, const float* manual, float* joints_out) {
+  if (!e || !cmd || !joints_out) return fail(SHC_E_INVALID, "cmd and joints_out are required");
+  StepIO io;
+  std::memset(&io, 0, sizeof(io));
+  io.cmd = cmd; io.imu = imu; io.tip_force = tip_force; io.manual = manual;
+  io.efforts = e->have_efforts ? e->efforts.data() : nullptr;
+  io.joints_out = joints_out;
+  io.tile_begin = 0;
+  io.tile_end = (e->n + 31) / 32;
+  io.flags_out = (e->options & SHC_OPT_STATUS_FLAGS) ? e->flags.data() : nullptr;
+  io.pose_reset_mode = e->pose_reset_mode;
+  const bool full = engine_full(e->cfg);
+  return dispatch_D_raw(e->cfg.joint_count, [&](auto dtag) -> int {
+    constexpr int D = decltype(dtag)::value;
+    if (e->precision == SHC_PRECISION_F64) {
+      if (full) step_all<PrecF64, D, true>(e, io); else step_all<PrecF64, D, false>(e, io);
+    } else {
+      if (full) step_all<PrecMixed, D, true>(e, io); else step_all<PrecMixed, D, false>(e, io);
+    }
+    return SHC_OK;
+  });
+}
+}

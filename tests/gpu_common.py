@@ -88,26 +88,26 @@ class JointErrors:
     def exceed_fraction(self):
         return self.exceed / max(self.count, 1)
 
-    def check(self, max_fraction):
+    def check(self, max_fraction, label=""):
+        # printed so that the tail of a GPU test run records what was observed against the cap
+        print(f"[joint-errors] {label}: worst {self.worst:.3e} rad, {self.exceed}/{self.count} samples beyond 1e-6 "
+              f"(fraction {self.exceed_fraction:.2e}, cap {max_fraction:.1e})")
         assert self.worst <= self.CHATTER_BOUND, self.worst
         assert self.exceed_fraction <= max_fraction, (self.exceed_fraction, self.exceed, self.count, self.worst)
 
 
 def run_both(eng, ob, cycles, cmd_stream, imu_stream=None, force_stream=None, dt=0.02, threads=8, per_cycle=None):
-    """Steps the CUDA engine and the oracle on identical inputs; returns JointErrors over all cycles/joints (float32
-    output vs oracle double).  per_cycle(c, joints_gpu, oracle) is called after every cycle when given."""
-    import torch
-
+    """Steps the engine under test (a tests/backends.py stepper: numpy in, float64 joints out) and the oracle on identical
+    inputs; returns JointErrors over all cycles/joints (float32 output vs oracle double).  per_cycle(c, joints, oracle) is
+    called after every cycle when given."""
     errs = JointErrors()
     for c in range(cycles):
         cmd = cmd_stream.next()
         imu = imu_stream.next(dt) if imu_stream is not None else None
         force = force_stream.next() if force_stream is not None else None
-        j = eng.step(torch.from_numpy(cmd).cuda(), None if imu is None else torch.from_numpy(imu).cuda(),
-                     None if force is None else torch.from_numpy(force).cuda())
+        jg = eng.step(cmd, imu, force)
         ob.step(cmd.astype(np.float64), None if imu is None else imu.astype(np.float64),
                 None if force is None else force.astype(np.float64), threads=threads)
-        jg = j.cpu().numpy().astype(np.float64)
         errs.add(np.abs(jg - ob.joints()))
         if per_cycle is not None:
             per_cycle(c, jg, ob)
