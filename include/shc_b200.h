@@ -128,23 +128,36 @@ int shc_nccl_init(shc_engine* e, const void* uid128, int rank, int world_size);
 int shc_allgather_joints(shc_engine* e, const float* local, float* full, void* stream);
 int shc_rollout_allgather(shc_engine* e, int k_cycles, const float* cmd_seq, float* local2, float* full2, void* stream);
 
-/* Fused all-gather over peer memory (one node, <= 8 ranks, after shc_nccl_init): the control-cycle kernel stores every
- * finished tile of joint commands into ALL ranks' gather buffers (TMA bulk stores to peer-mapped device memory, CUDA
- * IPC), so the exchange travels over NVLink / NVSwitch while the rest of the batch is still being computed.
- *   shc_gather_alloc         allocates this rank's buffer (shc_gather_buffers() x world x [n][L][D] floats + flags),
- *                            returns its 64-byte IPC handle and (optionally) its device address
- *   shc_gather_open_peer     maps rank `peer_rank`'s buffer from its handle (the caller exchanges the handles)
- *   shc_rollout_gather_fused k cycles (every rank must make the same sequence of calls); cycle t lands in buffer
- *                            t % shc_gather_buffers() of every rank: element [buffer][rank r][robot][leg][joint].
- *                            Inside a call, sparse "landed" flags (one-warp kernel on a side stream, awaited with
- *                            cuStreamWaitValue32 on values that are already up) protect the reuse of a buffer 16 cycles
- *                            later; the call ends with the last cycle's flag and a 1-element ncclAllReduce on `stream`:
- *                            work ordered on `stream` after the call sees every rank's shard of every cycle of the call,
- *                            and a buffer is not rewritten before every rank has passed the consumers it ordered before
- *                            its next call.  *last_buffer_out = buffer of the last cycle. */
+/* Fused all-gather over peer memory (one node, <= 8 ranks; SURVEY.md 8(e) "fused variant"): the control-cycle kernel
+ * stores every finished tile of joint commands into ALL ranks' gather buffers, so the exchange travels over NVLink /
+ * NVSwitch while the rest of the batch is still being computed.  Cycle t lands in buffer t % shc_gather_buffers() of
+ * every rank: element [buffer][source rank][robot][leg][joint], followed (256-byte aligned) by one landed counter per
+ * source rank.  Two ways to map the buffers:
+ *   shc_gather_attach        the caller owns one symmetric buffer per rank (shc_gather_bytes() each, e.g. torch
+ *                            symmetric memory) and passes every rank's mapping of them and — when the fabric has NVLS —
+ *                            their NVSwitch multicast mapping: the kernel then issues ONE multimem.st per 16 bytes and the
+ *                            switch replicates it (egress per rank = its shard).  multicast_buffer NULL: unicast TMA bulk
+ *                            stores, one per peer.  The caller runs a barrier between attach and the first cycle.
+ *   shc_gather_alloc /       the engines cudaMalloc the buffers and exchange CUDA-IPC handles (after shc_nccl_init, which
+ *   shc_gather_open_peer     fixes rank and world size); unicast TMA bulk stores.
+ * Cycles (every rank makes the same sequence of calls; nothing on the per-cycle path is a collective):
+ *   shc_gather_step          one control cycle (inputs as shc_step) into the next buffer.  Behind the kernel a one-warp
+ *                            kernel on a high-priority side stream waits for the posted NVLink writes to drain and bumps
+ *                            this rank's landed counter on every rank (multimem.red / st.release.sys), concurrently with
+ *                            the next cycle; every 4th cycle a one-warp ld.acquire.sys spin kernel checks that no rank
+ *                            is more than a buffer-reuse window behind (it normally passes at once).
+ *   shc_gather_sync          `stream` continues once every rank's shard of every cycle issued so far has landed in this
+ *                            rank's buffer; *last_buffer_out = buffer of the last cycle.
+ *   shc_rollout_gather_fused k x shc_gather_step + shc_gather_sync.
+ *   shc_gather_status        SHC_E_CUDA once a device-side wait gave up (a peer stopped signalling for seconds). */
+size_t shc_gather_bytes(const shc_engine* e, int world_size);
+int shc_gather_attach(shc_engine* e, int rank, int world_size, void* const* peer_buffers, void* multicast_buffer);
 int shc_gather_alloc(shc_engine* e, void* handle64_out, float** buffer_out);
 int shc_gather_open_peer(shc_engine* e, int peer_rank, const void* handle64);
 int shc_gather_buffers(void);
+int shc_gather_step(shc_engine* e, const float* cmd, const float* imu, const float* tip_force, const float* manual, void* stream);
+int shc_gather_sync(shc_engine* e, int* last_buffer_out, void* stream);
+int shc_gather_status(shc_engine* e);
 int shc_rollout_gather_fused(shc_engine* e, int k_cycles, const float* cmd_seq, int* last_buffer_out, void* stream);
 
 /* The engine's own CUDA stream (cudaStream_t) and a blocking wait on it. */

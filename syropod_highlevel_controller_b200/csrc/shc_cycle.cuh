@@ -40,6 +40,7 @@ struct StepIO {
   // gather[p][gather_offset + ...], p = 0 .. n_gather-1 — peer-mapped device pointers (CUDA IPC), i.e. plain stores that
   // travel over NVLink / NVSwitch while the other tiles are still being computed.  The own rank's buffer is one of them.
   float* gather[8];
+  float* gather_mc;         // multicast mapping of the gather buffers (NVLS) or null: one store reaches every rank
   long long gather_offset;  // elements: buffer index * world * N * L * D + rank * N * L * D
   int n_gather;
   int tile_begin, tile_end;  // tiles (32 robots each) of this launch: a step may be issued as several tile ranges so that
@@ -108,6 +109,22 @@ __device__ __forceinline__ void bulk_commit_and_wait_read() {
 }
 __device__ __forceinline__ void store_release_sys(int* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int load_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// NVSwitch multicast (NVLS): a store to the multicast mapping of a symmetric buffer lands in every rank's copy.
+__device__ __forceinline__ void multimem_st_v4(float* mc, float4 v) {
+  asm volatile("multimem.st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void multimem_st_f32(float* mc, float v) {
+  asm volatile("multimem.st.global.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_red_release_add(int* mc, int v) {
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+  asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   unsigned done;
@@ -440,11 +457,14 @@ template <class P, int D, bool FULL> struct Cycle {
   // -DSHC_ALIAS_BARRIERS (tuning variant, off: measured 94.1 us against 94.5 us per launch, i.e. no gain): the two mbarriers
   // live in the last 16 bytes of the joint tile instead — lane 31's entries of the last two legs, which are only written
   // after the last wait on the respective barrier — so a hexapod f64 warp needs 13568 B and a 16th one-warp block fits.
+  // bytes of the per-warp scratch planes behind the barriers: the body velocity (3 x T) of the tile's robots, written by
+  // the robot-level stage and read by every leg (keeps six registers out of the leg loop without an L2 round trip per leg)
+  static __host__ __device__ __forceinline__ int scratch_bytes() { return 3 * 32 * (int)sizeof(T); }
   static __host__ __device__ __forceinline__ int smem_per_warp(int frontS, int L) {
 #ifdef SHC_ALIAS_BARRIERS
-    return (2 * slot_bytes(frontS) + 32 * L * D * 4 + 127) / 128 * 128;
+    return (2 * slot_bytes(frontS) + 32 * L * D * 4 + scratch_bytes() + 127) / 128 * 128;
 #else
-    return (2 * slot_bytes(frontS) + 32 * L * D * 4 + 16 + 127) / 128 * 128;
+    return (2 * slot_bytes(frontS) + 32 * L * D * 4 + 16 + scratch_bytes() + 127) / 128 * 128;
 #endif
   }
 
@@ -483,6 +503,11 @@ template <class P, int D, bool FULL> struct Cycle {
     uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + 2 * s_bytes + 32 * L * D * 4);
     auto bar_of = [&](int s) { return bars + s; };
 #endif
+#ifdef SHC_ALIAS_BARRIERS
+    T* __restrict__ scratch = reinterpret_cast<T*>(wsm + 2 * s_bytes + 32 * L * D * 4) + lane;
+#else
+    T* __restrict__ scratch = reinterpret_cast<T*>(wsm + 2 * s_bytes + 32 * L * D * 4 + 16) + lane;
+#endif
     const S* tileS = pl.s + tile * (size_t)(ci.nS * 32);
     const double* tileD = pl.d + tile * (size_t)(ci.nD * 32);
     const int* tileI = pl.i + tile * (size_t)(ci.nI * 32);
@@ -516,11 +541,17 @@ template <class P, int D, bool FULL> struct Cycle {
       }
     }
     PoseT<K> owpp = ldPose(sp, RS_OWPP);
-    PoseT<K> man = pose_identity<K>();
-    if (ci.manual_posing) man = ldPose(sp, RS_MAN);
     T dvx = T(sp[(RS_VEL) * 32]), dvy = T(sp[(RS_VEL + 1) * 32]), dw = T(sp[(RS_ANGVEL) * 32]);
     const K walker_wp_z = K(sp[(RS_WPL + 2) * 32]);
     const V3<K> walker_wpn_k = ld3K(sp, RS_WPN);
+    // the manual pose is the identity on almost every robot (state bit): only the others pay for its seven planes
+    PoseT<K> man = pose_identity<K>();
+    bool man_identity = true;
+    if (ci.manual_posing && !((rbits >> RB_MANUAL_IDENTITY) & 1)) {
+      man = ldPose(sp, RS_MAN);
+      man_identity = man.p.x == K(0) && man.p.y == K(0) && man.p.z == K(0) && man.q.w == K(1) && man.q.x == K(0) &&
+                     man.q.y == K(0) && man.q.z == K(0);
+    }
 
     // ---- inputs: bodyVelocityInputCallback (state_controller.cpp:1127-1136) --------------------------------------
     double vin_x = (double)io.cmd[3 * (size_t)r + 0] * cd.body_velocity_scaler;
@@ -615,12 +646,12 @@ template <class P, int D, bool FULL> struct Cycle {
 
     PoseT<K> cur_pose = pose_add(pose_identity<K>(), wpp);
     if (ci.manual_posing) {
-      const bool man_identity = man.p.x == K(0) && man.p.y == K(0) && man.p.z == K(0) && man.q.w == K(1) &&
-                                man.q.x == K(0) && man.q.y == K(0) && man.q.z == K(0);
       if (!(man_identity && io.manual == nullptr && io.pose_reset_mode == 0)) {
         // (with an identity pose, no input and no reset the update returns the identity again, exactly)
         man = manual_pose_update(ck, man, io.manual ? io.manual + 6 * (size_t)r : nullptr, io.pose_reset_mode);
         stPose(sp, RS_MAN, man);
+        man_identity = man.p.x == K(0) && man.p.y == K(0) && man.p.z == K(0) && man.q.w == K(1) && man.q.x == K(0) &&
+                       man.q.y == K(0) && man.q.z == K(0);
         cur_pose = pose_add(cur_pose, man);
       }
     }
@@ -746,6 +777,10 @@ template <class P, int D, bool FULL> struct Cycle {
     // =================================================================================================================
     // 2. WalkController::updateWalk — robot-level part (walk_controller.cpp:440-564)
     // =================================================================================================================
+    // odometry_ideal_ (updated right after the body velocity below: it depends on nothing else): the loads fly while the
+    // limits and the velocity are worked out
+    const Q4<T> odom_q{T(sp[(RS_ODOMQ) * 32]), T(sp[(RS_ODOMQ + 1) * 32]), T(sp[(RS_ODOMQ + 2) * 32]), T(sp[(RS_ODOMQ + 3) * 32])};
+    const double odom_x = dp[(RD_ODOMP) * 32], odom_y = dp[(RD_ODOMP + 1) * 32], odom_z = dp[(RD_ODOMP + 2) * 32];
     double lim[4] = {2147483647.0, 2147483647.0, 2147483647.0, 2147483647.0};
 #pragma unroll
     for (int l = 0; l < kMaxLegs; ++l) {  // getLimit (:414): the four calls share the bearing of each leg
@@ -753,22 +788,20 @@ template <class P, int D, bool FULL> struct Cycle {
       const double tx = tips_x[l], ty = tips_y[l];
       double sx = vin_x + win * (-ty), sy = vin_y + win * tx;
       // bucket = mod(roundToInt(deg(atan2(sy, sx))), 360) / 45 (int / int floors to the 45-degree bucket, trap 1),
-      // decided without atan2: the rounding makes the bucket edges sit at 44.5, 89.5, 134.5, 179.5 degrees on the upper
-      // half plane and at -0.5, -45.5, -90.5, -135.5 on the lower one; theta >= phi <=> sin(theta - phi) >= 0.
-      int bucket;
-      if (sx == 0.0 && sy == 0.0) {
-        bucket = 0;
-      } else if (sy >= 0.0) {
-        bucket = 0;
+      // decided without atan2: the rounding puts the bucket edges at 44.5, 89.5, 134.5, 179.5 degrees on the upper half
+      // plane (closed below: theta >= edge) and, mirrored through the origin, at -135.5, -90.5, -45.5, -0.5 on the lower
+      // one (open: theta > edge).  theta >= phi <=> sin(theta - phi) >= 0, and a point of the lower half plane has passed
+      // the mirrored edge exactly when its own sine against the upper edge is negative: one set of four tests serves
+      // both halves, with no divergence between lanes.
+      int passed_hi = 0, passed_lo = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) bucket += (sy * cd.sec_cos[k] - sx * cd.sec_sin[k] >= 0.0) ? 1 : 0;
-      } else {
-        bucket = 4;
-        if (sy * cd.sec_cos[4] + sx * cd.sec_sin[4] > 0.0) bucket = 0;
-        else if (sy * cd.sec_cos[5] + sx * cd.sec_sin[5] > 0.0) bucket = 7;
-        else if (sy * cd.sec_cos[6] + sx * cd.sec_sin[6] > 0.0) bucket = 6;
-        else if (sy * cd.sec_cos[7] + sx * cd.sec_sin[7] > 0.0) bucket = 5;
+      for (int k = 0; k < 4; ++k) {
+        const double t = sy * cd.sec_cos[k] - sx * cd.sec_sin[k];
+        passed_hi += t >= 0.0 ? 1 : 0;
+        passed_lo += t < 0.0 ? 1 : 0;
       }
+      int bucket = sy >= 0.0 ? passed_hi : ((4 + passed_lo) & 7);
+      if (sx == 0.0 && sy == 0.0) bucket = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) lim[k] = fmin(lim[k], cd.limits[k][bucket]);
     }
@@ -826,6 +859,11 @@ template <class P, int D, bool FULL> struct Cycle {
     sp[(RS_VEL) * 32] = S(dvx);
     sp[(RS_VEL + 1) * 32] = S(dvy);
     sp[(RS_ANGVEL) * 32] = S(dw);
+    // the values the legs (updateStride) and the odometry read back: the stored ones
+    dvx = T(S(dvx)); dvy = T(S(dvy)); dw = T(S(dw));
+    scratch[0] = dvx;
+    scratch[32] = dvy;
+    scratch[64] = dw;
 
     bool starting_now = false;  // STOPPED -> STARTING returns before any tip update (trap 7)
     if (walk_state == WALK_STOPPED && has_cmd) {
@@ -842,6 +880,24 @@ template <class P, int D, bool FULL> struct Cycle {
       walk_state = WALK_STOPPED;
     }
 
+    // calculateOdometry (:783): odometry_ideal_ = odometry_ideal_.addPose(velocity * dt); it depends on the body velocity
+    // only, so it is done here, while its planes (loaded with the other robot-level planes) are still at hand
+    if (!starting_now) {
+      V3<T> dpos = qrot(odom_q, V3<T>{dvx * ct.dt, dvy * ct.dt, T(0)});
+      dp[(RD_ODOMP) * 32] = odom_x + (double)dpos.x;
+      dp[(RD_ODOMP + 1) * 32] = odom_y + (double)dpos.y;
+      dp[(RD_ODOMP + 2) * 32] = odom_z + (double)dpos.z;
+      Q4<T> nq = qmul(odom_q, q_axis_z(dw * ct.dt));
+      sp[(RS_ODOMQ) * 32] = S(nq.w);
+      sp[(RS_ODOMQ + 1) * 32] = S(nq.x);
+      sp[(RS_ODOMQ + 2) * 32] = S(nq.y);
+      sp[(RS_ODOMQ + 3) * 32] = S(nq.z);
+    }
+    // flat walk plane (the only one a batch without rough-terrain inputs ever holds): the swing clearance is then
+    // (0, 0, swing_height) and the legs need not read the plane back
+    const bool plane_flat = walker_wpn_k.x == K(0) && walker_wpn_k.y == K(0) && walker_wpn_k.z == K(1);
+    const bool plane_changed_prev = (rbits >> RB_PLANE_CHANGED) & 1;
+    bool def_changed = false;
 
 
     // =================================================================================================================
@@ -898,6 +954,7 @@ template <class P, int D, bool FULL> struct Cycle {
       bool at_correct = (bits >> 18) & 1;
       bool completed = (bits >> 19) & 1;
       bool negate = (bits >> 20) & 1;
+      bool plane_saved = (bits >> LB_PLANE_SAVED) & 1;
       int swing_num = (int)(short)(prog & 0xffff);
       int stance_num = (int)(short)((prog >> 16) & 0xffff);
 
@@ -976,6 +1033,7 @@ template <class P, int D, bool FULL> struct Cycle {
               V3<K> proj = projection(sto - idt, cvt<K>(wpn_l));
               def = cvt<T>(idt + proj);
               st3(sl, LS::DEF, def);
+              def_changed = true;
               step_state = STEP_FORCE_STOP;
               at_correct = true;
               legs_at_correct++;
@@ -996,13 +1054,16 @@ template <class P, int D, bool FULL> struct Cycle {
         if (step_state != STEP_FORCE_STOP) {
           // updateStride (:921); the body velocity and the walker's plane were written / are still held in this
           // robot's planes (L1 hits), which keeps them out of the loop's live registers
-          const V3<T> walker_wp = ld3T(sp, RS_WPL);
-          const V3<T> walker_wpn = ld3T(sp, RS_WPN);
-          const T bvx = T(sp[(RS_VEL) * 32]), bvy = T(sp[(RS_VEL + 1) * 32]), bw = T(sp[(RS_ANGVEL) * 32]);
+          const T bvx = scratch[0], bvy = scratch[32], bw = scratch[64];
           stride = V3<T>{bvx - bw * T(tipy), bvy + bw * T(tipx), T(0)} * ct.stride_scale;
           st3(sl, LS::STRIDE, stride);
-          st3(sl, LS::WP, walker_wp);
-          st3(sl, LS::WPN, walker_wpn);
+          // walk_plane_ / walk_plane_normal_ of the leg = the walker's plane (:1049).  The copy in HBM already holds
+          // it unless the plane changed in the previous cycle or the leg sat out while it did.
+          if (!plane_saved || plane_changed_prev) {
+            st3(sl, LS::WP, ld3T(sp, RS_WPL));
+            st3(sl, LS::WPN, ld3T(sp, RS_WPN));
+          }
+          plane_saved = true;
           V3<T> delta;
           if (step_state == STEP_SWING) {
             int iteration = phase - ci.swing_start + 1;
@@ -1019,7 +1080,8 @@ template <class P, int D, bool FULL> struct Cycle {
             }
             // Control nodes relative to the swing origin (generatePrimary/SecondarySwingControlNodes :1238-1291);
             // only node differences enter quarticBezierDot, so the origin cancels.
-            V3<T> clr = normalized(walker_wpn) * ct.swing_height;
+            V3<T> clr{T(0), T(0), ct.swing_height};
+            if (!plane_flat) clr = normalized(ld3T(sp, RS_WPN)) * ct.swing_height;
             V3<T> tr = tgt - swo_p;
             V3<T> mid{tr.x * T(0.5) + clr.x, tr.y * T(0.5) + clr.y + lt.ysign * ct.swing_width, max_(T(0), tr.z) + clr.z};
             V3<T> sep1 = swo_v * (T(0.25) * (ct.dt / ct.swing_dt));
@@ -1071,6 +1133,8 @@ template <class P, int D, bool FULL> struct Cycle {
           dl[(LD_TIP + 1) * 32] = tipy;
           dl[(LD_TIP + 2) * 32] = tipz;
           st3(sl, LS::TIPVEL, delta * ct.inv_dt);
+        } else if (plane_changed_prev) {
+          plane_saved = false;  // the leg sits this cycle out: its saved plane is now older than the walker's
         }
 
         // ---- LegStepper::iteratePhase (:871) + updateStepState (:901) ----
@@ -1100,7 +1164,7 @@ template <class P, int D, bool FULL> struct Cycle {
       }
       SHC_STAMP(6 + 3 * l);
       bits = (phase & 0xffff) | (step_state << 16) | ((at_correct ? 1 : 0) << 18) | ((completed ? 1 : 0) << 19) |
-             ((negate ? 1 : 0) << 20);
+             ((negate ? 1 : 0) << 20) | ((plane_saved ? 1 : 0) << LB_PLANE_SAVED);
       prog = (swing_num & 0xffff) | ((stance_num & 0xffff) << 16);
       il[(LI_BITS) * 32] = bits;
       il[(LI_PROG) * 32] = prog;
@@ -1172,35 +1236,39 @@ template <class P, int D, bool FULL> struct Cycle {
     // =================================================================================================================
     // 4. updateWalkPlane (:748) + odometry (:783)
     // =================================================================================================================
-    bool plane_changed = false;  // a cycle without updateWalkPlane (trap 7) leaves the plane as it was
+    // The plane is the least-squares fit of the legs' default tips, which only move when a stopping leg re-seats its
+    // default tip (def_changed) — otherwise the fit of the previous cycle, already in HBM, is this cycle's result bit for
+    // bit.  RB_PLANE_STALE (states written from outside) forces one fit.  A cycle without updateWalkPlane (trap 7)
+    // leaves everything as it was.
+    bool plane_changed = plane_changed_prev;
+    bool plane_stale = (rbits >> RB_PLANE_STALE) & 1;
     if (!starting_now) {
-      V3<double> new_wpl{0.0, 0.0, 0.0}, new_wpn{0.0, 0.0, 1.0};
-      if (L >= 3) {
-        // normal equations over the (possibly updated) default tips: A = [x y 1], b = z.  Re-read here rather than
-        // accumulated inside the leg loop to keep eight doubles out of its live registers.
-        double sxx = 0, sxy = 0, sx1 = 0, syy = 0, sy1 = 0, sxz = 0, syz = 0, sz1 = 0;
-#pragma unroll
-        for (int l = 0; l < kMaxLegs; ++l) {
-          if (l >= L) break;
-          const S* __restrict__ sl = sp + (ci.offS_leg + l * ci.strideS_leg) * 32;
-          double x = (double)sl[(LS::DEF) * 32], y = (double)sl[(LS::DEF + 1) * 32], z = (double)sl[(LS::DEF + 2) * 32];
-          sxx += x * x; sxy += x * y; sx1 += x; syy += y * y; sy1 += y; sxz += x * z; syz += y * z; sz1 += z;
+      plane_changed = false;
+      if (def_changed || plane_stale) {
+        V3<double> new_wpl{0.0, 0.0, 0.0}, new_wpn{0.0, 0.0, 1.0};
+        if (L >= 3) {
+          // normal equations over the (possibly updated) default tips: A = [x y 1], b = z
+          double sxx = 0, sxy = 0, sx1 = 0, syy = 0, sy1 = 0, sxz = 0, syz = 0, sz1 = 0;
+#pragma unroll 1
+          for (int l = 0; l < L; ++l) {
+            const S* __restrict__ sl = sp + (ci.offS_leg + l * ci.strideS_leg) * 32;
+            double x = (double)sl[(LS::DEF) * 32], y = (double)sl[(LS::DEF + 1) * 32], z = (double)sl[(LS::DEF + 2) * 32];
+            sxx += x * x; sxy += x * y; sx1 += x; syy += y * y; sy1 += y; sxz += x * z; syz += y * z; sz1 += z;
+          }
+          // solve (A^T A) w = A^T b with A^T A = [[sxx sxy sx1],[sxy syy sy1],[sx1 sy1 L]]
+          double n = (double)L;
+          double c00 = syy * n - sy1 * sy1, c01 = sx1 * sy1 - sxy * n, c02 = sxy * sy1 - syy * sx1;
+          double c11 = sxx * n - sx1 * sx1, c12 = sxy * sx1 - sxx * sy1;
+          double c22 = sxx * syy - sxy * sxy;
+          double det = sxx * c00 + sxy * c01 + sx1 * c02;
+          double id = 1.0 / det;
+          double a = (c00 * sxz + c01 * syz + c02 * sz1) * id;
+          double b = (c01 * sxz + c11 * syz + c12 * sz1) * id;
+          double cc = (c02 * sxz + c12 * syz + c22 * sz1) * id;
+          V3<double> nrm = normalized(V3<double>{-a, -b, 1.0});
+          new_wpl = V3<double>{a, b, cc};
+          new_wpn = nrm;
         }
-        // solve (A^T A) w = A^T b with A^T A = [[sxx sxy sx1],[sxy syy sy1],[sx1 sy1 L]]
-        double n = (double)L;
-        double c00 = syy * n - sy1 * sy1, c01 = sx1 * sy1 - sxy * n, c02 = sxy * sy1 - syy * sx1;
-        double c11 = sxx * n - sx1 * sx1, c12 = sxy * sx1 - sxx * sy1;
-        double c22 = sxx * syy - sxy * sxy;
-        double det = sxx * c00 + sxy * c01 + sx1 * c02;
-        double id = 1.0 / det;
-        double a = (c00 * sxz + c01 * syz + c02 * sz1) * id;
-        double b = (c01 * sxz + c11 * syz + c12 * sz1) * id;
-        double cc = (c02 * sxz + c12 * syz + c22 * sz1) * id;
-        V3<double> nrm = normalized(V3<double>{-a, -b, 1.0});
-        new_wpl = V3<double>{a, b, cc};
-        new_wpn = nrm;
-      }
-      {
         // stored values as the next cycle will read them; "changed" compares the stored bits
         const V3<S> ol = {sp[(RS_WPL) * 32], sp[(RS_WPL + 1) * 32], sp[(RS_WPL + 2) * 32]};
         const V3<S> on = {sp[(RS_WPN) * 32], sp[(RS_WPN + 1) * 32], sp[(RS_WPN + 2) * 32]};
@@ -1208,24 +1276,14 @@ template <class P, int D, bool FULL> struct Cycle {
                           on.y == S(new_wpn.y) && on.z == S(new_wpn.z));
         st3(sp, RS_WPL, new_wpl);
         st3(sp, RS_WPN, new_wpn);
+        plane_stale = false;
       }
-      // odometry_ideal_ = odometry_ideal_.addPose(calculateOdometry(dt))
-      Q4<T> oq{T(sp[(RS_ODOMQ) * 32]), T(sp[(RS_ODOMQ + 1) * 32]), T(sp[(RS_ODOMQ + 2) * 32]),
-               T(sp[(RS_ODOMQ + 3) * 32])};
-      const T ovx = T(sp[(RS_VEL) * 32]), ovy = T(sp[(RS_VEL + 1) * 32]), ow = T(sp[(RS_ANGVEL) * 32]);
-      V3<T> dpos = qrot(oq, V3<T>{ovx * ct.dt, ovy * ct.dt, T(0)});
-      dp[(RD_ODOMP) * 32] += (double)dpos.x;
-      dp[(RD_ODOMP + 1) * 32] += (double)dpos.y;
-      dp[(RD_ODOMP + 2) * 32] += (double)dpos.z;
-      Q4<T> nq = qmul(oq, q_axis_z(ow * ct.dt));
-      sp[(RS_ODOMQ) * 32] = S(nq.w);
-      sp[(RS_ODOMQ + 1) * 32] = S(nq.x);
-      sp[(RS_ODOMQ + 2) * 32] = S(nq.y);
-      sp[(RS_ODOMQ + 3) * 32] = S(nq.z);
     }
 
     rbits = (walk_state & 3) | ((legs_at_correct & 15) << 2) | ((legs_completed & 15) << 6) | ((rtd & 1) << 10) |
-            ((pose_state & 3) << 11) | ((auto_state & 3) << 13) | ((plane_changed ? 1 : 0) << RB_PLANE_CHANGED) | (status << 16);
+            ((pose_state & 3) << 11) | ((auto_state & 3) << 13) | ((plane_changed ? 1 : 0) << RB_PLANE_CHANGED) |
+            ((status & RB_STATUS_MASK) << RB_STATUS_SHIFT) | ((man_identity ? 1 : 0) << RB_MANUAL_IDENTITY) |
+            (int)((plane_stale ? 1u : 0u) << RB_PLANE_STALE);
     ip[(RI_BITS) * 32] = rbits;
     if (io.flags_out && live) io.flags_out[r] = status;
     SHC_STAMP(30);

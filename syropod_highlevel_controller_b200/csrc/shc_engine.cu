@@ -74,7 +74,18 @@ __global__ void SHC_KERNEL_BOUNDS control_cycle_kernel(const __grid_constant__ C
     }
   };
   if (lane == 0) fence_proxy_async_smem();  // the lanes' generic-proxy writes of the tile, ordered by the __syncwarp above
-  put(io.joints_out + base);
+  if (io.joints_out) put(io.joints_out + base);
+  if (io.gather_mc) {
+    // NVSwitch multicast: ONE store per 16 bytes leaves this GPU and the switch replicates it into every rank's gather
+    // buffer (this rank's included) — egress per rank and cycle is the shard itself, not (world - 1) copies of it
+    float* dst = io.gather_mc + io.gather_offset + base;
+    if ((reinterpret_cast<unsigned long long>(dst) & 15ull) == 0 && (valid & 3) == 0) {
+      const float4* src4 = reinterpret_cast<const float4*>(src);
+      for (int i = lane; i < valid / 4; i += 32) multimem_st_v4(dst + 4 * i, src4[i]);
+    } else {
+      for (int i = lane; i < valid; i += 32) multimem_st_f32(dst + i, src[i]);
+    }
+  }
   for (int p = 0; p < io.n_gather; ++p) put(io.gather[p] + io.gather_offset + base);
   if (any_bulk && lane == 0) bulk_commit_and_wait_read();  // shared memory may go away once the TMA unit has read it
 #ifdef SHC_TRACE
@@ -82,15 +93,43 @@ __global__ void SHC_KERNEL_BOUNDS control_cycle_kernel(const __grid_constant__ C
 #endif
 }
 
-// "This rank's shard of cycle c has landed everywhere": launched behind the control-cycle kernel on the same stream (its
-// peer-memory stores are performed when it completes), it raises this rank's flag in every peer's flag array.  The peers
-// wait on their local flags with stream memory operations (cuStreamWaitValue32): no collective per cycle.
+// "This rank's shard of one more cycle has landed everywhere": launched on a side stream behind the control-cycle kernel
+// (its stores are performed when it completes; the system-scope release below waits for the posted NVLink writes to
+// drain), it bumps this rank's landed counter in every rank's flag array — through the multicast address when there is
+// one (multimem.red, the same path the data took), else with one st.release.sys per peer.  Counters are monotonic: the
+// value is the number of cycles of this source rank that have landed.
 struct SignalArgs {
   int* flag[8];
+  int* mc_flag;
   int n, value;
 };
 __global__ void gather_signal_kernel(SignalArgs a) {
-  if (threadIdx.x < a.n) store_release_sys(a.flag[threadIdx.x], a.value);
+  if (a.mc_flag) {
+    if (threadIdx.x == 0) multimem_red_release_add(a.mc_flag, 1);
+  } else if (threadIdx.x < a.n) {
+    store_release_sys(a.flag[threadIdx.x], a.value);
+  }
+}
+// Device-side wait on the local landed counters (ld.acquire.sys spin, one lane per source rank): the stream continues
+// once every source has landed `need[p]` cycles here.  Gives up after ~4 s (a peer died) and records it in *err instead of
+// hanging the GPU.
+struct WaitArgs {
+  const int* flags;
+  int need[8];
+  int n;
+  int* err;
+};
+__global__ void gather_wait_kernel(WaitArgs a) {
+  if (threadIdx.x >= a.n) return;
+  const int* f = a.flags + threadIdx.x;
+  const long long t0 = clock64();
+  while (load_acquire_sys(f) - a.need[threadIdx.x] < 0) {
+    __nanosleep(200);
+    if (clock64() - t0 > 8000000000ll) {
+      if (a.err) *a.err = 1 + threadIdx.x;
+      break;
+    }
+  }
 }
 
 template <int D>
@@ -151,13 +190,9 @@ template <class F> static int dispatch_D(int D, F&& f) {
     if (err__ != cudaSuccess) return fail(SHC_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(err__)); \
   } while (0)
 
-// Cycle k writes buffer k % B of every rank (B = 16).  Rewriting a buffer needs a landed signal of cycle k - B + 1 or
-// later (every rank has then started the cycle after the one whose data is overwritten, i.e. is past any stream-ordered
-// consumer of it).  Signals are raised for every kGatherSignalEvery-th cycle and for the last cycle of a call (the flags
-// are monotonic cycle numbers), so inside a long rollout the per-cycle path carries neither a signal nor a wait; a call
-// of one cycle signals and waits every cycle, which is what a consumer of every cycle's data needs.
+// Fused gather: cycle k writes buffer k % B of every rank (B = 16); see shc_gather_step for the protocol.
 constexpr int kGatherBuffers = 16;
-constexpr int kGatherSignalEvery = 8;
+constexpr int kGatherWaitEvery = 4;   // reuse check every 4th cycle, for the next 4 cycles
 constexpr int kHostChunks = 8;  // tile ranges of one shc_step_host call (kernel k+1 overlaps the D2H of range k)
 
 struct GraphKey {
@@ -205,21 +240,20 @@ struct shc_engine {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   bool done_valid[2] = {false, false};
-  // fused all-gather over peer memory: this rank's gather buffer (kGatherBuffers x world x N x L x D floats, cudaMalloc'ed
-  // so that it can be exported through CUDA IPC), the peers' buffers opened from their handles, a 1-element buffer for the
-  // per-cycle NCCL all-reduce that tells every rank "all shards of this cycle have landed"
-  // landed signals: 0 = per-source flags (one-warp kernel, st.release.sys) + cuStreamWaitValue32 inside a call, barrier
-  // all-reduce at the end of a call (default); 1 = no mid-call flags (when cuStreamWaitValue32 is unavailable: calls must then
-  // be shorter than the 16-buffer reuse window); 2 = none (tuning only)
-  int gather_signal_mode = 0;
+  // fused all-gather over peer memory: every rank's gather buffer ([kGatherBuffers][world][N][L][D] floats + one landed
+  // counter per source rank), mapped here either through CUDA IPC (shc_gather_alloc / shc_gather_open_peer: cudaMalloc'ed
+  // and owned by the engines) or handed in by the caller (shc_gather_attach: e.g. torch symmetric memory, which also
+  // provides the NVSwitch multicast mapping of the same buffers)
   float* gather_own = nullptr;
   float* gather_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float* gather_mc = nullptr;
+  bool gather_owned = false;
   bool gather_opened[8] = {false, false, false, false, false, false, false, false};
-  int* gather_token = nullptr;
-  cudaEvent_t ev_kernel[kGatherBuffers] = {};  // "cycle's kernel done", for the side-stream flag kernels
-  long long gather_cycle = 0, gather_waited = -1;  // cycles issued; newest cycle whose landed signal this stream waited for
-  long long gather_signal_hist[4] = {-1, -1, -1, -1};  // the last cycles for which a landed signal was issued (same on every rank)
-  unsigned gather_signal_pos = 0;
+  int* gather_err = nullptr;  // mapped pinned word: set by a device-side wait that gave up
+  cudaStream_t signal = nullptr;  // high-priority stream of the landed-signal kernels
+  cudaEvent_t ev_kernel[kGatherBuffers] = {};  // "cycle's kernel done", for the side-stream signal kernels
+  long long gather_cycle = 0;   // cycles issued (same on every rank)
+  long long gather_waited = 0;  // every source is known to have landed at least this many cycles here
 };
 
 // NCCL is resolved at run time from the libnccl already loaded in the process (torch's), so libshc_b200.so has no
@@ -253,26 +287,6 @@ NcclApi& nccl() {
     }
   }
   return api;
-}
-}  // namespace
-
-// cuStreamWaitValue32 (driver API) is resolved at run time from the libcuda already loaded in the process, so the
-// library has no link-time dependency on it (the CPU-only symbol checks load libshc_b200.so without a driver).
-namespace {
-typedef int (*StreamWaitValue32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
-StreamWaitValue32Fn stream_wait_value32() {
-  static StreamWaitValue32Fn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_NOLOAD);
-    if (!h) h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
-    if (h) {
-      fn = (StreamWaitValue32Fn)dlsym(h, "cuStreamWaitValue32_v2");
-      if (!fn) fn = (StreamWaitValue32Fn)dlsym(h, "cuStreamWaitValue32");
-    }
-  }
-  return fn;
 }
 }  // namespace
 
@@ -464,12 +478,12 @@ void shc_destroy(shc_engine* e) {
     if (e->ev_done[b]) cudaEventDestroy(e->ev_done[b]);
   }
   if (e->side) cudaStreamDestroy(e->side);
+  if (e->signal) cudaStreamDestroy(e->signal);
   if (e->copy) cudaStreamDestroy(e->copy);
   for (int p = 0; p < 8; ++p)
     if (e->gather_opened[p]) cudaIpcCloseMemHandle(e->gather_peer[p]);
-  cudaFree(e->gather_own);
-
-  cudaFree(e->gather_token);
+  if (e->gather_owned) cudaFree(e->gather_own);
+  if (e->gather_err) cudaFreeHost(e->gather_err);
   for (int b = 0; b < kGatherBuffers; ++b) {
     if (e->ev_kernel[b]) cudaEventDestroy(e->ev_kernel[b]);
   }
@@ -538,6 +552,7 @@ static StepIO make_io(shc_engine* e, const float* cmd, const float* imu, const f
   io.tile_end = (e->n + 31) / 32;
   io.n_gather = 0;
   io.gather_offset = 0;
+  io.gather_mc = nullptr;
   for (auto& g : io.gather) g = nullptr;
 
   io.flags_out = (e->options & SHC_OPT_STATUS_FLAGS) ? e->d_flags : nullptr;
@@ -765,28 +780,75 @@ int shc_rollout_allgather(shc_engine* e, int k_cycles, const float* cmd_seq, flo
 }
 
 // ---- fused all-gather over peer memory (NVLink / NVSwitch) ---------------------------------------------------------------
-// Every rank allocates its gather buffer with cudaMalloc and exports it (CUDA IPC, 64-byte handle); the caller exchanges
-// the handles (e.g. torch.distributed.all_gather_object) and every rank opens its peers' buffers.  The control-cycle
-// kernel then stores each tile's joint commands into ALL ranks' buffers as it finishes the tile.
+// The control-cycle kernel stores each finished tile of joint commands into ALL ranks' gather buffers.  Two ways to get the
+// buffers mapped:
+//   * shc_gather_attach: the caller owns symmetric buffers (one per rank, same size) and passes every rank's mapping of
+//     them plus, when the fabric offers it, their NVSwitch MULTICAST mapping — then one multimem.st per 16 bytes leaves
+//     this GPU and the switch replicates it (egress = the shard, not world-1 copies of it);
+//   * shc_gather_alloc / shc_gather_open_peer: the engines cudaMalloc the buffers and exchange CUDA-IPC handles; the
+//     kernel then issues one TMA bulk store per peer (unicast).
+static size_t gather_data_bytes(const shc_engine* e, int world) {
+  const size_t per_rank = (size_t)e->n * e->cfg.leg_count * e->cfg.joint_count;
+  return ((size_t)kGatherBuffers * world * per_rank * 4 + 255) / 256 * 256;
+}
+static int* gather_flags_of(const shc_engine* e, int p) {
+  return reinterpret_cast<int*>(reinterpret_cast<char*>(e->gather_peer[p]) + gather_data_bytes(e, e->world));
+}
+static int gather_common_init(shc_engine* e) {
+  if (!e->signal) {
+    int lo = 0, hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&e->signal, cudaStreamNonBlocking, hi));
+  }
+  for (int b = 0; b < kGatherBuffers; ++b)
+    if (!e->ev_kernel[b]) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_kernel[b], cudaEventDisableTiming));
+  if (!e->gather_err) {
+    CUDA_TRY(cudaHostAlloc((void**)&e->gather_err, 4, cudaHostAllocMapped));
+    *e->gather_err = 0;
+  }
+  e->gather_cycle = 0;
+  e->gather_waited = 0;
+  return SHC_OK;
+}
+
+size_t shc_gather_bytes(const shc_engine* e, int world_size) {
+  if (!e || world_size < 1) return 0;
+  return gather_data_bytes(e, world_size) + 256;
+}
+int shc_gather_buffers(void) { return kGatherBuffers; }
+
+int shc_gather_attach(shc_engine* e, int rank, int world_size, void* const* peer_buffers, void* multicast_buffer) {
+  if (!e || !peer_buffers || rank < 0 || rank >= world_size) return fail(SHC_E_INVALID, "shc_gather_attach: bad arguments");
+  if (world_size > 8) return fail(SHC_E_UNSUPPORTED, "fused gather supports up to 8 ranks (one node)");
+  if (e->gather_own) return fail(SHC_E_INVALID, "a gather buffer is already attached");
+  for (int p = 0; p < world_size; ++p)
+    if (!peer_buffers[p]) return fail(SHC_E_INVALID, "shc_gather_attach: null peer buffer");
+  CUDA_TRY(cudaSetDevice(e->device));
+  e->rank = rank;
+  e->world = world_size;
+  for (int p = 0; p < world_size; ++p) e->gather_peer[p] = (float*)peer_buffers[p];
+  e->gather_own = e->gather_peer[rank];
+  e->gather_mc = (float*)multicast_buffer;
+  e->gather_owned = false;
+  // landed counters start at zero; the caller runs a barrier between this call and the first cycle
+  CUDA_TRY(cudaMemset(reinterpret_cast<char*>(e->gather_own) + gather_data_bytes(e, world_size), 0, 256));
+  CUDA_TRY(cudaDeviceSynchronize());
+  return gather_common_init(e);
+}
+
 int shc_gather_alloc(shc_engine* e, void* handle64_out, float** buffer_out) {
   if (!e || !handle64_out) return fail(SHC_E_INVALID, "shc_gather_alloc: bad arguments");
   if (!e->nccl_comm) return fail(SHC_E_INVALID, "shc_nccl_init has not been called");
   if (e->world > 8) return fail(SHC_E_UNSUPPORTED, "fused gather supports up to 8 ranks (one node)");
   CUDA_TRY(cudaSetDevice(e->device));
-  const size_t per_rank = (size_t)e->n * e->cfg.leg_count * e->cfg.joint_count;
   if (!e->gather_own) {
-    // [kGatherBuffers][world][n][L][D] floats, then (256-byte aligned) one landed flag per source rank
-    const size_t data_bytes = ((size_t)kGatherBuffers * e->world * per_rank * 4 + 255) / 256 * 256;
-    CUDA_TRY(cudaMalloc((void**)&e->gather_own, data_bytes + 256));
-    CUDA_TRY(cudaMemset(e->gather_own, 0, data_bytes + 256));
-    if (const char* m = getenv("SHC_GATHER_SIGNAL")) e->gather_signal_mode = !strcmp(m, "none") ? 2 : !strcmp(m, "barrier") ? 1 : 0;
-    if (e->gather_signal_mode == 0 && !stream_wait_value32()) e->gather_signal_mode = 1;
-    CUDA_TRY(cudaMalloc((void**)&e->gather_token, 4));
-    CUDA_TRY(cudaMemset(e->gather_token, 0, 4));
-    for (int b = 0; b < kGatherBuffers; ++b) {
-      CUDA_TRY(cudaEventCreateWithFlags(&e->ev_kernel[b], cudaEventDisableTiming));
-    }
+    const size_t bytes = gather_data_bytes(e, e->world) + 256;
+    CUDA_TRY(cudaMalloc((void**)&e->gather_own, bytes));
+    e->gather_owned = true;
+    CUDA_TRY(cudaMemset(e->gather_own, 0, bytes));
     CUDA_TRY(cudaDeviceSynchronize());
+    int rc = gather_common_init(e);
+    if (rc != SHC_OK) return rc;
   }
   cudaIpcMemHandle_t h;
   CUDA_TRY(cudaIpcGetMemHandle(&h, e->gather_own));
@@ -810,85 +872,106 @@ int shc_gather_open_peer(shc_engine* e, int peer_rank, const void* handle64) {
   return SHC_OK;
 }
 
-int shc_gather_buffers(void) { return kGatherBuffers; }
-
-// k control cycles; cycle t stores its joint commands into buffer (t % shc_gather_buffers()) of EVERY rank's gather buffer
-// from inside the kernel (TMA bulk stores to peer-mapped memory); a one-warp kernel behind it raises this rank's "cycle t
-// has landed" flag on every peer, which the peers wait on with stream memory operations (SHC_GATHER_SIGNAL=nccl falls back
-// to a 1-element NCCL all-reduce per cycle on a side stream).
-// On return (stream-ordered) the caller's stream has waited for the last cycle's signals; *last_buffer_out = index of
-// the buffer holding the last cycle.
-int shc_rollout_gather_fused(shc_engine* e, int k_cycles, const float* cmd_seq, int* last_buffer_out, void* stream) {
-  if (!e || !cmd_seq || k_cycles < 1) return fail(SHC_E_INVALID, "shc_rollout_gather_fused: bad arguments");
-  if (!e->gather_own) return fail(SHC_E_INVALID, "shc_gather_alloc has not been called");
+static int gather_ready(shc_engine* e, const char* who) {
+  if (!e->gather_own) return fail(SHC_E_INVALID, std::string(who) + ": no gather buffer (shc_gather_attach / shc_gather_alloc)");
   for (int p = 0; p < e->world; ++p)
-    if (!e->gather_peer[p]) return fail(SHC_E_INVALID, "shc_gather_open_peer has not been called for every peer");
+    if (!e->gather_peer[p]) return fail(SHC_E_INVALID, std::string(who) + ": a peer's gather buffer is not mapped");
+  return SHC_OK;
+}
+
+// The stream waits until every source rank has landed `need` cycles in this rank's buffer.
+static int gather_wait(shc_engine* e, long long need, cudaStream_t st) {
+  if (need <= e->gather_waited) return SHC_OK;
+  WaitArgs wa;
+  wa.flags = gather_flags_of(e, e->rank);
+  wa.n = e->world;
+  for (int p = 0; p < 8; ++p) wa.need[p] = (int)need;
+  wa.err = nullptr;
+  if (cudaHostGetDevicePointer((void**)&wa.err, e->gather_err, 0) != cudaSuccess) { cudaGetLastError(); wa.err = nullptr; }
+  gather_wait_kernel<<<1, 32, 0, st>>>(wa);
+  CUDA_TRY(cudaGetLastError());
+  e->gather_waited = need;
+  return SHC_OK;
+}
+
+// One control cycle whose joint commands land in buffer (cycle % shc_gather_buffers()) of EVERY rank, stored from inside
+// the kernel.  Per-cycle protocol (no collective, nothing on the critical path but the kernel itself):
+//   * reuse: buffer b was last written by cycle c - B.  A peer's consumers of that data were ordered on its stream
+//     before its kernel c - B + 1, so "every source has landed c - B + 2 cycles here" proves they are done.  Checked
+//     every kGatherWaitEvery cycles for the cycles up to the next check, by a one-warp spin kernel on counters that are
+//     normally long past the mark (peers run within a cycle or two of each other);
+//   * landed signal: an event behind the kernel, then on the high-priority side stream a one-warp kernel whose
+//     system-scope release waits for this cycle's posted NVLink writes to drain and bumps this rank's counter on every
+//     rank — concurrent with the next cycle's kernel.
+int shc_gather_step(shc_engine* e, const float* cmd, const float* imu, const float* tip_force, const float* manual, void* stream) {
+  if (!e || !cmd) return fail(SHC_E_INVALID, "shc_gather_step: cmd is required");
+  int rc = gather_ready(e, "shc_gather_step");
+  if (rc != SHC_OK) return rc;
   CUDA_TRY(cudaSetDevice(e->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-  const size_t n = e->n, per_rank = n * e->cfg.leg_count * e->cfg.joint_count;
-  const size_t data_bytes = ((size_t)kGatherBuffers * e->world * per_rank * 4 + 255) / 256 * 256;
-  auto flags_of = [&](int p) { return reinterpret_cast<int*>(reinterpret_cast<char*>(e->gather_peer[p]) + data_bytes); };
-  const bool flags_ok = e->gather_signal_mode == 0;
-  // raises this rank's "cycle c has landed" flag on every peer, behind the kernels already on stream `s`
-  auto raise_flags = [&](long long c, cudaStream_t s) {
-    SignalArgs sa;
-    sa.n = 0;
-    for (int p = 0; p < e->world; ++p)
-      if (p != e->rank) sa.flag[sa.n++] = flags_of(p) + e->rank;
-    sa.value = (int)(c + 1);
-    gather_signal_kernel<<<1, 32, 0, s>>>(sa);
-  };
-  for (int k = 0; k < k_cycles; ++k) {
-    const long long cyc = e->gather_cycle++;
-    const int b = (int)(cyc % kGatherBuffers);
-    int rc;
-    // Rewriting buffer b needs a landed signal of cycle cyc - B + 1 or later from every rank.  Inside a call the stream
-    // waits (cuStreamWaitValue32 on the local flags) for the OLDEST signalled cycle that qualifies: it is >= 8 cycles
-    // back, so the flags are already up and the wait passes at once (a wait that really has to wait costs ~0.5 ms on
-    // this driver, which is why the end of the call uses a collective instead).
-    if (flags_ok && cyc - kGatherBuffers + 1 > e->gather_waited) {
-      long long target = -1;
-      for (long long sgn : e->gather_signal_hist)
-        if (sgn >= cyc - kGatherBuffers + 1 && (target < 0 || sgn < target)) target = sgn;
-      if (target < 0) return fail(SHC_E_INVALID, "fused gather: no landed signal in the reuse window");
-      for (int p = 0; p < e->world; ++p) {
-        if (p == e->rank) continue;
-        if (stream_wait_value32()(st, (unsigned long long)(uintptr_t)(flags_of(e->rank) + p), (unsigned)(target + 1), /*GEQ*/ 0) != 0)
-          return fail(SHC_E_CUDA, "cuStreamWaitValue32 failed");
-      }
-      e->gather_waited = target;
-    }
-    StepIO io = make_io(e, cmd_seq + (size_t)k * n * 3, nullptr, nullptr, nullptr, e->gather_own + ((size_t)b * e->world + e->rank) * per_rank);
-    io.n_gather = 0;
+  const size_t per_rank = (size_t)e->n * e->cfg.leg_count * e->cfg.joint_count;
+  const long long cyc = e->gather_cycle;
+  const int b = (int)(cyc % kGatherBuffers);
+  if (cyc % kGatherWaitEvery == 0) {
+    const long long need = cyc + kGatherWaitEvery - 1 - kGatherBuffers + 2;  // for the cycles cyc .. cyc + W - 1
+    if (need > 0 && (rc = gather_wait(e, need, st)) != SHC_OK) return rc;
+  }
+  float* own_slot = e->gather_own + ((size_t)b * e->world + e->rank) * per_rank;
+  StepIO io = make_io(e, cmd, imu, tip_force, manual, e->gather_mc ? nullptr : own_slot);
+  io.gather_offset = (long long)(((size_t)b * e->world + e->rank) * per_rank);
+  io.gather_mc = e->gather_mc;
+  io.n_gather = 0;
+  if (!e->gather_mc)
     for (int p = 0; p < e->world; ++p)
       if (p != e->rank) io.gather[io.n_gather++] = e->gather_peer[p];
-    io.gather_offset = (long long)(((size_t)b * e->world + e->rank) * per_rank);
-    rc = launch_cycle(e, io, st);
-    if (rc != SHC_OK) return rc;
-    const bool last = k == k_cycles - 1;
-    if (flags_ok && !last && cyc % kGatherSignalEvery == kGatherSignalEvery - 1) {
-      // mid-call signal, on the side stream: its system-scope release waits for the kernel's posted peer writes to drain
-      // through NVLink, and on the main stream that drain would serialise with the next cycle instead of hiding behind it
-      CUDA_TRY(cudaEventRecord(e->ev_kernel[b], st));
-      CUDA_TRY(cudaStreamWaitEvent(e->side, e->ev_kernel[b], 0));
-      raise_flags(cyc, e->side);
-      e->gather_signal_hist[e->gather_signal_pos++ % 4] = cyc;
-    }
-    if (last_buffer_out) *last_buffer_out = b;
+  if ((rc = launch_cycle(e, io, st)) != SHC_OK) return rc;
+  CUDA_TRY(cudaEventRecord(e->ev_kernel[b], st));
+  CUDA_TRY(cudaStreamWaitEvent(e->signal, e->ev_kernel[b], 0));
+  SignalArgs sa;
+  sa.n = 0;
+  sa.mc_flag = nullptr;
+  if (e->gather_mc) {
+    sa.mc_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(e->gather_mc) + gather_data_bytes(e, e->world)) + e->rank;
+  } else {
+    for (int p = 0; p < e->world; ++p) sa.flag[sa.n++] = gather_flags_of(e, p) + e->rank;  // own counter included
   }
-  // End of the call: this rank's flag for the last cycle (in line: the release waits for the peer writes to drain), then
-  // a 1-element all-reduce as the barrier — once it completes here, every rank has drained and flagged its last cycle, so
-  // every shard of every cycle of the call has landed in this rank's buffer; every rank has also passed all consumers it
-  // had ordered before this call, which re-arms the reuse window.
-  const long long done = e->gather_cycle;
-  if (e->gather_signal_mode != 2) {
-    raise_flags(done - 1, st);
-    int rc = nccl().AllReduce(e->gather_token, e->gather_token, 1, /*ncclInt32*/ 2, /*ncclSum*/ 0, e->nccl_comm, st);
-    if (rc != 0) return fail(SHC_E_CUDA, std::string("ncclAllReduce: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error"));
-    e->gather_signal_hist[e->gather_signal_pos++ % 4] = done - 1;
-    e->gather_waited = done - 1;
-  }
+  sa.value = (int)(cyc + 1);
+  gather_signal_kernel<<<1, 32, 0, e->signal>>>(sa);
+  CUDA_TRY(cudaGetLastError());
+  e->gather_cycle = cyc + 1;
   return SHC_OK;
+}
+
+// `stream` continues once every rank's shard of every cycle issued so far has landed in this rank's buffer.
+int shc_gather_sync(shc_engine* e, int* last_buffer_out, void* stream) {
+  if (!e) return fail(SHC_E_INVALID, "null engine");
+  int rc = gather_ready(e, "shc_gather_sync");
+  if (rc != SHC_OK) return rc;
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  if (last_buffer_out) *last_buffer_out = e->gather_cycle > 0 ? (int)((e->gather_cycle - 1) % kGatherBuffers) : -1;
+  return gather_wait(e, e->gather_cycle, st);
+}
+
+// 0 while every device-side wait has completed; SHC_E_CUDA once one gave up (a peer stopped signalling).
+int shc_gather_status(shc_engine* e) {
+  if (!e || !e->gather_err) return SHC_OK;
+  if (*(volatile int*)e->gather_err != 0)
+    return fail(SHC_E_CUDA, "fused gather: a device-side wait for a peer's landed counter timed out (source rank " +
+                                std::to_string(*(volatile int*)e->gather_err - 1) + ")");
+  return SHC_OK;
+}
+
+// k cycles + the final wait.  Every rank must make the same sequence of calls.  A failure leaves the engine's cycle
+// counter where the last successful cycle put it: the caller can tell how far every rank got and resume or tear down.
+int shc_rollout_gather_fused(shc_engine* e, int k_cycles, const float* cmd_seq, int* last_buffer_out, void* stream) {
+  if (!e || !cmd_seq || k_cycles < 1) return fail(SHC_E_INVALID, "shc_rollout_gather_fused: bad arguments");
+  const size_t n = e->n;
+  for (int k = 0; k < k_cycles; ++k) {
+    int rc = shc_gather_step(e, cmd_seq + (size_t)k * n * 3, nullptr, nullptr, nullptr, stream);
+    if (rc != SHC_OK) return rc;
+  }
+  return shc_gather_sync(e, last_buffer_out, stream);
 }
 
 #ifdef SHC_TRACE

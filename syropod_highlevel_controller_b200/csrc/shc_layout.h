@@ -72,9 +72,15 @@ enum : int { AI_FLAGS = 0 /*4 latch bits per AutoPoser*/, AI_PHASE = 1 /*pose_ph
 enum : int { LI_BITS = 0, LI_PROG = 1, LI_COUNT = 2 };
 
 // RI_BITS: walk_state[0:2) legs_at_correct_phase[2:6) legs_completed_first_step[6:10) return_to_default_attempted[10]
-//          pose_state[11:13) auto_posing_state[13:15) walk plane changed by the last cycle / unknown [15]  status flags [16:32)
-enum : int { RB_PLANE_CHANGED = 15 };
+//          pose_state[11:13) auto_posing_state[13:15) walk plane changed by the last cycle / unknown [15]  status flags [16:28)
+//          manual pose is exactly the identity [30]  walk plane not known to be the least-squares plane of the stored
+//          default tips (state written from outside) [31]
+// The last three are bookkeeping of the engine, not reference state: they let a cycle skip work whose result is already
+// in HBM (the saved plane copies of the legs, the plane fit over unchanged default tips, the identity manual pose).
+enum : int { RB_PLANE_CHANGED = 15, RB_STATUS_SHIFT = 16, RB_STATUS_MASK = 0xfff, RB_MANUAL_IDENTITY = 30, RB_PLANE_STALE = 31 };
 // LI_BITS: phase[0:16) step_state[16:18) at_correct_phase[18] completed_first_step[19] negate_auto_pose[20]
+//          the leg's saved walk plane (WP / WPN planes) equals the walker's plane of the previous cycle's start [21]
+enum : int { LB_PLANE_SAVED = 21 };
 // LI_PROG: swing progress numerator (int16, -1 = "-1.0") | stance progress numerator (int16) << 16
 //          progress = numerator / swing_period (resp. stance_period): walk_controller.cpp:878-896 divides two ints
 //          converted to double, so keeping the numerator makes the value exact in every precision.

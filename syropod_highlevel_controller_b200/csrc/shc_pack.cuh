@@ -120,7 +120,13 @@ template <class E> void pack(const E* e, const shc_robot_state* in, size_t n, Ho
     }
     I(RI_BITS, r) = (s.walk_state & 3) | ((s.legs_at_correct_phase & 15) << 2) | ((s.legs_completed_first_step & 15) << 6) |
                     ((s.return_to_default_attempted & 1) << 10) | ((s.pose_state & 3) << 11) | ((s.auto_posing_state & 3) << 13) |
-                    (1 << RB_PLANE_CHANGED);  // a state written from outside: the first cycle reads the legs' saved planes
+                    (1 << RB_PLANE_CHANGED) |  // a state written from outside: the first cycle reads the legs' saved planes
+                    (1u << RB_PLANE_STALE);    // ... and fits the walk plane to the default tips whatever they are
+    {
+      const double* m = s.manual_pose;
+      const bool ident = m[0] == 0.0 && m[1] == 0.0 && m[2] == 0.0 && m[3] == 1.0 && m[4] == 0.0 && m[5] == 0.0 && m[6] == 0.0;
+      if (ident) I(RI_BITS, r) |= 1 << RB_MANUAL_IDENTITY;
+    }
     for (int l = 0; l < L; ++l) {
       const shc_leg_state& g = s.legs[l];
       const int sb = ci.offS_leg + l * ci.strideS_leg;
@@ -209,7 +215,7 @@ template <int D, class E> void unpack(const E* e, const HostPlanes& h, shc_robot
     s.return_to_default_attempted = (rb >> 10) & 1;
     s.pose_state = (rb >> 11) & 3;
     s.auto_posing_state = (rb >> 13) & 3;
-    s.status_flags = (rb >> 16) & 0xffff;
+    s.status_flags = (rb >> RB_STATUS_SHIFT) & RB_STATUS_MASK;
     // Model::current_pose_ is recomputed every cycle from the stored sub-poses (pose_controller.cpp:811-859)
     {
       PoseT<double> p = pose_identity<double>();
