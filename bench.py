@@ -35,7 +35,6 @@ sys.path.insert(0, ROOT)
 METRIC = "control-cycle steps/sec (6-leg x 3-DOF IK+Bezier)"
 UNIT = "steps/s"
 ROBOTS_PER_GPU = 131072
-REF_SAMPLE_ROBOTS = 16384
 
 
 def measured_peak():
@@ -68,15 +67,19 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(precision):
-    """dram bytes per launch of the control-cycle kernel from the committed ncu --set full capture, if any."""
+def ncu_traffic(precision, workload):
+    """dram__bytes_read + dram__bytes_write per launch of the control-cycle kernel.  NOT measured in this run: it is read
+    from the committed `ncu --set full` capture of the same command (profiles/ncu_summary.json), and labelled so."""
     path = os.path.join(ROOT, "profiles", "ncu_summary.json")
     try:
         with open(path) as f:
             d = json.load(f)
-        return d.get("traffic_bytes_per_launch", {}).get(precision)
+        key = precision if workload == "hexapod" else f"{workload}_{precision}"
+        v = d.get("traffic_bytes_per_launch", {}).get(key)
+        return v, (f"static: ncu --set full capture {d.get('capture', '?')} (profiles/ncu_summary.json), not measured in this run"
+                   if v is not None else None)
     except Exception:
-        return None
+        return None, None
 
 
 class ClockSampler(threading.Thread):
@@ -119,50 +122,65 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_baseline(cfg, threads, robots=8192, cycles=200):
-    """The CPU oracle on the host cores (bounded sample of the same workload)."""
+def _oracle_rate(cfg, robots, cycles, warm, threads):
+    """steps/s of the CPU oracle over `robots` robots: per-robot command streams generated BEFORE the timed region, the
+    whole rollout inside the C library (std::threads spawned once, robots partitioned over them)."""
     from oracle import oracle_py as O
     from syropod_highlevel_controller_b200.streams import CommandStream
 
     ob = O.OracleBatch(cfg, robots)
-    cmd = CommandStream(robots).next().astype(np.float64)
-    ob.run(cmd, 20, threads)  # warm-up: leaves the STOPPED state
-    secs = ob.run(cmd, cycles, threads)
+    cs = CommandStream(robots)
+    seq = np.stack([cs.next() for _ in range(warm + cycles)]).astype(np.float64)
+    if warm:
+        ob.run_seq(seq[:warm], threads)
+    secs = ob.run_seq(seq[warm:], threads)
     ob.close()
-    return {"value": robots * cycles / secs, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{robots} hexapods x {cycles} cycles, constant per-robot commands from the synthetic stream, "
-                      f"{threads} std::thread(s) over robots, g++ -O3 -march=native; a restatement with static storage "
-                      f"(upper bound on the real reference, which cannot be built without ROS/Eigen/Boost)"}
+    return robots * cycles / secs, secs
+
+
+def cpu_baseline(cfg, threads, robots=16384, cycles=100):
+    """The CPU oracle on the host cores (bounded sample of the same workload), all cores and one core."""
+    value, _ = _oracle_rate(cfg, robots, cycles, 20, threads)
+    single, _ = _oracle_rate(cfg, 2048, 100, 20, 1)
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "single_thread_value": single,
+            "sample": f"{robots} hexapods x {cycles} cycles of the synthetic per-robot command streams (20 warm-up cycles), "
+                      f"{threads} std::thread(s) over robots inside the C library, g++ -O3 -march=native; single_thread_value: "
+                      f"2048 robots x 100 cycles on one thread; a restatement with static storage (upper bound on the real "
+                      f"reference, which cannot be built without ROS/Eigen/Boost)"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port) on the host cores, same metric / config."""
+    """--impl reference: the reference's CPU path (oracle port: the reference itself needs ROS + Eigen + Boost) on the host
+    cores, same metric / config.  The timed region is the in-C oracle loop only: streams are generated beforehand and the
+    worker threads live for the whole rollout.  The full per-GPU shard (131072 robots, ~5 GB of oracle state) is used when
+    the host has the memory for it, else the largest power-of-two sample that fits."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import oracle_py as O
     from syropod_highlevel_controller_b200.config import hexapod_config
-    from syropod_highlevel_controller_b200.streams import CommandStream
 
-    cfg = hexapod_config("tripod_gait")
+    cfg = hexapod_config(args.gait)
     threads = os.cpu_count() or 1
-    n = REF_SAMPLE_ROBOTS
-    ob = O.OracleBatch(cfg, n)
-    cs = CommandStream(n)
-    for _ in range(args.warmup):
-        ob.step(cs.next().astype(np.float64), threads=threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ob.step(cs.next().astype(np.float64), threads=threads)
-    secs = time.perf_counter() - t0
-    value = n * args.steps / secs
-    sample = (f"each step = one control cycle over a {n}-robot sample of the {ROBOTS_PER_GPU}-robot per-GPU workload, "
-              f"CPU oracle (port of the reference arithmetic), {threads} threads")
+    n = args.robots_per_gpu
+    try:
+        avail_kb = int(next(l for l in open("/proc/meminfo") if l.startswith("MemAvailable")).split()[1])
+        while n > 1024 and n * 48 > 0.5 * avail_kb:  # ~40 KB of oracle state per robot + the command sequence
+            n //= 2
+    except Exception:
+        n = min(n, 16384)
+    value, secs = _oracle_rate(cfg, n, args.steps, args.warmup, threads)
+    single, _ = _oracle_rate(cfg, 2048, max(args.steps, 20), args.warmup, 1)
+    same = n == args.robots_per_gpu
+    sample = (f"each step = one control cycle over {'the full ' if same else 'a '}{n}-robot "
+              f"{'per-GPU shard' if same else f'sample of the {args.robots_per_gpu}-robot per-GPU shard'}, CPU oracle (port of the "
+              f"reference arithmetic), {threads} threads inside the C library, command streams pre-generated")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"config5 shard: {ROBOTS_PER_GPU} hexapods/GPU, tripod gait, default.yaml", "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": f"config5 shard: {args.robots_per_gpu} hexapods/GPU, {args.gait}, default.yaml", "sample": sample,
+                       "same_config": same},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "single_thread_value": single},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -181,6 +199,9 @@ def main():
                     help="hexapod = the headline workload (configs[4] shard); octopod = configs[3]: 8 legs x 5 DOF with "
                          "admittance + IMU + inclination posing, 262144 robots (secondary line, same JSON shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather-path", default="auto", choices=["auto", "symm", "symm-unicast", "ipc"],
+                    help="fused gather: auto = torch symmetric memory with NVSwitch multicast when available, else CUDA IPC")
+    ap.add_argument("--no-verify-gather", action="store_true", help="N > 1: skip the bit-exact check of the gathered shards")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N > 1: fused = the kernel stores joint angles into every rank's buffer over NVLink (peer memory); "
                          "nccl = library-issued ncclAllGather per cycle on a side stream")
@@ -225,28 +246,38 @@ def main():
         ims, fs = ImuStream(n, robot_offset=shard.offset), ForceStream(n, L, robot_offset=shard.offset)
         imu_dev = torch.from_numpy(np.stack([ims.next(cfg.time_delta) for _ in range(8)])).to(dev)
         force_dev = torch.from_numpy(np.stack([fs.next() for _ in range(8)])).to(dev)
-    # N > 1: one NCCL all-gather of the joint angles per cycle, issued by the library on a side stream and double
-    # buffered so that cycle t's gather overlaps cycle t+1's kernel (shc_rollout_allgather)
+    # N > 1: the per-cycle all-gather of the joint angles.  fused (default): the kernel stores every tile into every rank's
+    # buffer over NVLink (NVSwitch multicast when the fabric has it); nccl: library-issued ncclAllGather on a side stream
+    gather_mode = None
     if world > 1:
-        eng.init_nccl(rank, world)
         if args.gather == "fused":
             try:
-                eng.init_gather_fused(rank, world)
-            except RuntimeError as ex:  # raised on every rank together: CUDA IPC / peer access not available on this box
+                eng.init_gather_fused(rank, world, mode=args.gather_path)
+                gather_mode = eng.gather_mode
+            except RuntimeError as ex:  # raised on every rank together: no peer-memory path on this box
                 if rank == 0:
                     print(f"bench.py: {ex}; falling back to --gather nccl", file=sys.stderr)
                 args.gather = "nccl"
         if args.gather != "fused":
+            eng.init_nccl(rank, world)
             local2 = torch.empty((2, n, L, D), dtype=torch.float32, device=dev)
             full2 = torch.empty((2, n * world, L, D), dtype=torch.float32, device=dev)
+            gather_mode = "NCCL all-gather per cycle on a side stream"
+
+    def inputs(i):
+        return cmd_dev[i], None if imu_dev is None else imu_dev[i & 7], None if force_dev is None else force_dev[i & 7]
 
     def run(lo, hi):
         if world == 1:
             for i in range(lo, hi):
-                eng.step(cmd_dev[i], None if imu_dev is None else imu_dev[i & 7], None if force_dev is None else force_dev[i & 7])
+                eng.step(*inputs(i))
         elif args.gather == "fused":
-            eng.rollout_gather_fused(cmd_dev[lo:hi])
+            for i in range(lo, hi):
+                eng.gather_step(*inputs(i))
+            eng.gather_sync()
         else:
+            if octo:
+                raise SystemExit("bench.py: --workload octopod with N > 1 needs --gather fused (the NCCL rollout carries commands only)")
             eng.rollout_allgather(cmd_dev[lo:hi], local2, full2)
 
     run(0, pre + W)
@@ -272,20 +303,38 @@ def main():
     ms_per_step = ms_total / K
     value = n * world * K / (ms_total * 1e-3)
 
+    # N > 1: what landed in this rank's gather buffer for the last cycle must be, bit for bit, what a plain NCCL all_gather
+    # of every rank's own shard gives (driver-side correctness evidence of the fused exchange)
+    gather_ok = None
+    if world > 1 and args.gather == "fused" and not args.no_verify_gather:
+        b = eng.gather_sync()
+        torch.cuda.synchronize()
+        eng.gather_status()
+        dist.barrier()
+        got = eng.gather[b]  # [world, n, L, D]
+        own = got[rank].clone()
+        want = torch.empty_like(got)
+        dist.all_gather_into_tensor(want.view(world * n, L, D), own)
+        okt = torch.tensor([1 if torch.equal(got, want) and bool(torch.isfinite(got).all()) and float(got.abs().max()) > 0 else 0],
+                           device=dev, dtype=torch.int32)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        gather_ok = bool(int(okt.item()))
+
     # kernel-only duration (no all-gather in the region) for the roofline: one launch per step on this stream
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     k0.record()
     for i in range(pre + W, pre + W + K):
-        eng.step(cmd_dev[i], None if imu_dev is None else imu_dev[i & 7], None if force_dev is None else force_dev[i & 7])
+        eng.step(*inputs(i))
     k1.record()
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / K
     peak, peak_src = measured_peak()
     b_alg = eng.bytes_per_step_algorithmic
     achieved = n * b_alg / (kernel_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(args.precision, args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None if octo else ncu_traffic(args.precision), "kernel": "control_cycle_kernel", "kernel_ms": kernel_ms,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "control_cycle_kernel", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_step": b_alg, "device_bytes_per_step": eng.bytes_per_step_device,
                 "device_bytes_GBps": n * eng.bytes_per_step_device / (kernel_ms * 1e-3) / 1e9, "peak_source": peak_src}
 
@@ -316,19 +365,24 @@ def main():
                   "stores write each tile's joint angles straight into the caller's page-locked buffer over PCIe, stream sync)",
            "gpu_launches_per_step": 1}
 
+    io_bytes = (3 + (10 + 3 * L if octo else 0) + L * D) * 4
+    state_mb = n * (eng.bytes_per_step_device - io_bytes) / 2 / 1e6
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
             "config": {"workload": (f"configs[3]: {n} octopods/GPU (8 legs x 5 DOF), admittance + IMU + inclination posing, {args.gait}, "
                                     f"per-robot command / IMU / tip-force streams" if octo else
                                     f"config5 shard: {n} hexapods/GPU (6 legs x 3 DOF), {args.gait}, default.yaml parameters, "
-                                    f"per-robot splitmix64 command streams") + (("; all-gather of joint angles per cycle fused into the kernel (peer-memory stores over NVLink)" if args.gather == "fused"
-                                     else "; NCCL all-gather of joint angles per cycle") if world > 1 else ""),
+                                    f"per-robot splitmix64 command streams") +
+                                   (f"; all-gather of the joint angles every cycle: {gather_mode}" if world > 1 else ""),
                        "robots_per_gpu": n, "robots_total": n * world, "precision": args.precision,
-                       "l2": f"state {n * (eng.bytes_per_step_device - 84) // 2 / 1e6:.0f} MB per GPU > 126 MB L2 (inputs larger than L2, no flush)",
+                       "l2": f"state {state_mb:.0f} MB per GPU > 126 MB L2 (inputs larger than L2, no flush)",
                        "pre_roll_cycles": pre},
             "gpu_launches": K, "e2e": e2e, "roofline": roofline, "clocks": clocks}
 
+    if gather_ok is not None:
+        line["gather_ok"] = gather_ok
+        line["gpu_launches"] = 2 * K + (K + 3) // 4 + 1  # control cycle + landed signal per step, reuse checks, final wait
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(cfg, os.cpu_count() or 1)

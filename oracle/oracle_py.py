@@ -59,6 +59,8 @@ def _bind(L):
         L.shc_oracle_batch_step.argtypes = [C.c_void_p, dp, dp, dp, dp, C.c_int]
         L.shc_oracle_batch_run.restype = C.c_double
         L.shc_oracle_batch_run.argtypes = [C.c_void_p, dp, C.c_int, C.c_int]
+        L.shc_oracle_batch_run_seq.restype = C.c_double
+        L.shc_oracle_batch_run_seq.argtypes = [C.c_void_p, dp, C.c_int, C.c_int]
         L.shc_oracle_batch_get_joints.argtypes = [C.c_void_p, dp]
         L.shc_oracle_batch_get_state.argtypes = [C.c_void_p, C.POINTER(ShcRobotState)]
         L.shc_oracle_batch_set_state.argtypes = [C.c_void_p, C.POINTER(ShcRobotState)]
@@ -128,6 +130,12 @@ class OracleBatch:
     def run(self, cmd, cycles: int, threads: int = 1) -> float:
         cmd = _arr(cmd)
         return self._lib.shc_oracle_batch_run(self._h, _dp(cmd), cycles, threads)
+
+    def run_seq(self, cmd_seq, threads: int = 1) -> float:
+        """All cycles of cmd_seq [cycles, n, 3] inside the C library (threads spawned once); returns wall seconds."""
+        cmd_seq = _arr(cmd_seq)
+        assert cmd_seq.ndim == 3 and cmd_seq.shape[1:] == (self.n, 3)
+        return self._lib.shc_oracle_batch_run_seq(self._h, _dp(cmd_seq), int(cmd_seq.shape[0]), threads)
 
     def set_pose_reset_mode(self, mode: int):
         """poser_->setPoseResetMode (state_controller.cpp:1199): 0 none, 1 Z+yaw, 2 X+Y, 3 pitch+roll, 4 all, 5 immediate."""

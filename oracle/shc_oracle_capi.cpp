@@ -294,6 +294,28 @@ double shc_oracle_batch_run(void* h, const double* cmd, int cycles, int n_thread
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// Runs `cycles` control cycles with PER-CYCLE commands cmd_seq [cycles][n][3] (pre-generated by the caller, so that the
+// timed region holds nothing but the control cycles) and returns wall seconds.  Robots are partitioned over n_threads
+// std::threads once; each thread runs all cycles of its own robots.
+double shc_oracle_batch_run_seq(void* h, const double* cmd_seq, int cycles, int n_threads) {
+  Batch* b = static_cast<Batch*>(h);
+  const int n = int(b->robots.size());
+  auto work = [&](int lo, int hi) {
+    for (int i = lo; i < hi; ++i)
+      for (int c = 0; c < cycles; ++c) stepOne(*b->robots[i], cmd_seq + ((size_t)c * n + i) * 3, nullptr, nullptr, nullptr);
+  };
+  auto t0 = std::chrono::steady_clock::now();
+  if (n_threads <= 1) {
+    work(0, n);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work, int((long long)n * t / n_threads), int((long long)n * (t + 1) / n_threads));
+    for (auto& t : th) t.join();
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
 void shc_oracle_batch_get_joints(void* h, double* out) {  // [n][L][D]
   Batch* b = static_cast<Batch*>(h);
   const int L = b->cfg.leg_count, D = b->cfg.joint_count;

@@ -354,7 +354,11 @@ SHC_HD K ik_result_value(const LegConsts<K>& lc, const Chain<K, D>& ch2, const K
 // ---------------------------------------------------------------------------------------------------------------------
 // FULL = false compiles the walking-only engine (no auto / IMU / inclination posing, no admittance): the optional stages
 // and the registers they keep alive across the leg loop disappear at compile time.
+#ifndef SHC_SLOTS
+#define SHC_SLOTS 1
+#endif
 template <class P, int D, bool FULL> struct Cycle {
+  static constexpr int kSlots = SHC_SLOTS;
   using S = typename P::S;
   using T = typename P::T;
   using K = typename P::K;
@@ -453,19 +457,15 @@ template <class P, int D, bool FULL> struct Cycle {
   static __host__ __device__ __forceinline__ int slot_bytes(int frontS) {
     return slot_s_bytes(frontS) + LD_COUNT * 32 * 8 + LI_COUNT * 32 * 4;
   }
-  // Dynamic shared memory of one warp: [slot 0][slot 1][joint tile: 32 robots x L*D floats][2 mbarriers], 128-B granular.
-  // -DSHC_ALIAS_BARRIERS (tuning variant, off: measured 94.1 us against 94.5 us per launch, i.e. no gain): the two mbarriers
-  // live in the last 16 bytes of the joint tile instead — lane 31's entries of the last two legs, which are only written
-  // after the last wait on the respective barrier — so a hexapod f64 warp needs 13568 B and a 16th one-warp block fits.
+  // Dynamic shared memory of one warp: [kSlots staging slots][joint tile: 32 robots x L*D floats][2 mbarriers][scratch],
+  // 128-B granular.  kSlots = 1: leg l+1's planes are requested as soon as leg l has copied its own out of the slot (a leg
+  // body is several DRAM latencies long, so one slot already hides HBM); the warp then needs ~9 KB and the SM holds as
+  // many warps as the register budget allows.  kSlots = 2 requests two legs ahead.
   // bytes of the per-warp scratch planes behind the barriers: the body velocity (3 x T) of the tile's robots, written by
   // the robot-level stage and read by every leg (keeps six registers out of the leg loop without an L2 round trip per leg)
   static __host__ __device__ __forceinline__ int scratch_bytes() { return 3 * 32 * (int)sizeof(T); }
   static __host__ __device__ __forceinline__ int smem_per_warp(int frontS, int L) {
-#ifdef SHC_ALIAS_BARRIERS
-    return (2 * slot_bytes(frontS) + 32 * L * D * 4 + scratch_bytes() + 127) / 128 * 128;
-#else
-    return (2 * slot_bytes(frontS) + 32 * L * D * 4 + 16 + scratch_bytes() + 127) / 128 * 128;
-#endif
+    return (kSlots * slot_bytes(frontS) + 32 * L * D * 4 + 16 + scratch_bytes() + 127) / 128 * 128;
   }
 
   // One warp = one tile of 32 robots (lane = robot).  `wsm` is the warp's shared memory (see smem_per_warp): the joint
@@ -493,27 +493,16 @@ template <class P, int D, bool FULL> struct Cycle {
     SHC_STAMP(0);
     // ---- staging ring ------------------------------------------------------------------------------------------------
     const int sS_bytes = slot_s_bytes(front), s_bytes = slot_bytes(front);
-    float* __restrict__ stage = reinterpret_cast<float*>(wsm + 2 * s_bytes) + lane * (L * D);
-#ifdef SHC_ALIAS_BARRIERS
-    // slot (L-1)&1 is waited on last at the start of leg L-1, the other slot at the start of leg L-2; the aliased tile entries
-    // (lane 31: [leg L-2, last joint .. leg L-1]) are written at the end of those legs, i.e. after the barrier is dead
-    uint64_t* bars_end = reinterpret_cast<uint64_t*>(wsm + 2 * s_bytes + 32 * L * D * 4) - 2;
-    auto bar_of = [&](int s) { return bars_end + (s == ((L - 1) & 1) ? 1 : 0); };
-#else
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + 2 * s_bytes + 32 * L * D * 4);
+    float* __restrict__ stage = reinterpret_cast<float*>(wsm + kSlots * s_bytes) + lane * (L * D);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + kSlots * s_bytes + 32 * L * D * 4);
     auto bar_of = [&](int s) { return bars + s; };
-#endif
-#ifdef SHC_ALIAS_BARRIERS
-    T* __restrict__ scratch = reinterpret_cast<T*>(wsm + 2 * s_bytes + 32 * L * D * 4) + lane;
-#else
-    T* __restrict__ scratch = reinterpret_cast<T*>(wsm + 2 * s_bytes + 32 * L * D * 4 + 16) + lane;
-#endif
+    T* __restrict__ scratch = reinterpret_cast<T*>(wsm + kSlots * s_bytes + 32 * L * D * 4 + 16) + lane;
     const S* tileS = pl.s + tile * (size_t)(ci.nS * 32);
     const double* tileD = pl.d + tile * (size_t)(ci.nD * 32);
     const int* tileI = pl.i + tile * (size_t)(ci.nI * 32);
     auto issue_leg = [&](int l) {  // lane 0: ask the TMA unit for leg l's every-cycle planes
-      unsigned char* slot = wsm + (l & 1) * s_bytes;
-      uint64_t* bar = bar_of(l & 1);
+      unsigned char* slot = wsm + (l % kSlots) * s_bytes;
+      uint64_t* bar = bar_of(l % kSlots);
       mbar_expect_tx(bar, (unsigned)s_bytes);
       bulk_g2s(slot, tileS + (ci.offS_leg + l * ci.strideS_leg - front) * 32, (unsigned)sS_bytes, bar);
       bulk_g2s(slot + sS_bytes, tileD + (ci.offD_leg + l * ci.strideD_leg) * 32, LD_COUNT * 32 * 8, bar);
@@ -580,7 +569,7 @@ template <class P, int D, bool FULL> struct Cycle {
     // needs, and the legs' planes stream in behind it while that stage computes (-3 % per launch, measured).
     if (SHC_LANE0(lane) && rbits != 0x7fffffff) {
       issue_leg(0);
-      if (L > 1) issue_leg(1);
+      if (kSlots > 1 && L > 1) issue_leg(1);
     }
     SHC_STAMP(2);
     int walk_state = rbits & 3;
@@ -913,9 +902,9 @@ template <class P, int D, bool FULL> struct Cycle {
       const LegConsts<K>& lk = ck.leg[l];
       const LegConsts<T>& lt = ct.leg[l];
       // the staged copy of this leg's every-cycle planes: wait for the TMA transfer issued two legs ago
-      const unsigned char* slot = wsm + (l & 1) * s_bytes;
+      const unsigned char* slot = wsm + (l % kSlots) * s_bytes;
       SHC_STAMP(4 + 3 * l);
-      mbar_wait(bar_of(l & 1), (unsigned)((l >> 1) & 1));
+      mbar_wait(bar_of(l % kSlots), (unsigned)((l / kSlots) & 1));
       SHC_STAMP(5 + 3 * l);
       const S* __restrict__ ss = reinterpret_cast<const S*>(slot) + front * 32 + lane;
       const double* __restrict__ sd = reinterpret_cast<const double*>(slot + sS_bytes) + lane;
@@ -1064,10 +1053,20 @@ template <class P, int D, bool FULL> struct Cycle {
             st3(sl, LS::WPN, ld3T(sp, RS_WPN));
           }
           plane_saved = true;
-          V3<T> delta;
+          // tip += dt_u * B'(u) for a quartic Bezier B.  Only the four node differences enter B', and for all three
+          // curves of the reference they collapse to three vectors:
+          //   stance (generateStanceControlNodes :1295)         differences (sep, sep, sep, sep)
+          //   swing, first half (generatePrimary... :1238)      (sep1, sep1, n3 - n2, n4 - n3)
+          //   swing, second half (generateSecondary... :1267)   (m1 - m0, m2 - m1, sep2, sep2), with m1 - m0 = n4 - n3: the
+          //                                                     first-half list read backwards, i.e. with (s, t) swapped
+          // so every lane evaluates ONE curve  X (4 s^3 + 12 s^2 t) + Y 12 s t^2 + Z 4 t^3  on its own (X, Y, Z, s, t):
+          // the swing / stance and first / second half branches only select operands.
+          V3<T> X, Y, Z;
+          T bs, bt, bdt;
           if (step_state == STEP_SWING) {
             int iteration = phase - ci.swing_start + 1;
-            bool first_half = iteration <= ci.swing_iterations / 2;
+            const int half = ci.swing_iterations / 2;
+            const bool first_half = iteration <= half;
             V3<T> swo_p, swo_v;
             if (iteration == 1) {
               swo_p = V3<T>{T(tipx), T(tipy), T(tipz)};
@@ -1078,8 +1077,7 @@ template <class P, int D, bool FULL> struct Cycle {
               swo_p = ld3T(ss, LS::SWO_P);
               swo_v = ld3T(ss, LS::SWO_V);
             }
-            // Control nodes relative to the swing origin (generatePrimary/SecondarySwingControlNodes :1238-1291);
-            // only node differences enter quarticBezierDot, so the origin cancels.
+            // Control nodes relative to the swing origin (the origin cancels in the differences).
             V3<T> clr{T(0), T(0), ct.swing_height};
             if (!plane_flat) clr = normalized(ld3T(sp, RS_WPN)) * ct.swing_height;
             V3<T> tr = tgt - swo_p;
@@ -1088,44 +1086,43 @@ template <class P, int D, bool FULL> struct Cycle {
             V3<T> n2 = sep1 * T(2);
             V3<T> n3 = (mid + n2) * T(0.5);
             n3.z = mid.z;
-            V3<T> n4 = mid;
             V3<T> ftv = -stride * (stance_dt / ct.dt);
             V3<T> sep2 = ftv * (T(0.25) * (ct.dt / ct.swing_dt));
-            V3<T> m0 = n4;
             V3<T> m2 = tr - sep2 * T(2);
             V3<T> m1;
-            if (ci.force_normal_touchdown) {  // forceNormalTouchdown (:1314)
+            if (ci.force_normal_touchdown) {  // forceNormalTouchdown (:1314): n4 = m0 = bo, n3 = bo - h, m1 = bo + h
               V3<T> bo = tr - sep2 * T(4);
               bo.z = max_(T(0), tr.z);
               bo = bo + clr;
-              n4 = bo;
-              m0 = bo;
-              n3 = m0 - (m2 - bo) * T(0.5);
-              m1 = m0 + (m2 - bo) * T(0.5);
-            } else {
-              m1 = n4 - (n3 - n4);
+              Z = (m2 - bo) * T(0.5);
+              n3 = bo - Z;
+              m1 = bo + Z;
+            } else {  // n4 = m0 = mid, m1 = n4 - (n3 - n4)
+              Z = mid - n3;
+              m1 = mid + Z;
             }
-            if (first_half) {
-              T t = ct.swing_dt * T(iteration);
-              delta = quartic_bezier_dot(V3<T>{T(0), T(0), T(0)}, sep1, n2, n3, n4, t) * ct.swing_dt;
-            } else {
-              T t = ct.swing_dt * T(iteration - ci.swing_iterations / 2);
-              V3<T> m3 = tr - sep2;
-              delta = quartic_bezier_dot(m0, m1, m2, m3, tr, t) * ct.swing_dt;
-            }
+            X = first_half ? sep1 : sep2;
+            Y = first_half ? n3 - n2 : m2 - m1;
+            const T u = ct.swing_dt * T(first_half ? iteration : iteration - half);
+            bs = first_half ? T(1) - u : u;
+            bt = first_half ? u : T(1) - u;
+            bdt = ct.swing_dt;
           } else {  // STANCE / FORCE_STANCE
             int mod_start = standard ? ci.stance_start : ci.phase_offset[l];
             int iteration = phase - mod_start;  // mod(phase + (period - start), period) + 1, both in [0, period)
             iteration += iteration < 0 ? ci.period + 1 : 1;
             if (iteration == 1) st3(sl, LS::STO_P, V3<T>{T(tipx), T(tipy), T(tipz)});
             T scaler = standard ? T(1) : lt.stride_scaler_mod;
-            V3<T> sep = -stride * scaler * T(0.25);
-            // stance nodes are origin + k*sep (generateStanceControlNodes :1295): all four node differences are sep
-            T t = T(iteration) * stance_dt;
-            T s = T(1) - t;
-            T w = T(4) * s * s * s + T(12) * s * s * t + T(12) * s * t * t + T(4) * t * t * t;
-            delta = sep * w * stance_dt;
+            X = -stride * scaler * T(0.25);
+            Y = X;
+            Z = X;
+            bt = T(iteration) * stance_dt;
+            bs = T(1) - bt;
+            bdt = stance_dt;
           }
+          const T bss = bs * bs, btt = bt * bt;
+          const T w01 = T(4) * bss * (bs + T(3) * bt), w2 = T(12) * bs * btt, w3 = T(4) * btt * bt;
+          const V3<T> delta = (X * w01 + Y * w2 + Z * w3) * bdt;
           tipx += (double)delta.x;
           tipy += (double)delta.y;
           tipz += (double)delta.z;
@@ -1158,9 +1155,9 @@ template <class P, int D, bool FULL> struct Cycle {
       }
       // every lane has read what it needs from this slot: hand it back to the TMA unit for leg l + 2
       SHC_SYNCWARP();
-      if (SHC_LANE0(lane) && l + 2 < L) {
+      if (SHC_LANE0(lane) && l + kSlots < L) {
         fence_proxy_async_smem();
-        issue_leg(l + 2);
+        issue_leg(l + kSlots);
       }
       SHC_STAMP(6 + 3 * l);
       bits = (phase & 0xffff) | (step_state << 16) | ((at_correct ? 1 : 0) << 18) | ((completed ? 1 : 0) << 19) |

@@ -61,7 +61,7 @@ __global__ void SHC_KERNEL_BOUNDS control_cycle_kernel(const __grid_constant__ C
   const int robots = min(32, c.i.n_robots - tile_first);
   const int valid = robots * LD;
   const size_t base = (size_t)tile_first * LD;
-  const float* src = reinterpret_cast<const float*>(wsm + 2 * CY::slot_bytes(front));
+  const float* src = reinterpret_cast<const float*>(wsm + CY::kSlots * CY::slot_bytes(front));
   bool any_bulk = false;
   auto put = [&](float* dst) {
     // whole tiles go as one bulk store when the destination is 16-byte aligned (always, unless a shard's robot count makes
@@ -193,6 +193,7 @@ template <class F> static int dispatch_D(int D, F&& f) {
 // Fused gather: cycle k writes buffer k % B of every rank (B = 16); see shc_gather_step for the protocol.
 constexpr int kGatherBuffers = 16;
 constexpr int kGatherWaitEvery = 4;   // reuse check every 4th cycle, for the next 4 cycles
+constexpr size_t kMaxCachedGraphs = 16;
 constexpr int kHostChunks = 8;  // tile ranges of one shc_step_host call (kernel k+1 overlaps the D2H of range k)
 
 struct GraphKey {
@@ -398,6 +399,7 @@ int shc_create(const shc_config* cfg, const shc_startup* startup, int n_robots, 
   shc_engine* e = new shc_engine();
   e->device = device;
   core_init(e, *cfg, startup, n_robots, precision);
+  if (!check_step_cycle(e->su, err)) { delete e; return fail(SHC_E_UNSUPPORTED, err); }
 
   e->s_elem = precision == SHC_PRECISION_F64 ? 8 : 4;
   {
@@ -507,18 +509,29 @@ int shc_get_startup(const shc_engine* e, shc_startup* out) {
 }
 int shc_n_robots(const shc_engine* e) { return e ? e->n : 0; }
 int shc_options(const shc_engine* e) { return e ? e->options : 0; }
+// Captured rollouts bake the kernel arguments in (options, pose reset mode, efforts pointer): changing any of them drops
+// the cached graphs, so that the next shc_rollout captures the new values.
+static void drop_graphs(shc_engine* e) {
+  if (e->graphs.empty()) return;
+  cudaSetDevice(e->device);
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  e->graphs.clear();
+}
 int shc_set_options(shc_engine* e, int options) {
   if (!e) return fail(SHC_E_INVALID, "null engine");
+  if (options != e->options) drop_graphs(e);
   e->options = options;
   return SHC_OK;
 }
 int shc_set_pose_reset_mode(shc_engine* e, int mode) {
   if (!e || mode < 0 || mode > 5) return fail(SHC_E_INVALID, "bad pose reset mode");
+  if (mode != e->pose_reset_mode) drop_graphs(e);
   e->pose_reset_mode = mode;
   return SHC_OK;
 }
 int shc_set_joint_efforts(shc_engine* e, const float* efforts_dev) {
   if (!e) return fail(SHC_E_INVALID, "null engine");
+  if (efforts_dev != e->d_efforts) drop_graphs(e);
   e->d_efforts = efforts_dev;
   return SHC_OK;
 }
@@ -566,6 +579,7 @@ static StepIO make_io(shc_engine* e, const float* cmd, const float* imu, const f
 int shc_step(shc_engine* e, const float* cmd, const float* imu, const float* tip_force, const float* manual, float* joints_out,
              void* stream) {
   if (!e || !cmd || !joints_out) return fail(SHC_E_INVALID, "shc_step: cmd and joints_out are required");
+  CUDA_TRY(cudaSetDevice(e->device));
   return launch_cycle(e, make_io(e, cmd, imu, tip_force, manual, joints_out), stream ? (cudaStream_t)stream : e->stream);
 }
 
@@ -672,7 +686,6 @@ int shc_rollout(shc_engine* e, int k_cycles, const float* cmd_seq, const float* 
   auto it = e->graphs.find(key);
   if (it == e->graphs.end()) {
     const size_t n = e->n, L = e->cfg.leg_count;
-    cudaGraph_t graph;
     // capture on the engine's own stream (the legacy default stream cannot be captured), launch on the caller's
     cudaStream_t cap = e->stream;
     CUDA_TRY(cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed));
@@ -680,12 +693,19 @@ int shc_rollout(shc_engine* e, int k_cycles, const float* cmd_seq, const float* 
     for (int k = 0; k < k_cycles && rc == SHC_OK; ++k)
       rc = shc_step(e, cmd_seq + (size_t)k * n * 3, imu_seq ? imu_seq + (size_t)k * n * 10 : nullptr,
                     force_seq ? force_seq + (size_t)k * n * L * 3 : nullptr, nullptr, joints_out, cap);
+    cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamEndCapture(cap, &graph);
-    if (rc != SHC_OK) return rc;
-    if (ce != cudaSuccess) return fail(SHC_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+    if (rc != SHC_OK || ce != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      if (rc != SHC_OK) return rc;
+      return fail(SHC_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+    }
     cudaGraphExec_t exec;
-    CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+    cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return fail(SHC_E_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ie));
+    // a caller sliding a window over a long command buffer presents a new pointer set every call: keep the cache small
+    if (e->graphs.size() >= kMaxCachedGraphs) drop_graphs(e);
     it = e->graphs.emplace(key, exec).first;
   }
   CUDA_TRY(cudaGraphLaunch(it->second, st));
@@ -749,6 +769,7 @@ int shc_nccl_init(shc_engine* e, const void* uid128, int rank, int world_size) {
 int shc_allgather_joints(shc_engine* e, const float* local, float* full, void* stream) {
   if (!e || !local || !full) return fail(SHC_E_INVALID, "shc_allgather_joints: bad arguments");
   if (!e->nccl_comm) return fail(SHC_E_INVALID, "shc_nccl_init has not been called");
+  CUDA_TRY(cudaSetDevice(e->device));
   size_t count = (size_t)e->n * e->cfg.leg_count * e->cfg.joint_count;
   int rc = nccl().AllGather(local, full, count, /*ncclFloat32*/ 7, e->nccl_comm, stream ? (cudaStream_t)stream : e->side);
   if (rc != 0) return fail(SHC_E_CUDA, std::string("ncclAllGather: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error"));

@@ -310,6 +310,19 @@ inline bool check_supported(const shc_config& cfg, std::string& err, bool& unsup
   return true;
 }
 
+// The packed integer state (shc_layout.h) keeps the phase in 16 bits and the progress numerators in signed 16 bits: a
+// step cycle that does not fit (step_frequency below ~0.003 Hz at 50 Hz control rate; the reference allows 0.001) is
+// refused instead of silently aliasing phases.
+inline bool check_step_cycle(const shc_startup& su, std::string& err) {
+  if (su.period < 1 || su.period > 65535 || su.swing_period < 1 || su.swing_period > 32767 || su.stance_period < 0 ||
+      su.stance_period > 32767) {
+    err = "step cycle does not fit the packed phase / progress words (period <= 65535, swing and stance period <= 32767): "
+          "raise step_frequency or time_delta";
+    return false;
+  }
+  return true;
+}
+
 // Constants block + start-up results of an engine (host arithmetic only).  `startup` = null: the engine's own restatement
 // of the reference's start-up path (shc_host.cuh).
 template <class E> int core_init(E* e, const shc_config& cfg, const shc_startup* startup, int n_robots, int precision) {

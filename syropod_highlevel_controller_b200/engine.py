@@ -58,6 +58,12 @@ def lib():
         L.shc_nccl_init.argtypes = [vp, vp, C.c_int, C.c_int]
         L.shc_allgather_joints.argtypes = [vp, vp, vp, vp]
         L.shc_rollout_allgather.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+        L.shc_gather_bytes.argtypes = [vp, C.c_int]
+        L.shc_gather_bytes.restype = C.c_size_t
+        L.shc_gather_attach.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), vp]
+        L.shc_gather_step.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.shc_gather_sync.argtypes = [vp, C.POINTER(C.c_int), vp]
+        L.shc_gather_status.argtypes = [vp]
         L.shc_gather_alloc.argtypes = [vp, vp, C.POINTER(vp)]
         L.shc_gather_open_peer.argtypes = [vp, C.c_int, vp]
         L.shc_rollout_gather_fused.argtypes = [vp, C.c_int, vp, C.POINTER(C.c_int), vp]
@@ -193,6 +199,26 @@ class Engine:
         assert tuple(t.shape) == shape, (tuple(t.shape), shape)
         return t
 
+    def _out(self, out):
+        """The [N, L, D] float32 device tensor a kernel writes the joint angles to (the kernel trusts this pointer)."""
+        if out is None:
+            return self.joints
+        torch = self.torch
+        if not (isinstance(out, torch.Tensor) and out.is_cuda and out.device == self.device and out.dtype == torch.float32
+                and out.is_contiguous() and tuple(out.shape) == (self.n, self.L, self.D)):
+            raise ShcError(f"out must be a contiguous float32 tensor of shape {(self.n, self.L, self.D)} on {self.device}")
+        return out
+
+    def _seq(self, t, per_cycle_shape, k):
+        """A [k, ...] float32 per-cycle input sequence on this engine's device (or None)."""
+        if t is None:
+            return None
+        torch = self.torch
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.device == self.device and t.dtype == torch.float32
+                and t.is_contiguous() and tuple(t.shape) == (k,) + tuple(per_cycle_shape)):
+            raise ShcError(f"sequence must be a contiguous float32 tensor of shape {(k,) + tuple(per_cycle_shape)} on {self.device}")
+        return t
+
     def step(self, cmd, imu=None, tip_force=None, manual=None, out=None, stream=None):
         """One control cycle with device-resident inputs (torch CUDA tensors).  Asynchronous on `stream` (default:
         torch's current stream).  Returns the [N, L, D] float32 joint-angle tensor."""
@@ -201,7 +227,7 @@ class Engine:
         imu = self._f32(imu, (self.n, 10))
         tip_force = self._f32(tip_force, (self.n, self.L, 3))
         manual = self._f32(manual, (self.n, 6))
-        out = self.joints if out is None else out
+        out = self._out(out)
         _check(lib().shc_step(self._h, _ptr(cmd), _ptr(imu), _ptr(tip_force), _ptr(manual), _ptr(out),
                               _stream_handle(torch, self.device, stream)))
         self._keep = (cmd, imu, tip_force, manual)  # keep inputs alive until the launch has consumed them
@@ -241,8 +267,10 @@ class Engine:
         """k cycles with per-cycle device-resident inputs cmd_seq [k, N, 3]; one CUDA graph launch."""
         torch = self.torch
         k = int(cmd_seq.shape[0])
-        assert cmd_seq.is_cuda and cmd_seq.dtype == torch.float32 and cmd_seq.is_contiguous()
-        out = self.joints if out is None else out
+        cmd_seq = self._seq(cmd_seq, (self.n, 3), k)
+        imu_seq = self._seq(imu_seq, (self.n, 10), k)
+        force_seq = self._seq(force_seq, (self.n, self.L, 3), k)
+        out = self._out(out)
         _check(lib().shc_rollout(self._h, k, _ptr(cmd_seq), _ptr(imu_seq), _ptr(force_seq), _ptr(out),
                                  _stream_handle(torch, self.device, stream)))
         self._keep = (cmd_seq, imu_seq, force_seq)
@@ -265,58 +293,122 @@ class Engine:
         raw = bytes(uid.cpu().numpy().tobytes())
         _check(lib().shc_nccl_init(self._h, C.c_char_p(raw), rank, world_size))
         self.world_size = world_size
+        self._nccl_ready = True
 
     def rollout_allgather(self, cmd_seq, local2, full2, stream=None):
         """k cycles, each followed by the all-gather of its joint angles (overlapped, double buffered)."""
         torch = self.torch
         k = int(cmd_seq.shape[0])
-        assert cmd_seq.is_cuda and cmd_seq.dtype == torch.float32 and cmd_seq.is_contiguous()
+        cmd_seq = self._seq(cmd_seq, (self.n, 3), k)
+        per = self.n * self.L * self.D
+        for t, cnt in ((local2, 2 * per), (full2, 2 * per * self.world_size)):
+            if not (t.is_cuda and t.device == self.device and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == cnt):
+                raise ShcError("rollout_allgather: local2 / full2 must be contiguous float32 [2, n, L, D] / [2, world * n, L, D]")
         _check(lib().shc_rollout_allgather(self._h, k, _ptr(cmd_seq), _ptr(local2), _ptr(full2),
                                            _stream_handle(torch, self.device, stream)))
         self._keep = (cmd_seq, local2, full2)
 
-    def init_gather_fused(self, rank: int, world_size: int):
-        """Sets up the fused all-gather over peer memory (after init_nccl): allocates this rank's gather buffer, exchanges
-        the CUDA IPC handles through torch.distributed and maps every peer's buffer.  Returns the own buffer as a torch
-        tensor [buffers, world, n, L, D] (a view of library-owned device memory).  Collective: every rank must call it;
-        if any rank cannot allocate, export or map a buffer, every rank raises RuntimeError (so that callers can fall
-        back to the NCCL path together)."""
+    def init_gather_fused(self, rank: int, world_size: int, mode: str = "auto"):
+        """Sets up the fused all-gather over peer memory.  Collective: every rank must call it.
+
+        mode "auto": torch symmetric memory (torch.distributed._symmetric_memory) allocates one buffer per rank, maps every
+        rank's buffer on every rank and — when the fabric has NVLS — provides their NVSwitch multicast mapping, which the
+        kernel then stores to (one multimem.st per 16 bytes, replicated by the switch).  If symmetric memory is not
+        available on any rank, falls back to "ipc": engine-owned cudaMalloc buffers exchanged as CUDA-IPC handles (after
+        init_nccl), unicast TMA bulk stores.  "symm" / "symm-unicast" / "ipc" force one path.  If no path works on every rank,
+        every rank raises RuntimeError together (so that callers can fall back to the NCCL gather together).
+        Returns the own buffer as a torch tensor [buffers, world, n, L, D]; self.gather_mode says which path is live."""
         import torch.distributed as dist
 
         torch = self.torch
 
-        def agree(ok: bool, what: str):
+        def agree(ok: bool) -> bool:
             flag = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if int(flag.item()) == 0:
-                raise RuntimeError(f"fused gather unavailable on at least one rank ({what})")
+            return int(flag.item()) == 1
 
+        nb = int(lib().shc_gather_buffers())
+        shape = (nb, world_size, self.n, self.L, self.D)
+        n_data = nb * world_size * self.n * self.L * self.D
+        self.world_size = world_size
+        if mode in ("auto", "symm", "symm-unicast"):
+            ok, err, peers, mc, buf, hdl = True, "", [], 0, None, None
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                nbytes = int(lib().shc_gather_bytes(self._h, world_size))
+                buf = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=self.device)
+                hdl = symm_mem.rendezvous(buf, dist.group.WORLD.group_name)
+                peers = [int(p) for p in hdl.buffer_ptrs]
+                mc = int(hdl.multicast_ptr) if mode != "symm-unicast" else 0
+            except Exception as ex:  # noqa: BLE001 - any failure means "not available here"
+                ok, err = False, f"{type(ex).__name__}: {ex}"
+            if agree(ok):
+                use_mc = agree(mc != 0)  # multicast only if every rank has the mapping
+                arr = (C.c_void_p * world_size)(*peers)
+                rc = lib().shc_gather_attach(self._h, rank, world_size, arr, C.c_void_p(mc if use_mc else 0))
+                if not agree(rc == 0):
+                    raise RuntimeError("fused gather: shc_gather_attach failed on at least one rank")
+                dist.barrier()  # every rank's landed counters are zeroed before anyone's first cycle
+                self._gather_keep = (buf, hdl)
+                self.gather = buf[:n_data].view(shape)
+                self.gather_mode = "multicast (NVLS multimem.st)" if use_mc else "unicast (TMA bulk stores, symmetric memory)"
+                return self.gather
+            if mode != "auto":
+                raise RuntimeError(f"fused gather: torch symmetric memory unavailable on at least one rank ({err})")
+        if not hasattr(self, "_nccl_ready"):
+            self.init_nccl(rank, world_size)
         handle = (C.c_char * 64)()
-        buf = C.c_void_p()
-        rc = lib().shc_gather_alloc(self._h, handle, C.byref(buf))
-        agree(rc == 0, "shc_gather_alloc")
+        bufp = C.c_void_p()
+        rc = lib().shc_gather_alloc(self._h, handle, C.byref(bufp))
+        if not agree(rc == 0):
+            raise RuntimeError("fused gather unavailable on at least one rank (shc_gather_alloc)")
         handles = [None] * world_size
         dist.all_gather_object(handles, bytes(handle.raw))
         ok = True
         for p, hb in enumerate(handles):
             if p != rank and lib().shc_gather_open_peer(self._h, p, C.c_char_p(hb)) != 0:
                 ok = False
-        agree(ok, "shc_gather_open_peer")
-        nb = int(lib().shc_gather_buffers())
-        shape = (nb, world_size, self.n, self.L, self.D)
+        if not agree(ok):
+            raise RuntimeError("fused gather unavailable on at least one rank (shc_gather_open_peer)")
+        dist.barrier()
 
         class _Dev:  # __cuda_array_interface__ view of the library's buffer
-            __cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (int(buf.value), False), "version": 2}
+            __cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (int(bufp.value), False), "version": 2}
 
         self.gather = torch.as_tensor(_Dev(), device=self.device)
+        self.gather_mode = "unicast (TMA bulk stores, CUDA IPC)"
         return self.gather
 
+    def gather_step(self, cmd, imu=None, tip_force=None, manual=None, stream=None):
+        """One control cycle whose joint commands land in every rank's gather buffer (no wait: see gather_sync)."""
+        torch = self.torch
+        cmd = self._f32(cmd, (self.n, 3))
+        imu = self._f32(imu, (self.n, 10))
+        tip_force = self._f32(tip_force, (self.n, self.L, 3))
+        manual = self._f32(manual, (self.n, 6))
+        _check(lib().shc_gather_step(self._h, _ptr(cmd), _ptr(imu), _ptr(tip_force), _ptr(manual),
+                                     _stream_handle(torch, self.device, stream)))
+        self._keep = (cmd, imu, tip_force, manual)
+
+    def gather_sync(self, stream=None) -> int:
+        """The stream continues once every rank's shard of every cycle issued so far has landed here.  Returns the index
+        of the buffer that holds the last cycle."""
+        last = C.c_int(-1)
+        _check(lib().shc_gather_sync(self._h, C.byref(last), _stream_handle(self.torch, self.device, stream)))
+        return int(last.value)
+
+    def gather_status(self):
+        """Raises ShcError if a device-side wait for a peer gave up (a rank stopped signalling)."""
+        _check(lib().shc_gather_status(self._h))
+
     def rollout_gather_fused(self, cmd_seq, stream=None) -> int:
-        """k cycles whose joint commands land in every rank's gather buffer from inside the kernel (peer-memory stores over
-        NVLink).  Returns the index of the buffer that holds the last cycle."""
+        """k cycles whose joint commands land in every rank's gather buffer from inside the kernel (stores over NVLink),
+        then the wait for the last cycle.  Returns the index of the buffer that holds the last cycle."""
         torch = self.torch
         k = int(cmd_seq.shape[0])
         assert cmd_seq.is_cuda and cmd_seq.dtype == torch.float32 and cmd_seq.is_contiguous()
+        assert tuple(cmd_seq.shape[1:]) == (self.n, 3) and cmd_seq.device == self.device
         last = C.c_int(-1)
         _check(lib().shc_rollout_gather_fused(self._h, k, _ptr(cmd_seq), C.byref(last), _stream_handle(torch, self.device, stream)))
         self._keep = (cmd_seq,)

@@ -66,7 +66,7 @@ static void step_all(shc_emu* e, const StepIO& io_in) {
   const int tiles = (e->n + 31) / 32;
   for (int tile = 0; tile < tiles; ++tile) {
     for (int lane = 0; lane < 32; ++lane) CY::run(e->c, pl, tile, lane, io_in, wsm);
-    const float* src = reinterpret_cast<const float*>(wsm + 2 * CY::slot_bytes(front));
+    const float* src = reinterpret_cast<const float*>(wsm + CY::kSlots * CY::slot_bytes(front));
     const int robots = std::min(32, e->n - tile * 32);
     for (int k = 0; k < robots * LD; ++k) io_in.joints_out[(size_t)tile * 32 * LD + k] = src[k];
   }
@@ -82,6 +82,7 @@ int shc_emu_create(const shc_config* cfg, const shc_startup* startup, int n_robo
   if (!check_supported(*cfg, err, unsupported)) return fail(unsupported ? SHC_E_UNSUPPORTED : SHC_E_INVALID, err);
   shc_emu* e = new shc_emu();
   core_init(e, *cfg, startup, n_robots, precision);
+  if (!check_step_cycle(e->su, err)) { delete e; return fail(SHC_E_UNSUPPORTED, err); }
   const bool full = engine_full(e->cfg);
   const int front = full ? e->c.i.frontS_leg : 0;
   dispatch_D_raw(cfg->joint_count, [&](auto dtag) -> int {

@@ -211,7 +211,7 @@ def test_fused_gather_two_gpus():
            "--master-port", "29533", os.path.join(root, "tools", "dev_p2p_check.py"), "2065"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert out.stdout.count("-> OK") == 2
+    assert out.stdout.count("-> OK") >= 2 and "MISMATCH" not in out.stdout
 
 
 def test_host_entry_point_tile_ranges_and_pinned_buffers(shc_lib):
