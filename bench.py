@@ -272,9 +272,12 @@ def main():
             for i in range(lo, hi):
                 eng.step(*inputs(i))
         elif args.gather == "fused":
-            for i in range(lo, hi):
-                eng.gather_step(*inputs(i))
-            eng.gather_sync()
+            if octo:  # per-cycle IMU / tip-force frames: one C-ABI call per cycle, then the wait for the last one
+                for i in range(lo, hi):
+                    eng.gather_step(*inputs(i))
+                eng.gather_sync()
+            else:     # commands only: the whole rollout is one C-ABI call (k x shc_gather_step + shc_gather_sync)
+                eng.rollout_gather_fused(cmd_dev[lo:hi])
         else:
             if octo:
                 raise SystemExit("bench.py: --workload octopod with N > 1 needs --gather fused (the NCCL rollout carries commands only)")
@@ -288,6 +291,12 @@ def main():
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if world > 1:
+        # the host-side barrier above lets the ranks' processes leave up to a millisecond apart; a stream-ordered 1-element
+        # all-reduce makes the GPUs themselves start the timed region together (a rank's region cannot end before the
+        # slowest rank's last shard has landed, so start skew would be billed to the fastest rank)
+        align = torch.zeros(1, device=dev)
+        dist.all_reduce(align)
     ev0.record()
     run(pre + W, pre + W + K)
     ev1.record()
@@ -382,7 +391,7 @@ def main():
 
     if gather_ok is not None:
         line["gather_ok"] = gather_ok
-        line["gpu_launches"] = 2 * K + (K + 3) // 4 + 1  # control cycle + landed signal per step, reuse checks, final wait
+        line["gpu_launches"] = 2 * K + (K + 7) // 8 + 1  # control cycle + landed signal per step, reuse checks, final wait
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(cfg, os.cpu_count() or 1)

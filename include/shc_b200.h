@@ -144,7 +144,7 @@ int shc_rollout_allgather(shc_engine* e, int k_cycles, const float* cmd_seq, flo
  *   shc_gather_step          one control cycle (inputs as shc_step) into the next buffer.  Behind the kernel a one-warp
  *                            kernel on a high-priority side stream waits for the posted NVLink writes to drain and bumps
  *                            this rank's landed counter on every rank (multimem.red / st.release.sys), concurrently with
- *                            the next cycle; every 4th cycle a one-warp ld.acquire.sys spin kernel checks that no rank
+ *                            the next cycle; every 8th cycle a one-warp ld.acquire.sys spin kernel checks that no rank
  *                            is more than a buffer-reuse window behind (it normally passes at once).
  *   shc_gather_sync          `stream` continues once every rank's shard of every cycle issued so far has landed in this
  *                            rank's buffer; *last_buffer_out = buffer of the last cycle.

@@ -42,6 +42,9 @@ typedef struct shc_leg_state {
   double admittance_state[2];       /* admittance_state_ */
   double admittance_delta[3];       /* admittance_delta_ */
   double tip_force_calculated[3];   /* tip_force_calculated_ */
+  double virtual_stiffness;         /* virtual_stiffness_ (model.h:516): dynamic stiffness of AdmittanceController::
+                                     * updateStiffness (admittance_controller.cpp:96); only read by LegState.msg (trap 3);
+                                     * never initialised by the reference before the first update - 0 here */
   /* LegPoser auto-pose negation latch (pose_controller.h:575) */
   int negate_auto_pose;
   int pad0;

@@ -95,6 +95,7 @@ void exportState(const Robot& r, shc_robot_state* s) {
     o.admittance_state[1] = leg.admittance_state_[1];
     put3(o.admittance_delta, leg.admittance_delta_);
     put3(o.tip_force_calculated, leg.tip_force_calculated_);
+    o.virtual_stiffness = leg.virtual_stiffness_;
     o.negate_auto_pose = leg.poser.negate_auto_pose_;
     put3(o.model_tip_position, leg.current_tip_pose_.position_);
     put3(o.desired_tip_position, leg.desired_tip_pose_.position_);
@@ -162,6 +163,7 @@ void importState(Robot& r, const shc_robot_state* s) {
     leg.admittance_state_[1] = o.admittance_state[1];
     leg.admittance_delta_ = get3(o.admittance_delta);
     leg.tip_force_calculated_ = get3(o.tip_force_calculated);
+    leg.virtual_stiffness_ = o.virtual_stiffness;
     leg.poser.negate_auto_pose_ = o.negate_auto_pose != 0;
   }
 }

@@ -93,6 +93,7 @@ class ShcLegState(C.Structure):
         ("swing_progress", _d), ("stance_progress", _d),
         ("phase", _i), ("step_state", _i), ("at_correct_phase", _i), ("completed_first_step", _i),
         ("admittance_state", _d * 2), ("admittance_delta", _d * 3), ("tip_force_calculated", _d * 3),
+        ("virtual_stiffness", _d),
         ("negate_auto_pose", _i), ("pad0", _i),
         ("model_tip_position", _d * 3), ("desired_tip_position", _d * 3), ("ik_result", _d),
     ]

@@ -52,6 +52,7 @@ template <class R> struct RealConsts {
   R pid_p, pid_i, pid_d;
   R adm_P[4], adm_q[2];  // 30 RK4 steps of the virtual mass-spring-damper as one affine map x <- P x + q F (A.6)
   R force_gain;
+  R virtual_stiffness, swing_stiffness_scaler, load_stiffness_scaler;  // updateStiffness (admittance_controller.cpp:96)
   R body_velocity_scaler;  // bodyVelocityInputCallback (state_controller.cpp:1131)
   // auto posers (pose_controller.cpp:1338)
   R ap_pos[kMaxPosers][3], ap_rot[kMaxPosers][3], ap_gravity[kMaxPosers];
@@ -67,7 +68,7 @@ struct IntConsts {
   int phase_offset[kMaxLegs];
   int mod_stance_start[kMaxLegs];  // = phase offset
   // flags
-  int manual_posing, auto_posing, inclination_posing, imu_posing, admittance_control, use_joint_effort;
+  int manual_posing, auto_posing, inclination_posing, imu_posing, admittance_control, use_joint_effort, dynamic_stiffness;
   int clamp_joint_positions, clamp_joint_velocities, velocity_input_mode, force_normal_touchdown;
   // auto posing
   int n_posers, pose_phase_length, pose_normaliser, pose_sync, auto_ref_leg;

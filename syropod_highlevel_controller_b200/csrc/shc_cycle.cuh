@@ -110,6 +110,9 @@ __device__ __forceinline__ void bulk_commit_and_wait_read() {
 __device__ __forceinline__ void store_release_sys(int* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_release_sys_add(int* p, int v) {
+  asm volatile("red.release.sys.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ int load_acquire_sys(const int* p) {
   int v;
   asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -573,6 +576,8 @@ template <class P, int D, bool FULL> struct Cycle {
     }
     SHC_STAMP(2);
     int walk_state = rbits & 3;
+    // AdmittanceController::updateStiffness runs at the top of loop() when the walker is not STOPPED (state_controller.cpp:175)
+    const bool f_stiff = FULL && ci.dynamic_stiffness && walk_state != WALK_STOPPED;
     int legs_at_correct = (rbits >> 2) & 15;
     int legs_completed = (rbits >> 6) & 15;
     int rtd = (rbits >> 10) & 1;
@@ -944,6 +949,13 @@ template <class P, int D, bool FULL> struct Cycle {
       bool completed = (bits >> 19) & 1;
       bool negate = (bits >> 20) & 1;
       bool plane_saved = (bits >> LB_PLANE_SAVED) & 1;
+      if (f_stiff) {
+        // updateStiffness (admittance_controller.cpp:96) looks at every leg as the cycle found it: a swinging leg's own
+        // stiffness drops and its neighbours' rise with |tip z - default z| / swing height.  The per-leg reference is
+        // parked in the leg's stiffness plane and combined across legs behind the loop.
+        const K z_diff = K(tipz) - K(def.z);
+        sl[(LS::STIFF) * 32] = S(step_state == STEP_SWING ? abs_(z_diff / ck.swing_height) : K(-1));
+      }
       int swing_num = (int)(short)(prog & 0xffff);
       int stance_num = (int)(short)((prog >> 16) & 0xffff);
 
@@ -1233,6 +1245,43 @@ template <class P, int D, bool FULL> struct Cycle {
     // =================================================================================================================
     // 4. updateWalkPlane (:748) + odometry (:783)
     // =================================================================================================================
+    if (f_stiff) {
+      // reset every leg to the global stiffness, then in leg order: a swinging leg takes its swing stiffness and adds
+      // its load term to whatever its two neighbours hold at that point (a later swinging neighbour overwrites it)
+      K kk[kMaxLegs], ref[kMaxLegs];
+#pragma unroll
+      for (int l = 0; l < kMaxLegs; ++l) {
+        kk[l] = ck.virtual_stiffness;
+        ref[l] = K(-1);
+        if (l < L) ref[l] = K(sp[(ci.offS_leg + l * ci.strideS_leg + LS::STIFF) * 32]);
+      }
+#pragma unroll
+      for (int l = 0; l < kMaxLegs; ++l) {
+        if (l < L && ref[l] >= K(0)) {
+          const K swing_k = ck.virtual_stiffness * (ref[l] * (ck.swing_stiffness_scaler - K(1)) + K(1));
+          const K load_k = ck.virtual_stiffness * (ref[l] * (ck.load_stiffness_scaler - K(1)));
+          const int a1 = l == 0 ? L - 1 : l - 1, a2 = l == L - 1 ? 0 : l + 1;
+          // same order as the reference: both neighbours are read, then the three writes (so that legs coinciding on
+          // robots of one or two legs end with the value the reference ends with)
+          K c1 = K(0), c2 = K(0);
+#pragma unroll
+          for (int j = 0; j < kMaxLegs; ++j) {
+            if (j == a1) c1 = kk[j];
+            if (j == a2) c2 = kk[j];
+          }
+          kk[l] = swing_k;
+#pragma unroll
+          for (int j = 0; j < kMaxLegs; ++j) {
+            if (j == a1) kk[j] = c1 + load_k;
+            if (j == a2) kk[j] = c2 + load_k;
+          }
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < kMaxLegs; ++l)
+        if (l < L) sp[(ci.offS_leg + l * ci.strideS_leg + LS::STIFF) * 32] = S(kk[l]);
+    }
+
     // The plane is the least-squares fit of the legs' default tips, which only move when a stopping leg re-seats its
     // default tip (def_changed) — otherwise the fit of the previous cycle, already in HBM, is this cycle's result bit for
     // bit.  RB_PLANE_STALE (states written from outside) forces one fit.  A cycle without updateWalkPlane (trap 7)

@@ -101,15 +101,24 @@ __global__ void SHC_KERNEL_BOUNDS control_cycle_kernel(const __grid_constant__ C
 struct SignalArgs {
   int* flag[8];
   int* mc_flag;
-  int n, value;
+  int n;
+  unsigned long long* trace;  // tuning (SHC_GATHER_TRACE): globaltimer stamps of this launch, else null
 };
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __global__ void gather_signal_kernel(SignalArgs a) {
+  if (a.trace && threadIdx.x == 0) a.trace[1] = global_ns();
   if (a.mc_flag) {
     if (threadIdx.x == 0) multimem_red_release_add(a.mc_flag, 1);
   } else if (threadIdx.x < a.n) {
-    store_release_sys(a.flag[threadIdx.x], a.value);
+    red_release_sys_add(a.flag[threadIdx.x], 1);
   }
+  if (a.trace && threadIdx.x == 0) a.trace[2] = global_ns();
 }
+__global__ void gather_stamp_kernel(unsigned long long* slot) { *slot = global_ns(); }
 // Device-side wait on the local landed counters (ld.acquire.sys spin, one lane per source rank): the stream continues
 // once every source has landed `need[p]` cycles here.  Gives up after ~4 s (a peer died) and records it in *err instead of
 // hanging the GPU.
@@ -118,8 +127,10 @@ struct WaitArgs {
   int need[8];
   int n;
   int* err;
+  unsigned long long* trace;
 };
 __global__ void gather_wait_kernel(WaitArgs a) {
+  if (a.trace && threadIdx.x == 0) a.trace[0] = global_ns();
   if (threadIdx.x >= a.n) return;
   const int* f = a.flags + threadIdx.x;
   const long long t0 = clock64();
@@ -130,6 +141,7 @@ __global__ void gather_wait_kernel(WaitArgs a) {
       break;
     }
   }
+  if (a.trace) atomicMax(a.trace + 1, global_ns());
 }
 
 template <int D>
@@ -192,7 +204,7 @@ template <class F> static int dispatch_D(int D, F&& f) {
 
 // Fused gather: cycle k writes buffer k % B of every rank (B = 16); see shc_gather_step for the protocol.
 constexpr int kGatherBuffers = 16;
-constexpr int kGatherWaitEvery = 4;   // reuse check every 4th cycle, for the next 4 cycles
+constexpr int kGatherWaitEvery = 8;   // reuse check every 8th cycle, for the next 8 cycles
 constexpr size_t kMaxCachedGraphs = 16;
 constexpr int kHostChunks = 8;  // tile ranges of one shc_step_host call (kernel k+1 overlaps the D2H of range k)
 
@@ -252,6 +264,8 @@ struct shc_engine {
   bool gather_opened[8] = {false, false, false, false, false, false, false, false};
   int* gather_err = nullptr;  // mapped pinned word: set by a device-side wait that gave up
   cudaStream_t signal = nullptr;  // high-priority stream of the landed-signal kernels
+  unsigned long long* gather_trace = nullptr;  // tuning (SHC_GATHER_TRACE): mapped pinned stamps [4096][4]: kernel end, signal
+  long long gather_trace_waits = 0;            // start, signal end, -; waits from row 2048: start, end
   cudaEvent_t ev_kernel[kGatherBuffers] = {};  // "cycle's kernel done", for the side-stream signal kernels
   long long gather_cycle = 0;   // cycles issued (same on every rank)
   long long gather_waited = 0;  // every source is known to have landed at least this many cycles here
@@ -486,6 +500,7 @@ void shc_destroy(shc_engine* e) {
     if (e->gather_opened[p]) cudaIpcCloseMemHandle(e->gather_peer[p]);
   if (e->gather_owned) cudaFree(e->gather_own);
   if (e->gather_err) cudaFreeHost(e->gather_err);
+  if (e->gather_trace) cudaFreeHost(e->gather_trace);
   for (int b = 0; b < kGatherBuffers; ++b) {
     if (e->ev_kernel[b]) cudaEventDestroy(e->ev_kernel[b]);
   }
@@ -829,6 +844,10 @@ static int gather_common_init(shc_engine* e) {
   }
   e->gather_cycle = 0;
   e->gather_waited = 0;
+  if (getenv("SHC_GATHER_TRACE") && !e->gather_trace) {
+    CUDA_TRY(cudaHostAlloc((void**)&e->gather_trace, 4096 * 4 * 8, cudaHostAllocMapped));
+    std::memset(e->gather_trace, 0, 4096 * 4 * 8);
+  }
   return SHC_OK;
 }
 
@@ -909,6 +928,11 @@ static int gather_wait(shc_engine* e, long long need, cudaStream_t st) {
   for (int p = 0; p < 8; ++p) wa.need[p] = (int)need;
   wa.err = nullptr;
   if (cudaHostGetDevicePointer((void**)&wa.err, e->gather_err, 0) != cudaSuccess) { cudaGetLastError(); wa.err = nullptr; }
+  wa.trace = nullptr;
+  if (e->gather_trace && e->gather_trace_waits < 2048) {
+    e->gather_trace[(2048 + e->gather_trace_waits) * 4 + 2] = (unsigned long long)need;
+    wa.trace = e->gather_trace + (2048 + e->gather_trace_waits++) * 4;
+  }
   gather_wait_kernel<<<1, 32, 0, st>>>(wa);
   CUDA_TRY(cudaGetLastError());
   e->gather_waited = need;
@@ -937,18 +961,26 @@ int shc_gather_step(shc_engine* e, const float* cmd, const float* imu, const flo
     const long long need = cyc + kGatherWaitEvery - 1 - kGatherBuffers + 2;  // for the cycles cyc .. cyc + W - 1
     if (need > 0 && (rc = gather_wait(e, need, st)) != SHC_OK) return rc;
   }
+  // tuning switches (never set in production): SHC_GATHER_TUNE=nostore keeps the protocol but stores only locally,
+  // =nosignal stores everywhere but raises no landed signal (the waits then pass on the stale counters' timeout... so it
+  // also skips the waits): they separate the cost of the stores from the cost of the signalling
+  static const int tune = [] { const char* v = getenv("SHC_GATHER_TUNE"); return !v ? 0 : !strcmp(v, "nostore") ? 1 : !strcmp(v, "nosignal") ? 2 : 0; }();
   float* own_slot = e->gather_own + ((size_t)b * e->world + e->rank) * per_rank;
-  StepIO io = make_io(e, cmd, imu, tip_force, manual, e->gather_mc ? nullptr : own_slot);
+  const bool mc = e->gather_mc && tune != 1;
+  StepIO io = make_io(e, cmd, imu, tip_force, manual, mc ? nullptr : own_slot);
   io.gather_offset = (long long)(((size_t)b * e->world + e->rank) * per_rank);
-  io.gather_mc = e->gather_mc;
+  io.gather_mc = mc ? e->gather_mc : nullptr;
   io.n_gather = 0;
-  if (!e->gather_mc)
+  if (!e->gather_mc && tune != 1)
     for (int p = 0; p < e->world; ++p)
       if (p != e->rank) io.gather[io.n_gather++] = e->gather_peer[p];
   if ((rc = launch_cycle(e, io, st)) != SHC_OK) return rc;
+  if (tune == 2) { e->gather_cycle = cyc + 1; e->gather_waited = cyc + 1; return SHC_OK; }
+  if (e->gather_trace && cyc < 2048) gather_stamp_kernel<<<1, 1, 0, st>>>(e->gather_trace + cyc * 4);
   CUDA_TRY(cudaEventRecord(e->ev_kernel[b], st));
   CUDA_TRY(cudaStreamWaitEvent(e->signal, e->ev_kernel[b], 0));
   SignalArgs sa;
+  sa.trace = (e->gather_trace && cyc < 2048) ? e->gather_trace + cyc * 4 : nullptr;
   sa.n = 0;
   sa.mc_flag = nullptr;
   if (e->gather_mc) {
@@ -956,7 +988,6 @@ int shc_gather_step(shc_engine* e, const float* cmd, const float* imu, const flo
   } else {
     for (int p = 0; p < e->world; ++p) sa.flag[sa.n++] = gather_flags_of(e, p) + e->rank;  // own counter included
   }
-  sa.value = (int)(cyc + 1);
   gather_signal_kernel<<<1, 32, 0, e->signal>>>(sa);
   CUDA_TRY(cudaGetLastError());
   e->gather_cycle = cyc + 1;
@@ -973,6 +1004,10 @@ int shc_gather_sync(shc_engine* e, int* last_buffer_out, void* stream) {
   if (last_buffer_out) *last_buffer_out = e->gather_cycle > 0 ? (int)((e->gather_cycle - 1) % kGatherBuffers) : -1;
   return gather_wait(e, e->gather_cycle, st);
 }
+
+// Tuning (SHC_GATHER_TRACE=1): host pointer to the stamp table, [4096][4] u64 nanoseconds (rows 0..2047 per cycle: kernel
+// end, signal start, signal end; rows 2048.. per wait: start, end, cycles needed).
+unsigned long long* shc_gather_trace(shc_engine* e) { return e ? e->gather_trace : nullptr; }
 
 // 0 while every device-side wait has completed; SHC_E_CUDA once one gave up (a peer stopped signalling).
 int shc_gather_status(shc_engine* e) {

@@ -85,6 +85,9 @@ template <class R> void fill_static_consts(const shc_config& c, RealConsts<R>& k
   k.max_rotation_velocity = R(c.max_rotation_velocity);
   k.pid_p = R(c.rotation_pid_p); k.pid_i = R(c.rotation_pid_i); k.pid_d = R(c.rotation_pid_d);
   k.force_gain = R(c.force_gain);
+  k.virtual_stiffness = R(c.virtual_stiffness);
+  k.swing_stiffness_scaler = R(c.swing_stiffness_scaler);
+  k.load_stiffness_scaler = R(c.load_stiffness_scaler);
   k.body_velocity_scaler = R(c.body_velocity_scaler);
   for (int a = 0; a < c.auto_poser_count; ++a) {
     k.ap_pos[a][0] = R(c.x_amplitudes[a]); k.ap_pos[a][1] = R(c.y_amplitudes[a]); k.ap_pos[a][2] = R(c.z_amplitudes[a]);

@@ -49,18 +49,19 @@ template <int D> struct LegS {
     WP = 2 * D + 21,     // walk_plane_ (saved)
     WPN = 2 * D + 24,    // walk_plane_normal_ (saved)
     COUNT = 2 * D + 27,
-    ADM_DELTA = COUNT    // admittance_delta_ (3), appended when the admittance block is present
+    ADM_DELTA = COUNT,   // admittance_delta_ (3), appended when the admittance block is present
+    STIFF = COUNT + 3    // virtual_stiffness_ (dynamic stiffness, admittance_controller.cpp:96), same block
   };
 };
 // the same offsets for host code that knows D only at run time (pack)
 struct LegOff {
-  int Q, QD, DEF, STRIDE, SWO_P, SWO_V, STAGED, TIPVEL, STO_P, TGT, WP, WPN, COUNT, ADM_X, ADM_FORCE, ADM_DELTA;
+  int Q, QD, DEF, STRIDE, SWO_P, SWO_V, STAGED, TIPVEL, STO_P, TGT, WP, WPN, COUNT, ADM_X, ADM_FORCE, ADM_DELTA, STIFF;
   explicit LegOff(int D)
       : Q(0), QD(D), DEF(2 * D), STRIDE(2 * D + 3), SWO_P(2 * D + 6), SWO_V(2 * D + 9), STAGED(2 * D + 12), TIPVEL(2 * D + 12),
         STO_P(2 * D + 15), TGT(2 * D + 18), WP(2 * D + 21), WPN(2 * D + 24), COUNT(2 * D + 27), ADM_X(-5), ADM_FORCE(-3),
-        ADM_DELTA(2 * D + 27) {}
+        ADM_DELTA(2 * D + 27), STIFF(2 * D + 30) {}
 };
-enum : int { ADM_COUNT = 8 };  // planes of the optional per-leg admittance block (5 in front + 3 appended)
+enum : int { ADM_COUNT = 9 };  // planes of the optional per-leg admittance block (5 in front + 4 appended)
 
 // double planes
 enum : int { RD_ODOMP = 0 /*odometry_ideal_.position_ (3)*/, RD_COUNT = 3 };

@@ -44,6 +44,7 @@ inline void layout(const shc_config& cfg, int n, IntConsts& ci) {
   ci.inclination_posing = cfg.inclination_posing;
   ci.imu_posing = cfg.imu_posing;
   ci.admittance_control = cfg.admittance_control;
+  ci.dynamic_stiffness = cfg.admittance_control && cfg.dynamic_stiffness;
   ci.use_joint_effort = cfg.use_joint_effort;
   ci.clamp_joint_positions = cfg.clamp_joint_positions;
   ci.clamp_joint_velocities = cfg.clamp_joint_velocities;
@@ -153,6 +154,7 @@ template <class E> void pack(const E* e, const shc_robot_state* in, size_t n, Ho
           S(sb + lo.ADM_DELTA + k, r) = g.admittance_delta[k];
           S(sb + lo.ADM_FORCE + k, r) = g.tip_force_calculated[k];
         }
+        S(sb + lo.STIFF, r) = g.virtual_stiffness;
       }
       const int ib = ci.offI_leg + l * ci.strideI_leg;
       I(ib + LI_BITS, r) = (g.phase & 0xffff) | ((g.step_state & 3) << 16) | ((g.at_correct_phase ? 1 : 0) << 18) |
@@ -255,6 +257,7 @@ template <int D, class E> void unpack(const E* e, const HostPlanes& h, shc_robot
           g.admittance_delta[k] = S(sb + LS::ADM_DELTA + k, r);
           g.tip_force_calculated[k] = S(sb + LS::ADM_FORCE + k, r);
         }
+        g.virtual_stiffness = S(sb + LS::STIFF, r);
       }
       const int ib = ci.offI_leg + l * ci.strideI_leg;
       int b = I(ib + LI_BITS, r), pg = I(ib + LI_PROG, r);

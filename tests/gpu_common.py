@@ -8,7 +8,7 @@ INT_FIELDS_ROBOT = ("walk_state", "legs_at_correct_phase", "legs_completed_first
                     "pose_state", "auto_posing_state")
 STATE_FIELDS_LEG = ("tip_position", "tip_velocity", "swing_origin_position", "stance_origin_position",
                     "default_tip_position", "target_tip_position", "stride_vector", "walk_plane", "walk_plane_normal",
-                    "admittance_state", "admittance_delta", "tip_force_calculated", "model_tip_position")
+                    "admittance_state", "admittance_delta", "tip_force_calculated", "virtual_stiffness", "model_tip_position")
 INT_FIELDS_LEG = ("phase", "step_state", "at_correct_phase", "completed_first_step", "negate_auto_pose")
 
 
@@ -32,7 +32,8 @@ def state_diff(se, so, L, D):
             upd("joint_position", list(la.joint_position)[:D], list(lb.joint_position)[:D])
             upd("joint_velocity", list(la.joint_velocity)[:D], list(lb.joint_velocity)[:D])
             for f in STATE_FIELDS_LEG:
-                upd(f, list(getattr(la, f)), list(getattr(lb, f)))
+                va, vb = getattr(la, f), getattr(lb, f)
+                upd(f, va if isinstance(va, float) else list(va), vb if isinstance(vb, float) else list(vb))
             upd("swing_progress", la.swing_progress, lb.swing_progress)
             upd("stance_progress", la.stance_progress, lb.stance_progress)
             for f in INT_FIELDS_LEG:
