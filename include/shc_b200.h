@@ -82,6 +82,14 @@ int shc_set_pose_reset_mode(shc_engine* e, int mode);
  * Replaces the reference's getters over Model/Leg/LegStepper/PoseController members (state_controller.cpp:809-1078). */
 int shc_get_state(shc_engine* e, shc_robot_state* out, size_t n_records);
 int shc_set_state(shc_engine* e, const shc_robot_state* in, size_t n_records);
+/* Records of the robots [first, first + count) only: three small device->host copies however large the batch is (what the
+ * facade's per-robot getters use). */
+int shc_get_state_range(shc_engine* e, size_t first, size_t count, shc_robot_state* out);
+/* WalkController::set{LinearSpeed,AngularSpeed,LinearAcceleration,AngularAcceleration}LimitMap (walk_controller.h:126-141):
+ * replaces the limit tables getLimit (walk_controller.cpp:414) reads, 9 values each (bearings 0..360 step 45); NULL keeps a
+ * table.  From the next cycle on. */
+int shc_set_limit_maps(shc_engine* e, const double* max_linear_speed, const double* max_angular_speed,
+                       const double* max_linear_acceleration, const double* max_angular_acceleration);
 
 /* ONE control cycle for every robot = StateController::loop() in RUNNING state (state_controller.cpp:162-193):
  *   PoseController::updateCurrentPose -> WalkController::setPoseState -> [AdmittanceController::updateStiffness,

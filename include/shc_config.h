@@ -123,6 +123,9 @@ typedef struct shc_startup {
   /* auto-pose cycle (pose_controller.cpp:44-63) */
   int pose_phase_length, pose_normaliser;
   int auto_pose_reference_leg;
+  /* number of StateController::loop() calls the direct start-up takes until READY (state_controller.cpp:254-281,
+   * pose_controller.cpp:463): an auto poser with its own cycle (pose_frequency != -1) keeps cycling through them */
+  int startup_loops;
 } shc_startup;
 
 #ifdef __cplusplus

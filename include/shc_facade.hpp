@@ -6,8 +6,8 @@
 // StateController holds: Model, WalkController, PoseController, AdmittanceController.  The per-cycle methods record
 // their inputs; the last call of the cycle, Model::updateModel(), runs ONE fused control-cycle launch for the whole
 // batch once every robot of the batch has reached it (immediately for N = 1), through shc_step_host.  Getters read a
-// lazily refreshed host copy of the state (shc_get_state), replacing the member reads of the reference's publishers
-// (state_controller.cpp:777-1078).  Eigen is not required: Vector2d/Vector3d/Quaterniond/Pose below are plain structs
+// host copy of ONE robot's record, fetched on first use after a cycle (shc_get_state_range: three small copies however
+// large the batch is), replacing the member reads of the reference's publishers (state_controller.cpp:777-1078).  Eigen is not required: Vector2d/Vector3d/Quaterniond/Pose below are plain structs
 // with the member names the reference code uses (position_, rotation_, x(), w() ...).
 //
 // Reference interfaces mirrored (file:line under the reference tree):
@@ -16,6 +16,7 @@
 //   WalkController   walk_controller.h:54-277          LegStepper  walk_controller.h:286-535
 //   PoseController   pose_controller.h:36-321          AdmittanceController  admittance_controller.h
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <memory>
@@ -103,8 +104,20 @@ class LegStepper {  // walk_controller.h:286 — read-only view
   inline double getStanceProgress();
   inline bool hasCompletedFirstStep();
   inline bool isAtCorrectPhase();
+  inline Pose getIdentityTipPose();  // walk_controller.h:323 (stance position of the leg, rotation undefined)
+  inline Vector3d getSwingOriginTipPosition();
+  inline Vector3d getSwingOriginTipVelocity();
+  inline Vector3d getStanceOriginTipPosition();
+  /// Control nodes of the leg's quartic Beziers (walk_controller.h:327-333), i = 0..4, rebuilt from the leg's record with
+  /// the reference's formulas (generatePrimary/SecondarySwingControlNodes :1238-1291, generateStanceControlNodes :1295).
+  /// The reference regenerates them every cycle the leg is on that curve and keeps the last set otherwise (RViz shows
+  /// stale nodes of the other curve); here they are always those of the leg's CURRENT record.
+  inline Vector3d getSwing1ControlNode(int i);
+  inline Vector3d getSwing2ControlNode(int i);
+  inline Vector3d getStanceControlNode(int i);
 
  private:
+  inline void swingNodes(Vector3d n1[5], Vector3d n2[5]);
   Batch* b_;
   int robot_, leg_;
 };
@@ -121,6 +134,7 @@ class Leg {  // model.h:196
   inline Pose getDesiredTipPose();
   inline Vector3d getAdmittanceDelta();
   inline Vector3d getTipForceCalculated();
+  inline double getVirtualStiffness();  // model.h:264 (dynamic stiffness of AdmittanceController::updateStiffness)
   inline void setTipForceMeasured(const Vector3d& f);  // tipStatesCallback (state_controller.cpp:1645)
 
  private:
@@ -170,6 +184,18 @@ class WalkController {  // walk_controller.h:54
   inline double getTimeDelta() const;
   inline double getStepClearance() const;
   inline double getBodyClearance() const;
+  /// WalkController::getLimit (walk_controller.cpp:414) on the robot's current tips and limit tables.
+  inline double getLimit(const Vector2d& linear_velocity_input, const double& angular_velocity_input,
+                         const std::array<double, SHC_N_BEARINGS>& limit);
+  inline std::array<double, SHC_N_BEARINGS> getLinearSpeedLimitMap();
+  inline std::array<double, SHC_N_BEARINGS> getAngularSpeedLimitMap();
+  inline std::array<double, SHC_N_BEARINGS> getLinearAccelerationLimitMap();
+  inline std::array<double, SHC_N_BEARINGS> getAngularAccelerationLimitMap();
+  /// walk_controller.h:126-141 — batch-wide in the engine (every robot shares the constants block)
+  inline void setLinearSpeedLimitMap(const std::array<double, SHC_N_BEARINGS>& m);
+  inline void setAngularSpeedLimitMap(const std::array<double, SHC_N_BEARINGS>& m);
+  inline void setLinearAccelerationLimitMap(const std::array<double, SHC_N_BEARINGS>& m);
+  inline void setAngularAccelerationLimitMap(const std::array<double, SHC_N_BEARINGS>& m);
 
  private:
   Batch* b_;
@@ -189,6 +215,10 @@ class PoseController {  // pose_controller.h:36
   inline Pose getAutoPose();
   inline Vector3d getRotationAbsementError();
   inline Vector3d getRotationVelocityError();
+  inline Pose getWalkPlanePose();
+  inline Pose getManualPose();
+  inline Pose getImuPose();
+  inline Pose getInclinationPose();
 
  private:
   Batch* b_;
@@ -199,7 +229,8 @@ class AdmittanceController {  // admittance_controller.h
  public:
   AdmittanceController(Batch* b, int robot) : b_(b), robot_(robot) {}
   void updateAdmittance() {}                            // admittance_controller.cpp:22, inside the fused cycle
-  void updateStiffness(std::shared_ptr<WalkController>) {}  // :96 — only feeds LegState.msg in the reference (trap 3)
+  void updateStiffness(std::shared_ptr<WalkController>) {}  // :96, inside the fused cycle (dynamic_stiffness); read it
+                                                            // back with Leg::getVirtualStiffness
 
  private:
   Batch* b_;
@@ -226,6 +257,7 @@ class Batch {
     joints_.assign(size_t(n_) * L * D, 0.f);
     reached_.assign(n_, 0);
     state_.resize(n_);
+    fetched_.assign(n_, -1);
     for (int r = 0; r < n_; ++r) {
       Controllers c;
       c.model_ = std::make_shared<Model>(this, r);
@@ -234,7 +266,6 @@ class Batch {
       c.admittance_ = std::make_shared<AdmittanceController>(this, r);
       robots_.push_back(c);
     }
-    refresh();
   }
   ~Batch() { shc_destroy(e_); }
   Batch(const Batch&) = delete;
@@ -284,12 +315,20 @@ class Batch {
       throw std::runtime_error(std::string("shc_step_host: ") + shc_last_error());
     std::fill(reached_.begin(), reached_.end(), 0);
     arrived_ = 0;
-    stale_ = true;
     ++cycles_;
   }
+  /// Record of robot r as of the last cycle: fetched from the device the first time it is asked for after a cycle.
   const shc_robot_state& state(int r) {
-    if (stale_) refresh();
+    if (fetched_.at(r) != cycles_) {
+      if (shc_get_state_range(e_, size_t(r), 1, &state_[r]) != SHC_OK)
+        throw std::runtime_error(std::string("shc_get_state_range: ") + shc_last_error());
+      fetched_[r] = cycles_;
+    }
     return state_[r];
+  }
+  void setLimitMaps(const double* ls, const double* as, const double* la, const double* aa) {
+    if (shc_set_limit_maps(e_, ls, as, la, aa) != SHC_OK) throw std::runtime_error(std::string("shc_set_limit_maps: ") + shc_last_error());
+    have_startup_ = false;
   }
   const shc_startup& startup() {
     if (!have_startup_) { shc_get_startup(e_, &startup_); have_startup_ = true; }
@@ -298,11 +337,6 @@ class Batch {
   long cycles() const { return cycles_; }
 
  private:
-  void refresh() {
-    if (shc_get_state(e_, state_.data(), state_.size()) != SHC_OK)
-      throw std::runtime_error(std::string("shc_get_state: ") + shc_last_error());
-    stale_ = false;
-  }
   Parameters params_;
   int n_;
   shc_engine* e_ = nullptr;
@@ -311,7 +345,8 @@ class Batch {
   std::vector<char> reached_;
   int arrived_ = 0;
   std::vector<shc_robot_state> state_;
-  bool stale_ = true, have_startup_ = false;
+  std::vector<long> fetched_;  // cycle count at which state_[r] was fetched (-1: never)
+  bool have_startup_ = false;
   shc_startup startup_;
   long cycles_ = 0;
 };
@@ -341,6 +376,7 @@ inline Pose Leg::getCurrentTipPose() { Pose p; p.position_ = Vector3d(b_->state(
 inline Pose Leg::getDesiredTipPose() { Pose p; p.position_ = Vector3d(b_->state(robot_).legs[leg_].desired_tip_position); return p; }
 inline Vector3d Leg::getAdmittanceDelta() { return Vector3d(b_->state(robot_).legs[leg_].admittance_delta); }
 inline Vector3d Leg::getTipForceCalculated() { return Vector3d(b_->state(robot_).legs[leg_].tip_force_calculated); }
+inline double Leg::getVirtualStiffness() { return b_->state(robot_).legs[leg_].virtual_stiffness; }
 inline void Leg::setTipForceMeasured(const Vector3d& f) { b_->setTipForce(robot_, leg_, f); }
 
 inline Model::Model(Batch* b, int robot) : b_(b), robot_(robot) {
@@ -365,6 +401,82 @@ inline double LegStepper::getStanceProgress() { return b_->state(robot_).legs[le
 inline bool LegStepper::hasCompletedFirstStep() { return b_->state(robot_).legs[leg_].completed_first_step != 0; }
 inline bool LegStepper::isAtCorrectPhase() { return b_->state(robot_).legs[leg_].at_correct_phase != 0; }
 
+inline Pose LegStepper::getIdentityTipPose() {
+  Pose p;
+  p.position_ = Vector3d(b_->params().cfg.stance_x[leg_], b_->params().cfg.stance_y[leg_], 0.0);
+  p.rotation_ = Quaterniond(0, 0, 0, 0);
+  return p;
+}
+inline Vector3d LegStepper::getSwingOriginTipPosition() { return Vector3d(b_->state(robot_).legs[leg_].swing_origin_position); }
+inline Vector3d LegStepper::getSwingOriginTipVelocity() { return Vector3d(b_->state(robot_).legs[leg_].swing_origin_velocity); }
+inline Vector3d LegStepper::getStanceOriginTipPosition() { return Vector3d(b_->state(robot_).legs[leg_].stance_origin_position); }
+inline void LegStepper::swingNodes(Vector3d n1[5], Vector3d n2[5]) {
+  const shc_config& c = b_->params().cfg;
+  const shc_startup& su = b_->startup();
+  const shc_robot_state& rs = b_->state(robot_);
+  const shc_leg_state& g = rs.legs[leg_];
+  const double dt = c.time_delta;
+  // LegStepper::updateTipPosition (walk_controller.cpp:1035-1041): iteration counts in double, as written there
+  int swing_iterations = int((double(su.swing_period) / su.period) / (su.step_frequency * dt));
+  swing_iterations = (swing_iterations % 2 == 0) ? swing_iterations : swing_iterations + 1;
+  const double swing_dt = 1.0 / (swing_iterations / 2.0);
+  const bool standard = g.step_state == SWING || g.completed_first_step;
+  int stance_period = standard ? ((su.stance_end - su.stance_start) % su.period + su.period) % su.period
+                               : ((su.stance_end - su.phase_offsets[leg_]) % su.period + su.period) % su.period;
+  if (stance_period == 0) stance_period = su.period;
+  const int stance_iterations = int((double(stance_period) / su.period) / (su.step_frequency * dt));
+  const double stance_dt = 1.0 / stance_iterations;
+  auto V = [](const double* p) { return Vector3d(p); };
+  auto add = [](Vector3d a, Vector3d b) { return Vector3d(a[0] + b[0], a[1] + b[1], a[2] + b[2]); };
+  auto sub = [](Vector3d a, Vector3d b) { return Vector3d(a[0] - b[0], a[1] - b[1], a[2] - b[2]); };
+  auto mul = [](Vector3d a, double k) { return Vector3d(a[0] * k, a[1] * k, a[2] * k); };
+  Vector3d nrm = V(g.walk_plane_normal);
+  const double nn = nrm.norm();
+  if (nn > 0) nrm = mul(nrm, 1.0 / nn);
+  const Vector3d clearance = mul(nrm, c.swing_height);  // updateStride (:944)
+  const Vector3d origin = V(g.swing_origin_position), target = V(g.target_tip_position);
+  Vector3d mid = mul(add(origin, target), 0.5);
+  mid[2] = std::max(origin[2], target[2]);
+  mid = add(mid, clearance);
+  mid[1] += (c.stance_y[leg_] > 0 ? 1.0 : -1.0) * c.swing_width;
+  const Vector3d sep1 = mul(V(g.swing_origin_velocity), 0.25 * (dt / swing_dt));
+  n1[0] = origin;
+  n1[1] = add(origin, sep1);
+  n1[2] = add(origin, mul(sep1, 2.0));
+  n1[3] = mul(add(mid, n1[2]), 0.5);
+  n1[3][2] = mid[2];
+  n1[4] = mid;
+  const Vector3d final_tip_velocity = mul(V(g.stride_vector), -(stance_dt / dt));
+  const Vector3d sep2 = mul(final_tip_velocity, 0.25 * (dt / swing_dt));
+  n2[0] = n1[4];
+  n2[1] = sub(n1[4], sub(n1[3], n1[4]));
+  n2[2] = sub(target, mul(sep2, 2.0));
+  n2[3] = sub(target, sep2);
+  n2[4] = target;
+  if (c.force_normal_touchdown) {  // forceNormalTouchdown (:1314)
+    Vector3d bo = sub(target, mul(sep2, 4.0));
+    bo[2] = std::max(origin[2], target[2]);
+    bo = add(bo, clearance);
+    n1[4] = bo;
+    n2[0] = bo;
+    n1[3] = sub(n2[0], mul(sub(n2[2], bo), 0.5));
+    n2[1] = add(n2[0], mul(sub(n2[2], bo), 0.5));
+  }
+}
+inline Vector3d LegStepper::getSwing1ControlNode(int i) { Vector3d a[5], b[5]; swingNodes(a, b); return a[i]; }
+inline Vector3d LegStepper::getSwing2ControlNode(int i) { Vector3d a[5], b[5]; swingNodes(a, b); return b[i]; }
+inline Vector3d LegStepper::getStanceControlNode(int i) {
+  const shc_startup& su = b_->startup();
+  const shc_leg_state& g = b_->state(robot_).legs[leg_];
+  const bool standard = g.step_state == SWING || g.completed_first_step;
+  const int std_period = ((su.stance_end - su.stance_start) % su.period + su.period) % su.period;
+  int mod_period = ((su.stance_end - su.phase_offsets[leg_]) % su.period + su.period) % su.period;
+  if (mod_period == 0) mod_period = su.period;
+  const double scaler = standard ? 1.0 : double(mod_period) / std_period;
+  Vector3d o(g.stance_origin_position), st(g.stride_vector);
+  return Vector3d(o[0] - st[0] * scaler * 0.25 * i, o[1] - st[1] * scaler * 0.25 * i, o[2] - st[2] * scaler * 0.25 * i);
+}
+
 inline void WalkController::updateWalk(const Vector2d& lin, const double& ang) { b_->setCommand(robot_, lin[0], lin[1], ang); }
 inline WalkState WalkController::getWalkState() { return WalkState(b_->state(robot_).walk_state); }
 inline Vector2d WalkController::getDesiredLinearVelocity() { const auto& s = b_->state(robot_); return Vector2d(s.desired_linear_velocity[0], s.desired_linear_velocity[1]); }
@@ -385,11 +497,41 @@ inline double WalkController::getTimeDelta() const { return b_->params().cfg.tim
 inline double WalkController::getStepClearance() const { return b_->params().cfg.swing_height; }
 inline double WalkController::getBodyClearance() const { return b_->params().cfg.body_clearance; }
 
+inline double WalkController::getLimit(const Vector2d& lin, const double& ang, const std::array<double, SHC_N_BEARINGS>& limit) {
+  const shc_robot_state& s = b_->state(robot_);
+  double min_limit = 2147483647.0;  // UNASSIGNED_VALUE
+  const double pi = 3.14159265358979323846;
+  for (int l = 0; l < b_->params().cfg.leg_count; ++l) {
+    const double* tip = s.legs[l].tip_position;
+    const double sx = lin[0] + ang * (-tip[1]), sy = lin[1] + ang * tip[0];
+    const double deg = std::atan2(sy, sx) / pi * 180.0;
+    int bearing = int(deg >= 0 ? deg + 0.5 : -(0.5 - deg));          // roundToInt
+    bearing = ((bearing % 360) + 360) % 360;                           // mod
+    const int lower = bearing / 45 * 45, upper = lower + 45;
+    // interpolation with int / int (trap 1): the weight is 0, the result the lower bucket's value
+    const double v = limit[lower / 45] + (bearing - lower) / (upper - lower) * (limit[upper / 45 % SHC_N_BEARINGS] - limit[lower / 45]);
+    min_limit = std::min(min_limit, v);
+  }
+  return min_limit;
+}
+inline std::array<double, SHC_N_BEARINGS> WalkController::getLinearSpeedLimitMap() { std::array<double, SHC_N_BEARINGS> m; for (int i = 0; i < SHC_N_BEARINGS; ++i) m[i] = b_->startup().max_linear_speed[i]; return m; }
+inline std::array<double, SHC_N_BEARINGS> WalkController::getAngularSpeedLimitMap() { std::array<double, SHC_N_BEARINGS> m; for (int i = 0; i < SHC_N_BEARINGS; ++i) m[i] = b_->startup().max_angular_speed[i]; return m; }
+inline std::array<double, SHC_N_BEARINGS> WalkController::getLinearAccelerationLimitMap() { std::array<double, SHC_N_BEARINGS> m; for (int i = 0; i < SHC_N_BEARINGS; ++i) m[i] = b_->startup().max_linear_acceleration[i]; return m; }
+inline std::array<double, SHC_N_BEARINGS> WalkController::getAngularAccelerationLimitMap() { std::array<double, SHC_N_BEARINGS> m; for (int i = 0; i < SHC_N_BEARINGS; ++i) m[i] = b_->startup().max_angular_acceleration[i]; return m; }
+inline void WalkController::setLinearSpeedLimitMap(const std::array<double, SHC_N_BEARINGS>& m) { b_->setLimitMaps(m.data(), nullptr, nullptr, nullptr); }
+inline void WalkController::setAngularSpeedLimitMap(const std::array<double, SHC_N_BEARINGS>& m) { b_->setLimitMaps(nullptr, m.data(), nullptr, nullptr); }
+inline void WalkController::setLinearAccelerationLimitMap(const std::array<double, SHC_N_BEARINGS>& m) { b_->setLimitMaps(nullptr, nullptr, m.data(), nullptr); }
+inline void WalkController::setAngularAccelerationLimitMap(const std::array<double, SHC_N_BEARINGS>& m) { b_->setLimitMaps(nullptr, nullptr, nullptr, m.data()); }
+
 inline void PoseController::setManualPoseInput(const Vector3d& t, const Vector3d& r) { b_->setManual(robot_, t, r); }
 inline void PoseController::setPoseResetMode(const PoseResetMode& mode) { b_->setPoseResetMode(int(mode)); }
 inline PosingState PoseController::getAutoPoseState() { return PosingState(b_->state(robot_).auto_posing_state); }
 inline Pose PoseController::getAutoPose() { return Pose(b_->state(robot_).auto_pose); }
 inline Vector3d PoseController::getRotationAbsementError() { return Vector3d(b_->state(robot_).rotation_absement_error); }
 inline Vector3d PoseController::getRotationVelocityError() { return Vector3d(b_->state(robot_).rotation_velocity_error); }
+inline Pose PoseController::getWalkPlanePose() { return Pose(b_->state(robot_).walk_plane_pose); }
+inline Pose PoseController::getManualPose() { return Pose(b_->state(robot_).manual_pose); }
+inline Pose PoseController::getImuPose() { return Pose(b_->state(robot_).imu_pose); }
+inline Pose PoseController::getInclinationPose() { return Pose(b_->state(robot_).inclination_pose); }
 
 }  // namespace shc_b200

@@ -252,7 +252,10 @@ void shc_oracle_batch_destroy(void* h) {
 int shc_oracle_batch_size(void* h) { return int(static_cast<Batch*>(h)->robots.size()); }
 int shc_oracle_startup_loops(void* h) { return static_cast<Batch*>(h)->startup_loops; }
 
-void shc_oracle_get_startup(void* h, shc_startup* out) { fillStartup(*static_cast<Batch*>(h)->robots[0], out); }
+void shc_oracle_get_startup(void* h, shc_startup* out) {
+  fillStartup(*static_cast<Batch*>(h)->robots[0], out);
+  out->startup_loops = static_cast<Batch*>(h)->startup_loops;
+}
 
 // cmd [n][3]; imu [n][10] (quat wxyz, gyro xyz, accel xyz) or NULL; tip_force [n][L][3] or NULL; manual [n][6] or NULL.
 void shc_oracle_batch_step(void* h, const double* cmd, const double* imu, const double* tip_force, const double* manual,

@@ -79,6 +79,7 @@ class ShcStartup(C.Structure):
         ("swing_start", _i), ("swing_end", _i), ("stance_start", _i),
         ("phase_offsets", _i * MAX_LEGS),
         ("pose_phase_length", _i), ("pose_normaliser", _i), ("auto_pose_reference_leg", _i),
+        ("startup_loops", _i),
     ]
 
 

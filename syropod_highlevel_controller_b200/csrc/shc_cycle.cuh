@@ -354,6 +354,107 @@ SHC_HD K ik_result_value(const LegConsts<K>& lc, const Chain<K, D>& ch2, const K
   return prox;
 }
 
+// Model::estimateGravity (model.cpp:156) from the raw IMU orientation (all-zero quaternion when no IMU data: the
+// rotation matrix of the zero quaternion is the identity).
+template <class K> SHC_HD V3<K> estimate_gravity(Q4<K> imu_raw) {
+  V3<K> e = quat_to_euler(imu_raw, false);
+  K s, c;
+  sincos_(-e.y, &s, &c);  // rotate (0,0,g) about Y by -pitch
+  const K g = K(-9.81);
+  V3<K> v{s * g, K(0), c * g};
+  sincos_(-e.x, &s, &c);  // then about X by -roll
+  return {v.x, c * v.y - s * v.z, s * v.y + c * v.z};
+}
+
+// The AutoPoser loop of PoseController::updateAutoPose (pose_controller.cpp:1163-1178, AutoPoser::updatePose :1338): every
+// poser advances its start / end latches (4 bits each in `pflags`) and contributes its quartic-Bezier sway; returns the
+// summed auto pose and sets auto_state to POSE_COMPLETE when no poser is posing any more.
+template <class K>
+SHC_HD PoseT<K> auto_posers_update(const IntConsts& ci, const RealConsts<K>& ck, int master_phase, Q4<K> imu_raw, int& auto_state,
+                                   int& pflags) {
+  PoseT<K> auto_pose = pose_identity<K>();
+  int complete = 0;
+  V3<K> grav_dir{K(0), K(0), K(-1)};
+  bool grav_done = false;
+  for (int a = 0; a < ci.n_posers; ++a) {
+    int f = (pflags >> (4 * a)) & 15;
+    bool start_check = f & 1, end1 = f & 2, end2 = f & 4, allow = f & 8;
+    int phase = master_phase;
+    int start_phase = ci.ap_start[a] * ci.pose_normaliser;
+    int end_phase = ci.ap_end[a] * ci.pose_normaliser;
+    if (start_phase > end_phase) {
+      end_phase += ci.pose_phase_length;
+      if (phase < start_phase) phase += ci.pose_phase_length;
+    }
+    start_check = !ci.pose_sync || (!start_check && auto_state == POSE_POSING && phase == start_phase);
+    end1 = end1 || (auto_state == POSE_STOP_POSING && phase == start_phase);
+    end2 = end2 || (auto_state == POSE_STOP_POSING && phase == end_phase && end1);
+    if (!allow && start_check) {
+      allow = true;
+      end1 = end2 = false;
+    } else if (allow && ci.pose_sync && end1 && end2) {
+      allow = false;
+      start_check = false;
+    }
+    PoseT<K> upd = pose_identity<K>();
+    if (phase >= start_phase && phase < end_phase && allow) {
+      int iteration = phase - start_phase + 1;
+      int num_iterations = end_phase - start_phase;
+      bool first_half = iteration <= num_iterations / 2;
+      V3<K> rot_amp{ck.ap_rot[a][0], ck.ap_rot[a][1], ck.ap_rot[a][2]};
+      V3<K> pos_amp{ck.ap_pos[a][0], ck.ap_pos[a][1], ck.ap_pos[a][2]};
+      if (ck.ap_gravity[a] != K(0)) {
+        if (!grav_done) { grav_dir = normalized(estimate_gravity(imu_raw)); grav_done = true; }
+        pos_amp = grav_dir * ck.ap_gravity[a];
+      }
+      K delta_t = K(1) / (K(num_iterations) / K(2));
+      int offset = (int)(first_half ? 0.0 : num_iterations / 2.0);
+      K t = K(iteration - offset) * delta_t;
+      K s = K(1) - t;
+      // quartic Bezier with nodes {0,0,0,A,A} (first half) or {A,A,0,0,0} (second half)
+      K w = first_half ? (K(4) * t * t * t * s + t * t * t * t) : (s * s * s * s + K(4) * t * s * s * s);
+      upd.p = pos_amp * w;
+      upd.q = euler_to_quat(rot_amp * w, false);
+    }
+    complete += allow ? 0 : 1;
+    auto_pose = pose_add(auto_pose, upd);
+    f = (start_check ? 1 : 0) | (end1 ? 2 : 0) | (end2 ? 4 : 0) | (allow ? 8 : 0);
+    pflags = (pflags & ~(15 << (4 * a))) | (f << (4 * a));
+  }
+  if (complete == ci.n_posers) auto_state = POSE_COMPLETE;
+  return auto_pose;
+}
+
+// LegPoser::updateAutoPose (pose_controller.cpp:1716): the leg's own auto pose = the body's with the leg's negation
+// window blended out; `negate` is the leg's latch, `step_state` the state the cycle found the leg in.
+template <class K>
+SHC_HD PoseT<K> leg_auto_pose(const IntConsts& ci, K neg_ratio, int l, int master_phase, int step_state, const PoseT<K>& auto_pose,
+                              bool& negate) {
+  int start_phase = ci.neg_start[l] * ci.pose_normaliser;
+  int end_phase = ci.neg_end[l] * ci.pose_normaliser;
+  int negation_phase = master_phase;
+  if (start_phase == 0) start_phase = ci.pose_phase_length;
+  if (end_phase == 0) end_phase = ci.pose_phase_length;
+  if (start_phase > end_phase) {
+    end_phase += ci.pose_phase_length;
+    if (negation_phase < start_phase) negation_phase += ci.pose_phase_length;
+  }
+  if (step_state != STEP_FORCE_STANCE && step_state != STEP_FORCE_STOP && negation_phase == start_phase) negate = true;
+  if (negation_phase < start_phase || negation_phase > end_phase) negate = false;
+  if (!negate) return auto_pose;
+  int iteration = negation_phase - start_phase + 1;
+  int num_iterations = end_phase - start_phase;
+  bool first_half = iteration <= num_iterations / 2;
+  K ctrl = K(1);
+  if (neg_ratio > K(0)) {
+    if (first_half) ctrl = min_(K(1), K(iteration) / (K(num_iterations) * neg_ratio));
+    else ctrl = min_(K(1), K(num_iterations - iteration) / (K(num_iterations) * neg_ratio));
+  }
+  ctrl = smooth_step(ctrl);
+  PoseT<K> negation = pose_interpolate(pose_identity<K>(), ctrl, auto_pose);
+  return pose_remove(auto_pose, negation);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // FULL = false compiles the walking-only engine (no auto / IMU / inclination posing, no admittance): the optional stages
 // and the registers they keep alive across the leg loop disappear at compile time.
@@ -441,18 +542,6 @@ template <class P, int D, bool FULL> struct Cycle {
     out.p = {dpv[0], dpv[1], dpv[2]};
     out.q = correct_rotation(euler_to_quat(V3<K>{drv[0], drv[1], drv[2]}, true), qidentity<K>());
     return out;
-  }
-
-  // Model::estimateGravity (model.cpp:156) from the raw IMU orientation (all-zero quaternion when no IMU data: the
-  // rotation matrix of the zero quaternion is the identity).
-  static SHC_CYCLE_FN __forceinline__ V3<K> estimate_gravity(Q4<K> imu_raw) {
-    V3<K> e = quat_to_euler(imu_raw, false);
-    K s, c;
-    sincos_(-e.y, &s, &c);  // rotate (0,0,g) about Y by -pitch
-    const K g = K(-9.81);
-    V3<K> v{s * g, K(0), c * g};
-    sincos_(-e.x, &s, &c);  // then about X by -roll
-    return {v.x, c * v.y - s * v.z, s * v.y + c * v.z};
   }
 
   // Bytes of one staging slot: the staged storage planes of a leg, its double planes and its int planes.
@@ -712,56 +801,7 @@ template <class P, int D, bool FULL> struct Cycle {
         ip[(ci.offI_auto + AI_PHASE) * 32] = pose_phase;
       }
       int pflags = ip[(ci.offI_auto + AI_FLAGS) * 32];
-      auto_pose = pose_identity<K>();
-      int complete = 0;
-      V3<K> grav_dir{K(0), K(0), K(-1)};
-      bool grav_done = false;
-      for (int a = 0; a < ci.n_posers; ++a) {  // AutoPoser::updatePose (:1338)
-        int f = (pflags >> (4 * a)) & 15;
-        bool start_check = f & 1, end1 = f & 2, end2 = f & 4, allow = f & 8;
-        int phase = master_phase;
-        int start_phase = ci.ap_start[a] * ci.pose_normaliser;
-        int end_phase = ci.ap_end[a] * ci.pose_normaliser;
-        if (start_phase > end_phase) {
-          end_phase += ci.pose_phase_length;
-          if (phase < start_phase) phase += ci.pose_phase_length;
-        }
-        start_check = !ci.pose_sync || (!start_check && auto_state == POSE_POSING && phase == start_phase);
-        end1 = end1 || (auto_state == POSE_STOP_POSING && phase == start_phase);
-        end2 = end2 || (auto_state == POSE_STOP_POSING && phase == end_phase && end1);
-        if (!allow && start_check) {
-          allow = true;
-          end1 = end2 = false;
-        } else if (allow && ci.pose_sync && end1 && end2) {
-          allow = false;
-          start_check = false;
-        }
-        PoseT<K> upd = pose_identity<K>();
-        if (phase >= start_phase && phase < end_phase && allow) {
-          int iteration = phase - start_phase + 1;
-          int num_iterations = end_phase - start_phase;
-          bool first_half = iteration <= num_iterations / 2;
-          V3<K> rot_amp{ck.ap_rot[a][0], ck.ap_rot[a][1], ck.ap_rot[a][2]};
-          V3<K> pos_amp{ck.ap_pos[a][0], ck.ap_pos[a][1], ck.ap_pos[a][2]};
-          if (ck.ap_gravity[a] != K(0)) {
-            if (!grav_done) { grav_dir = normalized(estimate_gravity(imu_raw)); grav_done = true; }
-            pos_amp = grav_dir * ck.ap_gravity[a];
-          }
-          K delta_t = K(1) / (K(num_iterations) / K(2));
-          int offset = (int)(first_half ? 0.0 : num_iterations / 2.0);
-          K t = K(iteration - offset) * delta_t;
-          K s = K(1) - t;
-          // quartic Bezier with nodes {0,0,0,A,A} (first half) or {A,A,0,0,0} (second half)
-          K w = first_half ? (K(4) * t * t * t * s + t * t * t * t) : (s * s * s * s + K(4) * t * s * s * s);
-          upd.p = pos_amp * w;
-          upd.q = euler_to_quat(rot_amp * w, false);
-        }
-        complete += allow ? 0 : 1;
-        auto_pose = pose_add(auto_pose, upd);
-        f = (start_check ? 1 : 0) | (end1 ? 2 : 0) | (end2 ? 4 : 0) | (allow ? 8 : 0);
-        pflags = (pflags & ~(15 << (4 * a))) | (f << (4 * a));
-      }
-      if (complete == ci.n_posers) auto_state = POSE_COMPLETE;
+      auto_pose = auto_posers_update<K>(ci, ck, master_phase, imu_raw, auto_state, pflags);
       ip[(ci.offI_auto + AI_FLAGS) * 32] = pflags;
       stPose(sp, ci.offS_auto + AUTO_POSE, auto_pose);
       cur_pose = pose_add(cur_pose, auto_pose);
@@ -962,30 +1002,7 @@ template <class P, int D, bool FULL> struct Cycle {
       // LegPoser::updateAutoPose (pose_controller.cpp:1716) — uses the step state of the previous cycle
       PoseT<K> leg_auto = auto_pose;
       if (run_auto) {
-        int start_phase = ci.neg_start[l] * ci.pose_normaliser;
-        int end_phase = ci.neg_end[l] * ci.pose_normaliser;
-        int negation_phase = master_phase;
-        if (start_phase == 0) start_phase = ci.pose_phase_length;
-        if (end_phase == 0) end_phase = ci.pose_phase_length;
-        if (start_phase > end_phase) {
-          end_phase += ci.pose_phase_length;
-          if (negation_phase < start_phase) negation_phase += ci.pose_phase_length;
-        }
-        if (step_state != STEP_FORCE_STANCE && step_state != STEP_FORCE_STOP && negation_phase == start_phase) negate = true;
-        if (negation_phase < start_phase || negation_phase > end_phase) negate = false;
-        if (negate) {
-          int iteration = negation_phase - start_phase + 1;
-          int num_iterations = end_phase - start_phase;
-          bool first_half = iteration <= num_iterations / 2;
-          K ctrl = K(1);
-          if (lk.neg_ratio > K(0)) {
-            if (first_half) ctrl = min_(K(1), K(iteration) / (K(num_iterations) * lk.neg_ratio));
-            else ctrl = min_(K(1), K(num_iterations - iteration) / (K(num_iterations) * lk.neg_ratio));
-          }
-          ctrl = smooth_step(ctrl);
-          PoseT<K> negation = pose_interpolate(pose_identity<K>(), ctrl, auto_pose);
-          leg_auto = pose_remove(auto_pose, negation);
-        }
+        leg_auto = leg_auto_pose<K>(ci, lk.neg_ratio, l, master_phase, step_state, auto_pose, negate);
       } else if (f_auto) {
         leg_auto = pose_identity<K>();  // LegPoser::auto_pose_ is only refreshed by updateAutoPose; IMU posing keeps identity
       }

@@ -326,6 +326,27 @@ int download(shc_engine* e, HostPlanes& h) {
   return SHC_OK;
 }
 
+// The tiles [t0, t1) only: a tile's planes are contiguous in each plane set (tile-major layout), so a robot range costs
+// three small copies however large the batch is.
+int download_tiles(shc_engine* e, size_t t0, size_t t1, HostPlanes& h) {
+  const IntConsts& ci = e->c.i;
+  const size_t nt = t1 - t0;
+  h.s.resize((size_t)ci.nS * 32 * nt);
+  h.d.resize((size_t)ci.nD * 32 * nt);
+  h.i.resize((size_t)ci.nI * 32 * nt);
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (e->precision == SHC_PRECISION_F64) {
+    CUDA_TRY(cudaMemcpy(h.s.data(), (const double*)e->s_planes + t0 * ci.nS * 32, h.s.size() * 8, cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<float> tmp(h.s.size());
+    CUDA_TRY(cudaMemcpy(tmp.data(), (const float*)e->s_planes + t0 * ci.nS * 32, tmp.size() * 4, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < tmp.size(); ++k) h.s[k] = tmp[k];
+  }
+  CUDA_TRY(cudaMemcpy(h.d.data(), e->d_planes + t0 * ci.nD * 32, h.d.size() * 8, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(h.i.data(), e->i_planes + t0 * ci.nI * 32, h.i.size() * 4, cudaMemcpyDeviceToHost));
+  return SHC_OK;
+}
+
 int upload(shc_engine* e, const HostPlanes& h) {
   CUDA_TRY(cudaDeviceSynchronize());
   if (e->precision == SHC_PRECISION_F64) {
@@ -404,6 +425,7 @@ int shc_create(const shc_config* cfg, const shc_startup* startup, int n_robots, 
   std::string err;
   bool unsupported = false;
   if (!check_supported(*cfg, err, unsupported)) return fail(unsupported ? SHC_E_UNSUPPORTED : SHC_E_INVALID, err);
+  if (!startup && !own_startup_supported(*cfg, err)) return fail(SHC_E_UNSUPPORTED, err);
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
     return fail(SHC_E_CUDA, "no CUDA device: the SHC engine has no CPU fallback");
@@ -558,6 +580,40 @@ int shc_get_state(shc_engine* e, shc_robot_state* out, size_t n_records) {
   int rc = download(e, h);
   if (rc != SHC_OK) return rc;
   return dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int { unpack<decltype(dtag)::value>(e, h, out, n_records); return SHC_OK; });
+}
+
+// Records of the robots [first, first + count) only (the getters a publisher calls for one robot need not move the batch).
+int shc_get_state_range(shc_engine* e, size_t first, size_t count, shc_robot_state* out) {
+  if (!e || !out || count < 1 || first + count > (size_t)e->n) return fail(SHC_E_INVALID, "shc_get_state_range: range outside the batch");
+  CUDA_TRY(cudaSetDevice(e->device));
+  const size_t t0 = first / 32, t1 = (first + count + 31) / 32;
+  HostPlanes h;
+  int rc = download_tiles(e, t0, t1, h);
+  if (rc != SHC_OK) return rc;
+  return dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int {
+    unpack<decltype(dtag)::value>(e, h, out, count, first - t0 * 32);
+    return SHC_OK;
+  });
+}
+
+// WalkController::setLinearSpeedLimitMap / setAngularSpeedLimitMap / setLinearAccelerationLimitMap /
+// setAngularAccelerationLimitMap (walk_controller.h:126-141): replaces the four limit tables (9 bearings each, 0..360 in
+// steps of 45 degrees) that getLimit (walk_controller.cpp:414) reads; NULL keeps a table.  Takes effect from the next cycle.
+int shc_set_limit_maps(shc_engine* e, const double* max_linear_speed, const double* max_angular_speed,
+                       const double* max_linear_acceleration, const double* max_angular_acceleration) {
+  if (!e) return fail(SHC_E_INVALID, "null engine");
+  const double* src[4] = {max_linear_speed, max_angular_speed, max_linear_acceleration, max_angular_acceleration};
+  double* dst[4] = {e->su.max_linear_speed, e->su.max_angular_speed, e->su.max_linear_acceleration, e->su.max_angular_acceleration};
+  for (int k = 0; k < 4; ++k) {
+    if (!src[k]) continue;
+    for (int b = 0; b < SHC_N_BEARINGS; ++b) {
+      dst[k][b] = src[k][b];
+      e->c.d.limits[k][b] = src[k][b];
+      e->c.f.limits[k][b] = (float)src[k][b];
+    }
+  }
+  drop_graphs(e);  // captured rollouts carry the constants block
+  return SHC_OK;
 }
 
 int shc_set_state(shc_engine* e, const shc_robot_state* in, size_t n_records) {

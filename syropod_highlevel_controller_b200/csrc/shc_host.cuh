@@ -169,6 +169,9 @@ inline void compute_step_cycle(const shc_config& c, shc_startup& su) {
   su.auto_pose_reference_leg = 0;
   for (int l = 0; l < c.leg_count; ++l)
     if (c.offset_multiplier[l] == 0) su.auto_pose_reference_leg = l;
+  // PoseController::directStartup (:463) finishes its stepToPosition after round(time_to_start / dt) calls; the loop()
+  // that requested the transition comes on top (state_controller.cpp:254-281)
+  su.startup_loops = std::max(1, round_to_int(c.time_to_start / c.time_delta)) + 1;
 }
 
 // One Leg::applyIK(simulation) on host joint arrays; returns applyIK's value and the new tip (base_link frame).
@@ -449,7 +452,35 @@ template <int D> void initial_state(const shc_config& c, const RealConsts<double
     g.desired_tip_position[0] = tip.x; g.desired_tip_position[1] = tip.y; g.desired_tip_position[2] = tip.z;
     g.ik_result = 1.0;
   }
-  if (c.auto_posing) {
+  if (c.auto_posing && c.pose_frequency != -1.0) {
+    // An auto poser with its own cycle keeps cycling while the robot starts up (updateCurrentPose runs in every loop(),
+    // pose_controller.cpp:811): replay those loops with the routines the kernel uses — walk state STOPPED, legs in STANCE.
+    IntConsts ci;
+    std::memset(&ci, 0, sizeof(ci));
+    ci.n_posers = c.auto_poser_count;
+    ci.pose_sync = 0;
+    ci.pose_phase_length = su.pose_phase_length;
+    ci.pose_normaliser = su.pose_normaliser;
+    for (int a = 0; a < c.auto_poser_count; ++a) { ci.ap_start[a] = c.pose_phase_starts[a]; ci.ap_end[a] = c.pose_phase_ends[a]; }
+    for (int l = 0; l < c.leg_count; ++l) { ci.neg_start[l] = c.pose_negation_phase_starts[l]; ci.neg_end[l] = c.pose_negation_phase_ends[l]; }
+    int auto_state = POSE_COMPLETE, pflags = 0, pose_phase = 0;
+    bool negate[SHC_MAX_LEGS] = {false};
+    PoseT<double> ap = pose_identity<double>();
+    for (int it = 0; it + 1 < su.startup_loops; ++it) {  // the first loop() finds the robot state UNKNOWN: no pose update (:165)
+      auto_state = POSE_STOP_POSING;  // walk state STOPPED (:1146)
+      const int master = pose_phase;
+      pose_phase = (pose_phase + 1) % su.pose_phase_length;
+      ap = auto_posers_update<double>(ci, ck, master, Q4<double>{0.0, 0.0, 0.0, 0.0}, auto_state, pflags);
+      for (int l = 0; l < c.leg_count; ++l) leg_auto_pose<double>(ci, ck.leg[l].neg_ratio, l, master, STEP_STANCE, ap, negate[l]);
+    }
+    s.auto_posing_state = auto_state;
+    s.pose_state = auto_state;
+    s.pose_phase = pose_phase;
+    for (int a = 0; a < c.auto_poser_count; ++a) s.auto_poser_flags[a] = (pflags >> (4 * a)) & 15;
+    for (int l = 0; l < c.leg_count; ++l) s.legs[l].negate_auto_pose = negate[l];
+    s.auto_pose[0] = ap.p.x; s.auto_pose[1] = ap.p.y; s.auto_pose[2] = ap.p.z;
+    s.auto_pose[3] = ap.q.w; s.auto_pose[4] = ap.q.x; s.auto_pose[5] = ap.q.y; s.auto_pose[6] = ap.q.z;
+  } else if (c.auto_posing) {
     // The reference runs updateAutoPose during the ~300 start-up cycles (walk state STOPPED, master phase 0).  The
     // latches reach a fixed point after one evaluation (pose_controller.cpp:1359-1371, 1743-1751).
     const int len = su.pose_phase_length, norm = su.pose_normaliser;

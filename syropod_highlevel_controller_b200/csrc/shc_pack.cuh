@@ -165,7 +165,8 @@ template <class E> void pack(const E* e, const shc_robot_state* in, size_t n, Ho
   }
 }
 
-template <int D, class E> void unpack(const E* e, const HostPlanes& h, shc_robot_state* out, size_t n) {
+// Unpacks the records of the robots [r0, r0 + n) of `h` (robot indices relative to the first tile held in h) into out[0..n).
+template <int D, class E> void unpack(const E* e, const HostPlanes& h, shc_robot_state* out, size_t n, size_t r0 = 0) {
   const IntConsts& ci = e->c.i;
   const RealConsts<double>& ck = e->c.d;
   const size_t np = ci.n_pad;
@@ -175,8 +176,8 @@ template <int D, class E> void unpack(const E* e, const HostPlanes& h, shc_robot
   auto S = [&](int plane, size_t r) { return h.s[((r >> 5) * ci.nS + plane) * 32 + (r & 31)]; };
   auto Dd = [&](int plane, size_t r) { return h.d[((r >> 5) * ci.nD + plane) * 32 + (r & 31)]; };
   auto I = [&](int plane, size_t r) { return h.i[((r >> 5) * ci.nI + plane) * 32 + (r & 31)]; };
-  for (size_t r = 0; r < n; ++r) {
-    shc_robot_state& s = out[r];
+  for (size_t r = r0; r < r0 + n; ++r) {
+    shc_robot_state& s = out[r - r0];
     std::memset(&s, 0, sizeof(s));
     s.desired_linear_velocity[0] = S(RS_VEL, r);
     s.desired_linear_velocity[1] = S(RS_VEL + 1, r);
@@ -305,9 +306,8 @@ inline bool engine_full(const shc_config& cfg) {
 // Everything shc_create refuses: invalid configurations and reference features outside the built scope.
 inline bool check_supported(const shc_config& cfg, std::string& err, bool& unsupported) {
   if (!validate_config(cfg, err, unsupported)) return false;
-  if (cfg.auto_posing && cfg.pose_frequency != -1.0) {
-    unsupported = true;
-    err = "auto posing with its own pose_frequency (not synced to the step cycle) is not implemented";
+  if (cfg.auto_posing && cfg.pose_frequency != -1.0 && !(cfg.pose_frequency > 0.0 && cfg.pose_phase_length > 0)) {
+    err = "auto posing with its own cycle needs pose_frequency > 0 and pose_phase_length > 0 (or pose_frequency = -1 to follow the step cycle)";
     return false;
   }
   return true;
@@ -328,6 +328,18 @@ inline bool check_step_cycle(const shc_startup& su, std::string& err) {
 
 // Constants block + start-up results of an engine (host arithmetic only).  `startup` = null: the engine's own restatement
 // of the reference's start-up path (shc_host.cuh).
+// A poser with its own cycle sways the body while the reference computes its workspaces: the tip check of model.cpp:330
+// fails, the workspace and every speed limit come out zero (tests/parity_cases.py::auto_posing_own_cycle shows it on the
+// oracle).  The engine does not re-derive that accident: such a configuration needs explicit start-up constants.
+inline bool own_startup_supported(const shc_config& cfg, std::string& err) {
+  if (cfg.auto_posing && cfg.pose_frequency != -1.0) {
+    err = "auto posing with its own pose_frequency: pass explicit shc_startup constants (the engine's own start-up models a body "
+          "at rest; the reference's start-up under a free-running poser yields an empty workspace)";
+    return false;
+  }
+  return true;
+}
+
 template <class E> int core_init(E* e, const shc_config& cfg, const shc_startup* startup, int n_robots, int precision) {
   e->cfg = cfg;
   e->precision = precision;

@@ -50,6 +50,8 @@ def lib():
         L.shc_set_pose_reset_mode.argtypes = [vp, C.c_int]
         L.shc_get_state.argtypes = [vp, C.POINTER(ShcRobotState), C.c_size_t]
         L.shc_set_state.argtypes = [vp, C.POINTER(ShcRobotState), C.c_size_t]
+        L.shc_get_state_range.argtypes = [vp, C.c_size_t, C.c_size_t, C.POINTER(ShcRobotState)]
+        L.shc_set_limit_maps.argtypes = [vp, dp, dp, dp, dp]
         L.shc_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.shc_step_host.argtypes = [vp, fp, fp, fp, fp, fp]
         L.shc_rollout.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
@@ -187,6 +189,21 @@ class Engine:
 
     def set_state(self, arr):
         _check(lib().shc_set_state(self._h, arr, self.n))
+
+    def get_state_range(self, first: int, count: int = 1):
+        """Records of the robots [first, first + count) only (three small copies, whatever the batch size)."""
+        arr = (ShcRobotState * count)()
+        _check(lib().shc_get_state_range(self._h, first, count, arr))
+        return arr
+
+    def set_limit_maps(self, max_linear_speed=None, max_angular_speed=None, max_linear_acceleration=None,
+                       max_angular_acceleration=None):
+        """WalkController::set*LimitMap (walk_controller.h:126-141): 9 values per table (bearings 0..360 step 45)."""
+        dp = C.POINTER(C.c_double)
+        arrs = [None if m is None else np.ascontiguousarray(m, dtype=np.float64) for m in
+                (max_linear_speed, max_angular_speed, max_linear_acceleration, max_angular_acceleration)]
+        assert all(a is None or a.shape == (9,) for a in arrs)
+        _check(lib().shc_set_limit_maps(self._h, *[None if a is None else a.ctypes.data_as(dp) for a in arrs]))
 
     # ---- stepping --------------------------------------------------------------------------------------------------
     def _f32(self, t, shape):

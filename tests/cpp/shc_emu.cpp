@@ -80,6 +80,7 @@ int shc_emu_create(const shc_config* cfg, const shc_startup* startup, int n_robo
   std::string err;
   bool unsupported = false;
   if (!check_supported(*cfg, err, unsupported)) return fail(unsupported ? SHC_E_UNSUPPORTED : SHC_E_INVALID, err);
+  if (!startup && !own_startup_supported(*cfg, err)) return fail(SHC_E_UNSUPPORTED, err);
   shc_emu* e = new shc_emu();
   core_init(e, *cfg, startup, n_robots, precision);
   if (!check_step_cycle(e->su, err)) { delete e; return fail(SHC_E_UNSUPPORTED, err); }

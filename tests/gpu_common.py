@@ -5,7 +5,7 @@ STATE_FIELDS_ROBOT = ("desired_linear_velocity", "walk_plane", "walk_plane_norma
                       "origin_walk_plane_pose", "manual_pose", "imu_pose", "inclination_pose", "auto_pose",
                       "rotation_absement_error", "rotation_velocity_error", "current_pose")
 INT_FIELDS_ROBOT = ("walk_state", "legs_at_correct_phase", "legs_completed_first_step", "return_to_default_attempted",
-                    "pose_state", "auto_posing_state")
+                    "pose_state", "auto_posing_state", "pose_phase")
 STATE_FIELDS_LEG = ("tip_position", "tip_velocity", "swing_origin_position", "stance_origin_position",
                     "default_tip_position", "target_tip_position", "stride_vector", "walk_plane", "walk_plane_normal",
                     "admittance_state", "admittance_delta", "tip_force_calculated", "virtual_stiffness", "model_tip_position")

@@ -118,6 +118,33 @@ def auto_posing_100hz(backend, oracle, gaits=("tripod_gait", "wave_gait", "rippl
         eng.close(); ob.close()
 
 
+def auto_posing_own_cycle(backend, oracle, n=32, cycles=800):
+    """Auto posing on its own cycle (pose_frequency != -1: the non-synchronised branches of pose_controller.cpp:1134-1187 and
+    AutoPoser::updatePose :1338): the posers cycle from the second start-up loop on, whether the robot walks or not, and the
+    engine's initial state replays those loops (csrc/shc_host.cuh initial_state).  In the reference this mode leaves the
+    body swaying while generateWorkspaces runs, the tip check of model.cpp:330 fails and the workspace — hence every speed
+    limit — comes out zero: the robot poses but cannot walk (all shipped configurations use -1).  The oracle reproduces
+    that, so this case checks the posing itself; the engine refuses to compute its OWN start-up for such a configuration."""
+    from backends import Backend  # noqa: F401  (ShcError / EmuError types differ per backend)
+
+    for gait, dt, freq in (("tripod_gait", 0.02, 0.7), ("wave_gait", 0.01, 1.3)):
+        cfg = hexapod_config(gait, dt, auto_posing=1, pose_frequency=freq)
+        ob = oracle.OracleBatch(cfg, n)
+        assert max(ob.startup().walkspace) == 0.0
+        eng = backend.engine(cfg, n, startup=ob.startup())
+        assert_state_close(eng.get_state(), ob.get_state(), 6, 3, 1e-12, skip=JOINT_FIELDS)
+        errs = run_both(eng, ob, cycles, CommandStream(n, min_len=100, max_len=300), dt=dt)
+        errs.check(max_fraction=5e-3, label=f"auto posing, own cycle {freq} Hz, {gait}")
+        assert_state_close(eng.get_state(), ob.get_state(), 6, 3, 1e-8, skip=JOINT_FIELDS)
+        assert max(abs(v) for s in ob.get_state() for v in list(s.auto_pose)) > 1e-4  # the body is swaying
+        eng.close(); ob.close()
+        try:
+            backend.engine(cfg, 1, startup=None)
+            raise AssertionError("own start-up with a free-running poser should be refused")
+        except RuntimeError as ex:
+            assert "start-up" in str(ex)
+
+
 def parameter_variants(backend, oracle, n=96, cycles=500):
     """real-velocity input mode, force_normal_touchdown, swing width / stance span, no manual posing, unclamped joints."""
     variants = [dict(velocity_input_mode=1), dict(force_normal_touchdown=1), dict(swing_width=0.01, stance_span_modifier=0.3),

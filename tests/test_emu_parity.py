@@ -40,6 +40,10 @@ def test_emu_auto_posing_and_100hz(emu, oracle):
     P.auto_posing_100hz(emu, oracle, n=24, cycles=1200)
 
 
+def test_emu_auto_posing_own_cycle(emu, oracle):
+    P.auto_posing_own_cycle(emu, oracle, n=16)
+
+
 def test_emu_other_parameter_variants(emu, oracle):
     P.parameter_variants(emu, oracle, n=48, cycles=500)
 

@@ -39,6 +39,10 @@ def test_auto_posing_and_100hz(gpu, oracle):
     P.auto_posing_100hz(gpu, oracle)
 
 
+def test_auto_posing_own_cycle(gpu, oracle):
+    P.auto_posing_own_cycle(gpu, oracle)
+
+
 def test_other_parameter_variants(gpu, oracle):
     P.parameter_variants(gpu, oracle)
 

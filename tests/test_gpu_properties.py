@@ -107,6 +107,38 @@ def test_state_round_trip_is_idempotent(shc_lib):
         eng.close()
 
 
+def test_state_range_and_limit_maps(shc_lib):
+    """shc_get_state_range returns the bytes shc_get_state returns for the same robots (tile boundaries included), and
+    shc_set_limit_maps (WalkController::set*LimitMap) takes effect from the next cycle: with the linear-speed table halved,
+    the body velocity of a full-throttle robot settles at half the original limit."""
+    import torch
+
+    cfg = hexapod_config("tripod_gait")
+    n = 1000
+    eng = _engine(cfg, n, "f64")
+    cs = CommandStream(n, min_len=20, max_len=60)
+    for c in range(90):
+        eng.step(torch.from_numpy(cs.next()).cuda())
+    full = eng.get_state()
+    for first, count in ((0, 1), (31, 2), (32, 32), (500, 77), (999, 1), (0, 1000)):
+        part = eng.get_state_range(first, count)
+        assert bytes(part) == bytes(full)[first * C.sizeof(full[0]):(first + count) * C.sizeof(full[0])], (first, count)
+    su = eng.startup()
+    lim = np.array(list(su.max_linear_speed))
+    fwd = torch.tensor([[1.0, 0.0, 0.0]], device="cuda").repeat(n, 1)
+    for c in range(400):
+        eng.step(fwd)
+    v_full = np.array([eng.get_state_range(r, 1)[0].desired_linear_velocity[0] for r in (0, 499, 999)])
+    assert np.allclose(v_full, lim[0], rtol=1e-9)
+    eng.set_limit_maps(max_linear_speed=0.5 * lim)
+    assert list(eng.startup().max_linear_speed) == list(0.5 * lim)
+    for c in range(400):
+        eng.step(fwd)
+    v_half = np.array([eng.get_state_range(r, 1)[0].desired_linear_velocity[0] for r in (0, 499, 999)])
+    assert np.allclose(v_half, 0.5 * lim[0], rtol=1e-9)
+    eng.close()
+
+
 def test_host_entry_point_and_graph_rollout_match_step(shc_lib):
     """shc_step_host (pinned staging + H2D + kernel + D2H) and shc_rollout (CUDA graph) give the device path's bits."""
     import torch
