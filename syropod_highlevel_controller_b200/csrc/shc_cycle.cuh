@@ -129,6 +129,14 @@ __device__ __forceinline__ void multimem_red_release_add(int* mc, int v) {
   asm volatile("fence.acq_rel.sys;" ::: "memory");
   asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory");
 }
+// cp.async (LDGSTS): per-lane asynchronous global -> shared copies that need no registers while in flight
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   unsigned done;
   do {
@@ -149,6 +157,16 @@ inline void fence_proxy_async_smem() {}
 inline void mbar_expect_tx(uint64_t*, unsigned) {}
 inline void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t*) { std::memcpy(dst, src, bytes); }
 inline void mbar_wait(uint64_t*, unsigned) {}
+inline void cp_async_16(void* dst, const void* src) { std::memcpy(dst, src, 16); }
+inline void cp_async_4(void* dst, const void* src) { std::memcpy(dst, src, 4); }
+inline void cp_async_wait_all() {}
+#endif
+// The Euler decomposition (three atan2, ~700 instructions) as ONE out-of-line copy per kernel: the pose stages call it from
+// up to five places, and inlining every call bloats the instruction footprint of a kernel that is fetch-bound already.
+#if defined(__CUDA_ARCH__)
+template <class R> __device__ __noinline__ V3<R> quat_to_euler_nc(Q4<R> q, bool intrinsic) { return quat_to_euler(q, intrinsic); }
+#else
+template <class R> inline V3<R> quat_to_euler_nc(Q4<R> q, bool intrinsic) { return quat_to_euler(q, intrinsic); }
 #endif
 
 template <class S> struct Planes {
@@ -357,7 +375,7 @@ SHC_HD K ik_result_value(const LegConsts<K>& lc, const Chain<K, D>& ch2, const K
 // Model::estimateGravity (model.cpp:156) from the raw IMU orientation (all-zero quaternion when no IMU data: the
 // rotation matrix of the zero quaternion is the identity).
 template <class K> SHC_HD V3<K> estimate_gravity(Q4<K> imu_raw) {
-  V3<K> e = quat_to_euler(imu_raw, false);
+  V3<K> e = quat_to_euler_nc(imu_raw, false);
   K s, c;
   sincos_(-e.y, &s, &c);  // rotate (0,0,g) about Y by -pitch
   const K g = K(-9.81);
@@ -499,7 +517,7 @@ template <class P, int D, bool FULL> struct Cycle {
   static SHC_CYCLE_FN __forceinline__ PoseT<K> manual_pose_update(const RealConsts<K>& ck, PoseT<K> man, const float* in6,
                                                                 int reset_mode) {
     if (reset_mode == 5) return pose_identity<K>();  // IMMEDIATE_ALL_RESET
-    V3<K> cur_rot = quat_to_euler(man.q, true);
+    V3<K> cur_rot = quat_to_euler_nc(man.q, true);
     K tin[3] = {K(0), K(0), K(0)}, rin[3] = {K(0), K(0), K(0)};
     if (in6) {
       tin[0] = K(in6[0]); tin[1] = K(in6[1]); tin[2] = K(in6[2]);
@@ -606,6 +624,23 @@ template <class P, int D, bool FULL> struct Cycle {
       fence_mbar_init();
     }
     SHC_SYNCWARP();
+
+    // Measured tip forces ([N][L][3] floats, this robot's L*3 values contiguous): copied asynchronously (cp.async, no
+    // registers in flight) into the lane's own stretch of the joint tile, BEHIND the joints: leg l's force sits at float
+    // L*(D-3) + 3l of the lane's L*D floats, which the joint commands of the legs 0..l (written at the end of each leg) never
+    // reach before leg l has read it.  The robot-level stage below hides the latency.
+    const bool stage_forces = FULL && f_adm && !f_effort && io.tip_force != nullptr;
+    if (stage_forces) {
+      const float* fsrc = io.tip_force + (size_t)r * (L * 3);
+      float* fdst = stage + L * (D - 3);
+      const bool wide = ((L * 12) & 15) == 0 && ((L * D * 4) & 15) == 0 && ((L * (D - 3) * 4) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(io.tip_force) & 15) == 0;
+      if (wide) {
+        for (int k = 0; k < (L * 3) / 4; ++k) cp_async_16(fdst + 4 * k, fsrc + 4 * k);
+      } else {
+        for (int k = 0; k < L * 3; ++k) cp_async_4(fdst + k, fsrc + k);
+      }
+    }
 
     // ---- every unconditional robot-level load, issued back to back (one exposed HBM latency for the whole stage) ------
     int rbits = ip[(RI_BITS) * 32];
@@ -740,10 +775,21 @@ template <class P, int D, bool FULL> struct Cycle {
     }
     PoseT<K> auto_pose = pose_identity<K>();
     if (f_auto) auto_pose = ldPose(sp, ci.offS_auto + AUTO_POSE);
+    // With an identity manual pose and no auto pose (the usual case) the rotation the inclination stage removes and the
+    // target of the IMU stage are both the identity: "IMU rotation with the pose removed" and "rotation error" are then the
+    // same quaternion up to sign, their rotation matrices are identical bit for bit (every entry is a product of two
+    // components), and one Euler decomposition serves both stages.
+    const bool plain_rot = FULL && man_identity &&
+                           (!f_auto || (auto_pose.q.w == K(1) && auto_pose.q.x == K(0) && auto_pose.q.y == K(0) && auto_pose.q.z == K(0)));
+    V3<K> e_imu{K(0), K(0), K(0)};
+    if (FULL && plain_rot && (f_incl || f_imu)) e_imu = quat_to_euler_nc(qnormalized(imu_q), false);
     if (f_incl) {  // updateInclinationPose (:1240)
-      Q4<K> comb = qnormalized(qmul(man.q, auto_pose.q));
-      Q4<K> removed = qnormalized(qmul(imu_q, qinverse(comb)));
-      V3<K> e = quat_to_euler(removed, false);
+      V3<K> e = e_imu;
+      if (!plain_rot) {
+        Q4<K> comb = qnormalized(qmul(man.q, auto_pose.q));
+        Q4<K> removed = qnormalized(qmul(imu_q, qinverse(comb)));
+        e = quat_to_euler_nc(removed, false);
+      }
       K lon = -ck.body_clearance * tan_(e.y);
       K lat = ck.body_clearance * tan_(e.x);
       lon = clamp_(lon, -ck.max_translation[0], ck.max_translation[0]);
@@ -757,14 +803,16 @@ template <class P, int D, bool FULL> struct Cycle {
     int master_phase = 0;
     bool run_auto = false;
     if (f_imu) {  // updateIMUPose (:1191); robot_state is RUNNING in every engine cycle
-      Q4<K> current_rotation = correct_rotation(imu_q, qidentity<K>());
       Q4<K> target_rotation = correct_rotation(man.q, qidentity<K>());
-      Q4<K> rot_err = qnormalized(qmul(current_rotation, qinverse(target_rotation)));
-      V3<K> pe = quat_to_euler(rot_err, false);
+      V3<K> pe = e_imu;
+      if (!plain_rot) {
+        Q4<K> current_rotation = correct_rotation(imu_q, qidentity<K>());
+        Q4<K> rot_err = qnormalized(qmul(current_rotation, qinverse(target_rotation)));
+        pe = quat_to_euler_nc(rot_err, false);
+      }
       pe.z = K(0);
       const int b = ci.offS_imu;
-      Q4<K> imu_pose_q{K(sp[(b + IMU_Q) * 32]), K(sp[(b + IMU_Q + 1) * 32]),
-                       K(sp[(b + IMU_Q + 2) * 32]), K(sp[(b + IMU_Q + 3) * 32])};
+      Q4<K> imu_pose_q;
       // IMU_POSING_DEADBAND is 0.0: "norm < 0" never holds, the PID always runs (pose_controller.h:25)
       V3<K> abs_err = ld3K(sp, b + IMU_ABS) + pe * ck.dt;
       V3<K> vel_err = (-gyro) * K(0.15) + ld3K(sp, b + IMU_VEL) * (K(1) - K(0.15));
@@ -773,7 +821,7 @@ template <class P, int D, bool FULL> struct Cycle {
       V3<K> corr = -(vel_err * ck.pid_d + pe * ck.pid_p + abs_err * ck.pid_i);
       corr.x = clamp_(corr.x, -ck.max_rotation[0], ck.max_rotation[0]);
       corr.y = clamp_(corr.y, -ck.max_rotation[1], ck.max_rotation[1]);
-      corr.z = quat_to_euler(target_rotation, false).z;
+      corr.z = man_identity ? K(0) : quat_to_euler_nc(target_rotation, false).z;  // yaw of the identity is 0
       if (norm(corr) > K(100)) status |= 8;
       imu_pose_q = correct_rotation(euler_to_quat(corr, false), target_rotation);
       sp[(b + IMU_Q) * 32] = S(imu_pose_q.w);
@@ -938,6 +986,7 @@ template <class P, int D, bool FULL> struct Cycle {
     // 3. per leg: walk state machine + LegStepper + updateStance + Leg::applyIK
     // =================================================================================================================
     SHC_STAMP(3);
+    if (stage_forces) cp_async_wait_all();
 #pragma unroll 1
     for (int l = 0; l < L; ++l) {
       // per-leg plane bases in HBM (stores, rare loads): every field of this leg is at an immediate offset from them
@@ -974,8 +1023,8 @@ template <class P, int D, bool FULL> struct Cycle {
         adm_x0 = K(ss[(LS::ADM_X) * 32]);
         adm_x1 = K(ss[(LS::ADM_X + 1) * 32]);
         if (f_effort) adm_force = ld3K(ss, LS::ADM_FORCE);
-        else if (io.tip_force) {
-          const float* f = io.tip_force + 3 * ((size_t)r * L + l);
+        else if (stage_forces) {
+          const float* f = stage + L * (D - 3) + 3 * l;
           adm_force = {K(f[0]), K(f[1]), K(f[2])};
         }
       }
@@ -1221,7 +1270,9 @@ template <class P, int D, bool FULL> struct Cycle {
           x0 = n0;
           x1 = n1;
           K dl = clamp_(-x0, K(-0.2), K(0.2));
-          da[a] = abs_(dl) > K(0) ? (dl / abs_(dl)) * abs_(dl) : K(0);  // deadband 0 (trap 8)
+          // delta_direction * (|delta| - deadband) / (1 - deadband) with deadband 0 (trap 8): delta / |delta| is exactly
+          // +-1, so the product is delta itself for every non-zero delta
+          da[a] = dl != K(0) ? dl : K(0);
         }
         sl[(LS::ADM_X) * 32] = S(x0);
         sl[(LS::ADM_X + 1) * 32] = S(x1);

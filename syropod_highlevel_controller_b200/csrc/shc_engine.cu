@@ -35,7 +35,7 @@ using PrecMixed = Prec<float, float, double>;  // fp32 state + trajectory; fp64 
 // The full engine (auto / IMU / inclination posing, admittance) keeps more state live across the leg loop: it trades
 // occupancy for registers (SHC_MIN_BLOCKS_FULL warps per SM) instead of spilling.
 #ifndef SHC_MIN_BLOCKS_FULL
-#define SHC_MIN_BLOCKS_FULL 10
+#define SHC_MIN_BLOCKS_FULL 12
 #endif
 #ifdef SHC_MAXNREG
 #define SHC_KERNEL_BOUNDS __maxnreg__(SHC_MAXNREG)

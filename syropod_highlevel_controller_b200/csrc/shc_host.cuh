@@ -15,6 +15,7 @@
 
 #include "../../include/shc_state.h"
 #include "shc_cycle.cuh"
+#include "shc_startup.cuh"
 
 namespace shc {
 
@@ -178,113 +179,36 @@ inline void compute_step_cycle(const shc_config& c, shc_startup& su) {
 template <int D>
 double host_apply_ik(const RealConsts<double>& ck, const shc_config& c, int leg, double* q, double* qd, V3<double> desired,
                      bool simulation, V3<double>* tip_robot) {
-  Chain<double, D> ch;
-  leg_chain<double, D>(ck.leg[leg], q, ch);
-  V3<double> des_leg;
-  apply_ik_step<double, D>(ck, ck.leg[leg], ch, q, qd, desired, c.clamp_joint_positions != 0, c.clamp_joint_velocities != 0 && !simulation,
-                           &des_leg);
-  Chain<double, D> ch2;
-  leg_chain<double, D>(ck.leg[leg], q, ch2);
-  if (tip_robot) *tip_robot = t1_rotate(ck.leg[leg], ch2.tip) + V3<double>{ck.leg[leg].t1p[0], ck.leg[leg].t1p[1], ck.leg[leg].t1p[2]};
-  return ik_result_value<double, D>(ck.leg[leg], ch2, q, des_leg);
+  return apply_ik_full<D>(ck, leg, q, qd, desired, c.clamp_joint_positions != 0, c.clamp_joint_velocities != 0 && !simulation, tip_robot);
 }
 
-template <int D> V3<double> host_fk(const RealConsts<double>& ck, int leg, const double* q) {
-  Chain<double, D> ch;
-  leg_chain<double, D>(ck.leg[leg], q, ch);
-  return t1_rotate(ck.leg[leg], ch.tip) + V3<double>{ck.leg[leg].t1p[0], ck.leg[leg].t1p[1], ck.leg[leg].t1p[2]};
-}
+template <int D> V3<double> host_fk(const RealConsts<double>& ck, int leg, const double* q) { return leg_fk<D>(ck, leg, q); }
 
 // directStartup + generateWorkspaces + generateWalkspace + generateLimits.
 template <int D> void compute_startup(const shc_config& c, const RealConsts<double>& ck, shc_startup& su) {
   const int L = c.leg_count;
   const double dt = c.time_delta;
-  // Body pose during the start-up cycles: walk-plane pose (0,0,clearance) with identity rotation; manual, inclination
-  // and auto poses are identities while STOPPED with no inputs (pose_controller.cpp:811-859).
-  const PoseT<double> body{{0.0, 0.0, c.body_clearance}, qidentity<double>()};
   const double pi = kPi;
+  const StartupParams sp = startup_params(c);
 
   for (int l = 0; l < L; ++l) {
-    // ---- PoseController::directStartup (:463): simulate stepToPosition + applyIK(true) from the default joint state
-    double q0[D], q[D], qd[D];
-    for (int j = 0; j < D; ++j) {
-      q0[j] = clamp_(0.0, c.joint_min[l][j], c.joint_max[l][j]);  // Joint::default_position_ (model.cpp:1038)
-      q[j] = q0[j];
-      qd[j] = 0.0;
-    }
-    V3<double> origin = host_fk<D>(ck, l, q);
-    V3<double> target{c.stance_x[l], c.stance_y[l], 0.0};  // default tip pose, walk-plane frame
-    V3<double> pdelta = origin - pose_inverse_transform(body, target);
-    if (norm(pdelta) > 0.01) {  // TIP_TOLERANCE; lift_height is 0
-      int num = std::max(1, round_to_int(c.time_to_start / dt));
-      double delta_t = 1.0 / num;
-      int half = num / 2;
-      V3<double> o2t = origin - target;
-      V3<double> n1[5] = {origin, origin, origin, target + o2t * 0.75, target + o2t * 0.5};
-      V3<double> n2[5] = {target + o2t * 0.5, target + o2t * 0.25, target, target, target};
-      for (int count = 1; count <= num; ++count) {
-        double ratio = double(count - 1) / double(num);
-        PoseT<double> dpose = pose_interpolate(pose_identity<double>(), smooth_step(ratio), body);
-        int sic = (count + (num - 1)) % num + 1;
-        V3<double> tip;
-        if (sic <= half) tip = quartic_bezier(n1, sic * delta_t * 2.0);
-        else tip = quartic_bezier(n2, (sic - half) * delta_t * 2.0);
-        V3<double> cmd = pose_inverse_transform(dpose, tip);
-        host_apply_ik<D>(ck, c, l, q, qd, cmd, true, nullptr);
-      }
-    }
-    // LegPoser::transitionConfiguration (:1476): cubic Bezier (o,o,d,d); the last sample is at t = num * (1/num)
-    {
-      int num = std::max(1, round_to_int(c.time_to_start / dt));
-      double t = num * (1.0 / num), s = 1.0 - t;
-      for (int j = 0; j < D; ++j)
-        su.default_joint[l][j] = q0[j] * (s * s * s) + q0[j] * (3.0 * t * s * s) + q[j] * (3.0 * t * t * s) + q[j] * (t * t * t);
-    }
+    // ---- PoseController::directStartup (:463) from the default joint state (model.cpp:1038) ----
+    double q0[D], q[D];
+    for (int j = 0; j < D; ++j) q0[j] = clamp_(0.0, c.joint_min[l][j], c.joint_max[l][j]);  // Joint::default_position_
+    direct_startup_leg<D>(ck, sp, l, q0, q);
+    for (int j = 0; j < D; ++j) su.default_joint[l][j] = q[j];
   }
 
   // ---- Leg::generateWorkspace (model.cpp:309), simple workspace: one plane at height 0, 8 bearings ----
   for (int l = 0; l < L; ++l) {
     double qdef[D];
     for (int j = 0; j < D; ++j) qdef[j] = su.default_joint[l][j];
-    V3<double> identity_tip = pose_inverse_transform(body, V3<double>{c.stance_x[l], c.stance_y[l], 0.0});
-    V3<double> cur = host_fk<D>(ck, l, qdef);
     for (int b = 0; b < SHC_N_BEARINGS; ++b) su.workspace[l][b] = 1.0;  // MAX_WORKSPACE_RADIUS
-    if (norm(identity_tip - cur) > 0.005) {
+    if (!workspace_origin_pass<D>(ck, sp, l, 0.0, 0.1, qdef)) {  // search_height_delta = MAX_WORKSPACE_RADIUS / WORKSPACE_LAYERS
       for (int b = 0; b < SHC_N_BEARINGS; ++b) su.workspace[l][b] = 0.0;
       continue;
     }
-    double q[D], qd[D];
-    // bearing 0 pass: track from the current tip to the workplane origin, then make that the search default
-    {
-      for (int j = 0; j < D; ++j) { q[j] = qdef[j]; qd[j] = 0.0; }
-      int n = std::max(1, round_to_int((1.0 / 10) / 0.002));
-      V3<double> o = cur, tg = identity_tip, tip = cur;
-      bool within = true;
-      for (int it = 1; it <= n; ++it) {
-        double i = double(it) / n;
-        double res = host_apply_ik<D>(ck, c, l, q, qd, o * (1.0 - i) + tg * i, true, &tip);
-        within = within && res != 0.0;
-        if (!within) break;
-      }
-      for (int j = 0; j < D; ++j) qdef[j] = q[j];
-    }
-    for (int bearing = 45; bearing <= 360; bearing += 45) {
-      for (int j = 0; j < D; ++j) { q[j] = qdef[j]; qd[j] = 0.0; }
-      int n = round_to_int(1.0 / 0.002);
-      V3<double> o = identity_tip, tg = identity_tip;
-      double rad = bearing / 360.0 * 2.0 * pi;
-      tg.x += 1.0 * cos(rad);
-      tg.y += 1.0 * sin(rad);
-      V3<double> tip = identity_tip;
-      bool within = true;
-      for (int it = 1; it <= n; ++it) {
-        double i = double(it) / n;
-        double res = host_apply_ik<D>(ck, c, l, q, qd, o * (1.0 - i) + tg * i, true, &tip);
-        within = within && res != 0.0;
-        if (!within) break;
-      }
-      su.workspace[l][bearing / 45] = norm(tip - identity_tip);
-    }
+    for (int bearing = 45; bearing <= 360; bearing += 45) su.workspace[l][bearing / 45] = workspace_bearing_search<D>(ck, sp, l, 0.0, bearing, qdef);
     su.workspace[l][0] = su.workspace[l][8];
   }
 
