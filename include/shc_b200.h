@@ -122,6 +122,27 @@ int shc_rollout(shc_engine* e, int k_cycles, const float* cmd_seq, const float* 
  * pointer float [N][L][D], latched until changed; NULL = all zero.  Only read when use_joint_effort is set. */
 int shc_set_joint_efforts(shc_engine* e, const float* efforts_dev);
 
+/* Start-up on the device.
+ *   shc_startup_begin         PoseController::directStartup (pose_controller.cpp:463) begins for the whole batch: latches
+ *                             every robot's origin configuration (joint_positions_dev, double [N][L][D]: the measured joint
+ *                             states; NULL = the default joint positions), computes the desired configuration of every leg
+ *                             and resets the robots to the post-start-up stepper / walker / poser state.
+ *   shc_startup_step          one loop() of the start-up: LegPoser::transitionConfiguration (:1476) for every joint of the
+ *                             batch (one kernel); joints_out_dev (float [N][L][D]) gets the joint commands.  Returns the
+ *                             reference's progress (1..99, 100 = PROGRESS_COMPLETE: READY) or a negative SHC_E_* code.
+ *   shc_direct_startup        begin + the final iteration only (callers that do not need the trajectory).
+ *   shc_generate_workspaces   Leg::generateWorkspace (model.cpp:309-510) for every leg, the eight bearing searches of a
+ *                             workplane (<= 500 Leg::applyIK(true) steps each) on eight lanes; full = 0 the simple one-plane
+ *                             workspace, 1 the layered workspace of rough-terrain mode.  HOST outputs heights [L][max_planes],
+ *                             radii [L][max_planes][9], n_planes [L].
+ *   shc_host_generate_workspaces  the same routine on the host (no device needed). */
+int shc_startup_begin(shc_engine* e, const double* joint_positions_dev);
+int shc_startup_step(shc_engine* e, float* joints_out_dev, void* stream);
+int shc_direct_startup(shc_engine* e, const double* joint_positions_dev, float* joints_out_dev, void* stream);
+int shc_generate_workspaces(shc_engine* e, int full, int max_planes, double* heights_out, double* radii_out, int* n_planes_out);
+int shc_host_generate_workspaces(const shc_config* cfg, const shc_startup* startup, int full, int max_planes, double* heights_out,
+                                 double* radii_out, int* n_planes_out);
+
 /* Multi-GPU: robots are independent, so the batch is sharded across ranks with no data-path
  * collective; the one exchange is an all-gather of the joint angles per control cycle (BASELINE configs[4]).  NCCL is
  * resolved at run time from the libnccl already loaded in the process.

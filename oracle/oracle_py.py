@@ -81,6 +81,8 @@ def _bind(L):
         L.shc_oracle_solve_ik.argtypes = [C.POINTER(ShcConfig), C.c_int, dp, dp, dp, dp]
         L.shc_oracle_step_cycle.argtypes = [C.POINTER(ShcConfig), C.POINTER(ShcStartup)]
         L.shc_oracle_admittance.argtypes = [C.POINTER(ShcConfig), dp, dp, dp]
+        L.shc_oracle_workspace.argtypes = [C.POINTER(ShcConfig), C.c_int, C.c_int, C.c_int, dp, dp]
+        L.shc_oracle_startup_trajectory.argtypes = [C.POINTER(ShcConfig), dp, C.c_int, dp]
     return L
 
 
@@ -179,3 +181,21 @@ def step_cycle(cfg) -> ShcStartup:
     s = ShcStartup()
     lib().shc_oracle_step_cycle(C.byref(cfg), C.byref(s))
     return s
+
+
+def workspace(cfg, leg: int, full: bool, max_planes: int = 16):
+    """Leg::generateWorkspace (model.cpp:309-510) of one leg after the direct start-up: (heights [P], radii [P, 9])."""
+    h = np.zeros(max_planes)
+    r = np.zeros((max_planes, 9))
+    n = lib().shc_oracle_workspace(C.byref(cfg), leg, int(full), max_planes, _dp(h), _dp(r))
+    assert n <= max_planes
+    return h[:n], r[:n]
+
+
+def startup_trajectory(cfg, q_init=None, max_loops: int = 2000):
+    """Joint commands of every loop() of the direct start-up from joint angles q_init [L, D] (None: defaults): [loops, L, D]."""
+    L, D = cfg.leg_count, cfg.joint_count
+    out = np.zeros((max_loops, L, D))
+    q = None if q_init is None else np.ascontiguousarray(q_init, dtype=np.float64)
+    n = lib().shc_oracle_startup_trajectory(C.byref(cfg), _dp(q), max_loops, _dp(out))
+    return out[:n]

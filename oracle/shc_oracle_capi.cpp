@@ -464,3 +464,72 @@ double shc_oracle_apply_ik(const shc_config* cfg, int leg, double* q, double* qd
   return res;
 }
 }
+
+extern "C" {
+// Leg::generateWorkspace (model.cpp:309-510) of leg `leg` for a robot that has gone through the direct start-up: the
+// simple (full = 0) or the layered rough-terrain workspace (full = 1), planes in ascending height: heights [max_planes],
+// radii [max_planes][9].  Returns the number of planes.
+int shc_oracle_workspace(const shc_config* cfg, int leg, int full, int max_planes, double* heights, double* radii) {
+  Robot r(*cfg);
+  r.stateInit();
+  int loops = 0;
+  while (r.robot_state_ != READY && loops < 100000) {
+    r.requestRobotState(RUNNING);
+    r.loop();
+    ++loops;
+  }
+  const int saved = r.params_.rough_terrain_mode;
+  r.params_.rough_terrain_mode = full ? 1 : 0;  // generateWorkspace: simple_workspace = !rough_terrain_mode (model.cpp:313)
+  Leg search_leg = r.legs[leg];                 // as Model::generateWorkspaces (model.cpp:120) does
+  search_leg.workspace_.clear();
+  search_leg.stepper.leg_ = &search_leg;
+  search_leg.poser.leg_ = &search_leg;
+  search_leg.init(true);
+  Workspace ws = search_leg.generateWorkspace();
+  r.params_.rough_terrain_mode = saved;
+  int p = 0;
+  for (auto& kv : ws) {
+    if (p < max_planes) {
+      heights[p] = kv.first;
+      for (int b = 0; b < SHC_N_BEARINGS; ++b) radii[p * SHC_N_BEARINGS + b] = kv.second.count(b * 45) ? kv.second.at(b * 45) : 0.0;
+    }
+    ++p;
+  }
+  return p;
+}
+
+// The joint commands of every loop() of the direct start-up (state_controller.cpp:254-281, pose_controller.cpp:463) of a
+// robot whose joints are at q_init [L][D] when it begins (NULL: the default joint positions): out [max_loops][L][D], one row
+// per loop() from the first one that moves the joints.  Returns the number of rows.
+int shc_oracle_startup_trajectory(const shc_config* cfg, const double* q_init, int max_loops, double* out) {
+  Robot r(*cfg);
+  r.stateInit();
+  const int L = r.leg_count_, D = cfg->joint_count;
+  if (q_init) {  // jointStatesCallback + initModel(false) (state_controller.cpp:1565-1590, model.cpp:286)
+    for (int l = 0; l < L; ++l) {
+      for (int j = 0; j < D; ++j) {
+        Joint& jt = r.legs[l].joints[j + 1];
+        jt.current_position_ = q_init[l * D + j];
+        jt.desired_position_ = jt.current_position_;
+        jt.prev_desired_position_ = jt.desired_position_;
+      }
+      r.legs[l].applyFK();
+      r.legs[l].desired_tip_pose_ = r.legs[l].current_tip_pose_;
+    }
+  }
+  int rows = 0, loops = 0;
+  while (r.robot_state_ != READY && loops < 100000) {
+    r.requestRobotState(RUNNING);
+    const bool moving = r.robot_state_ == PACKED;  // the first loop() only leaves UNKNOWN
+    r.loop();
+    ++loops;
+    if (moving && rows < max_loops) {
+      for (int l = 0; l < L; ++l)
+        for (int j = 0; j < D; ++j) out[((size_t)rows * L + l) * D + j] = r.legs[l].joints[j + 1].desired_position_;
+      ++rows;
+    }
+  }
+  return rows;
+}
+}
+

@@ -182,6 +182,48 @@ __global__ void __launch_bounds__(128) apply_ik_kernel(const __grid_constant__ C
   if (result) result[i] = ik_result_value<double, D>(lc, ch2, q, des_leg);
 }
 
+// ---- start-up on the device ---------------------------------------------------------------------
+// Copies tile 0 of a plane set over the tiles 1 .. n_tiles-1 (a new batch is n_tiles copies of one initial tile).
+template <class W> __global__ void replicate_tile_kernel(W* planes, size_t tile_words, size_t n_tiles) {
+  const size_t total = tile_words * (n_tiles - 1);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    planes[tile_words + i] = planes[i % tile_words];
+}
+
+// One cycle of PoseController::directStartup (pose_controller.cpp:463) for the batch = LegPoser::transitionConfiguration
+// (:1476) of every joint of every robot: iteration `it` of the joint-space move from the robot's own origin configuration
+// (its joint angles when the start-up began) to the batch-wide desired configuration.  One thread per joint.  The joint
+// commands go to joints_out; the last iteration also seats the configuration in the state planes (velocities zero).
+template <class S, int D>
+__global__ void __launch_bounds__(256) transition_configuration_kernel(const __grid_constant__ Consts c, Planes<S> pl, const double* __restrict__ origin,
+                                                                       const double* __restrict__ desired, int it, int num,
+                                                                       float* __restrict__ joints_out, int write_state) {
+  const int L = c.i.L;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)c.i.n_robots * L * D) return;
+  const int j = (int)(i % D), l = (int)((i / D) % L), r = (int)(i / ((long long)D * L));
+  const LegConsts<double>& lc = c.d.leg[l];
+  const double o = origin ? origin[i] : clamp_(0.0, lc.jmin[j], lc.jmax[j]);  // Joint::default_position_ (model.cpp:1038)
+  const double q = transition_configuration(o, desired[l * kMaxDof + j], it, num);
+  if (joints_out) joints_out[i] = (float)(q + lc.joffset[j]);
+  if (write_state) {
+    S* sp_ = pl.s + ((size_t)(r >> 5) * c.i.nS + c.i.offS_leg + l * c.i.strideS_leg) * 32 + (r & 31);
+    sp_[(LegS<D>::Q + j) * 32] = S(q);
+    sp_[(LegS<D>::QD + j) * 32] = S(0);
+  }
+}
+
+// Leg::generateWorkspace (model.cpp:309-510) for every leg: one block per leg, eight lanes = the eight bearings of a plane.
+template <int D>
+__global__ void __launch_bounds__(32) workspace_sweep_kernel(const __grid_constant__ Consts c, StartupParams sp, const double* __restrict__ qdef,
+                                                             int full, int max_planes, double* heights, double* radii, int* n_planes) {
+  const int l = blockIdx.x, lane = threadIdx.x;
+  if (lane >= 8) return;
+  const int np = workspace_sweep_leg<D>(c.d, sp, l, qdef + l * kMaxDof, full != 0, max_planes, lane, 8, heights + (size_t)l * max_planes,
+                                        radii + (size_t)l * max_planes * SHC_N_BEARINGS);
+  if (lane == 0) n_planes[l] = np;
+}
+
 }  // namespace shc
 
 using namespace shc;
@@ -262,6 +304,11 @@ struct shc_engine {
   float* gather_mc = nullptr;
   bool gather_owned = false;
   bool gather_opened[8] = {false, false, false, false, false, false, false, false};
+  // direct start-up on the device (shc_startup_begin / shc_startup_step)
+  double* startup_origin = nullptr;   // [N][L][D] joint angles when the start-up began
+  double* startup_desired = nullptr;  // [kMaxLegs][kMaxDof] desired configuration
+  bool startup_has_origin = false;
+  int startup_iteration = 0, startup_num = 0;
   int* gather_err = nullptr;  // mapped pinned word: set by a device-side wait that gave up
   cudaStream_t signal = nullptr;  // high-priority stream of the landed-signal kernels
   unsigned long long* gather_trace = nullptr;  // tuning (SHC_GATHER_TRACE): mapped pinned stamps [4096][4]: kernel end, signal
@@ -364,6 +411,33 @@ int upload(shc_engine* e, const HostPlanes& h) {
 }  // namespace
 
 
+// Every robot of the batch into the post-start-up state: one packed tile goes up, the device replicates it.
+static int reset_to_initial_state(shc_engine* e) {
+  const IntConsts& ci = e->c.i;
+  const size_t n_tiles = ci.n_pad / 32;
+  HostPlanes t;
+  initial_tile(e, t);
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (e->precision == SHC_PRECISION_F64) {
+    CUDA_TRY(cudaMemcpy(e->s_planes, t.s.data(), t.s.size() * 8, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<float> tmp(t.s.begin(), t.s.end());
+    CUDA_TRY(cudaMemcpy(e->s_planes, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice));
+  }
+  CUDA_TRY(cudaMemcpy(e->d_planes, t.d.data(), t.d.size() * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(e->i_planes, t.i.data(), t.i.size() * 4, cudaMemcpyHostToDevice));
+  if (n_tiles > 1) {
+    const int blocks = 148 * 8;
+    if (e->precision == SHC_PRECISION_F64) replicate_tile_kernel<double><<<blocks, 256>>>((double*)e->s_planes, t.s.size(), n_tiles);
+    else replicate_tile_kernel<float><<<blocks, 256>>>((float*)e->s_planes, t.s.size(), n_tiles);
+    replicate_tile_kernel<double><<<blocks, 256>>>(e->d_planes, t.d.size(), n_tiles);
+    replicate_tile_kernel<int><<<blocks, 256>>>(e->i_planes, t.i.size(), n_tiles);
+    CUDA_TRY(cudaGetLastError());
+  }
+  CUDA_TRY(cudaDeviceSynchronize());
+  return SHC_OK;
+}
+
 // Calls f(kernel pointer, Planes) for the instantiation this engine runs.
 template <class F> static int with_cycle_kernel(shc_engine* e, F&& f) {
   const bool full = engine_full(e->cfg);
@@ -458,9 +532,7 @@ int shc_create(const shc_config* cfg, const shc_startup* startup, int n_robots, 
 
   // every robot starts in the post-start-up state
   {
-    HostPlanes h;
-    initial_planes(e, h);
-    int rc = upload(e, h);
+    int rc = reset_to_initial_state(e);
     if (rc != SHC_OK) { std::string m = g_err; return cleanup(rc, m); }
   }
   *out = e;
@@ -533,6 +605,8 @@ void shc_destroy(shc_engine* e) {
   cudaFree(e->d_planes);
   cudaFree(e->i_planes);
   cudaFree(e->d_flags);
+  cudaFree(e->startup_origin);
+  cudaFree(e->startup_desired);
   cudaFree(e->d_cmd); cudaFree(e->d_imu); cudaFree(e->d_force); cudaFree(e->d_manual); cudaFree(e->d_out);
   cudaFreeHost(e->h_cmd); cudaFreeHost(e->h_imu); cudaFreeHost(e->h_force); cudaFreeHost(e->h_manual); cudaFreeHost(e->h_out);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -809,6 +883,149 @@ int shc_apply_ik(shc_engine* e, int n_legs, const int* leg_id, double* q, double
     if (err != cudaSuccess) return fail(SHC_E_CUDA, std::string("apply_ik launch: ") + cudaGetErrorString(err));
     return SHC_OK;
   });
+}
+
+// PoseController::directStartup (pose_controller.cpp:463) for the whole batch on the device.
+//   shc_startup_begin  the start-up begins: every robot's origin configuration is latched (joint_positions_dev, double
+//                      [N][L][D]: the measured joint states of jointStatesCallback; NULL = the default joint positions), the
+//                      desired configuration of every leg is computed (test-leg IK replay, csrc/shc_startup.cuh) and the
+//                      robots' stepper / walker / poser state is reset to the post-start-up state.
+//   shc_startup_step   one loop() of the start-up: LegPoser::transitionConfiguration for every joint of the batch (one
+//                      kernel); joints_out_dev (float [N][L][D]) gets the joint commands to publish.  Returns the reference's
+//                      progress value (1..99 while moving, 100 = PROGRESS_COMPLETE: the robots are READY and their state
+//                      planes hold the configuration reached), or a negative SHC_E_* code.
+//   shc_direct_startup begin + the last iteration only: for callers that do not need the trajectory.
+int shc_startup_begin(shc_engine* e, const double* joint_positions_dev) {
+  if (!e) return fail(SHC_E_INVALID, "null engine");
+  CUDA_TRY(cudaSetDevice(e->device));
+  int rc = reset_to_initial_state(e);
+  if (rc != SHC_OK) return rc;
+  const size_t count = (size_t)e->n * e->cfg.leg_count * e->cfg.joint_count;
+  if (joint_positions_dev) {
+    if (!e->startup_origin) CUDA_TRY(cudaMalloc((void**)&e->startup_origin, count * 8));
+    CUDA_TRY(cudaMemcpy(e->startup_origin, joint_positions_dev, count * 8, cudaMemcpyDeviceToDevice));
+    e->startup_has_origin = true;
+  } else {
+    e->startup_has_origin = false;
+  }
+  double desired[kMaxLegs][kMaxDof] = {};
+  const StartupParams sp = startup_params(e->cfg);
+  dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int {
+    for (int l = 0; l < e->cfg.leg_count; ++l) startup_desired_configuration<decltype(dtag)::value>(e->c.d, sp, l, desired[l]);
+    return SHC_OK;
+  });
+  if (!e->startup_desired) CUDA_TRY(cudaMalloc((void**)&e->startup_desired, sizeof(desired)));
+  CUDA_TRY(cudaMemcpy(e->startup_desired, desired, sizeof(desired), cudaMemcpyHostToDevice));
+  e->startup_iteration = 0;
+  e->startup_num = sp.startup_iterations;
+  return SHC_OK;
+}
+
+static int startup_launch(shc_engine* e, int it, float* joints_out_dev, cudaStream_t st) {
+  const long long total = (long long)e->n * e->cfg.leg_count * e->cfg.joint_count;
+  const int threads = 256, blocks = (int)((total + threads - 1) / threads);
+  const double* origin = e->startup_has_origin ? e->startup_origin : nullptr;
+  const int last = it >= e->startup_num;
+  return dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int {
+    constexpr int D = decltype(dtag)::value;
+    if (e->precision == SHC_PRECISION_F64) {
+      Planes<double> pl{(double*)e->s_planes, e->d_planes, e->i_planes};
+      transition_configuration_kernel<double, D><<<blocks, threads, 0, st>>>(e->c, pl, origin, e->startup_desired, it, e->startup_num, joints_out_dev, last);
+    } else {
+      Planes<float> pl{(float*)e->s_planes, e->d_planes, e->i_planes};
+      transition_configuration_kernel<float, D><<<blocks, threads, 0, st>>>(e->c, pl, origin, e->startup_desired, it, e->startup_num, joints_out_dev, last);
+    }
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(SHC_E_CUDA, std::string("transition_configuration launch: ") + cudaGetErrorString(err));
+    return SHC_OK;
+  });
+}
+
+int shc_startup_step(shc_engine* e, float* joints_out_dev, void* stream) {
+  if (!e) return fail(SHC_E_INVALID, "null engine");
+  if (e->startup_num <= 0) return fail(SHC_E_INVALID, "shc_startup_begin has not been called");
+  if (e->startup_iteration >= e->startup_num) return 100;  // PROGRESS_COMPLETE
+  CUDA_TRY(cudaSetDevice(e->device));
+  const int it = ++e->startup_iteration;
+  int rc = startup_launch(e, it, joints_out_dev, stream ? (cudaStream_t)stream : e->stream);
+  if (rc != SHC_OK) return rc;
+  if (it >= e->startup_num) return 100;
+  const int progress = int((double(it - 1) / double(e->startup_num)) * 100);
+  return progress < 1 ? 1 : progress;
+}
+
+int shc_direct_startup(shc_engine* e, const double* joint_positions_dev, float* joints_out_dev, void* stream) {
+  int rc = shc_startup_begin(e, joint_positions_dev);
+  if (rc != SHC_OK) return rc;
+  e->startup_iteration = e->startup_num;
+  return startup_launch(e, e->startup_num, joints_out_dev, stream ? (cudaStream_t)stream : e->stream);
+}
+
+// Model::generateWorkspaces (model.cpp:120) / Leg::generateWorkspace (:309-510) on the device: one block per leg, the eight
+// bearing searches of a workplane (up to 500 Leg::applyIK(true) steps each) on eight lanes.  full = 0: the simple workspace
+// (one plane at height 0, what the engine's limit tables are built from); full = 1: the layered workspace of rough-terrain
+// mode.  Host outputs: heights [L][max_planes], radii [L][max_planes][9] (bearings 0..360 step 45), n_planes [L] (planes
+// generated; more than max_planes means the tail was dropped).  The legs start from the engine's default configuration.
+int shc_generate_workspaces(shc_engine* e, int full, int max_planes, double* heights_out, double* radii_out, int* n_planes_out) {
+  if (!e || max_planes < 1 || !heights_out || !radii_out || !n_planes_out) return fail(SHC_E_INVALID, "shc_generate_workspaces: bad arguments");
+  CUDA_TRY(cudaSetDevice(e->device));
+  const int L = e->cfg.leg_count;
+  double *d_q = nullptr, *d_h = nullptr, *d_r = nullptr;
+  int* d_n = nullptr;
+  const size_t nh = (size_t)L * max_planes, nr = nh * SHC_N_BEARINGS;
+  auto cleanup = [&] { cudaFree(d_q); cudaFree(d_h); cudaFree(d_r); cudaFree(d_n); };
+  if (cudaMalloc((void**)&d_q, sizeof(e->su.default_joint)) != cudaSuccess || cudaMalloc((void**)&d_h, nh * 8) != cudaSuccess ||
+      cudaMalloc((void**)&d_r, nr * 8) != cudaSuccess || cudaMalloc((void**)&d_n, L * 4) != cudaSuccess) {
+    cleanup();
+    return fail(SHC_E_CUDA, "shc_generate_workspaces: device allocation failed");
+  }
+  cudaMemcpy(d_q, e->su.default_joint, sizeof(e->su.default_joint), cudaMemcpyHostToDevice);
+  cudaMemset(d_h, 0, nh * 8);
+  cudaMemset(d_r, 0, nr * 8);
+  const StartupParams sp = startup_params(e->cfg);
+  int rc = dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int {
+    constexpr int D = decltype(dtag)::value;
+    workspace_sweep_kernel<D><<<L, 32, 0, e->stream>>>(e->c, sp, d_q, full, max_planes, d_h, d_r, d_n);
+    return SHC_OK;
+  });
+  cudaError_t err = cudaStreamSynchronize(e->stream);
+  if (err == cudaSuccess) err = cudaMemcpy(heights_out, d_h, nh * 8, cudaMemcpyDeviceToHost);
+  if (err == cudaSuccess) err = cudaMemcpy(radii_out, d_r, nr * 8, cudaMemcpyDeviceToHost);
+  if (err == cudaSuccess) err = cudaMemcpy(n_planes_out, d_n, L * 4, cudaMemcpyDeviceToHost);
+  cleanup();
+  if (err != cudaSuccess) return fail(SHC_E_CUDA, std::string("shc_generate_workspaces: ") + cudaGetErrorString(err));
+  return rc;
+}
+
+// The same sweep on the host (double, the very routine the kernel runs: csrc/shc_startup.cuh), for callers without a device
+// at hand and for the CPU tests.  `startup` NULL: the engine's own default configuration for `cfg`.
+int shc_host_generate_workspaces(const shc_config* cfg, const shc_startup* startup, int full, int max_planes, double* heights_out,
+                                 double* radii_out, int* n_planes_out) {
+  if (!cfg || max_planes < 1 || !heights_out || !radii_out || !n_planes_out) return fail(SHC_E_INVALID, "shc_host_generate_workspaces: bad arguments");
+  std::string err;
+  bool unsupported = false;
+  if (!check_supported(*cfg, err, unsupported)) return fail(unsupported ? SHC_E_UNSUPPORTED : SHC_E_INVALID, err);
+  shc_startup su;
+  if (startup) su = *startup;
+  else {
+    int rc = shc_compute_startup(cfg, &su);
+    if (rc != SHC_OK) return rc;
+  }
+  RealConsts<double>* ck = new RealConsts<double>();
+  fill_static_consts<double>(*cfg, *ck);
+  const StartupParams sp = startup_params(*cfg);
+  int rc = dispatch_D(cfg->joint_count, [&](auto dtag) -> int {
+    constexpr int D = decltype(dtag)::value;
+    for (int l = 0; l < cfg->leg_count; ++l) {
+      for (size_t k = 0; k < (size_t)max_planes; ++k) heights_out[(size_t)l * max_planes + k] = 0.0;
+      for (size_t k = 0; k < (size_t)max_planes * SHC_N_BEARINGS; ++k) radii_out[(size_t)l * max_planes * SHC_N_BEARINGS + k] = 0.0;
+      n_planes_out[l] = workspace_sweep_leg<D>(*ck, sp, l, su.default_joint[l], full != 0, max_planes, 0, 1, heights_out + (size_t)l * max_planes,
+                                               radii_out + (size_t)l * max_planes * SHC_N_BEARINGS);
+    }
+    return SHC_OK;
+  });
+  delete ck;
+  return rc;
 }
 
 int shc_nccl_unique_id(void* out128) {

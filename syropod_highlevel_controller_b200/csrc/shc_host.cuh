@@ -193,23 +193,19 @@ template <int D> void compute_startup(const shc_config& c, const RealConsts<doub
 
   for (int l = 0; l < L; ++l) {
     // ---- PoseController::directStartup (:463) from the default joint state (model.cpp:1038) ----
-    double q0[D], q[D];
-    for (int j = 0; j < D; ++j) q0[j] = clamp_(0.0, c.joint_min[l][j], c.joint_max[l][j]);  // Joint::default_position_
-    direct_startup_leg<D>(ck, sp, l, q0, q);
-    for (int j = 0; j < D; ++j) su.default_joint[l][j] = q[j];
+    double q[D];
+    startup_desired_configuration<D>(ck, sp, l, q);
+    for (int j = 0; j < D; ++j) {
+      const double q0 = clamp_(0.0, c.joint_min[l][j], c.joint_max[l][j]);  // Joint::default_position_: where a new robot's joints are
+      su.default_joint[l][j] = transition_configuration(q0, q[j], sp.startup_iterations, sp.startup_iterations);
+    }
   }
 
   // ---- Leg::generateWorkspace (model.cpp:309), simple workspace: one plane at height 0, 8 bearings ----
   for (int l = 0; l < L; ++l) {
-    double qdef[D];
-    for (int j = 0; j < D; ++j) qdef[j] = su.default_joint[l][j];
-    for (int b = 0; b < SHC_N_BEARINGS; ++b) su.workspace[l][b] = 1.0;  // MAX_WORKSPACE_RADIUS
-    if (!workspace_origin_pass<D>(ck, sp, l, 0.0, 0.1, qdef)) {  // search_height_delta = MAX_WORKSPACE_RADIUS / WORKSPACE_LAYERS
-      for (int b = 0; b < SHC_N_BEARINGS; ++b) su.workspace[l][b] = 0.0;
-      continue;
-    }
-    for (int bearing = 45; bearing <= 360; bearing += 45) su.workspace[l][bearing / 45] = workspace_bearing_search<D>(ck, sp, l, 0.0, bearing, qdef);
-    su.workspace[l][0] = su.workspace[l][8];
+    double h, radii[SHC_N_BEARINGS];
+    workspace_sweep_leg<D>(ck, sp, l, su.default_joint[l], false, 1, 0, 1, &h, radii);
+    for (int b = 0; b < SHC_N_BEARINGS; ++b) su.workspace[l][b] = radii[b];
   }
 
   // ---- WalkController::generateWalkspace (walk_controller.cpp:57) ----

@@ -362,22 +362,31 @@ template <class E> int core_init(E* e, const shc_config& cfg, const shc_startup*
   return SHC_OK;
 }
 
-// Planes of a new engine: every robot in the post-start-up state (one packed tile, replicated).
-template <class E> void initial_planes(const E* e, HostPlanes& h) {
+// One tile (32 robots) of a new engine: every robot in the post-start-up state.  `h` is sized for one tile.
+template <class E> void initial_tile(const E* e, HostPlanes& h) {
   const IntConsts& ci = e->c.i;
-  const size_t np = ci.n_pad;
   shc_robot_state init;
   dispatch_D_raw(e->cfg.joint_count, [&](auto dtag) -> int { initial_state<decltype(dtag)::value>(e->cfg, e->c.d, e->su, init); return 0; });
-  h.s.assign((size_t)ci.nS * np, 0.0);
-  h.d.assign((size_t)ci.nD * np, 0.0);
-  h.i.assign((size_t)ci.nI * np, 0);
+  h.s.assign((size_t)ci.nS * 32, 0.0);
+  h.d.assign((size_t)ci.nD * 32, 0.0);
+  h.i.assign((size_t)ci.nI * 32, 0);
   std::vector<shc_robot_state> tile_states(32, init);
   pack(e, tile_states.data(), 32, h, 32);
-  const size_t n_tiles = np / 32;
-  for (size_t t = 1; t < n_tiles; ++t) {
-    std::copy(h.s.begin(), h.s.begin() + (size_t)ci.nS * 32, h.s.begin() + t * (size_t)ci.nS * 32);
-    std::copy(h.d.begin(), h.d.begin() + (size_t)ci.nD * 32, h.d.begin() + t * (size_t)ci.nD * 32);
-    std::copy(h.i.begin(), h.i.begin() + (size_t)ci.nI * 32, h.i.begin() + t * (size_t)ci.nI * 32);
+}
+
+// Planes of a new engine: the initial tile, replicated over the batch (host side; the engine replicates on the device).
+template <class E> void initial_planes(const E* e, HostPlanes& h) {
+  const IntConsts& ci = e->c.i;
+  const size_t n_tiles = ci.n_pad / 32;
+  HostPlanes t;
+  initial_tile(e, t);
+  h.s.resize(t.s.size() * n_tiles);
+  h.d.resize(t.d.size() * n_tiles);
+  h.i.resize(t.i.size() * n_tiles);
+  for (size_t k = 0; k < n_tiles; ++k) {
+    std::copy(t.s.begin(), t.s.end(), h.s.begin() + k * t.s.size());
+    std::copy(t.d.begin(), t.d.end(), h.d.begin() + k * t.d.size());
+    std::copy(t.i.begin(), t.i.end(), h.i.begin() + k * t.i.size());
   }
 }
 

@@ -44,6 +44,11 @@ def lib():
         dp = C.POINTER(C.c_double)
         L.shc_host_apply_ik.argtypes = [C.POINTER(ShcConfig), C.c_int, dp, dp, dp, C.c_int, dp, dp]
         L.shc_get_startup.argtypes = [vp, C.POINTER(ShcStartup)]
+        L.shc_startup_begin.argtypes = [vp, vp]
+        L.shc_startup_step.argtypes = [vp, vp, vp]
+        L.shc_direct_startup.argtypes = [vp, vp, vp, vp]
+        L.shc_generate_workspaces.argtypes = [vp, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int)]
+        L.shc_host_generate_workspaces.argtypes = [C.POINTER(ShcConfig), C.POINTER(ShcStartup), C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int)]
         L.shc_n_robots.argtypes = [vp]
         L.shc_options.argtypes = [vp]
         L.shc_set_options.argtypes = [vp, C.c_int]
@@ -98,6 +103,17 @@ def compute_startup(cfg: ShcConfig) -> ShcStartup:
     s = ShcStartup()
     _check(lib().shc_compute_startup(C.byref(cfg), C.byref(s)))
     return s
+
+
+def host_generate_workspaces(cfg: ShcConfig, full: bool = False, max_planes: int = 16, startup: Optional[ShcStartup] = None):
+    """Leg::generateWorkspace (model.cpp:309-510) for every leg on the host with the routine the device sweep runs.
+    Returns (heights [L, P], radii [L, P, 9], n_planes [L]); planes in generation order."""
+    dp = C.POINTER(C.c_double)
+    L = cfg.leg_count
+    h, r, n = np.zeros((L, max_planes)), np.zeros((L, max_planes, 9)), np.zeros(L, dtype=np.int32)
+    _check(lib().shc_host_generate_workspaces(C.byref(cfg), C.byref(startup) if startup is not None else None, int(full), max_planes,
+                                              h.ctypes.data_as(dp), r.ctypes.data_as(dp), n.ctypes.data_as(C.POINTER(C.c_int))))
+    return h, r, n
 
 
 def host_apply_ik(cfg: ShcConfig, leg: int, q, qd, desired, simulation: bool = True):
@@ -179,6 +195,38 @@ class Engine:
         """int32 [N] status words of the last cycle (needs OPT_STATUS_FLAGS)."""
         out = np.empty(self.n, dtype=np.int32)
         _check(lib().shc_get_status_flags(self._h, out.ctypes.data_as(C.POINTER(C.c_int))))
+        return out
+
+    # ---- start-up on the device -------------------------------------------------------------------------------------
+    def generate_workspaces(self, full: bool = False, max_planes: int = 16):
+        """Leg::generateWorkspace for every leg on the device (one block per leg, eight lanes = eight bearings).
+        Returns (heights [L, P], radii [L, P, 9], n_planes [L])."""
+        dp = C.POINTER(C.c_double)
+        h, r, n = np.zeros((self.L, max_planes)), np.zeros((self.L, max_planes, 9)), np.zeros(self.L, dtype=np.int32)
+        _check(lib().shc_generate_workspaces(self._h, int(full), max_planes, h.ctypes.data_as(dp), r.ctypes.data_as(dp),
+                                             n.ctypes.data_as(C.POINTER(C.c_int))))
+        return h, r, n
+
+    def startup_begin(self, joint_positions=None):
+        """PoseController::directStartup begins: joint_positions [N, L, D] float64 device tensor (measured joint states) or None."""
+        if joint_positions is not None:
+            t = self.torch
+            assert joint_positions.is_cuda and joint_positions.dtype == t.float64 and joint_positions.is_contiguous()
+            assert tuple(joint_positions.shape) == (self.n, self.L, self.D)
+        _check(lib().shc_startup_begin(self._h, _ptr(joint_positions)))
+
+    def startup_step(self, out=None, stream=None) -> int:
+        """One loop() of the start-up for the batch; joint commands into `out` (default: self.joints).  Returns the progress
+        (100 = complete)."""
+        out = self._out(out)
+        rc = lib().shc_startup_step(self._h, _ptr(out), _stream_handle(self.torch, self.device, stream))
+        if rc < 0:
+            _check(rc)
+        return rc
+
+    def direct_startup(self, joint_positions=None, out=None, stream=None):
+        out = self._out(out)
+        _check(lib().shc_direct_startup(self._h, _ptr(joint_positions), _ptr(out), _stream_handle(self.torch, self.device, stream)))
         return out
 
     # ---- state ------------------------------------------------------------------------------------------------------
