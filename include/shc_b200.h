@@ -17,6 +17,7 @@
 #include <stddef.h>
 
 #include "shc_config.h"
+#include "shc_msgs.h"
 #include "shc_state.h"
 
 #ifdef __cplusplus
@@ -121,6 +122,15 @@ int shc_rollout(shc_engine* e, int k_cycles, const float* cmd_seq, const float* 
 /* Measured joint efforts for Leg::calculateTipForce (jointStatesCallback, state_controller.cpp:1565-1590): device
  * pointer float [N][L][D], latched until changed; NULL = all zero.  Only read when use_joint_effort is set. */
 int shc_set_joint_efforts(shc_engine* e, const float* efforts_dev);
+
+/* Output wire formats (records in shc_msgs.h): JointState, LegState, velocity / pose / rotation-error
+ * and frame-transform records of the robots [first, first + count) as of the last cycle, packed by ONE kernel from the state
+ * planes (one thread per leg) — the per-leg / per-joint host loops of state_controller.cpp:777-1047 disappear.  Outputs:
+ * joint_state_out [count], leg_state_out [count][L], body_out [count]; device memory or page-locked host memory (written
+ * in place, no copy); any may be NULL.  measured_joint_positions_dev: float [N][L][D] or NULL (LegState.actual_tip_pose).
+ * Asynchronous on `stream` (NULL = the engine's). */
+int shc_pack_messages(shc_engine* e, size_t first, size_t count, const float* measured_joint_positions_dev,
+                      shc_joint_state_msg* joint_state_out, shc_leg_state_msg* leg_state_out, shc_body_msg* body_out, void* stream);
 
 /* Start-up on the device.
  *   shc_startup_begin         PoseController::directStartup (pose_controller.cpp:463) begins for the whole batch: latches

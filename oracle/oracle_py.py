@@ -12,7 +12,8 @@ import subprocess
 
 import numpy as np
 
-from syropod_highlevel_controller_b200.config import ShcConfig, ShcRobotState, ShcStartup
+from syropod_highlevel_controller_b200.config import (ShcBodyMsg, ShcConfig, ShcJointStateMsg, ShcLegStateMsg, ShcRobotState,
+                                                      ShcStartup)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libshc_oracle.so")
@@ -81,6 +82,8 @@ def _bind(L):
         L.shc_oracle_solve_ik.argtypes = [C.POINTER(ShcConfig), C.c_int, dp, dp, dp, dp]
         L.shc_oracle_step_cycle.argtypes = [C.POINTER(ShcConfig), C.POINTER(ShcStartup)]
         L.shc_oracle_admittance.argtypes = [C.POINTER(ShcConfig), dp, dp, dp]
+        L.shc_oracle_batch_get_messages.argtypes = [C.c_void_p, C.c_int, dp, C.POINTER(ShcJointStateMsg), C.POINTER(ShcLegStateMsg),
+                                                    C.POINTER(ShcBodyMsg)]
         L.shc_oracle_workspace.argtypes = [C.POINTER(ShcConfig), C.c_int, C.c_int, C.c_int, dp, dp]
         L.shc_oracle_startup_trajectory.argtypes = [C.POINTER(ShcConfig), dp, C.c_int, dp]
     return L
@@ -158,6 +161,13 @@ class OracleBatch:
         arr = (ShcRobotState * self.n)()
         self._lib.shc_oracle_batch_get_state(self._h, arr)
         return arr
+
+    def messages(self, index: int, measured=None):
+        """The reference's publishers (state_controller.cpp:777-1047) for one robot: (JointState, LegState x L, body)."""
+        js, legs, body = ShcJointStateMsg(), (ShcLegStateMsg * self.L)(), ShcBodyMsg()
+        m = _arr(measured)
+        self._lib.shc_oracle_batch_get_messages(self._h, index, _dp(m), C.byref(js), legs, C.byref(body))
+        return js, legs, body
 
     def set_state(self, arr):
         self._lib.shc_oracle_batch_set_state(self._h, arr)

@@ -5,6 +5,7 @@
 #include <thread>
 #include <vector>
 
+#include "../include/shc_msgs.h"
 #include "../include/shc_state.h"
 #include "shc_oracle.hpp"
 
@@ -530,6 +531,77 @@ int shc_oracle_startup_trajectory(const shc_config* cfg, const double* q_init, i
     }
   }
   return rows;
+}
+}
+
+extern "C" {
+// The reference's publishers (state_controller.cpp:777-1047) for robot `index` of the batch, restated on the oracle's robot:
+// publishDesiredJointState, publishLegState (msg/LegState.msg), publishVelocity / Pose / RotationPoseError and
+// publishFrameTransforms, into the records of include/shc_msgs.h.  measured [L][D] = measured joint positions or NULL.
+void shc_oracle_batch_get_messages(void* h, int index, const double* measured, shc_joint_state_msg* js, shc_leg_state_msg* legs,
+                                   shc_body_msg* body) {
+  Batch* b = static_cast<Batch*>(h);
+  Robot& r = *b->robots[index];
+  const int L = r.leg_count_, D = b->cfg.joint_count;
+  std::memset(js, 0, sizeof(*js));
+  for (int l = 0; l < L; ++l) {
+    Leg& leg = r.legs[l];
+    shc_leg_state_msg& m = legs[l];
+    std::memset(&m, 0, sizeof(m));
+    putPose(m.walker_tip_pose, leg.stepper.current_tip_pose_);
+    putPose(m.target_tip_pose, leg.stepper.target_tip_pose_);
+    putPose(m.poser_tip_pose, leg.poser.current_tip_pose_);
+    putPose(m.model_tip_pose, leg.current_tip_pose_);
+    if (measured)
+      for (int j = 0; j < D; ++j) leg.joints[j + 1].current_position_ = measured[l * D + j];
+    else
+      for (int j = 0; j < D; ++j) leg.joints[j + 1].current_position_ = leg.joints[j + 1].desired_position_;
+    putPose(m.actual_tip_pose, leg.applyFK(false, true));
+    leg.applyFK(false, false);  // restore the transforms of the desired positions (the reference calls applyFK(): :842)
+    put3(m.model_tip_velocity, leg.current_tip_velocity_);
+    for (int j = 0; j < D; ++j) {
+      const Joint& jt = leg.joints[j + 1];
+      m.joint_positions[j] = jt.desired_position_;
+      m.joint_velocities[j] = jt.desired_velocity_;
+      m.joint_efforts[j] = jt.desired_effort_;
+      js->position[l * D + j] = jt.desired_position_;   // Leg::generateDesiredJointStateMsg (model.cpp:605)
+      js->velocity[l * D + j] = jt.desired_velocity_;
+      js->effort[l * D + j] = jt.desired_effort_;
+      js->position_command[l * D + j] = jt.desired_position_ + jt.offset_;  // :795
+      Pose jp = leg.jointPoseRobotFrame(j + 1);
+      Pose turned(jp.position_, jp.rotation_ * quatFromAngleAxis(jt.desired_position_, UnitZ()));  // :1030
+      putPose(m.joint_transform[j], turned);
+    }
+    putPose(m.tip_transform, leg.tipPoseRobotFrame());
+    m.swing_progress = leg.stepper.swing_progress_;
+    m.stance_progress = leg.stepper.stance_progress_;
+    const StepCycle& step = r.step_;
+    double swing_time = (double(step.swing_period_) / step.period_) / step.frequency_;
+    double stance_time = (double(step.stance_period_) / step.period_) / step.frequency_;
+    double time_to_swing_end;
+    if (leg.stepper.stance_progress_ >= 0.0) time_to_swing_end = stance_time * (1.0 - leg.stepper.stance_progress_) + swing_time;
+    else time_to_swing_end = swing_time * (1.0 - leg.stepper.swing_progress_);
+    m.time_to_swing_end = time_to_swing_end;
+    putPose(m.pose_delta, r.calculateOdometry(time_to_swing_end));
+    putPose(m.auto_pose, leg.poser.auto_pose_);
+    m.tip_force[0] = leg.tip_force_calculated_[0] * r.params_.force_gain;
+    m.tip_force[1] = leg.tip_force_calculated_[1] * r.params_.force_gain;
+    m.tip_force[2] = leg.tip_force_calculated_[2] * r.params_.force_gain;
+    put3(m.admittance_delta, leg.admittance_delta_);
+    m.virtual_stiffness = leg.virtual_stiffness_;
+  }
+  std::memset(body, 0, sizeof(*body));
+  body->velocity[0] = r.desired_linear_velocity_[0];
+  body->velocity[1] = r.desired_linear_velocity_[1];
+  body->velocity[5] = r.desired_angular_velocity_;
+  put3(body->pose, r.current_pose_.position_);
+  Vec3 e = om::quaternionToEulerAngles(r.current_pose_.rotation_, false);
+  put3(body->pose + 3, e);
+  put3(body->rotation_pose_error, r.rotation_absement_error_);
+  put3(body->rotation_pose_error + 3, r.rotation_position_error_);
+  put3(body->rotation_pose_error + 6, r.rotation_velocity_error_);
+  putPose(body->odom_ideal_to_base_link, r.odometry_ideal_.addPose(r.current_pose_));
+  putPose(body->base_link_to_walk_plane, ~r.current_pose_);
 }
 }
 

@@ -119,6 +119,26 @@ class ShcRobotState(C.Structure):
     ]
 
 
+# include/shc_msgs.h ----------------------------------------------------------------------------------------------
+class ShcJointStateMsg(C.Structure):
+    _fields_ = [("position", _d * (MAX_LEGS * MAX_DOF)), ("velocity", _d * (MAX_LEGS * MAX_DOF)),
+                ("effort", _d * (MAX_LEGS * MAX_DOF)), ("position_command", _d * (MAX_LEGS * MAX_DOF))]
+
+
+class ShcLegStateMsg(C.Structure):
+    _fields_ = [("walker_tip_pose", _d * 7), ("target_tip_pose", _d * 7), ("poser_tip_pose", _d * 7),
+                ("model_tip_pose", _d * 7), ("actual_tip_pose", _d * 7), ("model_tip_velocity", _d * 3),
+                ("joint_positions", _d * MAX_DOF), ("joint_velocities", _d * MAX_DOF), ("joint_efforts", _d * MAX_DOF),
+                ("stance_progress", _d), ("swing_progress", _d), ("time_to_swing_end", _d),
+                ("pose_delta", _d * 7), ("auto_pose", _d * 7), ("tip_force", _d * 3), ("admittance_delta", _d * 3),
+                ("virtual_stiffness", _d), ("joint_transform", (_d * 7) * MAX_DOF), ("tip_transform", _d * 7)]
+
+
+class ShcBodyMsg(C.Structure):
+    _fields_ = [("velocity", _d * 6), ("pose", _d * 6), ("rotation_pose_error", _d * 9),
+                ("odom_ideal_to_base_link", _d * 7), ("base_link_to_walk_plane", _d * 7)]
+
+
 # --------------------------------------------------------------------------------------------------------------
 # Gait tables — values of /root/reference/config/gait.yaml:13-50 (leg order AR,BR,CR,CL,BL,AL as default.yaml:26)
 # --------------------------------------------------------------------------------------------------------------

@@ -812,6 +812,7 @@ template <class P, int D, bool FULL> struct Cycle {
       }
       pe.z = K(0);
       const int b = ci.offS_imu;
+      st3(sp, b + IMU_POS, pe);  // rotation_position_error_ (:1210)
       Q4<K> imu_pose_q;
       // IMU_POSING_DEADBAND is 0.0: "norm < 0" never holds, the PID always runs (pose_controller.h:25)
       V3<K> abs_err = ld3K(sp, b + IMU_ABS) + pe * ck.dt;

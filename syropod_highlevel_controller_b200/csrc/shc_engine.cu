@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/shc_b200.h"
+#include "shc_msgs.cuh"
 #include "shc_pack.cuh"
 
 namespace shc {
@@ -180,6 +181,23 @@ __global__ void __launch_bounds__(128) apply_ik_kernel(const __grid_constant__ C
     tip_out[3 * (size_t)i + 2] = t.z;
   }
   if (result) result[i] = ik_result_value<double, D>(lc, ch2, q, des_leg);
+}
+
+// ---- output wire formats -----------------------------------------------------------------------
+// One thread per (robot, leg) of the range: the LegState record and the leg's slice of the JointState record; the thread of
+// leg 0 adds the robot's body record.  Replaces the per-leg / per-joint host loops of the reference's publishers.
+template <class S, int D>
+__global__ void __launch_bounds__(128) pack_messages_kernel(const __grid_constant__ Consts c, Planes<S> pl, int first, int count,
+                                                            const float* __restrict__ measured, shc_joint_state_msg* js,
+                                                            shc_leg_state_msg* legs, shc_body_msg* body) {
+  const int L = c.i.L;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)count * L) return;
+  const int k = (int)(i / L), l = (int)(i % L), r = first + k;
+  shc_leg_state_msg m;
+  pack_leg_message<S, D>(c, pl, r, l, measured ? measured + ((size_t)r * L + l) * D : nullptr, m, js ? &js[k] : nullptr);
+  if (legs) legs[(size_t)k * L + l] = m;
+  if (l == 0 && body) pack_body_message<S>(c, pl, r, body[k]);
 }
 
 // ---- start-up on the device ---------------------------------------------------------------------
@@ -881,6 +899,45 @@ int shc_apply_ik(shc_engine* e, int n_legs, const int* leg_id, double* q, double
     apply_ik_kernel<D><<<blocks, threads, 0, st>>>(e->c, n_legs, leg_id, q, qd, desired_tip, simulation, tip_out, ik_result);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(SHC_E_CUDA, std::string("apply_ik launch: ") + cudaGetErrorString(err));
+    return SHC_OK;
+  });
+}
+
+// Output wire formats (include/shc_msgs.h) of the robots [first, first + count) as of the last cycle, packed by one kernel.
+// Outputs may be device memory or page-locked host memory (written in place over PCIe: no copy); any of them may be NULL.
+// measured_joint_positions_dev (float [N][L][D], may be NULL): the measured joint states for LegState.actual_tip_pose.
+int shc_pack_messages(shc_engine* e, size_t first, size_t count, const float* measured_joint_positions_dev,
+                      shc_joint_state_msg* joint_state_out, shc_leg_state_msg* leg_state_out, shc_body_msg* body_out, void* stream) {
+  if (!e || count < 1 || first + count > (size_t)e->n) return fail(SHC_E_INVALID, "shc_pack_messages: range outside the batch");
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  auto alias = [](void* p) -> void* {  // page-locked host memory: the device-side alias of the same buffer
+    if (!p) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return p; }
+    if (a.type == cudaMemoryTypeHost) {
+      void* d = nullptr;
+      if (cudaHostGetDevicePointer(&d, p, 0) == cudaSuccess && d) return d;
+      cudaGetLastError();
+    }
+    return p;
+  };
+  auto* js = (shc_joint_state_msg*)alias(joint_state_out);
+  auto* legs = (shc_leg_state_msg*)alias(leg_state_out);
+  auto* body = (shc_body_msg*)alias(body_out);
+  const long long total = (long long)count * e->cfg.leg_count;
+  const int threads = 128, blocks = (int)((total + threads - 1) / threads);
+  return dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int {
+    constexpr int D = decltype(dtag)::value;
+    if (e->precision == SHC_PRECISION_F64) {
+      Planes<double> pl{(double*)e->s_planes, e->d_planes, e->i_planes};
+      pack_messages_kernel<double, D><<<blocks, threads, 0, st>>>(e->c, pl, (int)first, (int)count, measured_joint_positions_dev, js, legs, body);
+    } else {
+      Planes<float> pl{(float*)e->s_planes, e->d_planes, e->i_planes};
+      pack_messages_kernel<float, D><<<blocks, threads, 0, st>>>(e->c, pl, (int)first, (int)count, measured_joint_positions_dev, js, legs, body);
+    }
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(SHC_E_CUDA, std::string("pack_messages launch: ") + cudaGetErrorString(err));
     return SHC_OK;
   });
 }

@@ -24,7 +24,8 @@ enum : int {
 };
 // optional IMU block (imu_posing || inclination_posing), relative to offS_imu
 enum : int { IMU_Q = 0 /*imu_pose_.rotation_ (4)*/, IMU_ABS = 4 /*absement (3)*/, IMU_VEL = 7 /*velocity err (3)*/,
-             IMU_INCL = 10 /*inclination_pose_ x,y (2)*/, IMU_COUNT = 12 };
+             IMU_INCL = 10 /*inclination_pose_ x,y (2)*/, IMU_POS = 12 /*rotation_position_error_ (3): only read back by
+             publishRotationPoseError*/, IMU_COUNT = 15 };
 // optional auto-pose block (auto_posing), relative to offS_auto
 enum : int { AUTO_POSE = 0 /*auto_pose_ (7)*/, AUTO_COUNT = 7 };
 

@@ -198,6 +198,31 @@ template <class R> SHC_HD void quat_to_matrix(Q4<R> q, R m[3][3]) {
   m[1][0] = txy + twz;          m[1][1] = R(1) - (txx + tzz); m[1][2] = tyz - twx;
   m[2][0] = txz - twy;          m[2][1] = tyz + twx;          m[2][2] = R(1) - (txx + tyy);
 }
+// Eigen Quaternion(Matrix3) (QuaternionBase::operator=(MatrixBase), "Shoemake" branch on the trace), row-major m[3][3]
+template <class R> SHC_HD Q4<R> matrix_to_quat(const R m[3][3]) {
+  R t = m[0][0] + m[1][1] + m[2][2];
+  R q[4];  // x y z w
+  if (t > R(0)) {
+    t = sqrt_(t + R(1));
+    q[3] = R(0.5) * t;
+    t = R(0.5) / t;
+    q[0] = (m[2][1] - m[1][2]) * t;
+    q[1] = (m[0][2] - m[2][0]) * t;
+    q[2] = (m[1][0] - m[0][1]) * t;
+  } else {
+    int i = 0;
+    if (m[1][1] > m[0][0]) i = 1;
+    if (m[2][2] > m[i][i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt_(m[i][i] - m[j][j] - m[k][k] + R(1));
+    q[i] = R(0.5) * t;
+    t = R(0.5) / t;
+    q[3] = (m[k][j] - m[j][k]) * t;
+    q[j] = (m[j][i] + m[i][j]) * t;
+    q[k] = (m[k][i] + m[i][k]) * t;
+  }
+  return {q[3], q[0], q[1], q[2]};
+}
 // Eigen 3.3 eulerAngles(a0,a1,a2), a0 != a2 (first angle in [0,pi]) followed by the reference's range fix-up
 // (standard_includes.h:248-291).  Returns (roll, pitch, yaw).
 template <class R> SHC_HD V3<R> quat_to_euler(Q4<R> q, bool intrinsic) {

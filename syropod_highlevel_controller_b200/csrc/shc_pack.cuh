@@ -108,6 +108,7 @@ template <class E> void pack(const E* e, const shc_robot_state* in, size_t n, Ho
       for (int k = 0; k < 3; ++k) {
         S(ci.offS_imu + IMU_ABS + k, r) = s.rotation_absement_error[k];
         S(ci.offS_imu + IMU_VEL + k, r) = s.rotation_velocity_error[k];
+        S(ci.offS_imu + IMU_POS + k, r) = s.rotation_position_error[k];
       }
       S(ci.offS_imu + IMU_INCL, r) = s.inclination_pose[0];
       S(ci.offS_imu + IMU_INCL + 1, r) = s.inclination_pose[1];
@@ -201,6 +202,7 @@ template <int D, class E> void unpack(const E* e, const HostPlanes& h, shc_robot
       for (int k = 0; k < 3; ++k) {
         s.rotation_absement_error[k] = S(ci.offS_imu + IMU_ABS + k, r);
         s.rotation_velocity_error[k] = S(ci.offS_imu + IMU_VEL + k, r);
+        s.rotation_position_error[k] = S(ci.offS_imu + IMU_POS + k, r);
       }
       s.inclination_pose[0] = S(ci.offS_imu + IMU_INCL, r);
       s.inclination_pose[1] = S(ci.offS_imu + IMU_INCL + 1, r);

@@ -12,7 +12,7 @@ from typing import Optional
 
 import numpy as np
 
-from .config import ShcConfig, ShcRobotState, ShcStartup
+from .config import ShcBodyMsg, ShcConfig, ShcJointStateMsg, ShcLegStateMsg, ShcRobotState, ShcStartup
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SHC_B200_LIB", os.path.join(_PKG, "libshc_b200.so"))  # override: kernel-tuning builds only
@@ -44,6 +44,7 @@ def lib():
         dp = C.POINTER(C.c_double)
         L.shc_host_apply_ik.argtypes = [C.POINTER(ShcConfig), C.c_int, dp, dp, dp, C.c_int, dp, dp]
         L.shc_get_startup.argtypes = [vp, C.POINTER(ShcStartup)]
+        L.shc_pack_messages.argtypes = [vp, C.c_size_t, C.c_size_t, vp, vp, vp, vp, vp]
         L.shc_startup_begin.argtypes = [vp, vp]
         L.shc_startup_step.argtypes = [vp, vp, vp]
         L.shc_direct_startup.argtypes = [vp, vp, vp, vp]
@@ -196,6 +197,25 @@ class Engine:
         out = np.empty(self.n, dtype=np.int32)
         _check(lib().shc_get_status_flags(self._h, out.ctypes.data_as(C.POINTER(C.c_int))))
         return out
+
+    # ---- output wire formats ----------------------------------------------------------------------------------------
+    def pack_messages(self, first: int = 0, count: Optional[int] = None, measured_joint_positions=None):
+        """JointState / LegState / body records (include/shc_msgs.h) of the robots [first, first + count), packed by one
+        kernel straight into page-locked host memory.  Returns (joint_state [count], leg_state [count][L], body [count])
+        as ctypes arrays viewing pinned memory owned by the engine object."""
+        torch = self.torch
+        count = self.n - first if count is None else count
+        sizes = (C.sizeof(ShcJointStateMsg) * count, C.sizeof(ShcLegStateMsg) * count * self.L, C.sizeof(ShcBodyMsg) * count)
+        bufs = [torch.empty(sz, dtype=torch.uint8, pin_memory=True) for sz in sizes]
+        m = self._f32(measured_joint_positions, (self.n, self.L, self.D))
+        _check(lib().shc_pack_messages(self._h, first, count, _ptr(m), bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(),
+                                       _stream_handle(torch, self.device, None)))
+        torch.cuda.synchronize(self.device)
+        self._msg_keep = bufs
+        js = (ShcJointStateMsg * count).from_address(bufs[0].data_ptr())
+        legs = ((ShcLegStateMsg * self.L) * count).from_address(bufs[1].data_ptr())
+        body = (ShcBodyMsg * count).from_address(bufs[2].data_ptr())
+        return js, legs, body
 
     # ---- start-up on the device -------------------------------------------------------------------------------------
     def generate_workspaces(self, full: bool = False, max_planes: int = 16):

@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "../../syropod_highlevel_controller_b200/csrc/shc_msgs.cuh"
 #include "../../syropod_highlevel_controller_b200/csrc/shc_pack.cuh"
 
 using namespace shc;
@@ -153,6 +154,23 @@ int shc_emu_step(shc_emu* e, const float* cmd, const float* imu, const float* ti
     } else {
       if (full) step_all<PrecMixed, D, true>(e, io); else step_all<PrecMixed, D, false>(e, io);
     }
+    return SHC_OK;
+  });
+}
+
+// The message packer of shc_pack_messages (csrc/shc_msgs.cuh) on the emulator's planes: records of robot `r`.
+int shc_emu_pack_messages(shc_emu* e, int r, const float* measured, shc_joint_state_msg* js, shc_leg_state_msg* legs, shc_body_msg* body) {
+  if (!e || r < 0 || r >= e->n) return fail(SHC_E_INVALID, "robot out of range");
+  const int L = e->cfg.leg_count;
+  return dispatch_D_raw(e->cfg.joint_count, [&](auto dtag) -> int {
+    constexpr int D = decltype(dtag)::value;
+    auto go = [&](auto pl) {
+      using S = typename std::remove_pointer<decltype(pl.s)>::type;
+      for (int l = 0; l < L; ++l) pack_leg_message<S, D>(e->c, pl, r, l, measured ? measured + ((size_t)r * L + l) * D : nullptr, legs[l], js);
+      pack_body_message<S>(e->c, pl, r, *body);
+    };
+    if (e->precision == SHC_PRECISION_F64) go(Planes<double>{e->s64.data(), e->d.data(), e->i.data()});
+    else go(Planes<float>{e->s32.data(), e->d.data(), e->i.data()});
     return SHC_OK;
   });
 }

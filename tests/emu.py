@@ -12,7 +12,8 @@ import subprocess
 
 import numpy as np
 
-from syropod_highlevel_controller_b200.config import ShcConfig, ShcRobotState, ShcStartup
+from syropod_highlevel_controller_b200.config import (ShcBodyMsg, ShcConfig, ShcJointStateMsg, ShcLegStateMsg, ShcRobotState,
+                                                      ShcStartup)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "cpp", "shc_emu.cpp")
@@ -49,6 +50,7 @@ def lib():
         L.shc_emu_get_state.argtypes = [vp, C.POINTER(ShcRobotState), C.c_size_t]
         L.shc_emu_set_state.argtypes = [vp, C.POINTER(ShcRobotState), C.c_size_t]
         L.shc_emu_step.argtypes = [vp, fp, fp, fp, fp, fp]
+        L.shc_emu_pack_messages.argtypes = [vp, C.c_int, fp, C.POINTER(ShcJointStateMsg), C.POINTER(ShcLegStateMsg), C.POINTER(ShcBodyMsg)]
         _lib = L
     return _lib
 
@@ -117,6 +119,14 @@ class EmuEngine:
 
     def set_state(self, arr):
         _check(lib().shc_emu_set_state(self._h, arr, self.n))
+
+    def pack_messages(self, first=0, count=None, measured_joint_positions=None):
+        count = self.n - first if count is None else count
+        m, pm = _f32(measured_joint_positions, (self.n, self.L, self.D))
+        js, legs, body = (ShcJointStateMsg * count)(), ((ShcLegStateMsg * self.L) * count)(), (ShcBodyMsg * count)()
+        for k in range(count):
+            _check(lib().shc_emu_pack_messages(self._h, first + k, pm, C.byref(js[k]), legs[k], C.byref(body[k])))
+        return js, legs, body
 
     def step(self, cmd, imu=None, tip_force=None, manual=None):
         cmd, pc = _f32(cmd, (self.n, 3))

@@ -3,7 +3,7 @@ import numpy as np
 
 STATE_FIELDS_ROBOT = ("desired_linear_velocity", "walk_plane", "walk_plane_normal", "odometry_ideal", "walk_plane_pose",
                       "origin_walk_plane_pose", "manual_pose", "imu_pose", "inclination_pose", "auto_pose",
-                      "rotation_absement_error", "rotation_velocity_error", "current_pose")
+                      "rotation_absement_error", "rotation_position_error", "rotation_velocity_error", "current_pose")
 INT_FIELDS_ROBOT = ("walk_state", "legs_at_correct_phase", "legs_completed_first_step", "return_to_default_attempted",
                     "pose_state", "auto_posing_state", "pose_phase")
 STATE_FIELDS_LEG = ("tip_position", "tip_velocity", "swing_origin_position", "stance_origin_position",

@@ -377,3 +377,62 @@ def mixed_precision_statistics(backend, oracle, n=256, cycles=600):
     d = assert_state_close(eng.get_state(), ob.get_state(), 6, 3, 1.0, skip=())
     assert d["tip_position"] < 1e-6 and d["int:phase"] == 0 and d["int:walk_state"] == 0
     eng.close(); ob.close()
+
+
+def _msg_diff(a, b, skip=()):
+    """Largest absolute difference per field between two ctypes message records."""
+    out = {}
+    for name, _ in a._fields_:
+        if name in skip:
+            continue
+        out[name] = float(np.max(np.abs(np.ctypeslib.as_array(getattr(a, name)) - np.ctypeslib.as_array(getattr(b, name))))) \
+            if not isinstance(getattr(a, name), float) else abs(getattr(a, name) - getattr(b, name))
+    return out
+
+
+def wire_formats(backend, oracle, n=24, cycles=260):
+    """the JointState / LegState / body records packed from the state planes (shc_pack_messages)
+    against the oracle's restatement of the reference's publishers (state_controller.cpp:777-1047), along rollouts of the
+    hexapod and of the octopod with admittance + IMU posing + dynamic stiffness.  Fields the engine's state does not
+    determine are excluded and named: LegState.auto_pose / poser_tip_pose inside an auto-pose negation window (the
+    per-leg auto pose is not kept) and the tip velocity on a cycle whose joints hit a limit (reconstructed from
+    q - qd * dt)."""
+    for cfg, L, D, sensors in ((hexapod_config("ripple_gait"), 6, 3, False), (octopod_config("tripod_gait"), 8, 5, True)):
+        ob = oracle.OracleBatch(cfg, n)
+        eng = backend.engine(cfg, n, startup=ob.startup())
+        cs = CommandStream(n, min_len=30, max_len=120)
+        ims = ImuStream(n) if sensors else None
+        fs = ForceStream(n, L) if sensors else None
+        rng = np.random.default_rng(8)
+        lo = np.array([[cfg.joint_min[l][j] for j in range(D)] for l in range(L)])
+        hi = np.array([[cfg.joint_max[l][j] for j in range(D)] for l in range(L)])
+        measured = (lo + (hi - lo) * rng.uniform(0.1, 0.9, size=(n, L, D))).astype(np.float32)
+        worst = {}
+        for c in range(cycles):
+            cmd = cs.next()
+            imu = ims.next(cfg.time_delta) if ims else None
+            force = fs.next() if fs else None
+            sample = c % 20 == 19
+            if sample:  # one cycle from identical state, so that joint chatter does not blur the comparison
+                eng.set_state(ob.get_state())
+                eng.step(cmd, imu, force)
+            ob.step(cmd.astype(np.float64), None if imu is None else imu.astype(np.float64),
+                    None if force is None else force.astype(np.float64), threads=4)
+            if not sample:
+                continue
+            js, legs, body = eng.pack_messages(0, n, measured)
+            for r in range(0, n, 5):
+                jo, lo_, bo = ob.messages(r, measured[r].astype(np.float64))
+                d = _msg_diff(js[r], jo)
+                d.update({"body." + k: v for k, v in _msg_diff(body[r], bo).items()})
+                for l in range(L):
+                    clamped = any(abs(lo_[l].joint_positions[j] - lim[l][j]) < 1e-12 for lim in (lo, hi) for j in range(D))
+                    dl = _msg_diff(legs[r][l], lo_[l], skip=("model_tip_velocity",) if clamped else ())
+                    d.update({"leg." + k: max(v, d.get("leg." + k, 0.0)) for k, v in dl.items()})
+                for k, v in d.items():
+                    worst[k] = max(worst.get(k, 0.0), v)
+        print(f"[wire-formats] {L}x{D}: " + ", ".join(f"{k} {v:.1e}" for k, v in sorted(worst.items()) if v > 1e-9))
+        for k, v in worst.items():
+            tol = 1e-6 if k in ("leg.model_tip_velocity", "leg.tip_force") else 1e-9
+            assert v <= tol, (k, v)
+        eng.close(); ob.close()

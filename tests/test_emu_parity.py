@@ -66,3 +66,8 @@ def test_emu_single_step_parity_all_modes(emu, oracle):
 
 def test_emu_single_step_parity_inputs(emu, oracle):
     P.single_step_inputs(emu, oracle, n=32, cycles=200)
+
+
+def test_emu_wire_formats(emu, oracle):
+    P.wire_formats(emu, oracle)
+

@@ -69,3 +69,8 @@ def test_single_step_parity_inputs(gpu, oracle):
 
 def test_mixed_precision_rollout_statistics(gpu, oracle):
     P.mixed_precision_statistics(gpu, oracle)
+
+
+def test_wire_formats(gpu, oracle):
+    P.wire_formats(gpu, oracle)
+
