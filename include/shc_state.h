@@ -48,6 +48,12 @@ typedef struct shc_leg_state {
   /* LegPoser auto-pose negation latch (pose_controller.h:575) */
   int negate_auto_pose;
   int pad0;
+  /* LegStepper tip rotations, w x y z (walk_controller.h:513-516; walk_controller.cpp:1193 updateTipRotation): only live with
+   * gravity_aligned_tips on legs of more than three joints; all four components zero = UNDEFINED_ROTATION */
+  double tip_rotation[4];           /* current_tip_pose_.rotation_ */
+  double origin_tip_rotation[4];    /* origin_tip_pose_.rotation_ */
+  double target_tip_rotation[4];    /* target_tip_pose_.rotation_ (a constant of the configuration without rough-terrain
+                                     * targets: written by shc_get_state, ignored by shc_set_state) */
   /* outputs of the last cycle (recomputed every cycle; not algorithmic state) */
   double model_tip_position[3];     /* Leg::current_tip_pose_.position_ after applyFK (base_link frame) */
   double desired_tip_position[3];   /* Leg::desired_tip_pose_.position_ */
@@ -77,6 +83,9 @@ typedef struct shc_robot_state {
   double rotation_absement_error[3];
   double rotation_position_error[3];
   double rotation_velocity_error[3];
+  /* tip-align posing (pose_controller.cpp:1024 updateTipAlignPose): gravity_aligned_tips on legs of at most three joints */
+  double tip_align_pose[7];         /* tip_align_pose_ */
+  double origin_tip_align_pose[7];  /* origin_tip_align_pose_ */
   int auto_posing_state;            /* 0 POSING 1 STOP_POSING 2 POSING_COMPLETE */
   int pose_phase;
   /* AutoPoser latches (pose_controller.h:408-410): bit0 start_check, bit1 end_check.first, bit2 end_check.second,

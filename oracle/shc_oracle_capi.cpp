@@ -35,6 +35,7 @@ void putPose(double* o, const Pose& p) {
   o[3] = p.rotation_.w; o[4] = p.rotation_.x; o[5] = p.rotation_.y; o[6] = p.rotation_.z;
 }
 Pose getPose(const double* o) { return Pose(Vec3(o[0], o[1], o[2]), Quat(o[3], o[4], o[5], o[6])); }
+void putQuat(double* o, const Quat& q) { o[0] = q.w; o[1] = q.x; o[2] = q.y; o[3] = q.z; }
 void put3(double* o, const Vec3& v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }
 Vec3 get3(const double* o) { return Vec3(o[0], o[1], o[2]); }
 
@@ -60,6 +61,8 @@ void exportState(const Robot& r, shc_robot_state* s) {
   put3(s->rotation_absement_error, r.rotation_absement_error_);
   put3(s->rotation_position_error, r.rotation_position_error_);
   put3(s->rotation_velocity_error, r.rotation_velocity_error_);
+  putPose(s->tip_align_pose, r.tip_align_pose_);
+  putPose(s->origin_tip_align_pose, r.origin_tip_align_pose_);
   s->auto_posing_state = r.auto_posing_state_;
   s->pose_phase = r.pose_phase_;
   for (size_t k = 0; k < r.auto_posers_.size() && k < SHC_MAX_AUTO_POSERS; ++k) {
@@ -98,6 +101,9 @@ void exportState(const Robot& r, shc_robot_state* s) {
     put3(o.tip_force_calculated, leg.tip_force_calculated_);
     o.virtual_stiffness = leg.virtual_stiffness_;
     o.negate_auto_pose = leg.poser.negate_auto_pose_;
+    putQuat(o.tip_rotation, st.current_tip_pose_.rotation_);
+    putQuat(o.origin_tip_rotation, st.origin_tip_pose_.rotation_);
+    putQuat(o.target_tip_rotation, st.target_tip_pose_.rotation_);
     put3(o.model_tip_position, leg.current_tip_pose_.position_);
     put3(o.desired_tip_position, leg.desired_tip_pose_.position_);
     o.ik_result = leg.last_ik_result_;
@@ -125,6 +131,8 @@ void importState(Robot& r, const shc_robot_state* s) {
   r.rotation_absement_error_ = get3(s->rotation_absement_error);
   r.rotation_position_error_ = get3(s->rotation_position_error);
   r.rotation_velocity_error_ = get3(s->rotation_velocity_error);
+  r.tip_align_pose_ = getPose(s->tip_align_pose);
+  r.origin_tip_align_pose_ = getPose(s->origin_tip_align_pose);
   r.auto_posing_state_ = PosingState(s->auto_posing_state);
   r.pose_phase_ = s->pose_phase;
   for (size_t k = 0; k < r.auto_posers_.size() && k < SHC_MAX_AUTO_POSERS; ++k) {
@@ -166,6 +174,9 @@ void importState(Robot& r, const shc_robot_state* s) {
     leg.tip_force_calculated_ = get3(o.tip_force_calculated);
     leg.virtual_stiffness_ = o.virtual_stiffness;
     leg.poser.negate_auto_pose_ = o.negate_auto_pose != 0;
+    // target_tip_pose_.rotation_ is a constant of the configuration (no rough-terrain targets): left as constructed
+    st.current_tip_pose_.rotation_ = Quat(o.tip_rotation[0], o.tip_rotation[1], o.tip_rotation[2], o.tip_rotation[3]);
+    st.origin_tip_pose_.rotation_ = Quat(o.origin_tip_rotation[0], o.origin_tip_rotation[1], o.origin_tip_rotation[2], o.origin_tip_rotation[3]);
   }
 }
 

@@ -8,7 +8,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libshc_b200.so")
 SOURCES = ["shc_engine.cu"]
-HEADERS = ["shc_math.cuh", "shc_consts.h", "shc_layout.h", "shc_cycle.cuh", "shc_host.cuh"]
+HEADERS = ["shc_math.cuh", "shc_consts.h", "shc_layout.h", "shc_cycle.cuh", "shc_host.cuh", "shc_pack.cuh", "shc_msgs.cuh",
+           "shc_startup.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",

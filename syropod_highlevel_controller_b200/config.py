@@ -96,6 +96,7 @@ class ShcLegState(C.Structure):
         ("admittance_state", _d * 2), ("admittance_delta", _d * 3), ("tip_force_calculated", _d * 3),
         ("virtual_stiffness", _d),
         ("negate_auto_pose", _i), ("pad0", _i),
+        ("tip_rotation", _d * 4), ("origin_tip_rotation", _d * 4), ("target_tip_rotation", _d * 4),
         ("model_tip_position", _d * 3), ("desired_tip_position", _d * 3), ("ik_result", _d),
     ]
 
@@ -111,6 +112,7 @@ class ShcRobotState(C.Structure):
         ("imu_pose", _d * 7), ("inclination_pose", _d * 7), ("auto_pose", _d * 7),
         ("rotation_absement_error", _d * 3), ("rotation_position_error", _d * 3),
         ("rotation_velocity_error", _d * 3),
+        ("tip_align_pose", _d * 7), ("origin_tip_align_pose", _d * 7),
         ("auto_posing_state", _i), ("pose_phase", _i),
         ("auto_poser_flags", _i * MAX_AUTO_POSERS),
         ("current_pose", _d * 7),

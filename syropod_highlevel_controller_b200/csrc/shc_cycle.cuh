@@ -183,6 +183,7 @@ template <class K, int D> struct Chain {
   V3<K> p[D];  // joint origins in the leg frame (p[0] = 0)
   V3<K> tip;   // tip position in the leg frame
   V3<K> tipx;  // x axis of the tip frame in the leg frame (last-link direction)
+  V3<K> tipy, tipz;  // its other two axes (only the tip-orientation path reads them)
 };
 
 template <class K, int D, class QT>
@@ -204,6 +205,8 @@ SHC_HD void leg_chain(const LegConsts<K>& lc, const QT* q, Chain<K, D>& ch) {
   }
   ch.tip = ap;
   ch.tipx = ax;
+  ch.tipy = ay;
+  ch.tipz = az;
 }
 
 template <class K> SHC_HD V3<K> t1_rotate(const LegConsts<K>& lc, V3<K> v) {
@@ -354,6 +357,132 @@ SHC_HD int apply_ik_step(const RealConsts<K>& ck, const LegConsts<K>& lc, const 
   return status;
 }
 
+// Leg::updateJointPositions (model.cpp:799): q/qd from a joint position delta; returns the SHC_FLAG_*_CLAMP bits.
+template <class K, int D>
+SHC_HD int update_joint_positions(const RealConsts<K>& ck, const LegConsts<K>& lc, const K* dq, K* q, K* qd, bool clamp_positions,
+                                  bool clamp_velocities) {
+  int status = 0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    K v = dq[j] * ck.inv_dt;
+    if (clamp_velocities && abs_(v) > lc.vmax[j]) {
+      v = clamp_(v, -lc.vmax[j], lc.vmax[j]);
+      status |= 4;
+    }
+    K nq = q[j] + v * ck.dt;
+    if (clamp_positions) {
+      if (nq < lc.jmin[j]) { nq = lc.jmin[j]; status |= 2; }
+      else if (nq > lc.jmax[j]) { nq = lc.jmax[j]; status |= 2; }
+    }
+    q[j] = nq;
+    qd[j] = v;
+  }
+  return status;
+}
+
+// Leg::solveIK with solve_rotation = true and delta = [0; drot] (model.cpp:726-795): the full 6 x D Jacobian (linear rows
+// z_j x (tip - p_j), angular rows z_j), dq = J^T (J J^T + l^2 I6)^-1 (delta - J g) + g with the joint-limit cost gradient g.
+template <class K, int D>
+SHC_HD void solve_ik_rotation(const RealConsts<K>& ck, const LegConsts<K>& lc, const Chain<K, D>& ch, V3<K> drot, const K* q, const K* qd,
+                              K* dq) {
+  K J[6][D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    const V3<K> jp = cross(ch.z[j], ch.tip - ch.p[j]);
+    J[0][j] = jp.x; J[1][j] = jp.y; J[2][j] = jp.z;
+    J[3][j] = ch.z[j].x; J[4][j] = ch.z[j].y; J[5][j] = ch.z[j].z;
+  }
+  K g[D];
+  {
+    K pos_cost = K(0), vel_cost = K(0), gp[D], gv[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      K e = q[j] - lc.jcentre[j];
+      K cp = lc.jcost_pos[j] * e;
+      pos_cost += cp * cp;
+      gp[j] = lc.jgrad_pos[j] * e;
+      K cv = lc.jcost_vel[j] * qd[j];
+      vel_cost += cv * cv;
+      gv[j] = lc.jgrad_vel[j] * qd[j];
+    }
+    K sp = pos_cost == K(0) ? K(0) : rsqrt_(pos_cost);
+    K sv = vel_cost == K(0) ? K(0) : rsqrt_(vel_cost);
+#pragma unroll
+    for (int j = 0; j < D; ++j) g[j] = K(0.25) * (gp[j] * sp) + K(0.75) * (gv[j] * sv);
+  }
+  K A[6][6], b[6];
+  const K delta[6] = {K(0), K(0), K(0), drot.x, drot.y, drot.z};
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    K jg = K(0);
+#pragma unroll
+    for (int j = 0; j < D; ++j) jg += J[a][j] * g[j];
+    b[a] = delta[a] - jg;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      K s = a == c ? ck.lambda2 : K(0);
+#pragma unroll
+      for (int j = 0; j < D; ++j) s += J[a][j] * J[c][j];
+      A[a][c] = s;
+    }
+  }
+  spdN_solve<K, 6>(A, b);
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    K s = g[j];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) s += J[a][j] * b[a];
+    dq[j] = s;
+  }
+}
+
+template <class K, int D> SHC_HD bool ik_within_tolerance(const LegConsts<K>& lc, const Chain<K, D>& ch, V3<K> des_leg) {
+  V3<K> er = t1_rotate(lc, ch.tip - des_leg);  // current - desired tip position in the base_link frame
+  return !(abs_(er.x) > K(0.005) || abs_(er.y) > K(0.005) || abs_(er.z) > K(0.005));
+}
+
+// Leg::applyIK complete (model.cpp:861-941) for a desired tip POSE: the position step; when the desired rotation is defined
+// (gravity_aligned_tips on legs of more than three joints) a second, rotation-only step on the updated chain that turns
+// the last link towards the desired direction; the IK tolerance check; and, when a rotation-constrained attempt misses the
+// position tolerance or ends on a joint limit, one more position-only step (the reference recurses with the rotation dropped, :932-936).
+// `ch` is the chain at q on entry and at the new q on return.  *force_updates = how often calculateTipForce ran (the
+// recursion runs it at both levels).  Returns the clamp status bits; *ok = within IK_TOLERANCE.
+template <class K, int D>
+SHC_HD int apply_ik_pose(const RealConsts<K>& ck, const LegConsts<K>& lc, Chain<K, D>& ch, K* q, K* qd, V3<K> desired_robot,
+                         Q4<K> desired_rot, bool clamp_positions, bool clamp_velocities, V3<K>* des_leg_out, bool* ok, int* force_updates) {
+  const V3<K> des_leg = t1_rotate_inv(lc, desired_robot - V3<K>{lc.t1p[0], lc.t1p[1], lc.t1p[2]});
+  *des_leg_out = des_leg;
+  *force_updates = 1;
+  K dq[D];
+  int status = 0;
+  const bool rotation_constrained = !(desired_rot.w == K(0) && desired_rot.x == K(0) && desired_rot.y == K(0) && desired_rot.z == K(0));
+  solve_ik<K, D>(ck, lc, ch, des_leg - ch.tip, q, qd, dq);
+  if (rotation_constrained) {
+    const V3<K> current_dir = ch.tipx;  // the leg-frame tip direction the cycle started with (:866, :889)
+    status |= update_joint_positions<K, D>(ck, lc, dq, q, qd, clamp_positions, false);  // updateJointPositions(delta, true)
+    leg_chain<K, D>(lc, q, ch);
+    const V3<K> desired_dir = t1_rotate_inv(lc, qrot(qnormalized(desired_rot), V3<K>{K(1), K(0), K(0)}));
+    const V3<K> drot = rotation_vector(qnormalized(from_two_vectors(current_dir, desired_dir)));
+    solve_ik_rotation<K, D>(ck, lc, ch, drot, q, qd, dq);
+  }
+  status |= update_joint_positions<K, D>(ck, lc, dq, q, qd, clamp_positions, clamp_velocities);
+  leg_chain<K, D>(lc, q, ch);
+  *ok = ik_within_tolerance<K, D>(lc, ch, des_leg);
+  // "!ik_success" (:932) tests the DOUBLE applyIK would return: zero on a missed tolerance, but also when the smallest
+  // joint-limit proximity is exactly zero, i.e. when the update left a joint sitting on one of its limits
+  bool on_limit = false;
+#pragma unroll
+  for (int j = 0; j < D; ++j) on_limit = on_limit || (lc.jmax[j] != lc.jmin[j] && (q[j] == lc.jmin[j] || q[j] == lc.jmax[j]));
+  if (rotation_constrained && (!*ok || on_limit)) {
+    solve_ik<K, D>(ck, lc, ch, des_leg - ch.tip, q, qd, dq);
+    status |= update_joint_positions<K, D>(ck, lc, dq, q, qd, clamp_positions, clamp_velocities);
+    leg_chain<K, D>(lc, q, ch);
+    *ok = ik_within_tolerance<K, D>(lc, ch, des_leg);
+    *force_updates = 2;
+  }
+  return status;
+}
+
 // Return value of Leg::applyIK (model.cpp:845-856, 916-929): the smallest joint-limit proximity, or 0 when the tip
 // deviates from the desired position by more than IK_TOLERANCE on a base_link axis.  `ch2` is the chain at the NEW q.
 template <class K, int D>
@@ -479,7 +608,11 @@ SHC_HD PoseT<K> leg_auto_pose(const IntConsts& ci, K neg_ratio, int l, int maste
 #ifndef SHC_SLOTS
 #define SHC_SLOTS 1
 #endif
-template <class P, int D, bool FULL> struct Cycle {
+// MODE: 0 walking only, 1 = FULL, 2 = FULL + the tip-orientation path of gravity_aligned_tips (TIPALIGN: updateTipAlignPose on
+// legs of at most three joints; TIPROT: updateTipRotation and the rotation branch of Leg::applyIK beyond).
+template <class P, int D, int MODE> struct Cycle {
+  static constexpr bool FULL = MODE >= 1;
+  static constexpr bool TIPALIGN = MODE == 2 && D <= 3, TIPROT = MODE == 2 && D > 3;
   static constexpr int kSlots = SHC_SLOTS;
   using S = typename P::S;
   using T = typename P::T;
@@ -855,6 +988,53 @@ template <class P, int D, bool FULL> struct Cycle {
       stPose(sp, ci.offS_auto + AUTO_POSE, auto_pose);
       cur_pose = pose_add(cur_pose, auto_pose);
     }
+    if constexpr (TIPALIGN) {
+      // updateTipAlignPose (pose_controller.cpp:1024, EXPERIMENTAL in the reference): every leg with a swing progress, in leg
+      // order, moves the one tip_align_pose_ - a body translation that brings the leg's last joint over its tip along the
+      // walk-plane normal during the second half of the swing and back to zero during the first half of the next one.
+      PoseT<K> tap = ldPose(sp, ci.offS_tip + TA_POSE);
+      PoseT<K> otap = ldPose(sp, ci.offS_tip + TA_ORIGIN);
+#pragma unroll 1
+      for (int l = 0; l < L; ++l) {
+        const int n_swing = (int)(short)(ip[(ci.offI_leg + l * ci.strideI_leg + LI_PROG) * 32] & 0xffff);
+        if (n_swing < 0) continue;  // swing_progress == -1
+        const K swing_progress = K(n_swing) / K(ci.swing_period);
+        const S* __restrict__ sl = sp + (ci.offS_leg + l * ci.strideS_leg) * 32;
+        const LegConsts<K>& lk = ck.leg[l];
+        const V3<K> wpn = ld3K(sl, LS::WPN);
+        const Q4<K> wp_rot = from_two_vectors(V3<K>{K(0), K(0), K(1)}, wpn);
+        K ql[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) ql[j] = K(sl[(LS::Q + j) * 32]);
+        Chain<K, D> chl;
+        leg_chain<K, D>(lk, ql, chl);  // the model as the previous cycle's applyFK left it
+        const V3<K> tip_to_joint = t1_rotate(lk, chl.p[D - 1] - chl.tip);
+        const K link_length = norm(tip_to_joint);
+        V3<K> a = qrot(wp_rot, tip_to_joint);
+        V3<K> b = wpn * link_length;
+        const V3<K> to_alignment = -(a - b * (dot(a, b) / dot(b, b)));
+        a = tap.p;
+        b = wpn;
+        const V3<K> aligned_now = a - b * (dot(a, b) / dot(b, b));
+        V3<K> target = aligned_now + to_alignment;
+        // clamped(vector, limit) of standard_includes.h:134 bounds every axis above by limit[1]: kept
+        target.x = max_(-ck.max_translation[0], min_(target.x, ck.max_translation[1]));
+        target.y = max_(-ck.max_translation[1], min_(target.y, ck.max_translation[1]));
+        target.z = max_(-ck.max_translation[2], min_(target.z, ck.max_translation[1]));
+        K c = smooth_step(swing_progress);
+        if (swing_progress < K(0.5)) {
+          c = smooth_step(c * K(2));
+          tap = pose_interpolate(otap, c, pose_identity<K>());
+        } else {
+          c = smooth_step((c - K(0.5)) * K(2));
+          tap = pose_interpolate(pose_identity<K>(), c, PoseT<K>{target, qidentity<K>()});
+        }
+        if (swing_progress == K(1)) otap = tap;
+      }
+      stPose(sp, ci.offS_tip + TA_POSE, tap);
+      stPose(sp, ci.offS_tip + TA_ORIGIN, otap);
+      cur_pose = pose_add(cur_pose, tap);
+    }
     const int pose_state = auto_state;  // walker_->setPoseState(poser_->getAutoPoseState())
 
     // =================================================================================================================
@@ -1028,6 +1208,15 @@ template <class P, int D, bool FULL> struct Cycle {
           const float* f = stage + L * (D - 3) + 3 * l;
           adm_force = {K(f[0]), K(f[1]), K(f[2])};
         }
+      }
+      // tip-rotation state (gravity_aligned_tips, D > 3) and the chain at the joint angles the cycle starts with
+      Q4<K> tr_cur{K(0), K(0), K(0), K(0)}, tr_origin{K(0), K(0), K(0), K(0)};
+      Chain<K, D> ch;
+      if constexpr (TIPROT) {
+        const S* __restrict__ tp = sl + ci.tipS_leg * 32;
+        tr_cur = {K(tp[(TR_CUR) * 32]), K(tp[(TR_CUR + 1) * 32]), K(tp[(TR_CUR + 2) * 32]), K(tp[(TR_CUR + 3) * 32])};
+        tr_origin = {K(tp[(TR_ORIGIN) * 32]), K(tp[(TR_ORIGIN + 1) * 32]), K(tp[(TR_ORIGIN + 2) * 32]), K(tp[(TR_ORIGIN + 3) * 32])};
+        leg_chain<K, D>(lk, q, ch);
       }
       // the one HBM read the swing branch may need (tip velocity at the first swing iteration), issued early
       const bool swing_begins = (bits & 0xffff) == ci.swing_start;
@@ -1213,6 +1402,35 @@ template <class P, int D, bool FULL> struct Cycle {
           plane_saved = false;  // the leg sits this cycle out: its saved plane is now older than the walker's
         }
 
+        if constexpr (TIPROT) {
+          // ---- LegStepper::updateTipRotation (:1193), on the progress values the cycle found ----
+          const K swing_progress = swing_num < 0 ? K(-1) : K(swing_num) / K(ci.swing_period);
+          if (stance_num >= 0 || swing_progress >= K(0.5)) {
+            // the target rotation is the identity tip rotation for good (nothing un-defines it without rough-terrain targets)
+            const Q4<K> target_rot{ck.tip_target_rot[0], ck.tip_target_rot[1], ck.tip_target_rot[2], ck.tip_target_rot[3]};
+            tr_cur = correct_rotation(target_rot, tr_origin);
+            if (swing_progress >= K(0.5)) {
+              const K c = smooth_step(min_(K(1), K(2) * (swing_progress - K(0.5))));
+              const V3<K> ux{K(1), K(0), K(0)};
+              const V3<K> origin_dir = qrot(tr_origin, ux), target_dir = qrot(target_rot, ux);
+              const V3<K> new_dir = origin_dir * (K(1) - c) + target_dir * c;
+              tr_cur = correct_rotation(from_two_vectors(ux, normalized(new_dir)), tr_cur);
+            }
+          } else {
+            // origin = Leg::current_tip_pose_.rotation_: the tip frame of the last applyFK in the base_link frame
+            const V3<K> cx = t1_rotate(lk, ch.tipx), cy = t1_rotate(lk, ch.tipy), cz = t1_rotate(lk, ch.tipz);
+            const K m[3][3] = {{cx.x, cy.x, cz.x}, {cx.y, cy.y, cz.y}, {cx.z, cy.z, cz.z}};
+            tr_origin = qnormalized(matrix_to_quat(m));
+            tr_cur = {K(0), K(0), K(0), K(0)};
+            S* __restrict__ tp = sl + ci.tipS_leg * 32;
+            tp[(TR_ORIGIN) * 32] = S(tr_origin.w); tp[(TR_ORIGIN + 1) * 32] = S(tr_origin.x);
+            tp[(TR_ORIGIN + 2) * 32] = S(tr_origin.y); tp[(TR_ORIGIN + 3) * 32] = S(tr_origin.z);
+          }
+          S* __restrict__ tp = sl + ci.tipS_leg * 32;
+          tp[(TR_CUR) * 32] = S(tr_cur.w); tp[(TR_CUR + 1) * 32] = S(tr_cur.x);
+          tp[(TR_CUR + 2) * 32] = S(tr_cur.y); tp[(TR_CUR + 3) * 32] = S(tr_cur.z);
+        }
+
         // ---- LegStepper::iteratePhase (:871) + updateStepState (:901) ----
         phase = phase + 1 == ci.period ? 0 : phase + 1;  // (phase + 1) % period with phase in [0, period)
         if (step_state != STEP_FORCE_STOP) {
@@ -1254,8 +1472,7 @@ template <class P, int D, bool FULL> struct Cycle {
       V3<K> desired = pose_inverse_transform(leg_pose, V3<K>{K(tipx), K(tipy), K(tipz)});
 
       // ---- joint state + chain at the previous joint angles ----
-      Chain<K, D> ch;
-      leg_chain<K, D>(lk, q, ch);
+      if constexpr (!TIPROT) leg_chain<K, D>(lk, q, ch);
 
       // ---- AdmittanceController::updateAdmittance (admittance_controller.cpp:22) ----
       if (f_adm) {
@@ -1286,6 +1503,32 @@ template <class P, int D, bool FULL> struct Cycle {
 
       // ---- Leg::applyIK (model.cpp:861): one DLS step ----
       V3<K> des_leg;
+      if constexpr (TIPROT) {
+        // the poser's tip rotation (updateStance, pose_controller.cpp:129) is the desired one: position step, rotation step,
+        // and the position-only retry when the rotation-constrained attempt misses the tolerance
+        const Q4<K> desired_rot = qmul(qinverse(leg_pose.q), tr_cur);
+        bool ok;
+        int force_updates;
+        status |= apply_ik_pose<K, D>(ck, lk, ch, q, qd, desired, desired_rot, ci.clamp_joint_positions != 0,
+                                      ci.clamp_joint_velocities != 0, &des_leg, &ok, &force_updates);
+        if (!ok) status |= 1;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          sl[(LS::Q + j) * 32] = S(q[j]);
+          sl[(LS::QD + j) * 32] = S(qd[j]);
+          stage[l * D + j] = (float)(q[j] + lk.joffset[j]);
+        }
+        if (f_effort) {  // calculateTipForce runs at both levels of the retry (model.cpp:932-938)
+          K tau[D];
+#pragma unroll
+          for (int j = 0; j < D; ++j) tau[j] = io.efforts ? K(io.efforts[((size_t)r * L + l) * D + j]) : K(0);
+          const V3<K> raw = raw_tip_force<K, D>(ck, lk, ch, tau);
+          V3<K> f = adm_force;
+          for (int k = 0; k < force_updates; ++k) f = raw * (K(0.15) * ck.force_gain) + f * (K(1) - K(0.15));
+          st3(sl, LS::ADM_FORCE, f);
+        }
+        continue;
+      }
       status |= apply_ik_step<K, D>(ck, lk, ch, q, qd, desired, ci.clamp_joint_positions != 0, ci.clamp_joint_velocities != 0,
                                     &des_leg);
 #pragma unroll

@@ -38,20 +38,24 @@ using PrecMixed = Prec<float, float, double>;  // fp32 state + trajectory; fp64 
 #ifndef SHC_MIN_BLOCKS_FULL
 #define SHC_MIN_BLOCKS_FULL 12
 #endif
+// the tip-orientation path (6 x 6 solve, second DLS step and retry per leg) is not a throughput configuration: 8 warps per SM
+#ifndef SHC_MIN_BLOCKS_TIP
+#define SHC_MIN_BLOCKS_TIP 8
+#endif
 #ifdef SHC_MAXNREG
 #define SHC_KERNEL_BOUNDS __maxnreg__(SHC_MAXNREG)
 #else
-#define SHC_KERNEL_BOUNDS __launch_bounds__(SHC_BLOCK, FULL ? SHC_MIN_BLOCKS_FULL : SHC_MIN_BLOCKS)
+#define SHC_KERNEL_BOUNDS __launch_bounds__(SHC_BLOCK, MODE == 2 ? SHC_MIN_BLOCKS_TIP : MODE == 1 ? SHC_MIN_BLOCKS_FULL : SHC_MIN_BLOCKS)
 #endif
-template <class P, int D, bool FULL>
+template <class P, int D, int MODE>
 __global__ void SHC_KERNEL_BOUNDS control_cycle_kernel(const __grid_constant__ Consts c, Planes<typename P::S> pl, StepIO io) {
   extern __shared__ __align__(128) unsigned char shc_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tile = io.tile_begin + blockIdx.x * (SHC_BLOCK / 32) + warp;
   const int tile_first = tile * 32;
   if (tile >= io.tile_end || tile_first >= c.i.n_robots) return;  // whole warp
-  using CY = Cycle<P, D, FULL>;
-  const int front = FULL ? c.i.frontS_leg : 0;
+  using CY = Cycle<P, D, MODE>;
+  const int front = CY::FULL ? c.i.frontS_leg : 0;
   unsigned char* wsm = shc_smem + (size_t)warp * c.i.smem_per_warp;
   CY::run(c, pl, tile, lane, io, wsm);
   __syncwarp();
@@ -103,6 +107,7 @@ struct SignalArgs {
   int* flag[8];
   int* mc_flag;
   int n;
+  int count;                  // cycles this signal accounts for
   unsigned long long* trace;  // tuning (SHC_GATHER_TRACE): globaltimer stamps of this launch, else null
 };
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -113,9 +118,9 @@ __device__ __forceinline__ unsigned long long global_ns() {
 __global__ void gather_signal_kernel(SignalArgs a) {
   if (a.trace && threadIdx.x == 0) a.trace[1] = global_ns();
   if (a.mc_flag) {
-    if (threadIdx.x == 0) multimem_red_release_add(a.mc_flag, 1);
+    if (threadIdx.x == 0) multimem_red_release_add(a.mc_flag, a.count);
   } else if (threadIdx.x < a.n) {
-    red_release_sys_add(a.flag[threadIdx.x], 1);
+    red_release_sys_add(a.flag[threadIdx.x], a.count);
   }
   if (a.trace && threadIdx.x == 0) a.trace[2] = global_ns();
 }
@@ -334,6 +339,9 @@ struct shc_engine {
   cudaEvent_t ev_kernel[kGatherBuffers] = {};  // "cycle's kernel done", for the side-stream signal kernels
   long long gather_cycle = 0;   // cycles issued (same on every rank)
   long long gather_waited = 0;  // every source is known to have landed at least this many cycles here
+  long long gather_signalled = 0;  // cycles whose landed signal has been issued (<= gather_cycle)
+  int gather_signal_every = 4;     // a landed signal every so many cycles inside a call (and at every shc_gather_sync)
+  int gather_signal_memop = 0;     // 1: the signal is a stream memory operation (cuStreamWriteValue32) instead of a kernel
 };
 
 // NCCL is resolved at run time from the libnccl already loaded in the process (torch's), so libshc_b200.so has no
@@ -458,15 +466,17 @@ static int reset_to_initial_state(shc_engine* e) {
 
 // Calls f(kernel pointer, Planes) for the instantiation this engine runs.
 template <class F> static int with_cycle_kernel(shc_engine* e, F&& f) {
-  const bool full = engine_full(e->cfg);
+  const int mode = engine_mode(e->cfg);
   return dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int {
     constexpr int D = decltype(dtag)::value;
     if (e->precision == SHC_PRECISION_F64) {
       Planes<double> pl{(double*)e->s_planes, e->d_planes, e->i_planes};
-      return full ? f(control_cycle_kernel<PrecF64, D, true>, pl) : f(control_cycle_kernel<PrecF64, D, false>, pl);
+      return mode == 2 ? f(control_cycle_kernel<PrecF64, D, 2>, pl)
+             : mode == 1 ? f(control_cycle_kernel<PrecF64, D, 1>, pl) : f(control_cycle_kernel<PrecF64, D, 0>, pl);
     }
     Planes<float> pl{(float*)e->s_planes, e->d_planes, e->i_planes};
-    return full ? f(control_cycle_kernel<PrecMixed, D, true>, pl) : f(control_cycle_kernel<PrecMixed, D, false>, pl);
+    return mode == 2 ? f(control_cycle_kernel<PrecMixed, D, 2>, pl)
+           : mode == 1 ? f(control_cycle_kernel<PrecMixed, D, 1>, pl) : f(control_cycle_kernel<PrecMixed, D, 0>, pl);
   });
 }
 
@@ -477,8 +487,8 @@ static int configure_cycle_kernel(shc_engine* e) {
   const int front = full ? e->c.i.frontS_leg : 0;
   dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int {
     constexpr int D = decltype(dtag)::value;
-    e->c.i.smem_per_warp = e->precision == SHC_PRECISION_F64 ? Cycle<PrecF64, D, false>::smem_per_warp(front, e->cfg.leg_count)
-                                                            : Cycle<PrecMixed, D, false>::smem_per_warp(front, e->cfg.leg_count);
+    e->c.i.smem_per_warp = e->precision == SHC_PRECISION_F64 ? Cycle<PrecF64, D, 0>::smem_per_warp(front, e->cfg.leg_count)
+                                                            : Cycle<PrecMixed, D, 0>::smem_per_warp(front, e->cfg.leg_count);
     return 0;
   });
   e->smem_block = (size_t)e->c.i.smem_per_warp * (SHC_BLOCK / 32);
@@ -1153,6 +1163,18 @@ int shc_rollout_allgather(shc_engine* e, int k_cycles, const float* cmd_seq, flo
 //     this GPU and the switch replicates it (egress = the shard, not world-1 copies of it);
 //   * shc_gather_alloc / shc_gather_open_peer: the engines cudaMalloc the buffers and exchange CUDA-IPC handles; the
 //     kernel then issues one TMA bulk store per peer (unicast).
+// cuStreamWriteValue32 of the driver already loaded in the process (no link-time dependency on libcuda)
+typedef int (*StreamWriteValue32Fn)(cudaStream_t, unsigned long long, unsigned, unsigned);
+static StreamWriteValue32Fn stream_write_value32() {
+  static StreamWriteValue32Fn fn = [] {
+    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libcuda.so.1", RTLD_NOW);
+    StreamWriteValue32Fn f = h ? (StreamWriteValue32Fn)dlsym(h, "cuStreamWriteValue32_v2") : nullptr;
+    if (!f && h) f = (StreamWriteValue32Fn)dlsym(h, "cuStreamWriteValue32");
+    return f;
+  }();
+  return fn;
+}
 static size_t gather_data_bytes(const shc_engine* e, int world) {
   const size_t per_rank = (size_t)e->n * e->cfg.leg_count * e->cfg.joint_count;
   return ((size_t)kGatherBuffers * world * per_rank * 4 + 255) / 256 * 256;
@@ -1174,6 +1196,10 @@ static int gather_common_init(shc_engine* e) {
   }
   e->gather_cycle = 0;
   e->gather_waited = 0;
+  e->gather_signalled = 0;
+  // tuning switches: SHC_GATHER_SIGNAL_EVERY=k (1 <= k <= kGatherWaitEvery), SHC_GATHER_SIGNAL=memop
+  if (const char* v = getenv("SHC_GATHER_SIGNAL_EVERY")) e->gather_signal_every = std::min(std::max(atoi(v), 1), kGatherWaitEvery);
+  if (const char* v = getenv("SHC_GATHER_SIGNAL")) e->gather_signal_memop = !strcmp(v, "memop") && stream_write_value32() != nullptr;
   if (getenv("SHC_GATHER_TRACE") && !e->gather_trace) {
     CUDA_TRY(cudaHostAlloc((void**)&e->gather_trace, 4096 * 4 * 8, cudaHostAllocMapped));
     std::memset(e->gather_trace, 0, 4096 * 4 * 8);
@@ -1269,6 +1295,41 @@ static int gather_wait(shc_engine* e, long long need, cudaStream_t st) {
   return SHC_OK;
 }
 
+// "Every cycle issued so far has landed everywhere": an event behind the last kernel, then on the high-priority side
+// stream either a one-warp kernel whose system-scope release waits for the posted NVLink writes to drain and bumps this
+// rank's counter on every rank (through the multicast address when there is one: the path the data took), or
+// (SHC_GATHER_SIGNAL=memop) one stream memory operation per rank that writes the new count once the kernel has completed.
+// Sparse inside a call (every gather_signal_every cycles: the release holds up the SM it runs on while the next cycle's
+// warps on that SM keep storing) and always issued by shc_gather_sync.
+static int gather_signal(shc_engine* e, cudaStream_t st) {
+  const long long upto = e->gather_cycle;
+  if (upto <= e->gather_signalled) return SHC_OK;
+  const int slot = (int)((upto - 1) % kGatherBuffers);
+  CUDA_TRY(cudaEventRecord(e->ev_kernel[slot], st));
+  CUDA_TRY(cudaStreamWaitEvent(e->signal, e->ev_kernel[slot], 0));
+  if (e->gather_signal_memop) {
+    for (int p = 0; p < e->world; ++p) {
+      const int rc = stream_write_value32()(e->signal, (unsigned long long)(uintptr_t)(gather_flags_of(e, p) + e->rank), (unsigned)upto, 0);
+      if (rc != 0) return fail(SHC_E_CUDA, "cuStreamWriteValue32 failed (" + std::to_string(rc) + ")");
+    }
+  } else {
+    SignalArgs sa;
+    sa.trace = (e->gather_trace && upto - 1 < 2048) ? e->gather_trace + (upto - 1) * 4 : nullptr;
+    sa.n = 0;
+    sa.count = (int)(upto - e->gather_signalled);
+    sa.mc_flag = nullptr;
+    if (e->gather_mc) {
+      sa.mc_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(e->gather_mc) + gather_data_bytes(e, e->world)) + e->rank;
+    } else {
+      for (int p = 0; p < e->world; ++p) sa.flag[sa.n++] = gather_flags_of(e, p) + e->rank;  // own counter included
+    }
+    gather_signal_kernel<<<1, 32, 0, e->signal>>>(sa);
+    CUDA_TRY(cudaGetLastError());
+  }
+  e->gather_signalled = upto;
+  return SHC_OK;
+}
+
 // One control cycle whose joint commands land in buffer (cycle % shc_gather_buffers()) of EVERY rank, stored from inside
 // the kernel.  Per-cycle protocol (no collective, nothing on the critical path but the kernel itself):
 //   * reuse: buffer b was last written by cycle c - B.  A peer's consumers of that data were ordered on its stream
@@ -1305,22 +1366,10 @@ int shc_gather_step(shc_engine* e, const float* cmd, const float* imu, const flo
     for (int p = 0; p < e->world; ++p)
       if (p != e->rank) io.gather[io.n_gather++] = e->gather_peer[p];
   if ((rc = launch_cycle(e, io, st)) != SHC_OK) return rc;
-  if (tune == 2) { e->gather_cycle = cyc + 1; e->gather_waited = cyc + 1; return SHC_OK; }
-  if (e->gather_trace && cyc < 2048) gather_stamp_kernel<<<1, 1, 0, st>>>(e->gather_trace + cyc * 4);
-  CUDA_TRY(cudaEventRecord(e->ev_kernel[b], st));
-  CUDA_TRY(cudaStreamWaitEvent(e->signal, e->ev_kernel[b], 0));
-  SignalArgs sa;
-  sa.trace = (e->gather_trace && cyc < 2048) ? e->gather_trace + cyc * 4 : nullptr;
-  sa.n = 0;
-  sa.mc_flag = nullptr;
-  if (e->gather_mc) {
-    sa.mc_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(e->gather_mc) + gather_data_bytes(e, e->world)) + e->rank;
-  } else {
-    for (int p = 0; p < e->world; ++p) sa.flag[sa.n++] = gather_flags_of(e, p) + e->rank;  // own counter included
-  }
-  gather_signal_kernel<<<1, 32, 0, e->signal>>>(sa);
-  CUDA_TRY(cudaGetLastError());
   e->gather_cycle = cyc + 1;
+  if (tune == 2) { e->gather_waited = e->gather_signalled = cyc + 1; return SHC_OK; }
+  if (e->gather_trace && cyc < 2048) gather_stamp_kernel<<<1, 1, 0, st>>>(e->gather_trace + cyc * 4);
+  if ((cyc + 1) % e->gather_signal_every == 0) return gather_signal(e, st);
   return SHC_OK;
 }
 
@@ -1332,6 +1381,7 @@ int shc_gather_sync(shc_engine* e, int* last_buffer_out, void* stream) {
   CUDA_TRY(cudaSetDevice(e->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
   if (last_buffer_out) *last_buffer_out = e->gather_cycle > 0 ? (int)((e->gather_cycle - 1) % kGatherBuffers) : -1;
+  if ((rc = gather_signal(e, st)) != SHC_OK) return rc;
   return gather_wait(e, e->gather_cycle, st);
 }
 

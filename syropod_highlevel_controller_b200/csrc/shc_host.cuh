@@ -29,7 +29,6 @@ inline bool validate_config(const shc_config& c, std::string& err, bool& unsuppo
   if (!(c.step_frequency > 0.0)) return bad("step_frequency must be > 0");
   if (c.auto_poser_count < 0 || c.auto_poser_count > SHC_MAX_AUTO_POSERS) return bad("auto_poser_count out of range");
   if (c.rough_terrain_mode) { unsupported = true; return bad("rough_terrain_mode is outside the hot-path scope (needs tf2 / TipState touchdown inputs)"); }
-  if (c.gravity_aligned_tips) { unsupported = true; return bad("gravity_aligned_tips (tip rotation IK / tip-align pose) is not implemented"); }
   if (c.joint_count != 3 && c.joint_count != 4 && c.joint_count != 5) { unsupported = true; return bad("kernels are instantiated for 3, 4 and 5 joints per leg"); }
   return true;
 }
@@ -90,6 +89,12 @@ template <class R> void fill_static_consts(const shc_config& c, RealConsts<R>& k
   k.swing_stiffness_scaler = R(c.swing_stiffness_scaler);
   k.load_stiffness_scaler = R(c.load_stiffness_scaler);
   k.body_velocity_scaler = R(c.body_velocity_scaler);
+  if (c.gravity_aligned_tips && c.joint_count > 3) {
+    // WalkController::init (walk_controller.cpp:36-41): the identity tip rotation points the tip's x axis down; every leg's
+    // target_tip_pose_.rotation_ keeps it (nothing redefines it without rough-terrain targets)
+    Q4<double> q = correct_rotation(from_two_vectors(V3<double>{1.0, 0.0, 0.0}, V3<double>{0.0, 0.0, -1.0}), qidentity<double>());
+    k.tip_target_rot[0] = R(q.w); k.tip_target_rot[1] = R(q.x); k.tip_target_rot[2] = R(q.y); k.tip_target_rot[3] = R(q.z);
+  }
   for (int a = 0; a < c.auto_poser_count; ++a) {
     k.ap_pos[a][0] = R(c.x_amplitudes[a]); k.ap_pos[a][1] = R(c.y_amplitudes[a]); k.ap_pos[a][2] = R(c.z_amplitudes[a]);
     k.ap_rot[a][0] = R(c.roll_amplitudes[a]); k.ap_rot[a][1] = R(c.pitch_amplitudes[a]); k.ap_rot[a][2] = R(c.yaw_amplitudes[a]);
@@ -348,6 +353,7 @@ template <int D> void initial_state(const shc_config& c, const RealConsts<double
   auto ident = [](double* p) { for (int i = 0; i < 7; ++i) p[i] = 0.0; p[3] = 1.0; };
   ident(s.odometry_ideal); ident(s.walk_plane_pose); ident(s.origin_walk_plane_pose); ident(s.manual_pose);
   ident(s.imu_pose); ident(s.inclination_pose); ident(s.auto_pose); ident(s.current_pose);
+  ident(s.tip_align_pose); ident(s.origin_tip_align_pose);
   s.walk_plane_pose[2] = c.body_clearance;
   s.origin_walk_plane_pose[2] = c.body_clearance;
   s.current_pose[2] = c.body_clearance;
@@ -362,6 +368,8 @@ template <int D> void initial_state(const shc_config& c, const RealConsts<double
       g.default_tip_position[k] = id[k];
       g.target_tip_position[k] = id[k];
     }
+    if (c.gravity_aligned_tips && D > 3)  // LegStepper(): current = origin = target = identity tip pose (walk_controller.cpp:795)
+      for (int k = 0; k < 4; ++k) g.tip_rotation[k] = g.origin_tip_rotation[k] = g.target_tip_rotation[k] = ck.tip_target_rot[k];
     g.walk_plane_normal[2] = 1.0;
     g.swing_progress = -1.0;
     g.stance_progress = -1.0;

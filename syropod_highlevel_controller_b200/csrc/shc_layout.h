@@ -28,6 +28,13 @@ enum : int { IMU_Q = 0 /*imu_pose_.rotation_ (4)*/, IMU_ABS = 4 /*absement (3)*/
              publishRotationPoseError*/, IMU_COUNT = 15 };
 // optional auto-pose block (auto_posing), relative to offS_auto
 enum : int { AUTO_POSE = 0 /*auto_pose_ (7)*/, AUTO_COUNT = 7 };
+// optional tip-align block (gravity_aligned_tips on legs of at most three joints), relative to offS_tip
+enum : int { TA_POSE = 0 /*tip_align_pose_ (7)*/, TA_ORIGIN = 7 /*origin_tip_align_pose_ (7)*/, TA_COUNT = 14 };
+// optional per-leg tip-rotation block (gravity_aligned_tips on legs of more than three joints), relative to
+// offS_leg + leg * strideS_leg + tipS_leg: quaternions w x y z, all zero = UNDEFINED_ROTATION
+enum : int { TR_CUR = 0 /*LegStepper::current_tip_pose_.rotation_*/, TR_ORIGIN = 4 /*origin_tip_pose_.rotation_*/, TR_COUNT = 8 };
+// tip_mode of an engine
+enum : int { TIP_NONE = 0, TIP_ALIGN_POSE = 1, TIP_ROTATION = 2 };
 
 // per-leg storage planes, relative to offS_leg + leg * strideS_leg (the plane of the leg's first joint position).
 // The planes every cycle reads come first and are contiguous: [front .. STAGED) is what one TMA bulk copy stages into

@@ -265,6 +265,16 @@ template <class R> SHC_HD Q4<R> from_two_vectors(V3<R> a, V3<R> b) {
   R invs = R(1) / s;
   return {s * R(0.5), axis.x * invs, axis.y * invs, axis.z * invs};
 }
+// Eigen AngleAxis(Quaternion): angle = 2 atan2(|vec|, |w|), axis = vec / (+-|vec|); (0, x-axis) for a null vector part.
+// Returns axis * angle, the rotation vector the reference feeds to solveIK (model.cpp:893-894).
+template <class R> SHC_HD V3<R> rotation_vector(Q4<R> q) {
+  V3<R> v{q.x, q.y, q.z};
+  R n = norm(v);
+  if (n == R(0)) return {R(0), R(0), R(0)};
+  const R angle = R(2) * atan2_(n, abs_(q.w));
+  if (q.w < R(0)) n = -n;
+  return V3<R>{v.x / n, v.y / n, v.z / n} * angle;
+}
 template <class R> struct Eps;
 template <> struct Eps<double> { static constexpr double v = 2.220446049250313e-16; };
 template <> struct Eps<float> { static constexpr float v = 1.1920929e-07f; };

@@ -25,10 +25,15 @@ inline void layout(const shc_config& cfg, int n, IntConsts& ci) {
   if (imu) s += IMU_COUNT;
   ci.offS_auto = s;
   if (cfg.auto_posing) s += AUTO_COUNT;
+  ci.tip_mode = !cfg.gravity_aligned_tips ? TIP_NONE : D <= 3 ? TIP_ALIGN_POSE : TIP_ROTATION;
+  ci.offS_tip = s;
+  if (ci.tip_mode == TIP_ALIGN_POSE) s += TA_COUNT;
   const LegOff lo(D);
   ci.frontS_leg = adm ? -lo.ADM_X : 0;
   ci.offS_leg = s + ci.frontS_leg;  // plane of leg 0's first joint position; the staged admittance planes sit in front
   ci.strideS_leg = lo.COUNT + (adm ? ADM_COUNT : 0);
+  ci.tipS_leg = ci.strideS_leg - ci.frontS_leg;  // behind the appended admittance planes
+  if (ci.tip_mode == TIP_ROTATION) ci.strideS_leg += TR_COUNT;
   ci.nS = s + ci.strideS_leg * cfg.leg_count;
   ci.offD_leg = RD_COUNT;
   ci.strideD_leg = LD_COUNT;
@@ -120,6 +125,11 @@ template <class E> void pack(const E* e, const shc_robot_state* in, size_t n, Ho
       I(ci.offI_auto + AI_FLAGS, r) = pf;
       I(ci.offI_auto + AI_PHASE, r) = s.pose_phase;
     }
+    if (ci.tip_mode == TIP_ALIGN_POSE)
+      for (int k = 0; k < 7; ++k) {
+        S(ci.offS_tip + TA_POSE + k, r) = s.tip_align_pose[k];
+        S(ci.offS_tip + TA_ORIGIN + k, r) = s.origin_tip_align_pose[k];
+      }
     I(RI_BITS, r) = (s.walk_state & 3) | ((s.legs_at_correct_phase & 15) << 2) | ((s.legs_completed_first_step & 15) << 6) |
                     ((s.return_to_default_attempted & 1) << 10) | ((s.pose_state & 3) << 11) | ((s.auto_posing_state & 3) << 13) |
                     (1 << RB_PLANE_CHANGED) |  // a state written from outside: the first cycle reads the legs' saved planes
@@ -157,6 +167,11 @@ template <class E> void pack(const E* e, const shc_robot_state* in, size_t n, Ho
         }
         S(sb + lo.STIFF, r) = g.virtual_stiffness;
       }
+      if (ci.tip_mode == TIP_ROTATION)
+        for (int k = 0; k < 4; ++k) {
+          S(sb + ci.tipS_leg + TR_CUR + k, r) = g.tip_rotation[k];
+          S(sb + ci.tipS_leg + TR_ORIGIN + k, r) = g.origin_tip_rotation[k];
+        }
       const int ib = ci.offI_leg + l * ci.strideI_leg;
       I(ib + LI_BITS, r) = (g.phase & 0xffff) | ((g.step_state & 3) << 16) | ((g.at_correct_phase ? 1 : 0) << 18) |
                            ((g.completed_first_step ? 1 : 0) << 19) | ((g.negate_auto_pose ? 1 : 0) << 20);
@@ -195,7 +210,12 @@ template <int D, class E> void unpack(const E* e, const HostPlanes& h, shc_robot
       s.manual_pose[k] = S(RS_MAN + k, r);
     }
     auto ident = [](double* p) { for (int i = 0; i < 7; ++i) p[i] = 0.0; p[3] = 1.0; };
-    ident(s.imu_pose); ident(s.inclination_pose); ident(s.auto_pose);
+    ident(s.imu_pose); ident(s.inclination_pose); ident(s.auto_pose); ident(s.tip_align_pose); ident(s.origin_tip_align_pose);
+    if (ci.tip_mode == TIP_ALIGN_POSE)
+      for (int k = 0; k < 7; ++k) {
+        s.tip_align_pose[k] = S(ci.offS_tip + TA_POSE + k, r);
+        s.origin_tip_align_pose[k] = S(ci.offS_tip + TA_ORIGIN + k, r);
+      }
     if (!e->cfg.manual_posing) ident(s.manual_pose);
     if (imu) {
       for (int k = 0; k < 4; ++k) s.imu_pose[3 + k] = S(ci.offS_imu + IMU_Q + k, r);
@@ -230,6 +250,7 @@ template <int D, class E> void unpack(const E* e, const HostPlanes& h, shc_robot
       if (e->cfg.inclination_posing) p = pose_add(p, rd(s.inclination_pose));
       if (e->cfg.imu_posing) p = pose_add(p, rd(s.imu_pose));
       else if (e->cfg.auto_posing) p = pose_add(p, rd(s.auto_pose));
+      if (ci.tip_mode == TIP_ALIGN_POSE) p = pose_add(p, rd(s.tip_align_pose));
       s.current_pose[0] = p.p.x; s.current_pose[1] = p.p.y; s.current_pose[2] = p.p.z;
       s.current_pose[3] = p.q.w; s.current_pose[4] = p.q.x; s.current_pose[5] = p.q.y; s.current_pose[6] = p.q.z;
     }
@@ -262,6 +283,12 @@ template <int D, class E> void unpack(const E* e, const HostPlanes& h, shc_robot
         }
         g.virtual_stiffness = S(sb + LS::STIFF, r);
       }
+      if (ci.tip_mode == TIP_ROTATION)
+        for (int k = 0; k < 4; ++k) {
+          g.tip_rotation[k] = S(sb + ci.tipS_leg + TR_CUR + k, r);
+          g.origin_tip_rotation[k] = S(sb + ci.tipS_leg + TR_ORIGIN + k, r);
+          g.target_tip_rotation[k] = ck.tip_target_rot[k];
+        }
       const int ib = ci.offI_leg + l * ci.strideI_leg;
       int b = I(ib + LI_BITS, r), pg = I(ib + LI_PROG, r);
       g.phase = b & 0xffff;
@@ -302,8 +329,12 @@ template <class F> inline int dispatch_D_raw(int D, F&& f) {
 }
 
 inline bool engine_full(const shc_config& cfg) {
-  return cfg.auto_posing || cfg.admittance_control || cfg.imu_posing || cfg.inclination_posing || cfg.use_joint_effort;
+  return cfg.auto_posing || cfg.admittance_control || cfg.imu_posing || cfg.inclination_posing || cfg.use_joint_effort ||
+         cfg.gravity_aligned_tips;
 }
+// Kernel instantiation of an engine: 0 walking only, 1 every optional stage, 2 those plus the tip-orientation path
+// (gravity_aligned_tips: tip-align posing on legs of at most three joints, tip-rotation IK beyond)
+inline int engine_mode(const shc_config& cfg) { return cfg.gravity_aligned_tips ? 2 : engine_full(cfg) ? 1 : 0; }
 
 // Everything shc_create refuses: invalid configurations and reference features outside the built scope.
 inline bool check_supported(const shc_config& cfg, std::string& err, bool& unsupported) {

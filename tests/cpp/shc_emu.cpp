@@ -51,16 +51,16 @@ static void from_host(shc_emu* e, const HostPlanes& h) {
   e->i = h.i;
 }
 
-template <class P, int D, bool FULL>
+template <class P, int D, int MODE>
 static void step_all(shc_emu* e, const StepIO& io_in) {
-  using CY = Cycle<P, D, FULL>;
+  using CY = Cycle<P, D, MODE>;
   using S = typename P::S;
   const IntConsts& ci = e->c.i;
   Planes<S> pl;
   if constexpr (sizeof(S) == 8) pl.s = (S*)e->s64.data(); else pl.s = (S*)e->s32.data();
   pl.d = e->d.data();
   pl.i = e->i.data();
-  const int front = FULL ? ci.frontS_leg : 0;
+  const int front = CY::FULL ? ci.frontS_leg : 0;
   std::vector<unsigned char> raw(ci.smem_per_warp + 256);
   unsigned char* wsm = (unsigned char*)(((uintptr_t)raw.data() + 127) / 128 * 128);
   const int LD = ci.L * D;
@@ -89,8 +89,8 @@ int shc_emu_create(const shc_config* cfg, const shc_startup* startup, int n_robo
   const int front = full ? e->c.i.frontS_leg : 0;
   dispatch_D_raw(cfg->joint_count, [&](auto dtag) -> int {
     constexpr int D = decltype(dtag)::value;
-    e->c.i.smem_per_warp = precision == SHC_PRECISION_F64 ? Cycle<PrecF64, D, false>::smem_per_warp(front, cfg->leg_count)
-                                                          : Cycle<PrecMixed, D, false>::smem_per_warp(front, cfg->leg_count);
+    e->c.i.smem_per_warp = precision == SHC_PRECISION_F64 ? Cycle<PrecF64, D, 0>::smem_per_warp(front, cfg->leg_count)
+                                                          : Cycle<PrecMixed, D, 0>::smem_per_warp(front, cfg->leg_count);
     return 0;
   });
   HostPlanes h;
@@ -146,13 +146,13 @@ int shc_emu_step(shc_emu* e, const float* cmd, const float* imu, const float* ti
   io.tile_end = (e->n + 31) / 32;
   io.flags_out = (e->options & SHC_OPT_STATUS_FLAGS) ? e->flags.data() : nullptr;
   io.pose_reset_mode = e->pose_reset_mode;
-  const bool full = engine_full(e->cfg);
+  const int mode = engine_mode(e->cfg);
   return dispatch_D_raw(e->cfg.joint_count, [&](auto dtag) -> int {
     constexpr int D = decltype(dtag)::value;
     if (e->precision == SHC_PRECISION_F64) {
-      if (full) step_all<PrecF64, D, true>(e, io); else step_all<PrecF64, D, false>(e, io);
+      if (mode == 2) step_all<PrecF64, D, 2>(e, io); else if (mode == 1) step_all<PrecF64, D, 1>(e, io); else step_all<PrecF64, D, 0>(e, io);
     } else {
-      if (full) step_all<PrecMixed, D, true>(e, io); else step_all<PrecMixed, D, false>(e, io);
+      if (mode == 2) step_all<PrecMixed, D, 2>(e, io); else if (mode == 1) step_all<PrecMixed, D, 1>(e, io); else step_all<PrecMixed, D, 0>(e, io);
     }
     return SHC_OK;
   });

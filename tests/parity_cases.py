@@ -360,6 +360,67 @@ def single_step_inputs(backend, oracle, n=64, cycles=200):
     eng.close(); ob.close()
 
 
+def tip_orientation(backend, oracle, n=48, cycles=400):
+    """gravity_aligned_tips (SURVEY.md a2 / a15 / a22).  Legs of more than three joints: LegStepper::updateTipRotation
+    (walk_controller.cpp:1193) turns the stepper's tip rotation towards "tip x axis down" through the second half of every
+    swing, PoseController::updateStance carries it into the poser's tip pose, and Leg::applyIK (model.cpp:880-900, 932-936)
+    follows the position step by a rotation step with the full 6 x D Jacobian, retrying position-only when the constrained
+    attempt misses IK_TOLERANCE.  Legs of at most three joints: PoseController::updateTipAlignPose
+    (pose_controller.cpp:1024) shifts the body instead.  One cycle from identical state to 1e-11 on every field, then a
+    free-running rollout."""
+    for cfg, L, D in ((octopod_config("tripod_gait", gravity_aligned_tips=1), 8, 5),
+                      (octopod_config("ripple_gait", gravity_aligned_tips=1, use_joint_effort=1), 8, 5),
+                      (hexapod_config("tripod_gait", gravity_aligned_tips=1), 6, 3),
+                      (hexapod_config("wave_gait", gravity_aligned_tips=1, auto_posing=1), 6, 3)):
+        ob = oracle.OracleBatch(cfg, n)
+        eng = backend.engine(cfg, n, startup=ob.startup())
+        own = backend.engine(cfg, n, startup=None)  # the engine's own initial state carries the tip rotations too
+        assert_state_close(own.get_state(), ob.get_state(), L, D, 1e-7, skip=JOINT_FIELDS)
+        own.close()
+        cs = CommandStream(n, min_len=40, max_len=160)
+        ims = ImuStream(n) if cfg.imu_posing or cfg.inclination_posing else None
+        fs = ForceStream(n, L) if cfg.admittance_control and not cfg.use_joint_effort else None
+        rng = np.random.default_rng(21)
+        retried = rotated = shifted = 0
+        for c in range(cycles):
+            cmd = cs.next()
+            imu = ims.next(cfg.time_delta) if ims else None
+            force = fs.next() if fs else None
+            if cfg.use_joint_effort and c % 25 == 0:
+                eff = rng.normal(0.0, 2.0, size=(n, L, D)).astype(np.float32)
+                eng.set_joint_efforts(eff)
+                ob.set_joint_efforts(eff.astype(np.float64))
+            sample = c % 3 == 2
+            if sample:
+                eng.set_state(ob.get_state())
+                j = eng.step(cmd, imu, force)
+            ob.step(cmd.astype(np.float64), None if imu is None else imu.astype(np.float64),
+                    None if force is None else force.astype(np.float64), threads=4)
+            if sample:
+                so = ob.get_state()
+                assert np.abs(j - ob.joints()).max() <= 1e-7, c
+                d = assert_state_close(eng.get_state(), so, L, D, 1e-11, vel_tol=1e-9, skip=("tip_force_calculated",))
+                assert d["tip_force_calculated"] < 1e-9
+                for s in so:
+                    rotated += sum(1 for l in range(L) if any(v != 0.0 for v in s.legs[l].tip_rotation))
+                    retried += sum(1 for l in range(L) if s.legs[l].ik_result == 0.0)
+                    shifted += 1 if any(abs(v) > 1e-4 for v in list(s.tip_align_pose)[:3]) else 0
+        if D > 3:
+            assert rotated > 0 and retried > 0, (rotated, retried)  # rotation-constrained IK and its retry were both live
+        else:
+            assert shifted > 0  # the body really shifted
+        print(f"[tip-orientation] {L}x{D}: leg-cycles with a defined tip rotation {rotated}, IK results of 0 {retried}, "
+              f"robot-cycles with a tip-align shift {shifted}")
+        # free-running
+        eng.set_state(ob.get_state())
+        errs = run_both(eng, ob, 200, cs, ims, fs, dt=cfg.time_delta, threads=4) if not cfg.use_joint_effort else None
+        if errs is not None:
+            errs.check(max_fraction=5e-3, label=f"gravity_aligned_tips {L}x{D} free-running")
+            assert_state_close(eng.get_state(), ob.get_state(), L, D, 1e-6,
+                               skip=JOINT_FIELDS + (("tip_rotation", "origin_tip_rotation", "admittance_delta") if D > 3 else ()))
+        eng.close(); ob.close()
+
+
 def mixed_precision_statistics(backend, oracle, n=256, cycles=600):
     """Mixed precision over a long rollout: the typical joint error stays far below 1e-6 rad; excursions are bounded by
     the amplitude of the reference's own period-2 joint chatter (~2.3e-3 rad peak to peak), which fp32 state cannot

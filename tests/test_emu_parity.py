@@ -68,6 +68,10 @@ def test_emu_single_step_parity_inputs(emu, oracle):
     P.single_step_inputs(emu, oracle, n=32, cycles=200)
 
 
+def test_emu_tip_orientation(emu, oracle):
+    P.tip_orientation(emu, oracle, n=16, cycles=300)
+
+
 def test_emu_wire_formats(emu, oracle):
     P.wire_formats(emu, oracle)
 

@@ -71,6 +71,10 @@ def test_mixed_precision_rollout_statistics(gpu, oracle):
     P.mixed_precision_statistics(gpu, oracle)
 
 
+def test_tip_orientation(gpu, oracle):
+    P.tip_orientation(gpu, oracle, n=48, cycles=400)
+
+
 def test_wire_formats(gpu, oracle):
     P.wire_formats(gpu, oracle)
 

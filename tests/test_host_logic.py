@@ -49,7 +49,7 @@ def test_no_cpu_fallback(shc_lib):
 def test_unsupported_configs_are_rejected(shc_lib):
     from syropod_highlevel_controller_b200.engine import ShcError, compute_startup
 
-    for key in ("rough_terrain_mode", "gravity_aligned_tips"):
+    for key in ("rough_terrain_mode",):
         with pytest.raises(ShcError):
             compute_startup(hexapod_config(**{key: 1}))
     bad = hexapod_config()
