@@ -329,21 +329,26 @@ def main():
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         gather_ok = bool(int(okt.item()))
 
-    # kernel-only duration (no all-gather in the region) for the roofline: one launch per step on this stream
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    k0.record()
-    for i in range(pre + W, pre + W + K):
-        eng.step(*inputs(i))
-    k1.record()
-    torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / K
+    # Average launch duration of the control-cycle kernel for the roofline.  N = 1: the timed region above IS K launches of
+    # that kernel on this stream and nothing else, so its CUDA-event time / K is the figure (launch gaps included).  N > 1: the
+    # region also holds the exchange, so K more launches without it are timed the same way.
+    if world == 1:
+        kernel_ms, kernel_ms_src = ms / K, "timed region (K launches of the kernel, CUDA events on the launching stream)"
+    else:
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        k0.record()
+        for i in range(pre + W, pre + W + K):
+            eng.step(*inputs(i))
+        k1.record()
+        torch.cuda.synchronize()
+        kernel_ms, kernel_ms_src = k0.elapsed_time(k1) / K, "K launches without the exchange, after the timed region"
     peak, peak_src = measured_peak()
     b_alg = eng.bytes_per_step_algorithmic
     achieved = n * b_alg / (kernel_ms * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic(args.precision, args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_src, "kernel": "control_cycle_kernel", "kernel_ms": kernel_ms,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "control_cycle_kernel", "kernel_ms": kernel_ms, "kernel_ms_source": kernel_ms_src,
                 "algorithmic_bytes_per_step": b_alg, "device_bytes_per_step": eng.bytes_per_step_device,
                 "device_bytes_GBps": n * eng.bytes_per_step_device / (kernel_ms * 1e-3) / 1e9, "peak_source": peak_src}
 
