@@ -146,6 +146,31 @@ int shc_pack_messages(shc_engine* e, size_t first, size_t count, const float* me
  *                             workspace, 1 the layered workspace of rough-terrain mode.  HOST outputs heights [L][max_planes],
  *                             radii [L][max_planes][9], n_planes [L].
  *   shc_host_generate_workspaces  the same routine on the host (no device needed). */
+/* Stepping and joint-space sequences on the device, each call = one loop() for the whole batch:
+ *   shc_step_to_new_stance    PoseController::stepToNewStance (pose_controller.cpp:520): the legs of each robot's current
+ *                             group step to their default tip positions (LegPoser::stepToPosition :1571: dual quartic
+ *                             Bezier, swing height as lift, one step period, body pose blended in) + Leg::applyIK
+ *                             (model.cpp:861); the two leg groups alternate per robot as its own legs complete.
+ *                             joints_out_dev float [N][L][D] / progress_out_dev int [N] (each robot's return value), either
+ *                             may be NULL.  Returns the smallest progress over the batch (blocking on `stream`).
+ *   shc_sequence_reset        forgets a stepping sequence in progress.
+ *   shc_transition_begin/step PoseController::transitionConfiguration (:703) / LegPoser::transitionConfiguration (:1476): the
+ *                             batch moves from the joint positions its state holds to desired_configuration (HOST doubles
+ *                             [L][D]) in max(1, roundToInt(time / time_delta)) loops; step returns the progress 1..100.
+ *   shc_pack_legs / shc_unpack_legs  one loop() of PoseController::packLegs (:597) / unpackLegs (:661) towards
+ *                             shc_config.joint_packed / joint_unpacked; return the progress (100 = complete).
+ * PoseController::executeSequence (:145, the multi-step start-up / shut-down sequence generator) is not built. */
+int shc_step_to_new_stance(shc_engine* e, float* joints_out_dev, int* progress_out_dev, void* stream);
+int shc_sequence_reset(shc_engine* e);
+int shc_transition_begin(shc_engine* e, const double* desired_configuration, double transition_time);
+int shc_transition_step(shc_engine* e, float* joints_out_dev, void* stream);
+int shc_pack_legs(shc_engine* e, double time_to_pack, float* joints_out_dev, void* stream);
+int shc_unpack_legs(shc_engine* e, double time_to_unpack, float* joints_out_dev, void* stream);
+/* Host-buffer form of one loop() of a sequence (the C++ facade uses it): joints_out [N][L][D] / progress_out [N] are HOST
+ * arrays, either may be NULL; SHC_SEQ_DIRECT_STARTUP begins the direct start-up on its first call (default joint positions).
+ * Returns the smallest progress over the batch or a negative SHC_E_* code. */
+enum { SHC_SEQ_NEW_STANCE = 0, SHC_SEQ_PACK = 1, SHC_SEQ_UNPACK = 2, SHC_SEQ_DIRECT_STARTUP = 3 };
+int shc_sequence_step_host(shc_engine* e, int kind, double time, float* joints_out, int* progress_out);
 int shc_startup_begin(shc_engine* e, const double* joint_positions_dev);
 int shc_startup_step(shc_engine* e, float* joints_out_dev, void* stream);
 int shc_direct_startup(shc_engine* e, const double* joint_positions_dev, float* joints_out_dev, void* stream);

@@ -103,6 +103,11 @@ typedef struct shc_config {
   double force_gain;
   double load_stiffness_scaler;
   double swing_stiffness_scaler;
+
+  /* ---- pack / unpack (default.yaml:31-48 "packed" / "unpacked": Joint::packed_positions_ with one pack step,
+   *      Joint::unpacked_position_; model.cpp:1019-1036) ---- */
+  double joint_packed[SHC_MAX_LEGS][SHC_MAX_DOF];
+  double joint_unpacked[SHC_MAX_LEGS][SHC_MAX_DOF];
 } shc_config;
 
 /* Constants produced by the reference's start-up path (state_controller.cpp:263-281:

@@ -209,6 +209,12 @@ class PoseController {  // pose_controller.h:36
   void updateCurrentPose(const RobotState&) {}
   /// PoseController::updateStance (pose_controller.cpp:110): executed inside the fused cycle.
   void updateStance() {}
+  /// Sequences (one loop() per call, pose_controller.cpp:463 / :520 / :597 / :661): they act on the whole batch — the first
+  /// robot to call in a loop runs the device step for everyone, the other robots' calls of that loop read their own result.
+  inline int directStartup();
+  inline int stepToNewStance();
+  inline int packLegs(const double& time_to_pack);
+  inline int unpackLegs(const double& time_to_unpack);
   inline void setManualPoseInput(const Vector3d& translation, const Vector3d& rotation);  // pose_controller.h:116
   inline void setPoseResetMode(const PoseResetMode& mode);                                // pose_controller.h:105
   inline PosingState getAutoPoseState();
@@ -326,6 +332,19 @@ class Batch {
     }
     return state_[r];
   }
+  /// One loop() of a sequence as seen by robot r (see PoseController::directStartup ...).
+  int sequence(int r, int kind, double time) {
+    if (seq_used_.empty()) { seq_used_.assign(n_, 1); seq_progress_.assign(n_, 0); }
+    if (seq_used_[r] || kind != seq_kind_) {
+      if (shc_sequence_step_host(e_, kind, time, joints_.data(), seq_progress_.data()) < 0)
+        throw std::runtime_error(std::string("shc_sequence_step_host: ") + shc_last_error());
+      std::fill(seq_used_.begin(), seq_used_.end(), 0);
+      seq_kind_ = kind;
+      ++cycles_;
+    }
+    seq_used_[r] = 1;
+    return seq_progress_[r];
+  }
   void setLimitMaps(const double* ls, const double* as, const double* la, const double* aa) {
     if (shc_set_limit_maps(e_, ls, as, la, aa) != SHC_OK) throw std::runtime_error(std::string("shc_set_limit_maps: ") + shc_last_error());
     have_startup_ = false;
@@ -342,7 +361,9 @@ class Batch {
   shc_engine* e_ = nullptr;
   std::vector<Controllers> robots_;
   std::vector<float> cmd_, imu_, force_, manual_, joints_;
-  std::vector<char> reached_;
+  std::vector<char> reached_, seq_used_;
+  std::vector<int> seq_progress_;
+  int seq_kind_ = -1;
   int arrived_ = 0;
   std::vector<shc_robot_state> state_;
   std::vector<long> fetched_;  // cycle count at which state_[r] was fetched (-1: never)
@@ -523,6 +544,10 @@ inline void WalkController::setAngularSpeedLimitMap(const std::array<double, SHC
 inline void WalkController::setLinearAccelerationLimitMap(const std::array<double, SHC_N_BEARINGS>& m) { b_->setLimitMaps(nullptr, nullptr, m.data(), nullptr); }
 inline void WalkController::setAngularAccelerationLimitMap(const std::array<double, SHC_N_BEARINGS>& m) { b_->setLimitMaps(nullptr, nullptr, nullptr, m.data()); }
 
+inline int PoseController::directStartup() { return b_->sequence(robot_, SHC_SEQ_DIRECT_STARTUP, 0.0); }
+inline int PoseController::stepToNewStance() { return b_->sequence(robot_, SHC_SEQ_NEW_STANCE, 0.0); }
+inline int PoseController::packLegs(const double& t) { return b_->sequence(robot_, SHC_SEQ_PACK, t); }
+inline int PoseController::unpackLegs(const double& t) { return b_->sequence(robot_, SHC_SEQ_UNPACK, t); }
 inline void PoseController::setManualPoseInput(const Vector3d& t, const Vector3d& r) { b_->setManual(robot_, t, r); }
 inline void PoseController::setPoseResetMode(const PoseResetMode& mode) { b_->setPoseResetMode(int(mode)); }
 inline PosingState PoseController::getAutoPoseState() { return PosingState(b_->state(robot_).auto_posing_state); }

@@ -63,6 +63,7 @@ def _bind(L):
         L.shc_oracle_batch_run_seq.restype = C.c_double
         L.shc_oracle_batch_run_seq.argtypes = [C.c_void_p, dp, C.c_int, C.c_int]
         L.shc_oracle_batch_get_joints.argtypes = [C.c_void_p, dp]
+        L.shc_oracle_batch_sequence_step.argtypes = [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_int)]
         L.shc_oracle_batch_get_state.argtypes = [C.c_void_p, C.POINTER(ShcRobotState)]
         L.shc_oracle_batch_set_state.argtypes = [C.c_void_p, C.POINTER(ShcRobotState)]
         L.shc_oracle_batch_set_pose_reset_mode.argtypes = [C.c_void_p, C.c_int]
@@ -151,6 +152,14 @@ class OracleBatch:
         e = _arr(efforts)
         assert e is None or e.shape == (self.n, self.L, self.D)
         self._lib.shc_oracle_batch_set_joint_efforts(self._h, _dp(e))
+
+    def sequence_step(self, kind: str, time: float = 0.0) -> np.ndarray:
+        """One loop() of PoseController::stepToNewStance ("new_stance", pose_controller.cpp:520), packLegs(time) ("pack",
+        :597) or unpackLegs(time) ("unpack", :661) for every robot; returns each robot's progress value."""
+        out = np.zeros(self.n, dtype=np.int32)
+        self._lib.shc_oracle_batch_sequence_step(self._h, {"new_stance": 0, "pack": 1, "unpack": 2}[kind], float(time),
+                                                 out.ctypes.data_as(C.POINTER(C.c_int)))
+        return out
 
     def joints(self) -> np.ndarray:
         out = np.empty((self.n, self.L, self.D), dtype=np.float64)

@@ -64,6 +64,7 @@ struct Joint {
   double desired_position_ = 0, desired_velocity_ = 0, desired_effort_ = 0, prev_desired_position_ = 0;
   double current_position_ = UNASSIGNED_VALUE, current_velocity_ = 0, current_effort_ = 0;
   double default_position_ = UNASSIGNED_VALUE, default_velocity_ = 0, default_effort_ = 0;
+  double packed_position_ = 0, unpacked_position_ = 0;  // packed_positions_[0] / unpacked_position_ (model.cpp:1035-1056)
   Mat4 current_transform_ = Mat4::Identity();  // transform from previous joint to this joint
 };
 struct Link {
@@ -201,6 +202,8 @@ struct Robot {
   Pose manual_pose_, auto_pose_, imu_pose_, inclination_pose_, default_pose_, tip_align_pose_, origin_tip_align_pose_,
       walk_plane_pose_, origin_walk_plane_pose_;
   bool executing_transition_ = false;
+  int legs_completed_step_ = 0, current_group_ = 0, pack_step_ = 0;
+  bool reset_transition_sequence_ = true;
   int auto_pose_reference_leg_ = 0;
   std::vector<AutoPoser> auto_posers_;
   PosingState auto_posing_state_ = POSING_COMPLETE;
@@ -243,6 +246,9 @@ struct Robot {
   void setAutoPoseParams();
   void updateStance();
   int directStartup();
+  int stepToNewStance();
+  int packLegs(double time_to_pack);
+  int unpackLegs(double time_to_unpack);
   void updateCurrentPose(RobotState robot_state);
   void updateManualPose();
   void updateTipAlignPose();

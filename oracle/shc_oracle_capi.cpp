@@ -333,6 +333,17 @@ double shc_oracle_batch_run_seq(void* h, const double* cmd_seq, int cycles, int 
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// One loop() of a stepping / joint-space sequence for every robot: kind 0 = stepToNewStance
+// (pose_controller.cpp:520), 1 = packLegs(time) (:597), 2 = unpackLegs(time) (:661).  progress_out [n] gets each robot's return value.
+void shc_oracle_batch_sequence_step(void* h, int kind, double time, int* progress_out) {
+  Batch* b = static_cast<Batch*>(h);
+  for (size_t i = 0; i < b->robots.size(); ++i) {
+    Robot& r = *b->robots[i];
+    int p = kind == 0 ? r.stepToNewStance() : kind == 1 ? r.packLegs(time) : r.unpackLegs(time);
+    if (progress_out) progress_out[i] = p;
+  }
+}
+
 void shc_oracle_batch_get_joints(void* h, double* out) {  // [n][L][D]
   Batch* b = static_cast<Batch*>(h);
   const int L = b->cfg.leg_count, D = b->cfg.joint_count;

@@ -100,6 +100,8 @@ void Leg::construct(Robot* r, int id) {  // Leg::Leg (model.cpp:169-188) + Leg::
     j.max_position_ = p.joint_max[id][i - 1];
     j.offset_ = p.joint_offset[id][i - 1];
     j.max_angular_speed_ = p.joint_max_vel[id][i - 1];
+    j.packed_position_ = p.joint_packed[id][i - 1];
+    j.unpacked_position_ = p.joint_unpacked[id][i - 1];
     j.default_position_ = clamped(0.0, j.min_position_, j.max_position_);
     const Link& ref = links[i - 1];
     j.current_transform_ = createDHMatrix(ref.d, ref.theta, ref.r, ref.alpha);

@@ -111,6 +111,77 @@ int Robot::directStartup() {  // pose_controller.cpp:463
   return progress;
 }
 
+int Robot::stepToNewStance() {  // pose_controller.cpp:520 (tripod leg coordination)
+  int progress = 0;
+  int leg_count = leg_count_;
+  for (int i = 0; i < leg_count_; ++i) {
+    Leg& leg = legs[i];
+    if (leg.group_ == current_group_) {
+      LegStepper& leg_stepper = leg.stepper;
+      LegPoser& leg_poser = leg.poser;
+      double step_height = params_.swing_height;
+      double step_time = 1.0 / params_.step_frequency;
+      Pose target_tip_pose = leg_stepper.default_tip_pose_;
+      progress = leg_poser.stepToPosition(target_tip_pose, current_pose_, step_height, step_time);
+      leg.setDesiredTipPose(leg_poser.current_tip_pose_);
+      leg.applyIK();
+      legs_completed_step_ += int(progress == PROGRESS_COMPLETE);
+    }
+  }
+  progress = progress / 2 + current_group_ * 50;
+  current_group_ = legs_completed_step_ / (leg_count / 2);
+  if (legs_completed_step_ == leg_count) {
+    legs_completed_step_ = 0;
+    current_group_ = 0;
+  }
+  reset_transition_sequence_ = true;
+  return progress;
+}
+
+int Robot::packLegs(double time_to_pack) {  // pose_controller.cpp:597 (one pack step: Joint::packed_positions_ has one entry)
+  int progress = 0;
+  int number_pack_steps = 1;
+  for (int i = 0; i < leg_count_; ++i) {
+    Leg& leg = legs[i];
+    LegPoser& leg_poser = leg.poser;
+    if (!executing_transition_) {
+      std::vector<double> packed_configuration(leg.joint_count_, UNASSIGNED_VALUE);
+      for (int j = 1; j <= leg.joint_count_; ++j) packed_configuration[j - 1] = leg.joints[j].packed_position_;
+      leg_poser.desired_configuration_ = packed_configuration;
+    }
+    progress = leg_poser.transitionConfiguration(time_to_pack);
+  }
+  executing_transition_ = (progress != 0 && progress != PROGRESS_COMPLETE);
+  if (progress == PROGRESS_COMPLETE && pack_step_ < number_pack_steps - 1) {
+    executing_transition_ = false;
+    pack_step_++;
+    progress = 0;
+  }
+  return progress;
+}
+
+int Robot::unpackLegs(double time_to_unpack) {  // pose_controller.cpp:661
+  int progress = 0;
+  for (int i = 0; i < leg_count_; ++i) {
+    Leg& leg = legs[i];
+    LegPoser& leg_poser = leg.poser;
+    if (!executing_transition_) {
+      std::vector<double> unpacked_configuration(leg.joint_count_, UNASSIGNED_VALUE);
+      for (int j = 1; j <= leg.joint_count_; ++j)
+        unpacked_configuration[j - 1] = (pack_step_ > 0) ? leg.joints[j].packed_position_ : leg.joints[j].unpacked_position_;
+      leg_poser.desired_configuration_ = unpacked_configuration;
+    }
+    progress = leg_poser.transitionConfiguration(time_to_unpack);
+  }
+  executing_transition_ = (progress != 0 && progress != PROGRESS_COMPLETE);
+  if (progress == PROGRESS_COMPLETE && pack_step_ != 0) {
+    executing_transition_ = false;
+    pack_step_--;
+    progress = 0;
+  }
+  return progress;
+}
+
 void Robot::updateCurrentPose(RobotState robot_state) {  // pose_controller.cpp:811
   Pose new_pose = Pose::Identity();
   updateWalkPlanePose();

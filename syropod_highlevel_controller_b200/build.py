@@ -8,7 +8,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libshc_b200.so")
 SOURCES = ["shc_engine.cu"]
-HEADERS = ["shc_math.cuh", "shc_consts.h", "shc_layout.h", "shc_cycle.cuh", "shc_host.cuh", "shc_pack.cuh", "shc_msgs.cuh",
+HEADERS = ["shc_math.cuh", "shc_consts.h", "shc_layout.h", "shc_cycle.cuh", "shc_host.cuh", "shc_pack.cuh", "shc_msgs.cuh", "shc_sequence.cuh",
            "shc_startup.cuh"]
 
 NVCC_FLAGS = [

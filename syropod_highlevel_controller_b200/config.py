@@ -62,6 +62,7 @@ class ShcConfig(C.Structure):
         ("integrator_step_time", _d), ("virtual_mass", _d), ("virtual_stiffness", _d),
         ("virtual_damping_ratio", _d), ("force_gain", _d),
         ("load_stiffness_scaler", _d), ("swing_stiffness_scaler", _d),
+        ("joint_packed", (_d * MAX_DOF) * MAX_LEGS), ("joint_unpacked", (_d * MAX_DOF) * MAX_LEGS),
     ]
 
 
@@ -269,6 +270,7 @@ def hexapod_config(gait: str = "tripod_gait", time_delta: float = 0.02, **overri
         for j in range(3):
             cfg.joint_min[i][j], cfg.joint_max[i][j] = jmin[j], jmax[j]
             cfg.joint_max_vel[i][j], cfg.joint_offset[i][j] = 5.000, 0.000
+            cfg.joint_packed[i][j], cfg.joint_unpacked[i][j] = (-1.571, 1.900, 1.200)[j], (0.000, 0.785, -1.138)[j]
         # links: base, coxa, femur, tibia  -> (d, theta, r, alpha)
         links = [(0.0, base_theta[name], 0.050, 0.000), (0.0, 0.0, 0.050, 1.571),
                  (0.0, 0.0, 0.050, 0.000), (0.0, -0.100, 0.100, 0.000)]
@@ -316,6 +318,8 @@ def octopod_config(gait: str = "tripod_gait", time_delta: float = 0.02, **overri
         for j in range(5):
             cfg.joint_min[i][j], cfg.joint_max[i][j] = jmin[j], jmax[j]
             cfg.joint_max_vel[i][j], cfg.joint_offset[i][j] = 5.000, 0.000
+            cfg.joint_packed[i][j] = (-1.400 if right else 1.400, 0.000, 1.450, -1.900, 0.500)[j]
+            cfg.joint_unpacked[i][j] = (0.000, 0.000, 0.700, -1.200, -0.300)[j]
         rad = 0.200
         cfg.stance_x[i] = round(rad * math.cos(theta0), 3)
         cfg.stance_y[i] = round(rad * math.sin(theta0), 3)
@@ -381,6 +385,7 @@ def load_reference_yaml(default_yaml: str, gait_yaml: str, auto_pose_yaml: Optio
             jp = p[f"{leg}_{joints[j]}_joint_parameters"]
             cfg.joint_min[i][j], cfg.joint_max[i][j] = float(jp["min"]), float(jp["max"])
             cfg.joint_max_vel[i][j], cfg.joint_offset[i][j] = float(jp["max_vel"]), float(jp["offset"])
+            cfg.joint_packed[i][j], cfg.joint_unpacked[i][j] = float(jp.get("packed", 0.0)), float(jp.get("unpacked", 0.0))
         for k in range(D + 1):
             lp = p[f"{leg}_{links[k]}_link_parameters"]
             cfg.link_d[i][k], cfg.link_theta[i][k] = float(lp["d"]), float(lp["theta"])

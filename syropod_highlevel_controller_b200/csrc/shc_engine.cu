@@ -16,6 +16,7 @@
 
 #include "../../include/shc_b200.h"
 #include "shc_msgs.cuh"
+#include "shc_sequence.cuh"
 #include "shc_pack.cuh"
 
 namespace shc {
@@ -247,6 +248,35 @@ __global__ void __launch_bounds__(32) workspace_sweep_kernel(const __grid_consta
   if (lane == 0) n_planes[l] = np;
 }
 
+
+// PoseController::stepToNewStance (pose_controller.cpp:520) for every robot: one thread per robot (csrc/shc_sequence.cuh).
+template <class S, int D>
+__global__ void __launch_bounds__(128) step_to_new_stance_kernel(const __grid_constant__ Consts c, Planes<S> pl, SeqBuffers sq, NewStanceParams np,
+                                                                 float* __restrict__ joints_out, int* __restrict__ progress_out, int* min_progress) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= c.i.n_robots) return;
+  const int p = step_to_new_stance_robot<S, D>(c, pl, sq, np, r, joints_out);
+  if (progress_out) progress_out[r] = p;
+  atomicMin(min_progress, p);
+}
+template <class S, int D>
+__global__ void __launch_bounds__(256) transition_joint_kernel(const __grid_constant__ Consts c, Planes<S> pl, const double* __restrict__ origin,
+                                                               const double* __restrict__ desired, int it, int num, float* __restrict__ joints_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)c.i.n_robots * c.i.L * D) return;
+  transition_joint<S, D>(c, pl, origin, desired, it, num, i, joints_out);
+}
+template <class S, int D>
+__global__ void __launch_bounds__(256) latch_joint_kernel(const __grid_constant__ Consts c, Planes<S> pl, double* __restrict__ origin) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)c.i.n_robots * c.i.L * D) return;
+  latch_joint<S, D>(c, pl, i, origin);
+}
+__global__ void fill_int_kernel(int* p, size_t n, int v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
 }  // namespace shc
 
 using namespace shc;
@@ -267,8 +297,11 @@ template <class F> static int dispatch_D(int D, F&& f) {
     if (err__ != cudaSuccess) return fail(SHC_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(err__)); \
   } while (0)
 
-// Fused gather: cycle k writes buffer k % B of every rank (B = 16); see shc_gather_step for the protocol.
-constexpr int kGatherBuffers = 16;
+// Fused gather: cycle k writes buffer k % B of every rank (B = 24); see shc_gather_step for the protocol.  Reuse checks and
+// landed signals both come every 8th cycle; with 24 buffers a reuse check asks for a count the peers signalled a whole
+// signalling period earlier (need = cycle - 15 against a counter that reads cycle - 8 even if this cycle's signal is still
+// in flight), so it never waits on a signal that has only just been issued.
+constexpr int kGatherBuffers = 24;
 constexpr int kGatherWaitEvery = 8;   // reuse check every 8th cycle, for the next 8 cycles
 constexpr size_t kMaxCachedGraphs = 16;
 constexpr int kHostChunks = 8;  // tile ranges of one shc_step_host call (kernel k+1 overlaps the D2H of range k)
@@ -332,6 +365,15 @@ struct shc_engine {
   double* startup_desired = nullptr;  // [kMaxLegs][kMaxDof] desired configuration
   bool startup_has_origin = false;
   int startup_iteration = 0, startup_num = 0;
+  // stepping / joint-space sequences on the device (shc_step_to_new_stance, shc_transition_*, shc_pack_legs / shc_unpack_legs)
+  double* seq_origin = nullptr;   // [L][3][n_pad] LegPoser::origin_tip_pose_.position_
+  int* seq_count = nullptr;       // [L][n_pad] LegPoser::master_iteration_count_ (-1: first_iteration_)
+  int* seq_robot = nullptr;       // [2][n_pad] legs_completed_step_, current_group_
+  int* seq_min = nullptr;         // device word: smallest progress of the last stepToNewStance launch
+  double* tr_origin = nullptr;    // [N][L][D] joint positions when the transition began
+  double* tr_desired = nullptr;   // [kMaxLegs][kMaxDof]
+  int tr_iteration = 0, tr_num = 0;
+  bool tr_executing = false;      // PoseController::executing_transition_ (pack / unpack)
   int* gather_err = nullptr;  // mapped pinned word: set by a device-side wait that gave up
   cudaStream_t signal = nullptr;  // high-priority stream of the landed-signal kernels
   unsigned long long* gather_trace = nullptr;  // tuning (SHC_GATHER_TRACE): mapped pinned stamps [4096][4]: kernel end, signal
@@ -340,7 +382,7 @@ struct shc_engine {
   long long gather_cycle = 0;   // cycles issued (same on every rank)
   long long gather_waited = 0;  // every source is known to have landed at least this many cycles here
   long long gather_signalled = 0;  // cycles whose landed signal has been issued (<= gather_cycle)
-  int gather_signal_every = 4;     // a landed signal every so many cycles inside a call (and at every shc_gather_sync)
+  int gather_signal_every = 8;     // a landed signal every so many cycles inside a call (and at every shc_gather_sync)
   int gather_signal_memop = 0;     // 1: the signal is a stream memory operation (cuStreamWriteValue32) instead of a kernel
 };
 
@@ -635,6 +677,12 @@ void shc_destroy(shc_engine* e) {
   cudaFree(e->d_flags);
   cudaFree(e->startup_origin);
   cudaFree(e->startup_desired);
+  cudaFree(e->seq_origin);
+  cudaFree(e->seq_count);
+  cudaFree(e->seq_robot);
+  cudaFree(e->seq_min);
+  cudaFree(e->tr_origin);
+  cudaFree(e->tr_desired);
   cudaFree(e->d_cmd); cudaFree(e->d_imu); cudaFree(e->d_force); cudaFree(e->d_manual); cudaFree(e->d_out);
   cudaFreeHost(e->h_cmd); cudaFreeHost(e->h_imu); cudaFreeHost(e->h_force); cudaFreeHost(e->h_manual); cudaFreeHost(e->h_out);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -1026,6 +1074,189 @@ int shc_direct_startup(shc_engine* e, const double* joint_positions_dev, float* 
   if (rc != SHC_OK) return rc;
   e->startup_iteration = e->startup_num;
   return startup_launch(e, e->startup_num, joints_out_dev, stream ? (cudaStream_t)stream : e->stream);
+}
+
+// ---- stepping and joint-space sequences (device routines in csrc/shc_sequence.cuh) -----------------
+static int seq_alloc(shc_engine* e) {
+  if (e->seq_origin) return SHC_OK;
+  const int L = e->cfg.leg_count;
+  const size_t np = e->n_pad;
+  CUDA_TRY(cudaMalloc((void**)&e->seq_origin, seq_origin_count(L, np) * 8));
+  CUDA_TRY(cudaMalloc((void**)&e->seq_count, seq_count_count(L, np) * 4));
+  CUDA_TRY(cudaMalloc((void**)&e->seq_robot, seq_robot_count(np) * 4));
+  CUDA_TRY(cudaMalloc((void**)&e->seq_min, 4));
+  return shc_sequence_reset(e);
+}
+
+// Forgets any stepping sequence in progress: every LegPoser back to first_iteration_, group 0, no completed steps.
+int shc_sequence_reset(shc_engine* e) {
+  if (!e) return fail(SHC_E_INVALID, "null engine");
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (!e->seq_origin) return seq_alloc(e);
+  const size_t nc = seq_count_count(e->cfg.leg_count, e->n_pad);
+  fill_int_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, e->stream>>>(e->seq_count, nc, -1);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemsetAsync(e->seq_robot, 0, seq_robot_count(e->n_pad) * 4, e->stream));
+  CUDA_TRY(cudaMemsetAsync(e->seq_origin, 0, seq_origin_count(e->cfg.leg_count, e->n_pad) * 8, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return SHC_OK;
+}
+
+// One loop() of PoseController::stepToNewStance (pose_controller.cpp:520) for every robot of the batch: the legs of each
+// robot's current group step to their default tip positions (LegPoser::stepToPosition :1571 with the swing height as lift
+// and one step period as duration, under the robot's current body pose), followed by Leg::applyIK; the groups alternate as
+// each robot's own legs complete.  joints_out_dev float [N][L][D] or NULL; progress_out_dev int [N] or NULL (each robot's
+// return value).  Returns the smallest progress over the batch (>= 0; blocking on `stream`) or a negative SHC_E_* code.
+int shc_step_to_new_stance(shc_engine* e, float* joints_out_dev, int* progress_out_dev, void* stream) {
+  if (!e) return fail(SHC_E_INVALID, "null engine");
+  if (e->c.i.tip_mode == TIP_ROTATION) return fail(SHC_E_UNSUPPORTED, "stepping sequences with tip-rotation targets (gravity_aligned_tips, D > 3) are not built");
+  if (e->cfg.leg_count % 2 != 0) return fail(SHC_E_UNSUPPORTED, "stepToNewStance coordinates two leg groups: leg_count must be even");
+  CUDA_TRY(cudaSetDevice(e->device));
+  int rc = seq_alloc(e);
+  if (rc != SHC_OK) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  NewStanceParams np;
+  np.lift_height = e->cfg.swing_height;
+  np.num_iterations = std::max(1, round_to_int((1.0 / e->cfg.step_frequency) / e->cfg.time_delta));
+  np.apply_delta = 1;
+  SeqBuffers sq{e->seq_origin, e->seq_count, e->seq_robot, (size_t)e->n_pad};
+  const int init = 1000;
+  CUDA_TRY(cudaMemcpyAsync(e->seq_min, &init, 4, cudaMemcpyHostToDevice, st));
+  const int threads = 128, blocks = (e->n + threads - 1) / threads;
+  rc = dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int {
+    constexpr int D = decltype(dtag)::value;
+    if (e->precision == SHC_PRECISION_F64) {
+      Planes<double> pl{(double*)e->s_planes, e->d_planes, e->i_planes};
+      step_to_new_stance_kernel<double, D><<<blocks, threads, 0, st>>>(e->c, pl, sq, np, joints_out_dev, progress_out_dev, e->seq_min);
+    } else {
+      Planes<float> pl{(float*)e->s_planes, e->d_planes, e->i_planes};
+      step_to_new_stance_kernel<float, D><<<blocks, threads, 0, st>>>(e->c, pl, sq, np, joints_out_dev, progress_out_dev, e->seq_min);
+    }
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(SHC_E_CUDA, std::string("step_to_new_stance launch: ") + cudaGetErrorString(err));
+    return SHC_OK;
+  });
+  if (rc != SHC_OK) return rc;
+  int progress = 0;
+  CUDA_TRY(cudaMemcpyAsync(&progress, e->seq_min, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return progress;
+}
+
+// PoseController::transitionConfiguration (pose_controller.cpp:703) for the whole batch: from the joint positions the state
+// planes hold to desired_configuration (host doubles [L][D]) along LegPoser::transitionConfiguration's cubic Bezier (:1476)
+// in max(1, roundToInt(transition_time / time_delta)) loops.
+int shc_transition_begin(shc_engine* e, const double* desired_configuration, double transition_time) {
+  if (!e || !desired_configuration || !(transition_time >= 0.0)) return fail(SHC_E_INVALID, "shc_transition_begin: bad arguments");
+  CUDA_TRY(cudaSetDevice(e->device));
+  const int L = e->cfg.leg_count, D = e->cfg.joint_count;
+  const long long total = (long long)e->n * L * D;
+  if (!e->tr_origin) CUDA_TRY(cudaMalloc((void**)&e->tr_origin, (size_t)total * 8));
+  if (!e->tr_desired) CUDA_TRY(cudaMalloc((void**)&e->tr_desired, sizeof(double) * kMaxLegs * kMaxDof));
+  double desired[kMaxLegs][kMaxDof] = {};
+  for (int l = 0; l < L; ++l)
+    for (int j = 0; j < D; ++j) desired[l][j] = desired_configuration[l * D + j];
+  CUDA_TRY(cudaMemcpyAsync(e->tr_desired, desired, sizeof(desired), cudaMemcpyHostToDevice, e->stream));
+  const int threads = 256, blocks = (int)((total + threads - 1) / threads);
+  int rc = dispatch_D(D, [&](auto dtag) -> int {
+    constexpr int DD = decltype(dtag)::value;
+    if (e->precision == SHC_PRECISION_F64) latch_joint_kernel<double, DD><<<blocks, threads, 0, e->stream>>>(e->c, Planes<double>{(double*)e->s_planes, e->d_planes, e->i_planes}, e->tr_origin);
+    else latch_joint_kernel<float, DD><<<blocks, threads, 0, e->stream>>>(e->c, Planes<float>{(float*)e->s_planes, e->d_planes, e->i_planes}, e->tr_origin);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(SHC_E_CUDA, std::string("latch_joint launch: ") + cudaGetErrorString(err));
+    return SHC_OK;
+  });
+  if (rc != SHC_OK) return rc;
+  CUDA_TRY(cudaStreamSynchronize(e->stream));  // `desired` is a stack array
+  e->tr_iteration = 0;
+  e->tr_num = std::max(1, round_to_int(transition_time / e->cfg.time_delta));
+  return SHC_OK;
+}
+
+// One loop() of the transition: every joint of the batch moves one iteration on (one kernel); joints_out_dev (float
+// [N][L][D]) gets the joint commands.  Returns the reference's progress (1..99, 100 = PROGRESS_COMPLETE) or a negative code.
+int shc_transition_step(shc_engine* e, float* joints_out_dev, void* stream) {
+  if (!e) return fail(SHC_E_INVALID, "null engine");
+  if (e->tr_num <= 0) return fail(SHC_E_INVALID, "shc_transition_begin has not been called");
+  if (e->tr_iteration >= e->tr_num) return 100;
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  const int it = ++e->tr_iteration;
+  const long long total = (long long)e->n * e->cfg.leg_count * e->cfg.joint_count;
+  const int threads = 256, blocks = (int)((total + threads - 1) / threads);
+  int rc = dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int {
+    constexpr int D = decltype(dtag)::value;
+    if (e->precision == SHC_PRECISION_F64)
+      transition_joint_kernel<double, D><<<blocks, threads, 0, st>>>(e->c, Planes<double>{(double*)e->s_planes, e->d_planes, e->i_planes}, e->tr_origin, e->tr_desired, it, e->tr_num, joints_out_dev);
+    else
+      transition_joint_kernel<float, D><<<blocks, threads, 0, st>>>(e->c, Planes<float>{(float*)e->s_planes, e->d_planes, e->i_planes}, e->tr_origin, e->tr_desired, it, e->tr_num, joints_out_dev);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(SHC_E_CUDA, std::string("transition_joint launch: ") + cudaGetErrorString(err));
+    return SHC_OK;
+  });
+  if (rc != SHC_OK) return rc;
+  if (it >= e->tr_num) return 100;
+  const int progress = int((double(it - 1) / double(e->tr_num)) * 100);
+  return progress < 1 ? 1 : progress;
+}
+
+// One loop() of PoseController::packLegs (pose_controller.cpp:597) / unpackLegs (:661): the first call of a sequence latches
+// the batch's joint positions and targets the packed / unpacked joint positions of the configuration (one pack step),
+// every call moves the transition one iteration on.  Returns the progress (100 = complete, the next call starts anew).
+static int pack_unpack(shc_engine* e, bool pack, double time, float* joints_out_dev, void* stream) {
+  if (!e) return fail(SHC_E_INVALID, "null engine");
+  if (!e->tr_executing) {
+    double desired[kMaxLegs * kMaxDof];
+    const int L = e->cfg.leg_count, D = e->cfg.joint_count;
+    for (int l = 0; l < L; ++l)
+      for (int j = 0; j < D; ++j) desired[l * D + j] = pack ? e->cfg.joint_packed[l][j] : e->cfg.joint_unpacked[l][j];
+    int rc = shc_transition_begin(e, desired, time);
+    if (rc != SHC_OK) return rc;
+  }
+  const int progress = shc_transition_step(e, joints_out_dev, stream);
+  if (progress < 0) return progress;
+  e->tr_executing = progress != 0 && progress != 100;
+  return progress;
+}
+int shc_pack_legs(shc_engine* e, double time_to_pack, float* joints_out_dev, void* stream) { return pack_unpack(e, true, time_to_pack, joints_out_dev, stream); }
+int shc_unpack_legs(shc_engine* e, double time_to_unpack, float* joints_out_dev, void* stream) { return pack_unpack(e, false, time_to_unpack, joints_out_dev, stream); }
+
+// Host-buffer form of one loop() of a sequence, for callers without device memory of their own (the C++ facade): kind
+// SHC_SEQ_NEW_STANCE / SHC_SEQ_PACK / SHC_SEQ_UNPACK / SHC_SEQ_DIRECT_STARTUP (the direct start-up begins on its first call
+// from the default joint positions); joints_out [N][L][D] and progress_out [N] are HOST arrays (either may be NULL).
+// Returns the smallest progress over the batch or a negative SHC_E_* code.
+int shc_sequence_step_host(shc_engine* e, int kind, double time, float* joints_out, int* progress_out) {
+  if (!e) return fail(SHC_E_INVALID, "null engine");
+  int rc = ensure_staging(e, false, false, false);
+  if (rc != SHC_OK) return rc;
+  CUDA_TRY(cudaSetDevice(e->device));
+  const size_t n = e->n, L = e->cfg.leg_count, D = e->cfg.joint_count;
+  int progress;
+  int* d_progress = nullptr;
+  if (kind == SHC_SEQ_NEW_STANCE) {
+    if (progress_out) CUDA_TRY(cudaMalloc((void**)&d_progress, n * 4));
+    progress = shc_step_to_new_stance(e, e->d_out, d_progress, e->stream);
+  } else if (kind == SHC_SEQ_PACK) {
+    progress = shc_pack_legs(e, time, e->d_out, e->stream);
+  } else if (kind == SHC_SEQ_UNPACK) {
+    progress = shc_unpack_legs(e, time, e->d_out, e->stream);
+  } else if (kind == SHC_SEQ_DIRECT_STARTUP) {
+    if (e->startup_num <= 0 || e->startup_iteration >= e->startup_num) {
+      if ((rc = shc_startup_begin(e, nullptr)) != SHC_OK) return rc;
+    }
+    progress = shc_startup_step(e, e->d_out, e->stream);
+  } else {
+    return fail(SHC_E_INVALID, "shc_sequence_step_host: unknown sequence");
+  }
+  if (progress < 0) { cudaFree(d_progress); return progress; }
+  if (joints_out) CUDA_TRY(cudaMemcpyAsync(joints_out, e->d_out, n * L * D * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (progress_out) {
+    if (d_progress) CUDA_TRY(cudaMemcpyAsync(progress_out, d_progress, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    else for (size_t r = 0; r < n; ++r) progress_out[r] = progress;
+  }
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  cudaFree(d_progress);
+  return progress;
 }
 
 // Model::generateWorkspaces (model.cpp:120) / Leg::generateWorkspace (:309-510) on the device: one block per leg, the eight

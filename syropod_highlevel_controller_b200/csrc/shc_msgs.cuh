@@ -72,6 +72,7 @@ template <class S> SHC_HD PoseT<double> current_pose_of(const IntConsts& ci, con
   } else if (ci.auto_posing) {
     p = pose_add(p, rd.pose(ci.offS_auto + AUTO_POSE));
   }
+  if (ci.tip_mode == TIP_ALIGN_POSE) p = pose_add(p, rd.pose(ci.offS_tip + TA_POSE));
   return p;
 }
 

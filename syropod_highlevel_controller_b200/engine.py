@@ -48,6 +48,12 @@ def lib():
         L.shc_startup_begin.argtypes = [vp, vp]
         L.shc_startup_step.argtypes = [vp, vp, vp]
         L.shc_direct_startup.argtypes = [vp, vp, vp, vp]
+        L.shc_step_to_new_stance.argtypes = [vp, vp, vp, vp]
+        L.shc_sequence_reset.argtypes = [vp]
+        L.shc_transition_begin.argtypes = [vp, C.POINTER(C.c_double), C.c_double]
+        L.shc_transition_step.argtypes = [vp, vp, vp]
+        L.shc_pack_legs.argtypes = [vp, C.c_double, vp, vp]
+        L.shc_unpack_legs.argtypes = [vp, C.c_double, vp, vp]
         L.shc_generate_workspaces.argtypes = [vp, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int)]
         L.shc_host_generate_workspaces.argtypes = [C.POINTER(ShcConfig), C.POINTER(ShcStartup), C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int)]
         L.shc_n_robots.argtypes = [vp]
@@ -248,6 +254,62 @@ class Engine:
         out = self._out(out)
         _check(lib().shc_direct_startup(self._h, _ptr(joint_positions), _ptr(out), _stream_handle(self.torch, self.device, stream)))
         return out
+
+    # ---- stepping / joint-space sequences --------------------------------------------------------
+    def step_to_new_stance(self, out=None, progress_out=None, stream=None) -> int:
+        """One loop() of PoseController::stepToNewStance (pose_controller.cpp:520) for the batch; joint commands into `out`
+        (default: self.joints), per-robot progress into `progress_out` (int32 device tensor [N]) when given.  Returns the
+        smallest progress over the batch."""
+        out = self._out(out)
+        rc = lib().shc_step_to_new_stance(self._h, _ptr(out), _ptr(progress_out), _stream_handle(self.torch, self.device, stream))
+        if rc < 0:
+            _check(rc)
+        return rc
+
+    def sequence_reset(self):
+        _check(lib().shc_sequence_reset(self._h))
+
+    def transition_begin(self, desired_configuration, transition_time: float):
+        """PoseController::transitionConfiguration (pose_controller.cpp:703) begins: desired joint positions [L, D]."""
+        d = np.ascontiguousarray(desired_configuration, dtype=np.float64)
+        assert d.shape == (self.L, self.D)
+        _check(lib().shc_transition_begin(self._h, d.ctypes.data_as(C.POINTER(C.c_double)), float(transition_time)))
+
+    def transition_step(self, out=None, stream=None) -> int:
+        out = self._out(out)
+        rc = lib().shc_transition_step(self._h, _ptr(out), _stream_handle(self.torch, self.device, stream))
+        if rc < 0:
+            _check(rc)
+        return rc
+
+    def pack_legs(self, time_to_pack: float, out=None, stream=None) -> int:
+        """One loop() of PoseController::packLegs (pose_controller.cpp:597); returns the progress (100 = complete)."""
+        out = self._out(out)
+        rc = lib().shc_pack_legs(self._h, float(time_to_pack), _ptr(out), _stream_handle(self.torch, self.device, stream))
+        if rc < 0:
+            _check(rc)
+        return rc
+
+    def unpack_legs(self, time_to_unpack: float, out=None, stream=None) -> int:
+        """One loop() of PoseController::unpackLegs (pose_controller.cpp:661); returns the progress (100 = complete)."""
+        out = self._out(out)
+        rc = lib().shc_unpack_legs(self._h, float(time_to_unpack), _ptr(out), _stream_handle(self.torch, self.device, stream))
+        if rc < 0:
+            _check(rc)
+        return rc
+
+    def sequence_step(self, kind: str, time: float = 0.0):
+        """Test-facing form shared with the host emulator: one loop() of "new_stance" / "pack" / "unpack";
+        returns (joints float64 numpy [N, L, D], per-robot progress int32 numpy [N])."""
+        t = self.torch
+        if kind == "new_stance":
+            prog = t.zeros(self.n, dtype=t.int32, device=self.device)
+            self.step_to_new_stance(progress_out=prog)
+        else:
+            p = self.pack_legs(time) if kind == "pack" else self.unpack_legs(time)
+            prog = t.full((self.n,), p, dtype=t.int32, device=self.device)
+        t.cuda.synchronize(self.device)
+        return self.joints.cpu().numpy().astype(np.float64), prog.cpu().numpy()
 
     # ---- state ------------------------------------------------------------------------------------------------------
     def get_state(self):

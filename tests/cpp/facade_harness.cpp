@@ -6,6 +6,7 @@
 // writes, per cycle, the desired joint positions [n][L][D] (f64, from Joint::desired_position_) followed by each
 // robot's walk state (f64) to out.bin.
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -103,8 +104,29 @@ int main(int argc, char** argv) {
       }
       std::fwrite(row.data(), sizeof(double), row.size(), out);
     }
+    // Sequences through the facade (pose_controller.cpp:520 stepToNewStance, :597 packLegs): every robot's StateController
+    // calls its own poser_ each loop, as adjustParameter / the PACKED transition do; rows = joint commands + each robot's progress.
+    const long steps_before = batch.cycles();
+    const int num = std::max(1, int((1.0 / params.cfg.step_frequency) / params.cfg.time_delta + 0.5));
+    int seq_loops = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+      for (int k = 0; k < (phase == 0 ? 2 * num : 100000); ++k) {
+        int min_progress = 1000;
+        for (int r = 0; r < n; ++r) {
+          const int p = phase == 0 ? sc[r].poser_->stepToNewStance() : sc[r].poser_->packLegs(2.0);
+          row[size_t(n) * L * D + r] = double(p);
+          min_progress = std::min(min_progress, p);
+        }
+        const std::vector<float>& j = batch.desiredJointPositions();
+        for (size_t i = 0; i < size_t(n) * L * D; ++i) row[i] = j[i];
+        std::fwrite(row.data(), sizeof(double), row.size(), out);
+        ++seq_loops;
+        if (phase == 1 && min_progress == 100) break;
+      }
+    }
     std::fclose(out);
-    std::printf("facade harness: %d robots x %d cycles, %ld engine steps\n", n, cycles, batch.cycles());
+    std::printf("facade harness: %d robots x %d cycles, %ld engine steps, %d sequence loops in %ld device steps\n", n, cycles,
+                steps_before, seq_loops, batch.cycles() - steps_before);
   } catch (const std::exception& e) {
     std::fprintf(stderr, "error: %s\n", e.what());
     return 1;

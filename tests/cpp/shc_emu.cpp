@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../syropod_highlevel_controller_b200/csrc/shc_msgs.cuh"
+#include "../../syropod_highlevel_controller_b200/csrc/shc_sequence.cuh"
 #include "../../syropod_highlevel_controller_b200/csrc/shc_pack.cuh"
 
 using namespace shc;
@@ -33,6 +34,12 @@ struct shc_emu {
   std::vector<int> flags;
   std::vector<float> efforts;
   bool have_efforts = false;
+  // sequences (csrc/shc_sequence.cuh on host planes)
+  std::vector<double> seq_origin, tr_origin;
+  std::vector<int> seq_count, seq_robot;
+  double tr_desired[kMaxLegs * kMaxDof] = {};
+  int tr_iteration = 0, tr_num = 0;
+  bool tr_executing = false;
 };
 
 static thread_local std::string g_err;
@@ -155,6 +162,56 @@ int shc_emu_step(shc_emu* e, const float* cmd, const float* imu, const float* ti
       if (mode == 2) step_all<PrecMixed, D, 2>(e, io); else if (mode == 1) step_all<PrecMixed, D, 1>(e, io); else step_all<PrecMixed, D, 0>(e, io);
     }
     return SHC_OK;
+  });
+}
+
+// The sequence routines of csrc/shc_sequence.cuh (shc_step_to_new_stance, shc_pack_legs / shc_unpack_legs) on the emulator's
+// planes, robot after robot.  kind 0 = stepToNewStance, 1 = packLegs(time), 2 = unpackLegs(time); joints_out [n][L][D],
+// progress_out [n] (pack / unpack: the same value for every robot).
+int shc_emu_sequence_reset(shc_emu* e) {
+  e->seq_origin.assign(seq_origin_count(e->cfg.leg_count, e->n_pad), 0.0);
+  e->seq_count.assign(seq_count_count(e->cfg.leg_count, e->n_pad), -1);
+  e->seq_robot.assign(seq_robot_count(e->n_pad), 0);
+  return SHC_OK;
+}
+int shc_emu_sequence_step(shc_emu* e, int kind, double time, float* joints_out, int* progress_out) {
+  if (!e || !joints_out || !progress_out) return fail(SHC_E_INVALID, "bad arguments");
+  const int L = e->cfg.leg_count;
+  return dispatch_D_raw(e->cfg.joint_count, [&](auto dtag) -> int {
+    constexpr int D = decltype(dtag)::value;
+    auto go = [&](auto pl) -> int {
+      using S = typename std::remove_pointer<decltype(pl.s)>::type;
+      if (kind == 0) {
+        if (e->seq_count.empty()) shc_emu_sequence_reset(e);
+        NewStanceParams np;
+        np.lift_height = e->cfg.swing_height;
+        np.num_iterations = std::max(1, round_to_int((1.0 / e->cfg.step_frequency) / e->cfg.time_delta));
+        np.apply_delta = 1;
+        SeqBuffers sq{e->seq_origin.data(), e->seq_count.data(), e->seq_robot.data(), (size_t)e->n_pad};
+        for (int r = 0; r < e->n; ++r) progress_out[r] = step_to_new_stance_robot<S, D>(e->c, pl, sq, np, r, joints_out);
+        return SHC_OK;
+      }
+      const long long total = (long long)e->n * L * D;
+      if (!e->tr_executing) {
+        e->tr_origin.resize((size_t)total);
+        for (long long i = 0; i < total; ++i) latch_joint<S, D>(e->c, pl, i, e->tr_origin.data());
+        for (int l = 0; l < L; ++l)
+          for (int j = 0; j < D; ++j) e->tr_desired[l * kMaxDof + j] = kind == 1 ? e->cfg.joint_packed[l][j] : e->cfg.joint_unpacked[l][j];
+        e->tr_iteration = 0;
+        e->tr_num = std::max(1, round_to_int(time / e->cfg.time_delta));
+      }
+      int progress = 100;
+      if (e->tr_iteration < e->tr_num) {
+        const int it = ++e->tr_iteration;
+        for (long long i = 0; i < total; ++i) transition_joint<S, D>(e->c, pl, e->tr_origin.data(), e->tr_desired, it, e->tr_num, i, joints_out);
+        progress = it >= e->tr_num ? 100 : std::max(1, int((double(it - 1) / double(e->tr_num)) * 100));
+      }
+      e->tr_executing = progress != 0 && progress != 100;
+      for (int r = 0; r < e->n; ++r) progress_out[r] = progress;
+      return SHC_OK;
+    };
+    if (e->precision == SHC_PRECISION_F64) return go(Planes<double>{e->s64.data(), e->d.data(), e->i.data()});
+    return go(Planes<float>{e->s32.data(), e->d.data(), e->i.data()});
   });
 }
 

@@ -50,6 +50,8 @@ def lib():
         L.shc_emu_get_state.argtypes = [vp, C.POINTER(ShcRobotState), C.c_size_t]
         L.shc_emu_set_state.argtypes = [vp, C.POINTER(ShcRobotState), C.c_size_t]
         L.shc_emu_step.argtypes = [vp, fp, fp, fp, fp, fp]
+        L.shc_emu_sequence_reset.argtypes = [vp]
+        L.shc_emu_sequence_step.argtypes = [vp, C.c_int, C.c_double, fp, C.POINTER(C.c_int)]
         L.shc_emu_pack_messages.argtypes = [vp, C.c_int, fp, C.POINTER(ShcJointStateMsg), C.POINTER(ShcLegStateMsg), C.POINTER(ShcBodyMsg)]
         _lib = L
     return _lib
@@ -127,6 +129,17 @@ class EmuEngine:
         for k in range(count):
             _check(lib().shc_emu_pack_messages(self._h, first + k, pm, C.byref(js[k]), legs[k], C.byref(body[k])))
         return js, legs, body
+
+    def sequence_reset(self):
+        _check(lib().shc_emu_sequence_reset(self._h))
+
+    def sequence_step(self, kind, time=0.0):
+        """One loop() of stepToNewStance ("new_stance") / packLegs ("pack") / unpackLegs ("unpack"): (joints [n, L, D], progress [n])."""
+        out = np.zeros((self.n, self.L, self.D), dtype=np.float32)
+        prog = np.zeros(self.n, dtype=np.int32)
+        _check(lib().shc_emu_sequence_step(self._h, {"new_stance": 0, "pack": 1, "unpack": 2}[kind], float(time),
+                                           out.ctypes.data_as(C.POINTER(C.c_float)), prog.ctypes.data_as(C.POINTER(C.c_int))))
+        return out.astype(np.float64), prog
 
     def step(self, cmd, imu=None, tip_force=None, manual=None):
         cmd, pc = _f32(cmd, (self.n, 3))

@@ -421,6 +421,59 @@ def tip_orientation(backend, oracle, n=48, cycles=400):
         eng.close(); ob.close()
 
 
+def sequences(backend, oracle, n=32):
+    """SURVEY.md 8(f) rank 2: PoseController::stepToNewStance (pose_controller.cpp:520; LegPoser::stepToPosition :1571 +
+    Leg::applyIK) and packLegs / unpackLegs (:597 / :661; LegPoser::transitionConfiguration :1476), every loop() of each
+    sequence against the oracle, from the state a walking batch was stopped in (every robot's legs somewhere else)."""
+    for cfg, L, D in ((hexapod_config("ripple_gait"), 6, 3), (octopod_config("tripod_gait"), 8, 5)):
+        ob = oracle.OracleBatch(cfg, n)
+        eng = backend.engine(cfg, n, startup=ob.startup())
+        cs = CommandStream(n, min_len=30, max_len=90)
+        ims = ImuStream(n) if cfg.imu_posing or cfg.inclination_posing else None
+        fs = ForceStream(n, L) if cfg.admittance_control else None
+        for c in range(130):  # walk for a while: tips, body poses and admittance deltas differ from robot to robot
+            cmd = cs.next()
+            imu = ims.next(cfg.time_delta) if ims else None
+            force = fs.next() if fs else None
+            ob.step(cmd.astype(np.float64), None if imu is None else imu.astype(np.float64),
+                    None if force is None else force.astype(np.float64), threads=4)
+        eng.set_state(ob.get_state())
+        # stepToNewStance: two groups, one step period each
+        loops = 2 * max(1, int(round((1.0 / cfg.step_frequency) / cfg.time_delta)))
+        worst, seen = 0.0, set()
+        # (exactly one full sequence: LegPoser shares first_iteration_ / master_iteration_count_ between stepToPosition and
+        # transitionConfiguration, so the reference itself cannot start packLegs from a half-finished step)
+        for k in range(loops):
+            j, p = eng.sequence_step("new_stance")
+            po = ob.sequence_step("new_stance")
+            assert np.array_equal(p, po), (k, p[:8], po[:8])
+            worst = max(worst, float(np.abs(j - ob.joints()).max()))
+            seen.update(int(v) for v in po)
+        assert worst <= 1e-6, worst
+        assert max(seen) >= 99 and min(seen) == 0
+        d = assert_state_close(eng.get_state(), ob.get_state(), L, D, 1e-9, vel_tol=1e-7,
+                               skip=("model_tip_position", "desired_tip_position", "ik_result"))
+        print(f"[sequences] {L}x{D} stepToNewStance: {loops} loops, worst joint difference {worst:.2e} rad, "
+              f"joint state {d['joint_position']:.2e}")
+        # packLegs, then unpackLegs (2 s each)
+        for kind in ("pack", "unpack"):
+            worst, last = 0.0, 0
+            for k in range(400):
+                j, p = eng.sequence_step(kind, 2.0)
+                po = ob.sequence_step(kind, 2.0)
+                assert np.array_equal(p, po), (kind, k, p[:4], po[:4])
+                worst = max(worst, float(np.abs(j - ob.joints()).max()))
+                last = int(po[0])
+                if last == 100:
+                    break
+            assert last == 100 and k + 1 == int(round(2.0 / cfg.time_delta)), (kind, k, last)
+            assert worst <= 1e-6, (kind, worst)
+            want = np.array([[getattr(cfg, "joint_packed" if kind == "pack" else "joint_unpacked")[l][jj] for jj in range(D)] for l in range(L)])
+            assert np.abs(ob.joints()[0] - want).max() < 1e-12  # the sequence ends on the configured joint positions
+            print(f"[sequences] {L}x{D} {kind}Legs: {k + 1} loops, worst joint difference {worst:.2e} rad")
+        eng.close(); ob.close()
+
+
 def mixed_precision_statistics(backend, oracle, n=256, cycles=600):
     """Mixed precision over a long rollout: the typical joint error stays far below 1e-6 rad; excursions are bounded by
     the amplitude of the reference's own period-2 joint chatter (~2.3e-3 rad peak to peak), which fp32 state cannot

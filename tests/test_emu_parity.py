@@ -72,6 +72,10 @@ def test_emu_tip_orientation(emu, oracle):
     P.tip_orientation(emu, oracle, n=16, cycles=300)
 
 
+def test_emu_sequences(emu, oracle):
+    P.sequences(emu, oracle, n=16)
+
+
 def test_emu_wire_formats(emu, oracle):
     P.wire_formats(emu, oracle)
 

@@ -75,6 +75,10 @@ def test_tip_orientation(gpu, oracle):
     P.tip_orientation(gpu, oracle, n=48, cycles=400)
 
 
+def test_sequences(gpu, oracle):
+    P.sequences(gpu, oracle, n=96)
+
+
 def test_wire_formats(gpu, oracle):
     P.wire_formats(gpu, oracle)
 
