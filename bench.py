@@ -122,6 +122,32 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def nvlink_counters(index):
+    """NVLink data bytes (tx, rx, raw tx, raw rx) of one GPU summed over its links, from the NVML throughput counters (KiB,
+    monotonic); None when the driver does not expose them.  Read on both sides of the timed region at N > 1: the difference
+    per cycle is the driver-side evidence of what the fused gather puts on the wire."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ids = [pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX,
+               pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_RAW_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_RAW_RX]
+        vals = pynvml.nvmlDeviceGetFieldValues(h, [(i, 0xFFFFFFFF) for i in ids])  # scope UINT_MAX = all links
+        if all(v.nvmlReturn == 0 for v in vals):
+            return [int(v.value.ullVal) * 1024 for v in vals]
+        out = [0, 0, 0, 0]  # some drivers only answer per link
+        seen = False
+        for link in range(18):
+            vals = pynvml.nvmlDeviceGetFieldValues(h, [(i, link) for i in ids])
+            for k, v in enumerate(vals):
+                if v.nvmlReturn == 0:
+                    out[k] += int(v.value.ullVal) * 1024
+                    seen = True
+        return out if seen else None
+    except Exception:
+        return None
+
+
 def _oracle_rate(cfg, robots, cycles, warm, threads):
     """steps/s of the CPU oracle over `robots` robots: per-robot command streams generated BEFORE the timed region, the
     whole rollout inside the C library (std::threads spawned once, robots partitioned over them)."""
@@ -291,7 +317,9 @@ def main():
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    nvl0 = nvlink_counters(local_rank) if world > 1 else None  # (a slow host call: before the ranks are aligned)
     if world > 1:
+        dist.barrier()
         # the host-side barrier above lets the ranks' processes leave up to a millisecond apart; a stream-ordered 1-element
         # all-reduce makes the GPUs themselves start the timed region together (a rank's region cannot end before the
         # slowest rank's last shard has landed, so start skew would be billed to the fastest rank)
@@ -301,6 +329,7 @@ def main():
     run(pre + W, pre + W + K)
     ev1.record()
     torch.cuda.synchronize()
+    nvl1 = nvlink_counters(local_rank) if world > 1 else None
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
@@ -396,7 +425,13 @@ def main():
 
     if gather_ok is not None:
         line["gather_ok"] = gather_ok
-        line["gpu_launches"] = 2 * K + (K + 7) // 8 + 1  # control cycle + landed signal per step, reuse checks, final wait
+        # control cycle per step; landed signal every 8th cycle and at the sync; reuse checks every 8th cycle; final wait
+        line["gpu_launches"] = K + (K + 7) // 8 + 1 + (K + 7) // 8 + 1
+    if nvl0 is not None and nvl1 is not None:
+        d = [(b - a) / K for a, b in zip(nvl0, nvl1)]
+        line["nvlink"] = {"tx_bytes_per_step": d[0], "rx_bytes_per_step": d[1], "raw_tx_bytes_per_step": d[2],
+                          "raw_rx_bytes_per_step": d[3], "shard_bytes": n * L * D * 4,
+                          "source": "NVML NVLINK_THROUGHPUT_DATA/RAW counters of rank 0's GPU, all links, over the timed region"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(cfg, os.cpu_count() or 1)

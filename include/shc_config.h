@@ -27,7 +27,7 @@ typedef struct shc_config {
   double time_delta;
   int manual_posing;
   int auto_posing;
-  int rough_terrain_mode; /* must be 0: rough-terrain path is out of scope */
+  int rough_terrain_mode; /* layered workspace, default-tip updates, touchdown detection and target shifting */
   int admittance_control;
   int inclination_posing;
   int imu_posing;
@@ -108,6 +108,10 @@ typedef struct shc_config {
    *      Joint::unpacked_position_; model.cpp:1019-1036) ---- */
   double joint_packed[SHC_MAX_LEGS][SHC_MAX_DOF];
   double joint_unpacked[SHC_MAX_LEGS][SHC_MAX_DOF];
+
+  /* ---- touchdown detection (default.yaml:107-108; Leg::touchdownDetection, model.cpp:712) ---- */
+  double touchdown_threshold; /* N: |measured tip force| above it defines the step plane at the tip */
+  double liftoff_threshold;   /* N: below it the step plane is forgotten */
 } shc_config;
 
 /* Constants produced by the reference's start-up path (state_controller.cpp:263-281:

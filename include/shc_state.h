@@ -54,6 +54,10 @@ typedef struct shc_leg_state {
   double origin_tip_rotation[4];    /* origin_tip_pose_.rotation_ */
   double target_tip_rotation[4];    /* target_tip_pose_.rotation_ (a constant of the configuration without rough-terrain
                                      * targets: written by shc_get_state, ignored by shc_set_state) */
+  /* rough-terrain mode */
+  double step_plane_position[3];    /* Leg::step_plane_pose_.position_ (model.h:529): the tip pose at touchdown, base_link frame */
+  int step_plane_defined;           /* step_plane_pose_ != Pose::Undefined() */
+  int touchdown_detection;          /* LegStepper::touchdown_detection_ (walk_controller.h:495): tip state inputs have arrived */
   /* outputs of the last cycle (recomputed every cycle; not algorithmic state) */
   double model_tip_position[3];     /* Leg::current_tip_pose_.position_ after applyFK (base_link frame) */
   double desired_tip_position[3];   /* Leg::desired_tip_pose_.position_ */

@@ -76,6 +76,7 @@ struct LegStepper {
   Robot* robot = nullptr;
   Leg* leg_ = nullptr;
   bool at_correct_phase_ = false, completed_first_step_ = false;
+  bool touchdown_detection_ = false;  // walk_controller.h:495: set once tip state messages arrive (state_controller.cpp:1640)
   int phase_ = 0, phase_offset_ = 0;
   double step_progress_ = 0.0, swing_progress_ = -1.0, stance_progress_ = -1.0;
   StepState step_state_ = STANCE;
@@ -151,6 +152,7 @@ struct Leg {
   void updateDefaultConfiguration();                                                // model.cpp:593
   void setDesiredTipPose(const Pose& tip_pose = Pose::Undefined(), bool apply_delta = true);  // model.cpp:653
   void calculateTipForce();                                                         // model.cpp:667
+  void touchdownDetection();                                                        // model.cpp:712
   void solveIK(const double delta[6], bool solve_rotation, double* out);            // model.cpp:726
   double updateJointPositions(const double* delta, bool simulation);                // model.cpp:799
   double applyIK(bool simulation = false);                                          // model.cpp:861

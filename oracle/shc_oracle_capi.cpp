@@ -104,6 +104,9 @@ void exportState(const Robot& r, shc_robot_state* s) {
     putQuat(o.tip_rotation, st.current_tip_pose_.rotation_);
     putQuat(o.origin_tip_rotation, st.origin_tip_pose_.rotation_);
     putQuat(o.target_tip_rotation, st.target_tip_pose_.rotation_);
+    o.step_plane_defined = leg.step_plane_pose_ != Pose::Undefined();
+    if (o.step_plane_defined) put3(o.step_plane_position, leg.step_plane_pose_.position_);
+    o.touchdown_detection = st.touchdown_detection_;
     put3(o.model_tip_position, leg.current_tip_pose_.position_);
     put3(o.desired_tip_position, leg.desired_tip_pose_.position_);
     o.ik_result = leg.last_ik_result_;
@@ -174,6 +177,9 @@ void importState(Robot& r, const shc_robot_state* s) {
     leg.tip_force_calculated_ = get3(o.tip_force_calculated);
     leg.virtual_stiffness_ = o.virtual_stiffness;
     leg.poser.negate_auto_pose_ = o.negate_auto_pose != 0;
+    st.touchdown_detection_ = o.touchdown_detection != 0;
+    // (the rotation of the step plane pose is never read: walk_controller.cpp:1085-1110 uses its position and whether it is defined)
+    leg.step_plane_pose_ = o.step_plane_defined ? Pose(get3(o.step_plane_position), leg.current_tip_pose_.rotation_) : Pose::Undefined();
     // target_tip_pose_.rotation_ is a constant of the configuration (no rough-terrain targets): left as constructed
     st.current_tip_pose_.rotation_ = Quat(o.tip_rotation[0], o.tip_rotation[1], o.tip_rotation[2], o.tip_rotation[3]);
     st.origin_tip_pose_.rotation_ = Quat(o.origin_tip_rotation[0], o.origin_tip_rotation[1], o.origin_tip_rotation[2], o.origin_tip_rotation[3]);
@@ -220,8 +226,12 @@ struct Batch {
 void stepOne(Robot& r, const double* cmd, const double* imu, const double* tip_force, const double* manual) {
   // Inputs arrive through callbacks in ros::spinOnce() before the next loop() (main.cpp:130).
   if (imu) r.setImuData(Quat(imu[0], imu[1], imu[2], imu[3]), Vec3(imu[7], imu[8], imu[9]), Vec3(imu[4], imu[5], imu[6]));
-  if (tip_force)
-    for (int l = 0; l < r.leg_count_; ++l) r.legs[l].tip_force_measured_ = Vec3(tip_force[l * 3], tip_force[l * 3 + 1], tip_force[l * 3 + 2]);
+  if (tip_force)  // tipStatesCallback with wrench values (state_controller.cpp:1636-1648)
+    for (int l = 0; l < r.leg_count_; ++l) {
+      r.legs[l].stepper.touchdown_detection_ = true;
+      r.legs[l].tip_force_measured_ = Vec3(tip_force[l * 3], tip_force[l * 3 + 1], tip_force[l * 3 + 2]);
+      r.legs[l].touchdownDetection();
+    }
   if (manual) {  // poser_->setManualPoseInput (state_controller.cpp:1148)
     r.translation_velocity_input_ = Vec3(manual[0], manual[1], manual[2]);
     r.rotation_velocity_input_ = Vec3(manual[3], manual[4], manual[5]);

@@ -411,6 +411,14 @@ double Leg::updateJointPositions(const double* delta, bool simulation) {  // mod
   return min_limit_proximity;
 }
 
+void Leg::touchdownDetection() {  // model.cpp:712
+  if (tip_force_measured_.norm() > robot->params_.touchdown_threshold && step_plane_pose_ == Pose::Undefined()) {
+    step_plane_pose_ = current_tip_pose_;
+  } else if (tip_force_measured_.norm() < robot->params_.liftoff_threshold) {
+    step_plane_pose_ = Pose::Undefined();
+  }
+}
+
 double Leg::applyIK(bool simulation) {  // model.cpp:861
   Pose leg_frame_desired_tip_pose = jointPoseJointFrame(1, desired_tip_pose_);
   Pose leg_frame_current_tip_pose = jointPoseJointFrame(1, current_tip_pose_);

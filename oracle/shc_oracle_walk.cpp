@@ -562,8 +562,22 @@ void LegStepper::updateTipPosition() {  // walk_controller.cpp:1018
       swing_origin_tip_velocity_ = current_tip_velocity_;
       if (rough_terrain_mode) updateDefaultTipPosition();
     }
-    // rough_terrain_mode target shifting (walk_controller.cpp:1065-1107) is out of scope: requires tf2 / TipState.
-    bool ground_contact = false;
+    // Update the target to meet the step surface (walk_controller.cpp:1065-1107).  Externally requested targets (:1068-1078)
+    // need tf2 transforms and are out of scope: external_target_.defined_ is never set.
+    if (rough_terrain_mode) {
+      if (touchdown_detection_) {
+        Pose step_plane_pose = leg_->step_plane_pose_;
+        if (step_plane_pose != Pose::Undefined()) {  // proactive: the step plane is known
+          Vec3 step_plane_position = step_plane_pose.position_ - leg_->current_tip_pose_.position_;
+          Vec3 target_tip_position = current_tip_pose_.position_ + step_plane_position;
+          Vec3 difference = target_tip_position - target_tip_pose_.position_;
+          target_tip_pose_.position_ += getProjection(difference, walk_plane_normal_);
+        } else {  // reactive: reach down by the step depth and rely on contact detection
+          target_tip_pose_.position_ -= params.step_depth * UnitZ();
+        }
+      }
+    }
+    bool ground_contact = (leg_->step_plane_pose_ != Pose::Undefined() && rough_terrain_mode);
     generatePrimarySwingControlNodes();
     generateSecondarySwingControlNodes(!first_half && ground_contact);
     if (force_normal_touchdown && !ground_contact) forceNormalTouchdown();

@@ -63,6 +63,7 @@ class ShcConfig(C.Structure):
         ("virtual_damping_ratio", _d), ("force_gain", _d),
         ("load_stiffness_scaler", _d), ("swing_stiffness_scaler", _d),
         ("joint_packed", (_d * MAX_DOF) * MAX_LEGS), ("joint_unpacked", (_d * MAX_DOF) * MAX_LEGS),
+        ("touchdown_threshold", _d), ("liftoff_threshold", _d),
     ]
 
 
@@ -98,6 +99,7 @@ class ShcLegState(C.Structure):
         ("virtual_stiffness", _d),
         ("negate_auto_pose", _i), ("pad0", _i),
         ("tip_rotation", _d * 4), ("origin_tip_rotation", _d * 4), ("target_tip_rotation", _d * 4),
+        ("step_plane_position", _d * 3), ("step_plane_defined", _i), ("touchdown_detection", _i),
         ("model_tip_position", _d * 3), ("desired_tip_position", _d * 3), ("ik_result", _d),
     ]
 
@@ -254,6 +256,7 @@ def _common_defaults(cfg: ShcConfig) -> None:
     cfg.force_gain = 0.100
     cfg.load_stiffness_scaler = 5.000
     cfg.swing_stiffness_scaler = 0.100
+    cfg.touchdown_threshold, cfg.liftoff_threshold = 0.9, 0.1
 
 
 def hexapod_config(gait: str = "tripod_gait", time_delta: float = 0.02, **overrides) -> ShcConfig:
@@ -393,6 +396,7 @@ def load_reference_yaml(default_yaml: str, gait_yaml: str, auto_pose_yaml: Optio
         sp = p[f"{leg}_stance_position"]
         cfg.stance_x[i], cfg.stance_y[i] = float(sp["x"]), float(sp["y"])
     cfg.body_clearance = float(p["body_clearance"])
+    cfg.touchdown_threshold, cfg.liftoff_threshold = float(p.get("touchdown_threshold", 0.9)), float(p.get("liftoff_threshold", 0.1))
     for key in ("step_frequency", "swing_height", "swing_width", "step_depth", "stance_span_modifier",
                 "virtual_mass", "virtual_stiffness", "virtual_damping_ratio", "force_gain"):
         setattr(cfg, key, adj(p[key]))
