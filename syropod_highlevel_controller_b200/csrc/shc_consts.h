@@ -54,6 +54,8 @@ template <class R> struct RealConsts {
   R force_gain;
   R virtual_stiffness, swing_stiffness_scaler, load_stiffness_scaler;  // updateStiffness (admittance_controller.cpp:96)
   R body_velocity_scaler;  // bodyVelocityInputCallback (state_controller.cpp:1131)
+  R step_depth;            // rough-terrain mode: reactive reach below the default target (walk_controller.cpp:1099)
+  R touchdown_threshold, liftoff_threshold;  // Leg::touchdownDetection (model.cpp:712)
   R tip_target_rot[4];     // identity / target tip rotation w x y z with gravity_aligned_tips (walk_controller.cpp:36-41)
   // auto posers (pose_controller.cpp:1338)
   R ap_pos[kMaxPosers][3], ap_rot[kMaxPosers][3], ap_gravity[kMaxPosers];
@@ -70,6 +72,7 @@ struct IntConsts {
   int mod_stance_start[kMaxLegs];  // = phase offset
   // flags
   int manual_posing, auto_posing, inclination_posing, imu_posing, admittance_control, use_joint_effort, dynamic_stiffness;
+  int rough_terrain;           // rough_terrain_mode: default-tip updates, touchdown detection, target shifting
   int tip_mode;                // TIP_NONE / TIP_ALIGN_POSE (D <= 3) / TIP_ROTATION (D > 3): gravity_aligned_tips
   int clamp_joint_positions, clamp_joint_velocities, velocity_input_mode, force_normal_touchdown;
   // auto posing
@@ -80,6 +83,7 @@ struct IntConsts {
   int nS, nD, nI;              // number of storage / double / int planes
   int offS_imu, offS_auto, offS_leg, strideS_leg;
   int offS_tip;                // robot-level tip-align block (TIP_ALIGN_POSE)
+  int roughS_leg;              // per-leg rough-terrain block, relative to the leg's first joint plane (rough_terrain)
   int tipS_leg;                // per-leg tip-rotation block, relative to the leg's first joint plane (TIP_ROTATION)
   int frontS_leg;              // staged admittance planes in front of each leg's joint planes (0 or 5)
   int smem_per_warp;           // bytes of dynamic shared memory per warp (two staging slots + barriers)

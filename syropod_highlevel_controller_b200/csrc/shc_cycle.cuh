@@ -608,11 +608,12 @@ SHC_HD PoseT<K> leg_auto_pose(const IntConsts& ci, K neg_ratio, int l, int maste
 #ifndef SHC_SLOTS
 #define SHC_SLOTS 1
 #endif
-// MODE: 0 walking only, 1 = FULL, 2 = FULL + the tip-orientation path of gravity_aligned_tips (TIPALIGN: updateTipAlignPose on
-// legs of at most three joints; TIPROT: updateTipRotation and the rotation branch of Leg::applyIK beyond).
+// MODE: 0 walking only, 1 = FULL, 2 = EXT = FULL + the extended paths, each behind its own run-time flag: the tip-orientation
+// path of gravity_aligned_tips (updateTipAlignPose on legs of at most three joints; updateTipRotation and the rotation
+// branch of Leg::applyIK beyond) and rough-terrain mode (default-tip updates, touchdown detection, target shifting).
 template <class P, int D, int MODE> struct Cycle {
   static constexpr bool FULL = MODE >= 1;
-  static constexpr bool TIPALIGN = MODE == 2 && D <= 3, TIPROT = MODE == 2 && D > 3;
+  static constexpr bool EXT = MODE == 2;
   static constexpr int kSlots = SHC_SLOTS;
   using S = typename P::S;
   using T = typename P::T;
@@ -723,6 +724,8 @@ template <class P, int D, int MODE> struct Cycle {
     const int L = ci.L;
     const bool f_auto = FULL && ci.auto_posing, f_incl = FULL && ci.inclination_posing, f_imu = FULL && ci.imu_posing;
     const bool f_adm = FULL && ci.admittance_control, f_effort = FULL && ci.use_joint_effort;
+    const bool f_tipalign = EXT && D <= 3 && ci.tip_mode == TIP_ALIGN_POSE, f_tiprot = EXT && D > 3 && ci.tip_mode == TIP_ROTATION;
+    const bool f_rough = EXT && ci.rough_terrain;
     const int front = FULL ? ci.frontS_leg : 0;
     // tile-major planes [tile][plane][32 lanes]: every field of this robot is at a compile-time offset from these bases
     const size_t tile = (size_t)tile_idx;
@@ -988,7 +991,7 @@ template <class P, int D, int MODE> struct Cycle {
       stPose(sp, ci.offS_auto + AUTO_POSE, auto_pose);
       cur_pose = pose_add(cur_pose, auto_pose);
     }
-    if constexpr (TIPALIGN) {
+    if (f_tipalign) {
       // updateTipAlignPose (pose_controller.cpp:1024, EXPERIMENTAL in the reference): every leg with a swing progress, in leg
       // order, moves the one tip_align_pose_ - a body translation that brings the leg's last joint over its tip along the
       // walk-plane normal during the second half of the swing and back to zero during the first half of the next one.
@@ -1212,11 +1215,37 @@ template <class P, int D, int MODE> struct Cycle {
       // tip-rotation state (gravity_aligned_tips, D > 3) and the chain at the joint angles the cycle starts with
       Q4<K> tr_cur{K(0), K(0), K(0), K(0)}, tr_origin{K(0), K(0), K(0), K(0)};
       Chain<K, D> ch;
-      if constexpr (TIPROT) {
-        const S* __restrict__ tp = sl + ci.tipS_leg * 32;
-        tr_cur = {K(tp[(TR_CUR) * 32]), K(tp[(TR_CUR + 1) * 32]), K(tp[(TR_CUR + 2) * 32]), K(tp[(TR_CUR + 3) * 32])};
-        tr_origin = {K(tp[(TR_ORIGIN) * 32]), K(tp[(TR_ORIGIN + 1) * 32]), K(tp[(TR_ORIGIN + 2) * 32]), K(tp[(TR_ORIGIN + 3) * 32])};
+      bool step_plane_defined = false, touchdown_detection = false;
+      V3<K> step_plane{K(0), K(0), K(0)}, model_tip{K(0), K(0), K(0)};
+      if constexpr (EXT) {
         leg_chain<K, D>(lk, q, ch);
+        if (f_tiprot) {
+          const S* __restrict__ tp = sl + ci.tipS_leg * 32;
+          tr_cur = {K(tp[(TR_CUR) * 32]), K(tp[(TR_CUR + 1) * 32]), K(tp[(TR_CUR + 2) * 32]), K(tp[(TR_CUR + 3) * 32])};
+          tr_origin = {K(tp[(TR_ORIGIN) * 32]), K(tp[(TR_ORIGIN + 1) * 32]), K(tp[(TR_ORIGIN + 2) * 32]), K(tp[(TR_ORIGIN + 3) * 32])};
+        }
+        if (f_rough) {
+          // Leg::current_tip_pose_.position_ (base_link frame) as the previous cycle's applyFK left it
+          model_tip = t1_rotate(lk, ch.tip) + V3<K>{lk.t1p[0], lk.t1p[1], lk.t1p[2]};
+          step_plane_defined = (bits >> LB_STEP_PLANE) & 1;
+          touchdown_detection = (bits >> LB_TOUCHDOWN) & 1;
+          S* __restrict__ rp = sl + ci.roughS_leg * 32;
+          if (step_plane_defined) step_plane = ld3K(rp, RT_STEP_PLANE);
+          if (io.tip_force) {
+            // tipStatesCallback with wrench values (state_controller.cpp:1636-1648), delivered before this loop(): touchdown
+            // detection is on from now on, and Leg::touchdownDetection (model.cpp:712) defines / forgets the step plane
+            touchdown_detection = true;
+            const float* f = io.tip_force + ((size_t)r * L + l) * 3;
+            const K fn = norm(V3<K>{K(f[0]), K(f[1]), K(f[2])});
+            if (fn > ck.touchdown_threshold && !step_plane_defined) {
+              step_plane = model_tip;
+              step_plane_defined = true;
+              st3(rp, RT_STEP_PLANE, step_plane);
+            } else if (fn < ck.liftoff_threshold) {
+              step_plane_defined = false;
+            }
+          }
+        }
       }
       // the one HBM read the swing branch may need (tip velocity at the first swing iteration), issued early
       const bool swing_begins = (bits & 0xffff) == ci.swing_start;
@@ -1303,6 +1332,15 @@ template <class P, int D, int MODE> struct Cycle {
           phase = 0;
         }
 
+        // LegStepper::updateDefaultTipPosition (:984) without an external default: the identity tip under the model's default
+        // body pose (= this cycle's walk-plane pose), moved along the leg's walk-plane normal to the height the stance began at
+        auto update_default_tip = [&](V3<K> stance_origin, V3<K> normal) {
+          V3<K> idt{lk.identity_x, lk.identity_y + lk.span_dy, K(0)};
+          idt = pose_transform(ldPose(sp, RS_WPP), idt);
+          def = cvt<T>(idt + projection(stance_origin - idt, normal));
+          st3(sl, LS::DEF, def);
+          def_changed = true;
+        };
         // ---- LegStepper::updateTipPosition (walk_controller.cpp:1018) ----
         const bool standard = (step_state == STEP_SWING || completed);
         const T stance_dt = standard ? ct.stance_dt_std : lt.stance_dt_mod;
@@ -1345,6 +1383,25 @@ template <class P, int D, int MODE> struct Cycle {
               swo_p = ld3T(ss, LS::SWO_P);
               swo_v = ld3T(ss, LS::SWO_V);
             }
+            bool ground_contact = false;
+            if constexpr (EXT) {
+              if (f_rough) {
+                // the leg's walk_plane_normal_ is the walker's as of this cycle's start (updateStride above)
+                const V3<K> leg_wpn = ld3K(sp, RS_WPN);
+                if (iteration == 1) update_default_tip(ld3K(sl, LS::STO_P), leg_wpn);  // (:1058-1061)
+                // Target moved to meet the step surface (:1065-1107; externally requested targets need tf2: not built)
+                if (touchdown_detection) {
+                  if (step_plane_defined) {  // proactive: the step plane is known
+                    const V3<K> target_tip_position = V3<K>{K(tipx), K(tipy), K(tipz)} + (step_plane - model_tip);
+                    tgt = tgt + cvt<T>(projection(target_tip_position - cvt<K>(tgt), leg_wpn));
+                  } else {  // reactive: reach down by the step depth and rely on contact detection
+                    tgt.z -= ct.step_depth;
+                  }
+                  st3(sl, LS::TGT, tgt);
+                }
+                ground_contact = step_plane_defined;
+              }
+            }
             // Control nodes relative to the swing origin (the origin cancels in the differences).
             V3<T> clr{T(0), T(0), ct.swing_height};
             if (!plane_flat) clr = normalized(ld3T(sp, RS_WPN)) * ct.swing_height;
@@ -1358,7 +1415,7 @@ template <class P, int D, int MODE> struct Cycle {
             V3<T> sep2 = ftv * (T(0.25) * (ct.dt / ct.swing_dt));
             V3<T> m2 = tr - sep2 * T(2);
             V3<T> m1;
-            if (ci.force_normal_touchdown) {  // forceNormalTouchdown (:1314): n4 = m0 = bo, n3 = bo - h, m1 = bo + h
+            if (ci.force_normal_touchdown && !ground_contact) {  // forceNormalTouchdown (:1314): n4 = m0 = bo, n3 = bo - h, m1 = bo + h
               V3<T> bo = tr - sep2 * T(4);
               bo.z = max_(T(0), tr.z);
               bo = bo + clr;
@@ -1371,6 +1428,9 @@ template <class P, int D, int MODE> struct Cycle {
             }
             X = first_half ? sep1 : sep2;
             Y = first_half ? n3 - n2 : m2 - m1;
+            // ground contact in the second half (generateSecondarySwingControlNodes(true), :1282-1289): the nodes restart at
+            // the tip, one stance node separation apart - the tip only keeps its touchdown velocity
+            if (!first_half && ground_contact) { Y = sep2; Z = sep2; }
             const T u = ct.swing_dt * T(first_half ? iteration : iteration - half);
             bs = first_half ? T(1) - u : u;
             bt = first_half ? u : T(1) - u;
@@ -1379,7 +1439,12 @@ template <class P, int D, int MODE> struct Cycle {
             int mod_start = standard ? ci.stance_start : ci.phase_offset[l];
             int iteration = phase - mod_start;  // mod(phase + (period - start), period) + 1, both in [0, period)
             iteration += iteration < 0 ? ci.period + 1 : 1;
-            if (iteration == 1) st3(sl, LS::STO_P, V3<T>{T(tipx), T(tipy), T(tipz)});
+            if (iteration == 1) {
+              st3(sl, LS::STO_P, V3<T>{T(tipx), T(tipy), T(tipz)});
+              if constexpr (EXT) {
+                if (f_rough) update_default_tip(V3<K>{K(tipx), K(tipy), K(tipz)}, ld3K(sp, RS_WPN));  // (:1160-1163)
+              }
+            }
             T scaler = standard ? T(1) : lt.stride_scaler_mod;
             X = -stride * scaler * T(0.25);
             Y = X;
@@ -1402,7 +1467,7 @@ template <class P, int D, int MODE> struct Cycle {
           plane_saved = false;  // the leg sits this cycle out: its saved plane is now older than the walker's
         }
 
-        if constexpr (TIPROT) {
+        if (f_tiprot) {
           // ---- LegStepper::updateTipRotation (:1193), on the progress values the cycle found ----
           const K swing_progress = swing_num < 0 ? K(-1) : K(swing_num) / K(ci.swing_period);
           if (stance_num >= 0 || swing_progress >= K(0.5)) {
@@ -1458,7 +1523,8 @@ template <class P, int D, int MODE> struct Cycle {
       }
       SHC_STAMP(6 + 3 * l);
       bits = (phase & 0xffff) | (step_state << 16) | ((at_correct ? 1 : 0) << 18) | ((completed ? 1 : 0) << 19) |
-             ((negate ? 1 : 0) << 20) | ((plane_saved ? 1 : 0) << LB_PLANE_SAVED);
+             ((negate ? 1 : 0) << 20) | ((plane_saved ? 1 : 0) << LB_PLANE_SAVED) | ((step_plane_defined ? 1 : 0) << LB_STEP_PLANE) |
+             ((touchdown_detection ? 1 : 0) << LB_TOUCHDOWN);
       prog = (swing_num & 0xffff) | ((stance_num & 0xffff) << 16);
       il[(LI_BITS) * 32] = bits;
       il[(LI_PROG) * 32] = prog;
@@ -1472,7 +1538,7 @@ template <class P, int D, int MODE> struct Cycle {
       V3<K> desired = pose_inverse_transform(leg_pose, V3<K>{K(tipx), K(tipy), K(tipz)});
 
       // ---- joint state + chain at the previous joint angles ----
-      if constexpr (!TIPROT) leg_chain<K, D>(lk, q, ch);
+      if constexpr (!EXT) leg_chain<K, D>(lk, q, ch);
 
       // ---- AdmittanceController::updateAdmittance (admittance_controller.cpp:22) ----
       if (f_adm) {
@@ -1503,7 +1569,7 @@ template <class P, int D, int MODE> struct Cycle {
 
       // ---- Leg::applyIK (model.cpp:861): one DLS step ----
       V3<K> des_leg;
-      if constexpr (TIPROT) {
+      if (f_tiprot) {
         // the poser's tip rotation (updateStance, pose_controller.cpp:129) is the desired one: position step, rotation step,
         // and the position-only retry when the rotation-constrained attempt misses the tolerance
         const Q4<K> desired_rot = qmul(qinverse(leg_pose.q), tr_cur);

@@ -28,7 +28,11 @@ inline bool validate_config(const shc_config& c, std::string& err, bool& unsuppo
   if (c.stance_phase <= 0 || c.swing_phase <= 0 || c.phase_offset <= 0) return bad("gait phases must be > 0");
   if (!(c.step_frequency > 0.0)) return bad("step_frequency must be > 0");
   if (c.auto_poser_count < 0 || c.auto_poser_count > SHC_MAX_AUTO_POSERS) return bad("auto_poser_count out of range");
-  if (c.rough_terrain_mode) { unsupported = true; return bad("rough_terrain_mode is outside the hot-path scope (needs tf2 / TipState touchdown inputs)"); }
+  if (c.rough_terrain_mode && c.stance_span_modifier != 0.0) {
+    unsupported = true;  // calculateStanceSpanChange would interpolate the layered workspace every default-tip update
+    return bad("rough_terrain_mode with a stance_span_modifier is not built (stance span change over the layered workspace)");
+  }
+  if (c.rough_terrain_mode && !(c.liftoff_threshold <= c.touchdown_threshold)) return bad("liftoff_threshold must not exceed touchdown_threshold");
   if (c.joint_count != 3 && c.joint_count != 4 && c.joint_count != 5) { unsupported = true; return bad("kernels are instantiated for 3, 4 and 5 joints per leg"); }
   return true;
 }
@@ -89,6 +93,9 @@ template <class R> void fill_static_consts(const shc_config& c, RealConsts<R>& k
   k.swing_stiffness_scaler = R(c.swing_stiffness_scaler);
   k.load_stiffness_scaler = R(c.load_stiffness_scaler);
   k.body_velocity_scaler = R(c.body_velocity_scaler);
+  k.step_depth = R(c.step_depth);
+  k.touchdown_threshold = R(c.touchdown_threshold);
+  k.liftoff_threshold = R(c.liftoff_threshold);
   if (c.gravity_aligned_tips && c.joint_count > 3) {
     // WalkController::init (walk_controller.cpp:36-41): the identity tip rotation points the tip's x axis down; every leg's
     // target_tip_pose_.rotation_ keeps it (nothing redefines it without rough-terrain targets)
@@ -206,11 +213,44 @@ template <int D> void compute_startup(const shc_config& c, const RealConsts<doub
     }
   }
 
-  // ---- Leg::generateWorkspace (model.cpp:309), simple workspace: one plane at height 0, 8 bearings ----
+  // ---- Leg::generateWorkspace (model.cpp:309): the simple workspace (one plane at height 0, 8 bearings), or in
+  // rough-terrain mode the layered workspace, of which the start-up only reads the workplane at the height of the default
+  // tips, 0 (Leg::getWorkplane, model.cpp:514: interpolation between the two planes that bound the height) ----
   for (int l = 0; l < L; ++l) {
-    double h, radii[SHC_N_BEARINGS];
-    workspace_sweep_leg<D>(ck, sp, l, su.default_joint[l], false, 1, 0, 1, &h, radii);
-    for (int b = 0; b < SHC_N_BEARINGS; ++b) su.workspace[l][b] = radii[b];
+    if (!c.rough_terrain_mode) {
+      double h, radii[SHC_N_BEARINGS];
+      workspace_sweep_leg<D>(ck, sp, l, su.default_joint[l], false, 1, 0, 1, &h, radii);
+      for (int b = 0; b < SHC_N_BEARINGS; ++b) su.workspace[l][b] = radii[b];
+      continue;
+    }
+    constexpr int kMaxPlanes = 24;
+    double heights[kMaxPlanes], radii[kMaxPlanes * SHC_N_BEARINGS];
+    const int np = std::min(workspace_sweep_leg<D>(ck, sp, l, su.default_joint[l], true, kMaxPlanes, 0, 1, heights, radii), kMaxPlanes);
+    // the reference keeps the planes in a std::map keyed by height: a later plane of the same height replaces an earlier one
+    int order[kMaxPlanes], no = 0;
+    for (int p = 0; p < np; ++p) {
+      int dup = -1;
+      for (int k = 0; k < no; ++k)
+        if (heights[order[k]] == heights[p]) dup = k;
+      if (dup >= 0) order[dup] = p;
+      else order[no++] = p;
+    }
+    std::sort(order, order + no, [&](int a, int b) { return heights[a] < heights[b]; });
+    for (int b = 0; b < SHC_N_BEARINGS; ++b) su.workspace[l][b] = 0.0;
+    const double height = 0.0;
+    if (no == 0 || !(height >= heights[order[0]] && height <= heights[order[no - 1]])) continue;  // outside: empty workplane
+    if (no == 1) {
+      for (int b = 0; b < SHC_N_BEARINGS; ++b) su.workspace[l][b] = radii[order[0] * SHC_N_BEARINGS + b];
+      continue;
+    }
+    int up = 0;
+    while (up < no && !(heights[order[up]] > height)) ++up;  // std::map::upper_bound
+    if (up == 0 || up == no) continue;  // (the reference dereferences end() here; cannot happen for height 0 inside the range)
+    auto prec3 = [](double v) { return round_to_int(v * 1000.0) / 1000.0; };  // setPrecision(v, 3) (standard_includes.h:142)
+    const double hu = prec3(heights[order[up]]), hl = prec3(heights[order[up - 1]]);
+    const double i = (height - hl) / (hu - hl);
+    for (int b = 0; b < SHC_N_BEARINGS; ++b)
+      su.workspace[l][b] = radii[order[up - 1] * SHC_N_BEARINGS + b] * (1.0 - i) + radii[order[up] * SHC_N_BEARINGS + b] * i;
   }
 
   // ---- WalkController::generateWalkspace (walk_controller.cpp:57) ----

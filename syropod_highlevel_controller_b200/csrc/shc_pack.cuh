@@ -34,6 +34,9 @@ inline void layout(const shc_config& cfg, int n, IntConsts& ci) {
   ci.strideS_leg = lo.COUNT + (adm ? ADM_COUNT : 0);
   ci.tipS_leg = ci.strideS_leg - ci.frontS_leg;  // behind the appended admittance planes
   if (ci.tip_mode == TIP_ROTATION) ci.strideS_leg += TR_COUNT;
+  ci.rough_terrain = cfg.rough_terrain_mode;
+  ci.roughS_leg = ci.strideS_leg - ci.frontS_leg;
+  if (ci.rough_terrain) ci.strideS_leg += RT_COUNT;
   ci.nS = s + ci.strideS_leg * cfg.leg_count;
   ci.offD_leg = RD_COUNT;
   ci.strideD_leg = LD_COUNT;
@@ -172,9 +175,13 @@ template <class E> void pack(const E* e, const shc_robot_state* in, size_t n, Ho
           S(sb + ci.tipS_leg + TR_CUR + k, r) = g.tip_rotation[k];
           S(sb + ci.tipS_leg + TR_ORIGIN + k, r) = g.origin_tip_rotation[k];
         }
+      if (ci.rough_terrain)
+        for (int k = 0; k < 3; ++k) S(sb + ci.roughS_leg + RT_STEP_PLANE + k, r) = g.step_plane_position[k];
       const int ib = ci.offI_leg + l * ci.strideI_leg;
       I(ib + LI_BITS, r) = (g.phase & 0xffff) | ((g.step_state & 3) << 16) | ((g.at_correct_phase ? 1 : 0) << 18) |
-                           ((g.completed_first_step ? 1 : 0) << 19) | ((g.negate_auto_pose ? 1 : 0) << 20);
+                           ((g.completed_first_step ? 1 : 0) << 19) | ((g.negate_auto_pose ? 1 : 0) << 20) |
+                           ((ci.rough_terrain && g.step_plane_defined ? 1 : 0) << LB_STEP_PLANE) |
+                           ((ci.rough_terrain && g.touchdown_detection ? 1 : 0) << LB_TOUCHDOWN);
       int sn = prog_num(g.swing_progress, ci.swing_period), tn = prog_num(g.stance_progress, ci.stance_period);
       I(ib + LI_PROG, r) = (sn & 0xffff) | ((tn & 0xffff) << 16);
     }
@@ -296,6 +303,12 @@ template <int D, class E> void unpack(const E* e, const HostPlanes& h, shc_robot
       g.at_correct_phase = (b >> 18) & 1;
       g.completed_first_step = (b >> 19) & 1;
       g.negate_auto_pose = (b >> 20) & 1;
+      if (ci.rough_terrain) {
+        g.step_plane_defined = (b >> LB_STEP_PLANE) & 1;
+        g.touchdown_detection = (b >> LB_TOUCHDOWN) & 1;
+        if (g.step_plane_defined)
+          for (int k = 0; k < 3; ++k) g.step_plane_position[k] = S(sb + ci.roughS_leg + RT_STEP_PLANE + k, r);
+      }
       int sn = (int)(short)(pg & 0xffff), tn = (int)(short)((pg >> 16) & 0xffff);
       g.swing_progress = sn < 0 ? -1.0 : (double)sn / (double)ci.swing_period;
       g.stance_progress = tn < 0 ? -1.0 : (double)tn / (double)ci.stance_period;
@@ -330,11 +343,11 @@ template <class F> inline int dispatch_D_raw(int D, F&& f) {
 
 inline bool engine_full(const shc_config& cfg) {
   return cfg.auto_posing || cfg.admittance_control || cfg.imu_posing || cfg.inclination_posing || cfg.use_joint_effort ||
-         cfg.gravity_aligned_tips;
+         cfg.gravity_aligned_tips || cfg.rough_terrain_mode;
 }
-// Kernel instantiation of an engine: 0 walking only, 1 every optional stage, 2 those plus the tip-orientation path
-// (gravity_aligned_tips: tip-align posing on legs of at most three joints, tip-rotation IK beyond)
-inline int engine_mode(const shc_config& cfg) { return cfg.gravity_aligned_tips ? 2 : engine_full(cfg) ? 1 : 0; }
+// Kernel instantiation of an engine: 0 walking only, 1 every optional stage, 2 those plus the extended paths: tip orientation
+// (gravity_aligned_tips: tip-align posing on legs of at most three joints, tip-rotation IK beyond) and rough-terrain mode
+inline int engine_mode(const shc_config& cfg) { return (cfg.gravity_aligned_tips || cfg.rough_terrain_mode) ? 2 : engine_full(cfg) ? 1 : 0; }
 
 // Everything shc_create refuses: invalid configurations and reference features outside the built scope.
 inline bool check_supported(const shc_config& cfg, std::string& err, bool& unsupported) {

@@ -15,6 +15,9 @@ STATE_FIELDS_LEG = ("tip_position", "tip_velocity", "swing_origin_position", "st
 # when the record under test carries a target rotation
 ROTATION_FIELDS_LEG = ("tip_rotation", "origin_tip_rotation", "target_tip_rotation")
 INT_FIELDS_LEG = ("phase", "step_state", "at_correct_phase", "completed_first_step", "negate_auto_pose")
+# rough-terrain state: compared when the record under test is in touchdown-detection mode
+ROUGH_FIELDS_LEG = ("step_plane_position",)
+ROUGH_INT_FIELDS_LEG = ("step_plane_defined", "touchdown_detection")
 
 
 def state_diff(se, so, L, D):
@@ -37,12 +40,13 @@ def state_diff(se, so, L, D):
             upd("joint_position", list(la.joint_position)[:D], list(lb.joint_position)[:D])
             upd("joint_velocity", list(la.joint_velocity)[:D], list(lb.joint_velocity)[:D])
             with_rot = any(v != 0.0 for v in la.target_tip_rotation)
-            for f in STATE_FIELDS_LEG + (ROTATION_FIELDS_LEG if with_rot else ()):
+            rough = bool(la.touchdown_detection)
+            for f in STATE_FIELDS_LEG + (ROTATION_FIELDS_LEG if with_rot else ()) + (ROUGH_FIELDS_LEG if rough else ()):
                 va, vb = getattr(la, f), getattr(lb, f)
                 upd(f, va if isinstance(va, float) else list(va), vb if isinstance(vb, float) else list(vb))
             upd("swing_progress", la.swing_progress, lb.swing_progress)
             upd("stance_progress", la.stance_progress, lb.stance_progress)
-            for f in INT_FIELDS_LEG:
+            for f in INT_FIELDS_LEG + (ROUGH_INT_FIELDS_LEG if rough else ()):
                 upd("int:" + f, getattr(la, f), getattr(lb, f))
     return out
 

@@ -421,6 +421,65 @@ def tip_orientation(backend, oracle, n=48, cycles=400):
         eng.close(); ob.close()
 
 
+def rough_terrain(backend, oracle, n=48, cycles=420):
+    """SURVEY.md 8(f) rank 4: rough_terrain_mode.  Measured tip forces drive Leg::touchdownDetection (model.cpp:712); the
+    stepper re-seats its default tip at every swing and stance start (walk_controller.cpp:984-1014, 1058, 1160), moves the swing
+    target onto the detected step plane or reaches down by step_depth (:1065-1107), and freezes the second half of the swing
+    on ground contact (:1110-1112, 1282-1289); the walk plane, its pose and the swing clearance follow the default tips
+    (non-flat plane paths of updateWalkPlane / updateWalkPlanePose).  One cycle from identical state to 1e-11 on every field,
+    then a free-running rollout.  The start-up constants are the oracle's (layered workspace)."""
+    for cfg, L, D, full in ((hexapod_config("tripod_gait", rough_terrain_mode=1, step_depth=0.01), 6, 3, False),
+                            (hexapod_config("wave_gait", rough_terrain_mode=1, step_depth=0.02, force_normal_touchdown=1), 6, 3, False),
+                            (octopod_config("ripple_gait", rough_terrain_mode=1, step_depth=0.01), 8, 5, True)):
+        ob = oracle.OracleBatch(cfg, n)
+        eng = backend.engine(cfg, n, startup=ob.startup())
+        cs = CommandStream(n, min_len=40, max_len=160)
+        ims = ImuStream(n) if full else None
+        rng = np.random.default_rng(17)
+        contacts = planes = 0
+        force = np.zeros((n, L, 3), dtype=np.float32)
+
+        def contact_forces(st, c):
+            # a leg in stance, or late in its swing on a (varying) early touchdown, presses with ~5 N; a lifted tip reads ~0
+            for r in range(n):
+                for l in range(L):
+                    g = st[r].legs[l]
+                    early = g.swing_progress > 0.55 + 0.4 * ((r * 7 + l * 3 + c // 50) % 10) / 10.0
+                    force[r, l] = (rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5), rng.uniform(2.0, 8.0)) if (g.step_state != 0 or early) else \
+                                  (0.0, 0.0, rng.uniform(0.0, 0.05))
+
+        for c in range(cycles):
+            cmd = cs.next()
+            imu = ims.next(cfg.time_delta) if ims else None
+            st = ob.get_state()
+            contact_forces(st, c)
+            sample = c % 3 == 2
+            if sample:
+                eng.set_state(st)
+                j = eng.step(cmd, imu, force)
+            ob.step(cmd.astype(np.float64), None if imu is None else imu.astype(np.float64), force.astype(np.float64), threads=4)
+            if sample:
+                so = ob.get_state()
+                assert np.abs(j - ob.joints()).max() <= 1.3e-7, c  # float32 output rounding of angles beyond 2 rad (half an ulp = 1.2e-7)
+                assert_state_close(eng.get_state(), so, L, D, 1e-11, vel_tol=1e-9)
+                contacts += sum(1 for s in so for l in range(L) if s.legs[l].step_plane_defined and s.legs[l].step_state == 0)
+                planes += sum(1 for s in so if abs(s.walk_plane_normal[2] - 1.0) > 1e-9)
+        assert contacts > 0 and planes > 0, (contacts, planes)  # swings really ended on contact, the walk plane really tilted
+        print(f"[rough-terrain] {L}x{D}: swinging leg-cycles in ground contact {contacts}, robot-cycles with a tilted walk plane {planes}")
+        eng.set_state(ob.get_state())
+        errs = JointErrors()
+        for c in range(150):
+            cmd = cs.next()
+            imu = ims.next(cfg.time_delta) if ims else None
+            contact_forces(ob.get_state(), cycles + c)
+            j = eng.step(cmd, imu, force)
+            ob.step(cmd.astype(np.float64), None if imu is None else imu.astype(np.float64), force.astype(np.float64), threads=4)
+            errs.add(np.abs(j - ob.joints()))
+        errs.check(max_fraction=5e-3, label=f"rough terrain {L}x{D} free-running")
+        assert_state_close(eng.get_state(), ob.get_state(), L, D, 1e-7, skip=JOINT_FIELDS)
+        eng.close(); ob.close()
+
+
 def sequences(backend, oracle, n=32):
     """SURVEY.md 8(f) rank 2: PoseController::stepToNewStance (pose_controller.cpp:520; LegPoser::stepToPosition :1571 +
     Leg::applyIK) and packLegs / unpackLegs (:597 / :661; LegPoser::transitionConfiguration :1476), every loop() of each

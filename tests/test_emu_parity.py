@@ -72,6 +72,10 @@ def test_emu_tip_orientation(emu, oracle):
     P.tip_orientation(emu, oracle, n=16, cycles=300)
 
 
+def test_emu_rough_terrain(emu, oracle):
+    P.rough_terrain(emu, oracle, n=12, cycles=330)
+
+
 def test_emu_sequences(emu, oracle):
     P.sequences(emu, oracle, n=16)
 

@@ -75,6 +75,10 @@ def test_tip_orientation(gpu, oracle):
     P.tip_orientation(gpu, oracle, n=48, cycles=400)
 
 
+def test_rough_terrain(gpu, oracle):
+    P.rough_terrain(gpu, oracle, n=48, cycles=420)
+
+
 def test_sequences(gpu, oracle):
     P.sequences(gpu, oracle, n=96)
 

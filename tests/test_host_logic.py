@@ -49,9 +49,8 @@ def test_no_cpu_fallback(shc_lib):
 def test_unsupported_configs_are_rejected(shc_lib):
     from syropod_highlevel_controller_b200.engine import ShcError, compute_startup
 
-    for key in ("rough_terrain_mode",):
-        with pytest.raises(ShcError):
-            compute_startup(hexapod_config(**{key: 1}))
+    with pytest.raises(ShcError):  # stance span change over the layered workspace is not built
+        compute_startup(hexapod_config(rough_terrain_mode=1, stance_span_modifier=0.3))
     bad = hexapod_config()
     bad.leg_count = 9
     with pytest.raises(ShcError):
@@ -88,6 +87,26 @@ def test_engine_startup_matches_oracle(shc_lib, oracle, make, gait, dt):
     assert np.abs(np.array([list(r) for r in su.workspace]) - np.array([list(r) for r in so.workspace])).max() < 1e-7
     for f in ("walkspace", "max_linear_speed", "max_angular_speed", "max_linear_acceleration", "max_angular_acceleration"):
         assert np.abs(np.array(list(getattr(su, f))) - np.array(list(getattr(so, f)))).max() < 1e-7, f
+
+
+def test_engine_startup_rough_terrain_matches_oracle(shc_lib, oracle):
+    """rough_terrain_mode: the start-up reads the layered workspace (Leg::generateWorkspace in full, model.cpp:309-510)
+    through Leg::getWorkplane at the height of the default tips (model.cpp:514); walkspace and limit tables vs the oracle.
+    (The oracle's start-up record has no simple workspace in this mode: shc_startup.workspace is the engine's interpolated
+    workplane, checked against the layered workspace of the oracle directly.)"""
+    from syropod_highlevel_controller_b200.engine import compute_startup
+
+    for cfg in (hexapod_config("tripod_gait", rough_terrain_mode=1), octopod_config("tripod_gait", rough_terrain_mode=1)):
+        su = compute_startup(cfg)
+        so = oracle.OracleBatch(cfg, 1).startup()
+        for f in ("walkspace", "max_linear_speed", "max_angular_speed", "max_linear_acceleration", "max_angular_acceleration"):
+            assert np.abs(np.array(list(getattr(su, f))) - np.array(list(getattr(so, f)))).max() < 1e-6, f
+        assert max(su.walkspace) > 0.01
+        for leg in (0, cfg.leg_count - 1):
+            h, r = oracle.workspace(cfg, leg, True, 24)
+            k = int(np.argmin(np.abs(h)))  # the plane the search put at height ~0
+            assert abs(h[k]) < 1e-9
+            assert np.abs(np.array(list(su.workspace[leg])) - r[k]).max() < 1e-6
 
 
 def test_shared_kinematics_match_oracle(shc_lib, oracle):
