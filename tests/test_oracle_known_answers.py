@@ -132,6 +132,60 @@ def test_solve_ik_known_and_numpy(oracle):
             assert np.allclose(oracle.solve_ik(cfg, leg, q, qd, delta), _numpy_dls(cfg, leg, q, qd, delta), atol=1e-12)
 
 
+def _closed_form_ik_3dof(cfg, leg, tip_robot):
+    """Closed-form IK of the shipped 3-DOF leg (yaw - twist alpha - pitch - pitch; SURVEY.md §4 "Cross-check"), derived
+    independently of the DLS iteration.  In the leg frame (T1 removed) the tip is
+        p = Rz(q1) [ (r1 + u, v cos(alpha), v sin(alpha)) ],  (u, v) = the planar 2R point of femur and tibia,
+    so v = p_z / sin(alpha), (r1 + u)^2 = p_x^2 + p_y^2 - (v cos(alpha))^2, and q2, q3 follow from the planar 2R problem
+    (knee branch: tibia angle negative, as its joint limits demand)."""
+    th0, r0 = cfg.link_theta[leg][0], cfg.link_r[leg][0]
+    x, y, z = tip_robot[0] - r0 * math.cos(th0), tip_robot[1] - r0 * math.sin(th0), tip_robot[2] - cfg.link_d[leg][0]
+    px, py, pz = math.cos(th0) * x + math.sin(th0) * y, -math.sin(th0) * x + math.cos(th0) * y, z
+    r1, al = cfg.link_r[leg][1], cfg.link_alpha[leg][1]
+    r2, r3, off3 = cfg.link_r[leg][2], cfg.link_r[leg][3], cfg.link_theta[leg][3]
+    assert cfg.link_theta[leg][1] == 0 and cfg.link_theta[leg][2] == 0 and cfg.link_alpha[leg][2] == 0 and cfg.link_alpha[leg][3] == 0
+    v = pz / math.sin(al)
+    w = v * math.cos(al)
+    u = math.sqrt(px * px + py * py - w * w) - r1
+    q1 = math.atan2(py, px) - math.atan2(w, r1 + u)
+    c3 = (u * u + v * v - r2 * r2 - r3 * r3) / (2 * r2 * r3)
+    a3 = -math.acos(max(-1.0, min(1.0, c3)))
+    q2 = math.atan2(v, u) - math.atan2(r3 * math.sin(a3), r2 + r3 * math.cos(a3))
+    return np.array([q1, q2, a3 - off3])
+
+
+def test_dls_fixed_point_is_the_closed_form_ik(oracle):
+    """SURVEY.md §4: the 3-DOF leg has a closed-form IK; the fixed point of the reference's DLS iteration (Leg::applyIK
+    repeated on one target) must be that solution — up to the amplitude of its own stand-still limit cycle (DESIGN.md
+    "Reference dynamics": ~1e-3 rad, i.e. ~0.2 mm at the tip)."""
+    cfg = hexapod_config()
+    L_ = oracle.lib()
+    dp = C.POINTER(C.c_double)
+    L_.shc_oracle_apply_ik.restype = C.c_double
+    L_.shc_oracle_apply_ik.argtypes = [C.POINTER(type(cfg)), C.c_int, dp, dp, dp, C.c_int, dp]
+    rng = np.random.default_rng(9)
+    worst_q = worst_tip = 0.0
+    for leg in range(cfg.leg_count):
+        for _ in range(6):
+            q_true = np.array([rng.uniform(-0.45, 0.45), rng.uniform(-0.2, 1.1), rng.uniform(-2.0, -0.5)])
+            target = oracle.fk(cfg, leg, q_true)
+            # the closed form inverts the forward kinematics exactly ...
+            assert np.abs(_closed_form_ik_3dof(cfg, leg, target) - q_true).max() < 1e-10
+            # ... and the DLS iteration converges onto it from a perturbed start
+            q = q_true + rng.uniform(-0.08, 0.08, 3)
+            q[2] = min(q[2], -0.15)
+            qd, tip = np.zeros(3), np.zeros(3)
+            for _ in range(400):
+                L_.shc_oracle_apply_ik(C.byref(cfg), leg, q.ctypes.data_as(dp), qd.ctypes.data_as(dp),
+                                       np.ascontiguousarray(target).ctypes.data_as(dp), 0, tip.ctypes.data_as(dp))
+            worst_q, worst_tip = max(worst_q, float(np.abs(q - q_true).max())), max(worst_tip, float(np.abs(tip - target).max()))
+    # The iteration does not stop exactly on the solution: with damping, (I - J^+ J) is not zero for a square J, so the
+    # normalised cost gradient (a push of fixed size, model.cpp:788-790) keeps a small standing offset and the stand-still
+    # limit cycle on top of it.  Both stay far inside IK_TOLERANCE (5 mm).
+    print(f"[closed-form IK] worst joint deviation {worst_q:.2e} rad, worst tip deviation {worst_tip:.2e} m")
+    assert worst_q < 1.5e-2 and worst_tip < 5e-4
+
+
 def test_fk_matches_numpy_chain(oracle):
     rng = np.random.default_rng(2)
     for cfg in (hexapod_config(), octopod_config()):
