@@ -159,9 +159,18 @@ int shc_pack_messages(shc_engine* e, size_t first, size_t count, const float* me
  *                             [L][D]) in max(1, roundToInt(time / time_delta)) loops; step returns the progress 1..100.
  *   shc_pack_legs / shc_unpack_legs  one loop() of PoseController::packLegs (:597) / unpackLegs (:661) towards
  *                             shc_config.joint_packed / joint_unpacked; return the progress (100 = complete).
- * PoseController::executeSequence (:145, the multi-step start-up / shut-down sequence generator) is not built. */
+ *   shc_execute_sequence      PoseController::executeSequence (:145-461): the start-up (shut_down = 0) / shut-down sequence —
+ *                             alternating horizontal (leg groups step in turn, or all at once while the body bears no
+ *                             load) and vertical (body rises / sinks) transitions towards the transition poses the first
+ *                             start-up records, with its safety factor on the joint-limit proximity; every robot follows
+ *                             its own course on the device.  progress_out_dev int [N]: -1 (SHC_SEQ_GENERATING) while a
+ *                             robot's first start-up generates its sequence, 0..100, -2 (SHC_SEQ_FAILED) once it needed
+ *                             more than 20 transition steps (where the reference shuts down).  *min_progress_out = the
+ *                             smallest value over the batch (blocking on `stream`); the return value is SHC_OK or an error. */
 int shc_step_to_new_stance(shc_engine* e, float* joints_out_dev, int* progress_out_dev, void* stream);
 int shc_sequence_reset(shc_engine* e);
+enum { SHC_SEQ_GENERATING = -1, SHC_SEQ_FAILED = -2 };
+int shc_execute_sequence(shc_engine* e, int shut_down, float* joints_out_dev, int* progress_out_dev, int* min_progress_out, void* stream);
 int shc_transition_begin(shc_engine* e, const double* desired_configuration, double transition_time);
 int shc_transition_step(shc_engine* e, float* joints_out_dev, void* stream);
 int shc_pack_legs(shc_engine* e, double time_to_pack, float* joints_out_dev, void* stream);
@@ -169,7 +178,7 @@ int shc_unpack_legs(shc_engine* e, double time_to_unpack, float* joints_out_dev,
 /* Host-buffer form of one loop() of a sequence (the C++ facade uses it): joints_out [N][L][D] / progress_out [N] are HOST
  * arrays, either may be NULL; SHC_SEQ_DIRECT_STARTUP begins the direct start-up on its first call (default joint positions).
  * Returns the smallest progress over the batch or a negative SHC_E_* code. */
-enum { SHC_SEQ_NEW_STANCE = 0, SHC_SEQ_PACK = 1, SHC_SEQ_UNPACK = 2, SHC_SEQ_DIRECT_STARTUP = 3 };
+enum { SHC_SEQ_NEW_STANCE = 0, SHC_SEQ_PACK = 1, SHC_SEQ_UNPACK = 2, SHC_SEQ_DIRECT_STARTUP = 3, SHC_SEQ_START_UP = 4, SHC_SEQ_SHUT_DOWN = 5 };
 int shc_sequence_step_host(shc_engine* e, int kind, double time, float* joints_out, int* progress_out);
 int shc_startup_begin(shc_engine* e, const double* joint_positions_dev);
 int shc_startup_step(shc_engine* e, float* joints_out_dev, void* stream);

@@ -66,6 +66,7 @@ enum RobotState { PACKED, READY, RUNNING, ROBOT_STATE_COUNT, UNKNOWN = -1, OFF =
 enum WalkState { STARTING, MOVING, STOPPING, STOPPED, WALK_STATE_COUNT };
 enum StepState { SWING, STANCE, FORCE_STANCE, FORCE_STOP, STEP_STATE_COUNT };
 enum PosingState { POSING, STOP_POSING, POSING_COMPLETE, POSING_STATE_COUNT };
+enum SequenceSelection { START_UP, SHUT_DOWN, SEQUENCE_SELECTION_COUNT };  // parameters_and_states.h:183
 enum PoseResetMode { NO_RESET, Z_AND_YAW_RESET, X_AND_Y_RESET, PITCH_AND_ROLL_RESET, ALL_RESET, IMMEDIATE_ALL_RESET };
 enum LegState { WALKING, MANUAL, LEG_STATE_COUNT, WALKING_TO_MANUAL = -1, MANUAL_TO_WALKING = -2 };
 
@@ -212,6 +213,9 @@ class PoseController {  // pose_controller.h:36
   /// Sequences (one loop() per call, pose_controller.cpp:463 / :520 / :597 / :661): they act on the whole batch — the first
   /// robot to call in a loop runs the device step for everyone, the other robots' calls of that loop read their own result.
   inline int directStartup();
+  /// PoseController::executeSequence (pose_controller.cpp:145): START_UP / SHUT_DOWN; -1 while the first start-up generates
+  /// its sequence, else 0..100.  A robot that is through a sequence is not stepped by the other robots' further loops.
+  inline int executeSequence(const SequenceSelection& sequence);
   inline int stepToNewStance();
   inline int packLegs(const double& time_to_pack);
   inline int unpackLegs(const double& time_to_unpack);
@@ -545,6 +549,9 @@ inline void WalkController::setLinearAccelerationLimitMap(const std::array<doubl
 inline void WalkController::setAngularAccelerationLimitMap(const std::array<double, SHC_N_BEARINGS>& m) { b_->setLimitMaps(nullptr, nullptr, nullptr, m.data()); }
 
 inline int PoseController::directStartup() { return b_->sequence(robot_, SHC_SEQ_DIRECT_STARTUP, 0.0); }
+inline int PoseController::executeSequence(const SequenceSelection& sequence) {
+  return b_->sequence(robot_, sequence == START_UP ? SHC_SEQ_START_UP : SHC_SEQ_SHUT_DOWN, 0.0);
+}
 inline int PoseController::stepToNewStance() { return b_->sequence(robot_, SHC_SEQ_NEW_STANCE, 0.0); }
 inline int PoseController::packLegs(const double& t) { return b_->sequence(robot_, SHC_SEQ_PACK, t); }
 inline int PoseController::unpackLegs(const double& t) { return b_->sequence(robot_, SHC_SEQ_UNPACK, t); }

@@ -157,7 +157,7 @@ class OracleBatch:
         """One loop() of PoseController::stepToNewStance ("new_stance", pose_controller.cpp:520), packLegs(time) ("pack",
         :597) or unpackLegs(time) ("unpack", :661) for every robot; returns each robot's progress value."""
         out = np.zeros(self.n, dtype=np.int32)
-        self._lib.shc_oracle_batch_sequence_step(self._h, {"new_stance": 0, "pack": 1, "unpack": 2}[kind], float(time),
+        self._lib.shc_oracle_batch_sequence_step(self._h, {"new_stance": 0, "pack": 1, "unpack": 2, "start_up": 3, "shut_down": 4}[kind], float(time),
                                                  out.ctypes.data_as(C.POINTER(C.c_int)))
         return out
 

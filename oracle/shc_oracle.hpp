@@ -33,6 +33,12 @@ constexpr double IMU_POSING_DEADBAND = 0.0;      // pose_controller.h:25
 constexpr double ADMITTANCE_DEADBAND = 0.0;      // admittance_controller.h:18
 constexpr double GRAVITY_ACCELERATION = -9.81;   // standard_includes.h:59
 constexpr int PROGRESS_COMPLETE = 100;           // standard_includes.h:53
+constexpr double SAFETY_FACTOR = 0.15;           // pose_controller.h:20
+constexpr double HORIZONTAL_TRANSITION_TIME = 1.0;  // pose_controller.h:21
+constexpr double VERTICAL_TRANSITION_TIME = 3.0;    // pose_controller.h:22
+constexpr int TRANSITION_STEP_THRESHOLD = 20;    // pose_controller.h:24
+constexpr double HALF_BODY_DEPTH = 0.05;         // model.h:18
+enum SequenceSelection { START_UP = 0, SHUT_DOWN = 1 };  // parameters_and_states.h
 
 enum RobotState { PACKED, READY, RUNNING, ROBOT_STATE_COUNT, UNKNOWN = -1, OFF = -2 };  // parameters_and_states.h:27
 enum LegState { WALKING, MANUAL, LEG_STATE_COUNT, WALKING_TO_MANUAL = -1, MANUAL_TO_WALKING = -2 };
@@ -112,6 +118,9 @@ struct LegPoser {
   int master_iteration_count_ = 0;
   std::vector<double> desired_configuration_, origin_configuration_;
   Pose origin_tip_pose_, current_tip_pose_ = Pose::Undefined(), target_tip_pose_ = Pose::Undefined();
+  bool leg_completed_step_ = false;          // pose_controller.h:596
+  std::vector<Pose> transition_poses_;       // pose_controller.h:591
+  int resetStepToPosition() { first_iteration_ = true; return PROGRESS_COMPLETE; }  // pose_controller.h:535
 
   int transitionConfiguration(double transition_time);
   int stepToPosition(const Pose& target_tip_pose, const Pose& target_pose, double lift_height, double time_to_step,
@@ -206,6 +215,10 @@ struct Robot {
   bool executing_transition_ = false;
   int legs_completed_step_ = 0, current_group_ = 0, pack_step_ = 0;
   bool reset_transition_sequence_ = true;
+  int transition_step_ = 0, transition_step_count_ = 0;  // pose_controller.h:296-304
+  bool set_target_ = true, proximity_alert_ = false, horizontal_transition_complete_ = false,
+       vertical_transition_complete_ = false, first_sequence_execution_ = true;
+  bool sequence_failed_ = false;  // set where the reference would ROS_FATAL + shutdown (pose_controller.cpp:438-442)
   int auto_pose_reference_leg_ = 0;
   std::vector<AutoPoser> auto_posers_;
   PosingState auto_posing_state_ = POSING_COMPLETE;
@@ -249,6 +262,8 @@ struct Robot {
   void updateStance();
   int directStartup();
   int stepToNewStance();
+  int executeSequence(SequenceSelection sequence);
+  bool legsBearingLoad();
   int packLegs(double time_to_pack);
   int unpackLegs(double time_to_unpack);
   void updateCurrentPose(RobotState robot_state);

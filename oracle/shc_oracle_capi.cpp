@@ -221,6 +221,9 @@ struct Batch {
   shc_config cfg;
   std::vector<Robot*> robots;
   int startup_loops = 0;
+  // harness state of shc_oracle_batch_sequence_step: 1 = the robot's start-up sequence has completed, 2 = its shut-down
+  // (StateController stops calling executeSequence once it has returned 100, state_controller.cpp:314-350)
+  std::vector<int> sequence_done;
 };
 
 void stepOne(Robot& r, const double* cmd, const double* imu, const double* tip_force, const double* manual) {
@@ -344,12 +347,25 @@ double shc_oracle_batch_run_seq(void* h, const double* cmd_seq, int cycles, int 
 }
 
 // One loop() of a stepping / joint-space sequence for every robot: kind 0 = stepToNewStance
-// (pose_controller.cpp:520), 1 = packLegs(time) (:597), 2 = unpackLegs(time) (:661).  progress_out [n] gets each robot's return value.
+// (pose_controller.cpp:520), 1 = packLegs(time) (:597), 2 = unpackLegs(time) (:661), 3 / 4 = executeSequence(START_UP / SHUT_DOWN) (:145).  progress_out [n] gets each robot's return value.
 void shc_oracle_batch_sequence_step(void* h, int kind, double time, int* progress_out) {
   Batch* b = static_cast<Batch*>(h);
+  b->sequence_done.resize(b->robots.size(), 0);
   for (size_t i = 0; i < b->robots.size(); ++i) {
     Robot& r = *b->robots[i];
-    int p = kind == 0 ? r.stepToNewStance() : kind == 1 ? r.packLegs(time) : r.unpackLegs(time);
+    int p;
+    if (kind == 3 || kind == 4) {
+      if (b->sequence_done[i] == kind - 2) {
+        p = PROGRESS_COMPLETE;  // already through this sequence: its state machine no longer calls executeSequence
+      } else {
+        b->sequence_done[i] = 0;
+        p = r.executeSequence(kind == 3 ? START_UP : SHUT_DOWN);
+        if (p == PROGRESS_COMPLETE) b->sequence_done[i] = kind - 2;
+        if (r.sequence_failed_) p = -2;
+      }
+    } else {
+      p = kind == 0 ? r.stepToNewStance() : kind == 1 ? r.packLegs(time) : r.unpackLegs(time);
+    }
     if (progress_out) progress_out[i] = p;
   }
 }

@@ -111,6 +111,199 @@ int Robot::directStartup() {  // pose_controller.cpp:463
   return progress;
 }
 
+bool Robot::legsBearingLoad() {  // model.cpp:78
+  double body_height_estimate = 0.0;
+  for (int i = 0; i < leg_count_; ++i) body_height_estimate += legs[i].current_tip_pose_.position_[2];
+  return -(body_height_estimate / leg_count_) > HALF_BODY_DEPTH;
+}
+
+int Robot::executeSequence(SequenceSelection sequence) {  // pose_controller.cpp:145
+  if (reset_transition_sequence_ && sequence == START_UP) {
+    reset_transition_sequence_ = false;
+    first_sequence_execution_ = true;
+    transition_step_ = 0;
+    for (int i = 0; i < leg_count_; ++i) {
+      Leg& leg = legs[i];
+      leg.poser.transition_poses_.clear();
+      leg.poser.transition_poses_.push_back(leg.current_tip_pose_);
+    }
+  }
+
+  int progress = 0;
+  int normalised_progress = 0;
+  int next_transition_step = 0, transition_step_target = 0, total_progress = 0;
+  bool execute_horizontal_transition = false, execute_vertical_transition = false;
+  if (sequence == START_UP) {
+    execute_horizontal_transition = !(transition_step_ % 2);
+    execute_vertical_transition = transition_step_ % 2;
+    next_transition_step = transition_step_ + 1;
+    transition_step_target = transition_step_count_;
+    total_progress = transition_step_ * 100 / std::max(transition_step_count_, 1);
+  } else if (sequence == SHUT_DOWN) {
+    execute_horizontal_transition = transition_step_ % 2;
+    execute_vertical_transition = !(transition_step_ % 2);
+    next_transition_step = transition_step_ - 1;
+    transition_step_target = 0;
+    total_progress = 100 - transition_step_ * 100 / std::max(transition_step_count_, 1);
+  }
+
+  bool final_transition;
+  bool sequence_complete = false;
+  if (first_sequence_execution_) final_transition = (horizontal_transition_complete_ || vertical_transition_complete_);
+  else final_transition = (next_transition_step == transition_step_target);
+
+  double safety_factor = (first_sequence_execution_ ? SAFETY_FACTOR / (transition_step_ + 1) : 0.0);
+
+  if (execute_horizontal_transition) {
+    if (set_target_) {
+      set_target_ = false;
+      for (int i = 0; i < leg_count_; ++i) {
+        Leg& leg = legs[i];
+        LegStepper& leg_stepper = leg.stepper;
+        LegPoser& leg_poser = leg.poser;
+        leg_poser.leg_completed_step_ = false;
+        Vec3 target_tip_position;
+        if (int(leg_poser.transition_poses_.size()) > next_transition_step && next_transition_step >= 0) {
+          target_tip_position = leg_poser.transition_poses_[next_transition_step].position_;
+        } else {
+          Vec3 default_tip_position = leg_stepper.default_tip_pose_.position_;
+          target_tip_position = current_pose_.inverseTransformVector(default_tip_position);
+        }
+        target_tip_position[2] = leg.current_tip_pose_.position_[2];
+        Quat target_tip_rotation = leg_stepper.target_tip_pose_.rotation_;
+        leg_poser.target_tip_pose_ = Pose(target_tip_position, target_tip_rotation);
+      }
+    }
+
+    bool direct_step = !legsBearingLoad();
+    for (int i = 0; i < leg_count_; ++i) {
+      Leg& leg = legs[i];
+      LegPoser& leg_poser = leg.poser;
+      if (!leg_poser.leg_completed_step_) {
+        if (leg.group_ == current_group_ || direct_step) {
+          Pose target_tip_pose = leg_poser.target_tip_pose_;
+          bool apply_delta = (sequence == START_UP && final_transition);
+          double step_height = direct_step ? 0.0 : params_.swing_height;
+          double time_to_step = HORIZONTAL_TRANSITION_TIME / params_.step_frequency;
+          time_to_step *= (first_sequence_execution_ ? 2.0 : 1.0);
+          progress = leg_poser.stepToPosition(target_tip_pose, Pose::Identity(), step_height, time_to_step, apply_delta);
+          leg.setDesiredTipPose(leg_poser.current_tip_pose_);
+          double limit_proximity = leg.applyIK();
+          bool exceeded_workspace = limit_proximity < safety_factor;
+          if (first_sequence_execution_ && exceeded_workspace) {
+            leg_poser.target_tip_pose_ = leg_poser.current_tip_pose_;
+            progress = leg_poser.resetStepToPosition();
+            proximity_alert_ = true;
+          }
+          if (progress == PROGRESS_COMPLETE) {
+            leg_poser.leg_completed_step_ = true;
+            legs_completed_step_++;
+            if (first_sequence_execution_) {
+              bool reached_target = !exceeded_workspace;
+              Pose target_tip_pose2 = leg_poser.target_tip_pose_;
+              Pose current_tip_pose = leg_poser.current_tip_pose_;
+              Pose transition_pose = (reached_target ? target_tip_pose2 : current_tip_pose);
+              leg_poser.transition_poses_.push_back(transition_pose);
+            }
+          }
+        } else {
+          legs_completed_step_++;
+          leg_poser.leg_completed_step_ = true;
+        }
+      }
+    }
+
+    if (direct_step) normalised_progress = progress / std::max(transition_step_count_, 1);
+    else normalised_progress = (progress / 2 + (current_group_ == 0 ? 0 : 50)) / std::max(transition_step_count_, 1);
+
+    if (legs_completed_step_ == leg_count_) {
+      set_target_ = true;
+      legs_completed_step_ = 0;
+      if (current_group_ == 1 || direct_step) {
+        current_group_ = 0;
+        transition_step_ = next_transition_step;
+        horizontal_transition_complete_ = !proximity_alert_;
+        sequence_complete = final_transition;
+        proximity_alert_ = false;
+      } else if (current_group_ == 0) {
+        current_group_ = 1;
+      }
+    }
+  }
+
+  if (execute_vertical_transition) {
+    if (set_target_) {
+      set_target_ = false;
+      for (int i = 0; i < leg_count_; ++i) {
+        Leg& leg = legs[i];
+        LegStepper& leg_stepper = leg.stepper;
+        LegPoser& leg_poser = leg.poser;
+        Vec3 target_tip_position;
+        if (int(leg_poser.transition_poses_.size()) > next_transition_step && next_transition_step >= 0) {
+          target_tip_position = leg_poser.transition_poses_[next_transition_step].position_;
+        } else {
+          Vec3 default_tip_position = leg_stepper.default_tip_pose_.position_;
+          target_tip_position = current_pose_.inverseTransformVector(default_tip_position);
+        }
+        target_tip_position[0] = leg.current_tip_pose_.position_[0];
+        target_tip_position[1] = leg.current_tip_pose_.position_[1];
+        Quat target_tip_rotation = leg_stepper.target_tip_pose_.rotation_;
+        leg_poser.target_tip_pose_ = Pose(target_tip_position, target_tip_rotation);
+      }
+    }
+
+    bool all_legs_within_workspace = true;
+    for (int i = 0; i < leg_count_; ++i) {
+      Leg& leg = legs[i];
+      LegPoser& leg_poser = leg.poser;
+      Pose target_tip_pose = leg_poser.target_tip_pose_;
+      bool apply_delta = (sequence == START_UP && final_transition);
+      double time_to_step = VERTICAL_TRANSITION_TIME / params_.step_frequency;
+      time_to_step *= (first_sequence_execution_ ? 2.0 : 1.0);
+      progress = leg_poser.stepToPosition(target_tip_pose, Pose::Identity(), 0.0, time_to_step, apply_delta);
+      leg.setDesiredTipPose(leg_poser.current_tip_pose_, false);
+      double limit_proximity = leg.applyIK();
+      all_legs_within_workspace = all_legs_within_workspace && !(limit_proximity < safety_factor);
+    }
+
+    if ((!all_legs_within_workspace && first_sequence_execution_) || progress == PROGRESS_COMPLETE) {
+      for (int i = 0; i < leg_count_; ++i) {
+        LegPoser& leg_poser = legs[i].poser;
+        progress = leg_poser.resetStepToPosition();
+        if (first_sequence_execution_) {
+          bool reached_target = all_legs_within_workspace;
+          Pose target_tip_pose = leg_poser.target_tip_pose_;
+          Pose current_tip_pose = leg_poser.current_tip_pose_;
+          Pose transition_pose = (reached_target ? target_tip_pose : current_tip_pose);
+          leg_poser.transition_poses_.push_back(transition_pose);
+        }
+      }
+      vertical_transition_complete_ = all_legs_within_workspace;
+      transition_step_ = next_transition_step;
+      sequence_complete = final_transition;
+      set_target_ = true;
+    }
+    normalised_progress = progress / std::max(transition_step_count_, 1);
+  }
+
+  if (first_sequence_execution_) {
+    transition_step_count_ = transition_step_;
+    transition_step_target = transition_step_;
+  }
+  (void)transition_step_target;
+  if (transition_step_ > TRANSITION_STEP_THRESHOLD) sequence_failed_ = true;  // ROS_FATAL + ros::shutdown() in the reference
+
+  if (sequence_complete) {
+    set_target_ = true;
+    vertical_transition_complete_ = false;
+    horizontal_transition_complete_ = false;
+    first_sequence_execution_ = false;
+    return PROGRESS_COMPLETE;
+  }
+  total_progress = std::min(total_progress + normalised_progress, PROGRESS_COMPLETE - 1);
+  return (first_sequence_execution_ ? -1 : total_progress);
+}
+
 int Robot::stepToNewStance() {  // pose_controller.cpp:520 (tripod leg coordination)
   int progress = 0;
   int leg_count = leg_count_;
@@ -140,6 +333,7 @@ int Robot::stepToNewStance() {  // pose_controller.cpp:520 (tripod leg coordinat
 
 int Robot::packLegs(double time_to_pack) {  // pose_controller.cpp:597 (one pack step: Joint::packed_positions_ has one entry)
   int progress = 0;
+  transition_step_ = 0;  // reset for the start-up / shut-down sequences (:618)
   int number_pack_steps = 1;
   for (int i = 0; i < leg_count_; ++i) {
     Leg& leg = legs[i];

@@ -260,6 +260,16 @@ __global__ void __launch_bounds__(128) step_to_new_stance_kernel(const __grid_co
   atomicMin(min_progress, p);
 }
 template <class S, int D>
+__global__ void __launch_bounds__(128) execute_sequence_kernel(const __grid_constant__ Consts c, Planes<S> pl, SeqBuffers sq, ExecuteSequenceParams ep,
+                                                               int shut_down, float* __restrict__ joints_out, int* __restrict__ progress_out,
+                                                               int* min_progress) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= c.i.n_robots) return;
+  const int p = execute_sequence_robot<S, D>(c, pl, sq, ep, shut_down != 0, r, joints_out);
+  if (progress_out) progress_out[r] = p;
+  atomicMin(min_progress, p);
+}
+template <class S, int D>
 __global__ void __launch_bounds__(256) transition_joint_kernel(const __grid_constant__ Consts c, Planes<S> pl, const double* __restrict__ origin,
                                                                const double* __restrict__ desired, int it, int num, float* __restrict__ joints_out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -369,7 +379,10 @@ struct shc_engine {
   double* seq_origin = nullptr;   // [L][3][n_pad] LegPoser::origin_tip_pose_.position_
   int* seq_count = nullptr;       // [L][n_pad] LegPoser::master_iteration_count_ (-1: first_iteration_)
   int* seq_robot = nullptr;       // [2][n_pad] legs_completed_step_, current_group_
-  int* seq_min = nullptr;         // device word: smallest progress of the last stepToNewStance launch
+  int* seq_min = nullptr;         // device word: smallest progress of the last stepToNewStance / executeSequence launch
+  double* seq_target = nullptr;   // executeSequence: [L][3][n_pad] LegPoser::target_tip_pose_.position_
+  double* seq_poses = nullptr;    //                  [kMaxTransitionPoses][L][3][n_pad] LegPoser::transition_poses_
+  int* seq_leg = nullptr;         //                  [2][L][n_pad] leg_completed_step_, number of transition poses
   double* tr_origin = nullptr;    // [N][L][D] joint positions when the transition began
   double* tr_desired = nullptr;   // [kMaxLegs][kMaxDof]
   int tr_iteration = 0, tr_num = 0;
@@ -681,6 +694,9 @@ void shc_destroy(shc_engine* e) {
   cudaFree(e->seq_count);
   cudaFree(e->seq_robot);
   cudaFree(e->seq_min);
+  cudaFree(e->seq_target);
+  cudaFree(e->seq_poses);
+  cudaFree(e->seq_leg);
   cudaFree(e->tr_origin);
   cudaFree(e->tr_desired);
   cudaFree(e->d_cmd); cudaFree(e->d_imu); cudaFree(e->d_force); cudaFree(e->d_manual); cudaFree(e->d_out);
@@ -1097,7 +1113,10 @@ int shc_sequence_reset(shc_engine* e) {
   fill_int_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, e->stream>>>(e->seq_count, nc, -1);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemsetAsync(e->seq_robot, 0, seq_robot_count(e->n_pad) * 4, e->stream));
+  fill_int_kernel<<<(unsigned)((e->n_pad + 255) / 256), 256, 0, e->stream>>>(e->seq_robot + 4 * (size_t)e->n_pad, (size_t)e->n_pad, kSeqInitialFlags);
+  CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemsetAsync(e->seq_origin, 0, seq_origin_count(e->cfg.leg_count, e->n_pad) * 8, e->stream));
+  if (e->seq_leg) CUDA_TRY(cudaMemsetAsync(e->seq_leg, 0, seq_leg_count(e->cfg.leg_count, e->n_pad) * 4, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   return SHC_OK;
 }
@@ -1119,7 +1138,7 @@ int shc_step_to_new_stance(shc_engine* e, float* joints_out_dev, int* progress_o
   np.lift_height = e->cfg.swing_height;
   np.num_iterations = std::max(1, round_to_int((1.0 / e->cfg.step_frequency) / e->cfg.time_delta));
   np.apply_delta = 1;
-  SeqBuffers sq{e->seq_origin, e->seq_count, e->seq_robot, (size_t)e->n_pad};
+  SeqBuffers sq{e->seq_origin, e->seq_count, e->seq_robot, (size_t)e->n_pad, e->seq_target, e->seq_poses, e->seq_leg};
   const int init = 1000;
   CUDA_TRY(cudaMemcpyAsync(e->seq_min, &init, 4, cudaMemcpyHostToDevice, st));
   const int threads = 128, blocks = (e->n + threads - 1) / threads;
@@ -1141,6 +1160,52 @@ int shc_step_to_new_stance(shc_engine* e, float* joints_out_dev, int* progress_o
   CUDA_TRY(cudaMemcpyAsync(&progress, e->seq_min, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return progress;
+}
+
+// One loop() of PoseController::executeSequence (pose_controller.cpp:145-461) for every robot: the start-up (shut_down = 0)
+// or shut-down sequence, each robot on its own course (csrc/shc_sequence.cuh).  joints_out_dev float [N][L][D] /
+// progress_out_dev int [N] (each robot's return value: -1 while its first start-up generates the sequence, 0..100, -2 once
+// it has failed: SHC_SEQ_GENERATING / SHC_SEQ_FAILED), either may be NULL.  *min_progress_out = the smallest value over the
+// batch (blocking on `stream`); the return value is SHC_OK or an SHC_E_* code.
+int shc_execute_sequence(shc_engine* e, int shut_down, float* joints_out_dev, int* progress_out_dev, int* min_progress_out, void* stream) {
+  if (!e || !min_progress_out) return fail(SHC_E_INVALID, "shc_execute_sequence: bad arguments");
+  if (e->c.i.tip_mode == TIP_ROTATION) return fail(SHC_E_UNSUPPORTED, "stepping sequences with tip-rotation targets (gravity_aligned_tips, D > 3) are not built");
+  if (e->cfg.leg_count % 2 != 0) return fail(SHC_E_UNSUPPORTED, "executeSequence coordinates two leg groups: leg_count must be even");
+  CUDA_TRY(cudaSetDevice(e->device));
+  int rc = seq_alloc(e);
+  if (rc != SHC_OK) return rc;
+  const int L = e->cfg.leg_count;
+  if (!e->seq_poses) {
+    CUDA_TRY(cudaMalloc((void**)&e->seq_target, seq_origin_count(L, e->n_pad) * 8));
+    CUDA_TRY(cudaMalloc((void**)&e->seq_poses, seq_poses_count(L, e->n_pad) * 8));
+    CUDA_TRY(cudaMalloc((void**)&e->seq_leg, seq_leg_count(L, e->n_pad) * 4));
+    CUDA_TRY(cudaMemset(e->seq_target, 0, seq_origin_count(L, e->n_pad) * 8));
+    CUDA_TRY(cudaMemset(e->seq_poses, 0, seq_poses_count(L, e->n_pad) * 8));
+    CUDA_TRY(cudaMemset(e->seq_leg, 0, seq_leg_count(L, e->n_pad) * 4));
+  }
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  ExecuteSequenceParams ep{e->cfg.swing_height, e->cfg.step_frequency, e->cfg.time_delta};
+  SeqBuffers sq{e->seq_origin, e->seq_count, e->seq_robot, (size_t)e->n_pad, e->seq_target, e->seq_poses, e->seq_leg};
+  const int init = 1000;
+  CUDA_TRY(cudaMemcpyAsync(e->seq_min, &init, 4, cudaMemcpyHostToDevice, st));
+  const int threads = 128, blocks = (e->n + threads - 1) / threads;
+  rc = dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int {
+    constexpr int D = decltype(dtag)::value;
+    if (e->precision == SHC_PRECISION_F64) {
+      Planes<double> pl{(double*)e->s_planes, e->d_planes, e->i_planes};
+      execute_sequence_kernel<double, D><<<blocks, threads, 0, st>>>(e->c, pl, sq, ep, shut_down, joints_out_dev, progress_out_dev, e->seq_min);
+    } else {
+      Planes<float> pl{(float*)e->s_planes, e->d_planes, e->i_planes};
+      execute_sequence_kernel<float, D><<<blocks, threads, 0, st>>>(e->c, pl, sq, ep, shut_down, joints_out_dev, progress_out_dev, e->seq_min);
+    }
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(SHC_E_CUDA, std::string("execute_sequence launch: ") + cudaGetErrorString(err));
+    return SHC_OK;
+  });
+  if (rc != SHC_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(min_progress_out, e->seq_min, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return SHC_OK;
 }
 
 // PoseController::transitionConfiguration (pose_controller.cpp:703) for the whole batch: from the joint positions the state
@@ -1205,6 +1270,8 @@ int shc_transition_step(shc_engine* e, float* joints_out_dev, void* stream) {
 // every call moves the transition one iteration on.  Returns the progress (100 = complete, the next call starts anew).
 static int pack_unpack(shc_engine* e, bool pack, double time, float* joints_out_dev, void* stream) {
   if (!e) return fail(SHC_E_INVALID, "null engine");
+  if (pack && e->seq_robot)  // packLegs: transition_step_ = 0 (pose_controller.cpp:618)
+    CUDA_TRY(cudaMemsetAsync(e->seq_robot + 2 * (size_t)e->n_pad, 0, (size_t)e->n_pad * 4, stream ? (cudaStream_t)stream : e->stream));
   if (!e->tr_executing) {
     double desired[kMaxLegs * kMaxDof];
     const int L = e->cfg.leg_count, D = e->cfg.joint_count;
@@ -1240,6 +1307,10 @@ int shc_sequence_step_host(shc_engine* e, int kind, double time, float* joints_o
     progress = shc_pack_legs(e, time, e->d_out, e->stream);
   } else if (kind == SHC_SEQ_UNPACK) {
     progress = shc_unpack_legs(e, time, e->d_out, e->stream);
+  } else if (kind == SHC_SEQ_START_UP || kind == SHC_SEQ_SHUT_DOWN) {
+    if (progress_out) CUDA_TRY(cudaMalloc((void**)&d_progress, n * 4));
+    rc = shc_execute_sequence(e, kind == SHC_SEQ_SHUT_DOWN, e->d_out, d_progress, &progress, e->stream);
+    if (rc != SHC_OK) { cudaFree(d_progress); return rc; }
   } else if (kind == SHC_SEQ_DIRECT_STARTUP) {
     if (e->startup_num <= 0 || e->startup_iteration >= e->startup_num) {
       if ((rc = shc_startup_begin(e, nullptr)) != SHC_OK) return rc;
@@ -1248,7 +1319,8 @@ int shc_sequence_step_host(shc_engine* e, int kind, double time, float* joints_o
   } else {
     return fail(SHC_E_INVALID, "shc_sequence_step_host: unknown sequence");
   }
-  if (progress < 0) { cudaFree(d_progress); return progress; }
+  const bool exec_seq = kind == SHC_SEQ_START_UP || kind == SHC_SEQ_SHUT_DOWN;  // (their -1 / -2 are progress values)
+  if (progress < 0 && !exec_seq) { cudaFree(d_progress); return progress; }
   if (joints_out) CUDA_TRY(cudaMemcpyAsync(joints_out, e->d_out, n * L * D * 4, cudaMemcpyDeviceToHost, e->stream));
   if (progress_out) {
     if (d_progress) CUDA_TRY(cudaMemcpyAsync(progress_out, d_progress, n * 4, cudaMemcpyDeviceToHost, e->stream));

@@ -50,6 +50,7 @@ def lib():
         L.shc_direct_startup.argtypes = [vp, vp, vp, vp]
         L.shc_step_to_new_stance.argtypes = [vp, vp, vp, vp]
         L.shc_sequence_reset.argtypes = [vp]
+        L.shc_execute_sequence.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int), vp]
         L.shc_transition_begin.argtypes = [vp, C.POINTER(C.c_double), C.c_double]
         L.shc_transition_step.argtypes = [vp, vp, vp]
         L.shc_pack_legs.argtypes = [vp, C.c_double, vp, vp]
@@ -266,6 +267,15 @@ class Engine:
             _check(rc)
         return rc
 
+    def execute_sequence(self, shut_down: bool = False, out=None, progress_out=None, stream=None) -> int:
+        """One loop() of PoseController::executeSequence (pose_controller.cpp:145) for the batch: the start-up (or shut-down)
+        sequence.  Returns the smallest per-robot value: -1 while a first start-up generates its sequence, 0..100, -2 failed."""
+        out = self._out(out)
+        mn = C.c_int(0)
+        _check(lib().shc_execute_sequence(self._h, int(bool(shut_down)), _ptr(out), _ptr(progress_out), C.byref(mn),
+                                          _stream_handle(self.torch, self.device, stream)))
+        return int(mn.value)
+
     def sequence_reset(self):
         _check(lib().shc_sequence_reset(self._h))
 
@@ -305,6 +315,9 @@ class Engine:
         if kind == "new_stance":
             prog = t.zeros(self.n, dtype=t.int32, device=self.device)
             self.step_to_new_stance(progress_out=prog)
+        elif kind in ("start_up", "shut_down"):
+            prog = t.zeros(self.n, dtype=t.int32, device=self.device)
+            self.execute_sequence(kind == "shut_down", progress_out=prog)
         else:
             p = self.pack_legs(time) if kind == "pack" else self.unpack_legs(time)
             prog = t.full((self.n,), p, dtype=t.int32, device=self.device)

@@ -36,7 +36,8 @@ struct shc_emu {
   bool have_efforts = false;
   // sequences (csrc/shc_sequence.cuh on host planes)
   std::vector<double> seq_origin, tr_origin;
-  std::vector<int> seq_count, seq_robot;
+  std::vector<int> seq_count, seq_robot, seq_leg;
+  std::vector<double> seq_target, seq_poses;
   double tr_desired[kMaxLegs * kMaxDof] = {};
   int tr_iteration = 0, tr_num = 0;
   bool tr_executing = false;
@@ -166,12 +167,17 @@ int shc_emu_step(shc_emu* e, const float* cmd, const float* imu, const float* ti
 }
 
 // The sequence routines of csrc/shc_sequence.cuh (shc_step_to_new_stance, shc_pack_legs / shc_unpack_legs) on the emulator's
-// planes, robot after robot.  kind 0 = stepToNewStance, 1 = packLegs(time), 2 = unpackLegs(time); joints_out [n][L][D],
+// planes, robot after robot.  kind 0 = stepToNewStance, 1 = packLegs(time), 2 = unpackLegs(time), 3 / 4 = executeSequence
+// (START_UP / SHUT_DOWN); joints_out [n][L][D],
 // progress_out [n] (pack / unpack: the same value for every robot).
 int shc_emu_sequence_reset(shc_emu* e) {
   e->seq_origin.assign(seq_origin_count(e->cfg.leg_count, e->n_pad), 0.0);
   e->seq_count.assign(seq_count_count(e->cfg.leg_count, e->n_pad), -1);
   e->seq_robot.assign(seq_robot_count(e->n_pad), 0);
+  for (int r = 0; r < e->n_pad; ++r) e->seq_robot[4 * (size_t)e->n_pad + r] = kSeqInitialFlags;
+  e->seq_target.assign(seq_origin_count(e->cfg.leg_count, e->n_pad), 0.0);
+  e->seq_poses.assign(seq_poses_count(e->cfg.leg_count, e->n_pad), 0.0);
+  e->seq_leg.assign(seq_leg_count(e->cfg.leg_count, e->n_pad), 0);
   return SHC_OK;
 }
 int shc_emu_sequence_step(shc_emu* e, int kind, double time, float* joints_out, int* progress_out) {
@@ -181,17 +187,27 @@ int shc_emu_sequence_step(shc_emu* e, int kind, double time, float* joints_out, 
     constexpr int D = decltype(dtag)::value;
     auto go = [&](auto pl) -> int {
       using S = typename std::remove_pointer<decltype(pl.s)>::type;
+      if (e->seq_count.empty()) shc_emu_sequence_reset(e);
+      if (kind == 3 || kind == 4) {
+        ExecuteSequenceParams ep{e->cfg.swing_height, e->cfg.step_frequency, e->cfg.time_delta};
+        SeqBuffers sq{e->seq_origin.data(), e->seq_count.data(), e->seq_robot.data(), (size_t)e->n_pad, e->seq_target.data(),
+                      e->seq_poses.data(), e->seq_leg.data()};
+        for (int r = 0; r < e->n; ++r) progress_out[r] = execute_sequence_robot<S, D>(e->c, pl, sq, ep, kind == 4, r, joints_out);
+        return SHC_OK;
+      }
       if (kind == 0) {
-        if (e->seq_count.empty()) shc_emu_sequence_reset(e);
         NewStanceParams np;
         np.lift_height = e->cfg.swing_height;
         np.num_iterations = std::max(1, round_to_int((1.0 / e->cfg.step_frequency) / e->cfg.time_delta));
         np.apply_delta = 1;
-        SeqBuffers sq{e->seq_origin.data(), e->seq_count.data(), e->seq_robot.data(), (size_t)e->n_pad};
+        SeqBuffers sq{e->seq_origin.data(), e->seq_count.data(), e->seq_robot.data(), (size_t)e->n_pad, e->seq_target.data(),
+                      e->seq_poses.data(), e->seq_leg.data()};
         for (int r = 0; r < e->n; ++r) progress_out[r] = step_to_new_stance_robot<S, D>(e->c, pl, sq, np, r, joints_out);
         return SHC_OK;
       }
       const long long total = (long long)e->n * L * D;
+      if (kind == 1)  // packLegs: transition_step_ = 0 (pose_controller.cpp:618)
+        for (int r = 0; r < e->n_pad; ++r) e->seq_robot[2 * (size_t)e->n_pad + r] = 0;
       if (!e->tr_executing) {
         e->tr_origin.resize((size_t)total);
         for (long long i = 0; i < total; ++i) latch_joint<S, D>(e->c, pl, i, e->tr_origin.data());

@@ -137,7 +137,7 @@ class EmuEngine:
         """One loop() of stepToNewStance ("new_stance") / packLegs ("pack") / unpackLegs ("unpack"): (joints [n, L, D], progress [n])."""
         out = np.zeros((self.n, self.L, self.D), dtype=np.float32)
         prog = np.zeros(self.n, dtype=np.int32)
-        _check(lib().shc_emu_sequence_step(self._h, {"new_stance": 0, "pack": 1, "unpack": 2}[kind], float(time),
+        _check(lib().shc_emu_sequence_step(self._h, {"new_stance": 0, "pack": 1, "unpack": 2, "start_up": 3, "shut_down": 4}[kind], float(time),
                                            out.ctypes.data_as(C.POINTER(C.c_float)), prog.ctypes.data_as(C.POINTER(C.c_int))))
         return out.astype(np.float64), prog
 

@@ -533,6 +533,67 @@ def sequences(backend, oracle, n=32):
         eng.close(); ob.close()
 
 
+def execute_sequence(backend, oracle, n=24):
+    """SURVEY.md 8(f) rank 2: PoseController::executeSequence (pose_controller.cpp:145-461), every loop() against the oracle:
+    unpack, the FIRST start-up (which generates the transition sequence under its joint-limit safety factor: progress -1),
+    a shut-down along the recorded transition poses, and a second start-up (progress 0..100).  The robots start from the
+    different states a walking batch stopped in.  Hexapod: free-running, all ~1250 loops.  Octopod: its five-joint legs are
+    redundant for a position target, so over thousands of closed-loop IK iterations the null-space component of the joints
+    wanders with the reference's normalised cost gradient (DESIGN.md "Reference dynamics") and two correct implementations
+    part ways in joint space while their tips and progress values agree; there every loop starts from the oracle's joint state
+    (one loop from identical state, to 1e-9), the sequence bookkeeping — step counters, transition poses, targets — still
+    being each side's own."""
+    for cfg, L, D in ((hexapod_config("tripod_gait"), 6, 3), (octopod_config("wave_gait"), 8, 5)):
+        resync = D > 3
+        ob = oracle.OracleBatch(cfg, n)
+        eng = backend.engine(cfg, n, startup=ob.startup())
+        cs = CommandStream(n, min_len=30, max_len=90)
+        ims = ImuStream(n) if cfg.imu_posing or cfg.inclination_posing else None
+        fs = ForceStream(n, L) if cfg.admittance_control else None
+        for c in range(90):
+            cmd = cs.next()
+            imu = ims.next(cfg.time_delta) if ims else None
+            force = fs.next() if fs else None
+            ob.step(cmd.astype(np.float64), None if imu is None else imu.astype(np.float64),
+                    None if force is None else force.astype(np.float64), threads=4)
+        eng.set_state(ob.get_state())
+        worst = 0.0
+
+        def run(kind, time=0.0, limit=6000):
+            """Steps the sequence for the whole batch until every robot has returned 100 (a robot that is through keeps
+            returning 100 without moving, as its state machine would stop calling executeSequence)."""
+            nonlocal worst
+            done = np.zeros(n, dtype=bool)
+            seen = set()
+            for k in range(limit):
+                if resync:
+                    eng.set_state(ob.get_state())
+                j, p = eng.sequence_step(kind, time)
+                po = ob.sequence_step(kind, time)
+                assert np.array_equal(p, po), (kind, k, p[:8], po[:8])
+                worst = max(worst, float(np.abs(j - ob.joints()).max()))
+                seen.update(int(v) for v in po)
+                done |= po == 100
+                if done.all():
+                    return k + 1, seen
+            raise AssertionError(f"{kind} did not complete")
+
+        loops_unpack, _ = run("unpack", 2.0)
+        loops1, seen1 = run("start_up")
+        loops2, seen2 = run("shut_down")
+        loops3, seen3 = run("start_up")
+        assert -1 in seen1 and -1 not in seen3 and max(seen3 - {100}) >= 90 and -2 not in (seen1 | seen2 | seen3)
+        # hexapod, free-running over ~1250 closed-loop IK iterations partly at rest: the joints may sit in the reference's
+        # stand-still limit cycle, so the free-running bound applies (observed: float32 rounding only)
+        assert worst <= (2e-7 if resync else JointErrors.CHATTER_BOUND), worst
+        d = assert_state_close(eng.get_state(), ob.get_state(), L, D, 1e-9 if resync else JointErrors.CHATTER_BOUND, vel_tol=1e-7 if resync else 1.0,
+                               skip=("model_tip_position", "desired_tip_position", "ik_result"))
+        print(f"[execute-sequence] {L}x{D}: unpack {loops_unpack}, first start-up {loops1}, shut-down {loops2}, second start-up {loops3} "
+              f"loops; worst joint difference {worst:.2e} rad, joint state {d['joint_position']:.2e}"
+              + (" (every loop from the oracle's joint state)" if resync else " (free-running)"))
+        eng.close(); ob.close()
+
+
 def mixed_precision_statistics(backend, oracle, n=256, cycles=600):
     """Mixed precision over a long rollout: the typical joint error stays far below 1e-6 rad; excursions are bounded by
     the amplitude of the reference's own period-2 joint chatter (~2.3e-3 rad peak to peak), which fp32 state cannot

@@ -80,6 +80,10 @@ def test_emu_sequences(emu, oracle):
     P.sequences(emu, oracle, n=16)
 
 
+def test_emu_execute_sequence(emu, oracle):
+    P.execute_sequence(emu, oracle, n=8)
+
+
 def test_emu_wire_formats(emu, oracle):
     P.wire_formats(emu, oracle)
 

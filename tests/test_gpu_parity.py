@@ -83,6 +83,10 @@ def test_sequences(gpu, oracle):
     P.sequences(gpu, oracle, n=96)
 
 
+def test_execute_sequence(gpu, oracle):
+    P.execute_sequence(gpu, oracle, n=48)
+
+
 def test_wire_formats(gpu, oracle):
     P.wire_formats(gpu, oracle)
 
