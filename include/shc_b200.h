@@ -123,6 +123,12 @@ int shc_rollout(shc_engine* e, int k_cycles, const float* cmd_seq, const float* 
  * pointer float [N][L][D], latched until changed; NULL = all zero.  Only read when use_joint_effort is set. */
 int shc_set_joint_efforts(shc_engine* e, const float* efforts_dev);
 
+/* Tip range-sensor readings for rough-terrain mode (TipState.step_plane, tipStatesCallback state_controller.cpp:1650-1675):
+ * device pointer float [N][L][3] = (x slope, y slope, z range along the tip's x axis), latched until changed; NULL = no range
+ * sensors.  A range >= SHC_RANGE_UNASSIGNED (shc_config.h) means "no reading" (the reference's UNASSIGNED_VALUE): the leg's step plane is
+ * forgotten.  Only read when rough_terrain_mode is set. */
+int shc_set_tip_step_planes(shc_engine* e, const float* step_planes_dev);
+
 /* Output wire formats (records in shc_msgs.h): JointState, LegState, velocity / pose / rotation-error
  * and frame-transform records of the robots [first, first + count) as of the last cycle, packed by ONE kernel from the state
  * planes (one thread per leg) — the per-leg / per-joint host loops of state_controller.cpp:777-1047 disappear.  Outputs:

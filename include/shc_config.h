@@ -21,6 +21,8 @@ extern "C" {
 #define SHC_N_BEARINGS 9      /* LimitMap keys 0,45,...,360 (model.h:22 BEARING_STEP) */
 
 enum { SHC_VELOCITY_THROTTLE = 0, SHC_VELOCITY_REAL = 1 }; /* velocity_input_mode (default.yaml:90) */
+/* a tip range-sensor reading at or above this value stands for the reference's UNASSIGNED_VALUE ("no reading") */
+#define SHC_RANGE_UNASSIGNED 1.0e9f
 
 typedef struct shc_config {
   /* ---- control flags (default.yaml:9-15) ---- */

@@ -68,6 +68,7 @@ def _bind(L):
         L.shc_oracle_batch_set_state.argtypes = [C.c_void_p, C.POINTER(ShcRobotState)]
         L.shc_oracle_batch_set_pose_reset_mode.argtypes = [C.c_void_p, C.c_int]
         L.shc_oracle_batch_set_joint_efforts.argtypes = [C.c_void_p, dp]
+        L.shc_oracle_batch_set_step_planes.argtypes = [C.c_void_p, dp]
         L.shc_oracle_smooth_step.restype = C.c_double
         L.shc_oracle_smooth_step.argtypes = [C.c_double]
         L.shc_oracle_round_to_int.argtypes = [C.c_double]
@@ -160,6 +161,16 @@ class OracleBatch:
         self._lib.shc_oracle_batch_sequence_step(self._h, {"new_stance": 0, "pack": 1, "unpack": 2, "start_up": 3, "shut_down": 4}[kind], float(time),
                                                  out.ctypes.data_as(C.POINTER(C.c_int)))
         return out
+
+    def set_tip_step_planes(self, step_planes):
+        """Tip range-sensor readings [n, L, 3] (TipState.step_plane; z >= 1e9 stands for the reference's UNASSIGNED_VALUE), or None."""
+        if step_planes is None:
+            self._lib.shc_oracle_batch_set_step_planes(self._h, None)
+            return
+        sp = np.array(step_planes, dtype=np.float64)
+        assert sp.shape == (self.n, self.L, 3)
+        sp[..., 2] = np.where(sp[..., 2] >= 1e9, float(2 ** 31 - 1), sp[..., 2])
+        self._lib.shc_oracle_batch_set_step_planes(self._h, _dp(np.ascontiguousarray(sp)))
 
     def joints(self) -> np.ndarray:
         out = np.empty((self.n, self.L, self.D), dtype=np.float64)

@@ -224,9 +224,11 @@ struct Batch {
   // harness state of shc_oracle_batch_sequence_step: 1 = the robot's start-up sequence has completed, 2 = its shut-down
   // (StateController stops calling executeSequence once it has returned 100, state_controller.cpp:314-350)
   std::vector<int> sequence_done;
+  std::vector<double> step_planes;  // latched TipState.step_plane readings [n][L][3] (shc_oracle_batch_set_step_planes)
 };
 
-void stepOne(Robot& r, const double* cmd, const double* imu, const double* tip_force, const double* manual) {
+void stepOne(Robot& r, const double* cmd, const double* imu, const double* tip_force, const double* manual,
+             const double* step_plane = nullptr) {
   // Inputs arrive through callbacks in ros::spinOnce() before the next loop() (main.cpp:130).
   if (imu) r.setImuData(Quat(imu[0], imu[1], imu[2], imu[3]), Vec3(imu[7], imu[8], imu[9]), Vec3(imu[4], imu[5], imu[6]));
   if (tip_force)  // tipStatesCallback with wrench values (state_controller.cpp:1636-1648)
@@ -234,6 +236,20 @@ void stepOne(Robot& r, const double* cmd, const double* imu, const double* tip_f
       r.legs[l].stepper.touchdown_detection_ = true;
       r.legs[l].tip_force_measured_ = Vec3(tip_force[l * 3], tip_force[l * 3 + 1], tip_force[l * 3 + 2]);
       r.legs[l].touchdownDetection();
+    }
+  if (step_plane)  // tipStatesCallback with step-plane values (state_controller.cpp:1650-1675)
+    for (int l = 0; l < r.leg_count_; ++l) {
+      Leg& leg = r.legs[l];
+      leg.stepper.touchdown_detection_ = true;
+      const double* sp = step_plane + 3 * l;
+      if (sp[2] != UNASSIGNED_VALUE) {
+        Vec3 step_plane_position(sp[2], 0.0, 0.0);
+        Vec3 step_plane_normal(sp[0], sp[1], -1.0);
+        Quat step_plane_orientation = fromTwoVectors(Vec3(0, 0, 1.0), -step_plane_normal);
+        leg.step_plane_pose_ = leg.tipPoseRobotFrame(Pose(step_plane_position, step_plane_orientation));
+      } else {
+        leg.step_plane_pose_ = Pose::Undefined();
+      }
     }
   if (manual) {  // poser_->setManualPoseInput (state_controller.cpp:1148)
     r.translation_velocity_input_ = Vec3(manual[0], manual[1], manual[2]);
@@ -291,7 +307,7 @@ void shc_oracle_batch_step(void* h, const double* cmd, const double* imu, const 
   auto work = [&](int lo, int hi) {
     for (int i = lo; i < hi; ++i)
       stepOne(*b->robots[i], cmd + 3 * i, imu ? imu + 10 * i : nullptr, tip_force ? tip_force + 3 * L * i : nullptr,
-              manual ? manual + 6 * i : nullptr);
+              manual ? manual + 6 * i : nullptr, b->step_planes.empty() ? nullptr : b->step_planes.data() + (size_t)3 * L * i);
   };
   if (n_threads <= 1 || n < 2 * n_threads) {
     work(0, n);
@@ -396,6 +412,13 @@ void shc_oracle_batch_set_pose_reset_mode(void* h, int mode) {
 
 // jointStatesCallback (state_controller.cpp:1565-1590): measured joint efforts [n][L][D] (NULL = zero), read by
 // Leg::calculateTipForce (model.cpp:667) when use_joint_effort is set.
+// Tip range-sensor readings [n][L][3] (x, y, z; z = UNASSIGNED_VALUE for "no reading"), latched; NULL = none.
+void shc_oracle_batch_set_step_planes(void* h, const double* sp) {
+  Batch* b = static_cast<Batch*>(h);
+  if (!sp) { b->step_planes.clear(); return; }
+  b->step_planes.assign(sp, sp + b->robots.size() * b->cfg.leg_count * 3);
+}
+
 void shc_oracle_batch_set_joint_efforts(void* h, const double* eff) {
   Batch* b = static_cast<Batch*>(h);
   const int L = b->cfg.leg_count, D = b->cfg.joint_count;

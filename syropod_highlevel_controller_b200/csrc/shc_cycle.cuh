@@ -35,6 +35,8 @@ struct StepIO {
   const float* tip_force;  // [N][L][3] or null
   const float* manual;     // [N][6] or null
   const float* efforts;    // [N][L][D] or null: measured joint efforts (jointStatesCallback, state_controller.cpp:1565)
+  const float* step_planes;  // [N][L][3] or null: TipState.step_plane of the tip range sensors (x, y slopes, z range;
+                             // z >= SHC_RANGE_UNASSIGNED = no reading), tipStatesCallback (state_controller.cpp:1650-1675)
   float* joints_out;       // [N][L][D] (this shard's joint commands)
   // Fused all-gather (multi-GPU): when n_gather > 0 the tile is ALSO stored into every rank's gather buffer
   // gather[p][gather_offset + ...], p = 0 .. n_gather-1 — peer-mapped device pointers (CUDA IPC), i.e. plain stores that
@@ -1242,6 +1244,19 @@ template <class P, int D, int MODE> struct Cycle {
               step_plane_defined = true;
               st3(rp, RT_STEP_PLANE, step_plane);
             } else if (fn < ck.liftoff_threshold) {
+              step_plane_defined = false;
+            }
+          }
+          if (io.step_planes) {
+            // range sensor readings (:1650-1675): the step plane sits `range` along the tip's x axis; its orientation is
+            // never read (walk_controller.cpp:1085-1110 uses the position and whether the pose is defined)
+            touchdown_detection = true;
+            const float range = io.step_planes[((size_t)r * L + l) * 3 + 2];
+            if (range < SHC_RANGE_UNASSIGNED) {
+              step_plane = model_tip + t1_rotate(lk, ch.tipx) * K(range);
+              step_plane_defined = true;
+              st3(rp, RT_STEP_PLANE, step_plane);
+            } else {
               step_plane_defined = false;
             }
           }

@@ -348,6 +348,7 @@ struct shc_engine {
   int* i_planes = nullptr;
   int* d_flags = nullptr;
   const float* d_efforts = nullptr;
+  const float* d_step_planes = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t copy = nullptr;                       // D2H of shc_step_host, behind the tile-range kernels
   cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -739,6 +740,13 @@ int shc_set_joint_efforts(shc_engine* e, const float* efforts_dev) {
   return SHC_OK;
 }
 
+int shc_set_tip_step_planes(shc_engine* e, const float* step_planes_dev) {
+  if (!e) return fail(SHC_E_INVALID, "null engine");
+  if (step_planes_dev != e->d_step_planes) drop_graphs(e);
+  e->d_step_planes = step_planes_dev;
+  return SHC_OK;
+}
+
 int shc_get_state(shc_engine* e, shc_robot_state* out, size_t n_records) {
   if (!e || !out || n_records != (size_t)e->n) return fail(SHC_E_INVALID, "shc_get_state: need n_robots records");
   CUDA_TRY(cudaSetDevice(e->device));
@@ -796,7 +804,7 @@ int shc_set_state(shc_engine* e, const shc_robot_state* in, size_t n_records) {
 
 static StepIO make_io(shc_engine* e, const float* cmd, const float* imu, const float* tip_force, const float* manual, float* joints_out) {
   StepIO io;
-  io.cmd = cmd; io.imu = imu; io.tip_force = tip_force; io.manual = manual; io.efforts = e->d_efforts;
+  io.cmd = cmd; io.imu = imu; io.tip_force = tip_force; io.manual = manual; io.efforts = e->d_efforts; io.step_planes = e->d_step_planes;
   io.joints_out = joints_out;
   io.tile_begin = 0;
   io.tile_end = (e->n + 31) / 32;

@@ -48,6 +48,7 @@ def lib():
         L.shc_startup_begin.argtypes = [vp, vp]
         L.shc_startup_step.argtypes = [vp, vp, vp]
         L.shc_direct_startup.argtypes = [vp, vp, vp, vp]
+        L.shc_set_tip_step_planes.argtypes = [vp, vp]
         L.shc_step_to_new_stance.argtypes = [vp, vp, vp, vp]
         L.shc_sequence_reset.argtypes = [vp]
         L.shc_execute_sequence.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int), vp]
@@ -578,6 +579,12 @@ class Engine:
         efforts = self._f32(efforts, (self.n, self.L, self.D))
         self._efforts = efforts
         _check(lib().shc_set_joint_efforts(self._h, _ptr(efforts)))
+
+    def set_tip_step_planes(self, step_planes):
+        """Tip range-sensor readings [N, L, 3] (x, y slopes, z range; z >= 1e9 = no reading) for rough-terrain mode, or None."""
+        step_planes = self._f32(step_planes, (self.n, self.L, 3))
+        self._step_planes = step_planes
+        _check(lib().shc_set_tip_step_planes(self._h, _ptr(step_planes)))
 
     def apply_ik(self, leg_id, q, qd, desired_tip, simulation: bool = True):
         """Stand-alone batched Leg::applyIK in double.  Returns (q, qd, tip, ik_result) as torch tensors."""

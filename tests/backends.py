@@ -26,6 +26,9 @@ class _GpuStepper:
     def set_joint_efforts(self, eff):
         self.eng.set_joint_efforts(None if eff is None else self._dev(eff))
 
+    def set_tip_step_planes(self, sp):
+        self.eng.set_tip_step_planes(None if sp is None else self._dev(sp))
+
     def pack_messages(self, first=0, count=None, measured_joint_positions=None):
         return self.eng.pack_messages(first, count, None if measured_joint_positions is None else self._dev(measured_joint_positions))
 

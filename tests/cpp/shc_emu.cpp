@@ -32,8 +32,8 @@ struct shc_emu {
   std::vector<double> d;
   std::vector<int> i;
   std::vector<int> flags;
-  std::vector<float> efforts;
-  bool have_efforts = false;
+  std::vector<float> efforts, step_planes;
+  bool have_efforts = false, have_step_planes = false;
   // sequences (csrc/shc_sequence.cuh on host planes)
   std::vector<double> seq_origin, tr_origin;
   std::vector<int> seq_count, seq_robot, seq_leg;
@@ -121,6 +121,11 @@ int shc_emu_set_joint_efforts(shc_emu* e, const float* eff) {
   if (eff) e->efforts.assign(eff, eff + (size_t)e->n * e->cfg.leg_count * e->cfg.joint_count);
   return SHC_OK;
 }
+int shc_emu_set_tip_step_planes(shc_emu* e, const float* sp) {
+  e->have_step_planes = sp != nullptr;
+  if (sp) e->step_planes.assign(sp, sp + (size_t)e->n * e->cfg.leg_count * 3);
+  return SHC_OK;
+}
 int shc_emu_get_status_flags(shc_emu* e, int* out) {
   if (!(e->options & SHC_OPT_STATUS_FLAGS)) return fail(SHC_E_INVALID, "status flags are not enabled");
   for (int r = 0; r < e->n; ++r) out[r] = e->flags[r];
@@ -149,6 +154,7 @@ int shc_emu_step(shc_emu* e, const float* cmd, const float* imu, const float* ti
   std::memset(&io, 0, sizeof(io));
   io.cmd = cmd; io.imu = imu; io.tip_force = tip_force; io.manual = manual;
   io.efforts = e->have_efforts ? e->efforts.data() : nullptr;
+  io.step_planes = e->have_step_planes ? e->step_planes.data() : nullptr;
   io.joints_out = joints_out;
   io.tile_begin = 0;
   io.tile_end = (e->n + 31) / 32;

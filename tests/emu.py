@@ -46,6 +46,7 @@ def lib():
         L.shc_emu_set_options.argtypes = [vp, C.c_int]
         L.shc_emu_set_pose_reset_mode.argtypes = [vp, C.c_int]
         L.shc_emu_set_joint_efforts.argtypes = [vp, fp]
+        L.shc_emu_set_tip_step_planes.argtypes = [vp, fp]
         L.shc_emu_get_status_flags.argtypes = [vp, C.POINTER(C.c_int)]
         L.shc_emu_get_state.argtypes = [vp, C.POINTER(ShcRobotState), C.c_size_t]
         L.shc_emu_set_state.argtypes = [vp, C.POINTER(ShcRobotState), C.c_size_t]
@@ -108,6 +109,10 @@ class EmuEngine:
     def set_joint_efforts(self, eff):
         a, p = _f32(eff, (self.n, self.L, self.D))
         _check(lib().shc_emu_set_joint_efforts(self._h, p))
+
+    def set_tip_step_planes(self, sp):
+        a, p = _f32(sp, (self.n, self.L, 3))
+        _check(lib().shc_emu_set_tip_step_planes(self._h, p))
 
     def status_flags(self):
         out = np.empty(self.n, dtype=np.int32)

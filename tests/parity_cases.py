@@ -428,11 +428,13 @@ def rough_terrain(backend, oracle, n=48, cycles=420):
     on ground contact (:1110-1112, 1282-1289); the walk plane, its pose and the swing clearance follow the default tips
     (non-flat plane paths of updateWalkPlane / updateWalkPlanePose).  One cycle from identical state to 1e-11 on every field,
     then a free-running rollout.  The start-up constants are the oracle's (layered workspace)."""
-    for cfg, L, D, full in ((hexapod_config("tripod_gait", rough_terrain_mode=1, step_depth=0.01), 6, 3, False),
-                            (hexapod_config("wave_gait", rough_terrain_mode=1, step_depth=0.02, force_normal_touchdown=1), 6, 3, False),
-                            (octopod_config("ripple_gait", rough_terrain_mode=1, step_depth=0.01), 8, 5, True)):
+    for cfg, L, D, full, ranges in ((hexapod_config("tripod_gait", rough_terrain_mode=1, step_depth=0.01), 6, 3, False, False),
+                                    (hexapod_config("wave_gait", rough_terrain_mode=1, step_depth=0.02, force_normal_touchdown=1), 6, 3, False, False),
+                                    (hexapod_config("ripple_gait", rough_terrain_mode=1, step_depth=0.01), 6, 3, False, True),
+                                    (octopod_config("ripple_gait", rough_terrain_mode=1, step_depth=0.01), 8, 5, True, False)):
         ob = oracle.OracleBatch(cfg, n)
         eng = backend.engine(cfg, n, startup=ob.startup())
+        step_planes = np.zeros((n, L, 3), dtype=np.float32)
         cs = CommandStream(n, min_len=40, max_len=160)
         ims = ImuStream(n) if full else None
         rng = np.random.default_rng(17)
@@ -448,16 +450,31 @@ def rough_terrain(backend, oracle, n=48, cycles=420):
                     force[r, l] = (rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5), rng.uniform(2.0, 8.0)) if (g.step_state != 0 or early) else \
                                   (0.0, 0.0, rng.uniform(0.0, 0.05))
 
+        def range_readings(st, c):
+            # tip range sensors (TipState.step_plane): a reading while the tip is near the ground (stance, late swing), none
+            # ("UNASSIGNED") high in the swing; the wrench path is off in this variant
+            for r in range(n):
+                for l in range(L):
+                    g = st[r].legs[l]
+                    near = g.step_state != 0 or g.swing_progress > 0.5 + 0.3 * ((r * 5 + l + c // 40) % 7) / 7.0
+                    step_planes[r, l] = (rng.uniform(-0.05, 0.05), rng.uniform(-0.05, 0.05), rng.uniform(0.0, 0.03)) if near else (0.0, 0.0, 2.0e9)
+            eng.set_tip_step_planes(step_planes)
+            ob.set_tip_step_planes(step_planes)
+
         for c in range(cycles):
             cmd = cs.next()
             imu = ims.next(cfg.time_delta) if ims else None
             st = ob.get_state()
-            contact_forces(st, c)
+            if ranges:
+                range_readings(st, c)
+            else:
+                contact_forces(st, c)
             sample = c % 3 == 2
+            fin = None if ranges else force
             if sample:
                 eng.set_state(st)
-                j = eng.step(cmd, imu, force)
-            ob.step(cmd.astype(np.float64), None if imu is None else imu.astype(np.float64), force.astype(np.float64), threads=4)
+                j = eng.step(cmd, imu, fin)
+            ob.step(cmd.astype(np.float64), None if imu is None else imu.astype(np.float64), None if ranges else force.astype(np.float64), threads=4)
             if sample:
                 so = ob.get_state()
                 assert np.abs(j - ob.joints()).max() <= 1.3e-7, c  # float32 output rounding of angles beyond 2 rad (half an ulp = 1.2e-7)
@@ -465,15 +482,18 @@ def rough_terrain(backend, oracle, n=48, cycles=420):
                 contacts += sum(1 for s in so for l in range(L) if s.legs[l].step_plane_defined and s.legs[l].step_state == 0)
                 planes += sum(1 for s in so if abs(s.walk_plane_normal[2] - 1.0) > 1e-9)
         assert contacts > 0 and planes > 0, (contacts, planes)  # swings really ended on contact, the walk plane really tilted
-        print(f"[rough-terrain] {L}x{D}: swinging leg-cycles in ground contact {contacts}, robot-cycles with a tilted walk plane {planes}")
+        print(f"[rough-terrain] {L}x{D}{' (range sensors)' if ranges else ''}: swinging leg-cycles in ground contact {contacts}, robot-cycles with a tilted walk plane {planes}")
         eng.set_state(ob.get_state())
         errs = JointErrors()
         for c in range(150):
             cmd = cs.next()
             imu = ims.next(cfg.time_delta) if ims else None
-            contact_forces(ob.get_state(), cycles + c)
-            j = eng.step(cmd, imu, force)
-            ob.step(cmd.astype(np.float64), None if imu is None else imu.astype(np.float64), force.astype(np.float64), threads=4)
+            if ranges:
+                range_readings(ob.get_state(), cycles + c)
+            else:
+                contact_forces(ob.get_state(), cycles + c)
+            j = eng.step(cmd, imu, None if ranges else force)
+            ob.step(cmd.astype(np.float64), None if imu is None else imu.astype(np.float64), None if ranges else force.astype(np.float64), threads=4)
             errs.add(np.abs(j - ob.joints()))
         errs.check(max_fraction=5e-3, label=f"rough terrain {L}x{D} free-running")
         assert_state_close(eng.get_state(), ob.get_state(), L, D, 1e-7, skip=JOINT_FIELDS)
