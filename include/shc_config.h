@@ -29,7 +29,8 @@ typedef struct shc_config {
   double time_delta;
   int manual_posing;
   int auto_posing;
-  int rough_terrain_mode; /* layered workspace, default-tip updates, touchdown detection and target shifting */
+  int rough_terrain_mode; /* layered workspace, default-tip updates, touchdown detection (tip forces / range sensors),
+                           * external targets and defaults, target shifting */
   int admittance_control;
   int inclination_posing;
   int imu_posing;

@@ -58,6 +58,19 @@ typedef struct shc_leg_state {
   double step_plane_position[3];    /* Leg::step_plane_pose_.position_ (model.h:529): the tip pose at touchdown, base_link frame */
   int step_plane_defined;           /* step_plane_pose_ != Pose::Undefined() */
   int touchdown_detection;          /* LegStepper::touchdown_detection_ (walk_controller.h:495): tip state inputs have arrived */
+  /* externally requested swing target and default tip pose (LegStepper::external_target_ / external_default_,
+   * walk_controller.h:36-44, set by targetTipPoseCallback state_controller.cpp:1700-1760; `transform` = the robot's movement
+   * since the request, which the reference refreshes from the tf tree every loop, :703-750): rough-terrain mode only.
+   * Poses are px py pz qw qx qy qz. */
+  double external_target_pose[7];
+  double external_target_transform[7];
+  double external_target_clearance;  /* ExternalTarget::swing_clearance_ */
+  int external_target_defined;       /* cleared by the stepper at the start of the next stance */
+  int external_target_odom_frame;    /* frame_id_ == "odom_ideal": the target is led by the odometry until the swing ends */
+  double external_default_pose[7];
+  double external_default_transform[7];
+  int external_default_defined;
+  int pad1;
   /* outputs of the last cycle (recomputed every cycle; not algorithmic state) */
   double model_tip_position[3];     /* Leg::current_tip_pose_.position_ after applyFK (base_link frame) */
   double desired_tip_position[3];   /* Leg::desired_tip_pose_.position_ */

@@ -77,12 +77,23 @@ struct Link {
   double d = 0, theta = 0, r = 0, alpha = 0;
 };
 
+// ExternalTarget (walk_controller.h:36-44).  frame_id_ == "odom_ideal" is kept as a flag; time_ only serves the tf lookup
+// (state_controller.cpp:717-725), whose result the harness supplies as transform_.
+struct ExternalTarget {
+  Pose pose_;
+  double swing_clearance_ = 0.0;
+  bool odom_ideal_frame_ = false;
+  Pose transform_ = Pose::Identity();
+  bool defined_ = false;
+};
+
 // ---- LegStepper (walk_controller.h:286-535) -------------------------------------------------------------------
 struct LegStepper {
   Robot* robot = nullptr;
   Leg* leg_ = nullptr;
   bool at_correct_phase_ = false, completed_first_step_ = false;
   bool touchdown_detection_ = false;  // walk_controller.h:495: set once tip state messages arrive (state_controller.cpp:1640)
+  ExternalTarget external_target_, external_default_;  // walk_controller.h:533-534
   int phase_ = 0, phase_offset_ = 0;
   double step_progress_ = 0.0, swing_progress_ = -1.0, stance_progress_ = -1.0;
   StepState step_state_ = STANCE;

@@ -107,6 +107,14 @@ void exportState(const Robot& r, shc_robot_state* s) {
     o.step_plane_defined = leg.step_plane_pose_ != Pose::Undefined();
     if (o.step_plane_defined) put3(o.step_plane_position, leg.step_plane_pose_.position_);
     o.touchdown_detection = st.touchdown_detection_;
+    putPose(o.external_target_pose, st.external_target_.pose_);
+    putPose(o.external_target_transform, st.external_target_.transform_);
+    o.external_target_clearance = st.external_target_.swing_clearance_;
+    o.external_target_defined = st.external_target_.defined_;
+    o.external_target_odom_frame = st.external_target_.odom_ideal_frame_;
+    putPose(o.external_default_pose, st.external_default_.pose_);
+    putPose(o.external_default_transform, st.external_default_.transform_);
+    o.external_default_defined = st.external_default_.defined_;
     put3(o.model_tip_position, leg.current_tip_pose_.position_);
     put3(o.desired_tip_position, leg.desired_tip_pose_.position_);
     o.ik_result = leg.last_ik_result_;
@@ -178,6 +186,14 @@ void importState(Robot& r, const shc_robot_state* s) {
     leg.virtual_stiffness_ = o.virtual_stiffness;
     leg.poser.negate_auto_pose_ = o.negate_auto_pose != 0;
     st.touchdown_detection_ = o.touchdown_detection != 0;
+    st.external_target_.pose_ = getPose(o.external_target_pose);
+    st.external_target_.transform_ = getPose(o.external_target_transform);
+    st.external_target_.swing_clearance_ = o.external_target_clearance;
+    st.external_target_.defined_ = o.external_target_defined != 0;
+    st.external_target_.odom_ideal_frame_ = o.external_target_odom_frame != 0;
+    st.external_default_.pose_ = getPose(o.external_default_pose);
+    st.external_default_.transform_ = getPose(o.external_default_transform);
+    st.external_default_.defined_ = o.external_default_defined != 0;
     // (the rotation of the step plane pose is never read: walk_controller.cpp:1085-1110 uses its position and whether it is defined)
     leg.step_plane_pose_ = o.step_plane_defined ? Pose(get3(o.step_plane_position), leg.current_tip_pose_.rotation_) : Pose::Undefined();
     // target_tip_pose_.rotation_ is a constant of the configuration (no rough-terrain targets): left as constructed

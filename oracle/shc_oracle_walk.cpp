@@ -522,7 +522,12 @@ Vec3 LegStepper::calculateStanceSpanChange() {  // walk_controller.cpp:949
   return Vec3(0.0, radius * stance_span_modifier, 0.0);
 }
 
-void LegStepper::updateDefaultTipPosition() {  // walk_controller.cpp:984 (no external default: tf2 path is out of scope)
+void LegStepper::updateDefaultTipPosition() {  // walk_controller.cpp:984
+  if (external_default_.defined_) {  // externally requested default, transformed by the robot's movement since the request
+    Pose new_default_tip_pose = external_default_.pose_.removePose(external_default_.transform_);
+    default_tip_pose_ = new_default_tip_pose;
+    return;
+  }
   Vec3 identity_tip_position = identity_tip_pose_.position_;
   identity_tip_position += calculateStanceSpanChange();
   identity_tip_position = robot->default_pose_model_.transformVector(identity_tip_position);
@@ -562,10 +567,17 @@ void LegStepper::updateTipPosition() {  // walk_controller.cpp:1018
       swing_origin_tip_velocity_ = current_tip_velocity_;
       if (rough_terrain_mode) updateDefaultTipPosition();
     }
-    // Update the target to meet the step surface (walk_controller.cpp:1065-1107).  Externally requested targets (:1068-1078)
-    // need tf2 transforms and are out of scope: external_target_.defined_ is never set.
+    // Update the target to the externally requested pose or to meet the step surface (walk_controller.cpp:1065-1107)
     if (rough_terrain_mode) {
-      if (touchdown_detection_) {
+      if (external_target_.defined_) {
+        target_tip_pose_ = external_target_.pose_.removePose(external_target_.transform_);
+        swing_clearance_ = swing_clearance_.normalized() * external_target_.swing_clearance_;
+        if (external_target_.odom_ideal_frame_) {  // add lead to compensate for the moving target
+          double time_to_swing_end = (swing_iterations - iteration) * time_delta;
+          Vec3 target_lead = robot->calculateOdometry(time_to_swing_end).position_;
+          target_tip_pose_.position_ -= target_lead;
+        }
+      } else if (touchdown_detection_) {
         Pose step_plane_pose = leg_->step_plane_pose_;
         if (step_plane_pose != Pose::Undefined()) {  // proactive: the step plane is known
           Vec3 step_plane_position = step_plane_pose.position_ - leg_->current_tip_pose_.position_;
@@ -598,6 +610,7 @@ void LegStepper::updateTipPosition() {  // walk_controller.cpp:1018
     int iteration = mod(phase_ + (step.period_ - modified_stance_start), step.period_) + 1;
     if (iteration == 1) {
       stance_origin_tip_position_ = current_tip_pose_.position_;
+      external_target_.defined_ = false;  // reset external target after every swing period (:1159)
       if (rough_terrain_mode) updateDefaultTipPosition();
     }
     double stride_scaler = double(modified_stance_period) / (mod(step.stance_end_ - step.stance_start_, step.period_));

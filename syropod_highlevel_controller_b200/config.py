@@ -100,6 +100,10 @@ class ShcLegState(C.Structure):
         ("negate_auto_pose", _i), ("pad0", _i),
         ("tip_rotation", _d * 4), ("origin_tip_rotation", _d * 4), ("target_tip_rotation", _d * 4),
         ("step_plane_position", _d * 3), ("step_plane_defined", _i), ("touchdown_detection", _i),
+        ("external_target_pose", _d * 7), ("external_target_transform", _d * 7), ("external_target_clearance", _d),
+        ("external_target_defined", _i), ("external_target_odom_frame", _i),
+        ("external_default_pose", _d * 7), ("external_default_transform", _d * 7),
+        ("external_default_defined", _i), ("pad1", _i),
         ("model_tip_position", _d * 3), ("desired_tip_position", _d * 3), ("ik_result", _d),
     ]
 

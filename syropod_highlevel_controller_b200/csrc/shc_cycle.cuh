@@ -1218,6 +1218,7 @@ template <class P, int D, int MODE> struct Cycle {
       Q4<K> tr_cur{K(0), K(0), K(0), K(0)}, tr_origin{K(0), K(0), K(0), K(0)};
       Chain<K, D> ch;
       bool step_plane_defined = false, touchdown_detection = false;
+      bool ext_target = false, ext_odom = false, ext_default = false;  // external_target_ / external_default_ (rough terrain)
       V3<K> step_plane{K(0), K(0), K(0)}, model_tip{K(0), K(0), K(0)};
       if constexpr (EXT) {
         leg_chain<K, D>(lk, q, ch);
@@ -1231,6 +1232,9 @@ template <class P, int D, int MODE> struct Cycle {
           model_tip = t1_rotate(lk, ch.tip) + V3<K>{lk.t1p[0], lk.t1p[1], lk.t1p[2]};
           step_plane_defined = (bits >> LB_STEP_PLANE) & 1;
           touchdown_detection = (bits >> LB_TOUCHDOWN) & 1;
+          ext_target = (bits >> LB_EXT_TARGET) & 1;
+          ext_odom = (bits >> LB_EXT_ODOM) & 1;
+          ext_default = (bits >> LB_EXT_DEFAULT) & 1;
           S* __restrict__ rp = sl + ci.roughS_leg * 32;
           if (step_plane_defined) step_plane = ld3K(rp, RT_STEP_PLANE);
           if (io.tip_force) {
@@ -1327,12 +1331,18 @@ template <class P, int D, int MODE> struct Cycle {
             bool at_target = norm(err) < 0.01;  // TIP_TOLERANCE (pose_controller.h:19)
             if (at_target || rtd) {
               rtd = 0;
-              // LegStepper::updateDefaultTipPosition (:984), no external default
+              // LegStepper::updateDefaultTipPosition (:984)
               V3<K> idt{lk.identity_x, lk.identity_y + lk.span_dy, K(0)};
               idt = pose_transform(ldPose(sp, RS_WPP), idt);  // Model::default_pose_ = walk_plane_pose_ (pose_controller.cpp:819)
               V3<K> sto = ld3K(sl, LS::STO_P);
               V3<K> proj = projection(sto - idt, cvt<K>(wpn_l));
               def = cvt<T>(idt + proj);
+              if constexpr (EXT) {
+                if (ext_default) {  // an externally requested default, moved back by the robot's motion since the request (:988-992)
+                  const S* __restrict__ rp = sl + ci.roughS_leg * 32;
+                  def = cvt<T>(pose_transform(ldPose(rp, RT_ED_POSE), -ld3K(rp, RT_ED_TF)));
+                }
+              }
               st3(sl, LS::DEF, def);
               def_changed = true;
               step_state = STEP_FORCE_STOP;
@@ -1353,6 +1363,12 @@ template <class P, int D, int MODE> struct Cycle {
           V3<K> idt{lk.identity_x, lk.identity_y + lk.span_dy, K(0)};
           idt = pose_transform(ldPose(sp, RS_WPP), idt);
           def = cvt<T>(idt + projection(stance_origin - idt, normal));
+          if constexpr (EXT) {
+            if (ext_default) {  // externally requested default (:988-992): pose_.removePose(transform_)
+              const S* __restrict__ rp = sl + ci.roughS_leg * 32;
+              def = cvt<T>(pose_transform(ldPose(rp, RT_ED_POSE), -ld3K(rp, RT_ED_TF)));
+            }
+          }
           st3(sl, LS::DEF, def);
           def_changed = true;
         };
@@ -1399,13 +1415,27 @@ template <class P, int D, int MODE> struct Cycle {
               swo_v = ld3T(ss, LS::SWO_V);
             }
             bool ground_contact = false;
+            T ext_clearance = T(-1);  // >= 0: an external target scales the swing clearance (:1071)
             if constexpr (EXT) {
               if (f_rough) {
                 // the leg's walk_plane_normal_ is the walker's as of this cycle's start (updateStride above)
                 const V3<K> leg_wpn = ld3K(sp, RS_WPN);
                 if (iteration == 1) update_default_tip(ld3K(sl, LS::STO_P), leg_wpn);  // (:1058-1061)
-                // Target moved to meet the step surface (:1065-1107; externally requested targets need tf2: not built)
-                if (touchdown_detection) {
+                // Target set to the externally requested pose, moved back by the robot's motion since the request (the caller
+                // refreshes `transform` as the reference does from the tf tree) and, in the odometry frame, led by the distance
+                // the body will cover until the swing ends (:1068-1078) — else moved to meet the step surface (:1081-1100)
+                if (ext_target) {
+                  const S* __restrict__ rp = sl + ci.roughS_leg * 32;
+                  V3<K> t = pose_transform(ldPose(rp, RT_ET_POSE), -ld3K(rp, RT_ET_TF));
+                  ext_clearance = T(rp[(RT_ET_CLR) * 32]);
+                  if (ext_odom) {
+                    const K time_to_swing_end = K(ci.swing_iterations - iteration) * ck.dt;
+                    t.x -= K(bvx) * time_to_swing_end;
+                    t.y -= K(bvy) * time_to_swing_end;
+                  }
+                  tgt = cvt<T>(t);
+                  st3(sl, LS::TGT, tgt);
+                } else if (touchdown_detection) {
                   if (step_plane_defined) {  // proactive: the step plane is known
                     const V3<K> target_tip_position = V3<K>{K(tipx), K(tipy), K(tipz)} + (step_plane - model_tip);
                     tgt = tgt + cvt<T>(projection(target_tip_position - cvt<K>(tgt), leg_wpn));
@@ -1420,6 +1450,9 @@ template <class P, int D, int MODE> struct Cycle {
             // Control nodes relative to the swing origin (the origin cancels in the differences).
             V3<T> clr{T(0), T(0), ct.swing_height};
             if (!plane_flat) clr = normalized(ld3T(sp, RS_WPN)) * ct.swing_height;
+            if constexpr (EXT) {
+              if (ext_clearance >= T(0)) clr = normalized(clr) * ext_clearance;
+            }
             V3<T> tr = tgt - swo_p;
             V3<T> mid{tr.x * T(0.5) + clr.x, tr.y * T(0.5) + clr.y + lt.ysign * ct.swing_width, max_(T(0), tr.z) + clr.z};
             V3<T> sep1 = swo_v * (T(0.25) * (ct.dt / ct.swing_dt));
@@ -1456,6 +1489,7 @@ template <class P, int D, int MODE> struct Cycle {
             iteration += iteration < 0 ? ci.period + 1 : 1;
             if (iteration == 1) {
               st3(sl, LS::STO_P, V3<T>{T(tipx), T(tipy), T(tipz)});
+              ext_target = false;  // external_target_.defined_ = false after every swing period (:1159)
               if constexpr (EXT) {
                 if (f_rough) update_default_tip(V3<K>{K(tipx), K(tipy), K(tipz)}, ld3K(sp, RS_WPN));  // (:1160-1163)
               }
@@ -1539,7 +1573,8 @@ template <class P, int D, int MODE> struct Cycle {
       SHC_STAMP(6 + 3 * l);
       bits = (phase & 0xffff) | (step_state << 16) | ((at_correct ? 1 : 0) << 18) | ((completed ? 1 : 0) << 19) |
              ((negate ? 1 : 0) << 20) | ((plane_saved ? 1 : 0) << LB_PLANE_SAVED) | ((step_plane_defined ? 1 : 0) << LB_STEP_PLANE) |
-             ((touchdown_detection ? 1 : 0) << LB_TOUCHDOWN);
+             ((touchdown_detection ? 1 : 0) << LB_TOUCHDOWN) | ((ext_target ? 1 : 0) << LB_EXT_TARGET) |
+             ((ext_odom ? 1 : 0) << LB_EXT_ODOM) | ((ext_default ? 1 : 0) << LB_EXT_DEFAULT);
       prog = (swing_num & 0xffff) | ((stance_num & 0xffff) << 16);
       il[(LI_BITS) * 32] = bits;
       il[(LI_PROG) * 32] = prog;

@@ -34,7 +34,10 @@ enum : int { TA_POSE = 0 /*tip_align_pose_ (7)*/, TA_ORIGIN = 7 /*origin_tip_ali
 // offS_leg + leg * strideS_leg + tipS_leg: quaternions w x y z, all zero = UNDEFINED_ROTATION
 enum : int { TR_CUR = 0 /*LegStepper::current_tip_pose_.rotation_*/, TR_ORIGIN = 4 /*origin_tip_pose_.rotation_*/, TR_COUNT = 8 };
 // optional per-leg rough-terrain block (rough_terrain_mode), relative to offS_leg + leg * strideS_leg + roughS_leg
-enum : int { RT_STEP_PLANE = 0 /*Leg::step_plane_pose_.position_ (3), base_link frame*/, RT_COUNT = 3 };
+enum : int { RT_STEP_PLANE = 0 /*Leg::step_plane_pose_.position_ (3), base_link frame*/,
+             RT_ET_POSE = 3 /*external_target_.pose_ (7)*/, RT_ET_TF = 10 /*external_target_.transform_ (7)*/,
+             RT_ET_CLR = 17 /*external_target_.swing_clearance_*/, RT_ED_POSE = 18 /*external_default_.pose_ (7)*/,
+             RT_ED_TF = 25 /*external_default_.transform_ (7)*/, RT_COUNT = 32 };
 // tip_mode of an engine
 enum : int { TIP_NONE = 0, TIP_ALIGN_POSE = 1, TIP_ROTATION = 2 };
 
@@ -91,8 +94,9 @@ enum : int { LI_BITS = 0, LI_PROG = 1, LI_COUNT = 2 };
 enum : int { RB_PLANE_CHANGED = 15, RB_STATUS_SHIFT = 16, RB_STATUS_MASK = 0xfff, RB_MANUAL_IDENTITY = 30, RB_PLANE_STALE = 31 };
 // LI_BITS: phase[0:16) step_state[16:18) at_correct_phase[18] completed_first_step[19] negate_auto_pose[20]
 //          the leg's saved walk plane (WP / WPN planes) equals the walker's plane of the previous cycle's start [21]
-//          rough-terrain mode: step_plane_pose_ is defined [22]  touchdown_detection_ [23]
-enum : int { LB_PLANE_SAVED = 21, LB_STEP_PLANE = 22, LB_TOUCHDOWN = 23 };
+//          rough-terrain mode: step_plane_pose_ is defined [22]  touchdown_detection_ [23]  external_target_.defined_ [24]
+//          external target in the odom_ideal frame [25]  external_default_.defined_ [26]
+enum : int { LB_PLANE_SAVED = 21, LB_STEP_PLANE = 22, LB_TOUCHDOWN = 23, LB_EXT_TARGET = 24, LB_EXT_ODOM = 25, LB_EXT_DEFAULT = 26 };
 // LI_PROG: swing progress numerator (int16, -1 = "-1.0") | stance progress numerator (int16) << 16
 //          progress = numerator / swing_period (resp. stance_period): walk_controller.cpp:878-896 divides two ints
 //          converted to double, so keeping the numerator makes the value exact in every precision.

@@ -175,13 +175,24 @@ template <class E> void pack(const E* e, const shc_robot_state* in, size_t n, Ho
           S(sb + ci.tipS_leg + TR_CUR + k, r) = g.tip_rotation[k];
           S(sb + ci.tipS_leg + TR_ORIGIN + k, r) = g.origin_tip_rotation[k];
         }
-      if (ci.rough_terrain)
+      if (ci.rough_terrain) {
         for (int k = 0; k < 3; ++k) S(sb + ci.roughS_leg + RT_STEP_PLANE + k, r) = g.step_plane_position[k];
+        for (int k = 0; k < 7; ++k) {
+          S(sb + ci.roughS_leg + RT_ET_POSE + k, r) = g.external_target_pose[k];
+          S(sb + ci.roughS_leg + RT_ET_TF + k, r) = g.external_target_transform[k];
+          S(sb + ci.roughS_leg + RT_ED_POSE + k, r) = g.external_default_pose[k];
+          S(sb + ci.roughS_leg + RT_ED_TF + k, r) = g.external_default_transform[k];
+        }
+        S(sb + ci.roughS_leg + RT_ET_CLR, r) = g.external_target_clearance;
+      }
       const int ib = ci.offI_leg + l * ci.strideI_leg;
       I(ib + LI_BITS, r) = (g.phase & 0xffff) | ((g.step_state & 3) << 16) | ((g.at_correct_phase ? 1 : 0) << 18) |
                            ((g.completed_first_step ? 1 : 0) << 19) | ((g.negate_auto_pose ? 1 : 0) << 20) |
                            ((ci.rough_terrain && g.step_plane_defined ? 1 : 0) << LB_STEP_PLANE) |
-                           ((ci.rough_terrain && g.touchdown_detection ? 1 : 0) << LB_TOUCHDOWN);
+                           ((ci.rough_terrain && g.touchdown_detection ? 1 : 0) << LB_TOUCHDOWN) |
+                           ((ci.rough_terrain && g.external_target_defined ? 1 : 0) << LB_EXT_TARGET) |
+                           ((ci.rough_terrain && g.external_target_odom_frame ? 1 : 0) << LB_EXT_ODOM) |
+                           ((ci.rough_terrain && g.external_default_defined ? 1 : 0) << LB_EXT_DEFAULT);
       int sn = prog_num(g.swing_progress, ci.swing_period), tn = prog_num(g.stance_progress, ci.stance_period);
       I(ib + LI_PROG, r) = (sn & 0xffff) | ((tn & 0xffff) << 16);
     }
@@ -308,6 +319,16 @@ template <int D, class E> void unpack(const E* e, const HostPlanes& h, shc_robot
         g.touchdown_detection = (b >> LB_TOUCHDOWN) & 1;
         if (g.step_plane_defined)
           for (int k = 0; k < 3; ++k) g.step_plane_position[k] = S(sb + ci.roughS_leg + RT_STEP_PLANE + k, r);
+        g.external_target_defined = (b >> LB_EXT_TARGET) & 1;
+        g.external_target_odom_frame = (b >> LB_EXT_ODOM) & 1;
+        g.external_default_defined = (b >> LB_EXT_DEFAULT) & 1;
+        for (int k = 0; k < 7; ++k) {
+          g.external_target_pose[k] = S(sb + ci.roughS_leg + RT_ET_POSE + k, r);
+          g.external_target_transform[k] = S(sb + ci.roughS_leg + RT_ET_TF + k, r);
+          g.external_default_pose[k] = S(sb + ci.roughS_leg + RT_ED_POSE + k, r);
+          g.external_default_transform[k] = S(sb + ci.roughS_leg + RT_ED_TF + k, r);
+        }
+        g.external_target_clearance = S(sb + ci.roughS_leg + RT_ET_CLR, r);
       }
       int sn = (int)(short)(pg & 0xffff), tn = (int)(short)((pg >> 16) & 0xffff);
       g.swing_progress = sn < 0 ? -1.0 : (double)sn / (double)ci.swing_period;

@@ -16,8 +16,10 @@ STATE_FIELDS_LEG = ("tip_position", "tip_velocity", "swing_origin_position", "st
 ROTATION_FIELDS_LEG = ("tip_rotation", "origin_tip_rotation", "target_tip_rotation")
 INT_FIELDS_LEG = ("phase", "step_state", "at_correct_phase", "completed_first_step", "negate_auto_pose")
 # rough-terrain state: compared when the record under test is in touchdown-detection mode
-ROUGH_FIELDS_LEG = ("step_plane_position",)
-ROUGH_INT_FIELDS_LEG = ("step_plane_defined", "touchdown_detection")
+ROUGH_FIELDS_LEG = ("step_plane_position", "external_target_pose", "external_target_transform", "external_target_clearance",
+                    "external_default_pose", "external_default_transform")
+ROUGH_INT_FIELDS_LEG = ("step_plane_defined", "touchdown_detection", "external_target_defined", "external_target_odom_frame",
+                        "external_default_defined")
 
 
 def state_diff(se, so, L, D):

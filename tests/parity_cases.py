@@ -428,10 +428,12 @@ def rough_terrain(backend, oracle, n=48, cycles=420):
     on ground contact (:1110-1112, 1282-1289); the walk plane, its pose and the swing clearance follow the default tips
     (non-flat plane paths of updateWalkPlane / updateWalkPlanePose).  One cycle from identical state to 1e-11 on every field,
     then a free-running rollout.  The start-up constants are the oracle's (layered workspace)."""
-    for cfg, L, D, full, ranges in ((hexapod_config("tripod_gait", rough_terrain_mode=1, step_depth=0.01), 6, 3, False, False),
-                                    (hexapod_config("wave_gait", rough_terrain_mode=1, step_depth=0.02, force_normal_touchdown=1), 6, 3, False, False),
-                                    (hexapod_config("ripple_gait", rough_terrain_mode=1, step_depth=0.01), 6, 3, False, True),
-                                    (octopod_config("ripple_gait", rough_terrain_mode=1, step_depth=0.01), 8, 5, True, False)):
+    for cfg, L, D, full, ranges, external in (
+            (hexapod_config("tripod_gait", rough_terrain_mode=1, step_depth=0.01), 6, 3, False, False, False),
+            (hexapod_config("wave_gait", rough_terrain_mode=1, step_depth=0.02, force_normal_touchdown=1), 6, 3, False, False, False),
+            (hexapod_config("ripple_gait", rough_terrain_mode=1, step_depth=0.01), 6, 3, False, True, False),
+            (hexapod_config("amble_gait", rough_terrain_mode=1, step_depth=0.01), 6, 3, False, False, True),
+            (octopod_config("ripple_gait", rough_terrain_mode=1, step_depth=0.01), 8, 5, True, False, False)):
         ob = oracle.OracleBatch(cfg, n)
         eng = backend.engine(cfg, n, startup=ob.startup())
         step_planes = np.zeros((n, L, 3), dtype=np.float32)
@@ -461,10 +463,39 @@ def rough_terrain(backend, oracle, n=48, cycles=420):
             eng.set_tip_step_planes(step_planes)
             ob.set_tip_step_planes(step_planes)
 
+        def external_requests(c):
+            # externally requested swing targets and default tip poses (targetTipPoseCallback, state_controller.cpp:1700-1760):
+            # every 40 cycles a third of the legs get a target near their own and a fifth a new default; `transform` stands
+            # for the robot's movement since the request, which the reference reads from the tf tree every loop (:703-750)
+            st = ob.get_state()
+            for r in range(n):
+                for l in range(L):
+                    g = st[r].legs[l]
+                    pick = (r * 11 + l * 5 + c // 40) % 15
+                    if pick < 5:
+                        tgt = np.array(list(g.target_tip_position)) + rng.uniform(-0.015, 0.015, 3)
+                        g.external_target_pose[:] = list(tgt) + [1.0, 0.0, 0.0, 0.0]
+                        g.external_target_transform[:] = list(rng.uniform(-0.004, 0.004, 3)) + [1.0, 0.0, 0.0, 0.0]
+                        g.external_target_clearance = float(rng.uniform(0.01, 0.03))
+                        g.external_target_defined, g.external_target_odom_frame = 1, int(pick % 2)
+                    if pick in (7, 8, 9):
+                        dft = np.array(list(g.default_tip_position)) + rng.uniform(-0.01, 0.01, 3)
+                        g.external_default_pose[:] = list(dft) + [1.0, 0.0, 0.0, 0.0]
+                        g.external_default_transform[:] = list(rng.uniform(-0.003, 0.003, 3)) + [1.0, 0.0, 0.0, 0.0]
+                        g.external_default_defined = 1
+                    elif pick == 10:
+                        g.external_default_defined = 0
+            ob.set_state(st)
+
+        external_used = 0
         for c in range(cycles):
             cmd = cs.next()
             imu = ims.next(cfg.time_delta) if ims else None
+            if external and c % 40 == 20:
+                external_requests(c)
             st = ob.get_state()
+            if external:
+                external_used += sum(1 for s_ in st for l in range(L) if s_.legs[l].external_target_defined and s_.legs[l].step_state == 0)
             if ranges:
                 range_readings(st, c)
             else:
@@ -482,7 +513,8 @@ def rough_terrain(backend, oracle, n=48, cycles=420):
                 contacts += sum(1 for s in so for l in range(L) if s.legs[l].step_plane_defined and s.legs[l].step_state == 0)
                 planes += sum(1 for s in so if abs(s.walk_plane_normal[2] - 1.0) > 1e-9)
         assert contacts > 0 and planes > 0, (contacts, planes)  # swings really ended on contact, the walk plane really tilted
-        print(f"[rough-terrain] {L}x{D}{' (range sensors)' if ranges else ''}: swinging leg-cycles in ground contact {contacts}, robot-cycles with a tilted walk plane {planes}")
+        assert not external or external_used > 0  # swings really ran towards external targets
+        print(f"[rough-terrain] {L}x{D}{' (range sensors)' if ranges else ''}{f' (external targets: {external_used} swinging leg-cycles)' if external else ''}: swinging leg-cycles in ground contact {contacts}, robot-cycles with a tilted walk plane {planes}")
         eng.set_state(ob.get_state())
         errs = JointErrors()
         for c in range(150):
