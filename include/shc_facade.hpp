@@ -412,9 +412,19 @@ inline Pose Model::getCurrentPose() { return Pose(b_->state(robot_).current_pose
 inline void Model::setImuData(const Quaterniond& q, const Vector3d& acc, const Vector3d& gyro) { b_->setImu(robot_, q, acc, gyro); }
 inline void Model::updateModel() { b_->arrive(robot_); }
 
-inline Pose LegStepper::getCurrentTipPose() { Pose p; p.position_ = Vector3d(b_->state(robot_).legs[leg_].tip_position); p.rotation_ = Quaterniond(0, 0, 0, 0); return p; }
+// (tip rotations are all zero = UNDEFINED_ROTATION unless gravity_aligned_tips is live on legs of more than three joints)
+inline Pose LegStepper::getCurrentTipPose() {
+  const shc_leg_state& g = b_->state(robot_).legs[leg_];
+  Pose p; p.position_ = Vector3d(g.tip_position); p.rotation_ = Quaterniond(g.tip_rotation[0], g.tip_rotation[1], g.tip_rotation[2], g.tip_rotation[3]);
+  return p;
+}
 inline Pose LegStepper::getDefaultTipPose() { Pose p; p.position_ = Vector3d(b_->state(robot_).legs[leg_].default_tip_position); p.rotation_ = Quaterniond(0, 0, 0, 0); return p; }
-inline Pose LegStepper::getTargetTipPose() { Pose p; p.position_ = Vector3d(b_->state(robot_).legs[leg_].target_tip_position); p.rotation_ = Quaterniond(0, 0, 0, 0); return p; }
+inline Pose LegStepper::getTargetTipPose() {
+  const shc_leg_state& g = b_->state(robot_).legs[leg_];
+  Pose p; p.position_ = Vector3d(g.target_tip_position);
+  p.rotation_ = Quaterniond(g.target_tip_rotation[0], g.target_tip_rotation[1], g.target_tip_rotation[2], g.target_tip_rotation[3]);
+  return p;
+}
 inline Vector3d LegStepper::getStrideVector() { return Vector3d(b_->state(robot_).legs[leg_].stride_vector); }
 inline Vector3d LegStepper::getWalkPlane() { return Vector3d(b_->state(robot_).legs[leg_].walk_plane); }
 inline Vector3d LegStepper::getWalkPlaneNormal() { return Vector3d(b_->state(robot_).legs[leg_].walk_plane_normal); }
