@@ -86,6 +86,8 @@ int shc_set_state(shc_engine* e, const shc_robot_state* in, size_t n_records);
 /* Records of the robots [first, first + count) only: three small device->host copies however large the batch is (what the
  * facade's per-robot getters use). */
 int shc_get_state_range(shc_engine* e, size_t first, size_t count, shc_robot_state* out);
+/* The records of the robots [first, first + count) replaced; only the tiles of 32 robots that hold them travel. */
+int shc_set_state_range(shc_engine* e, size_t first, size_t count, const shc_robot_state* in);
 /* WalkController::set{LinearSpeed,AngularSpeed,LinearAcceleration,AngularAcceleration}LimitMap (walk_controller.h:126-141):
  * replaces the limit tables getLimit (walk_controller.cpp:414) reads, 9 values each (bearings 0..360 step 45); NULL keeps a
  * table.  From the next cycle on. */

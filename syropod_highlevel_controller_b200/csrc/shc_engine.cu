@@ -490,6 +490,23 @@ int upload(shc_engine* e, const HostPlanes& h) {
   return SHC_OK;
 }
 
+// The tiles [t0, t1) back to the device (h holds exactly those tiles).
+int upload_tiles(shc_engine* e, size_t t0, size_t t1, const HostPlanes& h) {
+  const IntConsts& ci = e->c.i;
+  (void)t1;
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (e->precision == SHC_PRECISION_F64) {
+    CUDA_TRY(cudaMemcpy((double*)e->s_planes + t0 * ci.nS * 32, h.s.data(), h.s.size() * 8, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<float> tmp(h.s.size());
+    for (size_t k = 0; k < tmp.size(); ++k) tmp[k] = (float)h.s[k];
+    CUDA_TRY(cudaMemcpy((float*)e->s_planes + t0 * ci.nS * 32, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice));
+  }
+  CUDA_TRY(cudaMemcpy(e->d_planes + t0 * ci.nD * 32, h.d.data(), h.d.size() * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(e->i_planes + t0 * ci.nI * 32, h.i.data(), h.i.size() * 4, cudaMemcpyHostToDevice));
+  return SHC_OK;
+}
+
 }  // namespace
 
 
@@ -768,6 +785,26 @@ int shc_get_state_range(shc_engine* e, size_t first, size_t count, shc_robot_sta
     unpack<decltype(dtag)::value>(e, h, out, count, first - t0 * 32);
     return SHC_OK;
   });
+}
+
+// The records of the robots [first, first + count) replaced (e.g. one robot's external swing target, its manual pose): only
+// the tiles of 32 robots that hold them travel — read, re-packed with the new records, written back.
+int shc_set_state_range(shc_engine* e, size_t first, size_t count, const shc_robot_state* in) {
+  if (!e || !in || count < 1 || first + count > (size_t)e->n) return fail(SHC_E_INVALID, "shc_set_state_range: range outside the batch");
+  CUDA_TRY(cudaSetDevice(e->device));
+  const size_t t0 = first / 32, t1 = (first + count + 31) / 32, lanes = (t1 - t0) * 32;
+  HostPlanes h;
+  int rc = download_tiles(e, t0, t1, h);
+  if (rc != SHC_OK) return rc;
+  std::vector<shc_robot_state> recs(lanes);
+  rc = dispatch_D(e->cfg.joint_count, [&](auto dtag) -> int {
+    unpack<decltype(dtag)::value>(e, h, recs.data(), lanes, 0);  // (padding lanes of the last tile hold valid robots too)
+    return SHC_OK;
+  });
+  if (rc != SHC_OK) return rc;
+  for (size_t k = 0; k < count; ++k) recs[first - t0 * 32 + k] = in[k];
+  pack(e, recs.data(), lanes, h, lanes);
+  return upload_tiles(e, t0, t1, h);
 }
 
 // WalkController::setLinearSpeedLimitMap / setAngularSpeedLimitMap / setLinearAccelerationLimitMap /

@@ -49,6 +49,7 @@ def lib():
         L.shc_startup_step.argtypes = [vp, vp, vp]
         L.shc_direct_startup.argtypes = [vp, vp, vp, vp]
         L.shc_set_tip_step_planes.argtypes = [vp, vp]
+        L.shc_set_state_range.argtypes = [vp, C.c_size_t, C.c_size_t, C.POINTER(ShcRobotState)]
         L.shc_step_to_new_stance.argtypes = [vp, vp, vp, vp]
         L.shc_sequence_reset.argtypes = [vp]
         L.shc_execute_sequence.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int), vp]
@@ -333,6 +334,10 @@ class Engine:
 
     def set_state(self, arr):
         _check(lib().shc_set_state(self._h, arr, self.n))
+
+    def set_state_range(self, first: int, records):
+        """Replaces the records of the robots [first, first + len(records))."""
+        _check(lib().shc_set_state_range(self._h, first, len(records), records))
 
     def get_state_range(self, first: int, count: int = 1):
         """Records of the robots [first, first + count) only (three small copies, whatever the batch size)."""

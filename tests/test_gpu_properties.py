@@ -108,7 +108,8 @@ def test_state_round_trip_is_idempotent(shc_lib):
 
 
 def test_state_range_and_limit_maps(shc_lib):
-    """shc_get_state_range returns the bytes shc_get_state returns for the same robots (tile boundaries included), and
+    """shc_get_state_range returns the bytes shc_get_state returns for the same robots (tile boundaries included),
+    shc_set_state_range writes ragged robot ranges through their tiles, and
     shc_set_limit_maps (WalkController::set*LimitMap) takes effect from the next cycle: with the linear-speed table halved,
     the body velocity of a full-throttle robot settles at half the original limit."""
     import torch
@@ -123,6 +124,15 @@ def test_state_range_and_limit_maps(shc_lib):
     for first, count in ((0, 1), (31, 2), (32, 32), (500, 77), (999, 1), (0, 1000)):
         part = eng.get_state_range(first, count)
         assert bytes(part) == bytes(full)[first * C.sizeof(full[0]):(first + count) * C.sizeof(full[0])], (first, count)
+    # shc_set_state_range: a second engine takes the first one's state in ragged pieces and ends up in the same state
+    twin = _engine(cfg, n, "f64")
+    for first, count in ((0, 5), (5, 60), (65, 31), (96, 904)):
+        twin.set_state_range(first, eng.get_state_range(first, count))
+    cmd = torch.from_numpy(cs.next()).cuda()
+    assert torch.equal(eng.step(cmd).clone(), twin.step(cmd).clone())
+    st_a, st_b = eng.get_state(), twin.get_state()
+    assert bytes(st_a) == bytes(st_b)
+    twin.close()
     su = eng.startup()
     lim = np.array(list(su.max_linear_speed))
     fwd = torch.tensor([[1.0, 0.0, 0.0]], device="cuda").repeat(n, 1)
