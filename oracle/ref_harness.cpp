@@ -1,0 +1,447 @@
+// oracle/ref_harness.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// extern "C" harness around the REFERENCE'S OWN control code.  oracle/Makefile.ref compiles the reference's unmodified
+// translation units where they lie (/root/reference/src/{state_controller,model,walk_controller,pose_controller,
+// admittance_controller,debug_visualiser}.cpp) against the stand-in headers of oracle/shim/ (ROS, tf2, Eigen and Boost are
+// absent from the image) and links them with this file into oracle/_ref/libshc_ref.so.  Nothing of the reference is
+// copied: this file only
+//   * fills the in-process parameter table the reference's StateController::initParameters reads (from the same
+//     shc_config the CUDA engine and the restated oracle are configured with),
+//   * delivers inputs by calling the reference's own subscriber callbacks (what ros::spinOnce() would do),
+//   * calls StateController::loop() and the reference's publishers, and
+//   * reads the controllers' members back into shc_robot_state / shc_startup records for comparison.
+// It is used by tests/ and by tests/golden/make_ref_golden.py to pin the oracle; the product never
+// loads it.  What it cannot pin is third-party arithmetic: Eigen's and Boost.Odeint's kernels are the stand-ins'.
+#include <cstring>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "ros/ros.h"
+#include "msg_common.h"
+#include "tf2_ros/tf2_common.h"
+#include "dynamic_reconfigure/server.h"
+#include "boost/numeric/odeint.hpp"
+#include "Eigen/Geometry"
+#include "syropod_highlevel_controller/msgs_generated.h"
+
+// the harness reads the controllers' private members (access specifiers do not change the layout)
+#define private public
+#define protected public
+#include "syropod_highlevel_controller/state_controller.h"
+#include "syropod_highlevel_controller/admittance_controller.h"
+#undef private
+#undef protected
+
+#include "../include/shc_config.h"
+#include "../include/shc_msgs.h"
+#include "../include/shc_state.h"
+
+namespace {
+
+std::vector<std::string> legNames(int L) {
+  if (L == 6) return {"AR", "BR", "CR", "CL", "BL", "AL"};
+  if (L == 8) return {"AR", "BR", "CR", "DR", "DL", "CL", "BL", "AL"};
+  std::vector<std::string> v;
+  for (int i = 0; i < L; ++i) v.push_back(std::string("L") + char('A' + i));
+  return v;
+}
+std::vector<std::string> jointNames(int D) {
+  static const char* n[] = {"coxa", "femur", "tibia", "tarsus", "pes", "j6"};
+  std::vector<std::string> v;
+  for (int i = 0; i < D; ++i) v.push_back(n[i]);
+  return v;
+}
+
+std::map<std::string, double> adjustable(double v) { return {{"default", v}, {"min", -1e9}, {"max", 1e9}, {"step", 0.0}}; }
+
+// The reference's rosparam tree (config/default.yaml, gait.yaml, auto_pose.yaml layout) from an shc_config.
+void fillParams(const shc_config& c) {
+  shc_shim::ParamTable& p = shc_shim::params();
+  p.clear();
+  const std::string P = "syropod/parameters/";
+  const int L = c.leg_count, D = c.joint_count;
+  const std::vector<std::string> legs = legNames(L), joints = jointNames(D);
+  p.d[P + "time_delta"] = c.time_delta;
+  p.b[P + "imu_posing"] = c.imu_posing;
+  p.b[P + "auto_posing"] = c.auto_posing;
+  p.b[P + "rough_terrain_mode"] = c.rough_terrain_mode;
+  p.b[P + "manual_posing"] = c.manual_posing;
+  p.b[P + "inclination_posing"] = c.inclination_posing;
+  p.b[P + "admittance_control"] = c.admittance_control;
+  p.b[P + "individual_control_interface"] = false;
+  p.b[P + "combined_control_interface"] = true;
+  p.s[P + "syropod_type"] = "harness";
+  p.vs[P + "leg_id"] = legs;
+  p.vs[P + "joint_id"] = joints;
+  std::vector<std::string> links = {"base"};
+  links.insert(links.end(), joints.begin(), joints.end());
+  p.vs[P + "link_id"] = links;
+  std::map<std::string, int> dof;
+  for (const auto& n : legs) dof[n] = D;
+  p.mi[P + "leg_DOF"] = dof;
+  p.b[P + "clamp_joint_positions"] = c.clamp_joint_positions;
+  p.b[P + "clamp_joint_velocities"] = c.clamp_joint_velocities;
+  p.b[P + "ignore_IK_warnings"] = true;
+  for (int l = 0; l < L; ++l) {
+    p.md[P + legs[l] + "_base_link_parameters"] = {{"d", c.link_d[l][0]}, {"theta", c.link_theta[l][0]}, {"r", c.link_r[l][0]}, {"alpha", c.link_alpha[l][0]}};
+    for (int j = 0; j < D; ++j) {
+      p.md[P + legs[l] + "_" + joints[j] + "_link_parameters"] = {{"d", c.link_d[l][j + 1]}, {"theta", c.link_theta[l][j + 1]}, {"r", c.link_r[l][j + 1]}, {"alpha", c.link_alpha[l][j + 1]}};
+      p.md[P + legs[l] + "_" + joints[j] + "_joint_parameters"] = {{"min", c.joint_min[l][j]}, {"max", c.joint_max[l][j]}, {"offset", c.joint_offset[l][j]}, {"packed", c.joint_packed[l][j]}, {"unpacked", c.joint_unpacked[l][j]}, {"max_vel", c.joint_max_vel[l][j]}};
+    }
+    p.md[P + legs[l] + "_stance_position"] = {{"x", c.stance_x[l]}, {"y", c.stance_y[l]}};
+  }
+  p.s[P + "gait_type"] = "harness_gait";
+  p.d[P + "body_clearance"] = c.body_clearance;
+  p.md[P + "step_frequency"] = adjustable(c.step_frequency);
+  p.md[P + "swing_height"] = adjustable(c.swing_height);
+  p.md[P + "swing_width"] = adjustable(c.swing_width);
+  p.md[P + "step_depth"] = adjustable(c.step_depth);
+  p.md[P + "stance_span_modifier"] = adjustable(c.stance_span_modifier);
+  p.s[P + "velocity_input_mode"] = c.velocity_input_mode == SHC_VELOCITY_REAL ? "real" : "throttle";
+  p.d[P + "body_velocity_scaler"] = c.body_velocity_scaler;
+  p.b[P + "force_cruise_velocity"] = true;
+  p.md[P + "linear_cruise_velocity"] = {{"x", 1.0}, {"y", 0.0}};
+  p.d[P + "angular_cruise_velocity"] = 0.5;
+  p.d[P + "cruise_control_time_limit"] = 0.0;
+  p.b[P + "overlapping_walkspaces"] = c.overlapping_walkspaces;
+  p.b[P + "force_normal_touchdown"] = c.force_normal_touchdown;
+  p.b[P + "gravity_aligned_tips"] = c.gravity_aligned_tips;
+  p.d[P + "touchdown_threshold"] = c.touchdown_threshold;
+  p.d[P + "liftoff_threshold"] = c.liftoff_threshold;
+  p.s[P + "auto_pose_type"] = "harness_pose";
+  p.b[P + "start_up_sequence"] = false;
+  p.d[P + "time_to_start"] = c.time_to_start;
+  p.md[P + "rotation_pid_gains"] = {{"p", c.rotation_pid_p}, {"i", c.rotation_pid_i}, {"d", c.rotation_pid_d}};
+  p.md[P + "max_translation"] = {{"x", c.max_translation[0]}, {"y", c.max_translation[1]}, {"z", c.max_translation[2]}};
+  p.md[P + "max_rotation"] = {{"roll", c.max_rotation[0]}, {"pitch", c.max_rotation[1]}, {"yaw", c.max_rotation[2]}};
+  p.d[P + "max_translation_velocity"] = c.max_translation_velocity;
+  p.d[P + "max_rotation_velocity"] = c.max_rotation_velocity;
+  p.s[P + "leg_manipulation_mode"] = "tip_control";
+  p.b[P + "dynamic_stiffness"] = c.dynamic_stiffness;
+  p.b[P + "use_joint_effort"] = c.use_joint_effort;
+  p.d[P + "integrator_step_time"] = c.integrator_step_time;
+  p.md[P + "virtual_mass"] = adjustable(c.virtual_mass);
+  p.md[P + "virtual_stiffness"] = adjustable(c.virtual_stiffness);
+  p.md[P + "virtual_damping_ratio"] = adjustable(c.virtual_damping_ratio);
+  p.md[P + "force_gain"] = adjustable(c.force_gain);
+  p.d[P + "load_stiffness_scaler"] = c.load_stiffness_scaler;
+  p.d[P + "swing_stiffness_scaler"] = c.swing_stiffness_scaler;
+  p.b[P + "debug_rviz"] = false;
+  p.s[P + "console_verbosity"] = "error";
+  for (const char* k : {"debug_move_to_joint_position", "debug_step_to_position", "debug_swing_trajectory", "debug_stance_trajectory",
+                        "debug_execute_sequence", "debug_workspace_calculations", "debug_ik"})
+    p.b[P + k] = false;
+  const std::string G = "syropod/gait_parameters/harness_gait/";
+  p.i[G + "stance_phase"] = c.stance_phase;
+  p.i[G + "swing_phase"] = c.swing_phase;
+  p.i[G + "phase_offset"] = c.phase_offset;
+  std::map<std::string, int> mult;
+  for (int l = 0; l < L; ++l) mult[legs[l]] = c.offset_multiplier[l];
+  p.mi[G + "offset_multiplier"] = mult;
+  const std::string A = "syropod/auto_pose_parameters/harness_pose/";
+  p.d[A + "pose_frequency"] = c.pose_frequency;
+  p.i[A + "pose_phase_length"] = c.pose_phase_length;
+  const int K = c.auto_poser_count;
+  p.vi[A + "pose_phase_starts"] = std::vector<int>(c.pose_phase_starts, c.pose_phase_starts + K);
+  p.vi[A + "pose_phase_ends"] = std::vector<int>(c.pose_phase_ends, c.pose_phase_ends + K);
+  std::map<std::string, int> ns, ne;
+  std::map<std::string, double> nr;
+  for (int l = 0; l < L; ++l) {
+    ns[legs[l]] = c.pose_negation_phase_starts[l];
+    ne[legs[l]] = c.pose_negation_phase_ends[l];
+    nr[legs[l]] = c.negation_transition_ratio[l];
+  }
+  p.mi[A + "pose_negation_phase_starts"] = ns;
+  p.mi[A + "pose_negation_phase_ends"] = ne;
+  p.md[A + "negation_transition_ratio"] = nr;
+  p.vd[A + "x_amplitudes"] = std::vector<double>(c.x_amplitudes, c.x_amplitudes + K);
+  p.vd[A + "y_amplitudes"] = std::vector<double>(c.y_amplitudes, c.y_amplitudes + K);
+  p.vd[A + "z_amplitudes"] = std::vector<double>(c.z_amplitudes, c.z_amplitudes + K);
+  p.vd[A + "gravity_amplitudes"] = std::vector<double>(c.gravity_amplitudes, c.gravity_amplitudes + K);
+  p.vd[A + "roll_amplitudes"] = std::vector<double>(c.roll_amplitudes, c.roll_amplitudes + K);
+  p.vd[A + "pitch_amplitudes"] = std::vector<double>(c.pitch_amplitudes, c.pitch_amplitudes + K);
+  p.vd[A + "yaw_amplitudes"] = std::vector<double>(c.yaw_amplitudes, c.yaw_amplitudes + K);
+}
+
+struct RefRobot {
+  shc_config cfg;
+  std::unique_ptr<StateController> sc;
+  std::vector<std::string> legs;
+  int startup_loops = 0;
+  int uninitialised_params = 0;
+};
+
+void put3(double* o, const Eigen::Vector3d& v) { o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; }
+void putQuat(double* o, const Eigen::Quaterniond& q) { o[0] = q.w(); o[1] = q.x(); o[2] = q.y(); o[3] = q.z(); }
+void putPose(double* o, const Pose& p) { put3(o, p.position_); putQuat(o + 3, p.rotation_); }
+
+std_msgs::Int8 int8(int v) { std_msgs::Int8 m; m.data = int8_t(v); return m; }
+
+}  // namespace
+
+extern "C" {
+
+// StateController() + what main.cpp does before its loop (main.cpp:98-99: init(), initModel(use_default_joint_positions =
+// true, no joint states have arrived)), then START is pressed (robot state RUNNING requested) every loop until the direct
+// start-up has brought the robot to READY (state_controller.cpp:254-281).  As in the restated oracle's harness the robot is
+// then put in RUNNING state directly, so that cycle 0 is the first full loop() in RUNNING state.
+void* shc_ref_create(const shc_config* cfg) {
+  RefRobot* r = new RefRobot();
+  r->cfg = *cfg;
+  r->legs = legNames(cfg->leg_count);
+  fillParams(*cfg);
+  shc_shim::runtime() = shc_shim::Runtime();
+  r->sc.reset(new StateController());
+  StateController& sc = *r->sc;
+  sc.systemStateCallback(int8(OPERATIONAL));
+  sc.init();
+  sc.initModel(true);
+  int loops = 0;
+  while (sc.robot_state_ != READY && loops < 100000) {
+    sc.robotStateCallback(int8(RUNNING));
+    sc.loop();
+    ++loops;
+  }
+  r->startup_loops = loops;
+  sc.robot_state_ = RUNNING;
+  sc.new_robot_state_ = RUNNING;
+  sc.transition_state_flag_ = false;
+  return r;
+}
+
+void shc_ref_destroy(void* h) { delete static_cast<RefRobot*>(h); }
+int shc_ref_startup_loops(void* h) { return static_cast<RefRobot*>(h)->startup_loops; }
+long shc_ref_assert_failures(char* first, int cap) {
+  const shc_shim::Runtime& rt = shc_shim::runtime();
+  if (first && cap > 0) {
+    std::strncpy(first, rt.first_assert.c_str(), size_t(cap) - 1);
+    first[cap - 1] = 0;
+  }
+  return rt.assert_failures;
+}
+int shc_ref_shutdown_requested(void) { return shc_shim::runtime().shutdown_requested ? 1 : 0; }
+
+void shc_ref_set_pose_reset_mode(void* h, int mode) { static_cast<RefRobot*>(h)->sc->poseResetCallback(int8(mode)); }
+
+// joint_states message with efforts only for the robot's joints in their current positions (jointStatesCallback)
+void shc_ref_set_joint_efforts(void* h, const double* efforts) {
+  RefRobot* r = static_cast<RefRobot*>(h);
+  StateController& sc = *r->sc;
+  sensor_msgs::JointState js;
+  int l = 0;
+  for (auto& lp : *sc.model_->getLegContainer()) {
+    int j = 0;
+    for (auto& jp : *lp.second->getJointContainer()) {
+      js.name.push_back(jp.second->id_name_);
+      js.position.push_back(jp.second->current_position_ + jp.second->offset_);
+      js.effort.push_back(efforts[(l * r->cfg.joint_count) + j]);
+      ++j;
+    }
+    ++l;
+  }
+  sc.jointStatesCallback(js);
+}
+
+// One control cycle: inputs through the reference's callbacks, then loop().
+// cmd [3]; imu [10] (quat wxyz, gyro xyz, accel xyz) or NULL; tip_force [L][3] or NULL; manual [6] or NULL;
+// step_plane [L][3] or NULL.
+void shc_ref_step(void* h, const double* cmd, const double* imu, const double* tip_force, const double* manual,
+                  const double* step_plane) {
+  RefRobot* r = static_cast<RefRobot*>(h);
+  StateController& sc = *r->sc;
+  const int L = r->cfg.leg_count;
+  shc_shim::runtime().now += r->cfg.time_delta;
+  if (imu) {
+    sensor_msgs::Imu m;
+    m.orientation.w = imu[0]; m.orientation.x = imu[1]; m.orientation.y = imu[2]; m.orientation.z = imu[3];
+    m.angular_velocity.x = imu[4]; m.angular_velocity.y = imu[5]; m.angular_velocity.z = imu[6];
+    m.linear_acceleration.x = imu[7]; m.linear_acceleration.y = imu[8]; m.linear_acceleration.z = imu[9];
+    sc.imuCallback(m);
+  }
+  if (tip_force) {
+    syropod_highlevel_controller::TipState ts;
+    for (int l = 0; l < L; ++l) {
+      ts.name.push_back(r->legs[l] + "_tip");
+      geometry_msgs::Wrench w;
+      w.force.x = tip_force[3 * l]; w.force.y = tip_force[3 * l + 1]; w.force.z = tip_force[3 * l + 2];
+      ts.wrench.push_back(w);
+    }
+    sc.tipStatesCallback(ts);
+  }
+  if (step_plane) {
+    syropod_highlevel_controller::TipState ts;
+    for (int l = 0; l < L; ++l) {
+      ts.name.push_back(r->legs[l] + "_tip");
+      geometry_msgs::Vector3 v;
+      v.x = step_plane[3 * l]; v.y = step_plane[3 * l + 1]; v.z = step_plane[3 * l + 2];
+      ts.step_plane.push_back(v);
+    }
+    sc.tipStatesCallback(ts);
+  }
+  if (manual) {
+    geometry_msgs::Twist t;
+    t.linear.x = manual[0]; t.linear.y = manual[1]; t.linear.z = manual[2];
+    t.angular.x = manual[3]; t.angular.y = manual[4]; t.angular.z = manual[5];
+    sc.bodyPoseInputCallback(t);
+  }
+  geometry_msgs::Twist v;
+  v.linear.x = cmd[0]; v.linear.y = cmd[1]; v.angular.z = cmd[2];
+  sc.bodyVelocityInputCallback(v);
+  sc.loop();
+}
+
+void shc_ref_get_joints(void* h, double* out) {
+  RefRobot* r = static_cast<RefRobot*>(h);
+  int k = 0;
+  for (auto& lp : *r->sc->model_->getLegContainer())
+    for (auto& jp : *lp.second->getJointContainer()) out[k++] = jp.second->desired_position_;
+}
+
+void shc_ref_get_state(void* h, shc_robot_state* s) {
+  RefRobot* r = static_cast<RefRobot*>(h);
+  StateController& sc = *r->sc;
+  WalkController& w = *sc.walker_;
+  PoseController& p = *sc.poser_;
+  Model& m = *sc.model_;
+  std::memset(s, 0, sizeof(*s));
+  s->desired_linear_velocity[0] = w.desired_linear_velocity_[0];
+  s->desired_linear_velocity[1] = w.desired_linear_velocity_[1];
+  s->desired_angular_velocity = w.desired_angular_velocity_;
+  s->walk_state = w.walk_state_;
+  s->legs_at_correct_phase = w.legs_at_correct_phase_;
+  s->legs_completed_first_step = w.legs_completed_first_step_;
+  s->return_to_default_attempted = w.return_to_default_attempted_;
+  s->pose_state = w.pose_state_;
+  put3(s->walk_plane, w.walk_plane_);
+  put3(s->walk_plane_normal, w.walk_plane_normal_);
+  putPose(s->odometry_ideal, w.odometry_ideal_);
+  putPose(s->walk_plane_pose, p.walk_plane_pose_);
+  putPose(s->origin_walk_plane_pose, p.origin_walk_plane_pose_);
+  putPose(s->manual_pose, p.manual_pose_);
+  putPose(s->imu_pose, p.imu_pose_);
+  putPose(s->inclination_pose, p.inclination_pose_);
+  putPose(s->auto_pose, p.auto_pose_);
+  put3(s->rotation_absement_error, p.rotation_absement_error_);
+  put3(s->rotation_position_error, p.rotation_position_error_);
+  put3(s->rotation_velocity_error, p.rotation_velocity_error_);
+  putPose(s->tip_align_pose, p.tip_align_pose_);
+  putPose(s->origin_tip_align_pose, p.origin_tip_align_pose_);
+  s->auto_posing_state = p.auto_posing_state_;
+  s->pose_phase = p.pose_phase_;
+  size_t k = 0;
+  for (auto& ap : p.auto_poser_container_) {
+    if (k >= SHC_MAX_AUTO_POSERS) break;
+    s->auto_poser_flags[k++] = (ap->start_check_ ? 1 : 0) | (ap->end_check_.first ? 2 : 0) | (ap->end_check_.second ? 4 : 0) |
+                               (ap->allow_posing_ ? 8 : 0);
+  }
+  putPose(s->current_pose, m.current_pose_);
+  int i = 0;
+  for (auto& lp : *m.getLegContainer()) {
+    Leg& leg = *lp.second;
+    LegStepper& st = *leg.leg_stepper_;
+    shc_leg_state& o = s->legs[i++];
+    int j = 0;
+    for (auto& jp : leg.joint_container_) {
+      o.joint_position[j] = jp.second->desired_position_;
+      o.joint_velocity[j] = jp.second->desired_velocity_;
+      ++j;
+    }
+    put3(o.tip_position, st.current_tip_pose_.position_);
+    put3(o.tip_velocity, st.current_tip_velocity_);
+    put3(o.swing_origin_position, st.swing_origin_tip_position_);
+    put3(o.swing_origin_velocity, st.swing_origin_tip_velocity_);
+    put3(o.stance_origin_position, st.stance_origin_tip_position_);
+    put3(o.default_tip_position, st.default_tip_pose_.position_);
+    put3(o.target_tip_position, st.target_tip_pose_.position_);
+    put3(o.stride_vector, st.stride_vector_);
+    put3(o.walk_plane, st.walk_plane_);
+    put3(o.walk_plane_normal, st.walk_plane_normal_);
+    o.swing_progress = st.swing_progress_;
+    o.stance_progress = st.stance_progress_;
+    o.phase = st.phase_;
+    o.step_state = st.step_state_;
+    o.at_correct_phase = st.at_correct_phase_;
+    o.completed_first_step = st.completed_first_step_;
+    o.admittance_state[0] = leg.admittance_state_[0];
+    o.admittance_state[1] = leg.admittance_state_[1];
+    put3(o.admittance_delta, leg.admittance_delta_);
+    put3(o.tip_force_calculated, leg.tip_force_calculated_);
+    o.virtual_stiffness = leg.virtual_stiffness_;
+    o.negate_auto_pose = leg.leg_poser_->negate_auto_pose_;
+    putQuat(o.tip_rotation, st.current_tip_pose_.rotation_);
+    putQuat(o.origin_tip_rotation, st.origin_tip_pose_.rotation_);
+    putQuat(o.target_tip_rotation, st.target_tip_pose_.rotation_);
+    o.step_plane_defined = leg.step_plane_pose_ != Pose::Undefined();
+    if (o.step_plane_defined) put3(o.step_plane_position, leg.step_plane_pose_.position_);
+    o.touchdown_detection = st.touchdown_detection_;
+    putPose(o.external_target_pose, st.external_target_.pose_);
+    putPose(o.external_target_transform, st.external_target_.transform_);
+    o.external_target_clearance = st.external_target_.swing_clearance_;
+    o.external_target_defined = st.external_target_.defined_;
+    o.external_target_odom_frame = st.external_target_.frame_id_ == "odom_ideal";
+    putPose(o.external_default_pose, st.external_default_.pose_);
+    putPose(o.external_default_transform, st.external_default_.transform_);
+    o.external_default_defined = st.external_default_.defined_;
+    put3(o.model_tip_position, leg.current_tip_pose_.position_);
+    put3(o.desired_tip_position, leg.desired_tip_pose_.position_);
+  }
+}
+
+void shc_ref_get_startup(void* h, shc_startup* out) {
+  RefRobot* r = static_cast<RefRobot*>(h);
+  StateController& sc = *r->sc;
+  WalkController& w = *sc.walker_;
+  std::memset(out, 0, sizeof(*out));
+  int i = 0;
+  for (auto& lp : *sc.model_->getLegContainer()) {
+    Leg& leg = *lp.second;
+    int j = 0;
+    for (auto& jp : leg.joint_container_) out->default_joint[i][j++] = jp.second->default_position_;
+    if (!leg.workspace_.empty()) {
+      const Workplane& wp = leg.workspace_.begin()->second;
+      for (int b = 0; b < SHC_N_BEARINGS; ++b) out->workspace[i][b] = wp.count(b * 45) ? wp.at(b * 45) : 0.0;
+    }
+    out->phase_offsets[i] = leg.leg_stepper_->phase_offset_;
+    ++i;
+  }
+  for (int b = 0; b < SHC_N_BEARINGS; ++b) {
+    const int k = b * 45;
+    out->walkspace[b] = w.walkspace_.count(k) ? w.walkspace_.at(k) : 0.0;
+    out->max_linear_speed[b] = w.max_linear_speed_.count(k) ? w.max_linear_speed_.at(k) : 0.0;
+    out->max_angular_speed[b] = w.max_angular_speed_.count(k) ? w.max_angular_speed_.at(k) : 0.0;
+    out->max_linear_acceleration[b] = w.max_linear_acceleration_.count(k) ? w.max_linear_acceleration_.at(k) : 0.0;
+    out->max_angular_acceleration[b] = w.max_angular_acceleration_.count(k) ? w.max_angular_acceleration_.at(k) : 0.0;
+  }
+  out->step_frequency = w.step_.frequency_;
+  out->period = w.step_.period_;
+  out->swing_period = w.step_.swing_period_;
+  out->stance_period = w.step_.stance_period_;
+  out->stance_end = w.step_.stance_end_;
+  out->swing_start = w.step_.swing_start_;
+  out->swing_end = w.step_.swing_end_;
+  out->stance_start = w.step_.stance_start_;
+  out->pose_phase_length = sc.poser_->pose_phase_length_;
+  out->pose_normaliser = sc.poser_->normaliser_;
+  out->auto_pose_reference_leg = sc.poser_->auto_pose_reference_leg_ ? sc.poser_->auto_pose_reference_leg_->getIDNumber() : 0;
+  out->startup_loops = r->startup_loops;
+}
+
+// Layered / simple workspace of one leg as the reference generated it in its start-up: heights [P], radii [P][9].
+int shc_ref_workspace(void* h, int leg_index, int max_planes, double* heights, double* radii) {
+  RefRobot* r = static_cast<RefRobot*>(h);
+  Leg& leg = *r->sc->model_->getLegByIDNumber(leg_index);
+  int n = 0;
+  for (auto& pl : leg.workspace_) {
+    if (n < max_planes) {
+      heights[n] = pl.first;
+      for (int b = 0; b < SHC_N_BEARINGS; ++b) radii[n * SHC_N_BEARINGS + b] = pl.second.count(b * 45) ? pl.second.at(b * 45) : 0.0;
+    }
+    ++n;
+  }
+  return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,2 @@
+// oracle/shim/geometry_msgs/Point.h — TEST INFRASTRUCTURE ONLY (see msg_common.h).
+#include "msg_common.h"
