@@ -199,6 +199,9 @@ void* shc_ref_create(const shc_config* cfg) {
   sc.systemStateCallback(int8(OPERATIONAL));
   sc.init();
   sc.initModel(true);
+  // Leg::virtual_stiffness_ has no initialiser in the reference (model.h:516; first written by updateStiffness,
+  // admittance_controller.cpp:103): zero until then, as in the restated oracle and the engine's state record.
+  for (auto& lp : *sc.model_->getLegContainer()) lp.second->virtual_stiffness_ = 0.0;
   int loops = 0;
   while (sc.robot_state_ != READY && loops < 100000) {
     sc.robotStateCallback(int8(RUNNING));
@@ -224,7 +227,11 @@ long shc_ref_assert_failures(char* first, int cap) {
 }
 int shc_ref_shutdown_requested(void) { return shc_shim::runtime().shutdown_requested ? 1 : 0; }
 
-void shc_ref_set_pose_reset_mode(void* h, int mode) { static_cast<RefRobot*>(h)->sc->poseResetCallback(int8(mode)); }
+// PoseController::setPoseResetMode — the setter the engine's shc_set_pose_reset_mode and the oracle's input stand for —
+// and, separately, the subscriber callback around it, which ignores requests while an IMMEDIATE_ALL_RESET is pending
+// (state_controller.cpp:1193-1203).
+void shc_ref_set_pose_reset_mode(void* h, int mode) { static_cast<RefRobot*>(h)->sc->poser_->setPoseResetMode(PoseResetMode(mode)); }
+void shc_ref_pose_reset_callback(void* h, int mode) { static_cast<RefRobot*>(h)->sc->poseResetCallback(int8(mode)); }
 
 // joint_states message with efforts only for the robot's joints in their current positions (jointStatesCallback)
 void shc_ref_set_joint_efforts(void* h, const double* efforts) {
@@ -377,13 +384,16 @@ void shc_ref_get_state(void* h, shc_robot_state* s) {
     o.step_plane_defined = leg.step_plane_pose_ != Pose::Undefined();
     if (o.step_plane_defined) put3(o.step_plane_position, leg.step_plane_pose_.position_);
     o.touchdown_detection = st.touchdown_detection_;
-    putPose(o.external_target_pose, st.external_target_.pose_);
-    putPose(o.external_target_transform, st.external_target_.transform_);
-    o.external_target_clearance = st.external_target_.swing_clearance_;
+    // An ExternalTarget the reference has not been given is indeterminate memory there (Pose() initialises nothing,
+    // pose.h:21; swing_clearance_ has no initialiser, walk_controller.h:41): reported as the identity record.
+    const Pose identity = Pose::Identity();
+    putPose(o.external_target_pose, st.external_target_.defined_ ? st.external_target_.pose_ : identity);
+    putPose(o.external_target_transform, st.external_target_.defined_ ? st.external_target_.transform_ : identity);
+    o.external_target_clearance = st.external_target_.defined_ ? st.external_target_.swing_clearance_ : 0.0;
     o.external_target_defined = st.external_target_.defined_;
-    o.external_target_odom_frame = st.external_target_.frame_id_ == "odom_ideal";
-    putPose(o.external_default_pose, st.external_default_.pose_);
-    putPose(o.external_default_transform, st.external_default_.transform_);
+    o.external_target_odom_frame = st.external_target_.defined_ && st.external_target_.frame_id_ == "odom_ideal";
+    putPose(o.external_default_pose, st.external_default_.defined_ ? st.external_default_.pose_ : identity);
+    putPose(o.external_default_transform, st.external_default_.defined_ ? st.external_default_.transform_ : identity);
     o.external_default_defined = st.external_default_.defined_;
     put3(o.model_tip_position, leg.current_tip_pose_.position_);
     put3(o.desired_tip_position, leg.desired_tip_pose_.position_);

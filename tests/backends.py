@@ -1,9 +1,12 @@
-"""The two things the parity cases (tests/parity_cases.py) can be run against, behind one numpy-in / numpy-out surface:
+"""The things the parity cases (tests/parity_cases.py) can be run against, behind one numpy-in / numpy-out surface:
 
   * GpuBackend — the product: the CUDA control-cycle kernel through the C-ABI (`-m gpu` tests, needs a B200);
-  * EmuBackend — tests/emu.py: the same cycle SOURCE compiled for the host (CPU tests in this GPU-less container).
+  * EmuBackend — tests/emu.py: the same cycle SOURCE compiled for the host (CPU tests in this GPU-less container);
+  * RefBackend — oracle/_ref: the REFERENCE'S OWN control code (its unmodified sources compiled against stand-in ROS /
+    Eigen / Boost headers, oracle/ref_py.py), one StateController per robot.  Running the cases with this backend checks
+    the restated oracle against the reference itself (tests/test_reference_pin.py): it is what pins the oracle.
 
-The oracle is the checker in both cases; neither backend touches it."""
+The oracle is the checker in the first two cases; neither backend touches it."""
 import numpy as np
 
 
@@ -50,10 +53,72 @@ class _EmuStepper:
         return getattr(self.eng, name)
 
 
+class _RefStepper:
+    """n independent instances of the reference's StateController (each through its own direct start-up)."""
+
+    def __init__(self, cfg, n, precision, startup):
+        from oracle import ref_py
+
+        assert precision == "f64"
+        self.cfg, self.n = cfg, n
+        self.L, self.D = cfg.leg_count, cfg.joint_count
+        self.robots = [ref_py.RefRobot(cfg) for _ in range(n)]
+        self._planes = None
+
+    @staticmethod
+    def _row(a, i):
+        return None if a is None else np.asarray(a[i], dtype=np.float64)
+
+    def step(self, cmd, imu=None, tip_force=None, manual=None):
+        out = np.empty((self.n, self.L, self.D))
+        for i, r in enumerate(self.robots):
+            r.step(self._row(cmd, i), self._row(imu, i), self._row(tip_force, i), self._row(manual, i), self._row(self._planes, i))
+            out[i] = r.joints()
+        return out
+
+    def get_state(self):
+        from syropod_highlevel_controller_b200.config import ShcRobotState
+
+        arr = (ShcRobotState * self.n)()
+        for i, r in enumerate(self.robots):
+            arr[i] = r.get_state()
+        return arr
+
+    def startup(self):
+        return self.robots[0].startup()
+
+    def set_pose_reset_mode(self, mode):
+        for r in self.robots:
+            r.set_pose_reset_mode(mode)
+
+    def set_joint_efforts(self, eff):
+        for i, r in enumerate(self.robots):
+            r.set_joint_efforts(np.asarray(eff[i], dtype=np.float64))
+
+    def set_tip_step_planes(self, sp):
+        if sp is None:
+            self._planes = None
+            return
+        sp = np.array(sp, dtype=np.float64)
+        sp[..., 2] = np.where(sp[..., 2] >= 1e9, float(2 ** 31 - 1), sp[..., 2])  # the reference's UNASSIGNED_VALUE
+        self._planes = sp
+
+    def set_options(self, *a, **k):
+        pass
+
+    def assert_failures(self):
+        return self.robots[0].assert_failures()
+
+    def close(self):
+        for r in self.robots:
+            r.close()
+        self.robots = []
+
+
 class Backend:
     def __init__(self, kind):
-        assert kind in ("gpu", "emu")
+        assert kind in ("gpu", "emu", "ref")
         self.kind = kind
 
     def engine(self, cfg, n, precision="f64", startup=None):
-        return (_GpuStepper if self.kind == "gpu" else _EmuStepper)(cfg, n, precision, startup)
+        return {"gpu": _GpuStepper, "emu": _EmuStepper, "ref": _RefStepper}[self.kind](cfg, n, precision, startup)

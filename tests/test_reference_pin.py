@@ -1,0 +1,247 @@
+"""Pins the restated oracle (oracle/*.cpp) to THE REFERENCE ITSELF.
+
+oracle/_ref/libshc_ref.so is the reference's own, unmodified control code — state_controller.cpp, model.cpp,
+walk_controller.cpp, pose_controller.cpp, admittance_controller.cpp compiled where they lie under /root/reference against
+self-written stand-ins for the absent ROS / tf2 / Eigen / Boost.Odeint headers (oracle/shim/, oracle/Makefile.ref) — driven
+through its own subscriber callbacks and StateController::loop() (oracle/ref_harness.cpp).  These tests run the restated
+oracle and the reference side by side on identical configurations and inputs and require
+
+  * the start-up constants (default stance joints, workspaces, walkspace, speed / acceleration limit maps, step cycle) to
+    be EQUAL, and
+  * every state field of every cycle of free-running rollouts to agree to 1e-12 (integers, walk / step / posing states
+    exactly) — in practice the two are bit-identical on the hexapod and within a few ulp on the octopod —
+
+over every gait, both control rates, hexapod and octopod, manual posing with the reset modes, auto posing (synchronised
+and on its own cycle), IMU / inclination posing, admittance with dynamic stiffness, joint-effort tip forces, the
+tip-orientation path and rough-terrain mode with tip forces and range sensors.  The parity cases the CUDA engine is
+checked with (tests/parity_cases.py) are run with the reference as the "backend" as well.  The library can only be built
+where /root/reference exists; the built .so travels with the repo snapshot, and tests/golden/ref_*.npz (made by
+tests/golden/make_ref_golden.py from this library) carry the reference's outputs to machines that have neither.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import parity_cases as P
+from backends import Backend
+from gpu_common import state_diff
+from syropod_highlevel_controller_b200.config import hexapod_config, octopod_config
+from syropod_highlevel_controller_b200.streams import CommandStream, ForceStream, ImuStream
+
+from oracle import ref_py
+
+pytestmark = pytest.mark.skipif(not ref_py.available(), reason="neither /root/reference nor a prebuilt oracle/_ref is here")
+
+EXACT_TOL = 1e-12   # 3-DOF legs: in practice the two are bit-identical
+# 5-DOF legs and joint-effort tip forces go through a 6 x 6 / D x D matrix inverse, which the stand-in Eigen (Gauss-Jordan
+# with partial pivoting) and the oracle (its own elimination) round differently: a few 1e-13 rad on the joints
+WIDE_TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def ref():
+    ref_py.build()
+    return Backend("ref")
+
+
+def _assert_equal_startup(so, sr, L):
+    for f in ("default_joint", "workspace"):
+        a, b = np.array(getattr(so, f))[:L], np.array(getattr(sr, f))[:L]
+        assert np.array_equal(a, b), (f, np.abs(a - b).max())
+    for f in ("walkspace", "max_linear_speed", "max_angular_speed", "max_linear_acceleration", "max_angular_acceleration"):
+        a, b = np.array(getattr(so, f)), np.array(getattr(sr, f))
+        assert np.array_equal(a, b), (f, np.abs(a - b).max())
+    for f in ("step_frequency", "period", "swing_period", "stance_period", "stance_end", "swing_start", "swing_end", "stance_start",
+              "pose_phase_length", "pose_normaliser", "startup_loops"):
+        assert getattr(so, f) == getattr(sr, f), (f, getattr(so, f), getattr(sr, f))
+    assert list(so.phase_offsets)[:L] == list(sr.phase_offsets)[:L]
+
+
+def _strict_rollout(ref, oracle, cfg, cycles, n=2, imu=False, force=False, manual=False, every=1, hook=None, tol=EXACT_TOL, label=""):
+    """Free-running, every state field compared every `every` cycles; returns the worst difference per field."""
+    L, D = cfg.leg_count, cfg.joint_count
+    ob = oracle.OracleBatch(cfg, n)
+    eng = ref.engine(cfg, n)
+    _assert_equal_startup(ob.startup(), eng.startup(), L)
+    cs = CommandStream(n, min_len=40, max_len=200)
+    ims = ImuStream(n) if imu else None
+    fs = ForceStream(n, L) if force else None
+    rng = np.random.default_rng(5)
+    worst = {}
+    states = set()
+    for c in range(cycles):
+        cmd = cs.next().astype(np.float64)
+        i = ims.next(cfg.time_delta).astype(np.float64) if ims else None
+        f = fs.next().astype(np.float64) if fs else None
+        m = None
+        if manual:
+            m = np.where(rng.random((n, 6)) < 0.5, rng.uniform(-1.0, 1.0, (n, 6)), 0.0) if (c // 60) % 2 == 0 else np.zeros((n, 6))
+        if hook is not None:
+            f = hook(c, eng, ob, f)
+        eng.step(cmd, i, f, m)
+        ob.step(cmd, i, f, m, threads=1)
+        if c % every == every - 1:
+            so = ob.get_state()
+            for k, v in state_diff(eng.get_state(), so, L, D).items():
+                worst[k] = max(worst.get(k, 0.0), v)
+            states.update(s.walk_state for s in so)
+    bad = {k: v for k, v in worst.items() if (v != 0 if k.startswith("int:") else v > (tol * 100 if k in ("joint_velocity", "tip_velocity") else tol))}
+    top = max((v for k, v in worst.items() if not k.startswith("int:")), default=0.0)
+    print(f"[reference-pin] {label}: {cycles} cycles x {n} robots, worst field difference {top:.2e}, walk states seen {sorted(states)}")
+    assert not bad, bad
+    n_assert, first = eng.assert_failures()
+    eng.close(); ob.close()
+    return worst, states, (n_assert, first)
+
+
+@pytest.mark.parametrize("gait", ["tripod_gait", "ripple_gait", "wave_gait", "amble_gait"])
+@pytest.mark.parametrize("dt", [0.02, 0.01])
+def test_hexapod_every_gait_both_rates_equal_the_reference(ref, oracle, gait, dt):
+    worst, states, _ = _strict_rollout(ref, oracle, hexapod_config(gait, dt), 1500 if dt == 0.01 else 900, label=f"hexapod {gait} dt={dt}")
+    assert states >= {0, 1, 2}  # STARTING, MOVING, STOPPING visited (and STOPPED, except for the slowest gait at 100 Hz)
+
+
+def test_octopod_imu_inclination_admittance_equal_the_reference(ref, oracle):
+    cfg = octopod_config("tripod_gait", 0.02)
+    assert cfg.admittance_control and cfg.imu_posing and cfg.inclination_posing
+    _strict_rollout(ref, oracle, cfg, 600, imu=True, force=True, tol=WIDE_TOL, label="octopod 8x5, IMU + inclination + admittance (dynamic stiffness)")
+
+
+def test_manual_posing_and_reset_modes_equal_the_reference(ref, oracle):
+    cfg = hexapod_config("tripod_gait", 0.02)
+
+    def hook(c, eng, ob, f):
+        if c % 90 == 45:
+            mode = (c // 90) % 6
+            eng.set_pose_reset_mode(mode)
+            ob.set_pose_reset_mode(mode)
+        return f
+
+    worst, _, _ = _strict_rollout(ref, oracle, cfg, 700, manual=True, hook=hook, label="manual posing, reset modes 0-5")
+
+
+@pytest.mark.parametrize("gait,dt,freq", [("tripod_gait", 0.02, -1.0), ("wave_gait", 0.01, -1.0), ("amble_gait", 0.02, -1.0),
+                                          ("ripple_gait", 0.02, -1.0), ("tripod_gait", 0.02, 0.7), ("wave_gait", 0.01, 1.3)])
+def test_auto_posing_equals_the_reference(ref, oracle, gait, dt, freq):
+    cfg = hexapod_config(gait, dt, auto_posing=1, pose_frequency=freq)
+    _strict_rollout(ref, oracle, cfg, 900, label=f"auto posing {gait} dt={dt} pose_frequency={freq}")
+
+
+@pytest.mark.parametrize("variant", [dict(velocity_input_mode=1), dict(force_normal_touchdown=1), dict(overlapping_walkspaces=1),
+                                     dict(stance_span_modifier=0.4), dict(swing_width=0.02, step_frequency=1.6),
+                                     dict(clamp_joint_velocities=0, clamp_joint_positions=0), dict(body_clearance=0.08, swing_height=0.035)],
+                         ids=lambda v: ",".join(f"{k}={x}" for k, x in v.items()))
+def test_parameter_variants_equal_the_reference(ref, oracle, variant):
+    _strict_rollout(ref, oracle, hexapod_config("tripod_gait", 0.02, **variant), 500, label=f"variant {variant}")
+
+
+@pytest.mark.parametrize("which", ["hexapod", "octopod"])
+def test_joint_effort_tip_force_equals_the_reference(ref, oracle, which):
+    cfg = (hexapod_config("tripod_gait", 0.02, admittance_control=1, use_joint_effort=1) if which == "hexapod" else
+           octopod_config("ripple_gait", 0.02, use_joint_effort=1))
+    L, D = cfg.leg_count, cfg.joint_count
+    rng = np.random.default_rng(3)
+
+    def hook(c, eng, ob, f):
+        if c % 20 == 0:
+            eff = rng.normal(0.0, 2.0, size=(eng.n, L, D))
+            eng.set_joint_efforts(eff)
+            ob.set_joint_efforts(eff)
+        return f
+
+    _strict_rollout(ref, oracle, cfg, 400, imu=(which == "octopod"), hook=hook, tol=WIDE_TOL, label=f"{which}: tip force from joint efforts")
+
+
+@pytest.mark.parametrize("cfg", [octopod_config("tripod_gait", gravity_aligned_tips=1), octopod_config("ripple_gait", gravity_aligned_tips=1),
+                                 hexapod_config("tripod_gait", gravity_aligned_tips=1), hexapod_config("wave_gait", gravity_aligned_tips=1, auto_posing=1)],
+                         ids=["octopod-tripod", "octopod-ripple", "hexapod-tripod", "hexapod-wave-autopose"])
+def test_tip_orientation_path_equals_the_reference(ref, oracle, cfg):
+    full = bool(cfg.imu_posing or cfg.inclination_posing)
+    _strict_rollout(ref, oracle, cfg, 500, imu=full, force=bool(cfg.admittance_control), tol=WIDE_TOL if cfg.joint_count > 3 else EXACT_TOL, label=f"gravity_aligned_tips {cfg.leg_count}x{cfg.joint_count}")
+
+
+@pytest.mark.parametrize("kind", ["forces-tripod", "forces-wave-normal-touchdown", "ranges-ripple", "octopod-forces"])
+def test_rough_terrain_mode_equals_the_reference(ref, oracle, kind):
+    """Rough-terrain mode free-running: the inputs (tip forces of legs in stance or touching down early, range-sensor
+    readings near the ground) are derived from the ORACLE's state each cycle and given to both."""
+    cfg = {"forces-tripod": hexapod_config("tripod_gait", rough_terrain_mode=1, step_depth=0.01),
+           "forces-wave-normal-touchdown": hexapod_config("wave_gait", rough_terrain_mode=1, step_depth=0.02, force_normal_touchdown=1),
+           "ranges-ripple": hexapod_config("ripple_gait", rough_terrain_mode=1, step_depth=0.01),
+           "octopod-forces": octopod_config("ripple_gait", rough_terrain_mode=1, step_depth=0.01)}[kind]
+    L = cfg.leg_count
+    ranges = kind.startswith("ranges")
+    rng = np.random.default_rng(17)
+    seen = {"contacts": 0, "tilted": 0}
+
+    def hook(c, eng, ob, f):
+        st = ob.get_state()
+        n = eng.n
+        seen["contacts"] += sum(1 for s in st for l in range(L) if s.legs[l].step_plane_defined and s.legs[l].step_state == 0)
+        seen["tilted"] += sum(1 for s in st if abs(s.walk_plane_normal[2] - 1.0) > 1e-9)
+        if ranges:
+            sp = np.zeros((n, L, 3))
+            for r in range(n):
+                for l in range(L):
+                    g = st[r].legs[l]
+                    near = g.step_state != 0 or g.swing_progress > 0.5 + 0.3 * ((r * 5 + l + c // 40) % 7) / 7.0
+                    sp[r, l] = (rng.uniform(-0.05, 0.05), rng.uniform(-0.05, 0.05), rng.uniform(0.0, 0.03)) if near else (0.0, 0.0, 2.0e9)
+            eng.set_tip_step_planes(sp)
+            ob.set_tip_step_planes(sp)
+            return None
+        force = np.zeros((n, L, 3))
+        for r in range(n):
+            for l in range(L):
+                g = st[r].legs[l]
+                early = g.swing_progress > 0.55 + 0.4 * ((r * 7 + l * 3 + c // 50) % 10) / 10.0
+                force[r, l] = (rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5), rng.uniform(2.0, 8.0)) if (g.step_state != 0 or early) else \
+                              (0.0, 0.0, rng.uniform(0.0, 0.05))
+        return force
+
+    _strict_rollout(ref, oracle, cfg, 500, imu=(L == 8), hook=hook, tol=WIDE_TOL if L == 8 else EXACT_TOL, label=f"rough terrain {kind}")
+    assert seen["contacts"] > 0 and seen["tilted"] > 0, seen  # swings really ended on contact, the walk plane really tilted
+
+
+def test_layered_workspace_equals_the_reference(ref, oracle):
+    """Rough-terrain start-up: the layered workspace (model.cpp:309-510) of every leg, plane by plane."""
+    cfg = hexapod_config("tripod_gait", rough_terrain_mode=1, step_depth=0.01)
+    r = ref_py.RefRobot(cfg)
+    for leg in range(6):
+        ho, ro = oracle.workspace(cfg, leg, full=True, max_planes=64)
+        hr, rr = r.workspace(leg, max_planes=64)
+        assert len(ho) == len(hr) > 1
+        assert np.array_equal(ho, hr) and np.array_equal(ro, rr), (leg, np.abs(ro - rr).max())
+    r.close()
+
+
+def test_reference_own_assertions_hold(ref, oracle):
+    """ROS_ASSERT violations inside the reference during a long walk (the stand-in counts instead of aborting)."""
+    _, _, (n_assert, first) = _strict_rollout(ref, oracle, hexapod_config("tripod_gait", 0.02), 600, n=1, label="assertions")
+    assert n_assert == 0, first
+
+
+# ---- the parity cases of the CUDA engine, with the reference in the engine's place ----------------------------------------
+
+@pytest.mark.parametrize("path", P.GOLDEN_FILES, ids=os.path.basename)
+def test_reference_reproduces_the_golden_fixtures(ref, oracle, path):
+    P.golden_rollout(ref, oracle, path)
+
+
+def test_reference_batch_tripod(ref, oracle):
+    P.batch_tripod(ref, oracle, n=16, cycles=300)
+
+
+def test_reference_octopod_full(ref, oracle):
+    P.octopod_full(ref, oracle, n=6, cycles=400)
+
+
+def test_reference_manual_pose_and_reset_modes(ref, oracle):
+    P.manual_pose_and_reset_modes(ref, oracle, n=8)
+
+
+def test_reference_joint_effort_tip_force(ref, oracle):
+    P.joint_effort_tip_force(ref, oracle, n=8)
+
+
+def test_reference_own_startup_free_running(ref, oracle):
+    P.own_startup_free_running(ref, oracle, n=8)
