@@ -33,7 +33,7 @@ typedef struct shc_leg_state_msg {
   double poser_tip_pose[7];      /* LegPoser::current_tip_pose_ (base_link frame): PoseController::updateStance */
   double model_tip_pose[7];      /* Leg::current_tip_pose_: forward kinematics of the desired joint positions */
   double actual_tip_pose[7];     /* Leg::applyFK(false, true): forward kinematics of the MEASURED joint positions */
-  double model_tip_velocity[3];  /* Leg::current_tip_velocity_ */
+  double model_tip_velocity[3];  /* Leg::current_tip_velocity_ as published: zero (state_controller.cpp:842 resets it before :846 reads it) */
   double joint_positions[SHC_MAX_DOF], joint_velocities[SHC_MAX_DOF], joint_efforts[SHC_MAX_DOF];
   double stance_progress, swing_progress;
   double time_to_swing_end;      /* :866-877 */

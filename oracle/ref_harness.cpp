@@ -71,7 +71,7 @@ void fillParams(const shc_config& c) {
   p.b[P + "manual_posing"] = c.manual_posing;
   p.b[P + "inclination_posing"] = c.inclination_posing;
   p.b[P + "admittance_control"] = c.admittance_control;
-  p.b[P + "individual_control_interface"] = false;
+  p.b[P + "individual_control_interface"] = true;
   p.b[P + "combined_control_interface"] = true;
   p.s[P + "syropod_type"] = "harness";
   p.vs[P + "leg_id"] = legs;
@@ -300,6 +300,41 @@ void shc_ref_step(void* h, const double* cmd, const double* imu, const double* t
   sc.loop();
 }
 
+// One loop() of a stepping / joint-space sequence, called on the reference's PoseController as StateController::
+// transitionRobotState does (state_controller.cpp:286-350): kind 0 = stepToNewStance, 1 = packLegs(time), 2 = unpackLegs(time),
+// 3 / 4 = executeSequence(START_UP / SHUT_DOWN).  Returns the progress value; -2 if the reference asked for a shutdown
+// (pose_controller.cpp:441: the generated sequence could not be executed).
+int shc_ref_sequence_step(void* h, int kind, double time) {
+  RefRobot* r = static_cast<RefRobot*>(h);
+  PoseController& p = *r->sc->poser_;
+  int progress;
+  switch (kind) {
+    case 0: progress = p.stepToNewStance(); break;
+    case 1: progress = p.packLegs(time); break;
+    case 2: progress = p.unpackLegs(time); break;
+    case 3: progress = p.executeSequence(START_UP); break;
+    default: progress = p.executeSequence(SHUT_DOWN); break;
+  }
+  if (shc_shim::runtime().shutdown_requested) progress = -2;
+  return progress;
+}
+
+// Overwrites the desired joint positions / velocities [L][D] and re-runs the forward kinematics (Leg::applyFK), the way the
+// oracle's state import does: lets a test take single loops "from identical joint state" on legs whose redundant joints
+// drift apart between any two double-precision builds over thousands of closed-loop IK iterations.
+void shc_ref_set_joint_state(void* h, const double* position, const double* velocity) {
+  RefRobot* r = static_cast<RefRobot*>(h);
+  int k = 0;
+  for (auto& lp : *r->sc->model_->getLegContainer()) {
+    for (auto& jp : lp.second->joint_container_) {
+      jp.second->desired_position_ = position[k];
+      jp.second->desired_velocity_ = velocity[k];
+      ++k;
+    }
+    lp.second->applyFK();
+  }
+}
+
 void shc_ref_get_joints(void* h, double* out) {
   RefRobot* r = static_cast<RefRobot*>(h);
   int k = 0;
@@ -437,6 +472,96 @@ void shc_ref_get_startup(void* h, shc_startup* out) {
   out->pose_normaliser = sc.poser_->normaliser_;
   out->auto_pose_reference_leg = sc.poser_->auto_pose_reference_leg_ ? sc.poser_->auto_pose_reference_leg_->getIDNumber() : 0;
   out->startup_loops = r->startup_loops;
+}
+
+// The reference's publishers (state_controller.cpp:777-1047) run as main.cpp runs them after loop(); what they published is
+// read off the stand-in message bus / tf broadcaster into the same records the engine's shc_pack_messages fills.
+// measured [L][D]: joint positions a joint_states message reports (NULL: the desired positions), through
+// jointStatesCallback.
+void shc_ref_get_messages(void* h, const double* measured, shc_joint_state_msg* js, shc_leg_state_msg* legs, shc_body_msg* body) {
+  RefRobot* r = static_cast<RefRobot*>(h);
+  StateController& sc = *r->sc;
+  const int D = r->cfg.joint_count;
+  {
+    sensor_msgs::JointState in;
+    int k = 0;
+    for (auto& lp : *sc.model_->getLegContainer())
+      for (auto& jp : *lp.second->getJointContainer()) {
+        in.name.push_back(jp.second->id_name_);
+        in.position.push_back((measured ? measured[k] : jp.second->desired_position_) + jp.second->offset_);
+        ++k;
+      }
+    sc.jointStatesCallback(in);
+  }
+  sc.publishLegState();
+  sc.publishVelocity();
+  sc.publishPose();
+  sc.publishRotationPoseError();
+  sc.publishFrameTransforms();
+  sc.publishDesiredJointState();
+  shc_shim::Bus& bus = shc_shim::bus();
+  auto pose7 = [](double* o, const geometry_msgs::Pose& p) {
+    o[0] = p.position.x; o[1] = p.position.y; o[2] = p.position.z;
+    o[3] = p.orientation.w; o[4] = p.orientation.x; o[5] = p.orientation.y; o[6] = p.orientation.z;
+  };
+  auto tf7 = [](double* o, const std::string& child) {
+    const geometry_msgs::Transform& t = shc_shim::tf_sent().at(child).transform;
+    o[0] = t.translation.x; o[1] = t.translation.y; o[2] = t.translation.z;
+    o[3] = t.rotation.w; o[4] = t.rotation.x; o[5] = t.rotation.y; o[6] = t.rotation.z;
+  };
+  std::memset(js, 0, sizeof(*js));
+  const sensor_msgs::JointState& out = *std::static_pointer_cast<sensor_msgs::JointState>(bus.last.at("desired_joint_states"));
+  for (size_t k = 0; k < out.position.size(); ++k) {
+    js->position[k] = out.position[k];
+    js->velocity[k] = out.velocity[k];
+    js->effort[k] = out.effort[k];
+  }
+  int l = 0;
+  for (auto& lp : *sc.model_->getLegContainer()) {
+    Leg& leg = *lp.second;
+    shc_leg_state_msg& m = legs[l];
+    std::memset(&m, 0, sizeof(m));
+    const syropod_highlevel_controller::LegState& ls =
+        *std::static_pointer_cast<syropod_highlevel_controller::LegState>(bus.last.at("shc/" + leg.getIDName() + "/state"));
+    pose7(m.walker_tip_pose, ls.walker_tip_pose.pose);
+    pose7(m.target_tip_pose, ls.target_tip_pose.pose);
+    pose7(m.poser_tip_pose, ls.poser_tip_pose.pose);
+    pose7(m.model_tip_pose, ls.model_tip_pose.pose);
+    pose7(m.actual_tip_pose, ls.actual_tip_pose.pose);
+    m.model_tip_velocity[0] = ls.model_tip_velocity.twist.linear.x;
+    m.model_tip_velocity[1] = ls.model_tip_velocity.twist.linear.y;
+    m.model_tip_velocity[2] = ls.model_tip_velocity.twist.linear.z;
+    int j = 0;
+    for (auto& jp : leg.joint_container_) {
+      m.joint_positions[j] = ls.joint_positions[j];
+      m.joint_velocities[j] = ls.joint_velocities[j];
+      m.joint_efforts[j] = ls.joint_efforts[j];
+      js->position_command[l * D + j] = std::static_pointer_cast<std_msgs::Float64>(bus.last.at(jp.second->id_name_ + "/command"))->data;
+      tf7(m.joint_transform[j], jp.second->id_name_);
+      ++j;
+    }
+    tf7(m.tip_transform, leg.getTip()->id_name_);
+    m.stance_progress = ls.stance_progress;
+    m.swing_progress = ls.swing_progress;
+    m.time_to_swing_end = ls.time_to_swing_end;
+    pose7(m.pose_delta, ls.pose_delta);
+    pose7(m.auto_pose, ls.auto_pose);
+    m.tip_force[0] = ls.tip_force.x; m.tip_force[1] = ls.tip_force.y; m.tip_force[2] = ls.tip_force.z;
+    m.admittance_delta[0] = ls.admittance_delta.x; m.admittance_delta[1] = ls.admittance_delta.y; m.admittance_delta[2] = ls.admittance_delta.z;
+    m.virtual_stiffness = ls.virtual_stiffness;
+    ++l;
+  }
+  std::memset(body, 0, sizeof(*body));
+  const geometry_msgs::Twist& v = *std::static_pointer_cast<geometry_msgs::Twist>(bus.last.at("shc/velocity"));
+  body->velocity[0] = v.linear.x; body->velocity[1] = v.linear.y; body->velocity[2] = v.linear.z;
+  body->velocity[3] = v.angular.x; body->velocity[4] = v.angular.y; body->velocity[5] = v.angular.z;
+  const geometry_msgs::Twist& bp = *std::static_pointer_cast<geometry_msgs::Twist>(bus.last.at("shc/pose"));
+  body->pose[0] = bp.linear.x; body->pose[1] = bp.linear.y; body->pose[2] = bp.linear.z;
+  body->pose[3] = bp.angular.x; body->pose[4] = bp.angular.y; body->pose[5] = bp.angular.z;
+  const std_msgs::Float32MultiArray& e = *std::static_pointer_cast<std_msgs::Float32MultiArray>(bus.last.at("shc/rotation_pose_error"));
+  for (int k = 0; k < 9; ++k) body->rotation_pose_error[k] = e.data[k];  // float32 on the wire
+  tf7(body->odom_ideal_to_base_link, "base_link");
+  tf7(body->base_link_to_walk_plane, "walk_plane");
 }
 
 // Layered / simple workspace of one leg as the reference generated it in its start-up: heights [P], radii [P][9].

@@ -13,7 +13,8 @@ import subprocess
 
 import numpy as np
 
-from syropod_highlevel_controller_b200.config import ShcConfig, ShcRobotState, ShcStartup
+from syropod_highlevel_controller_b200.config import (ShcBodyMsg, ShcConfig, ShcJointStateMsg, ShcLegStateMsg, ShcRobotState,
+                                                      ShcStartup)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_ref", "libshc_ref.so")
@@ -53,6 +54,9 @@ def lib():
         L.shc_ref_set_pose_reset_mode.argtypes = [C.c_void_p, C.c_int]
         L.shc_ref_set_joint_efforts.argtypes = [C.c_void_p, dp]
         L.shc_ref_step.argtypes = [C.c_void_p, dp, dp, dp, dp, dp]
+        L.shc_ref_sequence_step.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.shc_ref_set_joint_state.argtypes = [C.c_void_p, dp, dp]
+        L.shc_ref_get_messages.argtypes = [C.c_void_p, dp, C.POINTER(ShcJointStateMsg), C.POINTER(ShcLegStateMsg), C.POINTER(ShcBodyMsg)]
         L.shc_ref_get_joints.argtypes = [C.c_void_p, dp]
         L.shc_ref_get_state.argtypes = [C.c_void_p, C.POINTER(ShcRobotState)]
         L.shc_ref_get_startup.argtypes = [C.c_void_p, C.POINTER(ShcStartup)]
@@ -110,6 +114,23 @@ class RefRobot:
         e = _arr(efforts)
         assert e.shape == (self.L, self.D)
         self._lib.shc_ref_set_joint_efforts(self._h, _dp(e))
+
+    def sequence_step(self, kind: str, time: float = 0.0) -> int:
+        """One loop() of stepToNewStance / packLegs / unpackLegs / executeSequence on the reference's PoseController."""
+        return self._lib.shc_ref_sequence_step(self._h, {"new_stance": 0, "pack": 1, "unpack": 2, "start_up": 3, "shut_down": 4}[kind], float(time))
+
+    def set_joint_state(self, position, velocity):
+        """Desired joint positions / velocities [L, D] overwritten, forward kinematics re-run (see ref_harness.cpp)."""
+        p, v = _arr(position), _arr(velocity)
+        assert p.shape == v.shape == (self.L, self.D)
+        self._lib.shc_ref_set_joint_state(self._h, _dp(p), _dp(v))
+
+    def messages(self, measured=None):
+        """What the reference's own publishers put on the wire for this robot: (JointState, LegState x L, body)."""
+        js, legs, body = ShcJointStateMsg(), (ShcLegStateMsg * self.L)(), ShcBodyMsg()
+        m = _arr(measured)
+        self._lib.shc_ref_get_messages(self._h, _dp(m), C.byref(js), legs, C.byref(body))
+        return js, legs, body
 
     def joints(self) -> np.ndarray:
         out = np.empty((self.L, self.D), dtype=np.float64)

@@ -644,7 +644,10 @@ void shc_oracle_batch_get_messages(void* h, int index, const double* measured, s
     else
       for (int j = 0; j < D; ++j) leg.joints[j + 1].current_position_ = leg.joints[j + 1].desired_position_;
     putPose(m.actual_tip_pose, leg.applyFK(false, true));
-    leg.applyFK(false, false);  // restore the transforms of the desired positions (the reference calls applyFK(): :842)
+    // state_controller.cpp:842 restores the transforms of the desired positions with a plain applyFK(): set_current is
+    // true, so Leg::current_tip_velocity_ becomes (tip - tip) / time_delta = 0 BEFORE :846-848 read it — the reference
+    // publishes a zero model_tip_velocity (found by running its own publishers, tests/test_reference_pin.py).
+    leg.applyFK();
     put3(m.model_tip_velocity, leg.current_tip_velocity_);
     for (int j = 0; j < D; ++j) {
       const Joint& jt = leg.joints[j + 1];

@@ -93,12 +93,11 @@ SHC_HD void pack_leg_message(const Consts& c, Planes<S> pl, int r, int l, const 
   put_pose(m.target_tip_pose, V3<double>{rd.S_(sb + LS::TGT), rd.S_(sb + LS::TGT + 1), rd.S_(sb + LS::TGT + 2)}, undefined);
   const PoseT<double> cur = current_pose_of(ci, rd);
   put_pose(m.poser_tip_pose, pose_inverse_transform(cur, tip), undefined);  // updateStance (pose_controller.cpp:110)
-  double q[D], qd[D], qprev[D], qm[D];
+  double q[D], qd[D], qm[D];
 #pragma unroll
   for (int j = 0; j < D; ++j) {
     q[j] = rd.S_(sb + LS::Q + j);
     qd[j] = rd.S_(sb + LS::QD + j);
-    qprev[j] = q[j] - qd[j] * ck.dt;  // the joint positions one cycle ago (updateJointPositions: q += qd * dt)
     qm[j] = measured ? (double)measured[j] : q[j];
   }
   LegFrames<D> f;
@@ -119,9 +118,10 @@ SHC_HD void pack_leg_message(const Consts& c, Planes<S> pl, int r, int l, const 
     LegFrames<D> fa;
     leg_frames<D>(lc, qm, fa);
     put_pose(m.actual_tip_pose, fa.tip_p, fa.tip_q);
-    const V3<double> prev = leg_fk<D>(ck, l, qprev);
-    const V3<double> v = (f.tip_p - prev) * ck.inv_dt;  // applyFK (model.cpp:979): (new - old) / time_delta
-    m.model_tip_velocity[0] = v.x; m.model_tip_velocity[1] = v.y; m.model_tip_velocity[2] = v.z;
+    // publishLegState re-runs applyFK() on the unchanged desired joint positions (state_controller.cpp:842) before it reads
+    // Leg::current_tip_velocity_ (:846-848), which that call has just set to (tip - tip) / time_delta: the reference's wire
+    // value is zero, and so is this one (checked against the reference's own publishers, tests/test_reference_pin.py).
+    m.model_tip_velocity[0] = 0.0; m.model_tip_velocity[1] = 0.0; m.model_tip_velocity[2] = 0.0;
   }
 #pragma unroll
   for (int j = 0; j < SHC_MAX_DOF; ++j) {

@@ -106,6 +106,29 @@ class _RefStepper:
     def set_options(self, *a, **k):
         pass
 
+    def set_joint_state_from(self, states):
+        """Joint positions / velocities of shc_robot_state records (the oracle's) into the reference's joints."""
+        for i, r in enumerate(self.robots):
+            pos = np.array([list(states[i].legs[l].joint_position)[:self.D] for l in range(self.L)])
+            vel = np.array([list(states[i].legs[l].joint_velocity)[:self.D] for l in range(self.L)])
+            r.set_joint_state(pos, vel)
+
+    def sequence_step(self, kind, time=0.0):
+        done = getattr(self, "_seq_done", None)
+        if done is None:
+            done = self._seq_done = [None] * self.n
+        prog = np.zeros(self.n, dtype=np.int32)
+        out = np.empty((self.n, self.L, self.D))
+        for i, r in enumerate(self.robots):
+            if kind in ("start_up", "shut_down") and done[i] == kind:
+                prog[i] = 100  # through this sequence: StateController no longer calls executeSequence (state_controller.cpp:314-350)
+            else:
+                prog[i] = r.sequence_step(kind, time)
+                if kind in ("start_up", "shut_down"):
+                    done[i] = kind if prog[i] == 100 else None
+            out[i] = r.joints()
+        return out, prog
+
     def assert_failures(self):
         return self.robots[0].assert_failures()
 

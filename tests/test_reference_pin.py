@@ -245,3 +245,115 @@ def test_reference_joint_effort_tip_force(ref, oracle):
 
 def test_reference_own_startup_free_running(ref, oracle):
     P.own_startup_free_running(ref, oracle, n=8)
+
+
+# ---- stepping and joint-space sequences -------------------------------------------------------------
+
+@pytest.mark.parametrize("which", ["hexapod", "octopod"])
+def test_sequences_equal_the_reference(ref, oracle, which):
+    """PoseController::executeSequence (START_UP with sequence generation, SHUT_DOWN, second START_UP), stepToNewStance,
+    packLegs / unpackLegs on the reference's own PoseController against the restated oracle, every loop(): progress values
+    equal, joints equal.  Hexapod: free-running over all ~1500 loops, bit for bit.  Octopod: its five-joint legs are
+    redundant for a position target, so last-bit differences of the 6 x 6 inverse grow along thousands of closed-loop IK
+    iterations (to 0.03 rad with equal tips and progress values); every loop therefore starts from the oracle's joint
+    state (the sequence bookkeeping — step counters, transition poses, targets — stays each side's own) and agrees to 1e-12."""
+    cfg, L, D = (hexapod_config("tripod_gait"), 6, 3) if which == "hexapod" else (octopod_config("wave_gait"), 8, 5)
+    n = 2
+    resync = D > 3
+    ob = oracle.OracleBatch(cfg, n)
+    eng = ref.engine(cfg, n)
+    cs = CommandStream(n, min_len=30, max_len=90)
+    ims = ImuStream(n) if cfg.imu_posing or cfg.inclination_posing else None
+    fs = ForceStream(n, L) if cfg.admittance_control else None
+    for c in range(90):  # walk first: the robots' legs are somewhere else when the sequences begin
+        cmd = cs.next().astype(np.float64)
+        imu = ims.next(cfg.time_delta).astype(np.float64) if ims else None
+        force = fs.next().astype(np.float64) if fs else None
+        ob.step(cmd, imu, force)
+        eng.step(cmd, imu, force)
+    worst = 0.0
+
+    def one(kind, time):
+        nonlocal worst
+        if resync:
+            eng.set_joint_state_from(ob.get_state())
+        j, p = eng.sequence_step(kind, time)
+        po = ob.sequence_step(kind, time)
+        assert np.array_equal(p, po), (kind, p, po)
+        worst = max(worst, float(np.abs(j - ob.joints()).max()))
+        return po
+
+    def run(kind, time=0.0, limit=6000):
+        done = np.zeros(n, dtype=bool)
+        seen = set()
+        for k in range(limit):
+            po = one(kind, time)
+            seen.update(int(v) for v in po)
+            done |= po == 100
+            if done.all():
+                return k + 1, seen
+        raise AssertionError(f"{kind} did not complete")
+
+    loops = {}
+    loops["unpack"], _ = run("unpack", 2.0)
+    loops["start_up 1"], seen1 = run("start_up")
+    loops["shut_down"], seen2 = run("shut_down")
+    loops["start_up 2"], seen3 = run("start_up")
+    assert -1 in seen1 and -1 not in seen3 and -2 not in (seen1 | seen2 | seen3)
+    for k in range(2 * max(1, int(round((1.0 / cfg.step_frequency) / cfg.time_delta)))):
+        one("new_stance", 0.0)
+    for kind in ("pack", "unpack"):
+        loops[kind + " 2"], _ = run(kind, 2.0, limit=400)
+    d = state_diff(eng.get_state(), ob.get_state(), L, D)
+    print(f"[reference-pin] sequences {L}x{D}: loops {loops}, worst joint difference {worst:.2e} rad"
+          + (" (every loop from the oracle's joint state)" if resync else " (free-running)"))
+    assert worst <= (1e-12 if resync else 0.0), worst
+    assert d["joint_position"] <= 1e-12 and d["model_tip_position"] <= 1e-12, d
+    eng.close(); ob.close()
+
+
+# ---- output wire formats (SURVEY.md 8(f) rank 3) -----------------------------------------------------------------------------
+
+@pytest.mark.parametrize("which", ["hexapod", "octopod"])
+def test_publishers_equal_the_reference(ref, oracle, which):
+    """What the reference's OWN publishers put on the wire (publishDesiredJointState, publishLegState, publishVelocity,
+    publishPose, publishRotationPoseError, publishFrameTransforms: state_controller.cpp:777-1047, read off the stand-in
+    message bus and tf broadcaster) against the oracle's restatement of them — the record layout the engine's
+    shc_pack_messages is checked with — along free-running rollouts, with measured joint positions for actual_tip_pose."""
+    cfg, L, D, sensors = (hexapod_config("ripple_gait", auto_posing=1), 6, 3, False) if which == "hexapod" else (octopod_config("tripod_gait"), 8, 5, True)
+    n = 2
+    ob = oracle.OracleBatch(cfg, n)
+    eng = ref.engine(cfg, n)
+    cs = CommandStream(n, min_len=30, max_len=120)
+    ims = ImuStream(n) if sensors else None
+    fs = ForceStream(n, L) if sensors else None
+    rng = np.random.default_rng(8)
+    lo = np.array([[cfg.joint_min[l][j] for j in range(D)] for l in range(L)])
+    hi = np.array([[cfg.joint_max[l][j] for j in range(D)] for l in range(L)])
+    worst = {}
+    for c in range(300):
+        cmd = cs.next().astype(np.float64)
+        imu = ims.next(cfg.time_delta).astype(np.float64) if ims else None
+        force = fs.next().astype(np.float64) if fs else None
+        eng.step(cmd, imu, force)
+        ob.step(cmd, imu, force)
+        if c % 10 != 9:
+            continue
+        measured = lo + (hi - lo) * rng.uniform(0.1, 0.9, size=(n, L, D))
+        for r in range(n):
+            jr, lr, br = eng.robots[r].messages(measured[r])
+            jo, lo_, bo = ob.messages(r, measured[r])
+            d = P._msg_diff(jr, jo)
+            d.update({"body." + k: v for k, v in P._msg_diff(br, bo).items()})
+            for l in range(L):
+                dl = P._msg_diff(lr[l], lo_[l])
+                d.update({"leg." + k: max(v, d.get("leg." + k, 0.0)) for k, v in dl.items()})
+            for k, v in d.items():
+                worst[k] = max(worst.get(k, 0.0), v)
+    top = max(v for k, v in worst.items() if k != "body.rotation_pose_error")
+    print(f"[reference-pin] publishers {L}x{D}: {len(worst)} message fields, worst difference {top:.2e}"
+          f" (rotation_pose_error, float32 on the wire: {worst['body.rotation_pose_error']:.1e})")
+    for k, v in worst.items():
+        tol = 1e-6 if k == "body.rotation_pose_error" else (1e-10 if D > 3 else 1e-12)  # std_msgs/Float32MultiArray
+        assert v <= tol, (k, v)
+    eng.close(); ob.close()
