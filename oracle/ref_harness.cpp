@@ -15,8 +15,10 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <chrono>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ros/ros.h"
@@ -171,7 +173,7 @@ struct RefRobot {
   std::unique_ptr<StateController> sc;
   std::vector<std::string> legs;
   int startup_loops = 0;
-  int uninitialised_params = 0;
+  int id = 0;  // distinguishes the time stamps (hence the tf answers) of requests to different robots of one process
 };
 
 void put3(double* o, const Eigen::Vector3d& v) { o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; }
@@ -189,11 +191,14 @@ extern "C" {
 // start-up has brought the robot to READY (state_controller.cpp:254-281).  As in the restated oracle's harness the robot is
 // then put in RUNNING state directly, so that cycle 0 is the first full loop() in RUNNING state.
 void* shc_ref_create(const shc_config* cfg) {
+  static int next_id = 0;
   RefRobot* r = new RefRobot();
+  r->id = next_id++;
   r->cfg = *cfg;
   r->legs = legNames(cfg->leg_count);
   fillParams(*cfg);
   shc_shim::runtime() = shc_shim::Runtime();
+  shc_shim::tf_table().clear();
   r->sc.reset(new StateController());
   StateController& sc = *r->sc;
   sc.systemStateCallback(int8(OPERATIONAL));
@@ -335,6 +340,33 @@ void shc_ref_set_joint_state(void* h, const double* position, const double* velo
   }
 }
 
+// CPU baseline timing (bench.py --impl reference / cpu_baseline): `cycles` control cycles of n robots with per-cycle
+// commands cmd_seq [cycles][n][3], the robots partitioned once over n_threads std::threads (robots are independent);
+// returns wall seconds.  Each cycle is what ros::spinOnce() + StateController::loop() do for a velocity command.
+double shc_ref_batch_run_seq(void** handles, int n, const double* cmd_seq, int cycles, int n_threads) {
+  auto work = [&](int lo, int hi) {
+    for (int i = lo; i < hi; ++i) {
+      StateController& sc = *static_cast<RefRobot*>(handles[i])->sc;
+      for (int c = 0; c < cycles; ++c) {
+        const double* cmd = cmd_seq + (size_t(c) * n + i) * 3;
+        geometry_msgs::Twist v;
+        v.linear.x = cmd[0]; v.linear.y = cmd[1]; v.angular.z = cmd[2];
+        sc.bodyVelocityInputCallback(v);
+        sc.loop();
+      }
+    }
+  };
+  auto t0 = std::chrono::steady_clock::now();
+  if (n_threads <= 1) {
+    work(0, n);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work, int((long long)n * t / n_threads), int((long long)n * (t + 1) / n_threads));
+    for (auto& t : th) t.join();
+  }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 void shc_ref_get_joints(void* h, double* out) {
   RefRobot* r = static_cast<RefRobot*>(h);
   int k = 0;
@@ -419,16 +451,18 @@ void shc_ref_get_state(void* h, shc_robot_state* s) {
     o.step_plane_defined = leg.step_plane_pose_ != Pose::Undefined();
     if (o.step_plane_defined) put3(o.step_plane_position, leg.step_plane_pose_.position_);
     o.touchdown_detection = st.touchdown_detection_;
-    // An ExternalTarget the reference has not been given is indeterminate memory there (Pose() initialises nothing,
-    // pose.h:21; swing_clearance_ has no initialiser, walk_controller.h:41): reported as the identity record.
+    // An ExternalTarget the reference has never been given (empty frame id) is indeterminate memory there (Pose()
+    // initialises nothing, pose.h:21; swing_clearance_ has no initialiser, walk_controller.h:41): reported as the identity
+    // record.
     const Pose identity = Pose::Identity();
-    putPose(o.external_target_pose, st.external_target_.defined_ ? st.external_target_.pose_ : identity);
-    putPose(o.external_target_transform, st.external_target_.defined_ ? st.external_target_.transform_ : identity);
-    o.external_target_clearance = st.external_target_.defined_ ? st.external_target_.swing_clearance_ : 0.0;
+    const bool tgt = !st.external_target_.frame_id_.empty(), dft = !st.external_default_.frame_id_.empty();
+    putPose(o.external_target_pose, tgt ? st.external_target_.pose_ : identity);
+    putPose(o.external_target_transform, tgt ? st.external_target_.transform_ : identity);
+    o.external_target_clearance = tgt ? st.external_target_.swing_clearance_ : 0.0;
     o.external_target_defined = st.external_target_.defined_;
-    o.external_target_odom_frame = st.external_target_.defined_ && st.external_target_.frame_id_ == "odom_ideal";
-    putPose(o.external_default_pose, st.external_default_.defined_ ? st.external_default_.pose_ : identity);
-    putPose(o.external_default_transform, st.external_default_.defined_ ? st.external_default_.transform_ : identity);
+    o.external_target_odom_frame = tgt && st.external_target_.frame_id_ == "odom_ideal";
+    putPose(o.external_default_pose, dft ? st.external_default_.pose_ : identity);
+    putPose(o.external_default_transform, dft ? st.external_default_.transform_ : identity);
     o.external_default_defined = st.external_default_.defined_;
     put3(o.model_tip_position, leg.current_tip_pose_.position_);
     put3(o.desired_tip_position, leg.desired_tip_pose_.position_);
@@ -472,6 +506,53 @@ void shc_ref_get_startup(void* h, shc_startup* out) {
   out->pose_normaliser = sc.poser_->normaliser_;
   out->auto_pose_reference_leg = sc.poser_->auto_pose_reference_leg_ ? sc.poser_->auto_pose_reference_leg_->getIDNumber() : 0;
   out->startup_loops = r->startup_loops;
+}
+
+// Externally requested swing targets and default tip poses: one TargetTipPose message through targetTipPoseCallback
+// (state_controller.cpp:1706-1768), and — standing for the tf tree generateExternalTargetTransforms looks up every loop
+// (:703-750) — the robot's movement since each request, filed under the request's time stamp.  Per leg: *_defined [L],
+// *_pose / *_transform [L][7] (position, quaternion wxyz), clearance [L], odom_frame [L] (frame "odom_ideal" or "walk_plane").
+void shc_ref_request_tip_targets(void* h, const int* target_defined, const double* target_pose, const double* target_transform,
+                                 const double* clearance, const int* odom_frame, const int* default_defined,
+                                 const double* default_pose, const double* default_transform) {
+  RefRobot* r = static_cast<RefRobot*>(h);
+  const int L = r->cfg.leg_count;
+  syropod_highlevel_controller::TargetTipPose msg;
+  auto toMsg = [](const double* p) {
+    geometry_msgs::Pose m;
+    m.position.x = p[0]; m.position.y = p[1]; m.position.z = p[2];
+    m.orientation.w = p[3]; m.orientation.x = p[4]; m.orientation.y = p[5]; m.orientation.z = p[6];
+    return m;
+  };
+  auto file = [](const std::string& frame, double stamp, const double* t) {
+    geometry_msgs::TransformStamped ts;
+    ts.transform.translation.x = t[0]; ts.transform.translation.y = t[1]; ts.transform.translation.z = t[2];
+    ts.transform.rotation.w = t[3]; ts.transform.rotation.x = t[4]; ts.transform.rotation.y = t[5]; ts.transform.rotation.z = t[6];
+    shc_shim::tf_table()[frame + "@" + std::to_string(stamp) + "<-walk_plane"] = ts;
+  };
+  const geometry_msgs::Pose undefined = Pose::Undefined().toPoseMessage();
+  for (int l = 0; l < L; ++l) {
+    msg.name.push_back(r->legs[l]);
+    geometry_msgs::PoseStamped t, d;
+    t.pose = undefined;
+    d.pose = undefined;
+    if (target_defined[l]) {
+      t.pose = toMsg(target_pose + 7 * l);
+      t.header.frame_id = odom_frame[l] ? "odom_ideal" : "walk_plane";
+      t.header.stamp = ros::Time(1000.0 + 100.0 * r->id + l);
+      file(t.header.frame_id, t.header.stamp.toSec(), target_transform + 7 * l);
+    }
+    if (default_defined[l]) {
+      d.pose = toMsg(default_pose + 7 * l);
+      d.header.frame_id = "walk_plane";
+      d.header.stamp = ros::Time(1050.0 + 100.0 * r->id + l);
+      file(d.header.frame_id, d.header.stamp.toSec(), default_transform + 7 * l);
+    }
+    msg.target.push_back(t);
+    msg.stance.push_back(d);
+    msg.swing_clearance.push_back(clearance[l]);
+  }
+  r->sc->targetTipPoseCallback(msg);
 }
 
 // The reference's publishers (state_controller.cpp:777-1047) run as main.cpp runs them after loop(); what they published is

@@ -57,6 +57,10 @@ def lib():
         L.shc_ref_sequence_step.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.shc_ref_set_joint_state.argtypes = [C.c_void_p, dp, dp]
         L.shc_ref_get_messages.argtypes = [C.c_void_p, dp, C.POINTER(ShcJointStateMsg), C.POINTER(ShcLegStateMsg), C.POINTER(ShcBodyMsg)]
+        ip = C.POINTER(C.c_int)
+        L.shc_ref_request_tip_targets.argtypes = [C.c_void_p, ip, dp, dp, dp, ip, ip, dp, dp]
+        L.shc_ref_batch_run_seq.restype = C.c_double
+        L.shc_ref_batch_run_seq.argtypes = [C.POINTER(C.c_void_p), C.c_int, dp, C.c_int, C.c_int]
         L.shc_ref_get_joints.argtypes = [C.c_void_p, dp]
         L.shc_ref_get_state.argtypes = [C.c_void_p, C.POINTER(ShcRobotState)]
         L.shc_ref_get_startup.argtypes = [C.c_void_p, C.POINTER(ShcStartup)]
@@ -132,6 +136,15 @@ class RefRobot:
         self._lib.shc_ref_get_messages(self._h, _dp(m), C.byref(js), legs, C.byref(body))
         return js, legs, body
 
+    def request_tip_targets(self, target_defined, target_pose, target_transform, clearance, odom_frame, default_defined,
+                            default_pose, default_transform):
+        """One TargetTipPose message (targetTipPoseCallback) plus the tf answers for its requests; arrays per leg."""
+        ints = [np.ascontiguousarray(a, dtype=np.int32) for a in (target_defined, odom_frame, default_defined)]
+        dbl = [_arr(a) for a in (target_pose, target_transform, clearance, default_pose, default_transform)]
+        ipt = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        self._lib.shc_ref_request_tip_targets(self._h, ipt(ints[0]), _dp(dbl[0]), _dp(dbl[1]), _dp(dbl[2]), ipt(ints[1]), ipt(ints[2]),
+                                              _dp(dbl[3]), _dp(dbl[4]))
+
     def joints(self) -> np.ndarray:
         out = np.empty((self.L, self.D), dtype=np.float64)
         self._lib.shc_ref_get_joints(self._h, _dp(out))
@@ -153,3 +166,13 @@ class RefRobot:
         buf = C.create_string_buffer(512)
         n = self._lib.shc_ref_assert_failures(buf, 512)
         return int(n), buf.value.decode()
+
+
+def batch_run_seq(robots, cmd_seq, threads: int = 1) -> float:
+    """All cycles of cmd_seq [cycles, n, 3] for the given RefRobots inside the C library (threads spawned once, robots
+    partitioned over them); returns wall seconds.  The CPU baseline of bench.py: the reference's own loop()."""
+    cmd_seq = _arr(cmd_seq)
+    n = len(robots)
+    assert cmd_seq.ndim == 3 and cmd_seq.shape[1:] == (n, 3)
+    hs = (C.c_void_p * n)(*[r._h for r in robots])
+    return lib().shc_ref_batch_run_seq(hs, n, _dp(cmd_seq), int(cmd_seq.shape[0]), int(threads))

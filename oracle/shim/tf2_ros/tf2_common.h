@@ -1,6 +1,8 @@
 // oracle/shim/tf2_ros/tf2_common.h — TEST INFRASTRUCTURE ONLY: tf2 stand-in.  Broadcasters keep the last transform per
 // child frame; Buffer::lookupTransform answers from a table the harness fills (shc_shim::tf_table()), keyed
-// "target<-source", and throws tf2::TransformException when the harness has not provided one — the reference catches it.
+// "target<-source" (the time-travel form first tries "target@<target time><-source", so that requests stamped at
+// different times can see different robot movements), and throws tf2::TransformException when the harness has not
+// provided one — the reference catches it.
 #ifndef SHC_SHIM_TF2_COMMON_H
 #define SHC_SHIM_TF2_COMMON_H
 #include <map>
@@ -22,9 +24,11 @@ class Buffer {
     if (it == shc_shim::tf_table().end()) throw tf2::TransformException("no transform " + target + "<-" + source);
     return it->second;
   }
-  geometry_msgs::TransformStamped lookupTransform(const std::string& target, const ros::Time&, const std::string& source,
+  geometry_msgs::TransformStamped lookupTransform(const std::string& target, const ros::Time& target_time, const std::string& source,
                                                   const ros::Time&, const std::string&,
                                                   const ros::Duration = ros::Duration(0.0)) const {
+    auto it = shc_shim::tf_table().find(target + "@" + std::to_string(target_time.toSec()) + "<-" + source);
+    if (it != shc_shim::tf_table().end()) return it->second;
     return lookupTransform(target, source, ros::Time(0));
   }
 };

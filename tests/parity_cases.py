@@ -35,6 +35,8 @@ def cfg_for_golden(name):
         return hexapod_config("tripod_gait", 0.02)
     if name.startswith("octopod"):
         return octopod_config("tripod_gait", 0.02)
+    if name.startswith("autopose_tripod"):
+        return hexapod_config("tripod_gait", 0.02, auto_posing=1)
     return hexapod_config(name.split("_")[0] + "_gait", 0.02)
 
 

@@ -1,4 +1,5 @@
-"""CPU: behavioural invariants of the oracle's rollouts and the committed golden fixtures."""
+"""CPU: behavioural invariants of the oracle's rollouts and the committed golden fixtures — outputs of
+the reference's own code (oracle/_ref, tests/golden/make_golden.py), which the oracle must reproduce to 1e-12 rad."""
 import glob
 import os
 
@@ -11,18 +12,15 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def _cfg_for(name):
-    if name.startswith("config1_100hz"):
-        return hexapod_config("tripod_gait", 0.01)
-    if name.startswith("config1_50hz"):
-        return hexapod_config("tripod_gait", 0.02)
-    if name.startswith("octopod"):
-        return octopod_config("tripod_gait", 0.02)
-    return hexapod_config(name.split("_")[0] + "_gait", 0.02)
+    import parity_cases
+
+    return parity_cases.cfg_for_golden(name)
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))), ids=os.path.basename)
 def test_oracle_reproduces_golden(oracle, path):
-    """The oracle still produces the committed vectors (tests/golden/make_golden.py)."""
+    """The oracle reproduces the vectors the REFERENCE produced (tests/golden/make_golden.py runs oracle/_ref)."""
+    assert str(np.load(path)["source"]) == "reference"
     g = np.load(path)
     name = os.path.basename(path)[:-4]
     cfg = _cfg_for(name)

@@ -357,3 +357,67 @@ def test_publishers_equal_the_reference(ref, oracle, which):
         tol = 1e-6 if k == "body.rotation_pose_error" else (1e-10 if D > 3 else 1e-12)  # std_msgs/Float32MultiArray
         assert v <= tol, (k, v)
     eng.close(); ob.close()
+
+
+def test_external_targets_equal_the_reference(ref, oracle):
+    """Rough-terrain mode with externally requested swing targets and default tip poses: the reference takes them through
+    targetTipPoseCallback and looks the robot's movement since the request up in the tf tree every loop
+    (state_controller.cpp:703-750, 1706-1768; the stand-in tf buffer answers with the transform the test filed); the oracle
+    and the engine take pose + transform as state inputs.  Free-running, every state field every cycle."""
+    cfg = hexapod_config("amble_gait", rough_terrain_mode=1, step_depth=0.01)
+    L, D, n = 6, 3, 2
+    ob = oracle.OracleBatch(cfg, n)
+    eng = ref.engine(cfg, n)
+    cs = CommandStream(n, min_len=60, max_len=200)
+    rng = np.random.default_rng(17)
+    worst, used = {}, 0
+    ident = [1.0, 0.0, 0.0, 0.0]
+    for c in range(600):
+        cmd = cs.next().astype(np.float64)
+        st = ob.get_state()
+        if c % 40 == 20:
+            for r in range(n):
+                if st[r].walk_state == 3:  # STOPPED: the reference hands requests to the planner path instead
+                    continue
+                td, od, dd = np.zeros(L, np.int32), np.zeros(L, np.int32), np.zeros(L, np.int32)
+                tp, tt, dp_, dt_ = np.zeros((L, 7)), np.zeros((L, 7)), np.zeros((L, 7)), np.zeros((L, 7))
+                cl = np.zeros(L)
+                for l in range(L):
+                    g = st[r].legs[l]
+                    pick = (r * 11 + l * 5 + c // 40) % 15
+                    if pick < 5:
+                        td[l], od[l] = 1, pick % 2
+                        tp[l] = list(np.array(list(g.target_tip_position)) + rng.uniform(-0.015, 0.015, 3)) + ident
+                        tt[l] = list(rng.uniform(-0.004, 0.004, 3)) + ident
+                        cl[l] = rng.uniform(0.01, 0.03)
+                        g.external_target_pose[:] = list(tp[l])
+                        g.external_target_transform[:] = list(tt[l])
+                        g.external_target_clearance = float(cl[l])
+                        g.external_target_defined, g.external_target_odom_frame = 1, int(od[l])
+                    if pick in (7, 8, 9):
+                        dd[l] = 1
+                        dp_[l] = list(np.array(list(g.default_tip_position)) + rng.uniform(-0.01, 0.01, 3)) + ident
+                        dt_[l] = list(rng.uniform(-0.003, 0.003, 3)) + ident
+                        g.external_default_pose[:] = list(dp_[l])
+                        g.external_default_transform[:] = list(dt_[l])
+                        g.external_default_defined = 1
+                eng.robots[r].request_tip_targets(td, tp, tt, cl, od, dd, dp_, dt_)
+            ob.set_state(st)
+        used += sum(1 for s_ in st for l in range(L) if s_.legs[l].external_target_defined and s_.legs[l].step_state == 0)
+        force = np.zeros((n, L, 3))
+        for r in range(n):
+            for l in range(L):
+                g = st[r].legs[l]
+                early = g.swing_progress > 0.55 + 0.4 * ((r * 7 + l * 3 + c // 50) % 10) / 10.0
+                force[r, l] = (rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5), rng.uniform(2.0, 8.0)) if (g.step_state != 0 or early) else \
+                              (0.0, 0.0, rng.uniform(0.0, 0.05))
+        eng.step(cmd, None, force)
+        ob.step(cmd, None, force)
+        for k, v in state_diff(eng.get_state(), ob.get_state(), L, D).items():
+            worst[k] = max(worst.get(k, 0.0), v)
+    top = max(v for k, v in worst.items() if not k.startswith("int:"))
+    print(f"[reference-pin] external targets: swinging leg-cycles towards an external target {used}, worst field difference {top:.2e}")
+    assert used > 0
+    bad = {k: v for k, v in worst.items() if (v != 0 if k.startswith("int:") else v > 1e-12)}
+    assert not bad, bad
+    eng.close(); ob.close()
