@@ -2,8 +2,8 @@
 // product path (syropod_highlevel_controller_b200/); only tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs may use anything under oracle/.
 //
-// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures, and cannot be compiled here
-// (ROS, Eigen and Boost are absent), so this restatement is the oracle of record.
+// The reference ships no tests, golden vectors or fixtures; the restatement is pinned to the reference's
+// own sources compiled against stand-in headers (oracle/_ref, tests/test_reference_pin.py — see shc_oracle.hpp).
 //
 // Dependency-free IEEE-double restatement of the small part of Eigen 3.3 (unpinned by the reference's
 // CMakeLists.txt:33; 3.3.4 / 3.3.7 ship with the supported ROS distros) that the hot path uses, plus the scalar helpers of

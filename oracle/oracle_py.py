@@ -1,8 +1,10 @@
 """ctypes binding of the CPU parity oracle (oracle/libshc_oracle.so).
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
---impl reference legs.  The product package never imports this module.  PARITY UNPINNED: the
-reference ships no golden vectors and cannot be built here, so this restatement is the oracle of record.
+--impl reference legs.  The product package never imports this module.  The restatement is PINNED to the reference's own
+code: oracle/ref_py.py runs the reference's unmodified sources (compiled against stand-in ROS / Eigen / Boost headers) and
+tests/test_reference_pin.py requires the two to agree on every state field of every cycle; tests/golden/*.npz are the
+reference's outputs.
 """
 from __future__ import annotations
 

@@ -1,8 +1,15 @@
 // shc_oracle.hpp — TEST INFRASTRUCTURE ONLY (parity oracle + CPU baseline).  See oracle_math.hpp for the rules:
 // nothing in the product path may include, link or call this.
 //
-// PARITY UNPINNED: the reference has no tests/golden vectors and cannot be built here; this file is
-// a line-by-line restatement, in IEEE double, of the reference arithmetic for one robot:
+// PARITY PINNED TO THE REFERENCE'S OWN BUILD.  The reference ships no tests or golden vectors and its
+// catkin build needs ROS, tf2, Eigen and Boost, none of which are in the image — but its control sources compile
+// unmodified against self-written stand-ins for those headers (oracle/shim/, oracle/Makefile.ref -> oracle/_ref/
+// libshc_ref.so, driven by oracle/ref_harness.cpp).  tests/test_reference_pin.py runs that library and this restatement
+// side by side: equal start-up constants, every state field of every cycle equal (bit for bit on 3-DOF legs, <= 1e-13
+// rad on 5-DOF legs) over gaits, rates, posing modes, admittance, tip orientation, rough terrain, sequences, publishers;
+// tests/golden/*.npz are outputs of the reference.  What stays restated-from-publication is third-party arithmetic
+// (Eigen kernels, Boost.Odeint RK4): the stand-ins implement the same published formulas.
+// This file is a line-by-line restatement, in IEEE double, of the reference arithmetic for one robot:
 //   Model/Leg/Joint/Link/Tip   src/model.cpp, include/.../model.h
 //   WalkController/LegStepper  src/walk_controller.cpp
 //   PoseController/AutoPoser/LegPoser  src/pose_controller.cpp

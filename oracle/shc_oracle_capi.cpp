@@ -1,5 +1,5 @@
 // shc_oracle_capi.cpp — TEST INFRASTRUCTURE ONLY.  extern "C" surface of the parity oracle for ctypes
-// (tests/, __graft_entry__.smoke(), bench.py cpu_baseline / --impl reference).  PARITY UNPINNED.
+// (tests/, __graft_entry__.smoke(), bench.py cpu_baseline / --impl reference).  PINNED to the reference's own code (oracle/_ref, tests/test_reference_pin.py; see shc_oracle.hpp).
 #include <chrono>
 #include <cstdio>
 #include <thread>

@@ -1,5 +1,5 @@
 // shc_oracle_model.cpp — TEST INFRASTRUCTURE ONLY.  Restates /root/reference/src/model.cpp (+ model.h inline
-// chain helpers) in IEEE double for the parity oracle.  PARITY UNPINNED (see shc_oracle.hpp).
+// chain helpers) in IEEE double for the parity oracle.  PINNED to the reference's own code (oracle/_ref, tests/test_reference_pin.py; see shc_oracle.hpp).
 #include "shc_oracle.hpp"
 
 namespace shc_oracle {

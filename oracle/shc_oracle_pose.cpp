@@ -1,7 +1,7 @@
 // shc_oracle_pose.cpp — TEST INFRASTRUCTURE ONLY.  Restates the per-cycle and direct-start-up parts of
 // /root/reference/src/pose_controller.cpp, all of src/admittance_controller.cpp and the StateController
 // init/loop/transitionRobotState/runningState call order (src/state_controller.cpp:127-447) in IEEE double.
-// PARITY UNPINNED (see shc_oracle.hpp).
+// PINNED to the reference's own code (oracle/_ref, tests/test_reference_pin.py; see shc_oracle.hpp).
 #include "shc_oracle.hpp"
 
 namespace shc_oracle {

@@ -1,5 +1,5 @@
 // shc_oracle_walk.cpp — TEST INFRASTRUCTURE ONLY.  Restates /root/reference/src/walk_controller.cpp in IEEE
-// double for the parity oracle.  PARITY UNPINNED (see shc_oracle.hpp).
+// double for the parity oracle.  PINNED to the reference's own code (oracle/_ref, tests/test_reference_pin.py; see shc_oracle.hpp).
 #include "shc_oracle.hpp"
 
 namespace shc_oracle {

@@ -1,6 +1,7 @@
 // facade_harness.cpp — drives the batched engine through the C++ façade (include/shc_facade.hpp) with the call
 // sequence of the reference's StateController::loop() / runningState() (state_controller.cpp:162-193, 379-447).
-// ROS is absent from the image, so state_controller.cpp itself cannot be compiled; this harness is the stand-in caller.
+// ROS is absent from the image, so state_controller.cpp cannot be built as the node it is (oracle/_ref compiles it against
+// stand-in headers for the parity pin only); this harness is the stand-in caller of the facade.
 //
 //   facade_harness <config.bin> <startup.bin> <n_robots> <cycles> <cmd.bin [cycles][n][3] f32> <out.bin>
 // writes, per cycle, the desired joint positions [n][L][D] (f64, from Joint::desired_position_) followed by each

@@ -1,5 +1,5 @@
 """CPU: the oracle against every known answer derivable by hand from the reference code
-and against independent numpy restatements.  The reference ships no tests or golden vectors (parity unpinned)."""
+and against independent numpy restatements.  The reference ships no tests or golden vectors; the pin to the reference's own code is tests/test_reference_pin.py."""
 import ctypes as C
 import math
 

@@ -15,8 +15,8 @@ over every gait, both control rates, hexapod and octopod, manual posing with the
 and on its own cycle), IMU / inclination posing, admittance with dynamic stiffness, joint-effort tip forces, the
 tip-orientation path and rough-terrain mode with tip forces and range sensors.  The parity cases the CUDA engine is
 checked with (tests/parity_cases.py) are run with the reference as the "backend" as well.  The library can only be built
-where /root/reference exists; the built .so travels with the repo snapshot, and tests/golden/ref_*.npz (made by
-tests/golden/make_ref_golden.py from this library) carry the reference's outputs to machines that have neither.
+where /root/reference exists; the built .so travels with the repo snapshot, and tests/golden/*.npz (made by
+tests/golden/make_golden.py from this library) carry the reference's outputs to machines that have neither.
 """
 import os
 
