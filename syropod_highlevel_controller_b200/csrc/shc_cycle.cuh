@@ -1743,11 +1743,15 @@ template <class P, int D, int MODE> struct Cycle {
           new_wpl = V3<double>{a, b, cc};
           new_wpn = nrm;
         }
-        // stored values as the next cycle will read them; "changed" compares the stored bits
+        // stored values as the next cycle will read them; "changed" compares the stored BITS: the first fit turns the
+        // initial normal (0, 0, 1) into normalized(-0, -0, 1) = (-0, -0, 1), and the legs' saved copies must follow it
+        // (they are exact copies in the reference, walk_controller.cpp:1049) so that a state record does not depend on
+        // which cycles a leg happened to save its plane in
         const V3<S> ol = {sp[(RS_WPL) * 32], sp[(RS_WPL + 1) * 32], sp[(RS_WPL + 2) * 32]};
         const V3<S> on = {sp[(RS_WPN) * 32], sp[(RS_WPN + 1) * 32], sp[(RS_WPN + 2) * 32]};
-        plane_changed = !(ol.x == S(new_wpl.x) && ol.y == S(new_wpl.y) && ol.z == S(new_wpl.z) && on.x == S(new_wpn.x) &&
-                          on.y == S(new_wpn.y) && on.z == S(new_wpn.z));
+        auto same = [](S a, S b) { return a == b && copysign(S(1), a) == copysign(S(1), b); };
+        plane_changed = !(same(ol.x, S(new_wpl.x)) && same(ol.y, S(new_wpl.y)) && same(ol.z, S(new_wpl.z)) &&
+                          same(on.x, S(new_wpn.x)) && same(on.y, S(new_wpn.y)) && same(on.z, S(new_wpn.z)));
         st3(sp, RS_WPL, new_wpl);
         st3(sp, RS_WPN, new_wpn);
         plane_stale = false;

@@ -145,3 +145,44 @@ class Backend:
 
     def engine(self, cfg, n, precision="f64", startup=None):
         return {"gpu": _GpuStepper, "emu": _EmuStepper, "ref": _RefStepper}[self.kind](cfg, n, precision, startup)
+
+
+class RefOracle:
+    """The reference's own code behind the surface the parity cases expect of the ORACLE module (`OracleBatch`): lets a
+    case compare the engine under test with the reference directly instead of through the restated oracle.  Cases that
+    need the oracle's state import (set_state) cannot use it."""
+
+    class OracleBatch:
+        def __init__(self, cfg, n_robots=1):
+            self._s = _RefStepper(cfg, n_robots, "f64", None)
+            self.cfg, self.n = cfg, n_robots
+            self.L, self.D = cfg.leg_count, cfg.joint_count
+            self._j = np.stack([r.joints() for r in self._s.robots])
+
+        def step(self, cmd, imu=None, tip_force=None, manual=None, threads=1):
+            self._j = self._s.step(cmd, imu, tip_force, manual)
+
+        def joints(self):
+            return self._j
+
+        def get_state(self):
+            return self._s.get_state()
+
+        def startup(self):
+            return self._s.startup()
+
+        @property
+        def startup_loops(self):
+            return self._s.robots[0].startup_loops
+
+        def set_pose_reset_mode(self, mode):
+            self._s.set_pose_reset_mode(mode)
+
+        def set_joint_efforts(self, eff):
+            self._s.set_joint_efforts(eff)
+
+        def set_tip_step_planes(self, sp):
+            self._s.set_tip_step_planes(sp)
+
+        def close(self):
+            self._s.close()

@@ -87,3 +87,51 @@ def test_emu_execute_sequence(emu, oracle):
 def test_emu_wire_formats(emu, oracle):
     P.wire_formats(emu, oracle)
 
+
+
+# ---- the kernel source against THE REFERENCE'S OWN CODE (oracle/_ref), without the restated oracle in between ---------------
+
+def _ref_oracle():
+    from oracle import ref_py
+
+    if not ref_py.available():
+        pytest.skip("neither /root/reference nor a prebuilt oracle/_ref is here")
+    ref_py.build()
+    from backends import RefOracle
+
+    return RefOracle
+
+
+def test_emu_against_the_reference_itself_gaits(emu):
+    R = _ref_oracle()
+    P.batch_tripod(emu, R, n=24, cycles=300)
+    P.gait_sweep(emu, R, "ripple_gait", n=16, cycles=600, cap=2e-3)
+
+
+def test_emu_against_the_reference_itself_octopod_and_posing(emu):
+    R = _ref_oracle()
+    P.octopod_full(emu, R, n=8, cycles=300)
+    P.manual_pose_and_reset_modes(emu, R, n=8)
+    P.auto_posing_100hz(emu, R, gaits=("wave_gait",), n=6, cycles=800)
+
+
+def test_emu_imported_state_continues_bit_for_bit(emu):
+    """A second engine that imports the first one's state record ends up in the same state, byte for byte, after the next
+    cycles (the `-m gpu` twin is test_state_range_and_limit_maps): the legs' saved walk planes must not depend on which
+    cycles a leg happened to save them in (sign of zero of the fitted plane normal included)."""
+    from syropod_highlevel_controller_b200.config import hexapod_config
+    from syropod_highlevel_controller_b200.streams import CommandStream
+
+    cfg, n = hexapod_config("tripod_gait"), 64
+    a = emu.engine(cfg, n)
+    cs = CommandStream(n, min_len=20, max_len=60)
+    for c in range(90):
+        a.step(cs.next())
+    b = emu.engine(cfg, n)
+    b.set_state(a.get_state())
+    for c in range(6):
+        cmd = cs.next()
+        ja, jb = a.step(cmd), b.step(cmd)
+        assert (ja == jb).all()
+        assert bytes(a.get_state()) == bytes(b.get_state()), c
+    a.close(); b.close()

@@ -1,7 +1,8 @@
 """GPU: the CUDA control-cycle path (through the C-ABI) against the CPU oracle on identical inputs — the parity tests
-proper.  The cases live in tests/parity_cases.py (shared with the host-emulator CPU tests); the reference cannot be
-built on the GPU box (nor in the build container: ROS/Eigen/Boost absent), so the oracle — pinned by
-tests/test_oracle_*.py and the committed fixtures under tests/golden/ — is the checker."""
+proper.  The cases live in tests/parity_cases.py (shared with the host-emulator CPU tests).  The oracle is the checker: it
+is pinned to the reference's own code (tests/test_reference_pin.py), the fixtures under tests/golden/ are the reference's
+outputs, and the last two tests compare the CUDA path with the reference's own code directly (oracle/_ref is compiled
+from /root/reference in the build container; the prebuilt library travels to the GPU box)."""
 import os
 
 import pytest
@@ -90,3 +91,31 @@ def test_execute_sequence(gpu, oracle):
 def test_wire_formats(gpu, oracle):
     P.wire_formats(gpu, oracle)
 
+
+
+# ---- the CUDA path against THE REFERENCE'S OWN CODE (the prebuilt oracle/_ref travels to the GPU box) ----------------------
+
+def _ref_oracle():
+    from oracle import ref_py
+
+    if not ref_py.available():
+        pytest.skip("oracle/_ref (the reference's own sources, compiled where /root/reference exists) is not here")
+    ref_py.build()
+    from backends import RefOracle
+
+    return RefOracle
+
+
+def test_gpu_against_the_reference_itself_gaits(gpu):
+    R = _ref_oracle()
+    P.batch_tripod(gpu, R, n=48, cycles=300)
+    for gait in ("ripple_gait", "wave_gait", "amble_gait"):
+        P.gait_sweep(gpu, R, gait, n=24, cycles=600, cap=2e-3)
+
+
+def test_gpu_against_the_reference_itself_octopod_and_posing(gpu):
+    R = _ref_oracle()
+    P.octopod_full(gpu, R, n=12, cycles=300)
+    P.manual_pose_and_reset_modes(gpu, R, n=12)
+    P.auto_posing_100hz(gpu, R, gaits=("wave_gait", "tripod_gait"), n=8, cycles=800)
+    P.joint_effort_tip_force(gpu, R, n=12)
