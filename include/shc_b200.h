@@ -88,6 +88,19 @@ int shc_set_state(shc_engine* e, const shc_robot_state* in, size_t n_records);
 int shc_get_state_range(shc_engine* e, size_t first, size_t count, shc_robot_state* out);
 /* The records of the robots [first, first + count) replaced; only the tiles of 32 robots that hold them travel. */
 int shc_set_state_range(shc_engine* e, size_t first, size_t count, const shc_robot_state* in);
+/* Gait switch / parameter change for the whole batch = what StateController::changeGait does once the walker has STOPPED
+ * (state_controller.cpp:513-540: initGaitParameters, WalkController::generateStepCycle + generateLimits — step cycle, the
+ * four limit maps, the legs' phase offsets — and, with auto posing, initAutoPoseParameters + PoseController::
+ * setAutoPoseParams), and what a change of a constants-only adjustable parameter does (swing height / width, step depth,
+ * admittance parameters: state_controller.cpp:451-508 without the step-frequency branch, which re-phases walking legs).
+ * A NEW engine is created for `cfg` (same leg / joint counts, batch size, device and precision as `src`; `startup` as for
+ * shc_create) and the state records of `src` are carried over chunk by chunk, as the reference keeps its state across
+ * changeGait; options and the pose reset mode follow.  `src` is left untouched: the caller destroys it (and re-attaches
+ * gather / NCCL buffers and input latches to the new engine).  Call it in place of the cycle in which changeGait runs: that
+ * loop() of the reference updates no tips (state_controller.cpp:391-395, 427).  Checked against the reference's own
+ * changeGait (tests/test_reference_pin.py, tests/test_gpu_properties.py). */
+int shc_clone_reconfigured(shc_engine* src, const shc_config* cfg, const shc_startup* startup, shc_engine** out);
+
 /* WalkController::set{LinearSpeed,AngularSpeed,LinearAcceleration,AngularAcceleration}LimitMap (walk_controller.h:126-141):
  * replaces the limit tables getLimit (walk_controller.cpp:414) reads, 9 values each (bearings 0..360 step 45); NULL keeps a
  * table.  From the next cycle on. */

@@ -57,6 +57,8 @@ std::vector<std::string> jointNames(int D) {
   return v;
 }
 
+void fillGaitParams(const shc_config& c, const std::string& gait_name);
+
 std::map<std::string, double> adjustable(double v) { return {{"default", v}, {"min", -1e9}, {"max", 1e9}, {"step", 0.0}}; }
 
 // The reference's rosparam tree (config/default.yaml, gait.yaml, auto_pose.yaml layout) from an shc_config.
@@ -95,7 +97,7 @@ void fillParams(const shc_config& c) {
     }
     p.md[P + legs[l] + "_stance_position"] = {{"x", c.stance_x[l]}, {"y", c.stance_y[l]}};
   }
-  p.s[P + "gait_type"] = "harness_gait";
+  p.s[P + "gait_type"] = "tripod_gait";
   p.d[P + "body_clearance"] = c.body_clearance;
   p.md[P + "step_frequency"] = adjustable(c.step_frequency);
   p.md[P + "swing_height"] = adjustable(c.swing_height);
@@ -113,7 +115,7 @@ void fillParams(const shc_config& c) {
   p.b[P + "gravity_aligned_tips"] = c.gravity_aligned_tips;
   p.d[P + "touchdown_threshold"] = c.touchdown_threshold;
   p.d[P + "liftoff_threshold"] = c.liftoff_threshold;
-  p.s[P + "auto_pose_type"] = "harness_pose";
+  p.s[P + "auto_pose_type"] = "auto";
   p.b[P + "start_up_sequence"] = false;
   p.d[P + "time_to_start"] = c.time_to_start;
   p.md[P + "rotation_pid_gains"] = {{"p", c.rotation_pid_p}, {"i", c.rotation_pid_i}, {"d", c.rotation_pid_d}};
@@ -136,14 +138,23 @@ void fillParams(const shc_config& c) {
   for (const char* k : {"debug_move_to_joint_position", "debug_step_to_position", "debug_swing_trajectory", "debug_stance_trajectory",
                         "debug_execute_sequence", "debug_workspace_calculations", "debug_ik"})
     p.b[P + k] = false;
-  const std::string G = "syropod/gait_parameters/harness_gait/";
+  fillGaitParams(c, "tripod_gait");
+}
+
+// Gait and auto-pose parameter sets as gait.yaml / auto_pose.yaml file them: under the gait's name.  The harness uses the
+// four names of the reference's GaitDesignation merely as slots ("tripod_gait" at creation, another one per gait change).
+void fillGaitParams(const shc_config& c, const std::string& gait_name) {
+  shc_shim::ParamTable& p = shc_shim::params();
+  const int L = c.leg_count;
+  const std::vector<std::string> legs = legNames(L);
+  const std::string G = "syropod/gait_parameters/" + gait_name + "/";
   p.i[G + "stance_phase"] = c.stance_phase;
   p.i[G + "swing_phase"] = c.swing_phase;
   p.i[G + "phase_offset"] = c.phase_offset;
   std::map<std::string, int> mult;
   for (int l = 0; l < L; ++l) mult[legs[l]] = c.offset_multiplier[l];
   p.mi[G + "offset_multiplier"] = mult;
-  const std::string A = "syropod/auto_pose_parameters/harness_pose/";
+  const std::string A = "syropod/auto_pose_parameters/" + gait_name + "_pose/";
   p.d[A + "pose_frequency"] = c.pose_frequency;
   p.i[A + "pose_phase_length"] = c.pose_phase_length;
   const int K = c.auto_poser_count;
@@ -220,6 +231,46 @@ void* shc_ref_create(const shc_config* cfg) {
   return r;
 }
 
+// The joint commands of every loop() of the reference's direct start-up for a robot whose joints are at q_init [L][D] when it
+// begins: a joint_states message through jointStatesCallback, then init() / initModel(false) as main.cpp:66-99 does once all
+// joint positions have arrived.  out [max_loops][L][D], one row per loop() from the first that moves the joints; returns
+// the number of rows.
+int shc_ref_startup_trajectory(const shc_config* cfg, const double* q_init, int max_loops, double* out) {
+  fillParams(*cfg);
+  shc_shim::runtime() = shc_shim::Runtime();
+  StateController sc;
+  const int L = cfg->leg_count, D = cfg->joint_count;
+  sc.systemStateCallback(int8(OPERATIONAL));
+  bool use_defaults = true;
+  if (q_init) {
+    sensor_msgs::JointState js;
+    int k = 0;
+    for (auto& lp : *sc.model_->getLegContainer())
+      for (auto& jp : *lp.second->getJointContainer()) {
+        js.name.push_back(jp.second->id_name_);
+        js.position.push_back(q_init[k++] + jp.second->offset_);
+      }
+    sc.jointStatesCallback(js);
+    use_defaults = !sc.jointPositionsInitialised();
+  }
+  sc.init();
+  sc.initModel(use_defaults);
+  int rows = 0, loops = 0;
+  while (sc.robot_state_ != READY && loops < 100000) {
+    sc.robotStateCallback(int8(RUNNING));
+    const bool moving = sc.robot_state_ == PACKED;  // the first loop() only leaves UNKNOWN
+    sc.loop();
+    ++loops;
+    if (moving && rows < max_loops) {
+      int k = 0;
+      for (auto& lp : *sc.model_->getLegContainer())
+        for (auto& jp : *lp.second->getJointContainer()) out[size_t(rows) * L * D + k++] = jp.second->desired_position_;
+      ++rows;
+    }
+  }
+  return rows;
+}
+
 void shc_ref_destroy(void* h) { delete static_cast<RefRobot*>(h); }
 int shc_ref_startup_loops(void* h) { return static_cast<RefRobot*>(h)->startup_loops; }
 long shc_ref_assert_failures(char* first, int cap) {
@@ -256,6 +307,23 @@ void shc_ref_set_joint_efforts(void* h, const double* efforts) {
   }
   sc.jointStatesCallback(js);
 }
+
+// Gait switch (gaitSelectionCallback, then StateController::changeGait inside the following loop() calls: it zeroes the
+// velocity input until the walker has STOPPED, then re-reads the gait and auto-pose parameter sets, regenerates the step
+// cycle, the limit maps and phase offsets and the auto posers — state_controller.cpp:513-540).  new_cfg supplies the new
+// gait / auto-pose block (everything else must be unchanged).  Returns the slot name's index.
+int shc_ref_select_gait(void* h, const shc_config* new_cfg) {
+  RefRobot* r = static_cast<RefRobot*>(h);
+  StateController& sc = *r->sc;
+  static const char* names[] = {"wave_gait", "amble_gait", "ripple_gait", "tripod_gait"};  // GaitDesignation order
+  int slot = (int(sc.gait_selection_) + 1) % 4;
+  if (slot < 0) slot = 0;
+  fillGaitParams(*new_cfg, names[slot]);
+  r->cfg = *new_cfg;
+  sc.gaitSelectionCallback(int8(slot));
+  return slot;
+}
+int shc_ref_gait_change_pending(void* h) { return static_cast<RefRobot*>(h)->sc->gait_change_flag_ ? 1 : 0; }
 
 // One control cycle: inputs through the reference's callbacks, then loop().
 // cmd [3]; imu [10] (quat wxyz, gyro xyz, accel xyz) or NULL; tip_force [L][3] or NULL; manual [6] or NULL;

@@ -61,6 +61,9 @@ def lib():
         L.shc_ref_request_tip_targets.argtypes = [C.c_void_p, ip, dp, dp, dp, ip, ip, dp, dp]
         L.shc_ref_batch_run_seq.restype = C.c_double
         L.shc_ref_batch_run_seq.argtypes = [C.POINTER(C.c_void_p), C.c_int, dp, C.c_int, C.c_int]
+        L.shc_ref_startup_trajectory.argtypes = [C.POINTER(ShcConfig), dp, C.c_int, dp]
+        L.shc_ref_select_gait.argtypes = [C.c_void_p, C.POINTER(ShcConfig)]
+        L.shc_ref_gait_change_pending.argtypes = [C.c_void_p]
         L.shc_ref_get_joints.argtypes = [C.c_void_p, dp]
         L.shc_ref_get_state.argtypes = [C.c_void_p, C.POINTER(ShcRobotState)]
         L.shc_ref_get_startup.argtypes = [C.c_void_p, C.POINTER(ShcStartup)]
@@ -145,6 +148,15 @@ class RefRobot:
         self._lib.shc_ref_request_tip_targets(self._h, ipt(ints[0]), _dp(dbl[0]), _dp(dbl[1]), _dp(dbl[2]), ipt(ints[1]), ipt(ints[2]),
                                               _dp(dbl[3]), _dp(dbl[4]))
 
+    def select_gait(self, new_cfg: ShcConfig):
+        """gaitSelectionCallback: the following loop() calls stop the robot, then StateController::changeGait switches."""
+        self.cfg = new_cfg
+        return self._lib.shc_ref_select_gait(self._h, C.byref(new_cfg))
+
+    @property
+    def gait_change_pending(self) -> bool:
+        return bool(self._lib.shc_ref_gait_change_pending(self._h))
+
     def joints(self) -> np.ndarray:
         out = np.empty((self.L, self.D), dtype=np.float64)
         self._lib.shc_ref_get_joints(self._h, _dp(out))
@@ -176,3 +188,12 @@ def batch_run_seq(robots, cmd_seq, threads: int = 1) -> float:
     assert cmd_seq.ndim == 3 and cmd_seq.shape[1:] == (n, 3)
     hs = (C.c_void_p * n)(*[r._h for r in robots])
     return lib().shc_ref_batch_run_seq(hs, n, _dp(cmd_seq), int(cmd_seq.shape[0]), int(threads))
+
+
+def startup_trajectory(cfg, q_init=None, max_loops: int = 2000):
+    """Joint commands of every loop() of the reference's direct start-up from joint angles q_init [L, D] (None: defaults)."""
+    L, D = cfg.leg_count, cfg.joint_count
+    out = np.zeros((max_loops, L, D))
+    q = None if q_init is None else np.ascontiguousarray(q_init, dtype=np.float64)
+    n = lib().shc_ref_startup_trajectory(C.byref(cfg), _dp(q), max_loops, _dp(out))
+    return out[:n]

@@ -810,6 +810,30 @@ int shc_set_state_range(shc_engine* e, size_t first, size_t count, const shc_rob
 // WalkController::setLinearSpeedLimitMap / setAngularSpeedLimitMap / setLinearAccelerationLimitMap /
 // setAngularAccelerationLimitMap (walk_controller.h:126-141): replaces the four limit tables (9 bearings each, 0..360 in
 // steps of 45 degrees) that getLimit (walk_controller.cpp:414) reads; NULL keeps a table.  Takes effect from the next cycle.
+int shc_clone_reconfigured(shc_engine* src, const shc_config* cfg, const shc_startup* startup, shc_engine** out) {
+  if (!src || !cfg || !out) return fail(SHC_E_INVALID, "shc_clone_reconfigured: bad arguments");
+  if (cfg->leg_count != src->cfg.leg_count || cfg->joint_count != src->cfg.joint_count)
+    return fail(SHC_E_INVALID, "shc_clone_reconfigured: the new configuration must describe the same model (leg and joint counts)");
+  shc_engine* e2 = nullptr;
+  int rc = shc_create(cfg, startup, src->n, src->device, src->precision, &e2);
+  if (rc != SHC_OK) return rc;
+  e2->options = src->options;
+  e2->pose_reset_mode = src->pose_reset_mode;
+  const size_t n = (size_t)src->n, chunk = 8192;  // whole tiles of 32 robots per piece
+  std::vector<shc_robot_state> buf(std::min(n, chunk));
+  for (size_t first = 0; first < n && rc == SHC_OK; first += chunk) {
+    const size_t count = std::min(chunk, n - first);
+    rc = shc_get_state_range(src, first, count, buf.data());
+    if (rc == SHC_OK) rc = shc_set_state_range(e2, first, count, buf.data());
+  }
+  if (rc != SHC_OK) {
+    shc_destroy(e2);
+    return rc;
+  }
+  *out = e2;
+  return SHC_OK;
+}
+
 int shc_set_limit_maps(shc_engine* e, const double* max_linear_speed, const double* max_angular_speed,
                        const double* max_linear_acceleration, const double* max_angular_acceleration) {
   if (!e) return fail(SHC_E_INVALID, "null engine");

@@ -135,3 +135,77 @@ def test_emu_imported_state_continues_bit_for_bit(emu):
         assert (ja == jb).all()
         assert bytes(a.get_state()) == bytes(b.get_state()), c
     a.close(); b.close()
+
+
+def _gait_change_case(backend, switch, n=4):
+    """StateController::changeGait of the reference (gaitSelectionCallback; the robot is stopped, then the step cycle, limit
+    maps, phase offsets and auto posers are regenerated, state_controller.cpp:513-540) against the engine's way of doing
+    it: a new engine for the new gait that carries the old one's state (`switch(engine, new_cfg)`).  Tripod -> wave with
+    auto posing, walking before and after."""
+    import numpy as np
+
+    from gpu_common import JOINT_FIELDS, JointErrors, assert_state_close
+    from oracle import ref_py
+    from syropod_highlevel_controller_b200.config import ShcRobotState, hexapod_config
+    from syropod_highlevel_controller_b200.streams import CommandStream
+
+    if not ref_py.available():
+        pytest.skip("neither /root/reference nor a prebuilt oracle/_ref is here")
+    ref_py.build()
+    cfg_a, cfg_b = hexapod_config("tripod_gait", auto_posing=1), hexapod_config("wave_gait", auto_posing=1)
+    refs = [ref_py.RefRobot(cfg_a) for _ in range(n)]
+    eng = backend.engine(cfg_a, n, startup=refs[0].startup())
+    cs = CommandStream(n, min_len=60, max_len=200)
+    errs = JointErrors()
+
+    def ref_states():
+        arr = (ShcRobotState * n)()
+        for i, r in enumerate(refs):
+            arr[i] = r.get_state()
+        return arr
+
+    def step(e, cmd):
+        j = e.step(cmd)
+        for i, r in enumerate(refs):
+            r.step(cmd[i].astype(np.float64))
+        errs.add(np.abs(j - np.stack([r.joints() for r in refs])))
+
+    for c in range(300):
+        step(eng, cs.next())
+    # The batch is brought to rest first (zero velocity input, as changeGait itself would force), then the gait selection
+    # arrives: the next loop() of every reference robot runs changeGait and updates no tips (state_controller.cpp:391-395,
+    # 427) — the engine takes no cycle for it.
+    for k in range(3000):
+        if all(s.walk_state == 3 for s in ref_states()):
+            break
+        step(eng, np.zeros((n, 3), dtype=np.float32))
+    for r in refs:
+        r.select_gait(cfg_b)
+        r.step(np.zeros(3))
+    assert not any(r.gait_change_pending for r in refs)
+    eng2 = switch(eng, cfg_b)  # the state carried into an engine for the new gait
+    eng.close()
+    su_ref, su = refs[0].startup(), eng2.startup()
+    assert (su.period, su.swing_period, su.stance_period) == (su_ref.period, su_ref.swing_period, su_ref.stance_period)
+    assert list(su.phase_offsets)[:6] == list(su_ref.phase_offsets)[:6]
+    for f in ("max_linear_speed", "max_angular_speed", "max_linear_acceleration", "max_angular_acceleration", "walkspace"):
+        assert np.abs(np.array(list(getattr(su, f))) - np.array(list(getattr(su_ref, f)))).max() < 1e-7, f
+    assert_state_close(eng2.get_state(), ref_states(), 6, 3, 1e-9, skip=JOINT_FIELDS)
+    for c in range(700):
+        step(eng2, cs.next())
+    errs.check(max_fraction=2e-3, label="gait change tripod -> wave against the reference's changeGait")
+    st = ref_states()
+    assert_state_close(eng2.get_state(), st, 6, 3, 1e-8, skip=JOINT_FIELDS)
+    assert {s.walk_state for s in st} & {0, 1, 2}  # walking again under the new gait
+    eng2.close()
+    for r in refs:
+        r.close()
+
+
+def test_emu_gait_change_against_the_reference(emu):
+    def switch(eng, cfg):
+        new = emu.engine(cfg, eng.n, startup=None)  # the engine's own constants for the new gait
+        new.set_state(eng.get_state())
+        return new
+
+    _gait_change_case(emu, switch)

@@ -281,3 +281,23 @@ def test_host_entry_point_tile_ranges_and_pinned_buffers(shc_lib):
     assert bytes(a.get_state()) == bytes(b.get_state()) == bytes(c_.get_state())
     for e in (a, b, c_):
         e.close()
+
+
+def test_clone_reconfigured_gait_change_against_the_reference(shc_lib):
+    """shc_clone_reconfigured (Engine.reconfigured): a batch-wide gait switch on the B200 against the reference's own
+    StateController::changeGait (oracle/_ref), walking before and after — the case of tests/test_emu_parity.py through the
+    C-ABI.  Also: a model mismatch is refused and the source engine stays usable."""
+    import test_emu_parity as T
+    from backends import Backend
+    from syropod_highlevel_controller_b200.config import octopod_config
+    from syropod_highlevel_controller_b200.engine import ShcError
+
+    def switch(stepper, cfg):
+        new = stepper.__class__.__new__(stepper.__class__)
+        new.torch, new.n = stepper.torch, stepper.n
+        new.eng = stepper.eng.reconfigured(cfg)  # the engine's own constants for the new gait
+        with pytest.raises(ShcError):
+            stepper.eng.reconfigured(octopod_config())
+        return new
+
+    T._gait_change_case(Backend("gpu"), switch, n=6)

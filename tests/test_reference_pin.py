@@ -421,3 +421,20 @@ def test_external_targets_equal_the_reference(ref, oracle):
     bad = {k: v for k, v in worst.items() if (v != 0 if k.startswith("int:") else v > 1e-12)}
     assert not bad, bad
     eng.close(); ob.close()
+
+
+@pytest.mark.parametrize("which", ["hexapod", "octopod"])
+def test_direct_startup_trajectory_equals_the_reference(ref, oracle, which):
+    """The direct start-up (PoseController::directStartup, pose_controller.cpp:463; jointStatesCallback + initModel(false)
+    before it) from joint angles other than the defaults: the joint commands of every loop()."""
+    cfg = hexapod_config("tripod_gait") if which == "hexapod" else octopod_config("tripod_gait")
+    L, D = cfg.leg_count, cfg.joint_count
+    rng = np.random.default_rng(4)
+    lo = np.array([[cfg.joint_min[l][j] for j in range(D)] for l in range(L)])
+    hi = np.array([[cfg.joint_max[l][j] for j in range(D)] for l in range(L)])
+    for trial in range(3):
+        q0 = None if trial == 0 else lo + (hi - lo) * rng.uniform(0.15, 0.85, size=(L, D))
+        a = ref_py.startup_trajectory(cfg, q0)
+        b = oracle.startup_trajectory(cfg, q0)
+        assert a.shape == b.shape and len(a) == int(round(cfg.time_to_start / cfg.time_delta))
+        assert np.abs(a - b).max() <= (1e-12 if D > 3 else 0.0), np.abs(a - b).max()
