@@ -96,9 +96,14 @@ int shc_set_state_range(shc_engine* e, size_t first, size_t count, const shc_rob
  * A NEW engine is created for `cfg` (same leg / joint counts, batch size, device and precision as `src`; `startup` as for
  * shc_create) and the state records of `src` are carried over chunk by chunk, as the reference keeps its state across
  * changeGait; options and the pose reset mode follow.  `src` is left untouched: the caller destroys it (and re-attaches
- * gather / NCCL buffers and input latches to the new engine).  Call it in place of the cycle in which changeGait runs: that
- * loop() of the reference updates no tips (state_controller.cpp:391-395, 427).  Checked against the reference's own
- * changeGait (tests/test_reference_pin.py, tests/test_gpu_properties.py). */
+ * gather / NCCL buffers and input latches to the new engine).  Timing, as in the reference: a gait change takes the place of
+ * one cycle (the loop() in which changeGait runs updates no tips, state_controller.cpp:391-395, 427) once every robot has
+ * STOPPED; walk parameters act in the loop() that applies them (switch before that cycle); admittance parameters one loop
+ * later (updateAdmittance has run when runningState() applies them: switch after that cycle); step_frequency with the batch
+ * at rest (re-phasing walking legs, LegStepper::updatePhase, is not supported; nor is the reference's deferral of the new
+ * step cycle while its signed velocity test fails, state_controller.cpp:489-491 — that decision is the caller's, with
+ * shc_set_limit_maps for the interim speed limits).  Checked against the reference's own changeGait / adjustParameter
+ * (tests/test_emu_parity.py on the host, tests/test_gpu_properties.py on the B200). */
 int shc_clone_reconfigured(shc_engine* src, const shc_config* cfg, const shc_startup* startup, shc_engine** out);
 
 /* WalkController::set{LinearSpeed,AngularSpeed,LinearAcceleration,AngularAcceleration}LimitMap (walk_controller.h:126-141):

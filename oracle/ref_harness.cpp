@@ -325,6 +325,37 @@ int shc_ref_select_gait(void* h, const shc_config* new_cfg) {
 }
 int shc_ref_gait_change_pending(void* h) { return static_cast<RefRobot*>(h)->sc->gait_change_flag_ ? 1 : 0; }
 
+// Adjustable parameters (step_frequency, swing_height, swing_width, step_depth, stance_span_modifier, virtual_mass,
+// virtual_stiffness, virtual_damping_ratio, force_gain): one dynamic_reconfigure request carrying new_cfg's values through
+// dynamicParameterCallback (state_controller.cpp:1465-1548), which picks the FIRST parameter that differs;
+// StateController::adjustParameter applies it inside the following loop() (state_controller.cpp:451-508).  Returns 1 if a
+// parameter differed.
+int shc_ref_adjust_parameter(void* h, const shc_config* new_cfg) {
+  RefRobot* r = static_cast<RefRobot*>(h);
+  StateController& sc = *r->sc;
+  syropod_highlevel_controller::DynamicConfig c;
+  c.step_frequency = new_cfg->step_frequency;
+  c.swing_height = new_cfg->swing_height;
+  c.swing_width = new_cfg->swing_width;
+  c.step_depth = new_cfg->step_depth;
+  c.stance_span_modifier = new_cfg->stance_span_modifier;
+  c.virtual_mass = new_cfg->virtual_mass;
+  c.virtual_stiffness = new_cfg->virtual_stiffness;
+  c.virtual_damping_ratio = new_cfg->virtual_damping_ratio;
+  c.force_gain = new_cfg->force_gain;
+  const Parameters& p = sc.params_;
+  const bool differs = c.step_frequency != p.step_frequency.current_value || c.swing_height != p.swing_height.current_value ||
+                       c.swing_width != p.swing_width.current_value || c.step_depth != p.step_depth.current_value ||
+                       c.stance_span_modifier != p.stance_span_modifier.current_value || c.virtual_mass != p.virtual_mass.current_value ||
+                       c.virtual_stiffness != p.virtual_stiffness.current_value ||
+                       c.virtual_damping_ratio != p.virtual_damping_ratio.current_value || c.force_gain != p.force_gain.current_value;
+  if (!differs) return 0;
+  sc.dynamicParameterCallback(c, 0);
+  r->cfg = *new_cfg;
+  return 1;
+}
+int shc_ref_parameter_adjust_pending(void* h) { return static_cast<RefRobot*>(h)->sc->parameter_adjust_flag_ ? 1 : 0; }
+
 // One control cycle: inputs through the reference's callbacks, then loop().
 // cmd [3]; imu [10] (quat wxyz, gyro xyz, accel xyz) or NULL; tip_force [L][3] or NULL; manual [6] or NULL;
 // step_plane [L][3] or NULL.

@@ -64,6 +64,8 @@ def lib():
         L.shc_ref_startup_trajectory.argtypes = [C.POINTER(ShcConfig), dp, C.c_int, dp]
         L.shc_ref_select_gait.argtypes = [C.c_void_p, C.POINTER(ShcConfig)]
         L.shc_ref_gait_change_pending.argtypes = [C.c_void_p]
+        L.shc_ref_adjust_parameter.argtypes = [C.c_void_p, C.POINTER(ShcConfig)]
+        L.shc_ref_parameter_adjust_pending.argtypes = [C.c_void_p]
         L.shc_ref_get_joints.argtypes = [C.c_void_p, dp]
         L.shc_ref_get_state.argtypes = [C.c_void_p, C.POINTER(ShcRobotState)]
         L.shc_ref_get_startup.argtypes = [C.c_void_p, C.POINTER(ShcStartup)]
@@ -156,6 +158,16 @@ class RefRobot:
     @property
     def gait_change_pending(self) -> bool:
         return bool(self._lib.shc_ref_gait_change_pending(self._h))
+
+    def adjust_parameter(self, new_cfg: ShcConfig) -> bool:
+        """One dynamic_reconfigure request with new_cfg's adjustable parameters (the first that differs is taken);
+        StateController::adjustParameter applies it inside the following loop()."""
+        self.cfg = new_cfg
+        return bool(self._lib.shc_ref_adjust_parameter(self._h, C.byref(new_cfg)))
+
+    @property
+    def parameter_adjust_pending(self) -> bool:
+        return bool(self._lib.shc_ref_parameter_adjust_pending(self._h))
 
     def joints(self) -> np.ndarray:
         out = np.empty((self.L, self.D), dtype=np.float64)

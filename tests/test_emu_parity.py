@@ -209,3 +209,97 @@ def test_emu_gait_change_against_the_reference(emu):
         return new
 
     _gait_change_case(emu, switch)
+
+
+PARAMETER_CHANGES = [
+    # (model, base overrides, changed parameter, at rest?, cycles the reference lags, first command after the change)
+    ("hexapod", {}, dict(swing_height=0.035), False, 0, None),
+    ("hexapod", {}, dict(swing_width=0.02), False, 0, None),
+    ("hexapod", dict(rough_terrain_mode=1, step_depth=0.01), dict(step_depth=0.02), False, 0, None),
+    ("hexapod", {}, dict(stance_span_modifier=0.3), True, 0, None),
+    ("hexapod", {}, dict(step_frequency=1.5), True, 0, (0.7, 0.2, 0.3)),
+    ("octopod", {}, dict(virtual_stiffness=20.0), False, 1, None),
+    ("octopod", {}, dict(force_gain=0.3), False, 1, None),
+    ("octopod", {}, dict(virtual_mass=15.0), False, 1, None),
+    ("octopod", {}, dict(virtual_damping_ratio=1.2), False, 1, None),
+]
+
+
+def _parameter_change_case(backend, switch, model, base, change, at_rest, lag, first_cmd, n=3):
+    """StateController::adjustParameter of the reference (a dynamic_reconfigure request through dynamicParameterCallback,
+    applied inside the next loop(), state_controller.cpp:451-508, 1465-1548) against the engine's way of changing a
+    batch-wide parameter: a new engine for the new value that carries the state (`switch`).  Timing as in the reference:
+      * walk parameters (swing height / width, step depth; stance span modifier at rest) act in the loop() that applies them;
+      * admittance parameters act one loop later (updateAdmittance has already run when runningState() applies them);
+      * step_frequency at rest: regenerated step cycle, limit maps and phase offsets.  The reference defers this while a
+        SIGNED, component-wise velocity test fails (state_controller.cpp:489-491: a robot commanded backwards keeps its old
+        step cycle with the new speed limits); the case commands forwards.  Re-phasing WALKING legs (LegStepper::updatePhase)
+        is not supported by the engine: the batch is stopped first, as for a gait change."""
+    import numpy as np
+
+    from gpu_common import JOINT_FIELDS, JointErrors, assert_state_close
+    from oracle import ref_py
+    from syropod_highlevel_controller_b200.config import ShcRobotState, hexapod_config, octopod_config
+    from syropod_highlevel_controller_b200.streams import CommandStream, ForceStream, ImuStream
+
+    if not ref_py.available():
+        pytest.skip("neither /root/reference nor a prebuilt oracle/_ref is here")
+    ref_py.build()
+    make = hexapod_config if model == "hexapod" else octopod_config
+    cfg_a, cfg_b = make("tripod_gait", **base), make("tripod_gait", **dict(base, **change))
+    L, D = cfg_a.leg_count, cfg_a.joint_count
+    refs = [ref_py.RefRobot(cfg_a) for _ in range(n)]
+    eng = backend.engine(cfg_a, n, startup=refs[0].startup())
+    cs = CommandStream(n, min_len=60, max_len=200)
+    ims = ImuStream(n) if cfg_a.imu_posing or cfg_a.inclination_posing else None
+    fs = ForceStream(n, L) if cfg_a.admittance_control else None
+    errs = JointErrors()
+
+    def ref_states():
+        arr = (ShcRobotState * n)()
+        for i, r in enumerate(refs):
+            arr[i] = r.get_state()
+        return arr
+
+    def step(e, cmd):
+        imu = ims.next(cfg_a.time_delta) if ims else None
+        f = fs.next() if fs else None
+        j = e.step(cmd, imu, f)
+        for i, r in enumerate(refs):
+            r.step(cmd[i].astype(np.float64), None if imu is None else imu[i].astype(np.float64), None if f is None else f[i].astype(np.float64))
+        errs.add(np.abs(j - np.stack([r.joints() for r in refs])))
+
+    for c in range(200):
+        step(eng, cs.next())
+    if at_rest:
+        for k in range(3000):
+            if all(s.walk_state == 3 for s in ref_states()):
+                break
+            step(eng, np.zeros((n, 3), dtype=np.float32))
+    for r in refs:
+        assert r.adjust_parameter(cfg_b)
+    for k in range(lag):
+        step(eng, cs.next())
+    eng2 = switch(eng, cfg_b)
+    eng.close()
+    if first_cmd is not None:
+        for c in range(40):
+            step(eng2, np.tile(np.array(first_cmd, dtype=np.float32), (n, 1)))
+    for c in range(500):
+        step(eng2, cs.next())
+    assert not any(r.parameter_adjust_pending for r in refs)
+    errs.check(max_fraction=2e-3, label=f"{model}: {change} against the reference's adjustParameter")
+    assert_state_close(eng2.get_state(), ref_states(), L, D, 1e-8, skip=JOINT_FIELDS)
+    eng2.close()
+    for r in refs:
+        r.close()
+
+
+@pytest.mark.parametrize("model,base,change,at_rest,lag,first_cmd", PARAMETER_CHANGES, ids=[",".join(c[2]) for c in PARAMETER_CHANGES])
+def test_emu_parameter_change_against_the_reference(emu, model, base, change, at_rest, lag, first_cmd):
+    def switch(eng, cfg):
+        new = emu.engine(cfg, eng.n, startup=None)
+        new.set_state(eng.get_state())
+        return new
+
+    _parameter_change_case(emu, switch, model, base, change, at_rest, lag, first_cmd)

@@ -296,8 +296,11 @@ def test_clone_reconfigured_gait_change_against_the_reference(shc_lib):
         new = stepper.__class__.__new__(stepper.__class__)
         new.torch, new.n = stepper.torch, stepper.n
         new.eng = stepper.eng.reconfigured(cfg)  # the engine's own constants for the new gait
-        with pytest.raises(ShcError):
-            stepper.eng.reconfigured(octopod_config())
+        with pytest.raises(ShcError):  # another model is refused, the source engine stays usable
+            stepper.eng.reconfigured(octopod_config() if stepper.eng.L == 6 else hexapod_config())
         return new
 
     T._gait_change_case(Backend("gpu"), switch, n=6)
+    # constants-only parameters and a step-frequency change at rest, against the reference's adjustParameter
+    for model, base, change, at_rest, lag, first_cmd in T.PARAMETER_CHANGES[:1] + T.PARAMETER_CHANGES[3:6]:
+        T._parameter_change_case(Backend("gpu"), switch, model, base, change, at_rest, lag, first_cmd, n=4)
