@@ -473,8 +473,10 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = {"value": n * world * e2e_steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": n * (3 + (10 + 3 * L if octo else 0)) * 4,
            "d2h_bytes_per_step": n * L * D * 4, "steps": e2e_steps,
-           "api": "shc_step_host (C-ABI, page-locked host buffers: H2D of the commands, one kernel launch whose TMA bulk "
-                  "stores write each tile's joint angles straight into the caller's page-locked buffer over PCIe, stream sync)",
+           "api": "shc_step_host (C-ABI, page-locked host buffers: every step the kernel's warps read their robots' velocity "
+                  "commands from the caller's buffer over PCIe (IMU / tip-force records go up by a host-to-device copy first), "
+                  "one kernel launch whose TMA bulk stores write each tile's joint angles straight into the caller's "
+                  "page-locked buffer over PCIe, stream sync)",
            "gpu_launches_per_step": 1}
 
     io_bytes = (3 + (10 + 3 * L if octo else 0) + L * D) * 4

@@ -945,25 +945,46 @@ int shc_step_host(shc_engine* e, const float* cmd, const float* imu, const float
     CUDA_TRY(cudaMemcpyAsync(dev, from, bytes, cudaMemcpyHostToDevice, st));
     return SHC_OK;
   };
-  if ((rc = upload(cmd, e->h_cmd, e->d_cmd, n * 3 * 4)) != SHC_OK) return rc;
-  if (imu && (rc = upload(imu, e->h_imu, e->d_imu, n * 10 * 4)) != SHC_OK) return rc;
-  if (tip_force && (rc = upload(tip_force, e->h_force, e->d_force, n * L * 3 * 4)) != SHC_OK) return rc;
-  if (manual && (rc = upload(manual, e->h_manual, e->d_manual, n * 6 * 4)) != SHC_OK) return rc;
-
   const bool out_pinned = host_pinned(joints_out);
   // Page-locked output: the kernel's TMA bulk stores can target the caller's buffer directly (mapped host memory, same
   // address under UVA), so the joint angles cross PCIe as posted writes while the rest of the batch is still being
   // computed — one launch, no D2H copy.  SHC_HOST_ZEROCOPY=0 keeps the tile-range / copy-engine path below.
   static const bool zero_copy = [] { const char* v = getenv("SHC_HOST_ZEROCOPY"); return !(v && v[0] == '0'); }();
-  if (out_pinned && zero_copy) {
-    float* alias = nullptr;
-    if (cudaHostGetDevicePointer((void**)&alias, joints_out, 0) == cudaSuccess && alias) {
-      StepIO io = make_io(e, e->d_cmd, imu ? e->d_imu : nullptr, tip_force ? e->d_force : nullptr, manual ? e->d_manual : nullptr, alias);
-      if ((rc = launch_cycle(e, io, st)) != SHC_OK) return rc;
-      CUDA_TRY(cudaStreamSynchronize(st));
-      return SHC_OK;
+  // Page-locked inputs, same idea in the other direction for the SMALL records: each tile's warp reads its 32 robots'
+  // velocity commands (12 B per robot; manual-pose inputs, 24 B) straight from the caller's buffer over PCIe in its
+  // prologue instead of waiting behind a host-to-device copy of the whole batch: +5.7 % end to end on the hexapod shard
+  // (4.98e8 -> 5.26e8 steps/s, profiles/r2ae_zero_copy_inputs.log).  The IMU and tip-force records (40 + 12 L bytes per
+  // robot) stay on the copy engine: read in place they cost the octopod 7 % (SHC_HOST_ZEROCOPY_IN=2 reads everything
+  // in place, =0 copies everything).
+  static const int zero_copy_in = [] { const char* v = getenv("SHC_HOST_ZEROCOPY_IN"); return v ? atoi(v) : 1; }();
+  float* alias = nullptr;
+  const bool direct_out = out_pinned && zero_copy && cudaHostGetDevicePointer((void**)&alias, joints_out, 0) == cudaSuccess && alias;
+  if (!direct_out) cudaGetLastError();
+  auto input = [&](const float* src, float* staging, float* dev, size_t bytes, bool small, const float** use) -> int {
+    *use = nullptr;
+    if (!src) return SHC_OK;
+    if (direct_out && zero_copy_in >= (small ? 1 : 2) && host_pinned(src)) {
+      float* a = nullptr;
+      if (cudaHostGetDevicePointer((void**)&a, const_cast<float*>(src), 0) == cudaSuccess && a) {
+        *use = a;
+        return SHC_OK;
+      }
+      cudaGetLastError();
     }
-    cudaGetLastError();
+    *use = dev;
+    return upload(src, staging, dev, bytes);
+  };
+  const float *cmd_d, *imu_d, *force_d, *manual_d;
+  if ((rc = input(cmd, e->h_cmd, e->d_cmd, n * 3 * 4, true, &cmd_d)) != SHC_OK) return rc;
+  if ((rc = input(imu, e->h_imu, e->d_imu, n * 10 * 4, false, &imu_d)) != SHC_OK) return rc;
+  if ((rc = input(tip_force, e->h_force, e->d_force, n * L * 3 * 4, false, &force_d)) != SHC_OK) return rc;
+  if ((rc = input(manual, e->h_manual, e->d_manual, n * 6 * 4, true, &manual_d)) != SHC_OK) return rc;
+
+  if (direct_out) {
+    StepIO io = make_io(e, cmd_d, imu_d, force_d, manual_d, alias);
+    if ((rc = launch_cycle(e, io, st)) != SHC_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return SHC_OK;
   }
   float* down = out_pinned ? joints_out : e->h_out;
   StepIO io = make_io(e, e->d_cmd, imu ? e->d_imu : nullptr, tip_force ? e->d_force : nullptr, manual ? e->d_manual : nullptr, e->d_out);
