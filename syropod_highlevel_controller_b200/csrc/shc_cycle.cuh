@@ -49,11 +49,6 @@ struct StepIO {
                              // the D2H copy of one range overlaps the arithmetic of the next (shc_step_host)
   int* flags_out;          // [N] or null
   int pose_reset_mode;
-  // shc_step_host's copy-engine pipeline: when set, every tile bumps chunk_done[tile / chunk_tiles] once its joint commands
-  // are in joints_out, and the device-to-host copy of a chunk starts (a stream wait on that counter) while later tiles
-  // are still being computed
-  int* chunk_done;
-  int chunk_tiles;
 #ifdef SHC_TRACE
   unsigned long long* trace;  // kernel-tuning builds only (-DSHC_TRACE): [tiles][32] globaltimer stamps written by lane 0
 #endif

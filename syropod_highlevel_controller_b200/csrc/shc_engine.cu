@@ -94,13 +94,6 @@ __global__ void SHC_KERNEL_BOUNDS control_cycle_kernel(const __grid_constant__ C
   }
   for (int p = 0; p < io.n_gather; ++p) put(io.gather[p] + io.gather_offset + base);
   if (any_bulk && lane == 0) bulk_commit_and_wait_read();  // shared memory may go away once the TMA unit has read it
-  if (io.chunk_done) {
-    // the tile's stores have to be complete (not merely read out of shared memory) and visible before the counter moves
-    if (any_bulk && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) atomicAdd(io.chunk_done + tile / io.chunk_tiles, 1);
-  }
 #ifdef SHC_TRACE
   if (io.trace && lane == 0) io.trace[(size_t)tile * 32 + 31] = gtimer();
 #endif
@@ -358,8 +351,6 @@ struct shc_engine {
   const float* d_step_planes = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t copy = nullptr;                       // D2H of shc_step_host, behind the tile-range kernels
-  int* d_chunk_done = nullptr;                       // shc_step_host copy-engine pipeline: tiles finished per chunk (monotonic)
-  unsigned host_pipeline_steps = 0;
   cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // pinned staging for shc_step_host
   float *h_cmd = nullptr, *h_imu = nullptr, *h_force = nullptr, *h_manual = nullptr, *h_out = nullptr;
@@ -708,7 +699,6 @@ void shc_destroy(shc_engine* e) {
   for (int b = 0; b < kGatherBuffers; ++b) {
     if (e->ev_kernel[b]) cudaEventDestroy(e->ev_kernel[b]);
   }
-  if (e->d_chunk_done) cudaFree(e->d_chunk_done);
   for (auto ev : e->ev_chunk)
     if (ev) cudaEventDestroy(ev);
   if (e->stream) cudaStreamSynchronize(e->stream);
@@ -884,8 +874,6 @@ static StepIO make_io(shc_engine* e, const float* cmd, const float* imu, const f
   io.gather_mc = nullptr;
   for (auto& g : io.gather) g = nullptr;
 
-  io.chunk_done = nullptr;
-  io.chunk_tiles = 1;
   io.flags_out = (e->options & SHC_OPT_STATUS_FLAGS) ? e->d_flags : nullptr;
   io.pose_reset_mode = e->pose_reset_mode;
 #ifdef SHC_TRACE
@@ -927,19 +915,6 @@ static int ensure_staging(shc_engine* e, bool imu, bool force, bool manual) {
 }
 
 // Page-locked (cudaMallocHost / cudaHostRegister) host memory can be the source / target of the DMA directly.
-// cuStreamWaitValue32 of the driver already loaded in the process (no link-time dependency on libcuda)
-typedef int (*StreamWaitValue32Fn)(cudaStream_t, unsigned long long, unsigned, unsigned);
-static StreamWaitValue32Fn stream_wait_value32() {
-  static StreamWaitValue32Fn fn = [] {
-    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_NOLOAD);
-    if (!h) h = dlopen("libcuda.so.1", RTLD_NOW);
-    StreamWaitValue32Fn f = h ? (StreamWaitValue32Fn)dlsym(h, "cuStreamWaitValue32_v2") : nullptr;
-    if (!f && h) f = (StreamWaitValue32Fn)dlsym(h, "cuStreamWaitValue32");
-    return f;
-  }();
-  return fn;
-}
-
 static bool host_pinned(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -982,16 +957,13 @@ int shc_step_host(shc_engine* e, const float* cmd, const float* imu, const float
   // robot) stay on the copy engine: read in place they cost the octopod 7 % (SHC_HOST_ZEROCOPY_IN=2 reads everything
   // in place, =0 copies everything).
   static const int zero_copy_in = [] { const char* v = getenv("SHC_HOST_ZEROCOPY_IN"); return v ? atoi(v) : 1; }();
-  static const int pipeline_chunks = [] { const char* v = getenv("SHC_HOST_PIPELINE"); return v ? std::min(16, std::max(0, atoi(v))) : 0; }();
-  const int tiles_all = (int)((n + 31) / 32);
-  const bool pipeline_ok = pipeline_chunks >= 1 && out_pinned && tiles_all >= 64 * pipeline_chunks && stream_wait_value32() != nullptr;
   float* alias = nullptr;
-  const bool direct_out = !pipeline_ok && out_pinned && zero_copy && cudaHostGetDevicePointer((void**)&alias, joints_out, 0) == cudaSuccess && alias;
+  const bool direct_out = out_pinned && zero_copy && cudaHostGetDevicePointer((void**)&alias, joints_out, 0) == cudaSuccess && alias;
   if (!direct_out) cudaGetLastError();
   auto input = [&](const float* src, float* staging, float* dev, size_t bytes, bool small, const float** use) -> int {
     *use = nullptr;
     if (!src) return SHC_OK;
-    if ((direct_out || pipeline_ok) && zero_copy_in >= (small ? 1 : 2) && host_pinned(src)) {
+    if (direct_out && zero_copy_in >= (small ? 1 : 2) && host_pinned(src)) {
       float* a = nullptr;
       if (cudaHostGetDevicePointer((void**)&a, const_cast<float*>(src), 0) == cudaSuccess && a) {
         *use = a;
@@ -1008,34 +980,6 @@ int shc_step_host(shc_engine* e, const float* cmd, const float* imu, const float
   if ((rc = input(tip_force, e->h_force, e->d_force, n * L * 3 * 4, false, &force_d)) != SHC_OK) return rc;
   if ((rc = input(manual, e->h_manual, e->d_manual, n * 6 * 4, true, &manual_d)) != SHC_OK) return rc;
 
-  // Copy-engine pipeline (SHC_HOST_PIPELINE=<chunks>): ONE launch writes the joint commands to device memory, every tile bumps its
-  // chunk's counter, and the copy stream moves chunk k to the caller's page-locked buffer as soon as a stream wait on that
-  // counter passes — the DMA engine (56 GB/s into page-locked memory on this box) instead of the SMs' posted writes
-  // (45 GB/s), at the price of starting only when a whole chunk of tiles has finished.
-  if (pipeline_ok) {
-    const int kPipelineChunks = pipeline_chunks;
-    if (!e->d_chunk_done) {
-      CUDA_TRY(cudaMalloc(&e->d_chunk_done, 64 * sizeof(int)));
-      CUDA_TRY(cudaMemset(e->d_chunk_done, 0, 64 * sizeof(int)));
-      CUDA_TRY(cudaDeviceSynchronize());
-    }
-    StepIO io = make_io(e, cmd_d, imu_d, force_d, manual_d, e->d_out);
-    io.chunk_done = e->d_chunk_done;
-    io.chunk_tiles = (tiles_all + kPipelineChunks - 1) / kPipelineChunks;
-    const unsigned step = ++e->host_pipeline_steps;
-    if ((rc = launch_cycle(e, io, st)) != SHC_OK) return rc;
-    for (int k = 0; k < kPipelineChunks; ++k) {
-      const int t0 = k * io.chunk_tiles, t1 = std::min(tiles_all, (k + 1) * io.chunk_tiles);
-      if (t0 >= t1) break;
-      if (stream_wait_value32()(e->copy, (unsigned long long)(uintptr_t)(e->d_chunk_done + k), step * (unsigned)(t1 - t0), 0 /* GEQ */) != 0)
-        return fail(SHC_E_CUDA, "shc_step_host: cuStreamWaitValue32 failed");
-      const size_t r0 = (size_t)t0 * 32, r1 = std::min((size_t)t1 * 32, n);
-      CUDA_TRY(cudaMemcpyAsync(joints_out + r0 * L * D, e->d_out + r0 * L * D, (r1 - r0) * L * D * 4, cudaMemcpyDeviceToHost, e->copy));
-    }
-    CUDA_TRY(cudaStreamSynchronize(e->copy));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    return SHC_OK;
-  }
   if (direct_out) {
     StepIO io = make_io(e, cmd_d, imu_d, force_d, manual_d, alias);
     if ((rc = launch_cycle(e, io, st)) != SHC_OK) return rc;
