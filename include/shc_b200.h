@@ -102,7 +102,8 @@ int shc_set_state_range(shc_engine* e, size_t first, size_t count, const shc_rob
  * later (updateAdmittance has run when runningState() applies them: switch after that cycle); step_frequency with the batch
  * at rest (re-phasing walking legs, LegStepper::updatePhase, is not supported; nor is the reference's deferral of the new
  * step cycle while its signed velocity test fails, state_controller.cpp:489-491 — that decision is the caller's, with
- * shc_set_limit_maps for the interim speed limits).  Checked against the reference's own changeGait / adjustParameter
+ * shc_set_limit_maps for the interim speed limits): SHC_E_UNSUPPORTED if the step cycle changes while a robot is not
+ * STOPPED.  Checked against the reference's own changeGait / adjustParameter
  * (tests/test_emu_parity.py on the host, tests/test_gpu_properties.py on the B200). */
 int shc_clone_reconfigured(shc_engine* src, const shc_config* cfg, const shc_startup* startup, shc_engine** out);
 

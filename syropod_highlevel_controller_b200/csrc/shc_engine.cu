@@ -819,11 +819,25 @@ int shc_clone_reconfigured(shc_engine* src, const shc_config* cfg, const shc_sta
   if (rc != SHC_OK) return rc;
   e2->options = src->options;
   e2->pose_reset_mode = src->pose_reset_mode;
+  // A new step cycle (gait or step frequency) is only taken over by robots at rest: the reference re-phases walking legs
+  // (LegStepper::updatePhase) and defers per robot, neither of which a batch-wide switch reproduces.
+  const shc_startup &a = src->su, &b = e2->su;
+  bool cycle_changed = a.period != b.period || a.swing_period != b.swing_period || a.stance_period != b.stance_period ||
+                       a.stance_end != b.stance_end || a.swing_start != b.swing_start || a.swing_end != b.swing_end ||
+                       a.stance_start != b.stance_start;
+  for (int l = 0; l < cfg->leg_count; ++l) cycle_changed = cycle_changed || a.phase_offsets[l] != b.phase_offsets[l];
   const size_t n = (size_t)src->n, chunk = 8192;  // whole tiles of 32 robots per piece
   std::vector<shc_robot_state> buf(std::min(n, chunk));
   for (size_t first = 0; first < n && rc == SHC_OK; first += chunk) {
     const size_t count = std::min(chunk, n - first);
     rc = shc_get_state_range(src, first, count, buf.data());
+    if (rc == SHC_OK && cycle_changed)
+      for (size_t i = 0; i < count; ++i)
+        if (buf[i].walk_state != 3 /* STOPPED */) {
+          rc = fail(SHC_E_UNSUPPORTED, "shc_clone_reconfigured: the step cycle changes (gait or step frequency) and robot " +
+                                           std::to_string(first + i) + " is not STOPPED: stop the batch first");
+          break;
+        }
     if (rc == SHC_OK) rc = shc_set_state_range(e2, first, count, buf.data());
   }
   if (rc != SHC_OK) {

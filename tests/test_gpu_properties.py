@@ -301,6 +301,19 @@ def test_clone_reconfigured_gait_change_against_the_reference(shc_lib):
         return new
 
     T._gait_change_case(Backend("gpu"), switch, n=6)
+    # a new step cycle is refused while a robot is walking (the reference would re-phase its legs); constants-only changes pass
+    import torch
+
+    eng = _engine(hexapod_config("tripod_gait"), 64)
+    fwd = torch.tensor([[0.6, 0.0, 0.1]], device="cuda").repeat(64, 1)
+    for c in range(150):
+        eng.step(fwd)
+    with pytest.raises(ShcError, match="not STOPPED"):
+        eng.reconfigured(hexapod_config("wave_gait"))
+    with pytest.raises(ShcError, match="not STOPPED"):
+        eng.reconfigured(hexapod_config("tripod_gait", step_frequency=1.4))
+    eng.reconfigured(hexapod_config("tripod_gait", swing_height=0.03)).close()
+    eng.close()
     # constants-only parameters and a step-frequency change at rest, against the reference's adjustParameter
     for model, base, change, at_rest, lag, first_cmd in T.PARAMETER_CHANGES[:1] + T.PARAMETER_CHANGES[3:6]:
         T._parameter_change_case(Backend("gpu"), switch, model, base, change, at_rest, lag, first_cmd, n=4)
