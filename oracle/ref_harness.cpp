@@ -179,6 +179,8 @@ void fillGaitParams(const shc_config& c, const std::string& gait_name) {
   p.vd[A + "yaw_amplitudes"] = std::vector<double>(c.yaw_amplitudes, c.yaw_amplitudes + K);
 }
 
+bool g_transition_through_loop = false;
+
 struct RefRobot {
   shc_config cfg;
   std::unique_ptr<StateController> sc;
@@ -218,6 +220,9 @@ void* shc_ref_create(const shc_config* cfg) {
   // Leg::virtual_stiffness_ has no initialiser in the reference (model.h:516; first written by updateStiffness,
   // admittance_controller.cpp:103): zero until then, as in the restated oracle and the engine's state record.
   for (auto& lp : *sc.model_->getLegContainer()) lp.second->virtual_stiffness_ = 0.0;
+  // StateController::linear_velocity_input_ has no initialiser either (state_controller.h:366; angular_velocity_input_ has):
+  // "no command received yet" is zero
+  sc.linear_velocity_input_ = Eigen::Vector2d::Zero();
   int loops = 0;
   while (sc.robot_state_ != READY && loops < 100000) {
     sc.robotStateCallback(int8(RUNNING));
@@ -225,11 +230,24 @@ void* shc_ref_create(const shc_config* cfg) {
     ++loops;
   }
   r->startup_loops = loops;
+  if (g_transition_through_loop) {
+    // READY -> RUNNING the reference's own way (state_controller.cpp:283-288): START pressed again, and the loop() that makes
+    // the transition also runs its first runningState() — with a zero velocity input, since bodyVelocityInputCallback
+    // ignores commands before RUNNING (state_controller.cpp:1129)
+    sc.robotStateCallback(int8(RUNNING));
+    sc.loop();
+    return r;
+  }
   sc.robot_state_ = RUNNING;
   sc.new_robot_state_ = RUNNING;
   sc.transition_state_flag_ = false;
   return r;
 }
+
+// 1: the robots created from now on enter RUNNING through robotStateCallback + loop() (one control cycle with a zero command
+// has then already run); 0 (default): RUNNING is set directly, so that cycle 0 is the caller's.  tests/test_reference_pin.py
+// shows the two to be the same state one zero-command cycle apart.
+void shc_ref_transition_through_loop(int on) { g_transition_through_loop = on != 0; }
 
 // The joint commands of every loop() of the reference's direct start-up for a robot whose joints are at q_init [L][D] when it
 // begins: a joint_states message through jointStatesCallback, then init() / initModel(false) as main.cpp:66-99 does once all

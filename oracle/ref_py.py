@@ -85,11 +85,15 @@ def _arr(a):
 class RefRobot:
     """One instance of the reference's StateController, taken through its direct start-up and put in RUNNING state."""
 
-    def __init__(self, cfg: ShcConfig):
+    def __init__(self, cfg: ShcConfig, transition_through_loop: bool = False):
+        """transition_through_loop: READY -> RUNNING by robotStateCallback + loop() as the node does it (that loop() already
+        runs one control cycle with a zero command); default: RUNNING set directly, cycle 0 is the caller's."""
         self.cfg = cfg
         self.L, self.D = cfg.leg_count, cfg.joint_count
         self._lib = lib()
+        self._lib.shc_ref_transition_through_loop(int(transition_through_loop))
         self._h = self._lib.shc_ref_create(C.byref(cfg))
+        self._lib.shc_ref_transition_through_loop(0)
 
     def close(self):
         if self._h:

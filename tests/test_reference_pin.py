@@ -438,3 +438,32 @@ def test_direct_startup_trajectory_equals_the_reference(ref, oracle, which):
         b = oracle.startup_trajectory(cfg, q0)
         assert a.shape == b.shape and len(a) == int(round(cfg.time_to_start / cfg.time_delta))
         assert np.abs(a - b).max() <= (1e-12 if D > 3 else 0.0), np.abs(a - b).max()
+
+
+@pytest.mark.parametrize("cfg", [hexapod_config("tripod_gait"), hexapod_config("wave_gait", 0.01, auto_posing=1), octopod_config("tripod_gait")],
+                         ids=["hexapod", "hexapod-autopose-100hz", "octopod"])
+def test_running_state_shortcut_equals_the_references_own_transition(ref, cfg):
+    """The harnesses (this one and the oracle's) put the robot in RUNNING state directly after the direct start-up.  The
+    reference's own READY -> RUNNING transition (robotStateCallback + loop(), state_controller.cpp:283-288) is that plus one
+    control cycle with a zero command: same state record afterwards, bit for bit, and the same rollout from there."""
+    L, D = cfg.leg_count, cfg.joint_count
+    a = ref_py.RefRobot(cfg)                                # RUNNING set directly ...
+    a.step(np.zeros(3))                                     # ... then one zero-command cycle
+    b = ref_py.RefRobot(cfg, transition_through_loop=True)  # the reference's own transition
+    from syropod_highlevel_controller_b200.config import ShcRobotState
+
+    def rec(r):
+        arr = (ShcRobotState * 1)()
+        arr[0] = r.get_state()
+        return arr
+
+    d = state_diff(rec(a), rec(b), L, D)
+    assert all(v == 0 for v in d.values()), {k: v for k, v in d.items() if v != 0}
+    cs = CommandStream(1, min_len=40, max_len=120)
+    for c in range(300):
+        cmd = cs.next()[0].astype(np.float64)
+        a.step(cmd)
+        b.step(cmd)
+    d = state_diff(rec(a), rec(b), L, D)
+    assert all(v == 0 for v in d.values()), {k: v for k, v in d.items() if v != 0}
+    a.close(); b.close()
