@@ -105,7 +105,11 @@ int shc_set_state_range(shc_engine* e, size_t first, size_t count, const shc_rob
  * shc_set_limit_maps for the interim speed limits): SHC_E_UNSUPPORTED if the step cycle changes while a robot is not
  * STOPPED.  Checked against the reference's own changeGait / adjustParameter
  * (tests/test_emu_parity.py on the host, tests/test_gpu_properties.py on the B200). */
-int shc_clone_reconfigured(shc_engine* src, const shc_config* cfg, const shc_startup* startup, shc_engine** out);
+enum { SHC_RECONF_KEEP_POSE_CYCLE = 1 }; /* adjustParameter semantics: the auto-pose cycle (pose phase length and normaliser,
+                                          * PoseController::setAutoPoseParams) is NOT regenerated — the reference re-runs it
+                                          * in changeGait only, so a step-frequency change leaves a synchronised auto-pose
+                                          * cycle at its old length (state_controller.cpp:451-508 vs :513-540) */
+int shc_clone_reconfigured(shc_engine* src, const shc_config* cfg, const shc_startup* startup, int flags, shc_engine** out);
 
 /* WalkController::set{LinearSpeed,AngularSpeed,LinearAcceleration,AngularAcceleration}LimitMap (walk_controller.h:126-141):
  * replaces the limit tables getLimit (walk_controller.cpp:414) reads, 9 values each (bearings 0..360 step 45); NULL keeps a

@@ -284,9 +284,17 @@ class Batch {
   /// StateController::changeGait for the whole batch (state_controller.cpp:513-540), or a change of a constants-only
   /// adjustable parameter: the engine is replaced by one for the new parameters that carries the state over
   /// (shc_clone_reconfigured).  As in the reference, switch once every robot's walker has STOPPED, in place of a cycle.
-  void changeGait(const Parameters& params, const shc_startup* startup = nullptr) {
+  void changeGait(const Parameters& params, const shc_startup* startup = nullptr) { reconfigure(params, startup, 0); }
+  /// StateController::adjustParameter for the whole batch (state_controller.cpp:451-508): as changeGait, but the auto-pose
+  /// cycle keeps its length (the reference regenerates it in changeGait only).
+  void adjustParameter(const Parameters& params, const shc_startup* startup = nullptr) {
+    reconfigure(params, startup, SHC_RECONF_KEEP_POSE_CYCLE);
+  }
+
+ private:
+  void reconfigure(const Parameters& params, const shc_startup* startup, int flags) {
     shc_engine* e2 = nullptr;
-    if (shc_clone_reconfigured(e_, &params.cfg, startup, &e2) != SHC_OK)
+    if (shc_clone_reconfigured(e_, &params.cfg, startup, flags, &e2) != SHC_OK)
       throw std::runtime_error(std::string("shc_clone_reconfigured: ") + shc_last_error());
     shc_destroy(e_);
     e_ = e2;
@@ -294,6 +302,7 @@ class Batch {
     std::fill(fetched_.begin(), fetched_.end(), -1);
   }
 
+ public:
   Controllers& robot(int r) { return robots_.at(r); }
   int size() const { return n_; }
   shc_engine* engine() { return e_; }

@@ -810,12 +810,21 @@ int shc_set_state_range(shc_engine* e, size_t first, size_t count, const shc_rob
 // WalkController::setLinearSpeedLimitMap / setAngularSpeedLimitMap / setLinearAccelerationLimitMap /
 // setAngularAccelerationLimitMap (walk_controller.h:126-141): replaces the four limit tables (9 bearings each, 0..360 in
 // steps of 45 degrees) that getLimit (walk_controller.cpp:414) reads; NULL keeps a table.  Takes effect from the next cycle.
-int shc_clone_reconfigured(shc_engine* src, const shc_config* cfg, const shc_startup* startup, shc_engine** out) {
+int shc_clone_reconfigured(shc_engine* src, const shc_config* cfg, const shc_startup* startup, int flags, shc_engine** out) {
   if (!src || !cfg || !out) return fail(SHC_E_INVALID, "shc_clone_reconfigured: bad arguments");
   if (cfg->leg_count != src->cfg.leg_count || cfg->joint_count != src->cfg.joint_count)
     return fail(SHC_E_INVALID, "shc_clone_reconfigured: the new configuration must describe the same model (leg and joint counts)");
   shc_engine* e2 = nullptr;
-  int rc = shc_create(cfg, startup, src->n, src->device, src->precision, &e2);
+  int rc;
+  shc_startup su;
+  if (flags & SHC_RECONF_KEEP_POSE_CYCLE) {
+    if (startup) su = *startup;
+    else if ((rc = shc_compute_startup(cfg, &su)) != SHC_OK) return rc;
+    su.pose_phase_length = src->su.pose_phase_length;  // PoseController::setAutoPoseParams is not re-run (adjustParameter)
+    su.pose_normaliser = src->su.pose_normaliser;
+    startup = &su;
+  }
+  rc = shc_create(cfg, startup, src->n, src->device, src->precision, &e2);
   if (rc != SHC_OK) return rc;
   e2->options = src->options;
   e2->pose_reset_mode = src->pose_reset_mode;

@@ -50,7 +50,7 @@ def lib():
         L.shc_direct_startup.argtypes = [vp, vp, vp, vp]
         L.shc_set_tip_step_planes.argtypes = [vp, vp]
         L.shc_set_state_range.argtypes = [vp, C.c_size_t, C.c_size_t, C.POINTER(ShcRobotState)]
-        L.shc_clone_reconfigured.argtypes = [vp, C.POINTER(ShcConfig), C.POINTER(ShcStartup), C.POINTER(vp)]
+        L.shc_clone_reconfigured.argtypes = [vp, C.POINTER(ShcConfig), C.POINTER(ShcStartup), C.c_int, C.POINTER(vp)]
         L.shc_step_to_new_stance.argtypes = [vp, vp, vp, vp]
         L.shc_sequence_reset.argtypes = [vp]
         L.shc_execute_sequence.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int), vp]
@@ -182,17 +182,19 @@ class Engine:
         except Exception:
             pass
 
-    def reconfigured(self, cfg: ShcConfig, startup: Optional[ShcStartup] = None) -> "Engine":
+    def reconfigured(self, cfg: ShcConfig, startup: Optional[ShcStartup] = None, keep_pose_cycle: bool = False) -> "Engine":
         """A NEW engine for `cfg` (same model, batch size, device, precision) that carries this engine's state: the batch-
         wide gait switch of StateController::changeGait (state_controller.cpp:513-540) or a change of a constants-only
         parameter.  Call it in place of the cycle in which the reference switches (that loop() updates no tips), with every
-        robot STOPPED for a gait change, and close() this engine afterwards.  shc_clone_reconfigured in include/shc_b200.h."""
+        robot STOPPED for a gait change, and close() this engine afterwards.  keep_pose_cycle: adjustParameter semantics (the
+        auto-pose cycle length is not regenerated; the reference does that in changeGait only).  shc_clone_reconfigured in
+        include/shc_b200.h."""
         new = Engine.__new__(Engine)
         new.torch, new.cfg, new.n = self.torch, cfg, self.n
         new.L, new.D, new.device, new.precision = self.L, self.D, self.device, self.precision
         new._h = C.c_void_p()
         _check(lib().shc_clone_reconfigured(self._h, C.byref(cfg), C.byref(startup) if startup is not None else None,
-                                            C.byref(new._h)))
+                                            1 if keep_pose_cycle else 0, C.byref(new._h)))
         new.joints = self.torch.empty((self.n, self.L, self.D), dtype=self.torch.float32, device=self.device)
         return new
 

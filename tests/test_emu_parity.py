@@ -183,7 +183,7 @@ def _gait_change_case(backend, switch, n=4):
         r.select_gait(cfg_b)
         r.step(np.zeros(3))
     assert not any(r.gait_change_pending for r in refs)
-    eng2 = switch(eng, cfg_b)  # the state carried into an engine for the new gait
+    eng2 = switch(eng, cfg_b, False)  # the state carried into an engine for the new gait
     eng.close()
     su_ref, su = refs[0].startup(), eng2.startup()
     assert (su.period, su.swing_period, su.stance_period) == (su_ref.period, su_ref.swing_period, su_ref.stance_period)
@@ -202,13 +202,23 @@ def _gait_change_case(backend, switch, n=4):
         r.close()
 
 
-def test_emu_gait_change_against_the_reference(emu):
-    def switch(eng, cfg):
-        new = emu.engine(cfg, eng.n, startup=None)  # the engine's own constants for the new gait
+def _emu_switch(emu):
+    def switch(eng, cfg, keep_pose_cycle):
+        from syropod_highlevel_controller_b200.engine import compute_startup
+
+        su = compute_startup(cfg)  # the engine's own constants for the new parameters
+        if keep_pose_cycle:
+            old = eng.startup()
+            su.pose_phase_length, su.pose_normaliser = old.pose_phase_length, old.pose_normaliser
+        new = emu.engine(cfg, eng.n, startup=su)
         new.set_state(eng.get_state())
         return new
 
-    _gait_change_case(emu, switch)
+    return switch
+
+
+def test_emu_gait_change_against_the_reference(emu):
+    _gait_change_case(emu, _emu_switch(emu))
 
 
 PARAMETER_CHANGES = [
@@ -218,6 +228,8 @@ PARAMETER_CHANGES = [
     ("hexapod", dict(rough_terrain_mode=1, step_depth=0.01), dict(step_depth=0.02), False, 0, None),
     ("hexapod", {}, dict(stance_span_modifier=0.3), True, 0, None),
     ("hexapod", {}, dict(step_frequency=1.5), True, 0, (0.7, 0.2, 0.3)),
+    # with auto posing the reference keeps the OLD pose cycle length (setAutoPoseParams is re-run by changeGait only)
+    ("hexapod", dict(auto_posing=1), dict(step_frequency=1.5), True, 0, (0.7, 0.2, 0.3)),
     ("octopod", {}, dict(virtual_stiffness=20.0), False, 1, None),
     ("octopod", {}, dict(force_gain=0.3), False, 1, None),
     ("octopod", {}, dict(virtual_mass=15.0), False, 1, None),
@@ -280,7 +292,7 @@ def _parameter_change_case(backend, switch, model, base, change, at_rest, lag, f
         assert r.adjust_parameter(cfg_b)
     for k in range(lag):
         step(eng, cs.next())
-    eng2 = switch(eng, cfg_b)
+    eng2 = switch(eng, cfg_b, True)  # adjustParameter: the auto-pose cycle is not regenerated
     eng.close()
     if first_cmd is not None:
         for c in range(40):
@@ -295,11 +307,6 @@ def _parameter_change_case(backend, switch, model, base, change, at_rest, lag, f
         r.close()
 
 
-@pytest.mark.parametrize("model,base,change,at_rest,lag,first_cmd", PARAMETER_CHANGES, ids=[",".join(c[2]) for c in PARAMETER_CHANGES])
+@pytest.mark.parametrize("model,base,change,at_rest,lag,first_cmd", PARAMETER_CHANGES, ids=[",".join(c[2]) + ("+autopose" if c[1].get("auto_posing") else "") for c in PARAMETER_CHANGES])
 def test_emu_parameter_change_against_the_reference(emu, model, base, change, at_rest, lag, first_cmd):
-    def switch(eng, cfg):
-        new = emu.engine(cfg, eng.n, startup=None)
-        new.set_state(eng.get_state())
-        return new
-
-    _parameter_change_case(emu, switch, model, base, change, at_rest, lag, first_cmd)
+    _parameter_change_case(emu, _emu_switch(emu), model, base, change, at_rest, lag, first_cmd)

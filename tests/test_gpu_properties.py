@@ -292,10 +292,10 @@ def test_clone_reconfigured_gait_change_against_the_reference(shc_lib):
     from syropod_highlevel_controller_b200.config import octopod_config
     from syropod_highlevel_controller_b200.engine import ShcError
 
-    def switch(stepper, cfg):
+    def switch(stepper, cfg, keep_pose_cycle):
         new = stepper.__class__.__new__(stepper.__class__)
         new.torch, new.n = stepper.torch, stepper.n
-        new.eng = stepper.eng.reconfigured(cfg)  # the engine's own constants for the new gait
+        new.eng = stepper.eng.reconfigured(cfg, keep_pose_cycle=keep_pose_cycle)  # the engine's own constants for the new parameters
         with pytest.raises(ShcError):  # another model is refused, the source engine stays usable
             stepper.eng.reconfigured(octopod_config() if stepper.eng.L == 6 else hexapod_config())
         return new
@@ -315,5 +315,5 @@ def test_clone_reconfigured_gait_change_against_the_reference(shc_lib):
     eng.reconfigured(hexapod_config("tripod_gait", swing_height=0.03)).close()
     eng.close()
     # constants-only parameters and a step-frequency change at rest, against the reference's adjustParameter
-    for model, base, change, at_rest, lag, first_cmd in T.PARAMETER_CHANGES[:1] + T.PARAMETER_CHANGES[3:6]:
+    for model, base, change, at_rest, lag, first_cmd in T.PARAMETER_CHANGES[:1] + T.PARAMETER_CHANGES[3:7]:
         T._parameter_change_case(Backend("gpu"), switch, model, base, change, at_rest, lag, first_cmd, n=4)
