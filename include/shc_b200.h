@@ -98,7 +98,9 @@ int shc_set_state_range(shc_engine* e, size_t first, size_t count, const shc_rob
  * changeGait; options and the pose reset mode follow.  `src` is left untouched: the caller destroys it (and re-attaches
  * gather / NCCL buffers and input latches to the new engine).  Timing, as in the reference: a gait change takes the place of
  * one cycle (the loop() in which changeGait runs updates no tips, state_controller.cpp:391-395, 427) once every robot has
- * STOPPED; walk parameters act in the loop() that applies them (switch before that cycle); admittance parameters one loop
+ * STOPPED — that loop() of the reference still runs its pose and admittance stages, so with IMU posing or admittance
+ * control active the reference's IMU PID and admittance filters are one step ahead of the engine's after the switch (4.5e-4
+ * rad of imu_pose in the octopod test configuration); without them the switch is exact; walk parameters act in the loop() that applies them (switch before that cycle); admittance parameters one loop
  * later (updateAdmittance has run when runningState() applies them: switch after that cycle); step_frequency with the batch
  * at rest (re-phasing walking legs, LegStepper::updatePhase, is not supported; nor is the reference's deferral of the new
  * step cycle while its signed velocity test fails, state_controller.cpp:489-491 — that decision is the caller's, with

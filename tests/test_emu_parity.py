@@ -137,7 +137,7 @@ def test_emu_imported_state_continues_bit_for_bit(emu):
     a.close(); b.close()
 
 
-def _gait_change_case(backend, switch, n=4):
+def _gait_change_case(backend, switch, n=4, model="hexapod"):
     """StateController::changeGait of the reference (gaitSelectionCallback; the robot is stopped, then the step cycle, limit
     maps, phase offsets and auto posers are regenerated, state_controller.cpp:513-540) against the engine's way of doing
     it: a new engine for the new gait that carries the old one's state (`switch(engine, new_cfg)`).  Tripod -> wave with
@@ -146,13 +146,19 @@ def _gait_change_case(backend, switch, n=4):
 
     from gpu_common import JOINT_FIELDS, JointErrors, assert_state_close
     from oracle import ref_py
-    from syropod_highlevel_controller_b200.config import ShcRobotState, hexapod_config
-    from syropod_highlevel_controller_b200.streams import CommandStream
+    from syropod_highlevel_controller_b200.config import ShcRobotState, hexapod_config, octopod_config
+    from syropod_highlevel_controller_b200.streams import CommandStream, ForceStream, ImuStream
 
     if not ref_py.available():
         pytest.skip("neither /root/reference nor a prebuilt oracle/_ref is here")
     ref_py.build()
-    cfg_a, cfg_b = hexapod_config("tripod_gait", auto_posing=1), hexapod_config("wave_gait", auto_posing=1)
+    if model == "hexapod":
+        cfg_a, cfg_b = hexapod_config("tripod_gait", auto_posing=1), hexapod_config("wave_gait", auto_posing=1)
+    else:  # 8 x 5 with admittance, IMU and inclination posing
+        cfg_a, cfg_b = octopod_config("tripod_gait"), octopod_config("ripple_gait")
+    L, D = cfg_a.leg_count, cfg_a.joint_count
+    ims = ImuStream(n) if cfg_a.imu_posing or cfg_a.inclination_posing else None
+    fs = ForceStream(n, L) if cfg_a.admittance_control else None
     refs = [ref_py.RefRobot(cfg_a) for _ in range(n)]
     eng = backend.engine(cfg_a, n, startup=refs[0].startup())
     cs = CommandStream(n, min_len=60, max_len=200)
@@ -165,9 +171,11 @@ def _gait_change_case(backend, switch, n=4):
         return arr
 
     def step(e, cmd):
-        j = e.step(cmd)
+        imu = ims.next(cfg_a.time_delta) if ims else None
+        f = fs.next() if fs else None
+        j = e.step(cmd, imu, f)
         for i, r in enumerate(refs):
-            r.step(cmd[i].astype(np.float64))
+            r.step(cmd[i].astype(np.float64), None if imu is None else imu[i].astype(np.float64), None if f is None else f[i].astype(np.float64))
         errs.add(np.abs(j - np.stack([r.joints() for r in refs])))
 
     for c in range(300):
@@ -179,23 +187,25 @@ def _gait_change_case(backend, switch, n=4):
         if all(s.walk_state == 3 for s in ref_states()):
             break
         step(eng, np.zeros((n, 3), dtype=np.float32))
-    for r in refs:
+    for i, r in enumerate(refs):
         r.select_gait(cfg_b)
-        r.step(np.zeros(3))
+        imu = ims.next(cfg_a.time_delta) if ims else None  # the pose and admittance stages of that loop() still run
+        f = fs.next() if fs else None
+        r.step(np.zeros(3), None if imu is None else imu[i].astype(np.float64), None if f is None else f[i].astype(np.float64))
     assert not any(r.gait_change_pending for r in refs)
     eng2 = switch(eng, cfg_b, False)  # the state carried into an engine for the new gait
     eng.close()
     su_ref, su = refs[0].startup(), eng2.startup()
     assert (su.period, su.swing_period, su.stance_period) == (su_ref.period, su_ref.swing_period, su_ref.stance_period)
-    assert list(su.phase_offsets)[:6] == list(su_ref.phase_offsets)[:6]
+    assert list(su.phase_offsets)[:L] == list(su_ref.phase_offsets)[:L]
     for f in ("max_linear_speed", "max_angular_speed", "max_linear_acceleration", "max_angular_acceleration", "walkspace"):
         assert np.abs(np.array(list(getattr(su, f))) - np.array(list(getattr(su_ref, f)))).max() < 1e-7, f
-    assert_state_close(eng2.get_state(), ref_states(), 6, 3, 1e-9, skip=JOINT_FIELDS)
+    assert_state_close(eng2.get_state(), ref_states(), L, D, 1e-9, skip=JOINT_FIELDS)
     for c in range(700):
         step(eng2, cs.next())
-    errs.check(max_fraction=2e-3, label="gait change tripod -> wave against the reference's changeGait")
+    errs.check(max_fraction=2e-3, label=f"{model}: gait change against the reference's changeGait")
     st = ref_states()
-    assert_state_close(eng2.get_state(), st, 6, 3, 1e-8, skip=JOINT_FIELDS)
+    assert_state_close(eng2.get_state(), st, L, D, 1e-8, skip=JOINT_FIELDS)
     assert {s.walk_state for s in st} & {0, 1, 2}  # walking again under the new gait
     eng2.close()
     for r in refs:
@@ -218,7 +228,10 @@ def _emu_switch(emu):
 
 
 def test_emu_gait_change_against_the_reference(emu):
-    _gait_change_case(emu, _emu_switch(emu))
+    # (model="octopod" — IMU posing and admittance on — is NOT exact: the reference's switching loop() still advances the
+    # IMU PID and the admittance model by one step, while the engine's switch takes no cycle at all: imu_pose is 4.5e-4
+    # rad apart right after the switch.  Documented at shc_clone_reconfigured.)
+    _gait_change_case(emu, _emu_switch(emu), model="hexapod")
 
 
 PARAMETER_CHANGES = [
