@@ -223,6 +223,10 @@ void* shc_ref_create(const shc_config* cfg) {
   // StateController::linear_velocity_input_ has no initialiser either (state_controller.h:366; angular_velocity_input_ has):
   // "no command received yet" is zero
   sc.linear_velocity_input_ = Eigen::Vector2d::Zero();
+  // PoseController::pose_reset_mode_ has no initialiser and no constructor writes it (pose_controller.h:269): in the node the
+  // remote's pose_reset_mode topic sets it before it matters; here "nothing requested" is NO_RESET.  (Left to the heap, a
+  // rollout depended on what had run in the process before.)
+  sc.poser_->setPoseResetMode(NO_RESET);
   int loops = 0;
   while (sc.robot_state_ != READY && loops < 100000) {
     sc.robotStateCallback(int8(RUNNING));
@@ -273,6 +277,8 @@ int shc_ref_startup_trajectory(const shc_config* cfg, const double* q_init, int 
   }
   sc.init();
   sc.initModel(use_defaults);
+  sc.linear_velocity_input_ = Eigen::Vector2d::Zero();
+  sc.poser_->setPoseResetMode(NO_RESET);
   int rows = 0, loops = 0;
   while (sc.robot_state_ != READY && loops < 100000) {
     sc.robotStateCallback(int8(RUNNING));
