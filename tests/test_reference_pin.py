@@ -483,3 +483,22 @@ def test_reference_build_does_not_depend_on_heap_contents():
                          capture_output=True, text=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=900)
     assert out.returncode == 0, out.stdout[-1500:]
     assert " passed" in out.stdout and "failed" not in out.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(ref_py.REFERENCE_ROOT, "config")), reason="the reference's config/ directory is not on this machine")
+@pytest.mark.parametrize("gait", ["tripod_gait", "ripple_gait", "wave_gait", "amble_gait"])
+@pytest.mark.parametrize("auto_posing", [0, 1])
+def test_the_references_own_yaml_files(ref, oracle, gait, auto_posing):
+    """The reference's shipped config/default.yaml, gait.yaml and auto_pose.yaml, read as they are
+    (load_reference_yaml mirrors initParameters / initGaitParameters / initAutoPoseParameters), give the built-in
+    configuration; the oracle and the reference's own code then agree on every state field under it."""
+    import ctypes
+
+    from syropod_highlevel_controller_b200.config import load_reference_yaml
+
+    d = os.path.join(ref_py.REFERENCE_ROOT, "config")
+    cfg = load_reference_yaml(os.path.join(d, "default.yaml"), os.path.join(d, "gait.yaml"), os.path.join(d, "auto_pose.yaml"), gait=gait)
+    cfg.auto_posing = auto_posing
+    builtin = hexapod_config(gait, cfg.time_delta, auto_posing=auto_posing)
+    assert bytes(ctypes.string_at(ctypes.addressof(cfg), ctypes.sizeof(cfg))) == bytes(ctypes.string_at(ctypes.addressof(builtin), ctypes.sizeof(builtin)))
+    _strict_rollout(ref, oracle, cfg, 500, n=1, label=f"the reference's own YAML files, {gait}, auto_posing={auto_posing}")
