@@ -257,7 +257,7 @@ def test_reference_own_startup_free_running(ref, oracle):
 def test_sequences_equal_the_reference(ref, oracle, which):
     """PoseController::executeSequence (START_UP with sequence generation, SHUT_DOWN, second START_UP), stepToNewStance,
     packLegs / unpackLegs on the reference's own PoseController against the restated oracle, every loop(): progress values
-    equal, joints equal.  Hexapod: free-running over all ~1500 loops, bit for bit.  Octopod: its five-joint legs are
+    equal, joints equal.  Hexapod: free-running over all ~1650 loops, bit for bit.  Octopod: its five-joint legs are
     redundant for a position target, so last-bit differences of the 6 x 6 inverse grow along thousands of closed-loop IK
     iterations (to 0.03 rad with equal tips and progress values); every loop therefore starts from the oracle's joint
     state (the sequence bookkeeping — step counters, transition poses, targets — stays each side's own) and agrees to 1e-12."""
